@@ -1,0 +1,245 @@
+"""Golden-vector generator (test infrastructure).  Runs ONLY in the build container, where /root/reference exists.
+
+    python -m oracle.make_golden            # rewrites tests/golden/*.npz
+
+It executes the reference's OWN code on seeded synthetic inputs and stores inputs + outputs as small fixtures,
+so that the oracle restatement (and through it the CUDA path) is pinned to the reference wherever the
+reference is runnable on a CPU:
+
+* ``golden_lbs.npz``      reference ``utils/body_util.py`` ``get_global_RTs`` + ``apply_lbs`` (imported unchanged).
+* ``golden_steiner.npz``  reference ``models/model.py::get_transformation_from_triangle_steiner`` (module imported
+                          unchanged; third-party imports it cannot satisfy offline are stubbed in sys.modules).
+* ``golden_model.npz``    reference ``Model.forward`` + ``Renderer.forward`` UNMODIFIED, end to end on CPU:
+                          ``.cuda()`` is patched to a no-op, PyTorch3D's ``Meshes``/``so3_exp_map`` and the
+                          ``diff_gaussian_rasterization`` package are stubs (the latter backed by the C oracle and
+                          recording exactly what the reference hands to the rasterizer), normal renderer / shadow
+                          module are replaced by constants (they are "next" rows).
+* ``golden_lpips.npz``    reference ``utils/lpips`` LPIPS(net='vgg', pnet_rand=True) under torch.manual_seed(0)
+                          (ImageNet trunk weights are not downloadable offline) + its in-tree linear heads.
+
+Nothing here is imported by the product or by GPU tests; the GPU box has no /root/reference.
+"""
+from __future__ import annotations
+
+import os
+import sys
+import types
+from typing import NamedTuple
+
+import numpy as np
+import torch
+
+REF = "/root/reference"
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def _stub_module(name, **attrs):
+    m = types.ModuleType(name)
+    m.__dict__.update(attrs)
+    sys.modules[name] = m
+    return m
+
+
+class _Meshes:
+    """Minimal stand-in for pytorch3d.structures.Meshes (semantics: SURVEY.md App. B)."""
+
+    def __init__(self, verts, faces):
+        self.v, self.f = verts[0], faces[0]
+
+    def verts_packed(self):
+        return self.v
+
+    def faces_packed(self):
+        return self.f
+
+    def _edges(self):
+        f = self.f
+        e = torch.cat([f[:, [1, 2]], f[:, [2, 0]], f[:, [0, 1]]], dim=0)
+        e = torch.sort(e, dim=1)[0]
+        V = self.v.shape[0]
+        key = e[:, 0] * V + e[:, 1]
+        uniq, inv = torch.unique(key, sorted=True, return_inverse=True)
+        return torch.stack([uniq // V, uniq % V], dim=1), inv.reshape(3, -1).t()
+
+    def edges_packed(self):
+        return self._edges()[0]
+
+    def faces_packed_to_edges_packed(self):
+        return self._edges()[1]
+
+    def verts_normals_padded(self):
+        v, f = self.v, self.f
+        n = torch.cross(v[f[:, 1]] - v[f[:, 0]], v[f[:, 2]] - v[f[:, 0]], dim=1)
+        vn = torch.zeros_like(v)
+        for k in range(3):
+            vn = vn.index_add(0, f[:, k], n)
+        return torch.nn.functional.normalize(vn, eps=1e-6, dim=1)[None]
+
+
+class GaussianRasterizationSettings(NamedTuple):
+    image_height: int
+    image_width: int
+    tanfovx: float
+    tanfovy: float
+    bg: torch.Tensor
+    scale_modifier: float
+    viewmatrix: torch.Tensor
+    projmatrix: torch.Tensor
+    sh_degree: int
+    campos: torch.Tensor
+    prefiltered: bool
+    debug: bool
+
+
+RECORDED = []
+
+
+class GaussianRasterizer(torch.nn.Module):
+    """Records what the reference passes at gaussian.py:83-91 and answers with the C oracle."""
+
+    def __init__(self, raster_settings):
+        super().__init__()
+        self.raster_settings = raster_settings
+
+    def forward(self, means3D, means2D, opacities, shs=None, colors_precomp=None, scales=None, rotations=None,
+                cov3D_precomp=None):
+        from oracle import raster
+        s = self.raster_settings
+        assert shs is None and scales is None and rotations is None
+        rec = dict(means3D=means3D.detach().numpy().copy(), colors=colors_precomp.detach().numpy().copy(),
+                   opacities=opacities.detach().numpy().copy(), cov6=cov3D_precomp.detach().numpy().copy(),
+                   view=s.viewmatrix.detach().numpy().copy(), proj=s.projmatrix.detach().numpy().copy(),
+                   tanfovx=s.tanfovx, tanfovy=s.tanfovy, bg=s.bg.detach().numpy().copy(),
+                   H=s.image_height, W=s.image_width, campos=s.campos.detach().numpy().copy())
+        RECORDED.append(rec)
+        out = raster.forward(rec["means3D"], rec["cov6"], rec["colors"], rec["opacities"], rec["view"], rec["proj"],
+                             s.tanfovx, s.tanfovy, rec["bg"][:3], s.image_height, s.image_width)
+        return torch.from_numpy(out["color"]), torch.from_numpy(out["radii"])
+
+
+def _install_stubs():
+    from oracle import geometry as G
+    _stub_module("seaborn", color_palette=lambda *a, **k: [(0, 0, 0)])
+    tm = _stub_module("trimesh")
+    tm.remesh = _stub_module("trimesh.remesh", faces_to_edges=None, grouping=None)
+    p3 = _stub_module("pytorch3d")
+    p3.ops = _stub_module("pytorch3d.ops")
+    p3.ops.knn = _stub_module("pytorch3d.ops.knn", knn_points=None)
+    p3.structures = _stub_module("pytorch3d.structures", Meshes=_Meshes)
+    p3.transforms = _stub_module("pytorch3d.transforms")
+    p3.transforms.so3 = _stub_module("pytorch3d.transforms.so3", so3_exp_map=G.so3_exp_map, so3_log_map=None)
+    p3.loss = _stub_module("pytorch3d.loss")
+    p3.loss.chamfer = _stub_module("pytorch3d.loss.chamfer", chamfer_distance=None)
+    _stub_module("diff_gaussian_rasterization", GaussianRasterizationSettings=GaussianRasterizationSettings,
+                 GaussianRasterizer=GaussianRasterizer)
+
+
+def main():
+    assert os.path.isdir(REF), "golden vectors can only be regenerated where /root/reference is mounted"
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, REF)
+    os.makedirs(OUT, exist_ok=True)
+    from gomavatar_b200 import synthetic as S
+    _install_stubs()
+    torch.Tensor.cuda = lambda self, *a, **k: self            # reference Model.__init__ calls .cuda() (model.py:58,60)
+
+    # ---------------------------------------------------------------- LBS (reference code imported unchanged)
+    from utils.body_util import apply_lbs, get_global_RTs      # noqa: E402  (reference)
+    scene = S.make_humanoid(2000, seed=0)
+    frames = S.make_frames(scene, 3, img_size=64, seed=3)
+    params = S.make_params(scene, seed=1)
+    t = torch.from_numpy
+    Rs, Ts = get_global_RTs(t(frames["cnl_gtfms"]), t(frames["dst_Rs"]), t(frames["dst_Ts"]))
+    v_obs = torch.stack([apply_lbs(t(params["vertices"])[None], Rs[b:b + 1], Ts[b:b + 1], t(scene.lbs_weights))[0]
+                         for b in range(3)])
+    np.savez_compressed(os.path.join(OUT, "golden_lbs.npz"),
+                        vertices=params["vertices"], lbs_weights=scene.lbs_weights, cnl_gtfms=frames["cnl_gtfms"],
+                        dst_Rs=frames["dst_Rs"], dst_Ts=frames["dst_Ts"],
+                        global_Rs=Rs.numpy(), global_Ts=Ts.numpy(), vertices_observation=v_obs.numpy())
+
+    # ---------------------------------------------------------------- Steiner frame + full Model.forward
+    cwd = os.getcwd()
+    os.chdir(REF)                                             # make_cfg opens a relative path (configs/__init__.py:14)
+    try:
+        from configs import make_cfg
+        import models.model as ref_model                      # reference module, unchanged
+        cfg = make_cfg("exps/zju-mocap_377.yaml")
+    finally:
+        os.chdir(cwd)
+    tri = t(v_obs.numpy()[0]).permute(1, 0)[t(scene.faces).reshape(-1)].reshape(scene.n_faces, 3, 3)
+    A = ref_model.get_transformation_from_triangle_steiner(tri, 1e-3)
+    np.savez_compressed(os.path.join(OUT, "golden_steiner.npz"), triangles=tri.numpy(), sigma=np.float32(1e-3),
+                        transform=A.numpy())
+
+    H = W = 64
+    cfg.model.img_size = [W, H]
+    cfg.model.normal_renderer.name = "none"                   # mesh normal renderer / shadow MLP: "next" rows
+    cfg.model.shadow_module.name = "none"
+    if "eval_mode" not in cfg.model:
+        cfg.model.eval_mode = False
+    model = ref_model.Model(cfg.model, scene.canonical_info())
+    model.train()
+    with torch.no_grad():
+        model.so3.copy_(t(params["so3"]))
+        model.scale.copy_(t(params["scale"]))
+        model.appearance_module.appearance.copy_(t(params["appearance"]))
+    model.normal_renderer = lambda verts, normals, K, E, faces=None: (torch.zeros(1, H, W, 3), torch.ones(1, H, W, 1))
+    model.shadow_module = lambda n: torch.full((1, H * W, 1), 0.5)
+    gold = {}
+    for b in range(3):
+        RECORDED.clear()
+        sl = lambda k: t(frames[k][b:b + 1])
+        rgbs, masks, outputs = model(sl("K"), sl("E"), sl("cnl_gtfms"), sl("dst_Rs"), sl("dst_Ts"),
+                                     dst_posevec=sl("dst_posevec"), i_iter=0, bgcolor=sl("bgcolor"))
+        gold[f"rgbs_{b}"] = rgbs.detach().numpy()
+        gold[f"masks_{b}"] = masks.detach().numpy()
+        gold[f"albedo_{b}"] = outputs["albedo"].detach().numpy()
+        assert len(RECORDED) == 2                             # two 3-channel passes (gaussian.py:82-92)
+        for p, rec in enumerate(RECORDED):
+            for k in ("means3D", "colors", "opacities", "cov6", "view", "proj", "bg", "campos"):
+                gold[f"pass{p}_{k}_{b}"] = rec[k]
+            gold[f"pass{p}_tanfov_{b}"] = np.array([rec["tanfovx"], rec["tanfovy"]], np.float64)
+    # test-time pose optimisation branch (model.py:218-221)
+    RECORDED.clear()
+    gR, gT = torch.tensor([0.1, -0.2, 0.05]), torch.tensor([0.02, 0.01, -0.03])
+    sl = lambda k: t(frames[k][0:1])
+    rgbs, masks, _ = model(sl("K"), sl("E"), sl("cnl_gtfms"), sl("dst_Rs"), sl("dst_Ts"), dst_posevec=sl("dst_posevec"),
+                           i_iter=0, global_R=gR, global_T=gT)
+    gold["global_R"], gold["global_T"] = gR.numpy(), gT.numpy()
+    gold["rigid_means3D"] = RECORDED[0]["means3D"]
+    gold["rigid_cov6"] = RECORDED[0]["cov6"]
+    gold["rigid_rgbs"] = rgbs.detach().numpy()
+    np.savez_compressed(os.path.join(OUT, "golden_model.npz"), n_faces=np.int64(2000), scene_seed=np.int64(0),
+                        frames_seed=np.int64(3), params_seed=np.int64(1), img_size=np.int64(64),
+                        faces=scene.faces.astype(np.int32), so3=params["so3"], scale=params["scale"],
+                        appearance=params["appearance"],
+                        **{k: frames[k] for k in ("K", "E", "cnl_gtfms", "dst_Rs", "dst_Ts", "dst_posevec", "bgcolor")},
+                        **gold)
+
+    # ---------------------------------------------------------------- LPIPS (reference utils/lpips, random trunk)
+    try:
+        from utils import lpips as ref_lpips
+        torch.manual_seed(0)
+        net = ref_lpips.LPIPS(net="vgg", pnet_rand=True, verbose=False)
+        trunk_sum = float(sum(p.double().abs().sum() for p in net.net.parameters()))
+        g = torch.Generator().manual_seed(5)
+        x0 = torch.rand(2, 3, 64, 64, generator=g)
+        x1 = (x0 + 0.1 * torch.randn(2, 3, 64, 64, generator=g)).clamp(0, 1)
+        x0r = x0.clone().requires_grad_(True)
+        val = net(2 * x0r - 1, 2 * x1 - 1)
+        val.sum().backward()
+        heads = {f"lin{k}": net.lins[k].model[-1].weight.detach().numpy().reshape(-1) for k in range(5)}
+        np.savez_compressed(os.path.join(OUT, "golden_lpips.npz"), x0=x0.numpy(), x1=x1.numpy(),
+                            value=val.detach().numpy(), grad_x0=x0r.grad.numpy(), trunk_abs_sum=np.float64(trunk_sum),
+                            **heads)
+        print("lpips golden:", val.detach().reshape(-1).numpy(), "trunk |w| sum", trunk_sum)
+    except Exception as e:  # pragma: no cover
+        print("LPIPS golden skipped:", repr(e))
+    print("golden vectors written to", OUT)
+    for f in sorted(os.listdir(OUT)):
+        print("  ", f, os.path.getsize(os.path.join(OUT, f)), "bytes")
+
+
+if __name__ == "__main__":
+    main()
