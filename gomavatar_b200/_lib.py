@@ -1,0 +1,102 @@
+"""ctypes binding of libgom_b200.so (C ABI: include/gom_b200.h).
+
+There is deliberately NO fallback: if the library has not been built (``python -m gomavatar_b200.build``) every op
+raises.  The structs below mirror include/gom_b200.h field by field; their sizes are checked against the
+``gom_sizeof_*`` exports at load time.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_int, c_int32, c_int64, c_size_t, c_void_p, c_float, c_char_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libgom_b200.so")
+
+ABI_VERSION = 1
+STATUS_OVERFLOW = 1
+
+
+class GomCameraArgs(ctypes.Structure):
+    _fields_ = [("n_frames", c_int32), ("height", c_int32), ("width", c_int32), ("_pad", c_int32),
+                ("K", c_void_p), ("E", c_void_p), ("viewmatrix", c_void_p), ("projmatrix", c_void_p),
+                ("tanfov", c_void_p), ("campos", c_void_p)]
+
+
+class GomRasterFwdArgs(ctypes.Structure):
+    _fields_ = [("n_frames", c_int32), ("n_gauss", c_int32), ("height", c_int32), ("width", c_int32),
+                ("n_channels", c_int32), ("interleaved", c_int32), ("inst_capacity", c_int64),
+                ("means3D", c_void_p), ("means3D_stride", c_int64),
+                ("cov3D", c_void_p), ("cov3D_stride", c_int64),
+                ("colors", c_void_p), ("colors_stride", c_int64),
+                ("opacities", c_void_p), ("opacities_stride", c_int64),
+                ("viewmatrix", c_void_p), ("projmatrix", c_void_p), ("tanfov", c_void_p), ("bg", c_void_p),
+                ("out_color", c_void_p), ("final_T", c_void_p), ("n_contrib", c_void_p), ("radii", c_void_p),
+                ("depth", c_void_p), ("xy", c_void_p), ("conic_opacity", c_void_p), ("rect", c_void_p),
+                ("tile_count", c_void_p), ("tile_offset", c_void_p), ("tile_cursor", c_void_p),
+                ("inst_keys", c_void_p), ("point_list", c_void_p), ("status", c_void_p)]
+
+
+class GomRasterBwdArgs(ctypes.Structure):
+    _fields_ = [("n_frames", c_int32), ("n_gauss", c_int32), ("height", c_int32), ("width", c_int32),
+                ("n_channels", c_int32), ("interleaved", c_int32), ("inst_capacity", c_int64),
+                ("means3D", c_void_p), ("means3D_stride", c_int64),
+                ("cov3D", c_void_p), ("cov3D_stride", c_int64),
+                ("colors", c_void_p), ("colors_stride", c_int64),
+                ("viewmatrix", c_void_p), ("projmatrix", c_void_p), ("tanfov", c_void_p), ("bg", c_void_p),
+                ("final_T", c_void_p), ("n_contrib", c_void_p), ("radii", c_void_p), ("xy", c_void_p),
+                ("conic_opacity", c_void_p), ("tile_offset", c_void_p), ("point_list", c_void_p),
+                ("dL_dout", c_void_p),
+                ("dL_dmeans3D", c_void_p), ("dL_dcov3D", c_void_p),
+                ("dL_dcolors", c_void_p), ("dL_dcolors_stride", c_int64),
+                ("dL_dopacity", c_void_p), ("dL_dmeans2D", c_void_p), ("dL_dconic", c_void_p)]
+
+
+# every symbol include/gom_b200.h declares (tests check the .so exports all of them)
+EXPORTS = [
+    "gom_abi_version", "gom_last_error", "gom_camera_from_KE", "gom_raster_forward", "gom_raster_backward",
+    "gom_sizeof_camera_args", "gom_sizeof_raster_fwd_args", "gom_sizeof_raster_bwd_args",
+]
+
+_lib = None
+
+
+class GomError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load the library once; raise loudly if it is missing or does not match this binding."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise GomError(f"{LIB_PATH} not found: build it with `python -m gomavatar_b200.build` "
+                       "(there is no CPU / PyTorch fallback for the hot path)")
+    L = ctypes.CDLL(LIB_PATH)
+    L.gom_last_error.restype = c_char_p
+    L.gom_abi_version.restype = c_int
+    for name in ("gom_sizeof_camera_args", "gom_sizeof_raster_fwd_args", "gom_sizeof_raster_bwd_args"):
+        getattr(L, name).restype = c_size_t
+    if L.gom_abi_version() != ABI_VERSION:
+        raise GomError(f"libgom_b200.so ABI {L.gom_abi_version()} != binding {ABI_VERSION}: rebuild")
+    for cls, fn in ((GomCameraArgs, L.gom_sizeof_camera_args), (GomRasterFwdArgs, L.gom_sizeof_raster_fwd_args),
+                    (GomRasterBwdArgs, L.gom_sizeof_raster_bwd_args)):
+        if ctypes.sizeof(cls) != fn():
+            raise GomError(f"struct {cls.__name__}: ctypes mirror is {ctypes.sizeof(cls)} B, library says {fn()} B")
+    for name in ("gom_camera_from_KE", "gom_raster_forward", "gom_raster_backward"):
+        f = getattr(L, name)
+        f.restype = c_int
+        f.argtypes = [c_void_p, c_void_p]
+    _lib = L
+    return L
+
+
+def check(rc, what):
+    if rc != 0:
+        raise GomError(f"{what} failed ({rc}): {lib().gom_last_error().decode()}")
+
+
+def ptr(t):
+    """device pointer of a torch tensor (None -> NULL)"""
+    return None if t is None else c_void_p(t.data_ptr())

@@ -1,0 +1,118 @@
+// gom_common.cuh — shared helpers for the sm_100a kernels of libgom_b200.so
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/gom_b200.h"
+
+// ---------------------------------------------------------------------------------------------------- errors
+void gom_set_error(const char *fmt, ...);
+
+#define GOM_REQUIRE(cond, what)                                                     \
+    do {                                                                            \
+        if (!(cond)) {                                                              \
+            gom_set_error("%s: invalid argument: %s", __func__, what);              \
+            return GOM_ERR_INVALID;                                                 \
+        }                                                                           \
+    } while (0)
+
+#define GOM_CUDA(call)                                                              \
+    do {                                                                            \
+        cudaError_t e_ = (call);                                                    \
+        if (e_ != cudaSuccess) {                                                    \
+            gom_set_error("%s: %s failed: %s", __func__, #call, cudaGetErrorString(e_)); \
+            return GOM_ERR_CUDA;                                                    \
+        }                                                                           \
+    } while (0)
+
+#define GOM_LAUNCH_CHECK()                                                          \
+    do {                                                                            \
+        cudaError_t e_ = cudaGetLastError();                                        \
+        if (e_ != cudaSuccess) {                                                    \
+            gom_set_error("%s: kernel launch failed: %s", __func__, cudaGetErrorString(e_)); \
+            return GOM_ERR_CUDA;                                                    \
+        }                                                                           \
+    } while (0)
+
+static inline int gom_div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// ------------------------------------------------------------------------------- exactly-rounded fp32 arithmetic
+// Every integer decision of the rasterizer (cull, radius, tile rect, depth key) is computed with individually
+// rounded fp32 operations in a fixed association order, so that it is bit-identical to the CPU oracle
+// (oracle/raster_oracle.c, built with -ffp-contract=off).  nvcc would otherwise contract a*b+c into FMA.
+__device__ __forceinline__ float xmul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float xadd(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float xsub(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float xdiv(float a, float b) { return __fdiv_rn(a, b); }
+__device__ __forceinline__ float xsqrt(float a) { return __fsqrt_rn(a); }
+// a*b + c*d + e*f  (left-associated)
+__device__ __forceinline__ float xdot3(float a, float b, float c, float d, float e, float f) {
+    return xadd(xadd(xmul(a, b), xmul(c, d)), xmul(e, f));
+}
+
+// App. A.2: first three / four components of the row-vector product [p,1]·M, M = float[16] row-major.
+__device__ __forceinline__ void xform4x3(const float *m, const float p[3], float o[3]) {
+    o[0] = xadd(xdot3(m[0], p[0], m[4], p[1], m[8], p[2]), m[12]);
+    o[1] = xadd(xdot3(m[1], p[0], m[5], p[1], m[9], p[2]), m[13]);
+    o[2] = xadd(xdot3(m[2], p[0], m[6], p[1], m[10], p[2]), m[14]);
+}
+__device__ __forceinline__ float xform_w(const float *m, const float p[3]) {
+    return xadd(xdot3(m[3], p[0], m[7], p[1], m[11], p[2]), m[15]);
+}
+
+// App. A.3 step 6: upstream's literals are double -> evaluated in fp64, rounded to fp32 on return.
+__device__ __forceinline__ float ndc2pix(float v, int S) {
+    double d = __dadd_rn((double)v, 1.0);
+    d = __dmul_rn(d, (double)S);
+    d = __dadd_rn(d, -1.0);
+    d = __dmul_rn(d, 0.5);
+    return __double2float_rn(d);
+}
+
+// Clamped view-space point, rows of J·R and the 2-D covariance (App. A.3 step 3); shared by forward and backward.
+struct Cov2D {
+    float t[3];
+    float xm, ym;          // 0 when the tangent was clamped
+    float M0[3], M1[3];    // rows of J·R
+    float a, b, c;         // cov2D incl. +0.3 low-pass
+    float v0[3], v1[3];    // Sigma·M0^T, Sigma·M1^T
+};
+
+__device__ __forceinline__ void cov2d_exact(const float mean[3], const float s[6], const float *view, float fx,
+                                            float fy, float tanfovx, float tanfovy, Cov2D &o) {
+    float t[3];
+    xform4x3(view, mean, t);
+    const float limx = xmul(1.3f, tanfovx), limy = xmul(1.3f, tanfovy);
+    const float txtz = xdiv(t[0], t[2]), tytz = xdiv(t[1], t[2]);
+    o.xm = (txtz < -limx || txtz > limx) ? 0.f : 1.f;
+    o.ym = (tytz < -limy || tytz > limy) ? 0.f : 1.f;
+    t[0] = xmul(fminf(limx, fmaxf(-limx, txtz)), t[2]);
+    t[1] = xmul(fminf(limy, fmaxf(-limy, tytz)), t[2]);
+    o.t[0] = t[0]; o.t[1] = t[1]; o.t[2] = t[2];
+    const float tz2 = xmul(t[2], t[2]);
+    const float J00 = xdiv(fx, t[2]);
+    const float J02 = -xdiv(xmul(fx, t[0]), tz2);
+    const float J11 = xdiv(fy, t[2]);
+    const float J12 = -xdiv(xmul(fy, t[1]), tz2);
+#pragma unroll
+    for (int k = 0; k < 3; k++) {   // R[r][k] = view[4k + r]
+        o.M0[k] = xadd(xmul(J00, view[4 * k + 0]), xmul(J02, view[4 * k + 2]));
+        o.M1[k] = xadd(xmul(J11, view[4 * k + 1]), xmul(J12, view[4 * k + 2]));
+    }
+    const float S[3][3] = {{s[0], s[1], s[2]}, {s[1], s[3], s[4]}, {s[2], s[4], s[5]}};
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        o.v0[k] = xdot3(S[k][0], o.M0[0], S[k][1], o.M0[1], S[k][2], o.M0[2]);
+        o.v1[k] = xdot3(S[k][0], o.M1[0], S[k][1], o.M1[1], S[k][2], o.M1[2]);
+    }
+    o.a = xadd(xdot3(o.M0[0], o.v0[0], o.M0[1], o.v0[1], o.M0[2], o.v0[2]), 0.3f);
+    o.b = xdot3(o.M0[0], o.v1[0], o.M0[1], o.v1[1], o.M0[2], o.v1[2]);
+    o.c = xadd(xdot3(o.M1[0], o.v1[0], o.M1[1], o.v1[1], o.M1[2], o.v1[2]), 0.3f);
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    return v;
+}

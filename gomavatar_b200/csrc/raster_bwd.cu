@@ -1,0 +1,291 @@
+// raster_bwd.cu — tile-based 3D-Gaussian splat rasterizer, backward (sm_100a).
+//
+// Replaces `_C.rasterize_gaussians_backward` of the third-party diff_gaussian_rasterization (renderCUDA backward,
+// computeCov2DCUDA, preprocessCUDA backward).  Upstream issues ~10 global fp32 atomicAdds per
+// (pixel, Gaussian) hit; here each warp first reduces its 32 pixels with shuffles (skipped entirely when no lane of
+// the warp is hit), warps combine in shared memory, and one global atomic per (tile, Gaussian, component) remains.
+#include "gom_common.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+
+struct BwdDev {
+    int B, P, H, W, C, interleaved, gx, gy, T;
+    long long cap;
+    const float *means3D; long long means3D_stride;
+    const float *cov3D; long long cov3D_stride;
+    const float *colors; long long colors_stride;
+    const float *view, *proj, *tanfov, *bg;
+    const float *final_T; const uint32_t *n_contrib; const int32_t *radii;
+    const float2 *xy; const float4 *conic_opacity; const uint32_t *tile_offset, *point_list;
+    const float *dL_dout;
+    float *dL_dmeans3D, *dL_dcov3D, *dL_dcolors; long long dL_dcolors_stride;
+    float *dL_dopacity; float *dL_dmean2D; float *dL_dconic;
+};
+
+// ------------------------------------------------------------------------------------------ App. A.6 blend backward
+template <int C>
+__global__ void __launch_bounds__(kThreads) k_blend_bwd(BwdDev a) {
+    constexpr int NG = 6 + C;            // mean2D.xy, conic A B C, opacity, colour[C]
+    __shared__ uint32_t s_id[kThreads];
+    __shared__ float2 s_xy[kThreads];
+    __shared__ float4 s_co[kThreads];
+    __shared__ float s_col[kThreads * C];
+    __shared__ float s_grad[kThreads * NG];
+    __shared__ uint32_t s_max;
+
+    const int b = blockIdx.z;
+    const int tile = blockIdx.y * a.gx + blockIdx.x;
+    const int tid = threadIdx.y * 16 + threadIdx.x;
+    const int lane = tid & 31;
+    const uint32_t *off = a.tile_offset + (long long)b * (a.T + 1);
+    long long start = off[tile], end = off[tile + 1];
+    if (start > a.cap) start = a.cap;
+    if (end > a.cap) end = a.cap;
+    const int n = (int)(end - start);
+    if (n == 0) return;
+
+    const int x = blockIdx.x * 16 + threadIdx.x, y = blockIdx.y * 16 + threadIdx.y;
+    const bool inside = x < a.W && y < a.H;
+    const long long pix = ((long long)b * a.H + y) * a.W + x;
+    const float T_final = inside ? a.final_T[pix] : 0.f;
+    const uint32_t last_contributor = inside ? a.n_contrib[pix] : 0u;
+
+    if (tid == 0) s_max = 0u;
+    for (int i = tid; i < kThreads * NG; i += kThreads) s_grad[i] = 0.f;
+    __syncthreads();
+    if (last_contributor > 0) atomicMax(&s_max, last_contributor);
+    __syncthreads();
+    const int n_eff = min(n, (int)s_max);      // entries behind every pixel's last contributor are never visited
+    if (n_eff == 0) return;
+
+    float dpix[C], accum_rec[C], last_color[C];
+    float bg_dot = 0.f;
+    const float *bg = a.bg + b * C;
+#pragma unroll
+    for (int ch = 0; ch < C; ch++) {
+        float v = 0.f;
+        if (inside) {
+            v = a.interleaved ? a.dL_dout[pix * C + ch]
+                              : a.dL_dout[((long long)b * C + ch) * a.H * a.W + (long long)y * a.W + x];
+        }
+        dpix[ch] = v;
+        accum_rec[ch] = 0.f;
+        last_color[ch] = 0.f;
+        bg_dot += bg[ch] * v;
+    }
+    float T = T_final, last_alpha = 0.f;
+    const float pxf = (float)x, pyf = (float)y;
+    const float ddelx_dx = 0.5f * a.W, ddely_dy = 0.5f * a.H;
+
+    const uint32_t *plist = a.point_list + (long long)b * a.cap + start;
+    const float2 *gxy = a.xy + (long long)b * a.P;
+    const float4 *gco = a.conic_opacity + (long long)b * a.P;
+    const float *gcol = a.colors + b * a.colors_stride;
+    float *o_mean2D = a.dL_dmean2D + (long long)b * a.P * 2;
+    float *o_conic = a.dL_dconic + (long long)b * a.P * 3;
+    float *o_opac = a.dL_dopacity ? a.dL_dopacity + (long long)b * a.P : nullptr;
+    float *o_col = a.dL_dcolors + b * a.dL_dcolors_stride;
+
+    for (int hi = n_eff; hi > 0; hi -= kThreads) {
+        const int m = min(kThreads, hi);
+        __syncthreads();                                  // previous round's flush is complete
+        if (tid < m) {                                    // s_*[j] holds list entry hi-1-j (back to front)
+            const uint32_t id = plist[hi - 1 - tid];
+            s_id[tid] = id;
+            s_xy[tid] = gxy[id];
+            s_co[tid] = gco[id];
+#pragma unroll
+            for (int ch = 0; ch < C; ch++) s_col[tid * C + ch] = gcol[(long long)id * C + ch];
+        }
+        __syncthreads();
+        for (int j = 0; j < m; j++) {
+            const uint32_t k = (uint32_t)(hi - 1 - j);
+            bool valid = k < last_contributor;
+            float g[NG];
+            if (valid) {
+                const float2 c = s_xy[j];
+                const float4 co = s_co[j];
+                const float dx = c.x - pxf, dy = c.y - pyf;
+                const float power = -0.5f * (co.x * dx * dx + co.z * dy * dy) - co.y * dx * dy;
+                const float G = __expf(power);
+                const float alpha = fminf(0.99f, co.w * G);
+                valid = (power <= 0.0f) && (alpha >= 1.0f / 255.0f);
+                if (valid) {
+                    const float inv1ma = __fdividef(1.f, 1.f - alpha);
+                    T = T * inv1ma;
+                    const float dchannel_dcolor = alpha * T;
+                    float dL_dalpha = 0.f;
+#pragma unroll
+                    for (int ch = 0; ch < C; ch++) {
+                        const float col = s_col[j * C + ch];
+                        accum_rec[ch] = last_alpha * last_color[ch] + (1.f - last_alpha) * accum_rec[ch];
+                        last_color[ch] = col;
+                        dL_dalpha += (col - accum_rec[ch]) * dpix[ch];
+                        g[6 + ch] = dchannel_dcolor * dpix[ch];
+                    }
+                    dL_dalpha *= T;
+                    last_alpha = alpha;
+                    dL_dalpha += (-T_final * inv1ma) * bg_dot;
+                    const float dL_dG = co.w * dL_dalpha;          // the 0.99 clamp is ignored, as upstream
+                    const float gdx = G * dx, gdy = G * dy;
+                    const float dG_ddelx = -gdx * co.x - gdy * co.y;
+                    const float dG_ddely = -gdy * co.z - gdx * co.y;
+                    g[0] = dL_dG * dG_ddelx * ddelx_dx;
+                    g[1] = dL_dG * dG_ddely * ddely_dy;
+                    g[2] = -0.5f * gdx * dx * dL_dG;
+                    g[3] = -0.5f * gdx * dy * dL_dG;
+                    g[4] = -0.5f * gdy * dy * dL_dG;
+                    g[5] = G * dL_dalpha;
+                }
+            }
+            if (__ballot_sync(0xffffffffu, valid)) {
+#pragma unroll
+                for (int c = 0; c < NG; c++) {
+                    const float v = warp_sum(valid ? g[c] : 0.f);
+                    if (lane == 0) atomicAdd(&s_grad[j * NG + c], v);
+                }
+            }
+        }
+        __syncthreads();
+        if (tid < m) {                                    // one global atomic per (tile, Gaussian, component)
+            const uint32_t id = s_id[tid];
+            float *sg = &s_grad[tid * NG];
+            if (sg[0] != 0.f) atomicAdd(o_mean2D + 2LL * id, sg[0]);
+            if (sg[1] != 0.f) atomicAdd(o_mean2D + 2LL * id + 1, sg[1]);
+            if (sg[2] != 0.f) atomicAdd(o_conic + 3LL * id, sg[2]);
+            if (sg[3] != 0.f) atomicAdd(o_conic + 3LL * id + 1, sg[3]);
+            if (sg[4] != 0.f) atomicAdd(o_conic + 3LL * id + 2, sg[4]);
+            if (o_opac && sg[5] != 0.f) atomicAdd(o_opac + id, sg[5]);
+#pragma unroll
+            for (int ch = 0; ch < C; ch++)
+                if (sg[6 + ch] != 0.f) atomicAdd(o_col + (long long)id * C + ch, sg[6 + ch]);
+#pragma unroll
+            for (int c = 0; c < NG; c++) sg[c] = 0.f;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------- App. A.7 preprocess backward
+__global__ void __launch_bounds__(kThreads) k_preprocess_bwd(BwdDev a) {
+    __shared__ float cam[34];
+    const int b = blockIdx.y;
+    if (threadIdx.x < 16) cam[threadIdx.x] = a.view[b * 16 + threadIdx.x];
+    else if (threadIdx.x < 32) cam[threadIdx.x] = a.proj[b * 16 + threadIdx.x - 16];
+    else if (threadIdx.x < 34) cam[threadIdx.x] = a.tanfov[b * 2 + threadIdx.x - 32];
+    __syncthreads();
+    const int g = blockIdx.x * kThreads + threadIdx.x;
+    if (g >= a.P) return;
+    const float *view = cam, *proj = cam + 16;
+    const float tanfovx = cam[32], tanfovy = cam[33];
+    const long long o = (long long)b * a.P + g;
+    float dmean[3] = {0.f, 0.f, 0.f};
+    float dcov[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (a.radii[o] > 0) {
+        const float *mp = a.means3D + b * a.means3D_stride + 3LL * g;
+        const float p[3] = {mp[0], mp[1], mp[2]};
+        const float2 *cp = reinterpret_cast<const float2 *>(a.cov3D + b * a.cov3D_stride + 6LL * g);
+        const float2 c01 = cp[0], c23 = cp[1], c45 = cp[2];
+        const float s[6] = {c01.x, c01.y, c23.x, c23.y, c45.x, c45.y};
+        const float fx = xdiv((float)a.W, xmul(2.0f, tanfovx)), fy = xdiv((float)a.H, xmul(2.0f, tanfovy));
+        Cov2D q;
+        cov2d_exact(p, s, view, fx, fy, tanfovx, tanfovy, q);
+        const float ca = q.a, cb = q.b, cc = q.c;
+        const float gA = a.dL_dconic[3 * o], gB = a.dL_dconic[3 * o + 1], gC = a.dL_dconic[3 * o + 2];
+        const float den = ca * cc - cb * cb;
+        const float k2 = 1.0f / ((den * den) + 0.0000001f);
+        float dL_da = 0.f, dL_db = 0.f, dL_dc = 0.f;
+        if (k2 != 0.f) {
+            dL_da = k2 * (-cc * cc * gA + 2 * cb * cc * gB + (den - ca * cc) * gC);
+            dL_dc = k2 * (-ca * ca * gC + 2 * ca * cb * gB + (den - ca * cc) * gA);
+            dL_db = k2 * 2 * (cb * cc * gA - (den + 2 * cb * cb) * gB + ca * cb * gC);
+            const float *M0 = q.M0, *M1 = q.M1;
+            dcov[0] = M0[0] * M0[0] * dL_da + M0[0] * M1[0] * dL_db + M1[0] * M1[0] * dL_dc;
+            dcov[3] = M0[1] * M0[1] * dL_da + M0[1] * M1[1] * dL_db + M1[1] * M1[1] * dL_dc;
+            dcov[5] = M0[2] * M0[2] * dL_da + M0[2] * M1[2] * dL_db + M1[2] * M1[2] * dL_dc;
+            dcov[1] = 2 * M0[0] * M0[1] * dL_da + (M0[0] * M1[1] + M0[1] * M1[0]) * dL_db + 2 * M1[0] * M1[1] * dL_dc;
+            dcov[2] = 2 * M0[0] * M0[2] * dL_da + (M0[0] * M1[2] + M0[2] * M1[0]) * dL_db + 2 * M1[0] * M1[2] * dL_dc;
+            dcov[4] = 2 * M0[2] * M0[1] * dL_da + (M0[1] * M1[2] + M0[2] * M1[1]) * dL_db + 2 * M1[1] * M1[2] * dL_dc;
+        }
+        // (iii) cov2D -> mean through M = J(t)·R
+        float dJ00 = 0.f, dJ02 = 0.f, dJ11 = 0.f, dJ12 = 0.f;
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            const float dM0 = 2 * q.v0[k] * dL_da + q.v1[k] * dL_db;
+            const float dM1 = 2 * q.v1[k] * dL_dc + q.v0[k] * dL_db;
+            dJ00 += view[4 * k + 0] * dM0;
+            dJ02 += view[4 * k + 2] * dM0;
+            dJ11 += view[4 * k + 1] * dM1;
+            dJ12 += view[4 * k + 2] * dM1;
+        }
+        const float tz = 1.f / q.t[2], tz2 = tz * tz, tz3 = tz2 * tz;
+        const float dtx = q.xm * -fx * tz2 * dJ02;
+        const float dty = q.ym * -fy * tz2 * dJ12;
+        const float dtz = -fx * tz2 * dJ00 - fy * tz2 * dJ11 + (2 * fx * q.t[0]) * tz3 * dJ02 + (2 * fy * q.t[1]) * tz3 * dJ12;
+#pragma unroll
+        for (int k = 0; k < 3; k++) dmean[k] = view[4 * k + 0] * dtx + view[4 * k + 1] * dty + view[4 * k + 2] * dtz;
+        // (iv) mean2D -> mean through the projection
+        const float mhx = proj[0] * p[0] + proj[4] * p[1] + proj[8] * p[2] + proj[12];
+        const float mhy = proj[1] * p[0] + proj[5] * p[1] + proj[9] * p[2] + proj[13];
+        const float mhw = proj[3] * p[0] + proj[7] * p[1] + proj[11] * p[2] + proj[15];
+        const float mw = 1.0f / (mhw + 0.0000001f);
+        const float mul1 = mhx * mw * mw, mul2 = mhy * mw * mw;
+        const float g2x = a.dL_dmean2D[2 * o], g2y = a.dL_dmean2D[2 * o + 1];
+#pragma unroll
+        for (int k = 0; k < 3; k++)
+            dmean[k] += (proj[4 * k + 0] * mw - proj[4 * k + 3] * mul1) * g2x + (proj[4 * k + 1] * mw - proj[4 * k + 3] * mul2) * g2y;
+    }
+#pragma unroll
+    for (int k = 0; k < 3; k++) a.dL_dmeans3D[3 * o + k] = dmean[k];
+#pragma unroll
+    for (int k = 0; k < 6; k++) a.dL_dcov3D[6 * o + k] = dcov[k];
+}
+
+}  // namespace
+
+extern "C" int gom_raster_backward(const GomRasterBwdArgs *p, gom_stream_t stream_) {
+    GOM_REQUIRE(p != nullptr, "args");
+    GOM_REQUIRE(p->n_frames > 0 && p->n_gauss >= 0 && p->height > 0 && p->width > 0, "sizes");
+    GOM_REQUIRE(p->n_channels == 3 || p->n_channels == 4, "n_channels must be 3 or 4");
+    GOM_REQUIRE(p->n_frames <= 65535 && p->inst_capacity > 0, "n_frames / inst_capacity");
+    GOM_REQUIRE(p->means3D && p->cov3D && p->colors && p->viewmatrix && p->projmatrix && p->tanfov && p->bg, "null input");
+    GOM_REQUIRE(p->final_T && p->n_contrib && p->radii && p->xy && p->conic_opacity && p->tile_offset && p->point_list &&
+                    p->dL_dout, "null saved state");
+    GOM_REQUIRE(p->dL_dmeans3D && p->dL_dcov3D && p->dL_dcolors && p->dL_dmeans2D && p->dL_dconic, "null output");
+    GOM_REQUIRE(((uintptr_t)p->cov3D % 8) == 0 && (p->cov3D_stride % 2) == 0, "cov3D must be 8-byte aligned");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    BwdDev a;
+    a.B = p->n_frames; a.P = p->n_gauss; a.H = p->height; a.W = p->width; a.C = p->n_channels;
+    a.interleaved = p->interleaved;
+    a.gx = (a.W + GOM_TILE - 1) / GOM_TILE; a.gy = (a.H + GOM_TILE - 1) / GOM_TILE; a.T = a.gx * a.gy;
+    a.cap = p->inst_capacity;
+    a.means3D = p->means3D; a.means3D_stride = p->means3D_stride;
+    a.cov3D = p->cov3D; a.cov3D_stride = p->cov3D_stride;
+    a.colors = p->colors; a.colors_stride = p->colors_stride;
+    a.view = p->viewmatrix; a.proj = p->projmatrix; a.tanfov = p->tanfov; a.bg = p->bg;
+    a.final_T = p->final_T; a.n_contrib = p->n_contrib; a.radii = p->radii;
+    a.xy = reinterpret_cast<const float2 *>(p->xy);
+    a.conic_opacity = reinterpret_cast<const float4 *>(p->conic_opacity);
+    a.tile_offset = p->tile_offset; a.point_list = p->point_list; a.dL_dout = p->dL_dout;
+    a.dL_dmeans3D = p->dL_dmeans3D; a.dL_dcov3D = p->dL_dcov3D;
+    a.dL_dcolors = p->dL_dcolors; a.dL_dcolors_stride = p->dL_dcolors_stride;
+    a.dL_dopacity = p->dL_dopacity; a.dL_dmean2D = p->dL_dmeans2D; a.dL_dconic = p->dL_dconic;
+
+    const size_t BP = (size_t)a.B * a.P;
+    const size_t ncol = (p->dL_dcolors_stride == 0 ? (size_t)a.P : BP) * a.C;
+    if (a.P > 0) {
+        GOM_CUDA(cudaMemsetAsync(a.dL_dmean2D, 0, sizeof(float) * 2 * BP, stream));
+        GOM_CUDA(cudaMemsetAsync(a.dL_dconic, 0, sizeof(float) * 3 * BP, stream));
+        GOM_CUDA(cudaMemsetAsync(a.dL_dcolors, 0, sizeof(float) * ncol, stream));
+        if (a.dL_dopacity) GOM_CUDA(cudaMemsetAsync(a.dL_dopacity, 0, sizeof(float) * BP, stream));
+        dim3 bgrid(a.gx, a.gy, a.B), bblock(16, 16);
+        if (a.C == 3) k_blend_bwd<3><<<bgrid, bblock, 0, stream>>>(a);
+        else k_blend_bwd<4><<<bgrid, bblock, 0, stream>>>(a);
+        GOM_LAUNCH_CHECK();
+        dim3 grid(gom_div_up(a.P, kThreads), a.B);
+        k_preprocess_bwd<<<grid, kThreads, 0, stream>>>(a);
+        GOM_LAUNCH_CHECK();
+    }
+    return GOM_OK;
+}

@@ -1,0 +1,342 @@
+// raster_fwd.cu — tile-based 3D-Gaussian splat rasterizer, forward (sm_100a).
+//
+// Replaces the forward half of the third-party `diff_gaussian_rasterization._C` that the reference calls at
+// models/modules/renderer/gaussian.py:83-91 (algorithm: SURVEY.md App. A.3-A.5).  B200-first design:
+//   * a batch of B frames per launch (grid.z / grid.y = frame) so that the ~150 non-empty tiles of one 512^2 frame
+//     do not leave most of the 148 SMs idle;
+//   * no host synchronisation: upstream's D2H read of num_rendered is replaced by fixed-capacity instance buffers
+//     and a device status flag, which also makes the whole forward CUDA-graph capturable;
+//   * binning is count -> scan -> scatter into per-tile segments, and the depth sort is a per-tile bitonic sort in
+//     shared memory fused into the blend kernel, instead of a global 64-bit radix sort (6+ passes over HBM);
+//   * one fused pass renders 3 (reference layout) or 4 (RGB + alpha) channels.
+#include "gom_common.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kSortCap = 4096;   // tile lists up to this length are sorted in shared memory (32 KB)
+
+struct FwdDev {
+    int B, P, H, W, C, interleaved, gx, gy, T;
+    long long cap;
+    const float *means3D; long long means3D_stride;
+    const float *cov3D; long long cov3D_stride;
+    const float *colors; long long colors_stride;
+    const float *opac; long long opac_stride;
+    const float *view, *proj, *tanfov, *bg;
+    float *out_color, *final_T; uint32_t *n_contrib; int32_t *radii;
+    float *depth; float2 *xy; float4 *conic_opacity; int4 *rect;
+    uint32_t *tile_count, *tile_offset, *tile_cursor; unsigned long long *inst_keys; uint32_t *point_list;
+    uint32_t *status;
+};
+
+// ------------------------------------------------------------------------------------------- App. A.3 preprocess
+__global__ void __launch_bounds__(kThreads) k_preprocess(FwdDev a) {
+    __shared__ float cam[34];
+    const int b = blockIdx.y;
+    if (threadIdx.x < 16) cam[threadIdx.x] = a.view[b * 16 + threadIdx.x];
+    else if (threadIdx.x < 32) cam[threadIdx.x] = a.proj[b * 16 + threadIdx.x - 16];
+    else if (threadIdx.x < 34) cam[threadIdx.x] = a.tanfov[b * 2 + threadIdx.x - 32];
+    __syncthreads();
+    const int g = blockIdx.x * kThreads + threadIdx.x;
+    if (g >= a.P) return;
+    const float *view = cam, *proj = cam + 16;
+    const float tanfovx = cam[32], tanfovy = cam[33];
+    const long long o = (long long)b * a.P + g;
+
+    int radius = 0;
+    float depth = 0.f;
+    float2 pxy = make_float2(0.f, 0.f);
+    float4 co = make_float4(0.f, 0.f, 0.f, 0.f);
+    int4 rc = make_int4(0, 0, 0, 0);
+
+    const float *mp = a.means3D + b * a.means3D_stride + 3LL * g;
+    const float p[3] = {mp[0], mp[1], mp[2]};
+    float pv[3];
+    xform4x3(view, p, pv);
+    if (pv[2] > 0.2f) {                                      // near cull: z_view <= 0.2 is dropped
+        const float2 *cp = reinterpret_cast<const float2 *>(a.cov3D + b * a.cov3D_stride + 6LL * g);
+        const float2 c01 = cp[0], c23 = cp[1], c45 = cp[2];
+        const float s[6] = {c01.x, c01.y, c23.x, c23.y, c45.x, c45.y};
+        float ph[3];
+        xform4x3(proj, p, ph);
+        const float pw = xdiv(1.0f, xadd(xform_w(proj, p), 0.0000001f));
+        const float ppx = xmul(ph[0], pw), ppy = xmul(ph[1], pw);
+        const float fx = xdiv((float)a.W, xmul(2.0f, tanfovx)), fy = xdiv((float)a.H, xmul(2.0f, tanfovy));
+        Cov2D q;
+        cov2d_exact(p, s, view, fx, fy, tanfovx, tanfovy, q);
+        const float det = xsub(xmul(q.a, q.c), xmul(q.b, q.b));
+        if (det != 0.0f) {
+            const float det_inv = xdiv(1.f, det);
+            const float mid = xmul(0.5f, xadd(q.a, q.c));
+            const float disc = xsqrt(fmaxf(0.1f, xsub(xmul(mid, mid), det)));
+            const float lam1 = xadd(mid, disc), lam2 = xsub(mid, disc);
+            const int r = (int)ceilf(xmul(3.f, xsqrt(fmaxf(lam1, lam2))));
+            const float px = ndc2pix(ppx, a.W), py = ndc2pix(ppy, a.H);
+            const float rf = (float)r;
+            const int minx = min(a.gx, max(0, (int)xdiv(xsub(px, rf), 16.f)));
+            const int miny = min(a.gy, max(0, (int)xdiv(xsub(py, rf), 16.f)));
+            const int maxx = min(a.gx, max(0, (int)xdiv(xsub(xadd(xadd(px, rf), 16.f), 1.0f), 16.f)));
+            const int maxy = min(a.gy, max(0, (int)xdiv(xsub(xadd(xadd(py, rf), 16.f), 1.0f), 16.f)));
+            if ((maxx - minx) * (maxy - miny) > 0) {
+                radius = r;
+                depth = pv[2];
+                pxy = make_float2(px, py);
+                co = make_float4(xmul(q.c, det_inv), xmul(-q.b, det_inv), xmul(q.a, det_inv),
+                                 a.opac[b * a.opac_stride + g]);
+                rc = make_int4(minx, miny, maxx, maxy);
+                uint32_t *cnt = a.tile_count + (long long)b * a.T;
+                for (int y = miny; y < maxy; y++)
+                    for (int x = minx; x < maxx; x++) atomicAdd(cnt + y * a.gx + x, 1u);
+            }
+        }
+    }
+    a.radii[o] = radius;
+    a.depth[o] = depth;
+    a.xy[o] = pxy;
+    a.conic_opacity[o] = co;
+    a.rect[o] = rc;
+}
+
+// ------------------------------------------------------------------------- per-frame exclusive scan of tile counts
+__global__ void __launch_bounds__(1024) k_scan_tiles(FwdDev a) {
+    __shared__ uint32_t wsum[32];
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const uint32_t *cnt = a.tile_count + (long long)b * a.T;
+    uint32_t *off = a.tile_offset + (long long)b * (a.T + 1);
+    uint32_t *cur = a.tile_cursor + (long long)b * a.T;
+    unsigned long long carry = 0;
+    for (int base = 0; base < a.T; base += 1024) {
+        const int i = base + tid;
+        const uint32_t v = i < a.T ? cnt[i] : 0u;
+        uint32_t x = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, x, d);
+            if (lane >= d) x += y;
+        }
+        if (lane == 31) wsum[wid] = x;
+        __syncthreads();
+        if (wid == 0) {
+            uint32_t w = wsum[lane];
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xffffffffu, w, d);
+                if (lane >= d) w += y;
+            }
+            wsum[lane] = w;
+        }
+        __syncthreads();
+        const unsigned long long excl = carry + (x - v) + (wid > 0 ? wsum[wid - 1] : 0u);
+        if (i < a.T) {
+            const uint32_t e = (uint32_t)(excl > 0xffffffffULL ? 0xffffffffULL : excl);
+            off[i] = e;
+            cur[i] = e;
+        }
+        carry += wsum[31];
+        __syncthreads();
+    }
+    if (tid == 0) {
+        off[a.T] = (uint32_t)(carry > 0xffffffffULL ? 0xffffffffULL : carry);
+        a.status[b] = carry > (unsigned long long)a.cap ? GOM_STATUS_OVERFLOW : 0u;
+    }
+}
+
+// ----------------------------------------------------- App. A.4: one (depth,id) key per touched tile, into its segment
+__global__ void __launch_bounds__(kThreads) k_emit(FwdDev a) {
+    const int b = blockIdx.y;
+    const int g = blockIdx.x * kThreads + threadIdx.x;
+    if (g >= a.P) return;
+    const long long o = (long long)b * a.P + g;
+    const int4 rc = a.rect[o];
+    if (rc.z <= rc.x || rc.w <= rc.y) return;
+    const unsigned long long key = ((unsigned long long)__float_as_uint(a.depth[o]) << 32) | (uint32_t)g;
+    uint32_t *cur = a.tile_cursor + (long long)b * a.T;
+    unsigned long long *keys = a.inst_keys + (long long)b * a.cap;
+    for (int y = rc.y; y < rc.w; y++)
+        for (int x = rc.x; x < rc.z; x++) {
+            const uint32_t pos = atomicAdd(cur + y * a.gx + x, 1u);
+            if ((long long)pos < a.cap) keys[pos] = key;
+        }
+}
+
+// --------------------------------------------------------------------- bitonic network for arbitrary n (in place)
+// All compare-exchanges are ascending (min to the lower index), so virtual +inf padding above n never moves and
+// pairs that reach beyond n are simply skipped.  Works on shared or global memory (block-wide, kThreads threads).
+__device__ __forceinline__ void cmpxchg(unsigned long long *k, int i, int j) {
+    const unsigned long long x = k[i], y = k[j];
+    if (x > y) { k[i] = y; k[j] = x; }
+}
+
+__device__ void block_sort(unsigned long long *k, int n) {
+    if (n < 2) return;
+    int npad = 2;
+    while (npad < n) npad <<= 1;
+    const int half = npad >> 1;
+    for (int size = 2; size <= npad; size <<= 1) {
+        const int hs = size >> 1;
+        for (int t = threadIdx.x; t < half; t += kThreads) {          // flip
+            const int blk = t / hs, w = t - blk * hs;
+            const int i = blk * size + w, j = blk * size + (size - 1 - w);
+            if (j < n) cmpxchg(k, i, j);
+        }
+        __syncthreads();
+        for (int step = hs >> 1; step >= 1; step >>= 1) {              // disperse
+            for (int t = threadIdx.x; t < half; t += kThreads) {
+                const int i = 2 * step * (t / step) + (t % step), j = i + step;
+                if (j < n) cmpxchg(k, i, j);
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// ------------------------------------------------------------------------ App. A.5: per-tile depth sort + blend
+template <int C>
+__global__ void __launch_bounds__(kThreads) k_sort_blend(FwdDev a) {
+    __shared__ unsigned long long skeys[kSortCap];
+    __shared__ float2 s_xy[kThreads];
+    __shared__ float4 s_co[kThreads];
+    __shared__ float s_col[kThreads * C];
+
+    const int b = blockIdx.z;
+    const int tile = blockIdx.y * a.gx + blockIdx.x;
+    const int tid = threadIdx.y * 16 + threadIdx.x;
+    const uint32_t *off = a.tile_offset + (long long)b * (a.T + 1);
+    long long start = off[tile], end = off[tile + 1];
+    if (start > a.cap) start = a.cap;                      // overflowed frame: stay in bounds, result is flagged
+    if (end > a.cap) end = a.cap;
+    const int n = (int)(end - start);
+
+    unsigned long long *gkeys = a.inst_keys + (long long)b * a.cap + start;
+    unsigned long long *sk = gkeys;
+    if (n <= kSortCap) {
+        for (int i = tid; i < n; i += kThreads) skeys[i] = gkeys[i];
+        sk = skeys;
+        __syncthreads();
+    }
+    block_sort(sk, n);
+    uint32_t *plist = a.point_list + (long long)b * a.cap + start;
+    for (int i = tid; i < n; i += kThreads) plist[i] = (uint32_t)sk[i];
+
+    const int x = blockIdx.x * 16 + threadIdx.x, y = blockIdx.y * 16 + threadIdx.y;
+    const bool inside = x < a.W && y < a.H;
+    const float pxf = (float)x, pyf = (float)y;
+    const float2 *gxy = a.xy + (long long)b * a.P;
+    const float4 *gco = a.conic_opacity + (long long)b * a.P;
+    const float *gcol = a.colors + b * a.colors_stride;
+
+    bool done = !inside;
+    float T = 1.0f;
+    float acc[C];
+#pragma unroll
+    for (int ch = 0; ch < C; ch++) acc[ch] = 0.f;
+    uint32_t contributor = 0, last = 0;
+
+    for (int base = 0; base < n; base += kThreads) {
+        if (__syncthreads_count(done) == kThreads) break;
+        const int idx = base + tid;
+        if (idx < n) {
+            const uint32_t id = (uint32_t)sk[idx];
+            s_xy[tid] = gxy[id];
+            s_co[tid] = gco[id];
+#pragma unroll
+            for (int ch = 0; ch < C; ch++) s_col[tid * C + ch] = gcol[(long long)id * C + ch];
+        }
+        __syncthreads();
+        const int m = min(kThreads, n - base);
+        for (int j = 0; !done && j < m; j++) {
+            contributor++;
+            const float2 c = s_xy[j];
+            const float4 co = s_co[j];
+            const float dx = c.x - pxf, dy = c.y - pyf;
+            const float power = -0.5f * (co.x * dx * dx + co.z * dy * dy) - co.y * dx * dy;
+            if (power > 0.0f) continue;
+            const float alpha = fminf(0.99f, co.w * __expf(power));
+            if (alpha < 1.0f / 255.0f) continue;
+            const float test_T = T * (1.f - alpha);
+            if (test_T < 0.0001f) { done = true; continue; }
+            const float w = alpha * T;
+#pragma unroll
+            for (int ch = 0; ch < C; ch++) acc[ch] += s_col[j * C + ch] * w;
+            T = test_T;
+            last = contributor;
+        }
+    }
+    if (inside) {
+        const long long pix = ((long long)b * a.H + y) * a.W + x;
+        a.final_T[pix] = T;
+        a.n_contrib[pix] = last;
+        const float *bg = a.bg + b * C;
+        if (a.interleaved) {
+            if (C == 4) {
+                reinterpret_cast<float4 *>(a.out_color)[pix] =
+                    make_float4(acc[0] + T * bg[0], acc[1] + T * bg[1], acc[2] + T * bg[2], acc[C - 1] + T * bg[C - 1]);
+            } else {
+#pragma unroll
+                for (int ch = 0; ch < C; ch++) a.out_color[pix * C + ch] = acc[ch] + T * bg[ch];
+            }
+        } else {
+            const long long hw = (long long)a.H * a.W;
+#pragma unroll
+            for (int ch = 0; ch < C; ch++)
+                a.out_color[((long long)b * C + ch) * hw + (long long)y * a.W + x] = acc[ch] + T * bg[ch];
+        }
+    }
+}
+
+}  // namespace
+
+extern "C" int gom_raster_forward(const GomRasterFwdArgs *p, gom_stream_t stream_) {
+    GOM_REQUIRE(p != nullptr, "args");
+    GOM_REQUIRE(p->n_frames > 0 && p->n_gauss >= 0 && p->height > 0 && p->width > 0, "sizes");
+    GOM_REQUIRE(p->n_channels == 3 || p->n_channels == 4, "n_channels must be 3 or 4");
+    GOM_REQUIRE(p->inst_capacity > 0 && p->inst_capacity < 0xffffffffLL, "inst_capacity");
+    GOM_REQUIRE(p->n_frames <= 65535, "n_frames");
+    GOM_REQUIRE(p->means3D && p->cov3D && p->colors && p->opacities && p->viewmatrix && p->projmatrix && p->tanfov &&
+                    p->bg, "null input");
+    GOM_REQUIRE(p->out_color && p->final_T && p->n_contrib && p->radii && p->depth && p->xy && p->conic_opacity &&
+                    p->rect && p->tile_count && p->tile_offset && p->tile_cursor && p->inst_keys && p->point_list &&
+                    p->status, "null output/state");
+    GOM_REQUIRE(((uintptr_t)p->cov3D % 8) == 0 && (p->cov3D_stride % 2) == 0, "cov3D must be 8-byte aligned");
+    GOM_REQUIRE(!(p->interleaved && p->n_channels == 4) || ((uintptr_t)p->out_color % 16) == 0, "out_color alignment");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    FwdDev a;
+    a.B = p->n_frames; a.P = p->n_gauss; a.H = p->height; a.W = p->width; a.C = p->n_channels;
+    a.interleaved = p->interleaved;
+    a.gx = (a.W + GOM_TILE - 1) / GOM_TILE; a.gy = (a.H + GOM_TILE - 1) / GOM_TILE; a.T = a.gx * a.gy;
+    GOM_REQUIRE(a.gy <= 65535, "image too tall");
+    a.cap = p->inst_capacity;
+    a.means3D = p->means3D; a.means3D_stride = p->means3D_stride;
+    a.cov3D = p->cov3D; a.cov3D_stride = p->cov3D_stride;
+    a.colors = p->colors; a.colors_stride = p->colors_stride;
+    a.opac = p->opacities; a.opac_stride = p->opacities_stride;
+    a.view = p->viewmatrix; a.proj = p->projmatrix; a.tanfov = p->tanfov; a.bg = p->bg;
+    a.out_color = p->out_color; a.final_T = p->final_T; a.n_contrib = p->n_contrib; a.radii = p->radii;
+    a.depth = p->depth; a.xy = reinterpret_cast<float2 *>(p->xy);
+    a.conic_opacity = reinterpret_cast<float4 *>(p->conic_opacity); a.rect = reinterpret_cast<int4 *>(p->rect);
+    a.tile_count = p->tile_count; a.tile_offset = p->tile_offset; a.tile_cursor = p->tile_cursor;
+    a.inst_keys = reinterpret_cast<unsigned long long *>(p->inst_keys); a.point_list = p->point_list;
+    a.status = p->status;
+    GOM_REQUIRE(((uintptr_t)p->xy % 8) == 0 && ((uintptr_t)p->conic_opacity % 16) == 0 && ((uintptr_t)p->rect % 16) == 0 &&
+                    ((uintptr_t)p->inst_keys % 8) == 0, "state alignment");
+
+    GOM_CUDA(cudaMemsetAsync(a.tile_count, 0, sizeof(uint32_t) * (size_t)a.B * a.T, stream));
+    if (a.P > 0) {
+        dim3 grid(gom_div_up(a.P, kThreads), a.B);
+        k_preprocess<<<grid, kThreads, 0, stream>>>(a);
+        GOM_LAUNCH_CHECK();
+    }
+    k_scan_tiles<<<a.B, 1024, 0, stream>>>(a);
+    GOM_LAUNCH_CHECK();
+    if (a.P > 0) {
+        dim3 grid(gom_div_up(a.P, kThreads), a.B);
+        k_emit<<<grid, kThreads, 0, stream>>>(a);
+        GOM_LAUNCH_CHECK();
+    }
+    dim3 bgrid(a.gx, a.gy, a.B), bblock(16, 16);
+    if (a.C == 3) k_sort_blend<3><<<bgrid, bblock, 0, stream>>>(a);
+    else k_sort_blend<4><<<bgrid, bblock, 0, stream>>>(a);
+    GOM_LAUNCH_CHECK();
+    return GOM_OK;
+}

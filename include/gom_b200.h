@@ -1,0 +1,150 @@
+/*
+ * gom_b200.h — C ABI of the B200-native GoMAvatar hot path (libgom_b200.so, sm_100a).
+ *
+ * This is the drop-in boundary underneath the reference's two Python boundaries:
+ *   #1  Model.forward(K, E, cnl_gtfms, dst_Rs, dst_Ts, ...)            reference models/model.py:184-188
+ *   #2  GaussianRasterizationSettings / GaussianRasterizer.forward(...) reference models/modules/renderer/gaussian.py:9,20,53-67,83-91
+ * The reference's own native layer is the pybind11/ATen module `diff_gaussian_rasterization._C`
+ * (rasterize_gaussians / rasterize_gaussians_backward; third-party, not in the reference tree) plus ~60 small
+ * torch ops; this header is what replaces them.
+ *
+ * Conventions (every entry point):
+ *   - plain C structs of raw DEVICE pointers + sizes; no torch / C++ types cross the boundary;
+ *   - the CALLER owns every buffer, including scratch and state kept for backward (so a caching allocator and
+ *     CUDA graphs see them); the library never calls cudaMalloc, never synchronises the device, never touches the
+ *     default stream: all work is enqueued on the `stream` argument (a cudaStream_t passed as void*);
+ *   - returns 0 on success or a negative GOM_ERR_*; never throws; gom_last_error() gives the message (per thread);
+ *   - all arrays are fp32 / int32 / uint32 / uint64, C-contiguous in the stated shape; "frame stride" arguments
+ *     are in ELEMENTS; a stride of 0 shares one array between all frames of the batch;
+ *   - B = n_frames (the reference is B = 1), P = n_gauss (= faces F on the fused path), T = tiles per frame.
+ */
+#ifndef GOM_B200_H
+#define GOM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GOM_ABI_VERSION 1
+#define GOM_TILE 16              /* 16x16-pixel tiles, as upstream's BLOCK_X/BLOCK_Y */
+#define GOM_MAX_CHANNELS 4
+#define GOM_MAX_JOINTS 64
+
+enum {
+    GOM_OK = 0,
+    GOM_ERR_INVALID = -1,        /* bad argument (null pointer, unsupported size, ...) */
+    GOM_ERR_CUDA = -2,           /* a CUDA runtime call failed (message has the cudaError string) */
+    GOM_ERR_UNSUPPORTED = -3
+};
+
+/* status bits written to device memory by the rasterizer (checked lazily by the host) */
+#define GOM_STATUS_OVERFLOW 1u   /* a frame produced more (Gaussian,tile) instances than inst_capacity */
+
+typedef void *gom_stream_t;      /* cudaStream_t */
+
+int gom_abi_version(void);
+const char *gom_last_error(void);
+
+/* --------------------------------------------------------------------------------------------------------------
+ * Camera setup.  Replaces the host math + 4 .item() syncs + H2D of reference gaussian.py:30-47,60-61:
+ * K [B,3,3], E [B,4,4]  ->  viewmatrix = E^T, projmatrix = E^T K_ndc^T  (row-major [B,16] each, i.e. exactly the
+ * tensors the reference hands to GaussianRasterizationSettings), tanfov [B,2] = (W/2fx, H/2fy), campos [B,3].
+ * znear 0.001 / zfar 100 as in the reference.
+ */
+typedef struct {
+    int32_t n_frames, height, width, _pad;
+    const float *K;              /* [B,3,3] */
+    const float *E;              /* [B,4,4] */
+    float *viewmatrix;           /* [B,16] */
+    float *projmatrix;           /* [B,16] */
+    float *tanfov;               /* [B,2]  */
+    float *campos;               /* [B,3] (nullable) */
+} GomCameraArgs;
+int gom_camera_from_KE(const GomCameraArgs *a, gom_stream_t stream);
+
+/* --------------------------------------------------------------------------------------------------------------
+ * Splat rasterizer forward.  Replaces `_C.rasterize_gaussians` (preprocessCUDA -> InclusiveSum -> D2H sync ->
+ * duplicateWithKeys -> SortPairs -> identifyTileRanges -> renderCUDA), for the
+ * branch GoMAvatar uses: colors_precomp + cov3D_precomp, sh_degree 0, scale_modifier 1.
+ * No host sync: instance buffers have a fixed per-frame capacity; overflow sets GOM_STATUS_OVERFLOW in status[b]
+ * (the image of that frame is then invalid and the caller re-runs with a larger capacity).
+ */
+typedef struct {
+    int32_t n_frames, n_gauss, height, width;
+    int32_t n_channels;          /* 3 (reference pass) or 4 (fused RGB + alpha pass) */
+    int32_t interleaved;         /* 0: out_color [B,C,H,W] (reference layout); 1: [B,H,W,C] */
+    int64_t inst_capacity;       /* per-frame capacity of inst_keys / point_list */
+    /* inputs */
+    const float *means3D;   int64_t means3D_stride;     /* [B,P,3] */
+    const float *cov3D;     int64_t cov3D_stride;       /* [B,P,6]  xx,xy,xz,yy,yz,zz */
+    const float *colors;    int64_t colors_stride;      /* [B,P,C]  (stride 0: one [P,C] for all frames) */
+    const float *opacities; int64_t opacities_stride;   /* [B,P] */
+    const float *viewmatrix;     /* [B,16] */
+    const float *projmatrix;     /* [B,16] */
+    const float *tanfov;         /* [B,2]  */
+    const float *bg;             /* [B,C]  */
+    /* outputs */
+    float *out_color;            /* [B,C,H,W] or [B,H,W,C] */
+    float *final_T;              /* [B,H,W]  transmittance (mask = 1 - final_T over a zero background) */
+    uint32_t *n_contrib;         /* [B,H,W]  index of the last contributing list entry (1-based) */
+    int32_t *radii;              /* [B,P]    0 = culled */
+    /* per-Gaussian state kept for backward */
+    float *depth;                /* [B,P]   view-space z */
+    float *xy;                   /* [B,P,2] pixel centre */
+    float *conic_opacity;        /* [B,P,4] conic A,B,C + opacity */
+    int32_t *rect;               /* [B,P,4] tile rect minx,miny,maxx,maxy (max exclusive) */
+    /* binning state */
+    uint32_t *tile_count;        /* [B,T]   */
+    uint32_t *tile_offset;       /* [B,T+1] exclusive scan; [b][T] = N_dup of frame b */
+    uint32_t *tile_cursor;       /* [B,T]   scratch */
+    uint64_t *inst_keys;         /* [B,cap] (depth bits << 32 | gaussian id), grouped by tile, unsorted */
+    uint32_t *point_list;        /* [B,cap] gaussian ids grouped by tile, sorted by (depth, id) */
+    uint32_t *status;            /* [B]     GOM_STATUS_* bits */
+} GomRasterFwdArgs;
+int gom_raster_forward(const GomRasterFwdArgs *a, gom_stream_t stream);
+
+/* Splat rasterizer backward.  Replaces `_C.rasterize_gaussians_backward` (renderCUDA bwd, computeCov2DCUDA,
+ * preprocessCUDA bwd; App. A.6-A.7).  Gradient buffers are zeroed by the call itself. */
+typedef struct {
+    int32_t n_frames, n_gauss, height, width;
+    int32_t n_channels, interleaved;
+    int64_t inst_capacity;
+    const float *means3D;   int64_t means3D_stride;
+    const float *cov3D;     int64_t cov3D_stride;
+    const float *colors;    int64_t colors_stride;
+    const float *viewmatrix;
+    const float *projmatrix;
+    const float *tanfov;
+    const float *bg;
+    /* saved forward state */
+    const float *final_T;
+    const uint32_t *n_contrib;
+    const int32_t *radii;
+    const float *xy;
+    const float *conic_opacity;
+    const uint32_t *tile_offset;
+    const uint32_t *point_list;
+    /* upstream gradient */
+    const float *dL_dout;        /* same layout as out_color */
+    /* outputs */
+    float *dL_dmeans3D;          /* [B,P,3] */
+    float *dL_dcov3D;            /* [B,P,6] */
+    float *dL_dcolors;  int64_t dL_dcolors_stride;      /* [B,P,C]; stride 0: [P,C] summed over frames */
+    float *dL_dopacity;          /* [B,P] (nullable: not computed) */
+    float *dL_dmeans2D;          /* [B,P,2] screen-space gradient (App. A.6), also scratch */
+    float *dL_dconic;            /* [B,P,3] scratch */
+} GomRasterBwdArgs;
+int gom_raster_backward(const GomRasterBwdArgs *a, gom_stream_t stream);
+
+/* struct sizes, so that a foreign-language binding can assert its mirror of the structs */
+size_t gom_sizeof_camera_args(void);
+size_t gom_sizeof_raster_fwd_args(void);
+size_t gom_sizeof_raster_bwd_args(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GOM_B200_H */
