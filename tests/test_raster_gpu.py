@@ -8,7 +8,7 @@ import pytest
 import torch
 
 from oracle import raster as R
-from tests.util_scene import raster_inputs
+from util_scene import raster_inputs
 
 pytestmark = pytest.mark.gpu
 

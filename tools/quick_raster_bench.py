@@ -1,9 +1,10 @@
 """Development micro-benchmark: rasterizer forward / backward per-launch times with CUDA events (not bench.py)."""
 import sys, os, json
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+_R = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, _R); sys.path.insert(0, os.path.join(_R, "tests"))
 import numpy as np
 import torch
-from tests.util_scene import raster_inputs
+from util_scene import raster_inputs
 from gomavatar_b200.rasterizer import rasterize_gaussians
 
 
