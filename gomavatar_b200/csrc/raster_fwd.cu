@@ -168,21 +168,21 @@ __device__ __forceinline__ void cmpxchg(unsigned long long *k, int i, int j) {
     if (x > y) { k[i] = y; k[j] = x; }
 }
 
-__device__ void block_sort(unsigned long long *k, int n) {
+__device__ void block_sort(unsigned long long *k, int n, int tid) {
     if (n < 2) return;
     int npad = 2;
     while (npad < n) npad <<= 1;
     const int half = npad >> 1;
     for (int size = 2; size <= npad; size <<= 1) {
         const int hs = size >> 1;
-        for (int t = threadIdx.x; t < half; t += kThreads) {          // flip
+        for (int t = tid; t < half; t += kThreads) {                  // flip
             const int blk = t / hs, w = t - blk * hs;
             const int i = blk * size + w, j = blk * size + (size - 1 - w);
             if (j < n) cmpxchg(k, i, j);
         }
         __syncthreads();
         for (int step = hs >> 1; step >= 1; step >>= 1) {              // disperse
-            for (int t = threadIdx.x; t < half; t += kThreads) {
+            for (int t = tid; t < half; t += kThreads) {
                 const int i = 2 * step * (t / step) + (t % step), j = i + step;
                 if (j < n) cmpxchg(k, i, j);
             }
@@ -215,7 +215,7 @@ __global__ void __launch_bounds__(kThreads) k_sort_blend(FwdDev a) {
         sk = skeys;
         __syncthreads();
     }
-    block_sort(sk, n);
+    block_sort(sk, n, tid);
     uint32_t *plist = a.point_list + (long long)b * a.cap + start;
     for (int i = tid; i < n; i += kThreads) plist[i] = (uint32_t)sk[i];
 
