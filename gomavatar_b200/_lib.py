@@ -52,11 +52,62 @@ class GomRasterBwdArgs(ctypes.Structure):
                 ("dL_dopacity", c_void_p), ("dL_dmeans2D", c_void_p), ("dL_dconic", c_void_p)]
 
 
+class GomJointFwdArgs(ctypes.Structure):
+    _fields_ = [("n_frames", c_int32), ("n_joints", c_int32), ("parents", c_void_p), ("cnl_gtfms", c_void_p),
+                ("dst_Rs", c_void_p), ("dst_Ts", c_void_p), ("global_Rs", c_void_p), ("global_Ts", c_void_p),
+                ("chain_G", c_void_p), ("cnl_inv", c_void_p)]
+
+
+class GomJointBwdArgs(ctypes.Structure):
+    _fields_ = [("n_frames", c_int32), ("n_joints", c_int32), ("parents", c_void_p), ("dst_Rs", c_void_p),
+                ("dst_Ts", c_void_p), ("chain_G", c_void_p), ("cnl_inv", c_void_p), ("dL_dglobal_Rs", c_void_p),
+                ("dL_dglobal_Ts", c_void_p), ("dL_ddst_Rs", c_void_p), ("dL_ddst_Ts", c_void_p)]
+
+
+class GomLbsFwdArgs(ctypes.Structure):
+    _fields_ = [("n_frames", c_int32), ("n_joints", c_int32), ("n_verts", c_int32), ("_pad", c_int32),
+                ("xyz", c_void_p), ("xyz_stride", c_int64), ("lbs_weights", c_void_p), ("global_Rs", c_void_p),
+                ("global_Ts", c_void_p), ("out", c_void_p)]
+
+
+class GomLbsBwdArgs(ctypes.Structure):
+    _fields_ = [("n_frames", c_int32), ("n_joints", c_int32), ("n_verts", c_int32), ("_pad", c_int32),
+                ("xyz", c_void_p), ("xyz_stride", c_int64), ("lbs_weights", c_void_p), ("global_Rs", c_void_p),
+                ("global_Ts", c_void_p), ("dL_dout", c_void_p), ("dL_dxyz", c_void_p), ("dL_dxyz_stride", c_int64),
+                ("dL_dglobal_Rs", c_void_p), ("dL_dglobal_Ts", c_void_p)]
+
+
+class GomFaceFwdArgs(ctypes.Structure):
+    _fields_ = [("n_frames", c_int32), ("n_faces", c_int32), ("n_verts", c_int32), ("faces_int64", c_int32),
+                ("sigma", c_float), ("_pad", c_int32), ("verts", c_void_p), ("faces", c_void_p), ("so3", c_void_p),
+                ("scale", c_void_p), ("means3D", c_void_p), ("cov3D", c_void_p)]
+
+
+class GomFaceBwdArgs(ctypes.Structure):
+    _fields_ = [("n_frames", c_int32), ("n_faces", c_int32), ("n_verts", c_int32), ("faces_int64", c_int32),
+                ("sigma", c_float), ("_pad", c_int32), ("verts", c_void_p), ("faces", c_void_p), ("so3", c_void_p),
+                ("scale", c_void_p), ("dL_dmeans3D", c_void_p), ("dL_dcov3D", c_void_p), ("dL_dverts", c_void_p),
+                ("dL_dso3", c_void_p), ("dL_dscale", c_void_p)]
+
+
 # every symbol include/gom_b200.h declares (tests check the .so exports all of them)
 EXPORTS = [
     "gom_abi_version", "gom_last_error", "gom_camera_from_KE", "gom_raster_forward", "gom_raster_backward",
+    "gom_joint_transforms_forward", "gom_joint_transforms_backward", "gom_lbs_forward", "gom_lbs_backward",
+    "gom_face_gaussians_forward", "gom_face_gaussians_backward",
     "gom_sizeof_camera_args", "gom_sizeof_raster_fwd_args", "gom_sizeof_raster_bwd_args",
+    "gom_sizeof_joint_fwd_args", "gom_sizeof_joint_bwd_args", "gom_sizeof_lbs_fwd_args", "gom_sizeof_lbs_bwd_args",
+    "gom_sizeof_face_fwd_args", "gom_sizeof_face_bwd_args",
 ]
+
+_STRUCTS = {
+    "camera": GomCameraArgs, "raster_fwd": GomRasterFwdArgs, "raster_bwd": GomRasterBwdArgs,
+    "joint_fwd": GomJointFwdArgs, "joint_bwd": GomJointBwdArgs, "lbs_fwd": GomLbsFwdArgs, "lbs_bwd": GomLbsBwdArgs,
+    "face_fwd": GomFaceFwdArgs, "face_bwd": GomFaceBwdArgs,
+}
+_ENTRY_POINTS = ["gom_camera_from_KE", "gom_raster_forward", "gom_raster_backward", "gom_joint_transforms_forward",
+                 "gom_joint_transforms_backward", "gom_lbs_forward", "gom_lbs_backward", "gom_face_gaussians_forward",
+                 "gom_face_gaussians_backward"]
 
 _lib = None
 
@@ -76,15 +127,14 @@ def lib():
     L = ctypes.CDLL(LIB_PATH)
     L.gom_last_error.restype = c_char_p
     L.gom_abi_version.restype = c_int
-    for name in ("gom_sizeof_camera_args", "gom_sizeof_raster_fwd_args", "gom_sizeof_raster_bwd_args"):
-        getattr(L, name).restype = c_size_t
     if L.gom_abi_version() != ABI_VERSION:
         raise GomError(f"libgom_b200.so ABI {L.gom_abi_version()} != binding {ABI_VERSION}: rebuild")
-    for cls, fn in ((GomCameraArgs, L.gom_sizeof_camera_args), (GomRasterFwdArgs, L.gom_sizeof_raster_fwd_args),
-                    (GomRasterBwdArgs, L.gom_sizeof_raster_bwd_args)):
+    for key, cls in _STRUCTS.items():
+        fn = getattr(L, f"gom_sizeof_{key}_args")
+        fn.restype = c_size_t
         if ctypes.sizeof(cls) != fn():
             raise GomError(f"struct {cls.__name__}: ctypes mirror is {ctypes.sizeof(cls)} B, library says {fn()} B")
-    for name in ("gom_camera_from_KE", "gom_raster_forward", "gom_raster_backward"):
+    for name in _ENTRY_POINTS:
         f = getattr(L, name)
         f.restype = c_int
         f.argtypes = [c_void_p, c_void_p]
@@ -95,6 +145,17 @@ def lib():
 def check(rc, what):
     if rc != 0:
         raise GomError(f"{what} failed ({rc}): {lib().gom_last_error().decode()}")
+
+
+def stream_ptr():
+    """current torch CUDA stream as the gom_stream_t argument"""
+    import torch
+    return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def call(name, args):
+    """invoke an entry point on the current torch stream and raise on a non-zero return code"""
+    check(getattr(lib(), name)(ctypes.byref(args), stream_ptr()), name)
 
 
 def ptr(t):

@@ -18,6 +18,12 @@ extern "C" int gom_abi_version(void) { return GOM_ABI_VERSION; }
 extern "C" size_t gom_sizeof_camera_args(void) { return sizeof(GomCameraArgs); }
 extern "C" size_t gom_sizeof_raster_fwd_args(void) { return sizeof(GomRasterFwdArgs); }
 extern "C" size_t gom_sizeof_raster_bwd_args(void) { return sizeof(GomRasterBwdArgs); }
+extern "C" size_t gom_sizeof_joint_fwd_args(void) { return sizeof(GomJointFwdArgs); }
+extern "C" size_t gom_sizeof_joint_bwd_args(void) { return sizeof(GomJointBwdArgs); }
+extern "C" size_t gom_sizeof_lbs_fwd_args(void) { return sizeof(GomLbsFwdArgs); }
+extern "C" size_t gom_sizeof_lbs_bwd_args(void) { return sizeof(GomLbsBwdArgs); }
+extern "C" size_t gom_sizeof_face_fwd_args(void) { return sizeof(GomFaceFwdArgs); }
+extern "C" size_t gom_sizeof_face_bwd_args(void) { return sizeof(GomFaceBwdArgs); }
 
 // Host math of reference models/modules/renderer/gaussian.py:30-47,60-61 moved on device: the four .item() syncs and
 // the host-built K_ndc + H2D copy disappear.  Scalars are formed in fp64 from the fp32 K entries and rounded to fp32

@@ -1,0 +1,178 @@
+"""``Model``: the per-frame forward of GoMAvatar on the B200-native kernels, behind the reference's signature.
+
+Mirrors reference ``models/model.py::Model`` (constructor ``Model(model_cfg, canonical_info)``, ``forward`` signature at
+:184-188, return value ``(rgbs, masks, outputs)`` at :303) and keeps its state-dict keys and SoA parameter layouts
+(``vertices [3,V]``, ``so3 [3,F]``, ``scale [3,F]``, ``appearance_module.appearance [3,F]``, buffers ``faces``,
+``lbs_weights [J+1,V]``) so reference checkpoints load unchanged.
+
+What differs from the reference, by design:
+* every frame of the batch is processed by the same launches (the reference asserts B == 1, gaussian.py:24);
+* LBS -> face frame -> covariance -> splat is ~10 kernel launches with no host sync instead of ~150 launches and 6 syncs;
+* RGB and alpha are rendered in ONE 4-channel pass instead of the reference's two 3-channel passes
+  (gaussian.py:77-94) — same values, same gradients (tests/test_model_gpu.py).
+The pose-refinement / non-rigid MLPs, the mesh normal renderer and the shadow MLP are NOT part of the hot path
+(SURVEY.md §8f "next" rows); they plug in as optional callables with the reference's call signatures.
+"""
+from __future__ import annotations
+
+from types import SimpleNamespace
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from .camera import camera_from_KE
+from .rasterizer import rasterize_gaussians
+from .skinning import apply_lbs, face_gaussians, get_global_RTs
+
+
+def _get(cfg, path, default):
+    cur = cfg
+    for key in path.split("."):
+        if cur is None:
+            return default
+        cur = cur.get(key, None) if isinstance(cur, dict) else getattr(cur, key, None)
+    return default if cur is None else cur
+
+
+def default_model_cfg(img_size=(512, 512), sigma=1e-3):
+    """The subset of the reference's ``cfg.model`` node the hot path reads (configs/default.yaml:56-76)."""
+    return SimpleNamespace(img_size=list(img_size), eval_mode=False,
+                           canonical_geometry=SimpleNamespace(sigma=sigma, radius_scale=1.0, deform_scale=True, deform_so3=True),
+                           appearance=SimpleNamespace(color_init=0.5))
+
+
+def rodrigues(rvec):
+    """reference utils/network_util.py:66-92 (RodriguesModule), theta = sqrt(1e-5 + |r|^2); rvec [B,3] -> [B,3,3]."""
+    theta = torch.sqrt(1e-5 + torch.sum(rvec ** 2, dim=1))
+    r = rvec / theta[:, None]
+    c, s = torch.cos(theta), torch.sin(theta)
+    x, y, z = r[:, 0], r[:, 1], r[:, 2]
+    oc = 1.0 - c
+    return torch.stack((x * x + (1.0 - x * x) * c, x * y * oc - z * s, x * z * oc + y * s,
+                        x * y * oc + z * s, y * y + (1.0 - y * y) * c, y * z * oc - x * s,
+                        x * z * oc - y * s, y * z * oc + x * s, z * z + (1.0 - z * z) * c), dim=1).view(-1, 3, 3)
+
+
+class AppearanceModule(nn.Module):
+    """reference models/modules/appearance_module.py:6-23 — per-face RGB + zero background buffer."""
+
+    def __init__(self, n_faces, color_init=0.5):
+        super().__init__()
+        self.appearance = nn.Parameter(torch.ones(3, n_faces) * color_init)
+        self.register_buffer("bg_col", torch.zeros(3))
+
+    def forward(self, **kwargs):
+        return self.appearance, self.bg_col
+
+
+class Model(nn.Module):
+    def __init__(self, model_cfg, canonical_info, pose_refinement_module=None, non_rigid_module=None,
+                 normal_renderer=None, shadow_module=None, strict_raster=True):
+        super().__init__()
+        self.cfg = model_cfg
+        faces = torch.as_tensor(np.asarray(canonical_info["faces"]).astype(np.int64))
+        self.register_buffer("faces", faces)
+        w = torch.as_tensor(np.asarray(canonical_info["canonical_lbs_weights"])).float().transpose(1, 0)     # [J,V]
+        self.register_buffer("lbs_weights", torch.cat([w, torch.zeros_like(w[:1])], dim=0).contiguous())   # [J+1,V]
+        F = faces.shape[0]
+        verts = torch.as_tensor(np.asarray(canonical_info["canonical_vertex"])).float().transpose(1, 0).contiguous()
+        self.vertices = nn.Parameter(verts)
+        radius = float(_get(model_cfg, "canonical_geometry.radius_scale", 1.0))
+        if _get(model_cfg, "canonical_geometry.deform_so3", True):
+            self.so3 = nn.Parameter(torch.zeros(3, F))
+        else:
+            self.register_buffer("so3", torch.zeros(3, F))
+        if _get(model_cfg, "canonical_geometry.deform_scale", True):
+            self.scale = nn.Parameter(torch.ones(3, F) * radius)
+        else:
+            self.register_buffer("scale", torch.ones(3, F) * radius)
+        self.appearance_module = AppearanceModule(F, float(_get(model_cfg, "appearance.color_init", 0.5)))
+        self.pose_refinement_module = pose_refinement_module
+        self.non_rigid_module = non_rigid_module
+        self.normal_renderer = normal_renderer
+        self.shadow_module = shadow_module
+        self.strict_raster = strict_raster
+        self.last_raster_aux = None
+
+    def forward(self, K, E, cnl_gtfms, dst_Rs, dst_Ts, dst_posevec=None, canonical_joints=None,
+                i_iter=1e7, bgcolor=None, global_R=None, global_T=None, tb=None):
+        B = dst_Rs.shape[0]
+        W, H = _get(self.cfg, "img_size", [512, 512])
+        sigma = float(_get(self.cfg, "canonical_geometry.sigma", 1e-3))
+
+        if self.pose_refinement_module is not None and i_iter >= _get(self.cfg, "pose_refinement.kick_in_iter", 0):
+            J = dst_Rs.shape[1]                                    # reference model.py:193-196
+            delta = self.pose_refinement_module(dst_posevec)
+            dst_Rs = torch.matmul(dst_Rs.reshape(B * J, 3, 3), delta.reshape(B * J, 3, 3)).reshape(B, J, 3, 3)
+
+        vertices_canonical = self.vertices
+        if self.non_rigid_module is not None and i_iter >= _get(self.cfg, "non_rigid.kick_in_iter", 0):
+            vertices_pose, _, _ = self.non_rigid_module(vertices_canonical.unsqueeze(0), dst_posevec, i_iter, R=None, S=None)
+        else:                                                      # reference model.py:199-210
+            vertices_pose = vertices_canonical.unsqueeze(0)
+
+        global_Rs, global_Ts = get_global_RTs(cnl_gtfms, dst_Rs, dst_Ts)
+        vertices_observation = apply_lbs(vertices_pose, global_Rs, global_Ts, self.lbs_weights)     # [B,3,V]
+        if global_R is not None:                                   # reference model.py:218-221 (train_pose.py)
+            Rg = rodrigues(global_R.reshape(-1, 3))
+            gT = global_T.reshape(-1, 3)
+            vertices_observation = Rg @ vertices_observation + gT[:, :, None]
+
+        means3D, cov3D = face_gaussians(vertices_observation, self.faces, self.so3, self.scale, sigma)
+        appearance, bg_feat = self.appearance_module()
+        colors = torch.cat([appearance.permute(1, 0), torch.ones_like(appearance[:1]).permute(1, 0)], dim=1)   # [F,4]
+        opacity = torch.ones(B, colors.shape[0], device=colors.device)
+        view, proj, tanfov = camera_from_KE(K, E, H, W)
+        bg = torch.cat([bg_feat, bg_feat.new_zeros(1)])[None].expand(B, 4)
+        aux = {}
+        rgba, radii, final_T, _ = rasterize_gaussians(means3D, cov3D, colors, opacity, view, proj, tanfov, bg, H, W,
+                                                      interleaved=True, strict=self.strict_raster, aux=aux)
+        self.last_raster_aux = aux
+        albedos, masks = rgba[..., :3], rgba[..., 3]
+
+        normal = normal_mask = shadings = None
+        if self.normal_renderer is not None and self.shadow_module is not None:     # reference model.py:271-287
+            normals = self._vertex_normals(vertices_observation)
+            normals = torch.bmm(E[:, :3, :3], normals.permute(0, 2, 1)).permute(0, 2, 1)
+            normal, normal_mask = self.normal_renderer(vertices_observation, normals, K, E, faces=self.faces)
+            shadings = self.shadow_module(normal.reshape(B, H * W, 3)).reshape(B, H, W, 1) * 2
+            rgbs = albedos * shadings
+        else:
+            rgbs = albedos
+
+        outputs = {}
+        if self.training:
+            outputs["colors"] = appearance.permute(1, 0)
+            outputs["vertices_observation"] = vertices_observation
+            outputs["albedo"] = albedos[0]
+            outputs["radii"] = radii
+            if normal is not None:
+                outputs["normal"], outputs["normal_mask"], outputs["shadow"] = normal, normal_mask[..., 0], shadings
+        return rgbs, masks, outputs
+
+    def _vertex_normals(self, verts_b3v):
+        """PyTorch3D ``Meshes.verts_normals_padded`` semantics: area-weighted face normals
+        accumulated on vertices, normalised with eps 1e-6.  Only used when a normal renderer is plugged in."""
+        v = verts_b3v.permute(0, 2, 1)
+        f = self.faces
+        n = torch.cross(v[:, f[:, 1]] - v[:, f[:, 0]], v[:, f[:, 2]] - v[:, f[:, 0]], dim=-1)
+        vn = torch.zeros_like(v)
+        for k in range(3):
+            vn = vn.index_add(1, f[:, k], n)
+        return torch.nn.functional.normalize(vn, eps=1e-6, dim=-1)
+
+    def get_param_groups(self, cfg):
+        """reference models/model.py:305-324 (lr names from configs/default.yaml:91-99)."""
+        lr = cfg.lr if hasattr(cfg, "lr") else cfg["lr"]
+        g = lambda k: getattr(lr, k) if hasattr(lr, k) else lr[k]
+        groups = [{"name": "appearance", "params": list(self.appearance_module.parameters()), "lr": g("appearance")},
+                  {"name": "canonical_geometry_xyz", "params": [self.vertices], "lr": g("canonical_geometry_xyz")}]
+        for p in (self.scale, self.so3):
+            if isinstance(p, nn.Parameter):
+                groups.append({"name": "canonical_geometry", "params": [p], "lr": g("canonical_geometry")})
+        for name, mod in (("non_rigid", self.non_rigid_module), ("pose_refinement", self.pose_refinement_module),
+                          ("shadow", self.shadow_module)):
+            if isinstance(mod, nn.Module):
+                groups.append({"name": name, "params": list(mod.parameters()), "lr": g(name)})
+        return groups

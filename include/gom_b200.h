@@ -139,10 +139,110 @@ typedef struct {
 } GomRasterBwdArgs;
 int gom_raster_backward(const GomRasterBwdArgs *a, gom_stream_t stream);
 
+
+/* --------------------------------------------------------------------------------------------------------------
+ * Skeleton: per-joint skinning transforms.  Replaces reference utils/body_util.py:612-638 `get_global_RTs`
+ * (+ _construct_G_tensor :591-609): local G_i = [R_i|T_i], chained root-to-leaf along `parents` (parents[0] = -1,
+ * parents[i] < i; SMPL_PARENT at body_util.py:36-39), F_i = G_i inv(cnl_gtfms_i); returns F[:3,:3] and F[:3,3].
+ * ~50 torch launches (23 sequential matmul+clone, batched LU) become one.
+ */
+typedef struct {
+    int32_t n_frames, n_joints;
+    const int32_t *parents;      /* [J] (device) */
+    const float *cnl_gtfms;      /* [B,J,4,4] */
+    const float *dst_Rs;         /* [B,J,3,3] */
+    const float *dst_Ts;         /* [B,J,3]   */
+    float *global_Rs;            /* [B,J,3,3] out */
+    float *global_Ts;            /* [B,J,3]   out */
+    float *chain_G;              /* [B,J,12]  top three rows of the chained transforms (kept for backward) */
+    float *cnl_inv;              /* [B,J,16]  inverted canonical transforms (kept for backward) */
+} GomJointFwdArgs;
+int gom_joint_transforms_forward(const GomJointFwdArgs *a, gom_stream_t stream);
+
+typedef struct {
+    int32_t n_frames, n_joints;
+    const int32_t *parents;
+    const float *dst_Rs, *dst_Ts;    /* forward inputs */
+    const float *chain_G, *cnl_inv;  /* forward state */
+    const float *dL_dglobal_Rs;      /* [B,J,3,3] */
+    const float *dL_dglobal_Ts;      /* [B,J,3]   */
+    float *dL_ddst_Rs;               /* [B,J,3,3] out */
+    float *dL_ddst_Ts;               /* [B,J,3]   out */
+} GomJointBwdArgs;
+int gom_joint_transforms_backward(const GomJointBwdArgs *a, gom_stream_t stream);
+
+/* --------------------------------------------------------------------------------------------------------------
+ * Linear-blend skinning.  Replaces reference utils/body_util.py:641-644 `apply_lbs`:
+ *   out[b,:,v] = sum_{j<J} w[j,v] (R[b,j] xyz[:,v] + T[b,j]),  weights are the model's [J+1,V] buffer whose last
+ * (background) row is ignored; no renormalisation.  SoA layouts are the reference's ([3,V], [J+1,V]) so checkpoints
+ * load unchanged.  Weight tiles are staged into shared memory with TMA bulk copies (cp.async.bulk) when the buffer
+ * is 16-byte aligned, else with plain coalesced loads.
+ */
+typedef struct {
+    int32_t n_frames, n_joints, n_verts, _pad;
+    const float *xyz;        int64_t xyz_stride;        /* [B,3,V] or one [3,V] (stride 0) */
+    const float *lbs_weights;                            /* [J+1,V] (rows 0..J-1 are read) */
+    const float *global_Rs;                              /* [B,J,3,3] */
+    const float *global_Ts;                              /* [B,J,3]   */
+    float *out;                                          /* [B,3,V]   */
+} GomLbsFwdArgs;
+int gom_lbs_forward(const GomLbsFwdArgs *a, gom_stream_t stream);
+
+typedef struct {
+    int32_t n_frames, n_joints, n_verts, _pad;
+    const float *xyz;        int64_t xyz_stride;
+    const float *lbs_weights;
+    const float *global_Rs, *global_Ts;
+    const float *dL_dout;                                /* [B,3,V] */
+    float *dL_dxyz;          int64_t dL_dxyz_stride;     /* [B,3,V], or [3,V] summed over frames (stride 0) */
+    float *dL_dglobal_Rs;                                /* [B,J,3,3] (nullable together with dL_dglobal_Ts) */
+    float *dL_dglobal_Ts;                                /* [B,J,3]   */
+} GomLbsBwdArgs;
+int gom_lbs_backward(const GomLbsBwdArgs *a, gom_stream_t stream);
+
+/* --------------------------------------------------------------------------------------------------------------
+ * Gaussians on mesh: one Gaussian per face, carried by the face's Steiner-ellipse frame.  Replaces reference
+ * models/model.py:225-234 (+ get_transformation_from_triangle_steiner :27-41, PyTorch3D so3_exp_map) and the
+ * covariance packing of models/modules/renderer/gaussian.py:71-75:
+ *   mean_f = centroid(tri_f);  Sigma_f = A_f R(so3_f) S_f S_f^T R^T A_f^T packed (xx,xy,xz,yy,yz,zz).
+ * ~35 torch launches and a dozen [F,3,3] temporaries become one kernel.
+ */
+typedef struct {
+    int32_t n_frames, n_faces, n_verts, faces_int64;
+    float sigma; int32_t _pad;
+    const float *verts;          /* [B,3,V] posed ("observation") vertices, SoA */
+    const void *faces;           /* [F,3] int32, or int64 when faces_int64 (the model's registered buffer) */
+    const float *so3;            /* [3,F] */
+    const float *scale;          /* [3,F] */
+    float *means3D;              /* [B,F,3] out */
+    float *cov3D;                /* [B,F,6] out */
+} GomFaceFwdArgs;
+int gom_face_gaussians_forward(const GomFaceFwdArgs *a, gom_stream_t stream);
+
+typedef struct {
+    int32_t n_frames, n_faces, n_verts, faces_int64;
+    float sigma; int32_t _pad;
+    const float *verts;
+    const void *faces;
+    const float *so3, *scale;
+    const float *dL_dmeans3D;    /* [B,F,3] */
+    const float *dL_dcov3D;      /* [B,F,6] */
+    float *dL_dverts;            /* [B,3,V] out (zeroed by the call, scatter-added) */
+    float *dL_dso3;              /* [3,F]   out, summed over frames */
+    float *dL_dscale;            /* [3,F]   out, summed over frames */
+} GomFaceBwdArgs;
+int gom_face_gaussians_backward(const GomFaceBwdArgs *a, gom_stream_t stream);
+
 /* struct sizes, so that a foreign-language binding can assert its mirror of the structs */
 size_t gom_sizeof_camera_args(void);
 size_t gom_sizeof_raster_fwd_args(void);
 size_t gom_sizeof_raster_bwd_args(void);
+size_t gom_sizeof_joint_fwd_args(void);
+size_t gom_sizeof_joint_bwd_args(void);
+size_t gom_sizeof_lbs_fwd_args(void);
+size_t gom_sizeof_lbs_bwd_args(void);
+size_t gom_sizeof_face_fwd_args(void);
+size_t gom_sizeof_face_bwd_args(void);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,132 @@
+"""GPU parity: skeleton chain, LBS and Gaussians-on-mesh kernels (through the C ABI) against the reference's own
+outputs (tests/golden/golden_lbs.npz, produced by utils/body_util.py) and against the CPU oracle + its autograd.
+Tolerances: forward 1e-5 absolute on metre-scale coordinates / 1e-5 relative-to-row-max on covariances; gradients
+1e-3 relative (north_star)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from gomavatar_b200 import synthetic as S
+from oracle import geometry as G
+
+pytestmark = pytest.mark.gpu
+t = torch.from_numpy
+DEV = "cuda:0"
+
+
+def _rel(got, ref):
+    return float(np.abs(got - ref).max() / max(np.abs(ref).max(), 1e-30))
+
+
+def test_get_global_RTs_and_apply_lbs_match_reference_golden(golden_dir):
+    from gomavatar_b200.skinning import apply_lbs, get_global_RTs
+    g = np.load(os.path.join(golden_dir, "golden_lbs.npz"))
+    c = lambda k: t(g[k]).to(DEV)
+    Rs, Ts = get_global_RTs(c("cnl_gtfms"), c("dst_Rs"), c("dst_Ts"))
+    np.testing.assert_allclose(Rs.cpu().numpy(), g["global_Rs"], atol=2e-6)
+    np.testing.assert_allclose(Ts.cpu().numpy(), g["global_Ts"], atol=2e-6)
+    v = apply_lbs(c("vertices")[None], Rs, Ts, c("lbs_weights"))          # 3 frames share one vertex set
+    np.testing.assert_allclose(v.cpu().numpy(), g["vertices_observation"], atol=2e-6)
+    # reference call pattern: one frame at a time (models/model.py:213-216)
+    v0 = apply_lbs(c("vertices").unsqueeze(0), *get_global_RTs(c("cnl_gtfms")[:1], c("dst_Rs")[:1], c("dst_Ts")[:1]),
+                   c("lbs_weights"))[0]
+    np.testing.assert_allclose(v0.cpu().numpy(), g["vertices_observation"][0], atol=2e-6)
+
+
+def _random_affine(rng, n):
+    A = np.tile(np.eye(4, dtype=np.float32), (n, 1, 1))
+    for i in range(n):
+        A[i, :3, :3] = S.rvec_to_rmtx(rng.normal(0, 0.7, 3)) * rng.uniform(0.7, 1.4)
+        A[i, :3, 3] = rng.normal(0, 0.5, 3)
+    return A
+
+
+def test_joint_chain_general_matrices_and_backward():
+    from gomavatar_b200.skinning import get_global_RTs
+    rng = np.random.default_rng(0)
+    B, J = 5, 24
+    cnl = _random_affine(rng, B * J).reshape(B, J, 4, 4)
+    Rs = _random_affine(rng, B * J).reshape(B, J, 4, 4)[:, :, :3, :3].copy()
+    Ts = rng.normal(0, 0.3, (B, J, 3)).astype(np.float32)
+    gR, gT = rng.normal(size=(B, J, 3, 3)).astype(np.float32), rng.normal(size=(B, J, 3)).astype(np.float32)
+    # oracle, float64 autograd
+    oR, oT = t(Rs).double().requires_grad_(True), t(Ts).double().requires_grad_(True)
+    rR, rT = G.get_global_RTs(t(cnl).double(), oR, oT)
+    ((rR * t(gR).double()).sum() + (rT * t(gT).double()).sum()).backward()
+    dR_, dT_ = t(Rs).to(DEV).requires_grad_(True), t(Ts).to(DEV).requires_grad_(True)
+    kR, kT = get_global_RTs(t(cnl).to(DEV), dR_, dT_)
+    assert _rel(kR.detach().cpu().numpy(), rR.detach().numpy()) < 1e-5
+    assert _rel(kT.detach().cpu().numpy(), rT.detach().numpy()) < 1e-5
+    ((kR * t(gR).to(DEV)).sum() + (kT * t(gT).to(DEV)).sum()).backward()
+    assert _rel(dR_.grad.cpu().numpy(), oR.grad.numpy()) < 1e-4
+    assert _rel(dT_.grad.cpu().numpy(), oT.grad.numpy()) < 1e-4
+
+
+@pytest.mark.parametrize("n_faces,B,per_frame_xyz,misalign", [(2000, 1, False, False), (2000, 11, False, True),
+                                                               (13776, 3, True, False), (30000, 9, False, False)])
+def test_apply_lbs_forward_backward(n_faces, B, per_frame_xyz, misalign):
+    from gomavatar_b200.skinning import apply_lbs
+    sc = S.make_humanoid(n_faces, seed=1)
+    fr = S.make_frames(sc, B, img_size=64, seed=5)
+    V = sc.n_vertices
+    rng = np.random.default_rng(3)
+    Rs64, Ts64 = G.get_global_RTs(t(fr["cnl_gtfms"]).double(), t(fr["dst_Rs"]).double(), t(fr["dst_Ts"]).double())
+    xyz = sc.vertices.T.copy()[None]
+    if per_frame_xyz:
+        xyz = xyz + rng.normal(0, 0.01, (B, 3, V)).astype(np.float32)
+    gout = rng.normal(size=(B, 3, V)).astype(np.float32)
+    ox = t(xyz).double().requires_grad_(True)
+    oR, oT = Rs64.clone().requires_grad_(True), Ts64.clone().requires_grad_(True)
+    ref = torch.cat([G.apply_lbs(ox[b:b + 1] if per_frame_xyz else ox, oR[b:b + 1], oT[b:b + 1], t(sc.lbs_weights).double())
+                     for b in range(B)])
+    (ref * t(gout).double()).sum().backward()
+    w = t(sc.lbs_weights).to(DEV)
+    if misalign:       # a view whose data pointer is only 4-byte aligned -> plain-load staging path instead of TMA
+        buf = torch.zeros(w.numel() + 1, device=DEV)
+        buf[1:] = w.reshape(-1)
+        w = buf[1:].view_as(w)
+        assert w.data_ptr() % 16 != 0
+    kx = t(xyz).to(DEV).requires_grad_(True)
+    kR, kT = Rs64.float().to(DEV).requires_grad_(True), Ts64.float().to(DEV).requires_grad_(True)
+    out = apply_lbs(kx, kR, kT, w)
+    np.testing.assert_allclose(out.detach().cpu().numpy(), ref.detach().numpy(), atol=3e-6)
+    (out * t(gout).to(DEV)).sum().backward()
+    assert _rel(kx.grad.cpu().numpy(), ox.grad.numpy()) < 1e-4
+    assert _rel(kR.grad.cpu().numpy(), oR.grad.numpy()) < 1e-4
+    assert _rel(kT.grad.cpu().numpy(), oT.grad.numpy()) < 1e-4
+
+
+@pytest.mark.parametrize("n_faces,B,int32_faces,ref_init", [(2000, 1, False, False), (2000, 4, True, True), (30000, 2, False, False)])
+def test_face_gaussians_forward_backward(n_faces, B, int32_faces, ref_init):
+    from gomavatar_b200.skinning import face_gaussians
+    sc = S.make_humanoid(n_faces, seed=2)
+    pr = S.make_params(sc, seed=6, reference_init=ref_init)
+    if ref_init:
+        pr["scale"] = pr["scale"] * np.random.default_rng(1).uniform(0.8, 1.2, pr["scale"].shape).astype(np.float32)
+    fr = S.make_frames(sc, B, img_size=64, seed=8)
+    F, V = sc.n_faces, sc.n_vertices
+    rng = np.random.default_rng(4)
+    Rs, Ts = G.get_global_RTs(t(fr["cnl_gtfms"]), t(fr["dst_Rs"]), t(fr["dst_Ts"]))
+    v_obs = torch.cat([G.apply_lbs(t(pr["vertices"])[None], Rs[b:b + 1], Ts[b:b + 1], t(sc.lbs_weights)) for b in range(B)])
+    gm = rng.normal(size=(B, F, 3)).astype(np.float32)
+    gc = (rng.normal(size=(B, F, 6)) * 1e3).astype(np.float32)
+    ov = v_obs.double().requires_grad_(True)
+    ow, os_ = t(pr["so3"]).double().requires_grad_(True), t(pr["scale"]).double().requires_grad_(True)
+    means, covs = zip(*[G.face_gaussians(ov[b], t(sc.faces), ow, os_, 1e-3) for b in range(B)])
+    rm, rc = torch.stack(means), torch.stack([G.pack_cov6(c) for c in covs])
+    ((rm * t(gm).double()).sum() + (rc * t(gc).double()).sum()).backward()
+    faces = t(sc.faces).to(DEV)
+    if int32_faces:
+        faces = faces.int()
+    kv = v_obs.to(DEV).requires_grad_(True)
+    kw, ks = t(pr["so3"]).to(DEV).requires_grad_(True), t(pr["scale"]).to(DEV).requires_grad_(True)
+    m, c = face_gaussians(kv, faces, kw, ks, 1e-3)
+    np.testing.assert_allclose(m.detach().cpu().numpy(), rm.detach().numpy(), atol=2e-6)
+    rcn = rc.detach().numpy()
+    assert (np.abs(c.detach().cpu().numpy() - rcn) / np.abs(rcn).max(axis=-1, keepdims=True)).max() < 2e-5
+    ((m * t(gm).to(DEV)).sum() + (c * t(gc).to(DEV)).sum()).backward()
+    assert _rel(kv.grad.cpu().numpy(), ov.grad.numpy()) < 3e-4
+    assert _rel(kw.grad.cpu().numpy(), ow.grad.numpy()) < 3e-4
+    assert _rel(ks.grad.cpu().numpy(), os_.grad.numpy()) < 3e-4
