@@ -1,0 +1,379 @@
+#!/usr/bin/env python
+"""bench.py — training-step throughput of the GoMAvatar hot path on B200 (contract: see the task brief / DESIGN.md §5).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # B200-native arm (this repo)
+    python bench.py --impl reference [--steps K] [--warmup W]      # CPU arm: the reference's path via the oracle port
+
+One "step" = forward (joint chain -> LBS -> face frame / covariance -> splat raster) + photometric losses (unpack, L1 rgb,
+L1 mask, LPIPS-VGG) + backward + gradient all-reduce + Adam, over `--frames-per-step` frames per GPU at 512x512 with
+30 000 Gaussians (BASELINE.json configs[2], synthetic stand-in for ZJU-MoCap 377: no dataset/checkpoint offline).
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "train_step_frames_per_sec_512x512_30k_gaussians"
+UNIT = "frames/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--frames-per-step", type=int, default=8, help="frames per GPU per step (reference: 1)")
+    ap.add_argument("--faces", type=int, default=30000)
+    ap.add_argument("--img", type=int, default=512)
+    ap.add_argument("--pool-steps", type=int, default=4, help="distinct batches cycled through")
+    ap.add_argument("--lpips-tf32", type=int, default=0, help="1: run the LPIPS VGG convs with TF32 tensor cores")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-frames", type=int, default=2, help="frames in the bounded CPU-baseline sample")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------ clocks sampler
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx = float(f[2])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ B200 arm
+class Trainer:
+    def __init__(self, args, rank, world, device):
+        from gomavatar_b200 import synthetic as S
+        from gomavatar_b200.dist import FlatArena
+        from gomavatar_b200.lpips import LPIPS, seeded_random_trunk
+        from gomavatar_b200.model import Model, default_model_cfg
+        self.args, self.rank, self.world, self.dev = args, rank, world, device
+        self.B = args.frames_per_step
+        H = W = args.img
+        scene = S.make_humanoid(args.faces, seed=0)
+        self.scene = scene
+        self.model = Model(default_model_cfg(img_size=(W, H)), scene.canonical_info(), strict_raster=False).to(device)
+        pr = S.make_params(scene, seed=1)
+        with torch.no_grad():
+            self.model.so3.copy_(torch.from_numpy(pr["so3"]))
+            self.model.scale.copy_(torch.from_numpy(pr["scale"]))
+            self.model.appearance_module.appearance.copy_(torch.from_numpy(pr["appearance"]))
+        self.model.train()
+        heads = np.load(os.path.join(ROOT, "tests", "golden", "golden_lpips.npz"))
+        self.lpips = LPIPS(seeded_random_trunk(0), [heads[f"lin{k}"] for k in range(5)], allow_tf32=bool(args.lpips_tf32)).to(device)
+        # pool of frames: different poses / cameras / backgrounds per rank
+        n_pool = self.B * args.pool_steps
+        fr = S.make_frames(scene, n_pool, img_size=(W, H), seed=100 + rank)
+        self.keys = ("K", "E", "cnl_gtfms", "dst_Rs", "dst_Ts", "dst_posevec", "bgcolor")
+        self.host = {k: torch.from_numpy(fr[k]).pin_memory() for k in self.keys}
+        self.devd = {k: v.to(device) for k, v in self.host.items()}
+        # targets: render of a perturbed ("teacher") parameter set over the frame's random background
+        self._make_targets(S, n_pool)
+        self.arena = FlatArena(self.model)
+        self.arena.broadcast_params()
+        groups = self.model.get_param_groups(type("C", (), {"lr": {"appearance": 5e-4, "canonical_geometry": 5e-4,
+                                                                "canonical_geometry_xyz": 5e-4}})())
+        self.opt = torch.optim.Adam(groups, lr=5e-4, fused=True)
+        self.h2d_bytes = sum(v[: self.B].numel() * v.element_size() for v in self.host.values()) + \
+            self.host_tgt_rgb[: self.B].numel() * 4 + self.host_tgt_mask[: self.B].numel() * 4
+
+    def _make_targets(self, S, n_pool):
+        from gomavatar_b200.losses import unpack
+        m = self.model
+        rng = np.random.default_rng(7)
+        saved = [p.detach().clone() for p in (m.vertices, m.appearance_module.appearance)]
+        with torch.no_grad():
+            m.vertices.add_(torch.from_numpy(rng.normal(0, 3e-3, tuple(m.vertices.shape)).astype(np.float32)).to(self.dev))
+            m.appearance_module.appearance.copy_(torch.from_numpy(rng.uniform(0, 1, tuple(saved[1].shape)).astype(np.float32)).to(self.dev))
+            rgbs, masks = [], []
+            for s in range(0, n_pool, self.B):
+                sl = slice(s, s + self.B)
+                d = {k: v[sl] for k, v in self.devd.items()}
+                rgb, mask, _ = m(d["K"], d["E"], d["cnl_gtfms"], d["dst_Rs"], d["dst_Ts"], dst_posevec=d["dst_posevec"])
+                rgbs.append(unpack(rgb, mask, d["bgcolor"]).clamp(0, 1)); masks.append(mask.clamp(0, 1).clone())
+            m.vertices.copy_(saved[0]); m.appearance_module.appearance.copy_(saved[1])
+        self.tgt_rgb, self.tgt_mask = torch.cat(rgbs).contiguous(), torch.cat(masks).contiguous()
+        self.host_tgt_rgb, self.host_tgt_mask = self.tgt_rgb.cpu().pin_memory(), self.tgt_mask.cpu().pin_memory()
+
+    def _train(self, d, tgt_rgb, tgt_mask):
+        from gomavatar_b200.losses import compute_loss
+        self.arena.zero_grad()
+        rgb, mask, _ = self.model(d["K"], d["E"], d["cnl_gtfms"], d["dst_Rs"], d["dst_Ts"], dst_posevec=d["dst_posevec"],
+                                  bgcolor=d["bgcolor"])
+        loss, terms, _ = compute_loss(rgb, mask, d["bgcolor"], tgt_rgb, tgt_mask, lpips_func=self.lpips)
+        loss.backward()
+        self.arena.all_reduce_mean()
+        self.opt.step()
+        return loss
+
+    def step_device(self, i):
+        s = (i % self.args.pool_steps) * self.B
+        sl = slice(s, s + self.B)
+        return self._train({k: v[sl] for k, v in self.devd.items()}, self.tgt_rgb[sl], self.tgt_mask[sl])
+
+    def step_e2e(self, i):
+        s = (i % self.args.pool_steps) * self.B
+        sl = slice(s, s + self.B)
+        d = {k: v[sl].to(self.dev, non_blocking=True) for k, v in self.host.items()}
+        tr = self.host_tgt_rgb[sl].to(self.dev, non_blocking=True)
+        tm = self.host_tgt_mask[sl].to(self.dev, non_blocking=True)
+        return float(self._train(d, tr, tm).item())        # D2H read of the step's loss
+
+
+def timed_region(fn, steps, warmup, world, device):
+    """W warm-ups, barrier + sync, K steps between CUDA events on the launching stream, barrier + sync, max over ranks."""
+    import torch.distributed as dist
+    for i in range(warmup):
+        fn(i)
+    torch.cuda.synchronize(device)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(device)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        fn(warmup + i)
+    e1.record()
+    torch.cuda.synchronize(device)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(device)
+    ms = torch.tensor([e0.elapsed_time(e1)], device=device)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    return float(ms.item())
+
+
+def run_b200(args):
+    from gomavatar_b200 import _lib
+    from gomavatar_b200.dist import init_from_env
+    rank, local, world = init_from_env("nccl")
+    if world != args.gpus and rank == 0:
+        print(f"# note: --gpus {args.gpus} but WORLD_SIZE={world}; using WORLD_SIZE", file=sys.stderr)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the hot path has no CPU fallback (use --impl reference for the CPU arm)")
+    device = torch.device("cuda", local)
+    torch.cuda.set_device(device)
+    tr = Trainer(args, rank, world, device)
+    B, K, W_ = args.frames_per_step, args.steps, args.warmup
+    frames_total = K * B * world
+
+    # ---- e2e first (host buffers in, loss out every step), then the device-resident number with per-kernel timers
+    ms_e2e = timed_region(tr.step_e2e, K, max(W_, 3), world, device)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    _lib.profile_enable(True)
+    n0 = _lib.launch_count()
+    ms = timed_region(tr.step_device, K, max(W_, 3), world, device)
+    launches = _lib.launch_count() - n0
+    prof = _lib.profile_read()
+    _lib.profile_enable(False)
+    clocks = sampler.stop() if rank == 0 else None
+    launches_timed = int(round(launches * K / (K + max(W_, 3))))
+
+    # ---- roofline of the dominant hand-written kernel (by measured time inside the timed region)
+    aux = tr.model.last_raster_aux
+    T = ((args.img + 15) // 16) ** 2
+    n_dup = float(aux["tile_offset"][:, T].to(torch.int64).bitwise_and(0xFFFFFFFF).float().mean().item())
+    overflow = int(aux["status"].max().item())
+    HW, F, V = args.img * args.img, tr.scene.n_faces, tr.scene.n_vertices
+    alg_bytes_per_frame = {      # SURVEY.md §8d algorithmic bytes per frame
+        "sort_blend_fwd": 40 * n_dup + 24 * HW, "blend_bwd": 80 * n_dup + 44 * HW, "preprocess": 76 * F,
+        "preprocess_bwd": 76 * F + 36 * F, "emit": 12 * n_dup + 20 * F, "scan_tiles": 12 * T,
+        "lbs_fwd": 120 * V, "lbs_bwd": 120 * V, "face_fwd": 72 * F, "face_bwd": 72 * F + 36 * F,
+        "photo_fwd": 44 * HW, "photo_bwd": 60 * HW}
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "6650 GB/s (of fallback)"
+    kernels = {}
+    for name, (tot_ms, n) in prof.items():
+        per_launch_ms = tot_ms / max(n, 1)
+        byt = alg_bytes_per_frame.get(name, 0.0) * B
+        kernels[name] = {"ms_per_launch": per_launch_ms, "launches": n, "share_of_step": tot_ms / (K + max(W_, 3)) / (ms / K),
+                         "alg_bytes_per_launch": byt, "gbs": byt / (per_launch_ms * 1e-3) / 1e9 if per_launch_ms > 0 else None}
+    dom = max(kernels, key=lambda k: kernels[k]["ms_per_launch"]) if kernels else None
+    roofline = None
+    if dom:
+        k = kernels[dom]
+        roofline = {"kernel": dom, "bound": "hbm", "achieved": k["gbs"], "peak": peak, "unit": "GB/s", "frac": k["gbs"] / peak,
+                    "traffic": None, "peak_source": peak_src, "ms_per_launch": k["ms_per_launch"],
+                    "alg_bytes_per_launch": k["alg_bytes_per_launch"], "n_dup_per_frame": n_dup}
+
+    line = None
+    if rank == 0:
+        value = frames_total / (ms * 1e-3)
+        e2e_value = frames_total / (ms_e2e * 1e-3)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": max(W_, 3),
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic (seeded SMPL-topology humanoid, poses, ZJU-like cameras; LPIPS trunk = seeded random VGG16, "
+                    "no ImageNet weights offline)",
+            "config": {"workload": "ZJU-MoCap-377-like train step (LBS+face frame+splat raster+L1/LPIPS losses+backward+Adam), "
+                                   "512x512, 30k Gaussians (BASELINE configs[2])",
+                       "img": args.img, "n_gaussians": F, "n_vertices": V, "frames_per_step_per_gpu": B,
+                       "global_batch": B * world, "parallelism": f"frame-sharded dp{world}, 1 NCCL all-reduce of the flat grad arena/step",
+                       "lpips": "tf32" if args.lpips_tf32 else "fp32", "raster_overflow": overflow,
+                       "l2": "per-step working set (LPIPS activations, ~%d MB) exceeds the 126 MB L2; batches cycle through a pool"
+                             % int(B * 2 * 32e6 * 4 / 1e6)},
+            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / K, "h2d_bytes_per_step": int(tr.h2d_bytes),
+                    "d2h_bytes_per_step": 4},
+            "gpu_launches": launches_timed, "clocks": clocks, "roofline": roofline, "kernels": kernels,
+        }
+        if not args.no_cpu_baseline and world == 1:
+            line["cpu_baseline"] = cpu_path(args, n_frames=args.cpu_frames, gpu_trainer=tr)
+        print(json.dumps(line))
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
+    return line
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm (oracle)
+def cpu_path(args, n_frames, gpu_trainer=None, steps=1, warmup=0):
+    """The reference's path on the host cores: its PyTorch ops restated (oracle/geometry.py, losses.py) + the C
+    restatement of the un-vendored CUDA rasterizer (oracle/raster_oracle.c, OpenMP), forward + backward, n_frames frames
+    per step, batch 1 per frame like the reference.  The ONLY place bench.py touches oracle/."""
+    from gomavatar_b200 import synthetic as S
+    from oracle import camera as Cam, geometry as G, losses as OL, raster as R
+    H = W = args.img
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    t = torch.from_numpy
+    scene = S.make_humanoid(args.faces, seed=0)
+    pr = S.make_params(scene, seed=1)
+    fr = S.make_frames(scene, max(n_frames, 1), img_size=(W, H), seed=100)
+    heads = np.load(os.path.join(ROOT, "tests", "golden", "golden_lpips.npz"))
+    lp = OL.LPIPSVGG(OL.seeded_random_trunk_state(0), [heads[f"lin{k}"] for k in range(5)])
+    rng = np.random.default_rng(3)
+    tgt = t(rng.random((H, W, 3)).astype(np.float32))[None]
+    tgt_m = t((rng.random((H, W)) > 0.5).astype(np.float32))[None]
+    psnr = None
+
+    def one_frame(b):
+        nonlocal psnr
+        v = t(pr["vertices"]).requires_grad_(True)
+        so3, sc = t(pr["so3"]).requires_grad_(True), t(pr["scale"]).requires_grad_(True)
+        app = t(pr["appearance"]).requires_grad_(True)
+        _, xyz, cov = G.pose_geometry(v, t(scene.faces), t(scene.lbs_weights), so3, sc, t(fr["cnl_gtfms"][b]),
+                                      t(fr["dst_Rs"][b]), t(fr["dst_Ts"][b]))
+        cov6 = G.pack_cov6(cov)
+        st = Cam.raster_settings_from_KE(fr["K"][b], fr["E"][b], (W, H))
+        feat = np.concatenate([app.detach().numpy().T, np.ones((scene.n_faces, 1), np.float32)], 1)
+        f = R.forward(xyz.detach().numpy(), cov6.detach().numpy(), feat, np.ones(scene.n_faces, np.float32), st.viewmatrix,
+                      st.projmatrix, st.tanfovx, st.tanfovy, np.zeros(4, np.float32), H, W)
+        img = t(f["color"].transpose(1, 2, 0).copy())[None].requires_grad_(True)
+        u = OL.unpack(img[..., :3], img[..., 3], t(fr["bgcolor"][b:b + 1]))
+        l_rgb, l_mask = OL.l1_losses(u, img[..., 3], tgt, tgt_m)
+        loss = l_rgb + 5.0 * l_mask + OL.lpips_loss(lp, u, tgt)
+        loss.backward()
+        g = R.backward(f, img.grad[0].permute(2, 0, 1).contiguous().numpy())
+        ((xyz * t(g["means3D"])).sum() + (cov6 * t(g["cov6"])).sum()).backward()
+        if gpu_trainer is not None and psnr is None:      # PSNR of the B200 render against the oracle render, same frame
+            m = gpu_trainer.model
+            with torch.no_grad():
+                d = {k: t(fr[k][b:b + 1]).to(gpu_trainer.dev) for k in ("K", "E", "cnl_gtfms", "dst_Rs", "dst_Ts")}
+                rgb, mask, _ = m(d["K"], d["E"], d["cnl_gtfms"], d["dst_Rs"], d["dst_Ts"])
+            mse = float(((rgb[0].cpu() - img.detach()[0, ..., :3]) ** 2).mean())
+            psnr = float("inf") if mse == 0 else -10.0 * np.log10(mse)
+        return float(loss)
+
+    for _ in range(warmup):
+        one_frame(0)
+    t0 = time.perf_counter()
+    for s in range(steps):
+        for b in range(n_frames):
+            one_frame(b)
+    dt = time.perf_counter() - t0
+    out = {"value": steps * n_frames / dt, "unit": UNIT, "cores": cores, "kind": "port",
+           "sample": f"{steps} step(s) x {n_frames} frame(s) of the same workload (512x512, {scene.n_faces} Gaussians, fwd+loss+bwd, "
+                     f"batch 1 per frame like the reference); oracle port: torch-CPU ops + OpenMP C rasterizer ({R.num_threads()} threads)",
+           "seconds": dt}
+    if psnr is not None:
+        out["psnr_b200_vs_oracle_db"] = psnr if np.isfinite(psnr) else 999.0
+    return out
+
+
+def run_reference(args):
+    """`--impl reference`: the reference has no CPU-runnable implementation of this path (its rasterizer is a CUDA-only
+    third-party package, pytorch3d is absent), so the oracle port stands in (kind = "port")."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return None
+    K, W_ = args.steps, args.warmup
+    t0 = time.perf_counter()
+    res = cpu_path(args, n_frames=1, steps=K, warmup=min(W_, 1))
+    ms_per_step = 1e3 * res["seconds"] / K
+    line = {"impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": K,
+            "warmup": min(W_, 1), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic (same generator and seeds as the B200 arm)",
+            "config": {"workload": "same train step on the host cores, 1 frame per step (bounded sample of the B200 arm's batch)",
+                       "img": args.img, "n_gaussians": args.faces, "frames_per_step_per_gpu": 1},
+            "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "wall_s": time.perf_counter() - t0}
+    print(json.dumps(line))
+    return line
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)

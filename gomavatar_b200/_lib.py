@@ -90,12 +90,22 @@ class GomFaceBwdArgs(ctypes.Structure):
                 ("dL_dso3", c_void_p), ("dL_dscale", c_void_p)]
 
 
+class GomPhotoArgs(ctypes.Structure):
+    _fields_ = [("n_frames", c_int32), ("height", c_int32), ("width", c_int32), ("_pad", c_int32),
+                ("rgb", c_void_p), ("rgb_pixel_stride", c_int64), ("mask", c_void_p), ("mask_pixel_stride", c_int64),
+                ("bgcolor", c_void_p), ("gt_rgb", c_void_p), ("gt_mask", c_void_p), ("unpacked", c_void_p),
+                ("loss_sums", c_void_p), ("dL_dunpacked", c_void_p), ("dL_dlosses", c_void_p),
+                ("dL_drgb", c_void_p), ("dL_drgb_pixel_stride", c_int64),
+                ("dL_dmask", c_void_p), ("dL_dmask_pixel_stride", c_int64)]
+
+
 # every symbol include/gom_b200.h declares (tests check the .so exports all of them)
 EXPORTS = [
-    "gom_abi_version", "gom_last_error", "gom_camera_from_KE", "gom_raster_forward", "gom_raster_backward",
+    "gom_abi_version", "gom_last_error", "gom_launch_count", "gom_profile_enable", "gom_profile_num_slots",
+    "gom_profile_slot_name", "gom_profile_read", "gom_camera_from_KE", "gom_raster_forward", "gom_raster_backward",
     "gom_joint_transforms_forward", "gom_joint_transforms_backward", "gom_lbs_forward", "gom_lbs_backward",
-    "gom_face_gaussians_forward", "gom_face_gaussians_backward",
-    "gom_sizeof_camera_args", "gom_sizeof_raster_fwd_args", "gom_sizeof_raster_bwd_args",
+    "gom_face_gaussians_forward", "gom_face_gaussians_backward", "gom_photometric_forward", "gom_photometric_backward",
+    "gom_sizeof_photo_args", "gom_sizeof_camera_args", "gom_sizeof_raster_fwd_args", "gom_sizeof_raster_bwd_args",
     "gom_sizeof_joint_fwd_args", "gom_sizeof_joint_bwd_args", "gom_sizeof_lbs_fwd_args", "gom_sizeof_lbs_bwd_args",
     "gom_sizeof_face_fwd_args", "gom_sizeof_face_bwd_args",
 ]
@@ -103,11 +113,11 @@ EXPORTS = [
 _STRUCTS = {
     "camera": GomCameraArgs, "raster_fwd": GomRasterFwdArgs, "raster_bwd": GomRasterBwdArgs,
     "joint_fwd": GomJointFwdArgs, "joint_bwd": GomJointBwdArgs, "lbs_fwd": GomLbsFwdArgs, "lbs_bwd": GomLbsBwdArgs,
-    "face_fwd": GomFaceFwdArgs, "face_bwd": GomFaceBwdArgs,
+    "face_fwd": GomFaceFwdArgs, "face_bwd": GomFaceBwdArgs, "photo": GomPhotoArgs,
 }
 _ENTRY_POINTS = ["gom_camera_from_KE", "gom_raster_forward", "gom_raster_backward", "gom_joint_transforms_forward",
                  "gom_joint_transforms_backward", "gom_lbs_forward", "gom_lbs_backward", "gom_face_gaussians_forward",
-                 "gom_face_gaussians_backward"]
+                 "gom_face_gaussians_backward", "gom_photometric_forward", "gom_photometric_backward"]
 
 _lib = None
 
@@ -138,8 +148,31 @@ def lib():
         f = getattr(L, name)
         f.restype = c_int
         f.argtypes = [c_void_p, c_void_p]
+    L.gom_launch_count.restype = ctypes.c_longlong
+    L.gom_profile_slot_name.restype = c_char_p
+    L.gom_profile_read.argtypes = [c_int, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(c_int)]
     _lib = L
     return L
+
+
+def launch_count():
+    return int(lib().gom_launch_count())
+
+
+def profile_enable(on=True):
+    lib().gom_profile_enable(1 if on else 0)
+
+
+def profile_read():
+    """{kernel name: (total_ms, launches)} for every kernel timed since profile_enable(True)."""
+    L = lib()
+    out = {}
+    for s in range(L.gom_profile_num_slots()):
+        ms, n = ctypes.c_double(0), c_int(0)
+        check(L.gom_profile_read(s, ctypes.byref(ms), ctypes.byref(n)), "gom_profile_read")
+        if n.value:
+            out[L.gom_profile_slot_name(s).decode()] = (ms.value, n.value)
+    return out
 
 
 def check(rc, what):

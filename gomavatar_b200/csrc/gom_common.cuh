@@ -28,12 +28,24 @@ void gom_set_error(const char *fmt, ...);
 
 #define GOM_LAUNCH_CHECK()                                                          \
     do {                                                                            \
+        gom_count_launch();                                                         \
         cudaError_t e_ = cudaGetLastError();                                        \
         if (e_ != cudaSuccess) {                                                    \
             gom_set_error("%s: kernel launch failed: %s", __func__, cudaGetErrorString(e_)); \
             return GOM_ERR_CUDA;                                                    \
         }                                                                           \
     } while (0)
+
+// ---------------------------------------------------------------------------- launch counter + per-kernel timers
+// gom_launch_count(): kernels this library has launched in this process (bench.py's `gpu_launches` claim).
+// gom_profile_*(): optional CUDA-event timers around selected kernels, on the launching stream.
+enum GomProfSlot { GOM_PROF_PREPROCESS = 0, GOM_PROF_SCAN, GOM_PROF_EMIT, GOM_PROF_BLEND_FWD, GOM_PROF_BLEND_BWD,
+                   GOM_PROF_PREPROCESS_BWD, GOM_PROF_JOINT_FWD, GOM_PROF_JOINT_BWD, GOM_PROF_LBS_FWD, GOM_PROF_LBS_BWD,
+                   GOM_PROF_FACE_FWD, GOM_PROF_FACE_BWD, GOM_PROF_PHOTO_FWD, GOM_PROF_PHOTO_BWD, GOM_PROF_CAMERA,
+                   GOM_PROF_NSLOTS };
+void gom_count_launch(void);
+void gom_prof_begin(int slot, cudaStream_t stream);
+void gom_prof_end(int slot, cudaStream_t stream);
 
 static inline int gom_div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 

@@ -14,6 +14,56 @@ void gom_set_error(const char *fmt, ...) {
 }
 
 extern "C" const char *gom_last_error(void) { return g_err; }
+
+// ------------------------------------------------------------------------------------ launch counter / kernel timers
+#include <atomic>
+#include <vector>
+static std::atomic<long long> g_launches{0};
+void gom_count_launch(void) { g_launches.fetch_add(1, std::memory_order_relaxed); }
+extern "C" long long gom_launch_count(void) { return g_launches.load(); }
+
+struct ProfSlot { std::vector<cudaEvent_t> ev; size_t used = 0; };
+static bool g_prof_on = false;
+static ProfSlot g_prof[GOM_PROF_NSLOTS];
+static const char *kProfNames[GOM_PROF_NSLOTS] = {"preprocess", "scan_tiles", "emit", "sort_blend_fwd", "blend_bwd",
+    "preprocess_bwd", "joint_fwd", "joint_bwd", "lbs_fwd", "lbs_bwd", "face_fwd", "face_bwd", "photo_fwd", "photo_bwd",
+    "camera"};
+
+static cudaEvent_t prof_next(int slot) {
+    ProfSlot &s = g_prof[slot];
+    if (s.used == s.ev.size()) {
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        s.ev.push_back(e);
+    }
+    return s.ev[s.used++];
+}
+void gom_prof_begin(int slot, cudaStream_t stream) { if (g_prof_on) cudaEventRecord(prof_next(slot), stream); }
+void gom_prof_end(int slot, cudaStream_t stream) { if (g_prof_on) cudaEventRecord(prof_next(slot), stream); }
+
+extern "C" void gom_profile_enable(int on) {
+    g_prof_on = on != 0;
+    if (on) for (auto &s : g_prof) s.used = 0;
+}
+extern "C" int gom_profile_num_slots(void) { return GOM_PROF_NSLOTS; }
+extern "C" const char *gom_profile_slot_name(int slot) { return (slot >= 0 && slot < GOM_PROF_NSLOTS) ? kProfNames[slot] : ""; }
+// Sum of elapsed ms and number of launches recorded for a slot since gom_profile_enable(1).  Synchronises the events.
+extern "C" int gom_profile_read(int slot, double *total_ms, int *count) {
+    if (slot < 0 || slot >= GOM_PROF_NSLOTS || !total_ms || !count) return GOM_ERR_INVALID;
+    ProfSlot &s = g_prof[slot];
+    double tot = 0.0;
+    int n = 0;
+    for (size_t i = 0; i + 1 < s.used; i += 2) {
+        float ms = 0.f;
+        if (cudaEventSynchronize(s.ev[i + 1]) != cudaSuccess) return GOM_ERR_CUDA;
+        if (cudaEventElapsedTime(&ms, s.ev[i], s.ev[i + 1]) != cudaSuccess) return GOM_ERR_CUDA;
+        tot += ms;
+        n++;
+    }
+    *total_ms = tot;
+    *count = n;
+    return GOM_OK;
+}
 extern "C" int gom_abi_version(void) { return GOM_ABI_VERSION; }
 extern "C" size_t gom_sizeof_camera_args(void) { return sizeof(GomCameraArgs); }
 extern "C" size_t gom_sizeof_raster_fwd_args(void) { return sizeof(GomRasterFwdArgs); }
@@ -24,6 +74,7 @@ extern "C" size_t gom_sizeof_lbs_fwd_args(void) { return sizeof(GomLbsFwdArgs); 
 extern "C" size_t gom_sizeof_lbs_bwd_args(void) { return sizeof(GomLbsBwdArgs); }
 extern "C" size_t gom_sizeof_face_fwd_args(void) { return sizeof(GomFaceFwdArgs); }
 extern "C" size_t gom_sizeof_face_bwd_args(void) { return sizeof(GomFaceBwdArgs); }
+extern "C" size_t gom_sizeof_photo_args(void) { return sizeof(GomPhotoArgs); }
 
 // Host math of reference models/modules/renderer/gaussian.py:30-47,60-61 moved on device: the four .item() syncs and
 // the host-built K_ndc + H2D copy disappear.  Scalars are formed in fp64 from the fp32 K entries and rounded to fp32

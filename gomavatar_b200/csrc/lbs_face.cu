@@ -417,8 +417,10 @@ extern "C" int gom_joint_transforms_forward(const GomJointFwdArgs *p, gom_stream
     JointDev a{};
     a.B = p->n_frames; a.J = p->n_joints; a.parents = p->parents; a.cnl = p->cnl_gtfms; a.dst_Rs = p->dst_Rs;
     a.dst_Ts = p->dst_Ts; a.out_Rs = p->global_Rs; a.out_Ts = p->global_Ts; a.chain_G = p->chain_G; a.cnl_inv = p->cnl_inv;
+    gom_prof_begin(GOM_PROF_JOINT_FWD, (cudaStream_t)stream);
     k_joint_fwd<<<a.B, kMaxJ, 0, (cudaStream_t)stream>>>(a);
     GOM_LAUNCH_CHECK();
+    gom_prof_end(GOM_PROF_JOINT_FWD, (cudaStream_t)stream);
     return GOM_OK;
 }
 
@@ -431,8 +433,10 @@ extern "C" int gom_joint_transforms_backward(const GomJointBwdArgs *p, gom_strea
     a.B = p->n_frames; a.J = p->n_joints; a.parents = p->parents; a.dst_Rs = p->dst_Rs; a.dst_Ts = p->dst_Ts;
     a.chain_G = const_cast<float *>(p->chain_G); a.cnl_inv = const_cast<float *>(p->cnl_inv);
     a.dRs = p->dL_dglobal_Rs; a.dTs = p->dL_dglobal_Ts; a.d_dst_Rs = p->dL_ddst_Rs; a.d_dst_Ts = p->dL_ddst_Ts;
+    gom_prof_begin(GOM_PROF_JOINT_BWD, (cudaStream_t)stream);
     k_joint_bwd<<<a.B, kMaxJ, 0, (cudaStream_t)stream>>>(a);
     GOM_LAUNCH_CHECK();
+    gom_prof_end(GOM_PROF_JOINT_BWD, (cudaStream_t)stream);
     return GOM_OK;
 }
 
@@ -448,9 +452,11 @@ static int lbs_common(LbsDev &a, bool bwd, cudaStream_t stream) {
         }
     }
     dim3 grid(gom_div_up(a.V, kTile), gom_div_up(a.B, kFB));
+    gom_prof_begin(bwd ? GOM_PROF_LBS_BWD : GOM_PROF_LBS_FWD, stream);
     if (bwd) k_lbs_bwd<<<grid, kThreads, smem, stream>>>(a);
     else k_lbs_fwd<<<grid, kThreads, smem, stream>>>(a);
     GOM_LAUNCH_CHECK();
+    gom_prof_end(bwd ? GOM_PROF_LBS_BWD : GOM_PROF_LBS_FWD, stream);
     return GOM_OK;
 }
 
@@ -494,8 +500,10 @@ extern "C" int gom_face_gaussians_forward(const GomFaceFwdArgs *p, gom_stream_t 
     a.B = p->n_frames; a.F = p->n_faces; a.V = p->n_verts; a.faces_int64 = p->faces_int64; a.sigma = p->sigma;
     a.verts = p->verts; a.faces = p->faces; a.so3 = p->so3; a.scale = p->scale; a.means3D = p->means3D; a.cov3D = p->cov3D;
     dim3 grid(gom_div_up(a.F, kThreads), a.B);
+    gom_prof_begin(GOM_PROF_FACE_FWD, (cudaStream_t)stream);
     k_face_fwd<<<grid, kThreads, 0, (cudaStream_t)stream>>>(a);
     GOM_LAUNCH_CHECK();
+    gom_prof_end(GOM_PROF_FACE_FWD, (cudaStream_t)stream);
     return GOM_OK;
 }
 
@@ -514,7 +522,9 @@ extern "C" int gom_face_gaussians_backward(const GomFaceBwdArgs *p, gom_stream_t
     GOM_CUDA(cudaMemsetAsync(a.dso3, 0, sizeof(float) * 3 * (size_t)a.F, stream));
     GOM_CUDA(cudaMemsetAsync(a.dscale, 0, sizeof(float) * 3 * (size_t)a.F, stream));
     dim3 grid(gom_div_up(a.F, kThreads), a.B);
+    gom_prof_begin(GOM_PROF_FACE_BWD, (cudaStream_t)stream);
     k_face_bwd<<<grid, kThreads, 0, (cudaStream_t)stream>>>(a);
     GOM_LAUNCH_CHECK();
+    gom_prof_end(GOM_PROF_FACE_BWD, (cudaStream_t)stream);
     return GOM_OK;
 }

@@ -280,12 +280,16 @@ extern "C" int gom_raster_backward(const GomRasterBwdArgs *p, gom_stream_t strea
         GOM_CUDA(cudaMemsetAsync(a.dL_dcolors, 0, sizeof(float) * ncol, stream));
         if (a.dL_dopacity) GOM_CUDA(cudaMemsetAsync(a.dL_dopacity, 0, sizeof(float) * BP, stream));
         dim3 bgrid(a.gx, a.gy, a.B), bblock(16, 16);
+        gom_prof_begin(GOM_PROF_BLEND_BWD, stream);
         if (a.C == 3) k_blend_bwd<3><<<bgrid, bblock, 0, stream>>>(a);
         else k_blend_bwd<4><<<bgrid, bblock, 0, stream>>>(a);
         GOM_LAUNCH_CHECK();
+        gom_prof_end(GOM_PROF_BLEND_BWD, stream);
         dim3 grid(gom_div_up(a.P, kThreads), a.B);
+        gom_prof_begin(GOM_PROF_PREPROCESS_BWD, stream);
         k_preprocess_bwd<<<grid, kThreads, 0, stream>>>(a);
         GOM_LAUNCH_CHECK();
+        gom_prof_end(GOM_PROF_PREPROCESS_BWD, stream);
     }
     return GOM_OK;
 }

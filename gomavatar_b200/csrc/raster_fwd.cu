@@ -324,19 +324,27 @@ extern "C" int gom_raster_forward(const GomRasterFwdArgs *p, gom_stream_t stream
     GOM_CUDA(cudaMemsetAsync(a.tile_count, 0, sizeof(uint32_t) * (size_t)a.B * a.T, stream));
     if (a.P > 0) {
         dim3 grid(gom_div_up(a.P, kThreads), a.B);
+        gom_prof_begin(GOM_PROF_PREPROCESS, stream);
         k_preprocess<<<grid, kThreads, 0, stream>>>(a);
         GOM_LAUNCH_CHECK();
+        gom_prof_end(GOM_PROF_PREPROCESS, stream);
     }
+    gom_prof_begin(GOM_PROF_SCAN, stream);
     k_scan_tiles<<<a.B, 1024, 0, stream>>>(a);
     GOM_LAUNCH_CHECK();
+    gom_prof_end(GOM_PROF_SCAN, stream);
     if (a.P > 0) {
         dim3 grid(gom_div_up(a.P, kThreads), a.B);
+        gom_prof_begin(GOM_PROF_EMIT, stream);
         k_emit<<<grid, kThreads, 0, stream>>>(a);
         GOM_LAUNCH_CHECK();
+        gom_prof_end(GOM_PROF_EMIT, stream);
     }
     dim3 bgrid(a.gx, a.gy, a.B), bblock(16, 16);
+    gom_prof_begin(GOM_PROF_BLEND_FWD, stream);
     if (a.C == 3) k_sort_blend<3><<<bgrid, bblock, 0, stream>>>(a);
     else k_sort_blend<4><<<bgrid, bblock, 0, stream>>>(a);
     GOM_LAUNCH_CHECK();
+    gom_prof_end(GOM_PROF_BLEND_FWD, stream);
     return GOM_OK;
 }

@@ -48,6 +48,14 @@ typedef void *gom_stream_t;      /* cudaStream_t */
 int gom_abi_version(void);
 const char *gom_last_error(void);
 
+/* Instrumentation (used by bench.py): number of kernels this library has launched in this process, and optional
+ * CUDA-event timers recorded on the launching stream around each kernel (slot = kernel, see gom_profile_slot_name). */
+long long gom_launch_count(void);
+void gom_profile_enable(int on);                 /* on = 1 also clears previously recorded samples */
+int gom_profile_num_slots(void);
+const char *gom_profile_slot_name(int slot);
+int gom_profile_read(int slot, double *total_ms, int *count);   /* waits for the recorded events */
+
 /* --------------------------------------------------------------------------------------------------------------
  * Camera setup.  Replaces the host math + 4 .item() syncs + H2D of reference gaussian.py:30-47,60-61:
  * K [B,3,3], E [B,4,4]  ->  viewmatrix = E^T, projmatrix = E^T K_ndc^T  (row-major [B,16] each, i.e. exactly the
@@ -233,6 +241,32 @@ typedef struct {
 } GomFaceBwdArgs;
 int gom_face_gaussians_backward(const GomFaceBwdArgs *a, gom_stream_t stream);
 
+/* --------------------------------------------------------------------------------------------------------------
+ * Photometric losses.  Replaces reference train.py:53-55 (`unpack`: rgb*mask + bg*(1-mask), per-frame background)
+ * and train.py:101-111 (mean |rgb - gt|, mean |mask - gt_mask|), forward and backward, one pass each way.
+ * rgb / mask may be views into one interleaved [B,H,W,4] render (pixel strides 4 / 4) or separate tensors (3 / 1).
+ * forward : unpacked [B,H,W,3]; loss_sums[0] = sum |unpacked - gt_rgb|, loss_sums[1] = sum |mask - gt_mask| (nullable)
+ * backward: dL_drgb, dL_dmask from dL_dunpacked (nullable, e.g. LPIPS' gradient) and dL_dlosses[2] (device; gradient
+ *           of the two MEAN losses, i.e. the loss coefficients times the upstream scalar).
+ * bgcolor == NULL skips the compositing (unpacked = rgb), as the reference does when random_bgcolor is off.
+ */
+typedef struct {
+    int32_t n_frames, height, width, _pad;
+    const float *rgb;   int64_t rgb_pixel_stride;
+    const float *mask;  int64_t mask_pixel_stride;
+    const float *bgcolor;        /* [B,3] nullable */
+    const float *gt_rgb;         /* [B,H,W,3] nullable */
+    const float *gt_mask;        /* [B,H,W]   nullable */
+    float *unpacked;             /* [B,H,W,3] (forward) */
+    float *loss_sums;            /* [2]       (forward, nullable) */
+    const float *dL_dunpacked;   /* [B,H,W,3] (backward, nullable) */
+    const float *dL_dlosses;     /* [2]       (backward, nullable) */
+    float *dL_drgb;     int64_t dL_drgb_pixel_stride;
+    float *dL_dmask;    int64_t dL_dmask_pixel_stride;
+} GomPhotoArgs;
+int gom_photometric_forward(const GomPhotoArgs *a, gom_stream_t stream);
+int gom_photometric_backward(const GomPhotoArgs *a, gom_stream_t stream);
+
 /* struct sizes, so that a foreign-language binding can assert its mirror of the structs */
 size_t gom_sizeof_camera_args(void);
 size_t gom_sizeof_raster_fwd_args(void);
@@ -243,6 +277,7 @@ size_t gom_sizeof_lbs_fwd_args(void);
 size_t gom_sizeof_lbs_bwd_args(void);
 size_t gom_sizeof_face_fwd_args(void);
 size_t gom_sizeof_face_bwd_args(void);
+size_t gom_sizeof_photo_args(void);
 
 #ifdef __cplusplus
 }
