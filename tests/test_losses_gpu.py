@@ -38,7 +38,7 @@ def test_photometric_l1_forward_backward(layout, with_bg):
     np.testing.assert_allclose(float(kl_rgb), float(l_rgb), rtol=1e-5)
     np.testing.assert_allclose(float(kl_mask), float(l_mask), rtol=1e-5)
     ((ku * t(g_u).to(DEV)).sum() + 1.0 * kl_rgb + 5.0 * kl_mask).backward()
-    np.testing.assert_allclose(k.grad.cpu().numpy(), o.grad.numpy(), rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(k.grad.cpu().numpy(), o.grad.numpy(), rtol=1e-5, atol=2e-6)   # d/dmask sums mixed-sign terms
     if with_bg:
         np.testing.assert_allclose(unpack(rgb_in, mask_in, t(bg).to(DEV)).detach().cpu().numpy(), u.detach().numpy(), atol=1e-7)
 
@@ -50,10 +50,14 @@ def test_lpips_matches_reference_golden(golden_dir):
     s = float(sum(v.double().abs().sum() for v in trunk.values()))
     if abs(s - float(g["trunk_abs_sum"])) > 1e-6 * s:
         pytest.skip("torchvision's seeded VGG16 init differs from the one the golden was made with")
-    net = LPIPS(trunk, [g[f"lin{k}"] for k in range(5)]).to(DEV)
-    x0 = t(g["x0"]).to(DEV).requires_grad_(True)
-    val = net(2 * x0 - 1, 2 * t(g["x1"]).to(DEV) - 1)
-    np.testing.assert_allclose(val.detach().cpu().numpy(), g["value"], rtol=1e-4)
-    val.sum().backward()
     ref = g["grad_x0"]
-    assert np.abs(x0.grad.cpu().numpy() - ref).max() <= 1e-3 * np.abs(ref).max()
+    for precision, tol_val, tol_grad in (("fp32", 1e-4, 1e-3), ("tf32", 2e-2, None)):
+        net = LPIPS(trunk, [g[f"lin{k}"] for k in range(5)], conv_precision=precision).to(DEV)
+        x0 = t(g["x0"]).to(DEV).requires_grad_(True)
+        val = net(2 * x0 - 1, 2 * t(g["x1"]).to(DEV) - 1)
+        np.testing.assert_allclose(val.detach().cpu().numpy(), g["value"], rtol=tol_val)
+        val.sum().backward()
+        rel = np.abs(x0.grad.cpu().numpy() - ref).max() / np.abs(ref).max()
+        print(f"LPIPS {precision}: value rel err {np.abs(val.detach().cpu().numpy() - g['value']).max() / g['value'].max():.2e}, grad rel err {rel:.2e}")
+        if tol_grad is not None:
+            assert rel <= tol_grad, (precision, rel)
