@@ -41,6 +41,9 @@ def parse():
     ap.add_argument("--pool-steps", type=int, default=4, help="distinct batches cycled through")
     ap.add_argument("--lpips-precision", default="tf32", choices=["tf32", "fp32", "bf16"],
                     help="cuDNN conv precision of the LPIPS VGG trunk; tf32 = torch/cuDNN default = the reference's stock path")
+    ap.add_argument("--lpips-torch", action="store_true", help="A/B: plain torch LPIPS glue instead of csrc/lpips.cu")
+    ap.add_argument("--lpips-epilogue", default="cudnn", choices=["kernel", "cudnn"],
+                    help="bias+ReLU after each VGG convolution: own kernel, or cuDNN's fused conv-bias-activation")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-frames", type=int, default=2, help="frames in the bounded CPU-baseline sample")
     return ap.parse_args()
@@ -91,6 +94,30 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed `ncu --set full`
+# capture of this same command (profiles/); filled in by hand after each capture, None = not captured yet.
+NCU_TRAFFIC_BYTES = {}
+
+_VGG_LEVELS = ((64, 2), (128, 2), (256, 3), (512, 3), (512, 3))      # (channels, convolutions) per VGG16 block
+
+
+def lpips_alg_bytes_per_frame(H, W):
+    """Algorithmic HBM bytes per FRAME (= one prediction + one target image) of the hand-written LPIPS kernels, summed
+    over the layers each kernel serves (csrc/lpips.cu; formulas in DESIGN.md §4).  fp32 NHWC."""
+    out = {"lpips_input": (2 * 2 + 2) * 3 * H * W * 4.0, "bias_relu": 0.0, "relu_bwd": 0.0, "lpips_tap_fwd": 0.0,
+           "lpips_tap_bwd": 0.0}
+    h, w, cin = H, W, 3
+    for level, (C, n_conv) in enumerate(_VGG_LEVELS):
+        px = h * w
+        out["bias_relu"] += n_conv * 2 * (2 * px * C * 4.0)              # read + write, pred and gt
+        out["relu_bwd"] += (n_conv - 1) * 3 * (px * C * 4.0)             # act read, grad read + write (pred half)
+        pooled = (h // 2) * (w // 2) * C * 4.0 if level < 4 else 0.0
+        out["lpips_tap_fwd"] += 2 * px * C * 4.0 + 2 * pooled
+        out["lpips_tap_bwd"] += 2 * px * C * 4.0 + pooled + px * C * 4.0
+        h, w = h // 2, w // 2
+    return out
+
+
 # ------------------------------------------------------------------------------------------------ B200 arm
 class Trainer:
     def __init__(self, args, rank, world, device):
@@ -111,7 +138,8 @@ class Trainer:
             self.model.appearance_module.appearance.copy_(torch.from_numpy(pr["appearance"]))
         self.model.train()
         heads = np.load(os.path.join(ROOT, "tests", "golden", "golden_lpips.npz"))
-        self.lpips = LPIPS(seeded_random_trunk(0), [heads[f"lin{k}"] for k in range(5)], conv_precision=args.lpips_precision).to(device)
+        self.lpips = LPIPS(seeded_random_trunk(0), [heads[f"lin{k}"] for k in range(5)], conv_precision=args.lpips_precision,
+                           fused=not args.lpips_torch, conv_epilogue=args.lpips_epilogue).to(device)
         # pool of frames: different poses / cameras / backgrounds per rank
         n_pool = self.B * args.pool_steps
         fr = S.make_frames(scene, n_pool, img_size=(W, H), seed=100 + rank)
@@ -229,11 +257,12 @@ def run_b200(args):
     n_dup = float(aux["tile_offset"][:, T].to(torch.int64).bitwise_and(0xFFFFFFFF).float().mean().item())
     overflow = int(aux["status"].max().item())
     HW, F, V = args.img * args.img, tr.scene.n_faces, tr.scene.n_vertices
-    alg_bytes_per_frame = {      # SURVEY.md §8d algorithmic bytes per frame
+    alg_bytes_per_frame = {      # SURVEY.md §8d algorithmic bytes per frame (DESIGN.md §4 lists every formula)
         "sort_blend_fwd": 40 * n_dup + 24 * HW, "blend_bwd": 80 * n_dup + 44 * HW, "preprocess": 76 * F,
         "preprocess_bwd": 76 * F + 36 * F, "emit": 12 * n_dup + 20 * F, "scan_tiles": 12 * T,
         "lbs_fwd": 120 * V, "lbs_bwd": 120 * V, "face_fwd": 72 * F, "face_bwd": 72 * F + 36 * F,
         "photo_fwd": 44 * HW, "photo_bwd": 60 * HW}
+    alg_bytes_per_frame.update(lpips_alg_bytes_per_frame(args.img, args.img))
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -242,18 +271,24 @@ def run_b200(args):
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "6650 GB/s (of fallback)"
     kernels = {}
+    n_timed_steps = K + max(W_, 3)
     for name, (tot_ms, n) in prof.items():
-        per_launch_ms = tot_ms / max(n, 1)
-        byt = alg_bytes_per_frame.get(name, 0.0) * B
-        kernels[name] = {"ms_per_launch": per_launch_ms, "launches": n, "share_of_step": tot_ms / (K + max(W_, 3)) / (ms / K),
-                         "alg_bytes_per_launch": byt, "gbs": byt / (per_launch_ms * 1e-3) / 1e9 if per_launch_ms > 0 else None}
-    dom = max(kernels, key=lambda k: kernels[k]["ms_per_launch"]) if kernels else None
+        ms_step = tot_ms / n_timed_steps                     # all launches of this kernel in one step
+        byt_step = alg_bytes_per_frame.get(name, 0.0) * B    # algorithmic bytes of all those launches
+        per_step = n / n_timed_steps
+        kernels[name] = {"ms_per_step": ms_step, "launches_per_step": per_step, "ms_per_launch": tot_ms / max(n, 1),
+                         "share_of_step": ms_step / (ms / K), "alg_bytes_per_launch": byt_step / max(per_step, 1e-9),
+                         "gbs": byt_step / (ms_step * 1e-3) / 1e9 if ms_step > 0 else None}
+    dom = max(kernels, key=lambda k: kernels[k]["ms_per_step"]) if kernels else None
     roofline = None
     if dom:
         k = kernels[dom]
         roofline = {"kernel": dom, "bound": "hbm", "achieved": k["gbs"], "peak": peak, "unit": "GB/s", "frac": k["gbs"] / peak,
-                    "traffic": None, "peak_source": peak_src, "ms_per_launch": k["ms_per_launch"],
-                    "alg_bytes_per_launch": k["alg_bytes_per_launch"], "n_dup_per_frame": n_dup}
+                    "traffic": NCU_TRAFFIC_BYTES.get(dom), "peak_source": peak_src, "ms_per_launch": k["ms_per_launch"],
+                    "alg_bytes_per_launch": k["alg_bytes_per_launch"], "launches_per_step": k["launches_per_step"],
+                    "n_dup_per_frame": n_dup,
+                    "blend_pass": {kk: {"gbs": kernels[kk]["gbs"], "frac": kernels[kk]["gbs"] / peak, "ms_per_launch": kernels[kk]["ms_per_launch"]}
+                                   for kk in ("sort_blend_fwd", "blend_bwd") if kk in kernels}}
 
     line = None
     if rank == 0:

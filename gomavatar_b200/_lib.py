@@ -99,6 +99,25 @@ class GomPhotoArgs(ctypes.Structure):
                 ("dL_dmask", c_void_p), ("dL_dmask_pixel_stride", c_int64)]
 
 
+class GomLpipsInputArgs(ctypes.Structure):
+    _fields_ = [("n_frames", c_int32), ("height", c_int32), ("width", c_int32), ("from_unit_range", c_int32),
+                ("pred", c_void_p), ("gt", c_void_p), ("out", c_void_p), ("dL_dout", c_void_p), ("dL_dpred", c_void_p)]
+
+
+class GomBiasReluArgs(ctypes.Structure):
+    _fields_ = [("n_pixels", c_int64), ("channels", c_int32), ("_pad", c_int32), ("x", c_void_p), ("bias", c_void_p)]
+
+
+class GomReluBwdArgs(ctypes.Structure):
+    _fields_ = [("n", c_int64), ("act", c_void_p), ("grad", c_void_p)]
+
+
+class GomLpipsTapArgs(ctypes.Structure):
+    _fields_ = [("n_frames", c_int32), ("height", c_int32), ("width", c_int32), ("channels", c_int32),
+                ("pool", c_int32), ("_pad", c_int32), ("feats", c_void_p), ("lin", c_void_p), ("layer_sums", c_void_p),
+                ("pooled", c_void_p), ("dL_dval", c_void_p), ("dL_dpooled", c_void_p), ("dL_dpre", c_void_p)]
+
+
 # every symbol include/gom_b200.h declares (tests check the .so exports all of them)
 EXPORTS = [
     "gom_abi_version", "gom_last_error", "gom_launch_count", "gom_profile_enable", "gom_profile_num_slots",
@@ -108,16 +127,23 @@ EXPORTS = [
     "gom_sizeof_photo_args", "gom_sizeof_camera_args", "gom_sizeof_raster_fwd_args", "gom_sizeof_raster_bwd_args",
     "gom_sizeof_joint_fwd_args", "gom_sizeof_joint_bwd_args", "gom_sizeof_lbs_fwd_args", "gom_sizeof_lbs_bwd_args",
     "gom_sizeof_face_fwd_args", "gom_sizeof_face_bwd_args",
+    "gom_lpips_input_forward", "gom_lpips_input_backward", "gom_bias_relu", "gom_relu_backward",
+    "gom_lpips_tap_forward", "gom_lpips_tap_backward", "gom_sizeof_lpips_input_args", "gom_sizeof_bias_relu_args",
+    "gom_sizeof_relu_bwd_args", "gom_sizeof_lpips_tap_args",
 ]
 
 _STRUCTS = {
     "camera": GomCameraArgs, "raster_fwd": GomRasterFwdArgs, "raster_bwd": GomRasterBwdArgs,
     "joint_fwd": GomJointFwdArgs, "joint_bwd": GomJointBwdArgs, "lbs_fwd": GomLbsFwdArgs, "lbs_bwd": GomLbsBwdArgs,
     "face_fwd": GomFaceFwdArgs, "face_bwd": GomFaceBwdArgs, "photo": GomPhotoArgs,
+    "lpips_input": GomLpipsInputArgs, "bias_relu": GomBiasReluArgs, "relu_bwd": GomReluBwdArgs,
+    "lpips_tap": GomLpipsTapArgs,
 }
 _ENTRY_POINTS = ["gom_camera_from_KE", "gom_raster_forward", "gom_raster_backward", "gom_joint_transforms_forward",
                  "gom_joint_transforms_backward", "gom_lbs_forward", "gom_lbs_backward", "gom_face_gaussians_forward",
-                 "gom_face_gaussians_backward", "gom_photometric_forward", "gom_photometric_backward"]
+                 "gom_face_gaussians_backward", "gom_photometric_forward", "gom_photometric_backward",
+                 "gom_lpips_input_forward", "gom_lpips_input_backward", "gom_bias_relu", "gom_relu_backward",
+                 "gom_lpips_tap_forward", "gom_lpips_tap_backward"]
 
 _lib = None
 

@@ -1,0 +1,386 @@
+// lpips.cu — the non-GEMM half of LPIPS-VGG (v0.1), forward and backward, fused (sm_100a).
+//
+// Replaces, for reference utils/lpips/lpips.py:81-123 (+ ScalingLayer :126-133, NetLinLayer :136-146,
+// normalize_tensor __init__.py:40-42, the ReLU / MaxPool2d layers of pretrained_networks.py:96-134) as called from
+// train.py:113-121, everything that is NOT a convolution: input scaling, bias + ReLU, 2x2 max-pooling, channel-unit
+// normalisation, squared difference, the 1x1 "lin" heads, the spatial mean, and ALL of their backward passes
+// (autograd in the reference: ~25 elementwise/reduction launches per tapped layer, each a full pass over HBM).
+// The 3x3 convolutions themselves stay library tensor-core GEMMs (cuDNN), see gomavatar_b200/lpips.py.
+//
+// Layout: activations are NHWC fp32 ("channels_last"), so one pixel's channel vector is contiguous.  A batch holds
+// the B predicted images first and their B targets after them ([2B,h,w,C]); a warp owns one 2x2 pixel quad of one
+// (prediction, target) pair, lanes stride over channels with 8/16-byte loads, channel sums are warp shuffles.
+// Every kernel is a single pass over its tensors: HBM-bound by construction (roofline in DESIGN.md §4).
+#include "gom_common.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+constexpr float kEps = 1e-10f;          // normalize_tensor eps (inside and outside the sqrt)
+
+// ------------------------------------------------------------------------------------------------ input scaling
+// x = (v * mul + add - shift_c) / scale_c ; mul/add = (2,-1) when the caller hands [0,1] images (train.py:114-116).
+__constant__ float c_shift[3] = {-.030f, -.088f, -.188f};
+__constant__ float c_scale[3] = {.458f, .448f, .450f};
+
+__global__ void __launch_bounds__(kThreads) k_lpips_input_fwd(const float *pred, const float *gt, float *out,
+                                                              long long n_half, float mul, float add) {
+    // n_half = B*H*W*3 elements per half; out = [pred half | gt half]
+    for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < 2 * n_half; i += (long long)gridDim.x * kThreads) {
+        const float v = i < n_half ? pred[i] : gt[i - n_half];
+        const int c = (int)(i % 3);
+        out[i] = (v * mul + add - c_shift[c]) / c_scale[c];
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) k_lpips_input_bwd(const float *g, float *d_pred, long long n_half, float mul) {
+    for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < n_half; i += (long long)gridDim.x * kThreads)
+        d_pred[i] = g[i] * mul / c_scale[(int)(i % 3)];
+}
+
+// ------------------------------------------------------------------------------------------------ bias + ReLU
+// in place over [n_pix, C], C % 4 == 0.
+__global__ void __launch_bounds__(kThreads) k_bias_relu(float4 *x, const float4 *bias, long long n4, int c4) {
+    for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < n4; i += (long long)gridDim.x * kThreads) {
+        float4 v = x[i];
+        const float4 b = __ldg(bias + (int)(i % c4));
+        v.x = fmaxf(v.x + b.x, 0.f); v.y = fmaxf(v.y + b.y, 0.f); v.z = fmaxf(v.z + b.z, 0.f); v.w = fmaxf(v.w + b.w, 0.f);
+        x[i] = v;
+    }
+}
+
+// grad *= (act > 0), in place
+__global__ void __launch_bounds__(kThreads) k_relu_bwd(const float4 *act, float4 *grad, long long n4) {
+    for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < n4; i += (long long)gridDim.x * kThreads) {
+        const float4 a = act[i];
+        float4 g = grad[i];
+        g.x = a.x > 0.f ? g.x : 0.f; g.y = a.y > 0.f ? g.y : 0.f; g.z = a.z > 0.f ? g.z : 0.f; g.w = a.w > 0.f ? g.w : 0.f;
+        grad[i] = g;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ tapped layers
+struct TapDev {
+    int B, h, w, pool;
+    const float *feats;         // [2B,h,w,C]
+    const float *lin;           // [C]
+    float *layer_sums;          // [B]   += spatial mean of sum_c lin_c (u0_c - u1_c)^2
+    float *pooled;              // [2B,h/2,w/2,C]
+    const float *dval;          // [B]
+    const float *d_pooled;      // [B,h/2,w/2,C]
+    float *d_pre;               // [B,h,w,C]
+};
+
+template <int C> struct Lanes {
+    static constexpr int CPL = C / 32;                   // channels per lane
+    static constexpr int VW = CPL < 4 ? CPL : 4;         // vector width of one load
+    static constexpr int NV = CPL / VW;                  // loads per pixel per lane
+};
+
+// channel index of register r of this lane
+template <int C> __device__ __forceinline__ int chan_of(int lane, int r) {
+    using L = Lanes<C>;
+    return (r / L::VW) * 32 * L::VW + lane * L::VW + (r % L::VW);
+}
+
+template <int C> __device__ __forceinline__ void load_px(const float *p, int lane, float (&f)[Lanes<C>::CPL]) {
+    using L = Lanes<C>;
+#pragma unroll
+    for (int k = 0; k < L::NV; k++) {
+        const float *q = p + k * 32 * L::VW + lane * L::VW;
+        if constexpr (L::VW == 4) {
+            const float4 v = *reinterpret_cast<const float4 *>(q);
+            f[4 * k] = v.x; f[4 * k + 1] = v.y; f[4 * k + 2] = v.z; f[4 * k + 3] = v.w;
+        } else if constexpr (L::VW == 2) {
+            const float2 v = *reinterpret_cast<const float2 *>(q);
+            f[2 * k] = v.x; f[2 * k + 1] = v.y;
+        } else {
+            f[k] = *q;
+        }
+    }
+}
+
+template <int C> __device__ __forceinline__ void store_px(float *p, int lane, const float (&f)[Lanes<C>::CPL]) {
+    using L = Lanes<C>;
+#pragma unroll
+    for (int k = 0; k < L::NV; k++) {
+        float *q = p + k * 32 * L::VW + lane * L::VW;
+        if constexpr (L::VW == 4) *reinterpret_cast<float4 *>(q) = make_float4(f[4 * k], f[4 * k + 1], f[4 * k + 2], f[4 * k + 3]);
+        else if constexpr (L::VW == 2) *reinterpret_cast<float2 *>(q) = make_float2(f[2 * k], f[2 * k + 1]);
+        else *q = f[k];
+    }
+}
+
+__device__ __forceinline__ void warp_sum2(float &a, float &b) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, d);
+        b += __shfl_xor_sync(0xffffffffu, b, d);
+    }
+}
+
+// Forward: per (prediction, target) pair and pixel  d = sum_c lin_c (f0_c/(n0+eps) - f1_c/(n1+eps))^2,
+// n = sqrt(sum_c f_c^2 + eps); layer_sums[b] += mean over pixels; optionally the 2x2/2 max-pool of BOTH halves.
+template <int C>
+__global__ void __launch_bounds__(kThreads) k_lpips_tap_fwd(TapDev a) {
+    using L = Lanes<C>;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int b = blockIdx.y;
+    const int qw = (a.w + 1) >> 1, qh = (a.h + 1) >> 1, nq = qw * qh;
+    const int ph = a.h >> 1, pw = a.w >> 1;
+    const long long img = (long long)a.h * a.w * C;
+    const float *F0 = a.feats + (long long)b * img, *F1 = a.feats + (long long)(b + a.B) * img;
+    float lin[L::CPL];
+#pragma unroll
+    for (int r = 0; r < L::CPL; r++) lin[r] = __ldg(a.lin + chan_of<C>(lane, r));
+    float acc = 0.f;
+    for (int q = blockIdx.x * kWarps + wid; q < nq; q += gridDim.x * kWarps) {
+        const int qy = q / qw, qx = q - qy * qw;
+        float m0[L::CPL], m1[L::CPL];
+#pragma unroll
+        for (int r = 0; r < L::CPL; r++) { m0[r] = -INFINITY; m1[r] = -INFINITY; }
+#pragma unroll
+        for (int s = 0; s < 4; s++) {
+            const int y = 2 * qy + (s >> 1), x = 2 * qx + (s & 1);
+            if (y >= a.h || x >= a.w) continue;                   // warp-uniform
+            const long long o = ((long long)y * a.w + x) * C;
+            float f0[L::CPL], f1[L::CPL];
+            load_px<C>(F0 + o, lane, f0);
+            load_px<C>(F1 + o, lane, f1);
+            float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+            for (int r = 0; r < L::CPL; r++) {
+                s0 += f0[r] * f0[r]; s1 += f1[r] * f1[r];
+                m0[r] = fmaxf(m0[r], f0[r]); m1[r] = fmaxf(m1[r], f1[r]);
+            }
+            warp_sum2(s0, s1);
+            const float i0 = 1.f / (sqrtf(s0 + kEps) + kEps), i1 = 1.f / (sqrtf(s1 + kEps) + kEps);
+            float d = 0.f;
+#pragma unroll
+            for (int r = 0; r < L::CPL; r++) {
+                const float t = f0[r] * i0 - f1[r] * i1;
+                d += lin[r] * t * t;
+            }
+            acc += d;                                             // reduced across lanes once, at the end
+        }
+        if (a.pool && qy < ph && qx < pw) {
+            const long long po = ((long long)qy * pw + qx) * C, pimg = (long long)ph * pw * C;
+            store_px<C>(a.pooled + (long long)b * pimg + po, lane, m0);
+            store_px<C>(a.pooled + (long long)(b + a.B) * pimg + po, lane, m1);
+        }
+    }
+    __shared__ float sh[kWarps];
+    acc = warp_sum(acc);
+    if (lane == 0) sh[wid] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+#pragma unroll
+        for (int k = 0; k < kWarps; k++) t += sh[k];
+        atomicAdd(a.layer_sums + b, t / (float)((long long)a.h * a.w));
+    }
+}
+
+// Backward: gradient wrt the PRE-ReLU convolution output of the prediction half:
+//   [ dval_b * d(mean d)/df0  +  max-pool backward of d_pooled (first maximum in scan order, as torch) ] * (f0 > 0)
+template <int C>
+__global__ void __launch_bounds__(kThreads) k_lpips_tap_bwd(TapDev a) {
+    using L = Lanes<C>;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int b = blockIdx.y;
+    const int qw = (a.w + 1) >> 1, qh = (a.h + 1) >> 1, nq = qw * qh;
+    const int ph = a.h >> 1, pw = a.w >> 1;
+    const long long img = (long long)a.h * a.w * C;
+    const float *F0 = a.feats + (long long)b * img, *F1 = a.feats + (long long)(b + a.B) * img;
+    float *G = a.d_pre + (long long)b * img;
+    const float kscale = 2.f * a.dval[b] / (float)((long long)a.h * a.w);
+    float lin[L::CPL];
+#pragma unroll
+    for (int r = 0; r < L::CPL; r++) lin[r] = __ldg(a.lin + chan_of<C>(lane, r));
+    for (int q = blockIdx.x * kWarps + wid; q < nq; q += gridDim.x * kWarps) {
+        const int qy = q / qw, qx = q - qy * qw;
+        const bool pooled = a.pool && a.d_pooled && qy < ph && qx < pw;      // quad complete => all 4 pixels valid
+        float gp[L::CPL];
+        uint32_t am[L::CPL > 16 ? 2 : 1] = {};                               // 2-bit arg-max position per channel
+        if (pooled) {
+            load_px<C>(a.d_pooled + ((long long)b * ph * pw + (long long)qy * pw + qx) * C, lane, gp);
+            float best[L::CPL];
+#pragma unroll
+            for (int s = 0; s < 4; s++) {
+                float f[L::CPL];
+                load_px<C>(F0 + ((long long)(2 * qy + (s >> 1)) * a.w + 2 * qx + (s & 1)) * C, lane, f);
+#pragma unroll
+                for (int r = 0; r < L::CPL; r++) {
+                    if (s == 0) best[r] = f[r];
+                    else if (f[r] > best[r] || f[r] != f[r]) {               // strict: the first maximum wins (NaN propagates)
+                        best[r] = f[r];
+                        am[r >> 4] = (am[r >> 4] & ~(3u << (2 * (r & 15)))) | ((uint32_t)s << (2 * (r & 15)));
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int s = 0; s < 4; s++) {
+            const int y = 2 * qy + (s >> 1), x = 2 * qx + (s & 1);
+            if (y >= a.h || x >= a.w) continue;
+            const long long o = ((long long)y * a.w + x) * C;
+            float f0[L::CPL], f1[L::CPL];
+            load_px<C>(F0 + o, lane, f0);                         // second touch of the quad: L1/L2 hit
+            load_px<C>(F1 + o, lane, f1);
+            float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+            for (int r = 0; r < L::CPL; r++) { s0 += f0[r] * f0[r]; s1 += f1[r] * f1[r]; }
+            warp_sum2(s0, s1);
+            const float n0 = sqrtf(s0 + kEps), i0 = 1.f / (n0 + kEps), i1 = 1.f / (sqrtf(s1 + kEps) + kEps);
+            float e[L::CPL], dot = 0.f;
+#pragma unroll
+            for (int r = 0; r < L::CPL; r++) {
+                e[r] = kscale * lin[r] * (f0[r] * i0 - f1[r] * i1);
+                dot += e[r] * f0[r];
+            }
+            dot = warp_sum(dot);
+            const float k2 = dot * i0 * i0 / n0;
+            float g[L::CPL];
+#pragma unroll
+            for (int r = 0; r < L::CPL; r++) {
+                float v = e[r] * i0 - k2 * f0[r];
+                if (pooled && ((am[r >> 4] >> (2 * (r & 15))) & 3u) == (uint32_t)s) v += gp[r];
+                g[r] = f0[r] > 0.f ? v : 0.f;
+            }
+            store_px<C>(G + o, lane, g);
+        }
+    }
+}
+
+int grid_for(long long work_items, int per_block) {
+    long long g = (work_items + per_block - 1) / per_block;
+    const long long cap = 148LL * 16;            // 148 SMs x resident blocks; grid-stride loops cover the rest
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    return (int)g;
+}
+
+template <int C> int launch_tap(const TapDev &d, bool bwd, cudaStream_t stream) {
+    const int nq = ((d.w + 1) / 2) * ((d.h + 1) / 2);
+    int gx = (nq + kWarps - 1) / kWarps;
+    const int cap = (148 * 8 + d.B - 1) / d.B;   // ~8 resident blocks per SM over all images
+    if (gx > cap) gx = cap;
+    if (gx < 1) gx = 1;
+    dim3 grid(gx, d.B);
+    if (bwd) k_lpips_tap_bwd<C><<<grid, kThreads, 0, stream>>>(d);
+    else k_lpips_tap_fwd<C><<<grid, kThreads, 0, stream>>>(d);
+    GOM_LAUNCH_CHECK();
+    return GOM_OK;
+}
+
+int dispatch_tap(const GomLpipsTapArgs *p, bool bwd, cudaStream_t stream) {
+    TapDev d;
+    d.B = p->n_frames; d.h = p->height; d.w = p->width; d.pool = p->pool;
+    d.feats = p->feats; d.lin = p->lin; d.layer_sums = p->layer_sums; d.pooled = p->pooled;
+    d.dval = p->dL_dval; d.d_pooled = p->dL_dpooled; d.d_pre = p->dL_dpre;
+    switch (p->channels) {
+        case 32: return launch_tap<32>(d, bwd, stream);
+        case 64: return launch_tap<64>(d, bwd, stream);
+        case 128: return launch_tap<128>(d, bwd, stream);
+        case 256: return launch_tap<256>(d, bwd, stream);
+        case 512: return launch_tap<512>(d, bwd, stream);
+        default:
+            gom_set_error("gom_lpips_tap: channels must be 32, 64, 128, 256 or 512 (got %d)", p->channels);
+            return GOM_ERR_UNSUPPORTED;
+    }
+}
+
+}  // namespace
+
+extern "C" int gom_lpips_input_forward(const GomLpipsInputArgs *p, gom_stream_t stream_) {
+    GOM_REQUIRE(p != nullptr, "args");
+    GOM_REQUIRE(p->n_frames > 0 && p->height > 0 && p->width > 0, "sizes");
+    GOM_REQUIRE(p->pred && p->gt && p->out, "null pointer");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const long long n_half = 3LL * p->n_frames * p->height * p->width;
+    gom_prof_begin(GOM_PROF_LPIPS_INPUT, stream);
+    k_lpips_input_fwd<<<grid_for(2 * n_half, kThreads * 4), kThreads, 0, stream>>>(
+        p->pred, p->gt, p->out, n_half, p->from_unit_range ? 2.f : 1.f, p->from_unit_range ? -1.f : 0.f);
+    GOM_LAUNCH_CHECK();
+    gom_prof_end(GOM_PROF_LPIPS_INPUT, stream);
+    return GOM_OK;
+}
+
+extern "C" int gom_lpips_input_backward(const GomLpipsInputArgs *p, gom_stream_t stream_) {
+    GOM_REQUIRE(p != nullptr, "args");
+    GOM_REQUIRE(p->n_frames > 0 && p->height > 0 && p->width > 0, "sizes");
+    GOM_REQUIRE(p->dL_dout && p->dL_dpred, "null pointer");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const long long n_half = 3LL * p->n_frames * p->height * p->width;
+    gom_prof_begin(GOM_PROF_LPIPS_INPUT, stream);
+    k_lpips_input_bwd<<<grid_for(n_half, kThreads * 4), kThreads, 0, stream>>>(p->dL_dout, p->dL_dpred, n_half,
+                                                                              p->from_unit_range ? 2.f : 1.f);
+    GOM_LAUNCH_CHECK();
+    gom_prof_end(GOM_PROF_LPIPS_INPUT, stream);
+    return GOM_OK;
+}
+
+extern "C" int gom_bias_relu(const GomBiasReluArgs *p, gom_stream_t stream_) {
+    GOM_REQUIRE(p != nullptr, "args");
+    GOM_REQUIRE(p->n_pixels > 0 && p->channels > 0 && p->channels % 4 == 0, "channels must be a positive multiple of 4");
+    GOM_REQUIRE(p->x && p->bias, "null pointer");
+    GOM_REQUIRE(((uintptr_t)p->x % 16) == 0 && ((uintptr_t)p->bias % 16) == 0, "x / bias must be 16-byte aligned");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const long long n4 = p->n_pixels * (p->channels / 4);
+    gom_prof_begin(GOM_PROF_BIAS_RELU, stream);
+    k_bias_relu<<<grid_for(n4, kThreads * 4), kThreads, 0, stream>>>(reinterpret_cast<float4 *>(p->x),
+                                                                    reinterpret_cast<const float4 *>(p->bias), n4, p->channels / 4);
+    GOM_LAUNCH_CHECK();
+    gom_prof_end(GOM_PROF_BIAS_RELU, stream);
+    return GOM_OK;
+}
+
+extern "C" int gom_relu_backward(const GomReluBwdArgs *p, gom_stream_t stream_) {
+    GOM_REQUIRE(p != nullptr, "args");
+    GOM_REQUIRE(p->n > 0 && p->n % 4 == 0, "n must be a positive multiple of 4");
+    GOM_REQUIRE(p->act && p->grad, "null pointer");
+    GOM_REQUIRE(((uintptr_t)p->act % 16) == 0 && ((uintptr_t)p->grad % 16) == 0, "act / grad must be 16-byte aligned");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    gom_prof_begin(GOM_PROF_RELU_BWD, stream);
+    k_relu_bwd<<<grid_for(p->n / 4, kThreads * 4), kThreads, 0, stream>>>(reinterpret_cast<const float4 *>(p->act),
+                                                                         reinterpret_cast<float4 *>(p->grad), p->n / 4);
+    GOM_LAUNCH_CHECK();
+    gom_prof_end(GOM_PROF_RELU_BWD, stream);
+    return GOM_OK;
+}
+
+static int tap_common_checks(const GomLpipsTapArgs *p) {
+    GOM_REQUIRE(p != nullptr, "args");
+    GOM_REQUIRE(p->n_frames > 0 && p->n_frames <= 65535 && p->height > 0 && p->width > 0, "sizes");
+    GOM_REQUIRE(p->feats && p->lin, "null pointer");
+    GOM_REQUIRE(((uintptr_t)p->feats % 16) == 0, "feats must be 16-byte aligned");
+    return GOM_OK;
+}
+
+extern "C" int gom_lpips_tap_forward(const GomLpipsTapArgs *p, gom_stream_t stream_) {
+    if (int rc = tap_common_checks(p)) return rc;
+    GOM_REQUIRE(p->layer_sums, "layer_sums");
+    GOM_REQUIRE(!p->pool || (p->pooled && ((uintptr_t)p->pooled % 16) == 0), "pooled (16-byte aligned) is required when pool = 1");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    gom_prof_begin(GOM_PROF_LPIPS_TAP_FWD, stream);
+    const int rc = dispatch_tap(p, false, stream);
+    gom_prof_end(GOM_PROF_LPIPS_TAP_FWD, stream);
+    return rc;
+}
+
+extern "C" int gom_lpips_tap_backward(const GomLpipsTapArgs *p, gom_stream_t stream_) {
+    if (int rc = tap_common_checks(p)) return rc;
+    GOM_REQUIRE(p->dL_dval && p->dL_dpre && ((uintptr_t)p->dL_dpre % 16) == 0, "dL_dval / dL_dpre");
+    GOM_REQUIRE(!p->dL_dpooled || ((uintptr_t)p->dL_dpooled % 16) == 0, "dL_dpooled alignment");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    gom_prof_begin(GOM_PROF_LPIPS_TAP_BWD, stream);
+    const int rc = dispatch_tap(p, true, stream);
+    gom_prof_end(GOM_PROF_LPIPS_TAP_BWD, stream);
+    return rc;
+}
+
+extern "C" size_t gom_sizeof_lpips_input_args(void) { return sizeof(GomLpipsInputArgs); }
+extern "C" size_t gom_sizeof_bias_relu_args(void) { return sizeof(GomBiasReluArgs); }
+extern "C" size_t gom_sizeof_relu_bwd_args(void) { return sizeof(GomReluBwdArgs); }
+extern "C" size_t gom_sizeof_lpips_tap_args(void) { return sizeof(GomLpipsTapArgs); }

@@ -88,8 +88,11 @@ def compute_loss(rgbs, masks, bgcolors, rgb_gt, mask_gt, lpips_func=None, coeff_
     total = coeff_rgb * l_rgb + coeff_mask * l_mask
     terms = {"rgb": l_rgb, "mask": l_mask}
     if lpips_func is not None and coeff_lpips > 0:
-        s = lambda x: 2 * x - 1
-        l_lp = torch.mean(lpips_func(s(rgb_u.permute(0, 3, 1, 2)), s(rgb_gt.permute(0, 3, 1, 2))))
+        if getattr(lpips_func, "fused", False) and hasattr(lpips_func, "per_image"):
+            l_lp = torch.mean(lpips_func.per_image(rgb_u, rgb_gt, from_unit_range=True))       # 2x-1 folded into the kernel
+        else:
+            s = lambda x: 2 * x - 1
+            l_lp = torch.mean(lpips_func(s(rgb_u.permute(0, 3, 1, 2)), s(rgb_gt.permute(0, 3, 1, 2))))
         terms["lpips"] = l_lp
         total = total + coeff_lpips * l_lp
     return total, terms, rgb_u

@@ -1,10 +1,14 @@
 """LPIPS-VGG v0.1 perceptual loss (reference utils/lpips/lpips.py:81-123, pretrained_networks.py:96-134,
 __init__.py:40-42; used at train.py:113-121 and eval.py:110-116).
 
-The VGG16 convolutions are dense GEMM-shaped work and stay in cuDNN (library tensor-core kernels, as SURVEY.md §8a-12
-prescribes); what this module owns is the glue: layout (channels_last), the target-image feature cache (the ground
-truth of a frame does not change between the forward and anything else in the step, and carries no gradient), and
-the numerics switch ``conv_precision``:
+The VGG16 3x3 convolutions are dense GEMM-shaped work and stay in cuDNN (library tensor-core kernels, as SURVEY.md
+§8a-12 prescribes).  EVERYTHING ELSE of the loss — input scaling, bias + ReLU, max-pooling, channel normalisation,
+squared difference, the 1x1 heads, the spatial mean, and all of their backward passes — runs in the hand-written
+kernels of csrc/lpips.cu (``fused=True``, the default; one HBM pass per layer each way instead of ~25), driven by
+the hand-rolled backward in ``_FusedLpips``: prediction and target go through the trunk as ONE batch [B pred | B gt],
+only the prediction half is back-propagated, and the gradient arrives at each convolution's dgrad already masked by
+the ReLU and merged with the pooled / tapped contributions.  ``fused=False`` keeps the plain torch formulation (the
+A/B reference for the kernels' tests).  Numerics switch ``conv_precision``:
   "tf32" (default) — cuDNN may use TF32 tensor-core convolutions.  This IS the reference's stock behaviour: it never
           touches ``torch.backends.cudnn.allow_tf32``, whose default is True in the torch 1.13 it pins (README.md:19-20);
   "fp32"  — strict IEEE fp32 convolutions (what the CPU oracle computes; used by the parity tests);
@@ -20,6 +24,9 @@ import numpy as np
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
+
+from . import _lib
+from ._lib import GomBiasReluArgs, GomLpipsInputArgs, GomLpipsTapArgs, GomReluBwdArgs, call, ptr
 
 _VGG_CFG = [64, 64, "M", 128, 128, "M", 256, 256, 256, "M", 512, 512, 512, "M", 512, 512, 512]
 _TAPS = (3, 8, 15, 22, 29)
@@ -83,9 +90,105 @@ class _BackwardPrecision:
             return g, None
 
 
+_LEVELS = (2, 2, 3, 3, 3)           # convolutions per VGG16 block; the last ReLU of each block is tapped
+
+
+def _nhwc(t):
+    """[N,C,H,W] channels_last tensor -> the same storage seen as contiguous [N,H,W,C]"""
+    return t.permute(0, 2, 3, 1)
+
+
+class _FusedLpips(torch.autograd.Function):
+    """pred, gt: contiguous [B,H,W,3] fp32 -> per-image LPIPS value [B].  Only ``pred`` receives a gradient."""
+
+    @staticmethod
+    def forward(ctx, pred, gt, net, from_unit_range):
+        if pred.device.type != "cuda":
+            raise _lib.GomError("LPIPS (fused): inputs must live on a CUDA device (no CPU path exists)")
+        B, H, W, _ = pred.shape
+        dev = pred.device
+        pred, gt = pred.detach().contiguous().float(), gt.detach().contiguous().float()
+        x = torch.empty(2 * B, H, W, 3, dtype=torch.float32, device=dev)
+        call("gom_lpips_input_forward", GomLpipsInputArgs(n_frames=B, height=H, width=W, from_unit_range=int(from_unit_range),
+                                                          pred=ptr(pred), gt=ptr(gt), out=ptr(x)))
+        vals = torch.zeros(B, dtype=torch.float32, device=dev)
+        acts = [x.permute(0, 3, 1, 2)]                      # NCHW-shaped views of NHWC storage
+        h = acts[0]
+        prev = torch.backends.cudnn.allow_tf32
+        torch.backends.cudnn.allow_tf32 = net.conv_precision != "fp32"
+        try:
+            ci = 0
+            for level, n_conv in enumerate(_LEVELS):
+                for _ in range(n_conv):
+                    h = net._conv_bias_relu(h, ci)
+                    acts.append(h)
+                    ci += 1
+                N2, C, hh, ww = h.shape
+                pool = level < len(_LEVELS) - 1
+                pooled = torch.empty(N2, hh // 2, ww // 2, C, dtype=torch.float32, device=dev) if pool else None
+                call("gom_lpips_tap_forward", GomLpipsTapArgs(
+                    n_frames=B, height=hh, width=ww, channels=C, pool=int(pool), feats=ptr(h), lin=ptr(net._lin(level)),
+                    layer_sums=ptr(vals), pooled=ptr(pooled)))
+                if pool:
+                    h = pooled.permute(0, 3, 1, 2)
+                    acts.append(h)
+        finally:
+            torch.backends.cudnn.allow_tf32 = prev
+        ctx.net, ctx.acts, ctx.from_unit_range = net, acts, bool(from_unit_range)
+        ctx.dims = (B, H, W)
+        return vals
+
+    @staticmethod
+    def backward(ctx, g_vals):
+        net, acts = ctx.net, ctx.acts
+        B, H, W = ctx.dims
+        dev = g_vals.device
+        dval = g_vals.contiguous().float()
+        # index of the activation feeding / produced by every convolution, walking acts = [x, c0, c1, pool, c2, ...]
+        conv_in, conv_out, k = [], [], 0
+        for level, n_conv in enumerate(_LEVELS):
+            for _ in range(n_conv):
+                conv_in.append(k); conv_out.append(k + 1); k += 1
+            if level < len(_LEVELS) - 1:
+                k += 1
+        prev = torch.backends.cudnn.allow_tf32
+        torch.backends.cudnn.allow_tf32 = net.conv_precision != "fp32"
+        try:
+            g_pooled, ci = None, len(conv_in)
+            for level in reversed(range(len(_LEVELS))):
+                ci_last = ci - 1
+                a = acts[conv_out[ci_last]]
+                N2, C, hh, ww = a.shape
+                g_pre = torch.empty(B, hh, ww, C, dtype=torch.float32, device=dev)
+                call("gom_lpips_tap_backward", GomLpipsTapArgs(
+                    n_frames=B, height=hh, width=ww, channels=C, pool=int(g_pooled is not None), feats=ptr(a),
+                    lin=ptr(net._lin(level)), dL_dval=ptr(dval), dL_dpooled=ptr(g_pooled), dL_dpre=ptr(g_pre)))
+                for j in reversed(range(_LEVELS[level])):
+                    ci -= 1
+                    inp = acts[conv_in[ci]][:B]
+                    g_in = net._conv_dgrad(g_pre.permute(0, 3, 1, 2), inp, ci)
+                    g_in = _nhwc(g_in.contiguous(memory_format=torch.channels_last))
+                    if j > 0:                                # the input was itself a ReLU output of this block
+                        call("gom_relu_backward", GomReluBwdArgs(n=g_in.numel(), act=ptr(inp), grad=ptr(g_in)))
+                        g_pre = g_in
+                    else:                                    # the input was the pooled previous block (or the image)
+                        g_pooled = g_in
+        finally:
+            torch.backends.cudnn.allow_tf32 = prev
+        d_pred = torch.empty(B, H, W, 3, dtype=torch.float32, device=dev)
+        call("gom_lpips_input_backward", GomLpipsInputArgs(n_frames=B, height=H, width=W, from_unit_range=int(ctx.from_unit_range),
+                                                           dL_dout=ptr(g_pooled), dL_dpred=ptr(d_pred)))
+        ctx.acts = None
+        return d_pred, None, None, None
+
+
 class LPIPS(nn.Module):
-    def __init__(self, trunk_state, head_weights, conv_precision="tf32", channels_last=True):
+    def __init__(self, trunk_state, head_weights, conv_precision="tf32", channels_last=True, fused=True,
+                 conv_epilogue="cudnn"):
         super().__init__()
+        self.fused = bool(fused) and conv_precision != "bf16"      # the fused kernels are fp32-only
+        assert conv_epilogue in ("kernel", "cudnn")
+        self.conv_epilogue = conv_epilogue
         self.features = make_vgg16_features()
         self.features.load_state_dict(trunk_state)
         self.register_buffer("shift", torch.tensor([-.030, -.088, -.188])[None, :, None, None])
@@ -100,6 +203,39 @@ class LPIPS(nn.Module):
         self.eval()
         if channels_last:
             self.features = self.features.to(memory_format=torch.channels_last)
+        self._convs = [m for m in self.features if isinstance(m, nn.Conv2d)]
+        self._no_cudnn_epilogue = set()
+
+    # ---------------------------------------------------------------------------- fused path (csrc/lpips.cu + cuDNN)
+    def _lin(self, level):
+        return getattr(self, f"lin{level}").reshape(-1)
+
+    def _conv_bias_relu(self, h, ci):
+        """3x3 convolution (cuDNN) + bias + ReLU on a channels_last batch."""
+        conv = self._convs[ci]
+        w = conv.weight
+        if self.conv_epilogue == "cudnn" and ci not in self._no_cudnn_epilogue:
+            # cuDNN's fused conv + bias + activation: measured on B200 at the same time as the bare convolution
+            # (profiles/r1_conv_probe.md), so the epilogue costs no extra HBM pass.
+            try:
+                y = torch.cudnn_convolution_relu(h, w, conv.bias, (1, 1), (1, 1), (1, 1), 1)
+                return y.contiguous(memory_format=torch.channels_last)
+            except RuntimeError:
+                self._no_cudnn_epilogue.add(ci)          # unsupported shape: use the kernel epilogue for this layer
+        y = F.conv2d(h, w, None, padding=1)
+        y = y.contiguous(memory_format=torch.channels_last)
+        N, C, hh, ww = y.shape
+        call("gom_bias_relu", GomBiasReluArgs(n_pixels=N * hh * ww, channels=C, x=ptr(y), bias=ptr(conv.bias)))
+        return y
+
+    def _conv_dgrad(self, g_out, inp, ci):
+        w = self._convs[ci].weight
+        return torch.ops.aten.convolution_backward(g_out, inp, w, None, (1, 1), (1, 1), (1, 1), False, (0, 0), 1,
+                                                   (True, False, False))[0]
+
+    def per_image(self, pred_nhwc, gt_nhwc, from_unit_range=True):
+        """pred / gt contiguous [B,H,W,3] (in [0,1] when from_unit_range, else already in [-1,1]) -> LPIPS values [B]."""
+        return _FusedLpips.apply(pred_nhwc, gt_nhwc, self, from_unit_range)
 
     def _taps(self, x):
         h = (x - self.shift) / self.scale
@@ -135,6 +271,9 @@ class LPIPS(nn.Module):
 
     def forward(self, in0, in1=None, target_feats=None):
         """in0 / in1 in [-1,1], [B,3,H,W] -> [B,1,1,1]  (reference LPIPS.forward with normalize=False)."""
+        if self.fused and target_feats is None and self.conv_precision != "bf16":
+            B = in0.shape[0]
+            return self.per_image(in0.permute(0, 2, 3, 1), in1.permute(0, 2, 3, 1), from_unit_range=False).view(B, 1, 1, 1)
         if target_feats is None:
             target_feats = self.target_features(in1)
         if in0.requires_grad:

@@ -267,6 +267,60 @@ typedef struct {
 int gom_photometric_forward(const GomPhotoArgs *a, gom_stream_t stream);
 int gom_photometric_backward(const GomPhotoArgs *a, gom_stream_t stream);
 
+/* --------------------------------------------------------------------------------------------------------------
+ * LPIPS-VGG v0.1 perceptual loss — everything that is not a convolution (csrc/lpips.cu).  Replaces the torch ops of
+ * reference utils/lpips/lpips.py:81-123 (ScalingLayer :126-133, NetLinLayer :136-146), utils/lpips/__init__.py:40-42
+ * (normalize_tensor), and the ReLU / MaxPool2d layers of utils/lpips/pretrained_networks.py:96-134, forward AND
+ * backward, as called from train.py:113-121.  Activations are NHWC fp32; a batch is [B predictions | B targets].
+ */
+typedef struct {
+    int32_t n_frames, height, width;
+    int32_t from_unit_range;     /* 1: inputs are in [0,1] and the 2x-1 of train.py:114-116 is folded in */
+    const float *pred;           /* [B,H,W,3] */
+    const float *gt;             /* [B,H,W,3] */
+    float *out;                  /* [2B,H,W,3] (forward)  (v - shift_c) / scale_c, ScalingLayer */
+    const float *dL_dout;        /* [B,H,W,3]  (backward) gradient wrt the prediction half of `out` */
+    float *dL_dpred;             /* [B,H,W,3]  (backward) */
+} GomLpipsInputArgs;
+int gom_lpips_input_forward(const GomLpipsInputArgs *a, gom_stream_t stream);
+int gom_lpips_input_backward(const GomLpipsInputArgs *a, gom_stream_t stream);
+
+/* x = max(x + bias[c], 0) in place over [n_pixels, channels] (the epilogue of each VGG convolution) */
+typedef struct {
+    int64_t n_pixels; int32_t channels, _pad;
+    float *x;
+    const float *bias;           /* [channels] */
+} GomBiasReluArgs;
+int gom_bias_relu(const GomBiasReluArgs *a, gom_stream_t stream);
+
+/* grad *= (act > 0) in place (ReLU backward of the untapped layers) */
+typedef struct {
+    int64_t n;                   /* elements, multiple of 4 */
+    const float *act;            /* post-ReLU activation */
+    float *grad;
+} GomReluBwdArgs;
+int gom_relu_backward(const GomReluBwdArgs *a, gom_stream_t stream);
+
+/* One tapped layer (relu1_2, 2_2, 3_3, 4_3, 5_3).
+ * forward : layer_sums[b] += mean_{pixels} sum_c lin_c (f0_c/(|f0|+eps) - f1_c/(|f1|+eps))^2, |f| = sqrt(sum f^2 + eps),
+ *           f0 = feats[b], f1 = feats[B+b]; with pool = 1 also writes the 2x2/2 max-pool of all 2B images.
+ * backward: dL_dpre = [ dL_dval[b] * d(layer value)/df0 + maxpool-backward(dL_dpooled) ] * (f0 > 0): the gradient
+ *           wrt the PRE-ReLU convolution output of the prediction half, ready for the convolution's dgrad.
+ * channels in {32, 64, 128, 256, 512}. */
+typedef struct {
+    int32_t n_frames, height, width, channels;
+    int32_t pool, _pad;
+    const float *feats;          /* [2B,h,w,C] post-ReLU */
+    const float *lin;            /* [C] 1x1 head weights */
+    float *layer_sums;           /* [B]  (forward, accumulated into) */
+    float *pooled;               /* [2B,h/2,w/2,C] (forward, pool = 1) */
+    const float *dL_dval;        /* [B]  (backward) */
+    const float *dL_dpooled;     /* [B,h/2,w/2,C] (backward, nullable) */
+    float *dL_dpre;              /* [B,h,w,C] (backward) */
+} GomLpipsTapArgs;
+int gom_lpips_tap_forward(const GomLpipsTapArgs *a, gom_stream_t stream);
+int gom_lpips_tap_backward(const GomLpipsTapArgs *a, gom_stream_t stream);
+
 /* struct sizes, so that a foreign-language binding can assert its mirror of the structs */
 size_t gom_sizeof_camera_args(void);
 size_t gom_sizeof_raster_fwd_args(void);
@@ -278,6 +332,10 @@ size_t gom_sizeof_lbs_bwd_args(void);
 size_t gom_sizeof_face_fwd_args(void);
 size_t gom_sizeof_face_bwd_args(void);
 size_t gom_sizeof_photo_args(void);
+size_t gom_sizeof_lpips_input_args(void);
+size_t gom_sizeof_bias_relu_args(void);
+size_t gom_sizeof_relu_bwd_args(void);
+size_t gom_sizeof_lpips_tap_args(void);
 
 #ifdef __cplusplus
 }
