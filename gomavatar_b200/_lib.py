@@ -13,7 +13,7 @@ from ctypes import c_int, c_int32, c_int64, c_size_t, c_void_p, c_float, c_char_
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libgom_b200.so")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 STATUS_OVERFLOW = 1
 
 
@@ -39,7 +39,8 @@ class GomRasterFwdArgs(ctypes.Structure):
 
 class GomRasterBwdArgs(ctypes.Structure):
     _fields_ = [("n_frames", c_int32), ("n_gauss", c_int32), ("height", c_int32), ("width", c_int32),
-                ("n_channels", c_int32), ("interleaved", c_int32), ("inst_capacity", c_int64),
+                ("n_channels", c_int32), ("interleaved", c_int32), ("color_grad_channels", c_int32), ("_pad", c_int32),
+                ("inst_capacity", c_int64),
                 ("means3D", c_void_p), ("means3D_stride", c_int64),
                 ("cov3D", c_void_p), ("cov3D_stride", c_int64),
                 ("colors", c_void_p), ("colors_stride", c_int64),

@@ -129,3 +129,21 @@ __device__ __forceinline__ float warp_sum(float v) {
     for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
     return v;
 }
+
+// ------------------------------------------------------------------------------------------- per-warp entry culling
+// A warp of the blend kernels owns an 8x4-pixel sub-block of a 16x16 tile (lane -> (lane & 7, lane >> 3)).  A list
+// entry can only pass the per-pixel test  alpha = min(.99, o * exp(power)) >= 1/255  somewhere in that sub-block if
+// the axis-aligned bounding box of its ellipse  {q <= 2 ln(255 o)},  q = A dx^2 + 2 B dx dy + C dy^2 = -2 power,
+// reaches the sub-block: half extents sqrt(s C / det), sqrt(s A / det) (the ellipse's covariance is the inverse
+// conic).  The test is conservative (1e-3 relative + 0.01 px of slack against rounding), so skipping entries that
+// fail it changes no pixel: they would all have taken the `alpha < 1/255` branch.  Entries are tested one per lane
+// and the survivors visited through the ballot mask.
+__device__ __forceinline__ bool entry_reaches_rect(float2 c, float4 co, float rcx, float rcy, float rhw, float rhh) {
+    const float ko = 255.0f * co.w;
+    const float det = co.x * co.z - co.y * co.y;
+    if (!(ko > 1.0f) || !(det > 0.f)) return ko > 1.0f;           // degenerate conic: never cull (visible if o > 1/255)
+    const float s = 2.0f * __logf(ko) * 1.001f + 1e-3f;
+    const float inv = __fdividef(s, det);
+    const float ex = sqrtf(inv * co.z) + 0.01f, ey = sqrtf(inv * co.x) + 0.01f;
+    return fabsf(c.x - rcx) <= rhw + ex && fabsf(c.y - rcy) <= rhh + ey;
+}

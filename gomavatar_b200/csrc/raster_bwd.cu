@@ -2,13 +2,13 @@
 //
 // Replaces `_C.rasterize_gaussians_backward` of the third-party diff_gaussian_rasterization (renderCUDA backward,
 // computeCov2DCUDA, preprocessCUDA backward).  Upstream issues ~10 global fp32 atomicAdds per
-// (pixel, Gaussian) hit; here each warp first reduces its 32 pixels with shuffles (skipped entirely when no lane of
-// the warp is hit), warps combine in shared memory, and one global atomic per (tile, Gaussian, component) remains.
+// (pixel, Gaussian) hit; here each warp first reduces its 32 pixels with a transposing shuffle butterfly (skipped
+// entirely when no lane of the warp is hit) and one global RED per (8x4 sub-block, Gaussian, component) remains.
 #include "gom_common.cuh"
 
 namespace {
 
-constexpr int kThreads = 256;
+constexpr int kThreads = 256;      // per-Gaussian kernels
 
 struct BwdDev {
     int B, P, H, W, C, interleaved, gx, gy, T;
@@ -25,20 +25,52 @@ struct BwdDev {
 };
 
 // ------------------------------------------------------------------------------------------ App. A.6 blend backward
-template <int C>
-__global__ void __launch_bounds__(kThreads) k_blend_bwd(BwdDev a) {
-    constexpr int NG = 6 + C;            // mean2D.xy, conic A B C, opacity, colour[C]
-    __shared__ uint32_t s_id[kThreads];
-    __shared__ float2 s_xy[kThreads];
-    __shared__ float4 s_co[kThreads];
-    __shared__ float s_col[kThreads * C];
-    __shared__ float s_grad[kThreads * NG];
-    __shared__ uint32_t s_max;
+// Every warp is independent (no block barrier, no shared-memory atomics): it owns one 8x4-pixel sub-block of one tile,
+// walks that tile's sorted list back to front from ITS OWN last contributor, fetches 32 entries per chunk (one per
+// lane, next chunk prefetched), culls them against the sub-block (entry_reaches_rect) and visits the survivors through
+// the ballot mask.  The 8 per-Gaussian gradient components (mean2D.xy, conic A B C, colour rgb) of the 32 pixels are
+// summed with a transposing butterfly — 4+2+1+1+1 = 9 shuffles instead of 8 x 5 — that leaves component i's total on
+// lane group i, and 8 lanes issue ONE fire-and-forget RED.ADD.F32 each.
+constexpr int kBwdThreads = 128;
+constexpr int kBwdWarps = kBwdThreads / 32;
 
-    const int b = blockIdx.z;
-    const int tile = blockIdx.y * a.gx + blockIdx.x;
-    const int tid = threadIdx.y * 16 + threadIdx.x;
-    const int lane = tid & 31;
+// sum each of v[0..7] over the 32 lanes; on return lanes with (lane & 3) == 0 hold the total of component
+// ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1).
+__device__ __forceinline__ float butterfly8(const float (&v)[8], int lane) {
+    const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4;
+    float w[4], x[2];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const float keep = h16 ? v[i + 4] : v[i], send = h16 ? v[i] : v[i + 4];
+        w[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+        const float keep = h8 ? w[i + 2] : w[i], send = h8 ? w[i] : w[i + 2];
+        x[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+    float y = (h4 ? x[1] : x[0]) + __shfl_xor_sync(0xffffffffu, h4 ? x[0] : x[1], 4);
+    y += __shfl_xor_sync(0xffffffffu, y, 2);
+    y += __shfl_xor_sync(0xffffffffu, y, 1);
+    return y;
+}
+
+// C: rendered channels; CG: leading colour channels that need a gradient (GoMAvatar's 4th channel is the constant 1 that
+// renders alpha, gaussian.py:49); OPAC: dL/dopacity wanted (GoMAvatar: opacity == 1 without gradient, model.py:242).
+template <int C, int CG, bool OPAC>
+__global__ void __launch_bounds__(kBwdThreads) k_blend_bwd(BwdDev a) {
+    constexpr int NG = 5 + CG + (OPAC ? 1 : 0);            // mean2D.xy, conic A B C, colour[CG], (opacity)
+    __shared__ float2 s_xy[kBwdWarps][32];
+    __shared__ float4 s_co[kBwdWarps][32];
+    __shared__ __align__(16) float s_col[kBwdWarps][32 * C];
+    __shared__ uint32_t s_id[kBwdWarps][32];
+
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const long long gw = (long long)blockIdx.x * kBwdWarps + wib;      // global warp = (frame, tile, sub-block)
+    const int sub = (int)(gw & 7);
+    const long long ft = gw >> 3;
+    const int tile = (int)(ft % a.T), b = (int)(ft / a.T);
+    if (b >= a.B) return;
     const uint32_t *off = a.tile_offset + (long long)b * (a.T + 1);
     long long start = off[tile], end = off[tile + 1];
     if (start > a.cap) start = a.cap;
@@ -46,19 +78,15 @@ __global__ void __launch_bounds__(kThreads) k_blend_bwd(BwdDev a) {
     const int n = (int)(end - start);
     if (n == 0) return;
 
-    const int x = blockIdx.x * 16 + threadIdx.x, y = blockIdx.y * 16 + threadIdx.y;
+    const int tx = tile % a.gx, ty = tile / a.gx;
+    const int x0 = tx * 16 + (sub & 1) * 8, y0 = ty * 16 + (sub >> 1) * 4;
+    const int x = x0 + (lane & 7), y = y0 + (lane >> 3);
     const bool inside = x < a.W && y < a.H;
     const long long pix = ((long long)b * a.H + y) * a.W + x;
     const float T_final = inside ? a.final_T[pix] : 0.f;
     const uint32_t last_contributor = inside ? a.n_contrib[pix] : 0u;
-
-    if (tid == 0) s_max = 0u;
-    for (int i = tid; i < kThreads * NG; i += kThreads) s_grad[i] = 0.f;
-    __syncthreads();
-    if (last_contributor > 0) atomicMax(&s_max, last_contributor);
-    __syncthreads();
-    const int n_eff = min(n, (int)s_max);      // entries behind every pixel's last contributor are never visited
-    if (n_eff == 0) return;
+    const int n_eff = min(n, (int)__reduce_max_sync(0xffffffffu, last_contributor));
+    if (n_eff == 0) return;                    // entries behind every pixel's last contributor are never visited
 
     float dpix[C], accum_rec[C], last_color[C];
     float bg_dot = 0.f;
@@ -77,6 +105,7 @@ __global__ void __launch_bounds__(kThreads) k_blend_bwd(BwdDev a) {
     }
     float T = T_final, last_alpha = 0.f;
     const float pxf = (float)x, pyf = (float)y;
+    const float rcx = (float)x0 + 3.5f, rcy = (float)y0 + 1.5f;
     const float ddelx_dx = 0.5f * a.W, ddely_dy = 0.5f * a.H;
 
     const uint32_t *plist = a.point_list + (long long)b * a.cap + start;
@@ -88,25 +117,47 @@ __global__ void __launch_bounds__(kThreads) k_blend_bwd(BwdDev a) {
     float *o_opac = a.dL_dopacity ? a.dL_dopacity + (long long)b * a.P : nullptr;
     float *o_col = a.dL_dcolors + b * a.dL_dcolors_stride;
 
-    for (int hi = n_eff; hi > 0; hi -= kThreads) {
-        const int m = min(kThreads, hi);
-        __syncthreads();                                  // previous round's flush is complete
-        if (tid < m) {                                    // s_*[j] holds list entry hi-1-j (back to front)
-            const uint32_t id = plist[hi - 1 - tid];
-            s_id[tid] = id;
-            s_xy[tid] = gxy[id];
-            s_co[tid] = gco[id];
+    // destination of the component this lane ends up holding after butterfly8 (NG <= 8 path)
+    const int comp = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+    float *red_base = nullptr;
+    int red_stride = 0;
+    if ((lane & 3) == 0 && comp < NG) {
+        if (comp < 2) { red_base = o_mean2D + comp; red_stride = 2; }
+        else if (comp < 5) { red_base = o_conic + (comp - 2); red_stride = 3; }
+        else if (comp < 5 + CG) { red_base = o_col + (comp - 5); red_stride = C; }
+        else { red_base = o_opac; red_stride = 1; }
+    }
+
+    uint32_t id_c = 0; float2 xy_c = make_float2(0.f, 0.f); float4 co_c = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (n_eff - 1 - lane >= 0) { id_c = plist[n_eff - 1 - lane]; xy_c = __ldg(gxy + id_c); co_c = __ldg(gco + id_c); }
+    for (int hi = n_eff; hi > 0; hi -= 32) {               // lane j of a chunk holds list entry hi-1-j (back to front)
+        const bool rel = (hi - 1 - lane >= 0) && entry_reaches_rect(xy_c, co_c, rcx, rcy, 3.5f, 1.5f);
+        unsigned mask = __ballot_sync(0xffffffffu, rel);
+        if (rel) {
+            s_id[wib][lane] = id_c;
+            s_xy[wib][lane] = xy_c;
+            s_co[wib][lane] = co_c;
+            if constexpr (C == 4) {
+                reinterpret_cast<float4 *>(s_col[wib])[lane] = __ldg(reinterpret_cast<const float4 *>(gcol) + id_c);
+            } else {
 #pragma unroll
-            for (int ch = 0; ch < C; ch++) s_col[tid * C + ch] = gcol[(long long)id * C + ch];
+                for (int ch = 0; ch < C; ch++) s_col[wib][lane * C + ch] = __ldg(gcol + (long long)id_c * C + ch);
+            }
         }
-        __syncthreads();
-        for (int j = 0; j < m; j++) {
+        const int nidx = hi - 32 - 1 - lane;                // prefetch the next chunk
+        if (nidx >= 0) { id_c = plist[nidx]; xy_c = __ldg(gxy + id_c); co_c = __ldg(gco + id_c); }
+        __syncwarp();
+        while (mask) {
+            const int j = __ffs(mask) - 1;
+            mask &= mask - 1;
             const uint32_t k = (uint32_t)(hi - 1 - j);
             bool valid = k < last_contributor;
-            float g[NG];
+            float g[NG > 8 ? NG : 8];
+#pragma unroll
+            for (int c = 0; c < (NG > 8 ? NG : 8); c++) g[c] = 0.f;
             if (valid) {
-                const float2 c = s_xy[j];
-                const float4 co = s_co[j];
+                const float2 c = s_xy[wib][j];
+                const float4 co = s_co[wib][j];
                 const float dx = c.x - pxf, dy = c.y - pyf;
                 const float power = -0.5f * (co.x * dx * dx + co.z * dy * dy) - co.y * dx * dy;
                 const float G = __expf(power);
@@ -119,11 +170,11 @@ __global__ void __launch_bounds__(kThreads) k_blend_bwd(BwdDev a) {
                     float dL_dalpha = 0.f;
 #pragma unroll
                     for (int ch = 0; ch < C; ch++) {
-                        const float col = s_col[j * C + ch];
+                        const float col = s_col[wib][j * C + ch];
                         accum_rec[ch] = last_alpha * last_color[ch] + (1.f - last_alpha) * accum_rec[ch];
                         last_color[ch] = col;
                         dL_dalpha += (col - accum_rec[ch]) * dpix[ch];
-                        g[6 + ch] = dchannel_dcolor * dpix[ch];
+                        if (ch < CG) g[5 + ch] = dchannel_dcolor * dpix[ch];
                     }
                     dL_dalpha *= T;
                     last_alpha = alpha;
@@ -137,33 +188,28 @@ __global__ void __launch_bounds__(kThreads) k_blend_bwd(BwdDev a) {
                     g[2] = -0.5f * gdx * dx * dL_dG;
                     g[3] = -0.5f * gdx * dy * dL_dG;
                     g[4] = -0.5f * gdy * dy * dL_dG;
-                    g[5] = G * dL_dalpha;
+                    if (OPAC) g[5 + CG] = G * dL_dalpha;
                 }
             }
-            if (__ballot_sync(0xffffffffu, valid)) {
+            if (!__any_sync(0xffffffffu, valid)) continue;
+            const uint32_t id = s_id[wib][j];
+            if constexpr (NG <= 8) {
+                const float tot = butterfly8(g, lane);
+                if (red_base && tot != 0.f) atomicAdd(red_base + (long long)id * red_stride, tot);
+            } else {
 #pragma unroll
                 for (int c = 0; c < NG; c++) {
-                    const float v = warp_sum(valid ? g[c] : 0.f);
-                    if (lane == 0) atomicAdd(&s_grad[j * NG + c], v);
+                    const float tot = warp_sum(g[c]);
+                    if (lane == 0 && tot != 0.f) {
+                        float *dst = c < 2 ? o_mean2D + 2LL * id + c
+                                   : c < 5 ? o_conic + 3LL * id + (c - 2)
+                                   : c < 5 + CG ? o_col + (long long)id * C + (c - 5) : o_opac + id;
+                        atomicAdd(dst, tot);
+                    }
                 }
             }
         }
-        __syncthreads();
-        if (tid < m) {                                    // one global atomic per (tile, Gaussian, component)
-            const uint32_t id = s_id[tid];
-            float *sg = &s_grad[tid * NG];
-            if (sg[0] != 0.f) atomicAdd(o_mean2D + 2LL * id, sg[0]);
-            if (sg[1] != 0.f) atomicAdd(o_mean2D + 2LL * id + 1, sg[1]);
-            if (sg[2] != 0.f) atomicAdd(o_conic + 3LL * id, sg[2]);
-            if (sg[3] != 0.f) atomicAdd(o_conic + 3LL * id + 1, sg[3]);
-            if (sg[4] != 0.f) atomicAdd(o_conic + 3LL * id + 2, sg[4]);
-            if (o_opac && sg[5] != 0.f) atomicAdd(o_opac + id, sg[5]);
-#pragma unroll
-            for (int ch = 0; ch < C; ch++)
-                if (sg[6 + ch] != 0.f) atomicAdd(o_col + (long long)id * C + ch, sg[6 + ch]);
-#pragma unroll
-            for (int c = 0; c < NG; c++) sg[c] = 0.f;
-        }
+        __syncwarp();
     }
 }
 
@@ -254,6 +300,10 @@ extern "C" int gom_raster_backward(const GomRasterBwdArgs *p, gom_stream_t strea
                     p->dL_dout, "null saved state");
     GOM_REQUIRE(p->dL_dmeans3D && p->dL_dcov3D && p->dL_dcolors && p->dL_dmeans2D && p->dL_dconic, "null output");
     GOM_REQUIRE(((uintptr_t)p->cov3D % 8) == 0 && (p->cov3D_stride % 2) == 0, "cov3D must be 8-byte aligned");
+    GOM_REQUIRE(p->n_channels != 4 || (((uintptr_t)p->colors % 16) == 0 && (p->colors_stride % 4) == 0), "4-channel colors must be 16-byte aligned");
+    GOM_REQUIRE(p->color_grad_channels == 0 || p->color_grad_channels == p->n_channels ||
+                    (p->n_channels == 4 && p->color_grad_channels == 3), "color_grad_channels must be 0, n_channels, or 3 of 4");
+    GOM_REQUIRE((long long)p->n_frames * (((p->width + 15) / 16) * ((p->height + 15) / 16)) * 8 / kBwdWarps < 0x7fffffffLL, "grid too large");
     cudaStream_t stream = (cudaStream_t)stream_;
     BwdDev a;
     a.B = p->n_frames; a.P = p->n_gauss; a.H = p->height; a.W = p->width; a.C = p->n_channels;
@@ -279,10 +329,16 @@ extern "C" int gom_raster_backward(const GomRasterBwdArgs *p, gom_stream_t strea
         GOM_CUDA(cudaMemsetAsync(a.dL_dconic, 0, sizeof(float) * 3 * BP, stream));
         GOM_CUDA(cudaMemsetAsync(a.dL_dcolors, 0, sizeof(float) * ncol, stream));
         if (a.dL_dopacity) GOM_CUDA(cudaMemsetAsync(a.dL_dopacity, 0, sizeof(float) * BP, stream));
-        dim3 bgrid(a.gx, a.gy, a.B), bblock(16, 16);
+        const long long n_warps = (long long)a.B * a.T * 8;
+        const unsigned bgrid = (unsigned)((n_warps + kBwdWarps - 1) / kBwdWarps);
+        const int cg = p->color_grad_channels > 0 ? p->color_grad_channels : a.C;
+        const bool opac = a.dL_dopacity != nullptr;
         gom_prof_begin(GOM_PROF_BLEND_BWD, stream);
-        if (a.C == 3) k_blend_bwd<3><<<bgrid, bblock, 0, stream>>>(a);
-        else k_blend_bwd<4><<<bgrid, bblock, 0, stream>>>(a);
+        if (a.C == 3 && !opac) k_blend_bwd<3, 3, false><<<bgrid, kBwdThreads, 0, stream>>>(a);
+        else if (a.C == 3) k_blend_bwd<3, 3, true><<<bgrid, kBwdThreads, 0, stream>>>(a);
+        else if (cg == 3 && !opac) k_blend_bwd<4, 3, false><<<bgrid, kBwdThreads, 0, stream>>>(a);
+        else if (!opac) k_blend_bwd<4, 4, false><<<bgrid, kBwdThreads, 0, stream>>>(a);
+        else k_blend_bwd<4, 4, true><<<bgrid, kBwdThreads, 0, stream>>>(a);
         GOM_LAUNCH_CHECK();
         gom_prof_end(GOM_PROF_BLEND_BWD, stream);
         dim3 grid(gom_div_up(a.P, kThreads), a.B);

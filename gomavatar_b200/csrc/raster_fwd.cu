@@ -192,12 +192,18 @@ __device__ void block_sort(unsigned long long *k, int n, int tid) {
 }
 
 // ------------------------------------------------------------------------ App. A.5: per-tile depth sort + blend
+// One 256-thread block per tile sorts the tile's keys (shared memory), then its 8 warps blend INDEPENDENTLY: warp w
+// owns the 8x4-pixel sub-block (w & 1, w >> 1) and walks the sorted list in chunks of 32 entries — one entry per lane
+// is fetched and tested against the sub-block (entry_reaches_rect), survivors are staged in the warp's own shared
+// memory slots and visited through the ballot mask.  No block barrier after the sort: a warp whose 32 pixels are
+// saturated stops, the next chunk's records are prefetched while the current one is blended.
 template <int C>
 __global__ void __launch_bounds__(kThreads) k_sort_blend(FwdDev a) {
+    constexpr int kWarps = kThreads / 32;
     __shared__ unsigned long long skeys[kSortCap];
-    __shared__ float2 s_xy[kThreads];
-    __shared__ float4 s_co[kThreads];
-    __shared__ float s_col[kThreads * C];
+    __shared__ float2 s_xy[kWarps][32];
+    __shared__ float4 s_co[kWarps][32];
+    __shared__ __align__(16) float s_col[kWarps][32 * C];
 
     const int b = blockIdx.z;
     const int tile = blockIdx.y * a.gx + blockIdx.x;
@@ -219,9 +225,12 @@ __global__ void __launch_bounds__(kThreads) k_sort_blend(FwdDev a) {
     uint32_t *plist = a.point_list + (long long)b * a.cap + start;
     for (int i = tid; i < n; i += kThreads) plist[i] = (uint32_t)sk[i];
 
-    const int x = blockIdx.x * 16 + threadIdx.x, y = blockIdx.y * 16 + threadIdx.y;
+    const int lane = tid & 31, wib = tid >> 5;
+    const int x0 = blockIdx.x * 16 + (wib & 1) * 8, y0 = blockIdx.y * 16 + (wib >> 1) * 4;
+    const int x = x0 + (lane & 7), y = y0 + (lane >> 3);
     const bool inside = x < a.W && y < a.H;
     const float pxf = (float)x, pyf = (float)y;
+    const float rcx = (float)x0 + 3.5f, rcy = (float)y0 + 1.5f;
     const float2 *gxy = a.xy + (long long)b * a.P;
     const float4 *gco = a.conic_opacity + (long long)b * a.P;
     const float *gcol = a.colors + b * a.colors_stride;
@@ -231,24 +240,33 @@ __global__ void __launch_bounds__(kThreads) k_sort_blend(FwdDev a) {
     float acc[C];
 #pragma unroll
     for (int ch = 0; ch < C; ch++) acc[ch] = 0.f;
-    uint32_t contributor = 0, last = 0;
+    uint32_t last = 0;
 
-    for (int base = 0; base < n; base += kThreads) {
-        if (__syncthreads_count(done) == kThreads) break;
-        const int idx = base + tid;
-        if (idx < n) {
-            const uint32_t id = (uint32_t)sk[idx];
-            s_xy[tid] = gxy[id];
-            s_co[tid] = gco[id];
+    uint32_t id_c = 0; float2 xy_c = make_float2(0.f, 0.f); float4 co_c = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (lane < n) { id_c = (uint32_t)sk[lane]; xy_c = __ldg(gxy + id_c); co_c = __ldg(gco + id_c); }
+    for (int base = 0; base < n; base += 32) {
+        if (__all_sync(0xffffffffu, done)) break;
+        const bool rel = (base + lane < n) && entry_reaches_rect(xy_c, co_c, rcx, rcy, 3.5f, 1.5f);
+        unsigned mask = __ballot_sync(0xffffffffu, rel);
+        if (rel) {
+            s_xy[wib][lane] = xy_c;
+            s_co[wib][lane] = co_c;
+            if constexpr (C == 4) {
+                reinterpret_cast<float4 *>(s_col[wib])[lane] = __ldg(reinterpret_cast<const float4 *>(gcol) + id_c);
+            } else {
 #pragma unroll
-            for (int ch = 0; ch < C; ch++) s_col[tid * C + ch] = gcol[(long long)id * C + ch];
+                for (int ch = 0; ch < C; ch++) s_col[wib][lane * C + ch] = __ldg(gcol + (long long)id_c * C + ch);
+            }
         }
-        __syncthreads();
-        const int m = min(kThreads, n - base);
-        for (int j = 0; !done && j < m; j++) {
-            contributor++;
-            const float2 c = s_xy[j];
-            const float4 co = s_co[j];
+        const int nidx = base + 32 + lane;                 // prefetch the next chunk while this one is blended
+        if (nidx < n) { id_c = (uint32_t)sk[nidx]; xy_c = __ldg(gxy + id_c); co_c = __ldg(gco + id_c); }
+        __syncwarp();
+        while (mask) {
+            const int j = __ffs(mask) - 1;
+            mask &= mask - 1;
+            if (done) continue;
+            const float2 c = s_xy[wib][j];
+            const float4 co = s_co[wib][j];
             const float dx = c.x - pxf, dy = c.y - pyf;
             const float power = -0.5f * (co.x * dx * dx + co.z * dy * dy) - co.y * dx * dy;
             if (power > 0.0f) continue;
@@ -258,10 +276,11 @@ __global__ void __launch_bounds__(kThreads) k_sort_blend(FwdDev a) {
             if (test_T < 0.0001f) { done = true; continue; }
             const float w = alpha * T;
 #pragma unroll
-            for (int ch = 0; ch < C; ch++) acc[ch] += s_col[j * C + ch] * w;
+            for (int ch = 0; ch < C; ch++) acc[ch] += s_col[wib][j * C + ch] * w;
             T = test_T;
-            last = contributor;
+            last = (uint32_t)(base + j + 1);
         }
+        __syncwarp();
     }
     if (inside) {
         const long long pix = ((long long)b * a.H + y) * a.W + x;
@@ -300,6 +319,7 @@ extern "C" int gom_raster_forward(const GomRasterFwdArgs *p, gom_stream_t stream
                     p->status, "null output/state");
     GOM_REQUIRE(((uintptr_t)p->cov3D % 8) == 0 && (p->cov3D_stride % 2) == 0, "cov3D must be 8-byte aligned");
     GOM_REQUIRE(!(p->interleaved && p->n_channels == 4) || ((uintptr_t)p->out_color % 16) == 0, "out_color alignment");
+    GOM_REQUIRE(p->n_channels != 4 || (((uintptr_t)p->colors % 16) == 0 && (p->colors_stride % 4) == 0), "4-channel colors must be 16-byte aligned");
     cudaStream_t stream = (cudaStream_t)stream_;
     FwdDev a;
     a.B = p->n_frames; a.P = p->n_gauss; a.H = p->height; a.W = p->width; a.C = p->n_channels;

@@ -127,7 +127,8 @@ class Model(nn.Module):
         bg = torch.cat([bg_feat, bg_feat.new_zeros(1)])[None].expand(B, 4)
         aux = {}
         rgba, radii, final_T, _ = rasterize_gaussians(means3D, cov3D, colors, opacity, view, proj, tanfov, bg, H, W,
-                                                      interleaved=True, strict=self.strict_raster, aux=aux)
+                                                      interleaved=True, strict=self.strict_raster, aux=aux,
+                                                      color_grad_channels=3)
         self.last_raster_aux = aux
         albedos, masks = rgba[..., :3], rgba[..., 3]
 

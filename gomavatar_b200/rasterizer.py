@@ -41,7 +41,7 @@ class _Rasterize(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, means3D, cov3D, colors, opacities, means2D, view, proj, tanfov, bg, H, W, interleaved, strict,
-                capacity, aux):
+                capacity, aux, color_grad_channels=0):
         L = _lib.lib()
         dev = means3D.device
         if dev.type != "cuda":
@@ -80,6 +80,7 @@ class _Rasterize(torch.autograd.Function):
                 continue
             break
         ctx.dims = (B, P, H, W, C, bool(interleaved), cap, shared_colors)
+        ctx.color_grad_channels = int(color_grad_channels or 0)
         ctx.has_means2D = means2D is not None
         ctx.save_for_backward(m3, c3, col, view, proj, tanfov, bg, st["final_T"], st["n_contrib"], st["radii"],
                               st["xy"], st["conic_opacity"], st["tile_offset"], st["point_list"])
@@ -105,6 +106,7 @@ class _Rasterize(torch.autograd.Function):
         d_mean2D, d_conic = e(B, P, 2), e(B, P, 3)
         a = GomRasterBwdArgs(
             n_frames=B, n_gauss=P, height=H, width=W, n_channels=C, interleaved=int(interleaved), inst_capacity=cap,
+            color_grad_channels=ctx.color_grad_channels,
             means3D=ptr(m3), means3D_stride=P * 3, cov3D=ptr(c3), cov3D_stride=P * 6,
             colors=ptr(col), colors_stride=0 if shared_colors else P * C,
             viewmatrix=ptr(view), projmatrix=ptr(proj), tanfov=ptr(tanfov), bg=ptr(bg),
@@ -117,20 +119,24 @@ class _Rasterize(torch.autograd.Function):
         g_means2D = None
         if ctx.has_means2D and ctx.needs_input_grad[4]:
             g_means2D = torch.cat([d_mean2D, torch.zeros_like(d_mean2D[..., :1])], dim=-1)
-        return (d_means3D, d_cov3D, d_colors, d_op, g_means2D) + (None,) * 10
+        return (d_means3D, d_cov3D, d_colors, d_op, g_means2D) + (None,) * 11
 
 
 def rasterize_gaussians(means3D, cov3D, colors, opacities, viewmatrix, projmatrix, tanfov, bg, image_height,
-                        image_width, means2D=None, interleaved=False, strict=True, capacity=None, aux=None):
+                        image_width, means2D=None, interleaved=False, strict=True, capacity=None, aux=None,
+                        color_grad_channels=0):
     """Batched differentiable splatting of B frames in one launch sequence.
 
     means3D [B,P,3], cov3D [B,P,6] (xx,xy,xz,yy,yz,zz), colors [P,C] (shared by all frames) or [B,P,C] with C in
     {3,4}, opacities [B,P]; viewmatrix/projmatrix [B,4,4] exactly as the reference builds them (E^T, E^T K_ndc^T);
     tanfov [B,2]; bg [B,C].  Returns (color [B,C,H,W] or [B,H,W,C] if interleaved, radii [B,P] int32,
     final_T [B,H,W], n_contrib [B,H,W]).  ``aux`` (a dict) receives every intermediate buffer.
+    ``color_grad_channels=3`` with 4-channel colours skips the gradient of the 4th channel (GoMAvatar renders alpha with
+    a constant-1 "colour", reference gaussian.py:49), which puts the backward on its 8-component fast path.
     """
     return _Rasterize.apply(means3D, cov3D, colors, opacities, means2D, viewmatrix, projmatrix, tanfov, bg,
-                            int(image_height), int(image_width), bool(interleaved), bool(strict), capacity, aux)
+                            int(image_height), int(image_width), bool(interleaved), bool(strict), capacity, aux,
+                            int(color_grad_channels or 0))
 
 
 # ----------------------------------------------------------------------------------------------------------------

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define GOM_ABI_VERSION 1
+#define GOM_ABI_VERSION 2
 #define GOM_TILE 16              /* 16x16-pixel tiles, as upstream's BLOCK_X/BLOCK_Y */
 #define GOM_MAX_CHANNELS 4
 #define GOM_MAX_JOINTS 64
@@ -119,6 +119,8 @@ int gom_raster_forward(const GomRasterFwdArgs *a, gom_stream_t stream);
 typedef struct {
     int32_t n_frames, n_gauss, height, width;
     int32_t n_channels, interleaved;
+    int32_t color_grad_channels; /* 0 = all; 3 with n_channels 4: the 4th (constant alpha) channel gets no gradient (left 0) */
+    int32_t _pad;
     int64_t inst_capacity;
     const float *means3D;   int64_t means3D_stride;
     const float *cov3D;     int64_t cov3D_stride;

@@ -153,6 +153,37 @@ def test_backward_parity(n_faces, img, B, C):
     assert np.abs(got - ref_col).max() <= 1e-3 * np.abs(ref_col).max()
 
 
+@pytest.mark.parametrize("n_faces,img,B", [(2000, 64, 2), (4000, (200, 136), 2), (30000, 512, 2)])
+def test_backward_fast_path_rgb_only_no_opacity_grad(n_faces, img, B):
+    """The path Model.forward takes: RGBA render, gradient for the three colour channels only, opacity without gradient
+    (8 gradient components per Gaussian -> transposing butterfly + one RED per component)."""
+    from gomavatar_b200.rasterizer import rasterize_gaussians
+    d = raster_inputs(n_faces=n_faces, img=img, n_frames=B, channels=4)
+    c = _cuda(d)
+    H, W = d["H"], d["W"]
+    m = c["means3D"].clone().requires_grad_(True)
+    cv = c["cov6"].clone().requires_grad_(True)
+    col = c["colors"].clone().requires_grad_(True)
+    color, _, _, _ = rasterize_gaussians(m, cv, col, c["opacity"], c["view"], c["proj"], c["tanfov"], c["bg"], H, W,
+                                         interleaved=True, color_grad_channels=3)
+    rng = np.random.default_rng(13)
+    dL = rng.normal(size=(B, 4, H, W)).astype(np.float32)
+    (color * torch.from_numpy(np.ascontiguousarray(dL.transpose(0, 2, 3, 1))).cuda()).sum().backward()
+    torch.cuda.synchronize()
+    ref_col = np.zeros_like(d["colors"])
+    for b in range(B):
+        o = _oracle(d, b)
+        g = R.backward(o, dL[b])
+        ref_col += g["colors"]
+        for name, got, ref in (("means3D", m.grad[b], g["means3D"]), ("cov6", cv.grad[b], g["cov6"])):
+            got = got.cpu().numpy()
+            scale = np.abs(ref).max()
+            assert np.abs(got - ref).max() <= 1e-3 * scale, (name, b, np.abs(got - ref).max() / scale)
+    got = col.grad.cpu().numpy()
+    assert np.abs(got[:, :3] - ref_col[:, :3]).max() <= 1e-3 * np.abs(ref_col).max()
+    assert float(np.abs(got[:, 3]).max()) == 0.0
+
+
 def test_reference_api_shim_matches_two_pass_reference_usage():
     """Call pattern of reference models/modules/renderer/gaussian.py:53-100 through the drop-in module."""
     from diff_gaussian_rasterization import GaussianRasterizationSettings, GaussianRasterizer
