@@ -72,68 +72,67 @@ struct TapDev {
     float *d_pre;               // [B,h,w,C]
 };
 
-template <int C> struct Lanes {
-    static constexpr int CPL = C / 32;                   // channels per lane
-    static constexpr int VW = CPL < 4 ? CPL : 4;         // vector width of one load
-    static constexpr int NV = CPL / VW;                  // loads per pixel per lane
+// Lane layout: a pixel's C channels are spread over LPP = min(32, C/4) lanes with 16-byte loads, so a warp holds
+// PPW = 32/LPP pixels at once (C = 64: two pixels per warp, the quad in NIT = 2 iterations) and channel sums are
+// xor-shuffles inside the LPP-lane group.  Register r of a lane is channel (r/4)*4*LPP + 4*sl + r%4, sl = lane % LPP.
+template <int C> struct TL {
+    static_assert(C % 32 == 0 && C >= 32, "channels must be a multiple of 32");
+    static constexpr int LPP = C / 4 < 32 ? C / 4 : 32;  // lanes per pixel
+    static constexpr int PPW = 32 / LPP;                 // pixels per warp (1, 2 or 4)
+    static constexpr int CPL = C / LPP;                  // channels per lane (4, 8 or 16)
+    static constexpr int NV = CPL / 4;                   // float4 loads per pixel per lane
+    static constexpr int NIT = 4 / PPW;                  // iterations to cover a 2x2 quad
 };
 
-// channel index of register r of this lane
-template <int C> __device__ __forceinline__ int chan_of(int lane, int r) {
-    using L = Lanes<C>;
-    return (r / L::VW) * 32 * L::VW + lane * L::VW + (r % L::VW);
-}
-
-template <int C> __device__ __forceinline__ void load_px(const float *p, int lane, float (&f)[Lanes<C>::CPL]) {
-    using L = Lanes<C>;
+template <int C> __device__ __forceinline__ void load_px(const float *p, int sl, float (&f)[TL<C>::CPL]) {
+    using L = TL<C>;
 #pragma unroll
     for (int k = 0; k < L::NV; k++) {
-        const float *q = p + k * 32 * L::VW + lane * L::VW;
-        if constexpr (L::VW == 4) {
-            const float4 v = *reinterpret_cast<const float4 *>(q);
-            f[4 * k] = v.x; f[4 * k + 1] = v.y; f[4 * k + 2] = v.z; f[4 * k + 3] = v.w;
-        } else if constexpr (L::VW == 2) {
-            const float2 v = *reinterpret_cast<const float2 *>(q);
-            f[2 * k] = v.x; f[2 * k + 1] = v.y;
-        } else {
-            f[k] = *q;
-        }
+        const float4 v = *reinterpret_cast<const float4 *>(p + k * 4 * L::LPP + 4 * sl);
+        f[4 * k] = v.x; f[4 * k + 1] = v.y; f[4 * k + 2] = v.z; f[4 * k + 3] = v.w;
     }
 }
 
-template <int C> __device__ __forceinline__ void store_px(float *p, int lane, const float (&f)[Lanes<C>::CPL]) {
-    using L = Lanes<C>;
+template <int C> __device__ __forceinline__ void store_px(float *p, int sl, const float (&f)[TL<C>::CPL]) {
+    using L = TL<C>;
 #pragma unroll
-    for (int k = 0; k < L::NV; k++) {
-        float *q = p + k * 32 * L::VW + lane * L::VW;
-        if constexpr (L::VW == 4) *reinterpret_cast<float4 *>(q) = make_float4(f[4 * k], f[4 * k + 1], f[4 * k + 2], f[4 * k + 3]);
-        else if constexpr (L::VW == 2) *reinterpret_cast<float2 *>(q) = make_float2(f[2 * k], f[2 * k + 1]);
-        else *q = f[k];
-    }
+    for (int k = 0; k < L::NV; k++)
+        *reinterpret_cast<float4 *>(p + k * 4 * L::LPP + 4 * sl) = make_float4(f[4 * k], f[4 * k + 1], f[4 * k + 2], f[4 * k + 3]);
 }
 
-__device__ __forceinline__ void warp_sum2(float &a, float &b) {
+template <int C> __device__ __forceinline__ void load_lin(const float *lin, int sl, float (&f)[TL<C>::CPL]) {
+    using L = TL<C>;
 #pragma unroll
-    for (int d = 16; d > 0; d >>= 1) {
+    for (int r = 0; r < L::CPL; r++) f[r] = __ldg(lin + (r / 4) * 4 * L::LPP + 4 * sl + (r % 4));
+}
+
+template <int LPP> __device__ __forceinline__ void group_sum2(float &a, float &b) {
+#pragma unroll
+    for (int d = LPP / 2; d > 0; d >>= 1) {
         a += __shfl_xor_sync(0xffffffffu, a, d);
         b += __shfl_xor_sync(0xffffffffu, b, d);
     }
+}
+template <int LPP> __device__ __forceinline__ float group_sum(float a) {
+#pragma unroll
+    for (int d = LPP / 2; d > 0; d >>= 1) a += __shfl_xor_sync(0xffffffffu, a, d);
+    return a;
 }
 
 // Forward: per (prediction, target) pair and pixel  d = sum_c lin_c (f0_c/(n0+eps) - f1_c/(n1+eps))^2,
 // n = sqrt(sum_c f_c^2 + eps); layer_sums[b] += mean over pixels; optionally the 2x2/2 max-pool of BOTH halves.
 template <int C>
 __global__ void __launch_bounds__(kThreads) k_lpips_tap_fwd(TapDev a) {
-    using L = Lanes<C>;
+    using L = TL<C>;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int grp = lane / L::LPP, sl = lane % L::LPP;
     const int b = blockIdx.y;
     const int qw = (a.w + 1) >> 1, qh = (a.h + 1) >> 1, nq = qw * qh;
     const int ph = a.h >> 1, pw = a.w >> 1;
     const long long img = (long long)a.h * a.w * C;
     const float *F0 = a.feats + (long long)b * img, *F1 = a.feats + (long long)(b + a.B) * img;
     float lin[L::CPL];
-#pragma unroll
-    for (int r = 0; r < L::CPL; r++) lin[r] = __ldg(a.lin + chan_of<C>(lane, r));
+    load_lin<C>(a.lin, sl, lin);
     float acc = 0.f;
     for (int q = blockIdx.x * kWarps + wid; q < nq; q += gridDim.x * kWarps) {
         const int qy = q / qw, qx = q - qy * qw;
@@ -141,20 +140,26 @@ __global__ void __launch_bounds__(kThreads) k_lpips_tap_fwd(TapDev a) {
 #pragma unroll
         for (int r = 0; r < L::CPL; r++) { m0[r] = -INFINITY; m1[r] = -INFINITY; }
 #pragma unroll
-        for (int s = 0; s < 4; s++) {
+        for (int it = 0; it < L::NIT; it++) {
+            const int s = it * L::PPW + grp;
             const int y = 2 * qy + (s >> 1), x = 2 * qx + (s & 1);
-            if (y >= a.h || x >= a.w) continue;                   // warp-uniform
+            const bool ok = y < a.h && x < a.w;
             const long long o = ((long long)y * a.w + x) * C;
             float f0[L::CPL], f1[L::CPL];
-            load_px<C>(F0 + o, lane, f0);
-            load_px<C>(F1 + o, lane, f1);
+            if (ok) {
+                load_px<C>(F0 + o, sl, f0);
+                load_px<C>(F1 + o, sl, f1);
+            } else {
+#pragma unroll
+                for (int r = 0; r < L::CPL; r++) { f0[r] = 0.f; f1[r] = 0.f; }
+            }
             float s0 = 0.f, s1 = 0.f;
 #pragma unroll
             for (int r = 0; r < L::CPL; r++) {
                 s0 += f0[r] * f0[r]; s1 += f1[r] * f1[r];
-                m0[r] = fmaxf(m0[r], f0[r]); m1[r] = fmaxf(m1[r], f1[r]);
+                if (ok) { m0[r] = fmaxf(m0[r], f0[r]); m1[r] = fmaxf(m1[r], f1[r]); }
             }
-            warp_sum2(s0, s1);
+            group_sum2<L::LPP>(s0, s1);
             const float i0 = 1.f / (sqrtf(s0 + kEps) + kEps), i1 = 1.f / (sqrtf(s1 + kEps) + kEps);
             float d = 0.f;
 #pragma unroll
@@ -162,12 +167,22 @@ __global__ void __launch_bounds__(kThreads) k_lpips_tap_fwd(TapDev a) {
                 const float t = f0[r] * i0 - f1[r] * i1;
                 d += lin[r] * t * t;
             }
-            acc += d;                                             // reduced across lanes once, at the end
+            if (ok) acc += d;                                     // reduced across lanes once, at the end
         }
-        if (a.pool && qy < ph && qx < pw) {
-            const long long po = ((long long)qy * pw + qx) * C, pimg = (long long)ph * pw * C;
-            store_px<C>(a.pooled + (long long)b * pimg + po, lane, m0);
-            store_px<C>(a.pooled + (long long)(b + a.B) * pimg + po, lane, m1);
+        if (a.pool && qy < ph && qx < pw) {                       // warp-uniform; all four pixels exist
+#pragma unroll
+            for (int dlt = L::LPP; dlt < 32; dlt <<= 1) {
+#pragma unroll
+                for (int r = 0; r < L::CPL; r++) {
+                    m0[r] = fmaxf(m0[r], __shfl_xor_sync(0xffffffffu, m0[r], dlt));
+                    m1[r] = fmaxf(m1[r], __shfl_xor_sync(0xffffffffu, m1[r], dlt));
+                }
+            }
+            if (grp == 0) {
+                const long long po = ((long long)qy * pw + qx) * C, pimg = (long long)ph * pw * C;
+                store_px<C>(a.pooled + (long long)b * pimg + po, sl, m0);
+                store_px<C>(a.pooled + (long long)(b + a.B) * pimg + po, sl, m1);
+            }
         }
     }
     __shared__ float sh[kWarps];
@@ -186,8 +201,9 @@ __global__ void __launch_bounds__(kThreads) k_lpips_tap_fwd(TapDev a) {
 //   [ dval_b * d(mean d)/df0  +  max-pool backward of d_pooled (first maximum in scan order, as torch) ] * (f0 > 0)
 template <int C>
 __global__ void __launch_bounds__(kThreads) k_lpips_tap_bwd(TapDev a) {
-    using L = Lanes<C>;
+    using L = TL<C>;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int grp = lane / L::LPP, sl = lane % L::LPP;
     const int b = blockIdx.y;
     const int qw = (a.w + 1) >> 1, qh = (a.h + 1) >> 1, nq = qw * qh;
     const int ph = a.h >> 1, pw = a.w >> 1;
@@ -196,59 +212,73 @@ __global__ void __launch_bounds__(kThreads) k_lpips_tap_bwd(TapDev a) {
     float *G = a.d_pre + (long long)b * img;
     const float kscale = 2.f * a.dval[b] / (float)((long long)a.h * a.w);
     float lin[L::CPL];
-#pragma unroll
-    for (int r = 0; r < L::CPL; r++) lin[r] = __ldg(a.lin + chan_of<C>(lane, r));
+    load_lin<C>(a.lin, sl, lin);
     for (int q = blockIdx.x * kWarps + wid; q < nq; q += gridDim.x * kWarps) {
         const int qy = q / qw, qx = q - qy * qw;
-        const bool pooled = a.pool && a.d_pooled && qy < ph && qx < pw;      // quad complete => all 4 pixels valid
+        const bool pooled = a.pool && a.d_pooled && qy < ph && qx < pw;      // warp-uniform; quad complete
+        float f0[L::NIT][L::CPL];
+        bool ok[L::NIT];
+#pragma unroll
+        for (int it = 0; it < L::NIT; it++) {
+            const int s = it * L::PPW + grp;
+            const int y = 2 * qy + (s >> 1), x = 2 * qx + (s & 1);
+            ok[it] = y < a.h && x < a.w;
+            if (ok[it]) load_px<C>(F0 + ((long long)y * a.w + x) * C, sl, f0[it]);
+            else {
+#pragma unroll
+                for (int r = 0; r < L::CPL; r++) f0[it][r] = 0.f;
+            }
+        }
+        // which of the quad's four pixels (scan order s = 0..3) holds the FIRST maximum of each channel
         float gp[L::CPL];
-        uint32_t am[L::CPL > 16 ? 2 : 1] = {};                               // 2-bit arg-max position per channel
+        uint32_t am = 0;                                                     // 2 bits per register
         if (pooled) {
-            load_px<C>(a.d_pooled + ((long long)b * ph * pw + (long long)qy * pw + qx) * C, lane, gp);
-            float best[L::CPL];
+            load_px<C>(a.d_pooled + ((long long)b * ph * pw + (long long)qy * pw + qx) * C, sl, gp);
 #pragma unroll
-            for (int s = 0; s < 4; s++) {
-                float f[L::CPL];
-                load_px<C>(F0 + ((long long)(2 * qy + (s >> 1)) * a.w + 2 * qx + (s & 1)) * C, lane, f);
+            for (int r = 0; r < L::CPL; r++) {
+                float best = 0.f;
+                uint32_t arg = 0;
 #pragma unroll
-                for (int r = 0; r < L::CPL; r++) {
-                    if (s == 0) best[r] = f[r];
-                    else if (f[r] > best[r] || f[r] != f[r]) {               // strict: the first maximum wins (NaN propagates)
-                        best[r] = f[r];
-                        am[r >> 4] = (am[r >> 4] & ~(3u << (2 * (r & 15)))) | ((uint32_t)s << (2 * (r & 15)));
-                    }
+                for (int s = 0; s < 4; s++) {
+                    const float own = f0[s / L::PPW][r];
+                    const float v = L::PPW == 1 ? own : __shfl_sync(0xffffffffu, own, (s % L::PPW) * L::LPP + sl);
+                    if (s == 0 || v > best || v != v) { best = v; arg = s; }   // strict: the first maximum wins
                 }
+                am |= arg << (2 * r);
             }
         }
 #pragma unroll
-        for (int s = 0; s < 4; s++) {
+        for (int it = 0; it < L::NIT; it++) {
+            const int s = it * L::PPW + grp;
             const int y = 2 * qy + (s >> 1), x = 2 * qx + (s & 1);
-            if (y >= a.h || x >= a.w) continue;
             const long long o = ((long long)y * a.w + x) * C;
-            float f0[L::CPL], f1[L::CPL];
-            load_px<C>(F0 + o, lane, f0);                         // second touch of the quad: L1/L2 hit
-            load_px<C>(F1 + o, lane, f1);
+            float f1[L::CPL];
+            if (ok[it]) load_px<C>(F1 + o, sl, f1);
+            else {
+#pragma unroll
+                for (int r = 0; r < L::CPL; r++) f1[r] = 0.f;
+            }
             float s0 = 0.f, s1 = 0.f;
 #pragma unroll
-            for (int r = 0; r < L::CPL; r++) { s0 += f0[r] * f0[r]; s1 += f1[r] * f1[r]; }
-            warp_sum2(s0, s1);
+            for (int r = 0; r < L::CPL; r++) { s0 += f0[it][r] * f0[it][r]; s1 += f1[r] * f1[r]; }
+            group_sum2<L::LPP>(s0, s1);
             const float n0 = sqrtf(s0 + kEps), i0 = 1.f / (n0 + kEps), i1 = 1.f / (sqrtf(s1 + kEps) + kEps);
             float e[L::CPL], dot = 0.f;
 #pragma unroll
             for (int r = 0; r < L::CPL; r++) {
-                e[r] = kscale * lin[r] * (f0[r] * i0 - f1[r] * i1);
-                dot += e[r] * f0[r];
+                e[r] = kscale * lin[r] * (f0[it][r] * i0 - f1[r] * i1);
+                dot += e[r] * f0[it][r];
             }
-            dot = warp_sum(dot);
+            dot = group_sum<L::LPP>(dot);
             const float k2 = dot * i0 * i0 / n0;
             float g[L::CPL];
 #pragma unroll
             for (int r = 0; r < L::CPL; r++) {
-                float v = e[r] * i0 - k2 * f0[r];
-                if (pooled && ((am[r >> 4] >> (2 * (r & 15))) & 3u) == (uint32_t)s) v += gp[r];
-                g[r] = f0[r] > 0.f ? v : 0.f;
+                float v = e[r] * i0 - k2 * f0[it][r];
+                if (pooled && ((am >> (2 * r)) & 3u) == (uint32_t)s) v += gp[r];
+                g[r] = f0[it][r] > 0.f ? v : 0.f;
             }
-            store_px<C>(G + o, lane, g);
+            if (ok[it]) store_px<C>(G + o, sl, g);
         }
     }
 }
