@@ -190,20 +190,71 @@ class Trainer:
         sl = slice(s, s + self.B)
         return self._train({k: v[sl] for k, v in self.devd.items()}, self.tgt_rgb[sl], self.tgt_mask[sl])
 
+    # ---- end-to-end step: host buffers in, loss out, every step.  The input pipeline is the usual double-buffered one:
+    # while step i computes, step i+1's batch (pinned host memory) is copied on a side stream into the other buffer
+    # set, and the loss of step i-1 is read back (pinned, event-synchronised) so the host can run one step ahead.
+    def _e2e_setup(self):
+        if getattr(self, "_e2e_ready", False):
+            return
+        self.copy_stream = torch.cuda.Stream(device=self.dev)
+        mk = lambda v: torch.empty((self.B,) + tuple(v.shape[1:]), dtype=v.dtype, device=self.dev)
+        self.e2e_bufs = [({k: mk(v) for k, v in self.host.items()}, mk(self.host_tgt_rgb), mk(self.host_tgt_mask)) for _ in range(2)]
+        self.e2e_ready_ev = [torch.cuda.Event(), torch.cuda.Event()]           # batch has landed in buffer set s
+        self.e2e_done_ev = [None, None]                                        # compute that used buffer set s has finished
+        self.loss_host = [torch.zeros((), dtype=torch.float32).pin_memory() for _ in range(2)]
+        self.loss_ev = [None, None]
+        self.e2e_prefetched = None
+        self.losses_read = 0
+        self._e2e_ready = True
+
+    def _prefetch(self, i):
+        s = i % 2
+        st = (i % self.args.pool_steps) * self.B
+        sl = slice(st, st + self.B)
+        d, tr, tm = self.e2e_bufs[s]
+        with torch.cuda.stream(self.copy_stream):
+            if self.e2e_done_ev[s] is not None:
+                self.copy_stream.wait_event(self.e2e_done_ev[s])               # do not overwrite a batch still in use
+            for k, v in self.host.items():
+                d[k].copy_(v[sl], non_blocking=True)
+            tr.copy_(self.host_tgt_rgb[sl], non_blocking=True)
+            tm.copy_(self.host_tgt_mask[sl], non_blocking=True)
+            self.e2e_ready_ev[s].record(self.copy_stream)
+        self.e2e_prefetched = i
+
     def step_e2e(self, i):
-        s = (i % self.args.pool_steps) * self.B
-        sl = slice(s, s + self.B)
-        d = {k: v[sl].to(self.dev, non_blocking=True) for k, v in self.host.items()}
-        tr = self.host_tgt_rgb[sl].to(self.dev, non_blocking=True)
-        tm = self.host_tgt_mask[sl].to(self.dev, non_blocking=True)
-        return float(self._train(d, tr, tm).item())        # D2H read of the step's loss
+        self._e2e_setup()
+        s = i % 2
+        if self.e2e_prefetched != i:
+            self._prefetch(i)
+        cur = torch.cuda.current_stream(self.dev)
+        cur.wait_event(self.e2e_ready_ev[s])
+        self._prefetch(i + 1)                                                  # overlaps with this step's compute
+        d, tr, tm = self.e2e_bufs[s]
+        loss = self._train(d, tr, tm)
+        self.loss_host[s].copy_(loss.detach(), non_blocking=True)              # D2H of this step's loss
+        ev = torch.cuda.Event(); ev.record(cur)
+        self.loss_ev[s], self.e2e_done_ev[s] = ev, ev
+        p = 1 - s
+        if self.loss_ev[p] is not None:                                        # read the previous step's loss on the host
+            self.loss_ev[p].synchronize()
+            self.last_loss = float(self.loss_host[p]); self.loss_ev[p] = None; self.losses_read += 1
+
+    def flush_e2e(self):
+        for s in range(2):
+            if self.loss_ev[s] is not None:
+                self.loss_ev[s].synchronize()
+                self.last_loss = float(self.loss_host[s]); self.loss_ev[s] = None; self.losses_read += 1
 
 
-def timed_region(fn, steps, warmup, world, device):
-    """W warm-ups, barrier + sync, K steps between CUDA events on the launching stream, barrier + sync, max over ranks."""
+def timed_region(fn, steps, warmup, world, device, flush=None):
+    """W warm-ups, barrier + sync, K steps between CUDA events on the launching stream, barrier + sync, max over ranks.
+    `flush` (host-side completion of pipelined result reads) runs inside the timed region."""
     import torch.distributed as dist
     for i in range(warmup):
         fn(i)
+    if flush is not None:
+        flush()
     torch.cuda.synchronize(device)
     if world > 1:
         dist.barrier()
@@ -212,6 +263,8 @@ def timed_region(fn, steps, warmup, world, device):
     e0.record()
     for i in range(steps):
         fn(warmup + i)
+    if flush is not None:
+        flush()
     e1.record()
     torch.cuda.synchronize(device)
     if world > 1:
@@ -226,6 +279,7 @@ def timed_region(fn, steps, warmup, world, device):
 def run_b200(args):
     from gomavatar_b200 import _lib
     from gomavatar_b200.dist import init_from_env
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # keep NCCL's version banner off stdout (one JSON line only)
     rank, local, world = init_from_env("nccl")
     if world != args.gpus and rank == 0:
         print(f"# note: --gpus {args.gpus} but WORLD_SIZE={world}; using WORLD_SIZE", file=sys.stderr)
@@ -238,7 +292,8 @@ def run_b200(args):
     frames_total = K * B * world
 
     # ---- e2e first (host buffers in, loss out every step), then the device-resident number with per-kernel timers
-    ms_e2e = timed_region(tr.step_e2e, K, max(W_, 3), world, device)
+    ms_e2e = timed_region(tr.step_e2e, K, max(W_, 3), world, device, flush=tr.flush_e2e)
+    assert tr.losses_read == K + max(W_, 3), "every e2e step must deliver its loss to the host"
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()

@@ -119,6 +119,12 @@ class GomLpipsTapArgs(ctypes.Structure):
                 ("pooled", c_void_p), ("dL_dval", c_void_p), ("dL_dpooled", c_void_p), ("dL_dpre", c_void_p)]
 
 
+class GomEvalMetricsArgs(ctypes.Structure):
+    _fields_ = [("n_frames", c_int32), ("height", c_int32), ("width", c_int32), ("quantize", c_int32),
+                ("pred", c_void_p), ("gt", c_void_p), ("ssim_sum", c_void_p), ("sq_err_sum", c_void_p),
+                ("pred_8b", c_void_p)]
+
+
 # every symbol include/gom_b200.h declares (tests check the .so exports all of them)
 EXPORTS = [
     "gom_abi_version", "gom_last_error", "gom_launch_count", "gom_profile_enable", "gom_profile_num_slots",
@@ -130,7 +136,7 @@ EXPORTS = [
     "gom_sizeof_face_fwd_args", "gom_sizeof_face_bwd_args",
     "gom_lpips_input_forward", "gom_lpips_input_backward", "gom_bias_relu", "gom_relu_backward",
     "gom_lpips_tap_forward", "gom_lpips_tap_backward", "gom_sizeof_lpips_input_args", "gom_sizeof_bias_relu_args",
-    "gom_sizeof_relu_bwd_args", "gom_sizeof_lpips_tap_args",
+    "gom_sizeof_relu_bwd_args", "gom_sizeof_lpips_tap_args", "gom_eval_metrics", "gom_sizeof_eval_metrics_args",
 ]
 
 _STRUCTS = {
@@ -138,13 +144,13 @@ _STRUCTS = {
     "joint_fwd": GomJointFwdArgs, "joint_bwd": GomJointBwdArgs, "lbs_fwd": GomLbsFwdArgs, "lbs_bwd": GomLbsBwdArgs,
     "face_fwd": GomFaceFwdArgs, "face_bwd": GomFaceBwdArgs, "photo": GomPhotoArgs,
     "lpips_input": GomLpipsInputArgs, "bias_relu": GomBiasReluArgs, "relu_bwd": GomReluBwdArgs,
-    "lpips_tap": GomLpipsTapArgs,
+    "lpips_tap": GomLpipsTapArgs, "eval_metrics": GomEvalMetricsArgs,
 }
 _ENTRY_POINTS = ["gom_camera_from_KE", "gom_raster_forward", "gom_raster_backward", "gom_joint_transforms_forward",
                  "gom_joint_transforms_backward", "gom_lbs_forward", "gom_lbs_backward", "gom_face_gaussians_forward",
                  "gom_face_gaussians_backward", "gom_photometric_forward", "gom_photometric_backward",
                  "gom_lpips_input_forward", "gom_lpips_input_backward", "gom_bias_relu", "gom_relu_backward",
-                 "gom_lpips_tap_forward", "gom_lpips_tap_backward"]
+                 "gom_lpips_tap_forward", "gom_lpips_tap_backward", "gom_eval_metrics"]
 
 _lib = None
 

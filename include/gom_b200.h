@@ -323,6 +323,25 @@ typedef struct {
 int gom_lpips_tap_forward(const GomLpipsTapArgs *a, gom_stream_t stream);
 int gom_lpips_tap_backward(const GomLpipsTapArgs *a, gom_stream_t stream);
 
+/* --------------------------------------------------------------------------------------------------------------
+ * Evaluation metrics.  Replaces reference eval.py:101-108 (Evaluator.psnr_metric / ssim_metric: skimage 0.18
+ * structural_similarity defaults — 7x7 uniform window, sample covariance, K1 .01, K2 .03, data_range 2, 3-px crop)
+ * and the 8-bit quantisation before them (utils/image_util.py:21-22, eval.py:355-361).
+ *   quantize = 1: pred / gt are raw float images, quantised as uint8(255 * clip(v, 0, 1)) (truncation) first;
+ *   quantize = 0: pred / gt already are k / 255 (what Evaluator.evaluate receives).
+ * ssim_sum[b]   = sum of the per-pixel, per-channel SSIM over the cropped image: ssim = ssim_sum / (3 (H-6) (W-6));
+ * sq_err_sum[b] = sum of squared 8-bit differences: mse = sq_err_sum / (65025 * 3 H W), psnr = -10 log10(mse).
+ */
+typedef struct {
+    int32_t n_frames, height, width, quantize;
+    const float *pred;           /* [B,H,W,3] */
+    const float *gt;             /* [B,H,W,3] */
+    double *ssim_sum;            /* [B] out */
+    uint64_t *sq_err_sum;        /* [B] out */
+    uint8_t *pred_8b;            /* [B,H,W,3] out, nullable: the quantised prediction (what eval.py writes to PNG) */
+} GomEvalMetricsArgs;
+int gom_eval_metrics(const GomEvalMetricsArgs *a, gom_stream_t stream);
+
 /* struct sizes, so that a foreign-language binding can assert its mirror of the structs */
 size_t gom_sizeof_camera_args(void);
 size_t gom_sizeof_raster_fwd_args(void);
@@ -338,6 +357,7 @@ size_t gom_sizeof_lpips_input_args(void);
 size_t gom_sizeof_bias_relu_args(void);
 size_t gom_sizeof_relu_bwd_args(void);
 size_t gom_sizeof_lpips_tap_args(void);
+size_t gom_sizeof_eval_metrics_args(void);
 
 #ifdef __cplusplus
 }

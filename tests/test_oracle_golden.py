@@ -150,3 +150,30 @@ def test_ssim_psnr_sanity():
     # recompute the per-pixel map for channel 0 through the public function on a 7x7 crop
     assert abs(L.ssim(a[:7, :7, :1], b[:7, :7, :1]) - s00) < 1e-12
     assert abs(L.psnr(a, b) - (-10 * np.log10(((a - b) ** 2).mean()))) < 1e-12
+
+
+def test_ssim_oracle_matches_scipy_restatement_of_skimage():
+    """skimage is absent offline, scipy is not: restate skimage 0.18 ``structural_similarity`` literally on top of
+    ``scipy.ndimage.uniform_filter`` (the filter it calls) and check the oracle's cumulative-sum formulation against it."""
+    from scipy.ndimage import uniform_filter
+    from oracle import losses as L
+    rng = np.random.default_rng(3)
+    a = L.to_8b(rng.random((40, 52, 3)).astype(np.float32)) / 255.0
+    b = L.to_8b(np.clip(a + rng.normal(0, 0.08, a.shape), 0, 1).astype(np.float32)) / 255.0
+
+    def skimage_like(X, Y, win=7, K1=0.01, K2=0.03, R=2.0):
+        vals = []
+        for ch in range(X.shape[-1]):
+            x, y = X[..., ch].astype(np.float64), Y[..., ch].astype(np.float64)
+            NP = win ** 2
+            cov_norm = NP / (NP - 1)
+            f = lambda im: uniform_filter(im, size=win)
+            ux, uy, uxx, uyy, uxy = f(x), f(y), f(x * x), f(y * y), f(x * y)
+            vx, vy, vxy = cov_norm * (uxx - ux * ux), cov_norm * (uyy - uy * uy), cov_norm * (uxy - ux * uy)
+            C1, C2 = (K1 * R) ** 2, (K2 * R) ** 2
+            S = ((2 * ux * uy + C1) * (2 * vxy + C2)) / ((ux ** 2 + uy ** 2 + C1) * (vx + vy + C2))
+            pad = (win - 1) // 2
+            vals.append(S[pad:-pad, pad:-pad].mean())
+        return float(np.mean(vals))
+
+    assert abs(L.ssim(a, b) - skimage_like(a, b)) < 1e-12
