@@ -152,7 +152,8 @@ class Trainer:
         self.arena.broadcast_params()
         groups = self.model.get_param_groups(type("C", (), {"lr": {"appearance": 5e-4, "canonical_geometry": 5e-4,
                                                                 "canonical_geometry_xyz": 5e-4}})())
-        self.opt = torch.optim.Adam(groups, lr=5e-4, fused=True)
+        from gomavatar_b200.dist import ArenaAdam
+        self.opt = ArenaAdam(self.arena, groups)            # one launch over the flat arena (csrc/adam.cu)
         self.h2d_bytes = sum(v[: self.B].numel() * v.element_size() for v in self.host.values()) + \
             self.host_tgt_rgb[: self.B].numel() * 4 + self.host_tgt_mask[: self.B].numel() * 4
 
@@ -181,8 +182,7 @@ class Trainer:
                                   bgcolor=d["bgcolor"])
         loss, terms, _ = compute_loss(rgb, mask, d["bgcolor"], tgt_rgb, tgt_mask, lpips_func=self.lpips)
         loss.backward()
-        self.arena.all_reduce_mean()
-        self.opt.step()
+        self.opt.step(grad_scale=self.arena.all_reduce_sum())      # 1/world folded into the Adam launch
         return loss
 
     def step_device(self, i):

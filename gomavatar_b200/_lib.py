@@ -125,6 +125,21 @@ class GomEvalMetricsArgs(ctypes.Structure):
                 ("pred_8b", c_void_p)]
 
 
+class GomConvFirstArgs(ctypes.Structure):
+    _fields_ = [("n_images", c_int32), ("height", c_int32), ("width", c_int32), ("_pad", c_int32), ("x", c_void_p),
+                ("weight", c_void_p), ("bias", c_void_p), ("out", c_void_p), ("dL_dout", c_void_p), ("dL_dx", c_void_p)]
+
+
+ADAM_MAX_SEGMENTS = 16
+
+
+class GomAdamArgs(ctypes.Structure):
+    _fields_ = [("n", c_int64), ("param", c_void_p), ("grad", c_void_p), ("exp_avg", c_void_p), ("exp_avg_sq", c_void_p),
+                ("beta1", c_float), ("beta2", c_float), ("eps", c_float), ("grad_scale", c_float),
+                ("bias_correction1", c_float), ("bias_correction2", c_float), ("n_segments", c_int32), ("_pad", c_int32),
+                ("seg_end", c_int64 * ADAM_MAX_SEGMENTS), ("seg_lr", c_float * ADAM_MAX_SEGMENTS)]
+
+
 # every symbol include/gom_b200.h declares (tests check the .so exports all of them)
 EXPORTS = [
     "gom_abi_version", "gom_last_error", "gom_launch_count", "gom_profile_enable", "gom_profile_num_slots",
@@ -137,6 +152,8 @@ EXPORTS = [
     "gom_lpips_input_forward", "gom_lpips_input_backward", "gom_bias_relu", "gom_relu_backward",
     "gom_lpips_tap_forward", "gom_lpips_tap_backward", "gom_sizeof_lpips_input_args", "gom_sizeof_bias_relu_args",
     "gom_sizeof_relu_bwd_args", "gom_sizeof_lpips_tap_args", "gom_eval_metrics", "gom_sizeof_eval_metrics_args",
+    "gom_conv_first_forward", "gom_conv_first_backward", "gom_sizeof_conv_first_args",
+    "gom_adam_step", "gom_sizeof_adam_args",
 ]
 
 _STRUCTS = {
@@ -145,12 +162,14 @@ _STRUCTS = {
     "face_fwd": GomFaceFwdArgs, "face_bwd": GomFaceBwdArgs, "photo": GomPhotoArgs,
     "lpips_input": GomLpipsInputArgs, "bias_relu": GomBiasReluArgs, "relu_bwd": GomReluBwdArgs,
     "lpips_tap": GomLpipsTapArgs, "eval_metrics": GomEvalMetricsArgs,
+    "conv_first": GomConvFirstArgs, "adam": GomAdamArgs,
 }
 _ENTRY_POINTS = ["gom_camera_from_KE", "gom_raster_forward", "gom_raster_backward", "gom_joint_transforms_forward",
                  "gom_joint_transforms_backward", "gom_lbs_forward", "gom_lbs_backward", "gom_face_gaussians_forward",
                  "gom_face_gaussians_backward", "gom_photometric_forward", "gom_photometric_backward",
                  "gom_lpips_input_forward", "gom_lpips_input_backward", "gom_bias_relu", "gom_relu_backward",
-                 "gom_lpips_tap_forward", "gom_lpips_tap_backward", "gom_eval_metrics"]
+                 "gom_lpips_tap_forward", "gom_lpips_tap_backward", "gom_eval_metrics",
+                 "gom_conv_first_forward", "gom_conv_first_backward", "gom_adam_step"]
 
 _lib = None
 

@@ -26,7 +26,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import _lib
-from ._lib import GomBiasReluArgs, GomLpipsInputArgs, GomLpipsTapArgs, GomReluBwdArgs, call, ptr
+from ._lib import GomBiasReluArgs, GomConvFirstArgs, GomLpipsInputArgs, GomLpipsTapArgs, GomReluBwdArgs, call, ptr
 
 _VGG_CFG = [64, 64, "M", 128, 128, "M", 256, 256, 256, "M", 512, 512, 512, "M", 512, 512, 512]
 _TAPS = (3, 8, 15, 22, 29)
@@ -205,6 +205,10 @@ class LPIPS(nn.Module):
             self.features = self.features.to(memory_format=torch.channels_last)
         self._convs = [m for m in self.features if isinstance(m, nn.Conv2d)]
         self._no_cudnn_epilogue = set()
+        # conv1_1 (3 -> 64) runs in csrc/conv_first.cu: torch-contiguous [64,3,3,3] copy of its weight
+        self.own_first_conv = True
+        self.register_buffer("w_first", self._convs[0].weight.detach().clone(memory_format=torch.contiguous_format),
+                             persistent=False)
 
     # ---------------------------------------------------------------------------- fused path (csrc/lpips.cu + cuDNN)
     def _lin(self, level):
@@ -214,6 +218,15 @@ class LPIPS(nn.Module):
         """3x3 convolution (cuDNN) + bias + ReLU on a channels_last batch."""
         conv = self._convs[ci]
         w = conv.weight
+        if ci == 0 and self.own_first_conv:
+            N, _, hh, ww = h.shape
+            x = h.permute(0, 2, 3, 1)
+            if not x.is_contiguous():
+                x = x.contiguous()
+            y = torch.empty(N, hh, ww, 64, dtype=torch.float32, device=h.device)
+            call("gom_conv_first_forward", GomConvFirstArgs(n_images=N, height=hh, width=ww, x=ptr(x), weight=ptr(self.w_first),
+                                                            bias=ptr(conv.bias), out=ptr(y)))
+            return y.permute(0, 3, 1, 2)
         if self.conv_epilogue == "cudnn" and ci not in self._no_cudnn_epilogue:
             # cuDNN's fused conv + bias + activation: measured on B200 at the same time as the bare convolution
             # (profiles/r1_conv_probe.md), so the epilogue costs no extra HBM pass.
@@ -229,6 +242,15 @@ class LPIPS(nn.Module):
         return y
 
     def _conv_dgrad(self, g_out, inp, ci):
+        if ci == 0 and self.own_first_conv:
+            N, _, hh, ww = g_out.shape
+            g = g_out.permute(0, 2, 3, 1)
+            if not g.is_contiguous():
+                g = g.contiguous()
+            dx = torch.empty(N, hh, ww, 3, dtype=torch.float32, device=g.device)
+            call("gom_conv_first_backward", GomConvFirstArgs(n_images=N, height=hh, width=ww, weight=ptr(self.w_first),
+                                                             dL_dout=ptr(g), dL_dx=ptr(dx)))
+            return dx.permute(0, 3, 1, 2)
         w = self._convs[ci].weight
         return torch.ops.aten.convolution_backward(g_out, inp, w, None, (1, 1), (1, 1), (1, 1), False, (0, 0), 1,
                                                    (True, False, False))[0]

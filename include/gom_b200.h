@@ -323,6 +323,22 @@ typedef struct {
 int gom_lpips_tap_forward(const GomLpipsTapArgs *a, gom_stream_t stream);
 int gom_lpips_tap_backward(const GomLpipsTapArgs *a, gom_stream_t stream);
 
+/* First VGG16 convolution of LPIPS (3 -> 64 channels, 3x3, stride 1, zero padding 1) fused with bias + ReLU, and its
+ * input gradient, in exact fp32 (csrc/conv_first.cu).  Replaces `features[0:2]` of reference
+ * utils/lpips/pretrained_networks.py:96-134.  NHWC activations; weight is torch's contiguous [64,3,3,3].
+ * forward : out = relu(conv(x) + bias)          backward: dL_dx = conv_transpose(dL_dout)  (dL_dout already ReLU-masked) */
+typedef struct {
+    int32_t n_images, height, width, _pad;
+    const float *x;              /* [N,H,W,3]  (forward) */
+    const float *weight;         /* [64,3,3,3] */
+    const float *bias;           /* [64]       (forward) */
+    float *out;                  /* [N,H,W,64] (forward) */
+    const float *dL_dout;        /* [N,H,W,64] (backward) */
+    float *dL_dx;                /* [N,H,W,3]  (backward) */
+} GomConvFirstArgs;
+int gom_conv_first_forward(const GomConvFirstArgs *a, gom_stream_t stream);
+int gom_conv_first_backward(const GomConvFirstArgs *a, gom_stream_t stream);
+
 /* --------------------------------------------------------------------------------------------------------------
  * Evaluation metrics.  Replaces reference eval.py:101-108 (Evaluator.psnr_metric / ssim_metric: skimage 0.18
  * structural_similarity defaults — 7x7 uniform window, sample covariance, K1 .01, K2 .03, data_range 2, 3-px crop)
@@ -342,6 +358,27 @@ typedef struct {
 } GomEvalMetricsArgs;
 int gom_eval_metrics(const GomEvalMetricsArgs *a, gom_stream_t stream);
 
+/* --------------------------------------------------------------------------------------------------------------
+ * Adam over the flat parameter arena, one launch.  Replaces `optimizer.step()` of reference train.py:339 for the
+ * parameter groups of models/model.py:305-324 (torch.optim.Adam semantics, amsgrad off, weight decay 0).  Segment s
+ * covers arena elements [seg_end[s-1], seg_end[s]) with learning rate seg_lr[s]; grad_scale multiplies the gradient
+ * first (1 / world_size after the summing all-reduce).  The host owns the step counter and passes 1 - beta^step.
+ */
+#define GOM_ADAM_MAX_SEGMENTS 16
+typedef struct {
+    int64_t n;
+    float *param;                /* [n] updated in place */
+    const float *grad;           /* [n] */
+    float *exp_avg;              /* [n] */
+    float *exp_avg_sq;           /* [n] */
+    float beta1, beta2, eps, grad_scale;
+    float bias_correction1, bias_correction2;
+    int32_t n_segments, _pad;
+    int64_t seg_end[GOM_ADAM_MAX_SEGMENTS];
+    float seg_lr[GOM_ADAM_MAX_SEGMENTS];
+} GomAdamArgs;
+int gom_adam_step(const GomAdamArgs *a, gom_stream_t stream);
+
 /* struct sizes, so that a foreign-language binding can assert its mirror of the structs */
 size_t gom_sizeof_camera_args(void);
 size_t gom_sizeof_raster_fwd_args(void);
@@ -358,6 +395,8 @@ size_t gom_sizeof_bias_relu_args(void);
 size_t gom_sizeof_relu_bwd_args(void);
 size_t gom_sizeof_lpips_tap_args(void);
 size_t gom_sizeof_eval_metrics_args(void);
+size_t gom_sizeof_conv_first_args(void);
+size_t gom_sizeof_adam_args(void);
 
 #ifdef __cplusplus
 }

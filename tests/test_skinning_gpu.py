@@ -144,3 +144,36 @@ def test_face_gaussians_forward_backward(n_faces, B, int32_faces, ref_init):
     assert _rel(kv.grad.cpu().numpy(), ov.grad.numpy()) < 1e-3
     assert _rel(kw.grad.cpu().numpy(), ow.grad.numpy()) < 1e-3
     assert _rel(ks.grad.cpu().numpy(), os_.grad.numpy()) < 1e-3
+
+
+def test_arena_adam_matches_torch_adam():
+    """csrc/adam.cu (one launch over the flat arena, per-group learning rates, folded gradient scale) against
+    torch.optim.Adam on identical gradients for several steps, incl. a learning-rate change in between (train.py:166-175)."""
+    from gomavatar_b200.dist import ArenaAdam, FlatArena
+
+    class M(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            g = torch.Generator().manual_seed(3)
+            self.a = torch.nn.Parameter(torch.randn(3, 1001, generator=g))
+            self.b = torch.nn.Parameter(torch.randn(3, 777, generator=g))
+            self.c = torch.nn.Parameter(torch.randn(5, generator=g))
+
+    m1, m2 = M().to(DEV), M().to(DEV)
+    arena = FlatArena(m1)
+    groups1 = [{"name": "x", "params": [m1.a], "lr": 1e-2}, {"name": "y", "params": [m1.b, m1.c], "lr": 3e-3}]
+    groups2 = [{"params": [m2.a], "lr": 1e-2}, {"params": [m2.b, m2.c], "lr": 3e-3}]
+    opt1, opt2 = ArenaAdam(arena, groups1), torch.optim.Adam(groups2)
+    gen = torch.Generator(device=DEV).manual_seed(0)
+    for step in range(6):
+        if step == 3:
+            opt1.param_groups[0]["lr"] = 2e-3
+            opt2.param_groups[0]["lr"] = 2e-3
+        for p1, p2 in zip(m1.parameters(), m2.parameters()):
+            g = torch.randn(p1.shape, generator=gen, device=DEV) * (10.0 ** (step - 3))
+            p1.grad.copy_(2.0 * g)                 # the arena's gradient carries a factor that grad_scale removes
+            p2.grad = g.clone()
+        opt1.step(grad_scale=0.5)
+        opt2.step()
+    for p1, p2 in zip(m1.parameters(), m2.parameters()):
+        np.testing.assert_allclose(p1.detach().cpu().numpy(), p2.detach().cpu().numpy(), rtol=2e-6, atol=2e-7)
