@@ -96,20 +96,25 @@ class ClockSampler:
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed `ncu --set full`
 # capture of this same command (profiles/); filled in by hand after each capture, None = not captured yet.
-NCU_TRAFFIC_BYTES = {}
+NCU_TRAFFIC_BYTES = {      # profiles/r1f_ncu_full_summary.md (8 frames, 512x512): mean over the kernel's launches in one step,
+    # like `achieved` (tap_bwd 5 launches 3199.6 MB, tap_fwd 5 launches 2487.4 MB, relu_bwd 8 launches 3423.5 MB)
+    "lpips_tap_bwd": 639.9e6, "lpips_tap_fwd": 497.5e6, "relu_bwd": 427.9e6, "blend_bwd": 16.4e6, "sort_blend_fwd": 16.9e6}
 
 _VGG_LEVELS = ((64, 2), (128, 2), (256, 3), (512, 3), (512, 3))      # (channels, convolutions) per VGG16 block
 
 
-def lpips_alg_bytes_per_frame(H, W):
+def lpips_alg_bytes_per_frame(H, W, own_kernel_epilogue=False):
     """Algorithmic HBM bytes per FRAME (= one prediction + one target image) of the hand-written LPIPS kernels, summed
     over the layers each kernel serves (csrc/lpips.cu; formulas in DESIGN.md §4).  fp32 NHWC."""
     out = {"lpips_input": (2 * 2 + 2) * 3 * H * W * 4.0, "bias_relu": 0.0, "relu_bwd": 0.0, "lpips_tap_fwd": 0.0,
-           "lpips_tap_bwd": 0.0}
+           "lpips_tap_bwd": 0.0,
+           # conv1_1 in csrc/conv_first.cu (fp32-FMA-bound, 1728 FMA per pixel; bytes listed for completeness)
+           "conv_first_fwd": 2 * H * W * (3 + 64) * 4.0, "conv_first_bwd": H * W * (64 + 3) * 4.0}
     h, w, cin = H, W, 3
     for level, (C, n_conv) in enumerate(_VGG_LEVELS):
         px = h * w
-        out["bias_relu"] += n_conv * 2 * (2 * px * C * 4.0)              # read + write, pred and gt
+        if own_kernel_epilogue:
+            out["bias_relu"] += n_conv * 2 * (2 * px * C * 4.0)          # read + write, pred and gt
         out["relu_bwd"] += (n_conv - 1) * 3 * (px * C * 4.0)             # act read, grad read + write (pred half)
         pooled = (h // 2) * (w // 2) * C * 4.0 if level < 4 else 0.0
         out["lpips_tap_fwd"] += 2 * px * C * 4.0 + 2 * pooled
@@ -317,7 +322,8 @@ def run_b200(args):
         "preprocess_bwd": 76 * F + 36 * F, "emit": 12 * n_dup + 20 * F, "scan_tiles": 12 * T,
         "lbs_fwd": 120 * V, "lbs_bwd": 120 * V, "face_fwd": 72 * F, "face_bwd": 72 * F + 36 * F,
         "photo_fwd": 44 * HW, "photo_bwd": 60 * HW}
-    alg_bytes_per_frame.update(lpips_alg_bytes_per_frame(args.img, args.img))
+    alg_bytes_per_frame.update(lpips_alg_bytes_per_frame(args.img, args.img, args.lpips_epilogue == "kernel"))
+    alg_bytes_per_frame["adam"] = 28.0 * tr.arena.numel / B          # param r/w, grad r, two moments r/w: per STEP
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))

@@ -106,6 +106,14 @@ template <int C> __device__ __forceinline__ void load_lin(const float *lin, int 
     for (int r = 0; r < L::CPL; r++) f[r] = __ldg(lin + (r / 4) * 4 * L::LPP + 4 * sl + (r % 4));
 }
 
+// 1 / (sqrt(s + eps) + eps) and sqrt(s + eps) with the SFU approximations (MUFU.RSQ / MUFU.RCP, <= 2 ulp each): the
+// IEEE sqrt + divide sequences were ~40 of the ~110 instructions per pixel pair of an otherwise HBM-bound kernel.
+__device__ __forceinline__ float inv_norm(float s, float &n) {
+    const float se = s + kEps;                 // >= 1e-10: a normal float, rsqrt is finite
+    n = se * rsqrtf(se);
+    return __fdividef(1.f, n + kEps);
+}
+
 template <int LPP> __device__ __forceinline__ void group_sum2(float &a, float &b) {
 #pragma unroll
     for (int d = LPP / 2; d > 0; d >>= 1) {
@@ -134,8 +142,11 @@ __global__ void __launch_bounds__(kThreads) k_lpips_tap_fwd(TapDev a) {
     float lin[L::CPL];
     load_lin<C>(a.lin, sl, lin);
     float acc = 0.f;
-    for (int q = blockIdx.x * kWarps + wid; q < nq; q += gridDim.x * kWarps) {
-        const int qy = q / qw, qx = q - qy * qw;
+    const int q0 = blockIdx.x * kWarps + wid, qstride = gridDim.x * kWarps;
+    const int dqy = qstride / qw, dqx = qstride - dqy * qw;
+    int qy = q0 / qw, qx = q0 - qy * qw;
+    for (int q = q0; q < nq; q += qstride, qy += dqy, qx += dqx) {
+        if (qx >= qw) { qx -= qw; qy++; }
         float m0[L::CPL], m1[L::CPL];
 #pragma unroll
         for (int r = 0; r < L::CPL; r++) { m0[r] = -INFINITY; m1[r] = -INFINITY; }
@@ -160,7 +171,8 @@ __global__ void __launch_bounds__(kThreads) k_lpips_tap_fwd(TapDev a) {
                 if (ok) { m0[r] = fmaxf(m0[r], f0[r]); m1[r] = fmaxf(m1[r], f1[r]); }
             }
             group_sum2<L::LPP>(s0, s1);
-            const float i0 = 1.f / (sqrtf(s0 + kEps) + kEps), i1 = 1.f / (sqrtf(s1 + kEps) + kEps);
+            float n0, n1;
+            const float i0 = inv_norm(s0, n0), i1 = inv_norm(s1, n1);
             float d = 0.f;
 #pragma unroll
             for (int r = 0; r < L::CPL; r++) {
@@ -213,8 +225,11 @@ __global__ void __launch_bounds__(kThreads) k_lpips_tap_bwd(TapDev a) {
     const float kscale = 2.f * a.dval[b] / (float)((long long)a.h * a.w);
     float lin[L::CPL];
     load_lin<C>(a.lin, sl, lin);
-    for (int q = blockIdx.x * kWarps + wid; q < nq; q += gridDim.x * kWarps) {
-        const int qy = q / qw, qx = q - qy * qw;
+    const int q0 = blockIdx.x * kWarps + wid, qstride = gridDim.x * kWarps;
+    const int dqy = qstride / qw, dqx = qstride - dqy * qw;
+    int qy = q0 / qw, qx = q0 - qy * qw;
+    for (int q = q0; q < nq; q += qstride, qy += dqy, qx += dqx) {
+        if (qx >= qw) { qx -= qw; qy++; }
         const bool pooled = a.pool && a.d_pooled && qy < ph && qx < pw;      // warp-uniform; quad complete
         float f0[L::NIT][L::CPL];
         bool ok[L::NIT];
@@ -236,14 +251,26 @@ __global__ void __launch_bounds__(kThreads) k_lpips_tap_bwd(TapDev a) {
             load_px<C>(a.d_pooled + ((long long)b * ph * pw + (long long)qy * pw + qx) * C, sl, gp);
 #pragma unroll
             for (int r = 0; r < L::CPL; r++) {
-                float best = 0.f;
+                float v4[4];                                                 // the quad's four values of this channel
+                if constexpr (L::PPW == 1) {
+#pragma unroll
+                    for (int s = 0; s < 4; s++) v4[s] = f0[s][r];
+                } else if constexpr (L::PPW == 2) {                          // s = 2 it + group: own or the partner group's
+#pragma unroll
+                    for (int it = 0; it < 2; it++) {
+                        const float own = f0[it][r], oth = __shfl_xor_sync(0xffffffffu, own, L::LPP);
+                        v4[2 * it] = grp ? oth : own;                        // group 0's pixel comes first in scan order
+                        v4[2 * it + 1] = grp ? own : oth;
+                    }
+                } else {
+#pragma unroll
+                    for (int s = 0; s < 4; s++) v4[s] = __shfl_sync(0xffffffffu, f0[0][r], s * L::LPP + sl);
+                }
+                float best = v4[0];
                 uint32_t arg = 0;
 #pragma unroll
-                for (int s = 0; s < 4; s++) {
-                    const float own = f0[s / L::PPW][r];
-                    const float v = L::PPW == 1 ? own : __shfl_sync(0xffffffffu, own, (s % L::PPW) * L::LPP + sl);
-                    if (s == 0 || v > best || v != v) { best = v; arg = s; }   // strict: the first maximum wins
-                }
+                for (int s = 1; s < 4; s++)
+                    if (v4[s] > best || v4[s] != v4[s]) { best = v4[s]; arg = s; }   // strict: the first maximum wins
                 am |= arg << (2 * r);
             }
         }
@@ -262,7 +289,8 @@ __global__ void __launch_bounds__(kThreads) k_lpips_tap_bwd(TapDev a) {
 #pragma unroll
             for (int r = 0; r < L::CPL; r++) { s0 += f0[it][r] * f0[it][r]; s1 += f1[r] * f1[r]; }
             group_sum2<L::LPP>(s0, s1);
-            const float n0 = sqrtf(s0 + kEps), i0 = 1.f / (n0 + kEps), i1 = 1.f / (sqrtf(s1 + kEps) + kEps);
+            float n0, n1;
+            const float i0 = inv_norm(s0, n0), i1 = inv_norm(s1, n1);
             float e[L::CPL], dot = 0.f;
 #pragma unroll
             for (int r = 0; r < L::CPL; r++) {
@@ -270,7 +298,7 @@ __global__ void __launch_bounds__(kThreads) k_lpips_tap_bwd(TapDev a) {
                 dot += e[r] * f0[it][r];
             }
             dot = group_sum<L::LPP>(dot);
-            const float k2 = dot * i0 * i0 / n0;
+            const float k2 = __fdividef(dot * i0 * i0, n0);
             float g[L::CPL];
 #pragma unroll
             for (int r = 0; r < L::CPL; r++) {
