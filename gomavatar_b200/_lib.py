@@ -140,6 +140,16 @@ class GomAdamArgs(ctypes.Structure):
                 ("seg_end", c_int64 * ADAM_MAX_SEGMENTS), ("seg_lr", c_float * ADAM_MAX_SEGMENTS)]
 
 
+class GomMeshRasterArgs(ctypes.Structure):
+    _fields_ = [("n_frames", c_int32), ("n_verts", c_int32), ("n_faces", c_int32), ("height", c_int32), ("width", c_int32),
+                ("faces_int64", c_int32), ("soft", c_int32), ("faces_per_pixel", c_int32), ("blur_radius", c_float),
+                ("_pad", c_int32), ("list_capacity", c_int64), ("verts_ndc", c_void_p), ("faces", c_void_p),
+                ("vert_normals", c_void_p), ("tile_count", c_void_p), ("tile_offset", c_void_p), ("tile_cursor", c_void_p),
+                ("face_list", c_void_p), ("status", c_void_p), ("pix_to_face", c_void_p), ("normal_map", c_void_p),
+                ("alpha", c_void_p), ("zcut", c_void_p), ("idcut", c_void_p), ("dL_dnormal_map", c_void_p),
+                ("dL_dalpha", c_void_p), ("dL_dverts_ndc", c_void_p), ("dL_dvert_normals", c_void_p)]
+
+
 # every symbol include/gom_b200.h declares (tests check the .so exports all of them)
 EXPORTS = [
     "gom_abi_version", "gom_last_error", "gom_launch_count", "gom_profile_enable", "gom_profile_num_slots",
@@ -154,6 +164,7 @@ EXPORTS = [
     "gom_sizeof_relu_bwd_args", "gom_sizeof_lpips_tap_args", "gom_eval_metrics", "gom_sizeof_eval_metrics_args",
     "gom_conv_first_forward", "gom_conv_first_backward", "gom_sizeof_conv_first_args",
     "gom_adam_step", "gom_sizeof_adam_args",
+    "gom_mesh_raster_forward", "gom_mesh_raster_backward", "gom_sizeof_mesh_raster_args",
 ]
 
 _STRUCTS = {
@@ -163,13 +174,15 @@ _STRUCTS = {
     "lpips_input": GomLpipsInputArgs, "bias_relu": GomBiasReluArgs, "relu_bwd": GomReluBwdArgs,
     "lpips_tap": GomLpipsTapArgs, "eval_metrics": GomEvalMetricsArgs,
     "conv_first": GomConvFirstArgs, "adam": GomAdamArgs,
+    "mesh_raster": GomMeshRasterArgs,
 }
 _ENTRY_POINTS = ["gom_camera_from_KE", "gom_raster_forward", "gom_raster_backward", "gom_joint_transforms_forward",
                  "gom_joint_transforms_backward", "gom_lbs_forward", "gom_lbs_backward", "gom_face_gaussians_forward",
                  "gom_face_gaussians_backward", "gom_photometric_forward", "gom_photometric_backward",
                  "gom_lpips_input_forward", "gom_lpips_input_backward", "gom_bias_relu", "gom_relu_backward",
                  "gom_lpips_tap_forward", "gom_lpips_tap_backward", "gom_eval_metrics",
-                 "gom_conv_first_forward", "gom_conv_first_backward", "gom_adam_step"]
+                 "gom_conv_first_forward", "gom_conv_first_backward", "gom_adam_step",
+                 "gom_mesh_raster_forward", "gom_mesh_raster_backward"]
 
 _lib = None
 

@@ -155,13 +155,8 @@ class Model(nn.Module):
     def _vertex_normals(self, verts_b3v):
         """PyTorch3D ``Meshes.verts_normals_padded`` semantics: area-weighted face normals
         accumulated on vertices, normalised with eps 1e-6.  Only used when a normal renderer is plugged in."""
-        v = verts_b3v.permute(0, 2, 1)
-        f = self.faces
-        n = torch.cross(v[:, f[:, 1]] - v[:, f[:, 0]], v[:, f[:, 2]] - v[:, f[:, 0]], dim=-1)
-        vn = torch.zeros_like(v)
-        for k in range(3):
-            vn = vn.index_add(1, f[:, k], n)
-        return torch.nn.functional.normalize(vn, eps=1e-6, dim=-1)
+        from .mesh_renderer import vertex_normals
+        return vertex_normals(verts_b3v.permute(0, 2, 1), self.faces)
 
     def get_param_groups(self, cfg):
         """reference models/model.py:305-324 (lr names from configs/default.yaml:91-99)."""

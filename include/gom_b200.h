@@ -359,6 +359,47 @@ typedef struct {
 int gom_eval_metrics(const GomEvalMetricsArgs *a, gom_stream_t stream);
 
 /* --------------------------------------------------------------------------------------------------------------
+ * Mesh normal map + soft silhouette.  Replaces what reference models/modules/renderer/mesh.py:66-128 asks of PyTorch3D
+ * 0.7.0 on every Model.forward (models/model.py:271-274): MeshRasterizer(faces_per_pixel 1, blur 0) + NormalShader
+ * (per pixel: sum of the nearest inside face's three vertex normals, 0 on the background), and, when soft = 1
+ * (training), MeshRenderer(SoftSilhouetteShader) with faces_per_pixel = K and blur_radius:
+ *   alpha = 1 - prod_k (1 - sigmoid(-d_k / 1e-4)) over the K faces of smallest interpolated z whose signed squared
+ *   NDC distance d_k to the pixel centre is negative (inside) or below blur_radius.
+ * verts_ndc are the output of the reference's ndc_T_world (utils/pc_util.py:30-46): x, y in NDC (+X left, +Y up, the
+ * shorter image side spans [-1,1]), z = camera depth.  Faces are binned to 16x16 tiles into caller-owned lists of
+ * fixed capacity (overflow -> GOM_STATUS_OVERFLOW in status[b]).
+ * backward: dL_dvert_normals from dL_dnormal_map, dL_dverts_ndc (x, y; z gets 0) from dL_dalpha; both zeroed first.
+ */
+typedef struct {
+    int32_t n_frames, n_verts, n_faces, height, width;
+    int32_t faces_int64;         /* faces are int64 (the model's registered buffer) instead of int32 */
+    int32_t soft;                /* 1: also render the soft silhouette (training) */
+    int32_t faces_per_pixel;     /* K of the soft pass (reference: 50) */
+    float blur_radius;           /* of the soft pass, squared NDC units (reference: ln(1/1e-4 - 1) * sigma) */
+    int32_t _pad;
+    int64_t list_capacity;       /* per-frame capacity of face_list */
+    const float *verts_ndc;      /* [B,V,3] */
+    const void *faces;           /* [F,3] */
+    const float *vert_normals;   /* [B,V,3] (already rotated into the camera frame, model.py:271-273) */
+    uint32_t *tile_count;        /* [B,T]   */
+    uint32_t *tile_offset;       /* [B,T+1] */
+    uint32_t *tile_cursor;       /* [B,T]   */
+    uint32_t *face_list;         /* [B,cap] face ids grouped by tile */
+    uint32_t *status;            /* [B] */
+    int32_t *pix_to_face;        /* [B,H,W] nearest inside face, -1 = none */
+    float *normal_map;           /* [B,H,W,3] */
+    float *alpha;                /* [B,H,W]   (soft) */
+    float *zcut;                 /* [B,H,W]   (soft) K-nearest cut kept for backward: +inf = no truncation */
+    int32_t *idcut;              /* [B,H,W]   (soft) */
+    const float *dL_dnormal_map; /* [B,H,W,3] (backward, nullable) */
+    const float *dL_dalpha;      /* [B,H,W]   (backward, nullable) */
+    float *dL_dverts_ndc;        /* [B,V,3]   (backward) */
+    float *dL_dvert_normals;     /* [B,V,3]   (backward) */
+} GomMeshRasterArgs;
+int gom_mesh_raster_forward(const GomMeshRasterArgs *a, gom_stream_t stream);
+int gom_mesh_raster_backward(const GomMeshRasterArgs *a, gom_stream_t stream);
+
+/* --------------------------------------------------------------------------------------------------------------
  * Adam over the flat parameter arena, one launch.  Replaces `optimizer.step()` of reference train.py:339 for the
  * parameter groups of models/model.py:305-324 (torch.optim.Adam semantics, amsgrad off, weight decay 0).  Segment s
  * covers arena elements [seg_end[s-1], seg_end[s]) with learning rate seg_lr[s]; grad_scale multiplies the gradient
@@ -397,6 +438,7 @@ size_t gom_sizeof_lpips_tap_args(void);
 size_t gom_sizeof_eval_metrics_args(void);
 size_t gom_sizeof_conv_first_args(void);
 size_t gom_sizeof_adam_args(void);
+size_t gom_sizeof_mesh_raster_args(void);
 
 #ifdef __cplusplus
 }
