@@ -134,17 +134,28 @@ __device__ __forceinline__ float warp_sum(float v) {
 // ------------------------------------------------------------------------------------------- per-warp entry culling
 // A warp of the blend kernels owns an 8x4-pixel sub-block of a 16x16 tile (lane -> (lane & 7, lane >> 3)).  A list
 // entry can only pass the per-pixel test  alpha = min(.99, o * exp(power)) >= 1/255  somewhere in that sub-block if
-// the axis-aligned bounding box of its ellipse  {q <= 2 ln(255 o)},  q = A dx^2 + 2 B dx dy + C dy^2 = -2 power,
-// reaches the sub-block: half extents sqrt(s C / det), sqrt(s A / det) (the ellipse's covariance is the inverse
-// conic).  The test is conservative (1e-3 relative + 0.01 px of slack against rounding), so skipping entries that
-// fail it changes no pixel: they would all have taken the `alpha < 1/255` branch.  Entries are tested one per lane
-// and the survivors visited through the ballot mask.
+// the minimum over the sub-block's rectangle of  q = A dx^2 + 2 B dx dy + C dy^2 = -2 power  is at most
+// s = 2 ln(255 o).  q is a positive-definite quadratic, so its minimum over a rectangle that does not contain the
+// centre lies on the rectangle's boundary: four clamped 1-D minimisations.  The test is conservative (s is inflated by
+// 1e-3 relative + 1e-3 against rounding, and the rectangle is the continuous hull of the pixel centres), so skipping
+// entries that fail it changes no pixel: they would all have taken the `alpha < 1/255` branch.  Entries are tested
+// one per lane (the cost is per 32 entries, not per entry) and the survivors visited through the ballot mask.
+__device__ __forceinline__ float q_min_on_vertical(float A, float B, float C, float dx, float ylo, float yhi) {
+    const float dy = fminf(fmaxf(__fdividef(-B * dx, C), ylo), yhi);     // argmin over dy of q(dx, dy)
+    return A * dx * dx + 2.f * B * dx * dy + C * dy * dy;
+}
 __device__ __forceinline__ bool entry_reaches_rect(float2 c, float4 co, float rcx, float rcy, float rhw, float rhh) {
     const float ko = 255.0f * co.w;
     const float det = co.x * co.z - co.y * co.y;
-    if (!(ko > 1.0f) || !(det > 0.f)) return ko > 1.0f;           // degenerate conic: never cull (visible if o > 1/255)
+    if (!(ko > 1.0f)) return false;                                      // alpha < 1/255 everywhere
+    if (!(det > 0.f) || !(co.x > 0.f) || !(co.z > 0.f)) return true;     // degenerate conic: never cull
     const float s = 2.0f * __logf(ko) * 1.001f + 1e-3f;
-    const float inv = __fdividef(s, det);
-    const float ex = sqrtf(inv * co.z) + 0.01f, ey = sqrtf(inv * co.x) + 0.01f;
-    return fabsf(c.x - rcx) <= rhw + ex && fabsf(c.y - rcy) <= rhh + ey;
+    // rectangle relative to the centre, d = centre - pixel: dx in [xlo, xhi], dy in [ylo, yhi]
+    const float xlo = c.x - rcx - rhw, xhi = c.x - rcx + rhw, ylo = c.y - rcy - rhh, yhi = c.y - rcy + rhh;
+    if (xlo <= 0.f && xhi >= 0.f && ylo <= 0.f && yhi >= 0.f) return true;   // centre inside the sub-block
+    float q = q_min_on_vertical(co.x, co.y, co.z, xlo, ylo, yhi);
+    q = fminf(q, q_min_on_vertical(co.x, co.y, co.z, xhi, ylo, yhi));
+    q = fminf(q, q_min_on_vertical(co.z, co.y, co.x, ylo, xlo, xhi));        // horizontal edges: swap the roles of x and y
+    q = fminf(q, q_min_on_vertical(co.z, co.y, co.x, yhi, xlo, xhi));
+    return q <= s;
 }

@@ -173,17 +173,18 @@ __device__ void block_sort(unsigned long long *k, int n, int tid) {
     int npad = 2;
     while (npad < n) npad <<= 1;
     const int half = npad >> 1;
-    for (int size = 2; size <= npad; size <<= 1) {
-        const int hs = size >> 1;
+    for (int lsize = 1; (1 << lsize) <= npad; lsize++) {               // sizes are powers of two: shifts, no divisions
+        const int size = 1 << lsize, hs = size >> 1, lhs = lsize - 1;
         for (int t = tid; t < half; t += kThreads) {                  // flip
-            const int blk = t / hs, w = t - blk * hs;
-            const int i = blk * size + w, j = blk * size + (size - 1 - w);
+            const int blk = t >> lhs, w = t & (hs - 1);
+            const int i = (blk << lsize) + w, j = (blk << lsize) + (size - 1 - w);
             if (j < n) cmpxchg(k, i, j);
         }
         __syncthreads();
-        for (int step = hs >> 1; step >= 1; step >>= 1) {              // disperse
+        for (int lstep = lhs - 1; lstep >= 0; lstep--) {               // disperse
+            const int step = 1 << lstep;
             for (int t = tid; t < half; t += kThreads) {
-                const int i = 2 * step * (t / step) + (t % step), j = i + step;
+                const int i = ((t >> lstep) << (lstep + 1)) + (t & (step - 1)), j = i + step;
                 if (j < n) cmpxchg(k, i, j);
             }
             __syncthreads();

@@ -131,7 +131,7 @@ def _heads(golden_dir):
 
 
 @pytest.mark.parametrize("C,h,w,pool", [(64, 12, 10, True), (128, 7, 9, True), (256, 6, 6, True), (512, 4, 6, True),
-                                        (512, 5, 3, False), (32, 8, 8, True)])
+                                        (512, 5, 3, False), (32, 8, 8, True), (64, 37, 50, True), (128, 18, 17, False)])
 def test_lpips_tap_kernels_match_torch(C, h, w, pool):
     """One tapped layer: normalise -> squared difference -> 1x1 head -> spatial mean (+ 2x2 max-pool), forward and
     backward incl. ReLU mask and torch's first-maximum tie-breaking, against float64 torch autograd on the CPU."""
