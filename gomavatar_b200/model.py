@@ -54,6 +54,28 @@ def rodrigues(rvec):
                         x * z * oc - y * s, y * z * oc + x * s, z * z + (1.0 - z * z) * c), dim=1).view(-1, 3, 3)
 
 
+def mesh_edges(faces, vertices):
+    """(edge lengths [E] in PyTorch3D ``edges_packed`` order — unique (min, max) vertex pairs sorted by min * V + max —
+    and the pairs of faces that share an edge [E', 2]) of reference model.py:115-134.  Like the reference's
+    ``range(max_edge_id)`` loop, the edge with the largest id is left out of the connectivity."""
+    V = vertices.shape[0]
+    e = np.concatenate([faces[:, [1, 2]], faces[:, [2, 0]], faces[:, [0, 1]]], axis=0)
+    e = np.sort(e, axis=1)
+    key = e[:, 0].astype(np.int64) * V + e[:, 1]
+    uniq, inv = np.unique(key, return_inverse=True)
+    ev = np.stack([uniq // V, uniq % V], axis=1)
+    length = np.linalg.norm(vertices[ev[:, 0]] - vertices[ev[:, 1]], axis=1).astype(np.float32)
+    F = faces.shape[0]
+    face_of = np.tile(np.arange(F), 3)
+    order = np.lexsort((face_of, inv))                     # by edge id, then face index (torch.nonzero order)
+    eid, fid = inv[order], face_of[order]
+    first = np.flatnonzero(np.r_[True, eid[1:] != eid[:-1]])
+    count = np.diff(np.r_[first, len(eid)])
+    keep = (count == 2) & (eid[first] < uniq.shape[0] - 1)
+    conn = np.stack([fid[first[keep]], fid[first[keep] + 1]], axis=1).astype(np.int64)
+    return length, conn
+
+
 class AppearanceModule(nn.Module):
     """reference models/modules/appearance_module.py:6-23 — per-face RGB + zero background buffer."""
 
@@ -88,10 +110,22 @@ class Model(nn.Module):
         else:
             self.register_buffer("scale", torch.ones(3, F) * radius)
         self.appearance_module = AppearanceModule(F, float(_get(model_cfg, "appearance.color_init", 0.5)))
-        self.pose_refinement_module = pose_refinement_module
-        self.non_rigid_module = non_rigid_module
-        self.normal_renderer = normal_renderer
-        self.shadow_module = shadow_module
+        # The modules around the hot path (reference model.py:88-113): explicit arguments win; otherwise they are built
+        # from the reference's own cfg nodes (`name != 'none'`) with this package's implementations.
+        from . import mesh_renderer, modules
+        def build(given, node, ctor):
+            if given is not None:
+                return given
+            sub = _get(model_cfg, node, None)
+            return ctor(sub) if sub is not None and _get(sub, "name", "none") != "none" else None
+        self.pose_refinement_module = build(pose_refinement_module, "pose_refinement", modules.PoseRefinementModule)
+        self.non_rigid_module = build(non_rigid_module, "non_rigid", modules.NonRigidModule)
+        self.normal_renderer = build(normal_renderer, "normal_renderer", lambda sub: mesh_renderer.Renderer(
+            sub, canonical_info, img_size=_get(model_cfg, "img_size", [512, 512])))
+        self.shadow_module = build(shadow_module, "shadow_module", modules.ShadowModule)
+        tel, conn = mesh_edges(faces.numpy(), verts.numpy().T)
+        self.register_buffer("target_edge_length", torch.from_numpy(tel))       # reference model.py:58-60,127-134
+        self.register_buffer("face_connectivity", torch.from_numpy(conn), persistent=False)
         self.strict_raster = strict_raster
         self.last_raster_aux = None
 
@@ -145,6 +179,8 @@ class Model(nn.Module):
         outputs = {}
         if self.training:
             outputs["colors"] = appearance.permute(1, 0)
+            outputs["face_connectivity"] = self.face_connectivity
+            outputs["target_edge_length"] = self.target_edge_length
             outputs["vertices_observation"] = vertices_observation
             outputs["albedo"] = albedos[0]
             outputs["radii"] = radii

@@ -1,0 +1,151 @@
+"""The three small MLPs around the hot path, in plain torch, so that ``gomavatar_b200.model.Model`` is complete behind
+the reference's ``Model(model_cfg, canonical_info)`` constructor without importing the reference (SURVEY.md §2 rows
+6-8; they are dense cuBLAS work outside the north-star path):
+
+* ``ShadowModule``          reference models/modules/shadow_module.py:67-117 — per-pixel normal -> positional encoding
+                            (input + sin/cos at 2^0..2^(multires-1)) -> MLP -> sigmoid
+* ``NonRigidModule``        reference models/modules/non_rigid_module.py:75-147 — pose-conditioned vertex offsets,
+                            positional encoding faded in by a Hann window over training iterations (:15-72)
+* ``PoseRefinementModule``  reference models/modules/pose_refinement_module.py:10-48 — pose vector -> per-joint axis-angle
+                            corrections -> rotation matrices (root = identity)
+
+State-dict keys (``block_mlps.N.weight / bias``) and initialisation match the reference (Xavier-uniform with the ReLU
+gain, last layer U(-1e-5, 1e-5) with zero bias: utils/network_util.py:403-461), so reference checkpoints load unchanged;
+tests/golden/golden_modules.npz pins the forward passes against the reference's own modules.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn as nn
+
+
+def _get(cfg, key, default=None):
+    if cfg is None:
+        return default
+    if isinstance(cfg, dict):
+        return cfg.get(key, default)
+    return getattr(cfg, key, default)
+
+
+def _init_linear(m, gain):
+    nn.init.xavier_uniform_(m.weight, gain)
+    nn.init.zeros_(m.bias)
+
+
+def _mlp(in_dim, cond_dim, width, depth, out_dim, skips, init_last=1e-5):
+    """Linear/ReLU stack of the reference: layer i in `skips` (counted in Linear layers, from 1) re-reads the encoding."""
+    layers, cat_at = [nn.Linear(in_dim + cond_dim, width), nn.ReLU()], []
+    for i in range(1, depth):
+        if i in skips:
+            cat_at.append(len(layers))
+            layers += [nn.Linear(width + in_dim, width), nn.ReLU()]
+        else:
+            layers += [nn.Linear(width, width), nn.ReLU()]
+    layers.append(nn.Linear(width, out_dim))
+    mods = nn.ModuleList(layers)
+    relu_gain = nn.init.calculate_gain("relu")
+    for m in layers[:-1]:
+        if isinstance(m, nn.Linear):
+            _init_linear(m, relu_gain)
+    nn.init.uniform_(layers[-1].weight, -init_last, init_last)
+    nn.init.zeros_(layers[-1].bias)
+    return mods, cat_at
+
+
+def _run(mods, cat_at, h, enc):
+    for i, m in enumerate(mods):
+        if i in cat_at:
+            h = torch.cat([h, enc], dim=-1)
+        h = m(h)
+    return h
+
+
+def posenc(x, multires, include_input=True, window=None):
+    """[..., 3] -> [..., 3 (+3) * 2 * multires]: (x,) then for each frequency 2^k: sin(2^k x), cos(2^k x), each block
+    optionally scaled by window[k]."""
+    freqs = 2.0 ** torch.arange(multires, dtype=x.dtype, device=x.device)
+    xf = x[..., None, :] * freqs[:, None]                                   # [..., F, 3]
+    sc = torch.stack([torch.sin(xf), torch.cos(xf)], dim=-2)                # [..., F, 2, 3]
+    if window is not None:
+        sc = sc * window.to(x.dtype).to(x.device)[:, None, None]
+    sc = sc.reshape(*x.shape[:-1], multires * 6)
+    return torch.cat([x, sc], dim=-1) if include_input else sc
+
+
+def hann_window(multires, i_iter, kick_in_iter, full_band_iter):
+    """reference non_rigid_module.py:33-43: w_k = (1 - cos(pi clamp(alpha - k, 0, 1))) / 2, alpha = m t / N."""
+    t = max(float(i_iter) - float(kick_in_iter), 0.0)
+    alpha = multires * t / (float(full_band_iter) - float(kick_in_iter))
+    k = torch.arange(multires, dtype=torch.float32)
+    return (1.0 - torch.cos(math.pi * torch.clamp(alpha - k, min=0.0, max=1.0))) / 2.0
+
+
+class ShadowModule(nn.Module):
+    def __init__(self, module_cfg=None, **kwargs):
+        super().__init__()
+        self.multires = int(_get(module_cfg, "multires", 6))
+        width, depth = int(_get(module_cfg, "mlp_width", 128)), int(_get(module_cfg, "mlp_depth", 3))
+        skips = list(_get(module_cfg, "skips", [4]))
+        self.block_mlps, self.layers_to_cat_inputs = _mlp(3 + 6 * self.multires, 0, width, depth, 1, skips,
+                                                          float(_get(module_cfg, "init_scale", 1e-5)))
+
+    def forward(self, normals, **kwargs):
+        enc = posenc(normals, self.multires, include_input=True)
+        return torch.sigmoid(_run(self.block_mlps, self.layers_to_cat_inputs, enc, enc))
+
+
+class NonRigidModule(nn.Module):
+    def __init__(self, module_cfg=None, **kwargs):
+        super().__init__()
+        self.multires = int(_get(module_cfg, "multires", 6))
+        self.kick_in_iter = float(_get(module_cfg, "kick_in_iter", 0))
+        self.full_band_iter = float(_get(module_cfg, "full_band_iter", 50000))
+        self.update_rot, self.update_scale = bool(_get(module_cfg, "update_rot", False)), bool(_get(module_cfg, "update_scale", False))
+        if self.update_rot or self.update_scale:
+            raise NotImplementedError("update_rot / update_scale are off in every reference config (exps/*.yaml)")
+        width, depth = int(_get(module_cfg, "mlp_width", 128)), int(_get(module_cfg, "mlp_depth", 6))
+        self.block_mlps, self.layers_to_cat_inputs = _mlp(6 * self.multires, int(_get(module_cfg, "condition_code_size", 69)),
+                                                          width, depth, 3, list(_get(module_cfg, "skips", [4])),
+                                                          float(_get(module_cfg, "init_scale", 1e-5)))
+
+    def forward(self, xyzs_skeleton, dst_posevec, i_iter, R=None, S=None):
+        """xyzs_skeleton [B,3,V], dst_posevec [B,69] -> (xyzs_skeleton + offset [B,3,V], R, S)"""
+        xyzs = xyzs_skeleton.permute(0, 2, 1)
+        B, N, _ = xyzs.shape
+        if B != dst_posevec.shape[0]:
+            xyzs = xyzs.expand(dst_posevec.shape[0], -1, -1)
+            B = dst_posevec.shape[0]
+        enc = posenc(xyzs, self.multires, include_input=False,
+                     window=hann_window(self.multires, i_iter, self.kick_in_iter, self.full_band_iter))
+        h = torch.cat([dst_posevec[:, None, :].expand(B, N, -1), enc], dim=-1)
+        offset = _run(self.block_mlps, self.layers_to_cat_inputs, h, enc)
+        return xyzs_skeleton + offset.permute(0, 2, 1), R, S
+
+
+class PoseRefinementModule(nn.Module):
+    def __init__(self, module_cfg=None, **kwargs):
+        super().__init__()
+        emb, width, depth = int(_get(module_cfg, "embedding_size", 69)), int(_get(module_cfg, "mlp_width", 256)), int(_get(module_cfg, "mlp_depth", 4))
+        self.refine_root = bool(_get(module_cfg, "refine_root", False))
+        total = int(_get(module_cfg, "total_bones", 24))
+        self.total_bones = total if self.refine_root else total - 1
+        layers = [nn.Linear(emb, width), nn.ReLU()]
+        for _ in range(depth - 1):
+            layers += [nn.Linear(width, width), nn.ReLU()]
+        layers.append(nn.Linear(width, 3 * self.total_bones))
+        self.block_mlps = nn.Sequential(*layers)
+        g = nn.init.calculate_gain("relu")
+        for m in layers[:-1]:
+            if isinstance(m, nn.Linear):
+                _init_linear(m, g)
+        nn.init.uniform_(layers[-1].weight, -1e-5, 1e-5)
+        nn.init.zeros_(layers[-1].bias)
+
+    def forward(self, dst_posevec, **kwargs):
+        from .model import rodrigues
+        rvec = self.block_mlps(dst_posevec).view(-1, 3)
+        Rs = rodrigues(rvec).view(-1, self.total_bones, 3, 3)
+        eye = torch.eye(3, device=Rs.device, dtype=Rs.dtype)[None, None].expand(Rs.shape[0], 1, 3, 3)
+        return torch.cat([eye, Rs], dim=1)

@@ -241,5 +241,62 @@ def main():
         print("  ", f, os.path.getsize(os.path.join(OUT, f)), "bytes")
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and len(sys.argv) == 1:
     main()
+
+
+def modules_golden():
+    """``python -m oracle.make_golden modules``: golden_modules.npz — the reference's OWN ShadowModule, NonRigidModule and
+    PoseRefinementModule (models/modules/*.py imported unchanged; their pytorch3d imports are stubbed, none is used on
+    these paths) built from exps/zju-mocap_377.yaml, every parameter re-drawn from a seeded generator (the reference's
+    1e-5 last-layer init would make the outputs trivially small), run on seeded inputs."""
+    assert os.path.isdir(REF)
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, REF)
+    _install_stubs()
+    cwd = os.getcwd()
+    os.chdir(REF)
+    try:
+        from configs import make_cfg
+        cfg = make_cfg("exps/zju-mocap_377.yaml")
+        from models.modules.shadow_module import ShadowModule
+        from models.modules.non_rigid_module import NonRigidModule
+        from models.modules.pose_refinement_module import PoseRefinementModule
+    finally:
+        os.chdir(cwd)
+    g = torch.Generator().manual_seed(11)
+    out = {}
+
+    def redraw(mod, prefix):
+        for k, v in mod.state_dict().items():
+            new = torch.randn(v.shape, generator=g) * (0.3 if v.dim() > 1 else 0.1) / (v.shape[-1] ** 0.5 if v.dim() > 1 else 1.0) * 3
+            v.copy_(new)
+            out[f"{prefix}.{k}"] = new.numpy()
+
+    with torch.no_grad():
+        sh = ShadowModule(cfg.model.shadow_module)
+        redraw(sh, "shadow")
+        n = torch.nn.functional.normalize(torch.randn(2, 500, 3, generator=g), dim=-1) * torch.rand(2, 500, 1, generator=g) * 3
+        n[0, :50] = 0                                          # background pixels carry a zero normal
+        out["shadow_in"], out["shadow_out"] = n.numpy(), sh(n).numpy()
+        nr = NonRigidModule(cfg.model.non_rigid)
+        redraw(nr, "non_rigid")
+        xyz = torch.randn(2, 3, 300, generator=g) * 0.5
+        pv = torch.randn(2, 69, generator=g) * 0.3
+        out["non_rigid_xyz"], out["non_rigid_posevec"] = xyz.numpy(), pv.numpy()
+        for it in (150000, 163000, 187500, 300000):
+            out[f"non_rigid_out_{it}"] = nr(xyz, pv, it)[0].numpy()
+        pr = PoseRefinementModule(cfg.model.pose_refinement)
+        redraw(pr, "pose_refinement")
+        out["pose_in"] = pv.numpy()
+        out["pose_out"] = pr(pv).numpy()
+    for name in ("shadow_module", "non_rigid", "pose_refinement"):
+        for k, v in dict(cfg.model[name]).items():
+            if isinstance(v, (int, float)):
+                out[f"cfg.{name}.{k}"] = np.float64(v)
+    np.savez_compressed(os.path.join(OUT, "golden_modules.npz"), **out)
+    print("golden_modules.npz:", len(out), "arrays")
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "modules":
+    modules_golden()

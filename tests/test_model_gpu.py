@@ -114,3 +114,73 @@ def test_state_dict_keys_match_reference_checkpoint_layout(golden_dir):
     assert {"faces", "lbs_weights", "vertices", "so3", "scale", "appearance_module.appearance",
             "appearance_module.bg_col"} <= keys
     assert m.vertices.shape[0] == 3 and m.so3.shape[0] == 3 and m.lbs_weights.shape[0] == 25
+
+
+def test_full_model_with_all_reference_modules_matches_oracle_composition():
+    """Model built from a reference-shaped cfg (pose refinement, non-rigid, mesh normal renderer, shadow MLP all on):
+    rgbs = albedo * shading, masks, normal map and soft normal mask against the CPU composition of the oracles, and the
+    backward reaches every parameter group (reference models/model.py:184-303)."""
+    import copy
+    from gomavatar_b200.model import Model
+    from oracle import mesh_raster as MR
+    W = H = 64
+    cfg = {"img_size": [W, H], "eval_mode": False,
+           "canonical_geometry": {"sigma": 1e-3, "radius_scale": 1.0, "deform_scale": True, "deform_so3": True},
+           "appearance": {"color_init": 0.5},
+           "pose_refinement": {"name": "basic", "embedding_size": 69, "total_bones": 24, "mlp_width": 64, "mlp_depth": 2,
+                               "refine_root": False, "refine_t": False, "kick_in_iter": 0},
+           "non_rigid": {"name": "basic", "condition_code_size": 69, "mlp_width": 64, "mlp_depth": 3, "skips": [4], "multires": 6,
+                         "i_embed": 0, "kick_in_iter": 0, "full_band_iter": 10},
+           "normal_renderer": {"name": "mesh", "soft_mask": True, "sigma": 1e-5},
+           "shadow_module": {"name": "basic", "mlp_width": 64, "mlp_depth": 3, "skips": [4], "multires": 6}}
+    sc = S.make_humanoid(2000, seed=0)
+    fr = S.make_frames(sc, 1, img_size=(W, H), seed=3)
+    pr = S.make_params(sc, seed=1)
+    torch.manual_seed(4)
+    m = Model(cfg, sc.canonical_info())
+    assert m.pose_refinement_module is not None and m.non_rigid_module is not None and m.normal_renderer is not None and m.shadow_module is not None
+    with torch.no_grad():
+        m.so3.copy_(t(pr["so3"])); m.scale.copy_(t(pr["scale"])); m.appearance_module.appearance.copy_(t(pr["appearance"]))
+        m.pose_refinement_module.block_mlps[-1].weight.normal_(0, 2e-3)          # a visible pose correction
+        m.non_rigid_module.block_mlps[-1].weight.normal_(0, 2e-4)                # a visible (sub-centimetre) offset
+        m.shadow_module.block_mlps[-1].weight.normal_(0, 0.3)
+    cpu = copy.deepcopy(m)                                                       # same weights for the CPU composition
+    m = m.to(DEV).train()
+    d = {k: t(v).to(DEV) for k, v in fr.items()}
+    rgbs, masks, out = m(d["K"], d["E"], d["cnl_gtfms"], d["dst_Rs"], d["dst_Ts"], dst_posevec=d["dst_posevec"], i_iter=7)
+    for k in ("colors", "face_connectivity", "target_edge_length", "albedo", "normal", "normal_mask", "shadow"):
+        assert k in out, k
+    # ---- CPU composition
+    with torch.no_grad():
+        pv = t(fr["dst_posevec"])
+        dR = torch.matmul(t(fr["dst_Rs"]).reshape(-1, 3, 3), cpu.pose_refinement_module(pv).reshape(-1, 3, 3)).reshape(1, 24, 3, 3)
+        v_pose, _, _ = cpu.non_rigid_module(cpu.vertices[None], pv, 7)
+        v_obs, xyz, cov = G.pose_geometry(v_pose[0], t(sc.faces), t(sc.lbs_weights), t(pr["so3"]), t(pr["scale"]),
+                                          t(fr["cnl_gtfms"][0]), dR[0], t(fr["dst_Ts"][0]))
+        st = Cam.raster_settings_from_KE(fr["K"][0], fr["E"][0], (W, H))
+        app = pr["appearance"].T
+        feat = np.ascontiguousarray(np.concatenate([app, np.ones_like(app[:, :1])], 1), dtype=np.float32)
+        f = R.forward(xyz.numpy(), G.pack_cov6(cov).numpy(), feat, np.ones(len(app), np.float32), st.viewmatrix, st.projmatrix,
+                      st.tanfovx, st.tanfovy, np.zeros(4, np.float32), H, W)
+        albedo = t(f["color"].transpose(1, 2, 0).copy())
+        nm, nmask = MR.render(v_obs.T.contiguous(), t(sc.faces).long(), t(fr["K"][0]), t(fr["E"][0]), H, W, training=True, sigma_cfg=1e-5)
+        shade = cpu.shadow_module(nm.reshape(1, H * W, 3)).reshape(H, W, 1) * 2
+        ref_rgb = albedo[..., :3] * shade
+    got = rgbs[0].detach().cpu().numpy()
+    err = np.abs(got - ref_rgb.numpy())
+    assert (err > 1e-4 * np.abs(ref_rgb.numpy()) + 2e-5).mean() <= 3e-3 and err.max() < 5e-2, (float(err.max()), float((err > 1e-4).mean()))
+    _close_image(masks[0].detach().cpu().numpy(), albedo[..., 3].numpy(), "mask")
+    dn = np.abs(out["normal"][0].detach().cpu().numpy() - nm.numpy()).max(-1)
+    assert (dn > 1e-4).mean() <= 3e-3
+    dm = np.abs(out["normal_mask"][0].detach().cpu().numpy() - nmask.numpy())
+    assert (dm > 2e-3).mean() <= 3e-3
+    # ---- backward reaches every parameter group
+    rng = np.random.default_rng(0)
+    loss = (rgbs * t(rng.normal(size=(1, H, W, 3)).astype(np.float32)).to(DEV)).sum() + masks.sum() + out["normal_mask"].sum()
+    loss.backward()
+    for name, p in m.named_parameters():
+        assert p.grad is not None and torch.isfinite(p.grad).all(), name
+        assert float(p.grad.abs().max()) > 0, name
+    names = {g["name"] for g in m.get_param_groups({"lr": {"appearance": 1e-3, "canonical_geometry": 1e-3, "canonical_geometry_xyz": 1e-3,
+                                                           "non_rigid": 1e-3, "pose_refinement": 1e-4, "shadow": 1e-3}})}
+    assert {"appearance", "canonical_geometry_xyz", "canonical_geometry", "non_rigid", "pose_refinement", "shadow"} <= names
