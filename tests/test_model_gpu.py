@@ -184,3 +184,56 @@ def test_full_model_with_all_reference_modules_matches_oracle_composition():
     names = {g["name"] for g in m.get_param_groups({"lr": {"appearance": 1e-3, "canonical_geometry": 1e-3, "canonical_geometry_xyz": 1e-3,
                                                            "non_rigid": 1e-3, "pose_refinement": 1e-4, "shadow": 1e-3}})}
     assert {"appearance", "canonical_geometry_xyz", "canonical_geometry", "non_rigid", "pose_refinement", "shadow"} <= names
+
+
+def test_hot_path_is_cuda_graph_capturable(golden_dir):
+    """No host sync, no allocation outside torch's allocator, every launch on the caller's stream: forward + photometric
+    loss + backward of the hot path captured ONCE in a CUDA graph and replayed on new inputs equals the eager result
+    (the reference's rasterizer reads num_rendered back to the host twice per frame and cannot be captured)."""
+    from gomavatar_b200.losses import photometric_l1
+    g = np.load(os.path.join(golden_dir, "golden_model.npz"))
+    m, sc = _model_from_golden(g)
+    m.strict_raster = False                                   # overflow is a device flag, checked after the replay
+    B, H, W = 2, 64, 64
+    keys = ("K", "E", "cnl_gtfms", "dst_Rs", "dst_Ts", "bgcolor")
+    static = {k: t(g[k][:B]).to(DEV).clone() for k in keys}
+    rng = np.random.default_rng(3)
+    gt = t(rng.random((B, H, W, 3)).astype(np.float32)).to(DEV)
+    gtm = t((rng.random((B, H, W)) > 0.5).astype(np.float32)).to(DEV)
+    params = [m.vertices, m.so3, m.scale, m.appearance_module.appearance]
+    for p in params:
+        p.grad = torch.zeros_like(p)
+
+    def step():
+        for p in params:
+            p.grad.zero_()
+        rgb, mask, _ = m(static["K"], static["E"], static["cnl_gtfms"], static["dst_Rs"], static["dst_Ts"])
+        _, l_rgb, l_mask = photometric_l1(rgb, mask, static["bgcolor"], gt, gtm)
+        loss = l_rgb + 5.0 * l_mask
+        loss.backward()
+        return loss.detach(), rgb.detach()
+
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):                             # warm-up on a side stream, as torch's capture recipe asks
+        for _ in range(2):
+            step()
+    torch.cuda.current_stream().wait_stream(side)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        loss_g, rgb_g = step()
+    # new inputs: frames 1..2 instead of 0..1
+    for k in keys:
+        static[k].copy_(t(g[k][1:1 + B]).to(DEV))
+    graph.replay()
+    torch.cuda.synchronize()
+    got = [p.grad.clone() for p in params]
+    loss_replay, rgb_replay = loss_g.clone(), rgb_g.clone()
+    assert int(m.last_raster_aux["status"].max()) == 0
+    loss_e, rgb_e = step()                                    # eager on the same (new) inputs
+    torch.cuda.synchronize()
+    assert torch.equal(rgb_replay, rgb_e)
+    np.testing.assert_allclose(float(loss_replay), float(loss_e), rtol=1e-6)
+    for a, p in zip(got, params):
+        ref = p.grad
+        assert float((a - ref).abs().max()) <= 1e-4 * float(ref.abs().max()) + 1e-12      # atomics reorder the sums
