@@ -108,9 +108,10 @@ class ClockSampler:
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed `ncu --set full`
 # capture of this same command (profiles/); filled in by hand after each capture, None = not captured yet.
-NCU_TRAFFIC_BYTES = {      # profiles/r1f_ncu_full_summary.md (8 frames, 512x512): mean over the kernel's launches in one step,
-    # like `achieved` (tap_bwd 5 launches 3199.6 MB, tap_fwd 5 launches 2487.4 MB, relu_bwd 8 launches 3423.5 MB)
-    "lpips_tap_bwd": 639.9e6, "lpips_tap_fwd": 497.5e6, "relu_bwd": 427.9e6, "blend_bwd": 16.4e6, "sort_blend_fwd": 16.9e6}
+NCU_TRAFFIC_BYTES = {      # profiles/r1s_ncu_full_summary.md (8 frames, 512x512): mean over the kernel's launches in one step,
+    # like `achieved` (tap_bwd 5 launches 3201.5 MB, tap_fwd 5 launches 2497.0 MB, relu_bwd 8 launches 3418.0 MB)
+    "lpips_tap_bwd": 640.3e6, "lpips_tap_fwd": 499.4e6, "relu_bwd": 427.2e6, "conv_first_fwd": 1079.0e6,
+    "conv_first_bwd": 581.1e6, "blend_bwd": 16.4e6, "sort_blend_fwd": 16.8e6}
 
 _VGG_LEVELS = ((64, 2), (128, 2), (256, 3), (512, 3), (512, 3))      # (channels, convolutions) per VGG16 block
 

@@ -3,7 +3,7 @@
 // Replaces `optimizer.step()` of reference train.py:339 (torch.optim.Adam over the 6-8 parameter groups of
 // models/model.py:305-324; per-group learning rates, exponentially decayed by train.py:166-175) for the parameters
 // that live in gomavatar_b200.dist.FlatArena.  torch's fused Adam costs ~50 us per tensor list on B200 (4 launches,
-// profiles/r1f_launches_step.md) for 1.3 MB of state; here the whole arena is one grid-stride pass, the per-group
+// profiles/r1s_launches_step.md) for 1.3 MB of state; here the whole arena is one grid-stride pass, the per-group
 // learning rate is looked up from a segment table passed by value, and the 1/world_size of the gradient all-reduce
 // is folded in (grad_scale).  Same arithmetic as torch.optim.Adam (amsgrad off, weight decay 0):
 //   m = b1 m + (1-b1) g;  v = b2 v + (1-b2) g^2;  p -= (lr / (1-b1^t)) * m / (sqrt(v) / sqrt(1-b2^t) + eps)

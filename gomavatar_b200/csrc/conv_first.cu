@@ -4,7 +4,7 @@
 // Replaces, for reference utils/lpips/pretrained_networks.py:96-134 (`vgg16().features[0:2]`, slice1's conv1_1 +
 // ReLU) what cuDNN runs on B200 as a pre-Blackwell `sm80_xmma_fprop_implicit_gemm_indexed_wo_smem_tf32` kernel plus
 // two layout-conversion helpers (0.5 ms per 16 images at 512x512 — as long as conv1_2, which has 21x the FLOPs; see
-// profiles/r1f_launches_step.md) and a 0.4 ms TF32 dgrad.  With K = 27 the layer is not tensor-core work: it is bound
+// profiles/r1s_launches_step.md) and a 0.4 ms TF32 dgrad.  With K = 27 the layer is not tensor-core work: it is bound
 // by writing 64 channels per pixel (forward) / reading them (backward).  Here it is exact fp32 on the CUDA cores:
 //   forward : lane = output-channel pair, weights live in registers, a 3x3x3 input window slides along the row in
 //             registers (9 shared-memory broadcasts per pixel), 27 packed FFMA2 (Blackwell `fma.rn.f32x2`) per pixel,

@@ -1,0 +1,110 @@
+"""The mesh regularisers of the reference's training loss (reference train.py:123-160) without PyTorch3D, and the full
+``compute_loss`` that combines them with the photometric terms of ``gomavatar_b200.losses``.
+
+* ``laplacian_smoothing``   reference utils/network_util.py:669-792 with method "uniform": mean_i |sum_j (v_j - v_i)/deg(i)|^2
+                            (PyTorch3D ``Meshes.laplacian_packed``: L_ij = 1/deg(i) on edges, L_ii = -1)
+* ``normal_consistency``    pytorch3d.loss.mesh_normal_consistency (train.py:149): mean over pairs of faces sharing an
+                            edge of 1 - cos(n0, n1), normals taken with respect to the shared edge — PARITY UNPINNED
+                            (PyTorch3D absent offline; restated from its published source)
+* ``color_consistency``     reference utils/network_util.py:795-799
+* ``normal_mask_loss``      reference train.py:137-146: L1 between the soft mesh silhouette and the 7x7-dilated gt mask
+
+They are small sparse / elementwise torch ops on [V,3] / [F,3] tensors, not kernels.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn.functional as F
+
+from . import losses as L
+
+
+def unique_edges(faces, n_verts):
+    """[E,2] unique undirected edges (PyTorch3D ``edges_packed`` order: sorted by min * V + max)."""
+    f = faces.long()
+    e = torch.cat([f[:, [1, 2]], f[:, [2, 0]], f[:, [0, 1]]], dim=0)
+    e, _ = torch.sort(e, dim=1)
+    key = torch.unique(e[:, 0] * n_verts + e[:, 1], sorted=True)
+    return torch.stack([key // n_verts, key % n_verts], dim=1)
+
+
+def laplacian_smoothing(verts, faces, edges=None):
+    """verts [V,3] -> scalar."""
+    V = verts.shape[0]
+    e = unique_edges(faces, V) if edges is None else edges
+    nbr = torch.zeros_like(verts).index_add(0, e[:, 0], verts[e[:, 1]]).index_add(0, e[:, 1], verts[e[:, 0]])
+    deg = torch.zeros(V, dtype=verts.dtype, device=verts.device).index_add(
+        0, e.reshape(-1), torch.ones(e.numel(), dtype=verts.dtype, device=verts.device))
+    lv = torch.where(deg[:, None] > 0, nbr / deg.clamp(min=1)[:, None] - verts, torch.zeros_like(verts))
+    return (lv.norm(dim=1) ** 2).mean()
+
+
+def normal_consistency(verts, faces, face_connectivity):
+    """face_connectivity [P,2]: pairs of faces sharing an edge (``Model.face_connectivity``)."""
+    f = faces.long()
+    fa, fb = f[face_connectivity[:, 0]], f[face_connectivity[:, 1]]                     # [P,3] each
+    shared = (fa[:, :, None] == fb[:, None, :]).any(dim=2)                              # which corners of fa are shared
+    other_a = (fa * (~shared)).sum(dim=1)                                               # the one unshared vertex of each face
+    shared_b = (fb[:, :, None] == fa[:, None, :]).any(dim=2)
+    other_b = (fb * (~shared_b)).sum(dim=1)
+    # the shared edge, in a fixed order (smaller vertex index first), as PyTorch3D's edges_packed stores it
+    big = torch.iinfo(torch.int64).max
+    v0 = torch.where(shared, fa, torch.full_like(fa, big)).min(dim=1).values
+    v1 = torch.where(shared, fa, torch.full_like(fa, -1)).max(dim=1).values
+    e = verts[v1] - verts[v0]
+    n0 = torch.cross(e, verts[other_a] - verts[v0], dim=1)
+    n1 = -torch.cross(e, verts[other_b] - verts[v0], dim=1)
+    return (1.0 - F.cosine_similarity(n0, n1, dim=1)).mean()
+
+
+def color_consistency(color, face_connectivity):
+    return (color[face_connectivity[:, 0]] - color[face_connectivity[:, 1]]).abs().mean()
+
+
+def normal_mask_loss(normal_mask, mask_gt, kernel_size=7, dilate=True):
+    if dilate:
+        mask_gt = F.max_pool2d(mask_gt.unsqueeze(1), kernel_size=kernel_size, stride=1, padding=kernel_size // 2).squeeze(1)
+    return (normal_mask - mask_gt).abs().mean()
+
+
+def _c(cfg, path, default=0.0):
+    cur = cfg
+    for k in path.split("."):
+        if cur is None:
+            return default
+        cur = cur.get(k, None) if isinstance(cur, dict) else getattr(cur, k, None)
+    return default if cur is None else cur
+
+
+def compute_loss(rgbs, masks, bgcolors, rgb_gt, mask_gt, outputs, model, loss_cfg, lpips_func=None):
+    """reference train.py::compute_loss (:98-163) + ``unpack`` (:325-326) on this package's kernels.  ``outputs`` is what
+    ``Model.forward`` returned, ``loss_cfg`` the reference's ``cfg.train.losses`` node (or a dict of the same shape).
+    Returns (total, {name: {'unscaled', 'scaled'}})."""
+    total, terms, _ = L.compute_loss(rgbs, masks, bgcolors, rgb_gt, mask_gt, lpips_func=lpips_func,
+                                     coeff_rgb=_c(loss_cfg, "rgb.coeff", 1.0), coeff_mask=_c(loss_cfg, "mask.coeff", 5.0),
+                                     coeff_lpips=_c(loss_cfg, "lpips.coeff", 1.0))
+    losses = {k: {"unscaled": v, "scaled": v * {"rgb": _c(loss_cfg, "rgb.coeff", 1.0), "mask": _c(loss_cfg, "mask.coeff", 5.0),
+                                               "lpips": _c(loss_cfg, "lpips.coeff", 1.0)}[k]} for k, v in terms.items()}
+
+    def add(name, value, coeff):
+        nonlocal total
+        losses[name] = {"unscaled": value, "scaled": value * coeff}
+        total = total + value * coeff
+
+    faces = model.faces
+    if _c(loss_cfg, "laplacian.coeff_canonical") > 0:
+        add("laplacian_canonical", laplacian_smoothing(model.vertices.T, faces), _c(loss_cfg, "laplacian.coeff_canonical"))
+    if _c(loss_cfg, "laplacian.coeff_observation") > 0:
+        vo = outputs["vertices_observation"]                       # [B,3,V]; the reference is batch 1
+        lap = torch.stack([laplacian_smoothing(v.T, faces) for v in vo]).mean()
+        add("laplacian_observation", lap, _c(loss_cfg, "laplacian.coeff_observation"))
+    if _c(loss_cfg, "normal.coeff_mask") > 0 and outputs.get("normal_mask") is not None:
+        add("normal_mask", normal_mask_loss(outputs["normal_mask"], mask_gt, int(_c(loss_cfg, "normal.kernel_size", 7)),
+                                            bool(_c(loss_cfg, "normal.mask_dilate", True))), _c(loss_cfg, "normal.coeff_mask"))
+    if _c(loss_cfg, "normal.coeff_consist") > 0:
+        vo = outputs["vertices_observation"]
+        nc = torch.stack([normal_consistency(v.T, faces, outputs["face_connectivity"]) for v in vo]).mean()
+        add("normal_consist", nc, _c(loss_cfg, "normal.coeff_consist"))
+    if _c(loss_cfg, "color_consist.coeff") > 0:
+        add("color_consist", color_consistency(outputs["colors"], outputs["face_connectivity"]), _c(loss_cfg, "color_consist.coeff"))
+    return total, losses

@@ -1,0 +1,55 @@
+"""CPU: the mesh regularisers (gomavatar_b200/regularizers.py) against independent dense restatements and, for the
+colour term, the reference's own function (utils/network_util.py:795-799 is three lines of torch)."""
+import numpy as np
+import torch
+
+from gomavatar_b200 import regularizers as RG
+from gomavatar_b200 import synthetic as S
+from gomavatar_b200.model import mesh_edges
+
+t = torch.from_numpy
+
+
+def _scene():
+    sc = S.make_humanoid(2000, seed=0)
+    v = t(sc.vertices).double() + 0.003 * torch.randn(sc.n_vertices, 3, dtype=torch.float64, generator=torch.Generator().manual_seed(1))
+    _, conn = mesh_edges(sc.faces.astype(np.int64), sc.vertices)
+    return sc, v, t(sc.faces).long(), t(conn)
+
+
+def test_uniform_laplacian_matches_dense_matrix():
+    sc, v, f, _ = _scene()
+    V = v.shape[0]
+    A = torch.zeros(V, V, dtype=torch.float64)
+    for a, b in ((0, 1), (1, 2), (2, 0)):
+        A[f[:, a], f[:, b]] = 1
+        A[f[:, b], f[:, a]] = 1
+    Lm = A / A.sum(1, keepdim=True) - torch.eye(V, dtype=torch.float64)          # PyTorch3D laplacian_packed (uniform)
+    ref = ((Lm @ v).norm(dim=1) ** 2).mean()
+    assert abs(float(RG.laplacian_smoothing(v, f)) - float(ref)) < 1e-14
+    vg = v.clone().requires_grad_(True)
+    RG.laplacian_smoothing(vg, f).backward()
+    assert torch.isfinite(vg.grad).all() and float(vg.grad.abs().max()) > 0
+
+
+def test_normal_consistency_matches_face_normal_formulation():
+    sc, v, f, conn = _scene()
+    n = torch.cross(v[f[:, 1]] - v[f[:, 0]], v[f[:, 2]] - v[f[:, 0]], dim=1)     # consistently oriented closed mesh
+    ref = (1 - torch.nn.functional.cosine_similarity(n[conn[:, 0]], n[conn[:, 1]], dim=1)).mean()
+    got = RG.normal_consistency(v, f, conn)
+    assert abs(float(got) - float(ref)) < 1e-12 and float(got) > 0
+    flat = torch.tensor([[0., 0, 0], [1, 0, 0], [0, 1, 0], [1, 1, 0]], dtype=torch.float64)
+    ff = torch.tensor([[0, 1, 2], [2, 1, 3]])
+    assert abs(float(RG.normal_consistency(flat, ff, torch.tensor([[0, 1]])))) < 1e-14      # coplanar faces: zero
+
+
+def test_color_consistency_and_normal_mask():
+    rng = np.random.default_rng(0)
+    col = t(rng.random((50, 3)))
+    conn = t(rng.integers(0, 50, size=(80, 2)))
+    ref = torch.abs(col[conn[:, 0]] - col[conn[:, 1]]).mean()                      # reference network_util.py:795-799
+    assert float(RG.color_consistency(col, conn)) == float(ref)
+    m = torch.zeros(1, 16, 16); m[0, 8, 8] = 1
+    nm = torch.zeros(1, 16, 16)
+    assert abs(float(RG.normal_mask_loss(nm, m, 7)) - 49 / 256) < 1e-7               # a point dilates to 7x7
+    assert abs(float(RG.normal_mask_loss(nm, m, 7, dilate=False)) - 1 / 256) < 1e-7
