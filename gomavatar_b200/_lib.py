@@ -13,8 +13,9 @@ from ctypes import c_int, c_int32, c_int64, c_size_t, c_void_p, c_float, c_char_
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libgom_b200.so")
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 STATUS_OVERFLOW = 1
+STATUS_TIMEOUT = 2
 
 
 class GomCameraArgs(ctypes.Structure):
@@ -150,6 +151,14 @@ class GomMeshRasterArgs(ctypes.Structure):
                 ("dL_dalpha", c_void_p), ("dL_dverts_ndc", c_void_p), ("dL_dvert_normals", c_void_p)]
 
 
+class GomShadowMlpArgs(ctypes.Structure):
+    _fields_ = [("n_pixels", c_int64), ("capacity", c_int64), ("multires", c_int32), ("width", c_int32), ("depth", c_int32),
+                ("save_hidden", c_int32), ("normals", c_void_p), ("W_in", c_void_p), ("b_in", c_void_p), ("W_hid", c_void_p),
+                ("b_hid", c_void_p), ("W_out", c_void_p), ("b_out", c_void_p), ("block_count", c_void_p),
+                ("fg_index", c_void_p), ("n_fg", c_void_p), ("w_images", c_void_p), ("bg_value", c_void_p), ("out", c_void_p),
+                ("hidden", c_void_p), ("status", c_void_p)]
+
+
 # every symbol include/gom_b200.h declares (tests check the .so exports all of them)
 EXPORTS = [
     "gom_abi_version", "gom_last_error", "gom_launch_count", "gom_profile_enable", "gom_profile_num_slots",
@@ -165,6 +174,7 @@ EXPORTS = [
     "gom_conv_first_forward", "gom_conv_first_backward", "gom_sizeof_conv_first_args",
     "gom_adam_step", "gom_sizeof_adam_args",
     "gom_mesh_raster_forward", "gom_mesh_raster_backward", "gom_sizeof_mesh_raster_args",
+    "gom_shadow_mlp_forward", "gom_shadow_mlp_weight_image_bytes", "gom_sizeof_shadow_mlp_args",
 ]
 
 _STRUCTS = {
@@ -174,7 +184,7 @@ _STRUCTS = {
     "lpips_input": GomLpipsInputArgs, "bias_relu": GomBiasReluArgs, "relu_bwd": GomReluBwdArgs,
     "lpips_tap": GomLpipsTapArgs, "eval_metrics": GomEvalMetricsArgs,
     "conv_first": GomConvFirstArgs, "adam": GomAdamArgs,
-    "mesh_raster": GomMeshRasterArgs,
+    "mesh_raster": GomMeshRasterArgs, "shadow_mlp": GomShadowMlpArgs,
 }
 _ENTRY_POINTS = ["gom_camera_from_KE", "gom_raster_forward", "gom_raster_backward", "gom_joint_transforms_forward",
                  "gom_joint_transforms_backward", "gom_lbs_forward", "gom_lbs_backward", "gom_face_gaussians_forward",
@@ -182,7 +192,7 @@ _ENTRY_POINTS = ["gom_camera_from_KE", "gom_raster_forward", "gom_raster_backwar
                  "gom_lpips_input_forward", "gom_lpips_input_backward", "gom_bias_relu", "gom_relu_backward",
                  "gom_lpips_tap_forward", "gom_lpips_tap_backward", "gom_eval_metrics",
                  "gom_conv_first_forward", "gom_conv_first_backward", "gom_adam_step",
-                 "gom_mesh_raster_forward", "gom_mesh_raster_backward"]
+                 "gom_mesh_raster_forward", "gom_mesh_raster_backward", "gom_shadow_mlp_forward"]
 
 _lib = None
 
@@ -213,6 +223,8 @@ def lib():
         f = getattr(L, name)
         f.restype = c_int
         f.argtypes = [c_void_p, c_void_p]
+    L.gom_shadow_mlp_weight_image_bytes.restype = c_size_t
+    L.gom_shadow_mlp_weight_image_bytes.argtypes = [c_int]
     L.gom_launch_count.restype = ctypes.c_longlong
     L.gom_profile_slot_name.restype = c_char_p
     L.gom_profile_read.argtypes = [c_int, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(c_int)]

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define GOM_ABI_VERSION 2
+#define GOM_ABI_VERSION 3
 #define GOM_TILE 16              /* 16x16-pixel tiles, as upstream's BLOCK_X/BLOCK_Y */
 #define GOM_MAX_CHANNELS 4
 #define GOM_MAX_JOINTS 64
@@ -42,6 +42,7 @@ enum {
 
 /* status bits written to device memory by the rasterizer (checked lazily by the host) */
 #define GOM_STATUS_OVERFLOW 1u   /* a frame produced more (Gaussian,tile) instances than inst_capacity */
+#define GOM_STATUS_TIMEOUT 2u    /* a tcgen05 pipeline wait ran into its bound (protocol error); results are invalid */
 
 typedef void *gom_stream_t;      /* cudaStream_t */
 
@@ -420,6 +421,40 @@ typedef struct {
 } GomAdamArgs;
 int gom_adam_step(const GomAdamArgs *a, gom_stream_t stream);
 
+/* --------------------------------------------------------------------------------------------------------------
+ * Pseudo-shading MLP on the foreground pixels of the normal map.  Replaces `self.shadow_module(normal.reshape(-1, H*W, 3))`
+ * of reference models/model.py:281-283, i.e. models/modules/shadow_module.py:107-117 (positional encoding
+ * [x, sin(2^k x), cos(2^k x)]_k<multires of :14-62, then Linear/ReLU x depth, Linear(width,1), sigmoid) for the
+ * configurations the reference ships (exps/ all have mlp_width 128, mlp_depth 3, skips beyond the depth, multires 6).
+ * One call = pixel compaction (normal != 0; the background gets sigmoid(MLP(posenc(0))) as a constant), weight
+ * preparation and one persistent tcgen05 kernel (3xTF32 split products, fp32 accumulation in tensor memory).
+ * out[p] is the sigmoid output for EVERY pixel (the caller multiplies by 2, model.py:283).
+ * For a backward pass set save_hidden: hidden[l][j][r] = post-ReLU activation j of layer l of foreground row r
+ * (row r is pixel fg_index[r]; rows >= capacity are dropped and GOM_STATUS_OVERFLOW is set in status[0]).
+ */
+typedef struct {
+    int64_t n_pixels;            /* B*H*W */
+    int64_t capacity;            /* rows of `hidden` (save_hidden only) */
+    int32_t multires;            /* positional-encoding octaves (6): encoding width 3 + 6*multires <= 63 */
+    int32_t width;               /* must be 128 */
+    int32_t depth;               /* number of Linear+ReLU layers (mlp_depth, 3); 1..8 */
+    int32_t save_hidden;
+    const float *normals;        /* [n_pixels,3], 16-byte aligned */
+    const float *W_in, *b_in;    /* [width, 3+6*multires], [width]            (block_mlps.0) */
+    const float *W_hid, *b_hid;  /* [depth-1, width, width], [depth-1, width]  (block_mlps.2, .4, ...) */
+    const float *W_out, *b_out;  /* [width], [1]                               (last Linear) */
+    uint32_t *block_count;       /* scratch [ceil(n_pixels/1024)] */
+    int32_t *fg_index;           /* [n_pixels] out: foreground pixel ids in pixel order (first n_fg entries valid) */
+    int32_t *n_fg;               /* [1] out */
+    float *w_images;             /* scratch, gom_shadow_mlp_weight_image_bytes(depth) bytes, 128-byte aligned */
+    float *bg_value;             /* [1] out: the background constant */
+    float *out;                  /* [n_pixels] out */
+    float *hidden;               /* [depth, width, capacity] out (save_hidden), else NULL */
+    uint32_t *status;            /* [1] out: GOM_STATUS_OVERFLOW | GOM_STATUS_TIMEOUT */
+} GomShadowMlpArgs;
+int gom_shadow_mlp_forward(const GomShadowMlpArgs *a, gom_stream_t stream);
+size_t gom_shadow_mlp_weight_image_bytes(int depth);
+
 /* struct sizes, so that a foreign-language binding can assert its mirror of the structs */
 size_t gom_sizeof_camera_args(void);
 size_t gom_sizeof_raster_fwd_args(void);
@@ -439,6 +474,7 @@ size_t gom_sizeof_eval_metrics_args(void);
 size_t gom_sizeof_conv_first_args(void);
 size_t gom_sizeof_adam_args(void);
 size_t gom_sizeof_mesh_raster_args(void);
+size_t gom_sizeof_shadow_mlp_args(void);
 
 #ifdef __cplusplus
 }
