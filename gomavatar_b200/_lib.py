@@ -156,7 +156,9 @@ class GomShadowMlpArgs(ctypes.Structure):
                 ("save_hidden", c_int32), ("normals", c_void_p), ("W_in", c_void_p), ("b_in", c_void_p), ("W_hid", c_void_p),
                 ("b_hid", c_void_p), ("W_out", c_void_p), ("b_out", c_void_p), ("block_count", c_void_p),
                 ("fg_index", c_void_p), ("n_fg", c_void_p), ("w_images", c_void_p), ("bg_value", c_void_p), ("out", c_void_p),
-                ("hidden", c_void_p), ("status", c_void_p)]
+                ("act_img", c_void_p), ("status", c_void_p), ("g_out", c_void_p), ("dz_img", c_void_p), ("g_normals", c_void_p),
+                ("dzo_sums", c_void_p), ("partials", c_void_p), ("g_W_in", c_void_p), ("g_b_in", c_void_p), ("g_W_hid", c_void_p),
+                ("g_b_hid", c_void_p), ("g_w_out", c_void_p), ("g_b_out", c_void_p)]
 
 
 # every symbol include/gom_b200.h declares (tests check the .so exports all of them)
@@ -174,7 +176,8 @@ EXPORTS = [
     "gom_conv_first_forward", "gom_conv_first_backward", "gom_sizeof_conv_first_args",
     "gom_adam_step", "gom_sizeof_adam_args",
     "gom_mesh_raster_forward", "gom_mesh_raster_backward", "gom_sizeof_mesh_raster_args",
-    "gom_shadow_mlp_forward", "gom_shadow_mlp_weight_image_bytes", "gom_sizeof_shadow_mlp_args",
+    "gom_shadow_mlp_forward", "gom_shadow_mlp_backward", "gom_shadow_mlp_weight_image_bytes", "gom_shadow_mlp_tile_words",
+    "gom_shadow_mlp_partial_floats", "gom_shadow_mlp_num_ctas", "gom_sizeof_shadow_mlp_args",
 ]
 
 _STRUCTS = {
@@ -192,7 +195,7 @@ _ENTRY_POINTS = ["gom_camera_from_KE", "gom_raster_forward", "gom_raster_backwar
                  "gom_lpips_input_forward", "gom_lpips_input_backward", "gom_bias_relu", "gom_relu_backward",
                  "gom_lpips_tap_forward", "gom_lpips_tap_backward", "gom_eval_metrics",
                  "gom_conv_first_forward", "gom_conv_first_backward", "gom_adam_step",
-                 "gom_mesh_raster_forward", "gom_mesh_raster_backward", "gom_shadow_mlp_forward"]
+                 "gom_mesh_raster_forward", "gom_mesh_raster_backward", "gom_shadow_mlp_forward", "gom_shadow_mlp_backward"]
 
 _lib = None
 
@@ -225,6 +228,10 @@ def lib():
         f.argtypes = [c_void_p, c_void_p]
     L.gom_shadow_mlp_weight_image_bytes.restype = c_size_t
     L.gom_shadow_mlp_weight_image_bytes.argtypes = [c_int]
+    L.gom_shadow_mlp_tile_words.restype = c_size_t
+    L.gom_shadow_mlp_tile_words.argtypes = [c_int, c_int]
+    L.gom_shadow_mlp_partial_floats.restype = c_size_t
+    L.gom_shadow_mlp_num_ctas.restype = c_int
     L.gom_launch_count.restype = ctypes.c_longlong
     L.gom_profile_slot_name.restype = c_char_p
     L.gom_profile_read.argtypes = [c_int, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(c_int)]

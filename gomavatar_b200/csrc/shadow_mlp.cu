@@ -14,13 +14,22 @@
 //                  tcgen05.mma (A from TMEM, B = weight image in shared memory).  Every product is formed as
 //                  lo*hi + hi*lo + hi*hi (3xTF32, fp32 accumulate): error ~2^-21 like an fp32 GEMM, at a third of the
 //                  TF32 tensor rate instead of the FFMA rate.  The last layer (128 -> 1) and the sigmoid are done in
-//                  registers.  When the caller wants a backward pass the post-ReLU activations are written
-//                  feature-major ([layer][128][capacity], coalesced) for it.
+//                  registers.
+//   backward:   4. when a backward pass will follow, the forward also writes every operand it formed (encoding and
+//                  post-ReLU activations, already split into hi/lo) as ready-made K-major SWIZZLE_128B "activation
+//                  images" [feature][pixel row] per 32-row block, so that later kernels consume them with 1-D TMA;
+//               5. k_shadow_bwd_data: the same pipeline run backwards (dZ_l = (dZ_{l+1} W_{l+1}) * [H_l > 0], transposed
+//                  weight images), ending in the positional-encoding backward -> dL/dnormal; it writes dZ_l images;
+//               6. k_shadow_bwd_weights: split-K GEMMs dW_l = dZ_l^T H_{l-1} (both operands are the saved images, both
+//                  from shared memory), accumulated over all tiles of a CTA in tensor memory; a row of ones appended
+//                  to the B operand yields the bias gradients in the same MMAs; per-CTA partials are summed in a fixed
+//                  order by k_shadow_bwd_reduce (deterministic).
 //
-// TMEM map (512 columns allocated): [0,128) accumulator D, [128,256) A_hi, [256,384) A_lo; lane = pixel row of the tile.
-// Warp roles (192 threads): warps 0-3 epilogue (warp w owns TMEM lanes 32w..32w+31), warp 4 weight producer (TMA),
-// warp 5 MMA issuer.  Per tile and layer the chain a_ready -> MMAs -> z_ready -> epilogue is serial; the weight stream
-// (6 x 32 KB stages) runs ahead of it.
+// TMEM map of k_shadow_fwd / k_shadow_bwd_data (512 columns): [0,128) and [128,256) accumulators D0/D1 (alternating per
+// layer), [256,384) A_hi, [384,512) A_lo; lane = pixel row of the tile.
+// Warp roles (192 threads): warps 0-3 epilogue (warp w owns TMEM lanes 32w..32w+31), warp 4 producer (TMA), warp 5 MMA
+// issuer.  The next layer's MMAs start k-block by k-block while the epilogue is still producing the rest of its operand;
+// the weight stream (6 x 32 KB stages) runs ahead of both.
 #include "gom_common.cuh"
 
 namespace {
@@ -33,20 +42,40 @@ constexpr int kStages = 6;
 constexpr int kMaxDepth = 8;
 constexpr int kEncPad = 64;             // encoding columns in TMEM (3 + 6*multires <= 63)
 constexpr uint32_t kTmemCols = 512;
-constexpr uint32_t kColD = 0, kColAhi = 128, kColAlo = 256;
+constexpr uint32_t kColD = 0, kColAhi = 256, kColAlo = 384;   // D is double-buffered: [0,128), [128,256)
 constexpr int kThreads = 192;
 constexpr uint32_t kStatusTimeout = 2u;
 
 struct ShadowDev {
-    long long n_pixels, capacity;
-    int multires, enc, depth, save_hidden;
+    long long n_pixels, capacity;          // capacity: rows (a multiple of 128) the image buffers hold
+    int multires, enc, depth, save_hidden, n_ctas;
     const float *normals;
     const float *W_in, *b_in, *W_hid, *b_hid, *W_out, *b_out;
     uint32_t *block_count;
     int *fg_index, *n_fg;
-    float *w_images, *bg_value, *out, *hidden;
+    float *w_images, *bg_value, *out;
+    uint32_t *act_img, *dz_img;
     uint32_t *status;
+    const float *g_out;
+    float *g_normals, *dzo_sums, *partials;
+    float *g_W_in, *g_b_in, *g_W_hid, *g_b_hid, *g_w_out, *g_b_out;
 };
+
+// ------------------------------------------------------------------------------------------- activation images
+// One tile (128 pixel rows) of saved operands, in 32-bit words.  Row block kb = rows 32 kb .. 32 kb + 31 of the tile
+// (= the epilogue warp kb); inside an image, element (feature j, row-in-block q) sits at word swz(j, q): row j of a
+// K-major SWIZZLE_128B matrix whose K index is the pixel row.
+//   act tile: [slot 0 (encoding, 64 features): 4 blocks x (hi 2048 | lo 2048)] [slot s = 1..depth (H_s, 128 features):
+//             4 blocks x (hi 4096 | lo 4096)]
+//   dz tile:  [layer l = 0..depth-1 (dZ_l, 128 features): 4 blocks x (hi 4096 | lo 4096)] [dz_out, 16 rows of which row 0
+//             is used: 4 blocks x (hi 512 | lo 512)]
+__host__ __device__ __forceinline__ size_t act_tile_words(int depth) { return 16384 + (size_t)depth * 32768; }
+__host__ __device__ __forceinline__ size_t dz_tile_words(int depth) { return (size_t)depth * 32768 + 4096; }
+__host__ __device__ __forceinline__ size_t act_slot_block(int slot, int kb) {       // word offset of (slot, kb) in an act tile
+    return slot == 0 ? (size_t)kb * 4096 : 16384 + (size_t)(slot - 1) * 32768 + (size_t)kb * 8192;
+}
+__host__ __device__ __forceinline__ size_t act_slot_half(int slot) { return slot == 0 ? 2048 : 4096; }   // hi -> lo distance
+__device__ __forceinline__ int swz(int j, int q) { return j * 32 + ((((q >> 2) ^ (j & 7)) << 2) | (q & 3)); }
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -59,6 +88,7 @@ __device__ __forceinline__ void split_tf32(float x, uint32_t &hi, uint32_t &lo) 
 // number of 32-column K-blocks of layer l and the images before it
 __host__ __device__ __forceinline__ int layer_kblocks(int l) { return l == 0 ? 2 : 4; }
 __host__ __device__ __forceinline__ int images_total(int depth) { return 2 + 4 * (depth - 1); }
+__host__ __device__ __forceinline__ int images_total_with_backward(int depth) { return images_total(depth) + 4 * depth; }
 
 // ------------------------------------------------------------------------------------------------- weight images
 // Image (layer l, K-block kb) = 32 KB: hi part then lo part, each the canonical K-major SWIZZLE_128B layout of a
@@ -98,14 +128,22 @@ __global__ void k_shadow_prep(ShadowDev a) {
         return;
     }
     const int e = blockIdx.x * blockDim.x + threadIdx.x;            // one element of one image
-    if (e >= n_img * 4096) return;
+    const int n_img_all = n_img + (a.save_hidden ? 4 * a.depth : 0);
+    if (e >= n_img_all * 4096) return;
     const int img = e >> 12, n = (e >> 5) & 127, kl = e & 31;
-    int l, kb;
-    if (img < 2) { l = 0; kb = img; } else { l = 1 + (img - 2) / 4; kb = (img - 2) % 4; }
-    const int k = kb * 32 + kl;
     float w = 0.f;
-    if (l == 0) { if (k < a.enc) w = a.W_in[n * a.enc + k]; }
-    else w = a.W_hid[(size_t)(l - 1) * kWidth * kWidth + (size_t)n * kWidth + k];
+    if (img < n_img) {                                              // forward: B[n = output feature][k = input feature]
+        int l, kb;
+        if (img < 2) { l = 0; kb = img; } else { l = 1 + (img - 2) / 4; kb = (img - 2) % 4; }
+        const int k = kb * 32 + kl;
+        if (l == 0) { if (k < a.enc) w = a.W_in[n * a.enc + k]; }
+        else w = a.W_hid[(size_t)(l - 1) * kWidth * kWidth + (size_t)n * kWidth + k];
+    } else {                                                        // backward step s: layer l = depth-1-s, B[n = input][k = output]
+        const int s_ = (img - n_img) >> 2, kb = (img - n_img) & 3, l = a.depth - 1 - s_;
+        const int k = kb * 32 + kl;
+        if (l == 0) { if (n < a.enc) w = a.W_in[k * a.enc + n]; }
+        else w = a.W_hid[(size_t)(l - 1) * kWidth * kWidth + (size_t)k * kWidth + n];
+    }
     uint32_t hi, lo;
     split_tf32(w, hi, lo);
     uint32_t *dst = reinterpret_cast<uint32_t *>(a.w_images) + (size_t)img * (kStageBytes / 4);
@@ -257,13 +295,16 @@ __device__ __forceinline__ uint64_t make_b_desc(uint32_t smem_addr) {
 // cute::UMMA::InstrDescriptor: D = F32 (1 << 4), A = B = TF32 (2 << 7, 2 << 10), both K-major, N >> 3 at bit 17, M >> 4 at bit 24
 constexpr uint32_t kInstrDesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kWidth >> 3) << 17) | ((uint32_t)(kTileRows >> 4) << 24);
 
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t v[16]) {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t v[32]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+                 "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
                  : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                   "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                   "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
                  : "r"(taddr));
 }
-__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t v[16]) {
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t *v) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
                  ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
                    "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]) : "memory");
@@ -271,10 +312,35 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t v[16]) 
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+// positional encoding of one normal into 64 zero-padded columns: [n, sin(2^k n), cos(2^k n)]_k
+__device__ __forceinline__ void encode_normal(float nx, float ny, float nz, int multires, float enc[kEncPad]) {
+#pragma unroll
+    for (int c = 0; c < kEncPad; c++) enc[c] = 0.f;
+    enc[0] = nx; enc[1] = ny; enc[2] = nz;
+#pragma unroll
+    for (int k = 0; k < 10; k++) {
+        if (k < multires) {
+            const float f = (float)(1 << k);
+            float s, c;
+            sincosf(nx * f, &s, &c); enc[3 + 6 * k + 0] = s; enc[3 + 6 * k + 3] = c;
+            sincosf(ny * f, &s, &c); enc[3 + 6 * k + 1] = s; enc[3 + 6 * k + 4] = c;
+            sincosf(nz * f, &s, &c); enc[3 + 6 * k + 2] = s; enc[3 + 6 * k + 5] = c;
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ the MLP kernel
+// Pipeline (per CTA, g = running layer counter over all its tiles):
+//   epilogue(g)  reads accumulator D[g&1] 32 columns at a time, writes the next layer's A operand k-block by k-block and
+//                signals a_ready[kb] after each one;
+//   MMA(g+1)     starts on k-block kb as soon as a_ready[kb] fires and accumulates into the OTHER buffer D[(g+1)&1], so
+//                it overlaps the rest of epilogue(g); one commit -> z_ready when the layer is complete.
+//   The last layer's epilogue first writes the NEXT tile's encoding (prefetched and encoded while the tensor core was
+//   busy) so that MMA(next tile, layer 0) overlaps the final 128 -> 1 dot product.
+template <bool SAVE>
 __global__ void __launch_bounds__(kThreads, 1) k_shadow_fwd(ShadowDev a) {
     extern __shared__ uint8_t smem_raw[];
-    __shared__ uint64_t full_bar[kStages], empty_bar[kStages], a_ready, z_ready;
+    __shared__ uint64_t full_bar[kStages], empty_bar[kStages], a_ready[4], z_ready;
     __shared__ uint32_t tmem_slot;
     __shared__ int abort_flag;
     __shared__ float s_bias[kMaxDepth * kWidth], s_wout[kWidth], s_bout;
@@ -288,7 +354,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_shadow_fwd(ShadowDev a) {
     }
     if (threadIdx.x == 32) {
         for (int s = 0; s < kStages; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        mbar_init(&a_ready, kTileRows);
+        for (int kb = 0; kb < 4; kb++) mbar_init(&a_ready[kb], kTileRows);
         mbar_init(&z_ready, 1);
         abort_flag = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -325,14 +391,15 @@ __global__ void __launch_bounds__(kThreads, 1) k_shadow_fwd(ShadowDev a) {
     } else if (warp == 5) {
         // ================================================================================ MMA issuer (one thread)
         if (lane == 0) {
-            uint32_t it = 0, a_cnt = 0;
+            uint32_t it = 0, g = 0;
             for (int tile = blockIdx.x; tile < n_tiles && ok; tile += gridDim.x)
-                for (int l = 0; l < depth && ok; l++) {
-                    if (!mbar_wait(&a_ready, a_cnt & 1u, ab)) { ok = false; break; }
-                    a_cnt++;
-                    tc_fence_after();
+                for (int l = 0; l < depth && ok; l++, g++) {
+                    const uint32_t dcol = tmem + kColD + (g & 1u) * kWidth;
                     const int ksteps = (l == 0) ? ksteps0 : (kWidth / 8);
-                    for (int kb = 0; kb < layer_kblocks(l); kb++, it++) {
+                    for (int kb = 0; kb < 4 && ok; kb++) {
+                        if (!mbar_wait(&a_ready[kb], g & 1u, ab)) { ok = false; break; }
+                        if (kb >= layer_kblocks(l)) continue;
+                        tc_fence_after();
                         const uint32_t s = it % kStages, ph = (it / kStages) & 1u;
                         if (!mbar_wait(&full_bar[s], ph, ab)) { ok = false; break; }
                         tc_fence_after();
@@ -341,88 +408,125 @@ __global__ void __launch_bounds__(kThreads, 1) k_shadow_fwd(ShadowDev a) {
                         for (int ks = 0; ks < ks_n; ks++) {
                             const uint32_t kcol = (uint32_t)(kb * 32 + ks * 8);
                             const uint64_t b_hi = make_b_desc(sb + ks * 32), b_lo = make_b_desc(sb + kHalfStage + ks * 32);
-                            mma_tf32_ts(tmem + kColD, tmem + kColAlo + kcol, b_hi, kInstrDesc, (kb | ks) != 0);
-                            mma_tf32_ts(tmem + kColD, tmem + kColAhi + kcol, b_lo, kInstrDesc, 1u);
-                            mma_tf32_ts(tmem + kColD, tmem + kColAhi + kcol, b_hi, kInstrDesc, 1u);
+                            mma_tf32_ts(dcol, tmem + kColAlo + kcol, b_hi, kInstrDesc, (kb | ks) != 0);
+                            mma_tf32_ts(dcol, tmem + kColAhi + kcol, b_lo, kInstrDesc, 1u);
+                            mma_tf32_ts(dcol, tmem + kColAhi + kcol, b_hi, kInstrDesc, 1u);
                         }
                         tc_commit(&empty_bar[s]);          // frees the stage once these MMAs have read it
+                        it++;
                     }
-                    if (ok) tc_commit(&z_ready);           // accumulator complete
+                    if (ok) tc_commit(&z_ready);           // accumulator of layer g complete
                 }
         }
     } else {
         // ============================================ epilogue warps: thread r <-> pixel row r of the tile <-> TMEM lane r
         const int r = threadIdx.x;
         const uint32_t tl = tmem + ((uint32_t)(warp * 32) << 16);
-        uint32_t z_cnt = 0;
-        for (int tile = blockIdx.x; tile < n_tiles && ok; tile += gridDim.x) {
-            const long long row = (long long)tile * kTileRows + r;
-            const bool valid = row < n_fg;
-            const int pix = valid ? a.fg_index[row] : -1;
-            float nx = 0.f, ny = 0.f, nz = 0.f;
-            if (valid) { const float *q = a.normals + 3ll * pix; nx = q[0]; ny = q[1]; nz = q[2]; }
-            {   // positional encoding: [n, sin(2^k n), cos(2^k n)]_k, zero padded to 64 columns
-                float enc[kEncPad];
+        const int cap_tiles = (int)(a.capacity / kTileRows);
+        const size_t act_words = act_tile_words(depth);
+        uint32_t g = 0;
+
+        // Split one feature block (32 columns) of `v` into TF32 hi/lo; store it as A operand columns [32 fb, 32 fb + 32)
+        // (to_tmem) and, when a backward pass will follow, into the activation image `img` (word pointer to the hi part
+        // of (slot, row block = this warp); the lo part is `half` words further).
+        auto store_block = [&](const float *v, int fb, bool to_tmem, uint32_t *img, size_t half) {
+            uint32_t hi[32], lo[32];
 #pragma unroll
-                for (int c = 0; c < kEncPad; c++) enc[c] = 0.f;
-                enc[0] = nx; enc[1] = ny; enc[2] = nz;
+            for (int j = 0; j < 32; j++) split_tf32(v[j], hi[j], lo[j]);
+            if (to_tmem) {
+                tmem_st16(tl + kColAhi + fb * 32, hi);
+                tmem_st16(tl + kColAhi + fb * 32 + 16, hi + 16);
+                tmem_st16(tl + kColAlo + fb * 32, lo);
+                tmem_st16(tl + kColAlo + fb * 32 + 16, lo + 16);
+            }
+            if (SAVE && img) {
 #pragma unroll
-                for (int k = 0; k < 10; k++) {
-                    if (k < a.multires) {
-                        const float f = (float)(1 << k);
-                        float s, c;
-                        sincosf(nx * f, &s, &c); enc[3 + 6 * k + 0] = s; enc[3 + 6 * k + 3] = c;
-                        sincosf(ny * f, &s, &c); enc[3 + 6 * k + 1] = s; enc[3 + 6 * k + 4] = c;
-                        sincosf(nz * f, &s, &c); enc[3 + 6 * k + 2] = s; enc[3 + 6 * k + 5] = c;
-                    }
-                }
-#pragma unroll
-                for (int c = 0; c < kEncPad / 16; c++) {
-                    uint32_t hi[16], lo[16];
-#pragma unroll
-                    for (int j = 0; j < 16; j++) split_tf32(enc[c * 16 + j], hi[j], lo[j]);
-                    tmem_st16(tl + kColAhi + c * 16, hi);
-                    tmem_st16(tl + kColAlo + c * 16, lo);
+                for (int j = 0; j < 32; j++) {
+                    const int w = swz(fb * 32 + j, lane);
+                    img[w] = hi[j];
+                    img[half + w] = lo[j];
                 }
             }
+        };
+        auto act_img_ptr = [&](int t, int slot) -> uint32_t * {        // image of (tile t, slot, row block = this warp)
+            if (!SAVE || t >= cap_tiles) return nullptr;
+            return a.act_img + (size_t)t * act_words + act_slot_block(slot, warp);
+        };
+        auto publish_encoding = [&](const float *enc, int t) {          // layer-0 operand of tile t, then release all four
+            uint32_t *img = act_img_ptr(t, 0);
+            store_block(enc, 0, true, img, act_slot_half(0));
+            store_block(enc + 32, 1, true, img, act_slot_half(0));
             tmem_wait_st();
             tc_fence_before();
-            mbar_arrive(&a_ready);
-
-            for (int l = 0; l < depth; l++) {
-                if (!mbar_wait(&z_ready, z_cnt & 1u, ab)) { ok = false; break; }
-                z_cnt++;
-                tc_fence_after();
-                const bool last = (l == depth - 1);
-                const bool save = a.save_hidden && valid && row < a.capacity;
-                float *hsave = save ? a.hidden + (size_t)l * kWidth * (size_t)a.capacity + (size_t)row : nullptr;
-                float acc = 0.f;
-#pragma unroll 1
-                for (int c = 0; c < kWidth / 16; c++) {
-                    uint32_t z[16], hi[16], lo[16];
-                    tmem_ld16(tl + kColD + c * 16, z);
-                    tmem_wait_ld();
 #pragma unroll
-                    for (int j = 0; j < 16; j++) {
-                        const float h = fmaxf(__uint_as_float(z[j]) + s_bias[l * kWidth + c * 16 + j], 0.f);
-                        if (save) hsave[(size_t)(c * 16 + j) * (size_t)a.capacity] = h;
-                        acc = fmaf(h, s_wout[c * 16 + j], acc);
-                        split_tf32(h, hi[j], lo[j]);
-                    }
-                    if (!last) {
-                        tmem_st16(tl + kColAhi + c * 16, hi);
-                        tmem_st16(tl + kColAlo + c * 16, lo);
-                    }
-                }
+            for (int kb = 0; kb < 4; kb++) mbar_arrive(&a_ready[kb]);
+        };
+
+        int tile = blockIdx.x;
+        long long row = (long long)tile * kTileRows + r;
+        bool valid = tile < n_tiles && row < n_fg;
+        int pix = valid ? a.fg_index[row] : -1;
+        float nx = 0.f, ny = 0.f, nz = 0.f;
+        if (valid) { const float *q = a.normals + 3ll * pix; nx = q[0]; ny = q[1]; nz = q[2]; }
+        if (tile < n_tiles) {
+            float enc[kEncPad];
+            encode_normal(nx, ny, nz, a.multires, enc);
+            publish_encoding(enc, tile);
+        }
+        for (; tile < n_tiles && ok; tile += gridDim.x) {
+            // prefetch the next tile's pixel (index, then normal: two dependent global loads, consumed a whole tile later)
+            const int tile_n = tile + gridDim.x;
+            const long long row_n = (long long)tile_n * kTileRows + r;
+            const bool valid_n = tile_n < n_tiles && row_n < n_fg;
+            const int pix_n = valid_n ? a.fg_index[row_n] : -1;
+            float nxn = 0.f, nyn = 0.f, nzn = 0.f;
+            if (valid_n) { const float *q = a.normals + 3ll * pix_n; nxn = q[0]; nyn = q[1]; nzn = q[2]; }
+
+            for (int l = 0; l < depth; l++, g++) {
+                const bool last = (l == depth - 1);
+                const uint32_t dcol = tl + kColD + (g & 1u) * kWidth;
+                uint32_t *img = act_img_ptr(tile, l + 1);
                 if (!last) {
-                    tmem_wait_st();
-                    tc_fence_before();
-                    mbar_arrive(&a_ready);
-                } else if (valid) {
-                    a.out[pix] = 1.f / (1.f + expf(-(acc + s_bout)));
+                    if (!mbar_wait(&z_ready, g & 1u, ab)) { ok = false; break; }
+                    tc_fence_after();
+#pragma unroll 1
+                    for (int fb = 0; fb < 4; fb++) {
+                        uint32_t z[32];
+                        float h[32];
+                        tmem_ld32(dcol + fb * 32, z);
+                        tmem_wait_ld();
+#pragma unroll
+                        for (int j = 0; j < 32; j++) h[j] = fmaxf(__uint_as_float(z[j]) + s_bias[l * kWidth + fb * 32 + j], 0.f);
+                        store_block(h, fb, true, img, act_slot_half(1));
+                        tmem_wait_st();
+                        tc_fence_before();
+                        mbar_arrive(&a_ready[fb]);
+                    }
+                } else {
+                    float encn[kEncPad];
+                    if (tile_n < n_tiles) encode_normal(nxn, nyn, nzn, a.multires, encn);   // while the tensor core is busy
+                    if (!mbar_wait(&z_ready, g & 1u, ab)) { ok = false; break; }
+                    tc_fence_after();
+                    if (tile_n < n_tiles) publish_encoding(encn, tile_n);   // every MMA that read A has completed: start the next tile
+                    float acc = 0.f;
+#pragma unroll 1
+                    for (int fb = 0; fb < 4; fb++) {
+                        uint32_t z[32];
+                        float h[32];
+                        tmem_ld32(dcol + fb * 32, z);
+                        tmem_wait_ld();
+#pragma unroll
+                        for (int j = 0; j < 32; j++) {
+                            h[j] = fmaxf(__uint_as_float(z[j]) + s_bias[l * kWidth + fb * 32 + j], 0.f);
+                            acc = fmaf(h[j], s_wout[fb * 32 + j], acc);
+                        }
+                        if (SAVE) store_block(h, fb, false, img, act_slot_half(1));
+                    }
+                    if (valid) a.out[pix] = 1.f / (1.f + expf(-(acc + s_bout)));
+                    tc_fence_before();      // orders these tcgen05.ld before the a_ready arrivals of the next tile's layer 0
                 }
             }
-            tc_fence_before();      // orders this tile's tcgen05.ld before the next tile's a_ready arrive
+            row = row_n; valid = valid_n; pix = pix_n;
         }
     }
 
@@ -434,14 +538,412 @@ __global__ void __launch_bounds__(kThreads, 1) k_shadow_fwd(ShadowDev a) {
     }
 }
 
+// =========================================================================================== backward: data gradients
+// Same pipeline as k_shadow_fwd, run from the output back to the encoding.  Step s = 0..depth-1 multiplies dZ_l (l = depth-1-s,
+// in TMEM as hi/lo) with the transposed weight image of layer l; the epilogue masks the product with [H_l > 0] (read from
+// the forward's activation images) to get dZ_{l-1}, writes it back as the next operand and into the dZ images for
+// k_shadow_bwd_weights.  The last product is dL/d(encoding); its epilogue applies the positional-encoding Jacobian.
+__global__ void __launch_bounds__(kThreads, 1) k_shadow_bwd_data(ShadowDev a) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ uint64_t full_bar[kStages], empty_bar[kStages], a_ready[4], z_ready;
+    __shared__ uint32_t tmem_slot;
+    __shared__ int abort_flag;
+    __shared__ float s_wout[kWidth];
+
+    uint8_t *stages = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (threadIdx.x == 32) {
+        for (int s = 0; s < kStages; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int kb = 0; kb < 4; kb++) mbar_init(&a_ready[kb], kTileRows);
+        mbar_init(&z_ready, 1);
+        abort_flag = 0;
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int i = threadIdx.x; i < kWidth; i += kThreads) s_wout[i] = a.W_out[i];
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+
+    const int n_fg = a.n_fg[0];
+    const int cap_tiles = (int)(a.capacity / kTileRows);
+    const int n_tiles = min((n_fg + kTileRows - 1) / kTileRows, cap_tiles);
+    const int depth = a.depth, img0 = images_total(depth);
+    volatile int *ab = &abort_flag;
+    bool ok = true;
+
+    if (warp == 4) {
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < n_tiles && ok; tile += gridDim.x)
+                for (int img = 0; img < 4 * depth; img++, it++) {
+                    const uint32_t s = it % kStages, ph = (it / kStages) & 1u;
+                    if (!mbar_wait(&empty_bar[s], ph ^ 1u, ab)) { ok = false; break; }
+                    mbar_expect_tx(&full_bar[s], kStageBytes);
+                    tma_bulk_g2s(smem_u32(stages + (size_t)s * kStageBytes),
+                                 reinterpret_cast<const uint8_t *>(a.w_images) + (size_t)(img0 + img) * kStageBytes, kStageBytes, &full_bar[s]);
+                }
+        }
+    } else if (warp == 5) {
+        if (lane == 0) {
+            uint32_t it = 0, g = 0;
+            for (int tile = blockIdx.x; tile < n_tiles && ok; tile += gridDim.x)
+                for (int st = 0; st < depth && ok; st++, g++) {
+                    const uint32_t dcol = tmem + kColD + (g & 1u) * kWidth;
+                    for (int kb = 0; kb < 4 && ok; kb++, it++) {
+                        if (!mbar_wait(&a_ready[kb], g & 1u, ab)) { ok = false; break; }
+                        tc_fence_after();
+                        const uint32_t s = it % kStages, ph = (it / kStages) & 1u;
+                        if (!mbar_wait(&full_bar[s], ph, ab)) { ok = false; break; }
+                        tc_fence_after();
+                        const uint32_t sb = smem_u32(stages + (size_t)s * kStageBytes);
+                        for (int ks = 0; ks < 4; ks++) {
+                            const uint32_t kcol = (uint32_t)(kb * 32 + ks * 8);
+                            const uint64_t b_hi = make_b_desc(sb + ks * 32), b_lo = make_b_desc(sb + kHalfStage + ks * 32);
+                            mma_tf32_ts(dcol, tmem + kColAlo + kcol, b_hi, kInstrDesc, (kb | ks) != 0);
+                            mma_tf32_ts(dcol, tmem + kColAhi + kcol, b_lo, kInstrDesc, 1u);
+                            mma_tf32_ts(dcol, tmem + kColAhi + kcol, b_hi, kInstrDesc, 1u);
+                        }
+                        tc_commit(&empty_bar[s]);
+                    }
+                    if (ok) tc_commit(&z_ready);
+                }
+        }
+    } else {
+        const int r = threadIdx.x;
+        const uint32_t tl = tmem + ((uint32_t)(warp * 32) << 16);
+        const size_t act_words = act_tile_words(depth), dz_words = dz_tile_words(depth);
+        uint32_t g = 0;
+
+        // v (32 features of this row) -> TF32 hi/lo -> A operand columns [32 fb, 32 fb + 32) and the dZ image of `layer`
+        auto store_block = [&](const float *v, int fb, int t, int layer) {
+            uint32_t hi[32], lo[32];
+#pragma unroll
+            for (int j = 0; j < 32; j++) split_tf32(v[j], hi[j], lo[j]);
+            tmem_st16(tl + kColAhi + fb * 32, hi);
+            tmem_st16(tl + kColAhi + fb * 32 + 16, hi + 16);
+            tmem_st16(tl + kColAlo + fb * 32, lo);
+            tmem_st16(tl + kColAlo + fb * 32 + 16, lo + 16);
+            uint32_t *img = a.dz_img + (size_t)t * dz_words + (size_t)layer * 32768 + (size_t)warp * 8192;
+#pragma unroll
+            for (int j = 0; j < 32; j++) {
+                const int w = swz(fb * 32 + j, lane);
+                img[w] = hi[j];
+                img[4096 + w] = lo[j];
+            }
+        };
+        // [H_slot > 0] of this row, features [32 fb, 32 fb + 32): hi words of the forward's activation image (hi > 0 <=> H > 0)
+        auto load_mask = [&](int t, int slot, int fb, uint32_t m[32]) {
+            const uint32_t *img = a.act_img + (size_t)t * act_words + act_slot_block(slot, warp);
+#pragma unroll
+            for (int j = 0; j < 32; j++) m[j] = __ldg(img + swz(fb * 32 + j, lane));
+        };
+        // first operand of a tile: dZ_{depth-1} = dz_out * w_out * [H_depth > 0]; also the dz_out image + its warp sum
+        auto publish_first = [&](int t, float dzo) {
+            uint32_t dh, dl;
+            split_tf32(dzo, dh, dl);
+            uint32_t *dimg = a.dz_img + (size_t)t * dz_words + (size_t)depth * 32768 + (size_t)warp * 1024;
+            dimg[lane] = dh;                                   // row 0 of a 16-row image: swz(0, lane) = lane
+            dimg[512 + lane] = dl;
+            const float ws = warp_sum(dzo);
+            if (lane == 0) a.dzo_sums[(size_t)t * 4 + warp] = ws;
+#pragma unroll 1
+            for (int fb = 0; fb < 4; fb++) {
+                uint32_t m[32];
+                float v[32];
+                load_mask(t, depth, fb, m);
+#pragma unroll
+                for (int j = 0; j < 32; j++) v[j] = (__uint_as_float(m[j]) > 0.f) ? dzo * s_wout[fb * 32 + j] : 0.f;
+                store_block(v, fb, t, depth - 1);
+                tmem_wait_st();
+                tc_fence_before();
+                mbar_arrive(&a_ready[fb]);
+            }
+        };
+        auto row_inputs = [&](int t, int &pix, float &dzo, float &nx, float &ny, float &nz) {
+            const long long row = (long long)t * kTileRows + r;
+            pix = (t < n_tiles && row < n_fg) ? a.fg_index[row] : -1;
+            dzo = 0.f; nx = ny = nz = 0.f;
+            if (pix >= 0) {
+                const float y = a.out[pix];
+                dzo = a.g_out[pix] * y * (1.f - y);
+                const float *q = a.normals + 3ll * pix;
+                nx = q[0]; ny = q[1]; nz = q[2];
+            }
+        };
+
+        int tile = blockIdx.x, pix;
+        float dzo, nx, ny, nz;
+        row_inputs(tile, pix, dzo, nx, ny, nz);
+        if (tile < n_tiles) publish_first(tile, dzo);
+        for (; tile < n_tiles && ok; tile += gridDim.x) {
+            const int tile_n = tile + gridDim.x;
+            int pix_n;
+            float dzo_n, nxn, nyn, nzn;
+            row_inputs(tile_n, pix_n, dzo_n, nxn, nyn, nzn);           // consumed a whole tile later
+
+            for (int st = 0; st < depth; st++, g++) {
+                const bool last = (st == depth - 1);
+                const uint32_t dcol = tl + kColD + (g & 1u) * kWidth;
+                if (!mbar_wait(&z_ready, g & 1u, ab)) { ok = false; break; }
+                tc_fence_after();
+                if (!last) {
+                    const int slot = depth - 1 - st;                    // the product is dL/dH_slot
+#pragma unroll 1
+                    for (int fb = 0; fb < 4; fb++) {
+                        uint32_t z[32], m[32];
+                        float v[32];
+                        load_mask(tile, slot, fb, m);
+                        tmem_ld32(dcol + fb * 32, z);
+                        tmem_wait_ld();
+#pragma unroll
+                        for (int j = 0; j < 32; j++) v[j] = (__uint_as_float(m[j]) > 0.f) ? __uint_as_float(z[j]) : 0.f;
+                        store_block(v, fb, tile, slot - 1);
+                        tmem_wait_st();
+                        tc_fence_before();
+                        mbar_arrive(&a_ready[fb]);
+                    }
+                } else {
+                    if (tile_n < n_tiles) publish_first(tile_n, dzo_n);     // A is free: start the next tile
+                    // dL/d(encoding) of this row -> dL/dnormal = dX[0:3] + sum_k 2^k (cos(2^k n) dXsin_k - sin(2^k n) dXcos_k)
+                    uint32_t z0[32], z1[32];
+                    tmem_ld32(dcol, z0);
+                    tmem_ld32(dcol + 32, z1);
+                    tmem_wait_ld();
+                    float dx[kEncPad];
+#pragma unroll
+                    for (int j = 0; j < 32; j++) { dx[j] = __uint_as_float(z0[j]); dx[32 + j] = __uint_as_float(z1[j]); }
+                    float gx = dx[0], gy = dx[1], gz = dx[2];
+#pragma unroll
+                    for (int k = 0; k < 10; k++) {
+                        if (k < a.multires) {
+                            const float f = (float)(1 << k);
+                            float sn, cs;
+                            sincosf(nx * f, &sn, &cs); gx += f * (cs * dx[3 + 6 * k + 0] - sn * dx[3 + 6 * k + 3]);
+                            sincosf(ny * f, &sn, &cs); gy += f * (cs * dx[3 + 6 * k + 1] - sn * dx[3 + 6 * k + 4]);
+                            sincosf(nz * f, &sn, &cs); gz += f * (cs * dx[3 + 6 * k + 2] - sn * dx[3 + 6 * k + 5]);
+                        }
+                    }
+                    if (pix >= 0) { float *q = a.g_normals + 3ll * pix; q[0] = gx; q[1] = gy; q[2] = gz; }
+                    tc_fence_before();
+                }
+            }
+            pix = pix_n; dzo = dzo_n; nx = nxn; ny = nyn; nz = nzn;
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x == 0 && abort_flag) atomicOr(a.status, kStatusTimeout);
+    if (warp == 0) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols) : "memory");
+    }
+}
+
+// ========================================================================================= backward: weight gradients
+// Job j < depth:  D_j[f, 16 + i] += sum_r dZ_j[r, f] * A_j[r, i]   (A_0 = encoding, A_j = H_j), D_j[f, 0] += sum_r dZ_j[r, f]
+// Job depth:      D[f, 16]       += sum_r H_depth[r, f] * dz_out[r]                                  (-> dL/dw_out)
+// Both operands of every job are saved images (K = pixel row), streamed with 1-D TMA; 16 constant rows in front of the B
+// image (row 0 = ones) give the bias gradients.  One accumulator per job lives in tensor memory for the whole kernel.
+constexpr int kB2StageBytes = 32768 + 36864;     // A image | [ones 2 KB | B hi 16 KB | zeros 2 KB | B lo 16 KB]
+constexpr int kB2Stages = 3;
+constexpr int kB2BOff = 32768, kB2BLoOff = 32768 + 18432;
+constexpr int kPartialCols = 512;
+
+__host__ __device__ __forceinline__ int job_cols(int job, int depth) { return job == 0 ? 80 : (job < depth ? 144 : 32); }
+__host__ __device__ __forceinline__ int job_col0(int job, int depth) { return job == 0 ? 0 : 80 + (job - 1) * 144; }
+__host__ __device__ constexpr uint32_t instr_desc_n(int n) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kTileRows >> 4) << 24);
+}
+__device__ __forceinline__ void mma_tf32_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
+}
+
+__global__ void __launch_bounds__(kThreads, 1) k_shadow_bwd_weights(ShadowDev a) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ uint64_t full_bar[kB2Stages], empty_bar[kB2Stages], done_bar;
+    __shared__ uint32_t tmem_slot;
+    __shared__ int abort_flag;
+
+    uint8_t *stages = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (threadIdx.x == 32) {
+        for (int s = 0; s < kB2Stages; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        mbar_init(&done_bar, 1);
+        abort_flag = 0;
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    // the constant rows in front of every B image: hi part = [ones; 15 zero rows], lo part = zeros
+    for (int s = 0; s < kB2Stages; s++) {
+        float *bh = reinterpret_cast<float *>(stages + (size_t)s * kB2StageBytes + kB2BOff);
+        float *bl = reinterpret_cast<float *>(stages + (size_t)s * kB2StageBytes + kB2BLoOff);
+        for (int i = threadIdx.x; i < 512; i += kThreads) { bh[i] = (i < 32) ? 1.f : 0.f; bl[i] = 0.f; }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+
+    const int n_fg = a.n_fg[0];
+    const int cap_tiles = (int)(a.capacity / kTileRows);
+    const int n_tiles = min((n_fg + kTileRows - 1) / kTileRows, cap_tiles);
+    const int depth = a.depth, n_jobs = depth + 1;
+    const size_t act_words = act_tile_words(depth), dz_words = dz_tile_words(depth);
+    const bool has_work = (int)blockIdx.x < n_tiles;
+    volatile int *ab = &abort_flag;
+    bool ok = true;
+
+    if (warp == 4) {
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < n_tiles && ok; tile += gridDim.x) {
+                const uint32_t *act = a.act_img + (size_t)tile * act_words, *dz = a.dz_img + (size_t)tile * dz_words;
+                for (int job = 0; job < n_jobs && ok; job++)
+                    for (int kb = 0; kb < 4; kb++, it++) {
+                        const uint32_t s = it % kB2Stages, ph = (it / kB2Stages) & 1u;
+                        if (!mbar_wait(&empty_bar[s], ph ^ 1u, ab)) { ok = false; break; }
+                        const uint32_t *A = (job < depth) ? dz + (size_t)job * 32768 + (size_t)kb * 8192
+                                                          : act + act_slot_block(depth, kb);
+                        const uint32_t *Bh;
+                        uint32_t part_words;                 // words of one part (hi or lo) of the B image
+                        if (job < depth) { Bh = act + act_slot_block(job, kb); part_words = (uint32_t)act_slot_half(job); }
+                        else { Bh = dz + (size_t)depth * 32768 + (size_t)kb * 1024; part_words = 512; }
+                        const uint32_t sb = smem_u32(stages + (size_t)s * kB2StageBytes);
+                        mbar_expect_tx(&full_bar[s], 32768 + 8 * part_words);
+                        tma_bulk_g2s(sb, A, 32768, &full_bar[s]);
+                        tma_bulk_g2s(sb + kB2BOff + 2048, Bh, 4 * part_words, &full_bar[s]);
+                        tma_bulk_g2s(sb + kB2BLoOff + 2048, Bh + part_words, 4 * part_words, &full_bar[s]);
+                    }
+            }
+        }
+    } else if (warp == 5) {
+        if (lane == 0) {
+            uint32_t it = 0;
+            bool first = true;
+            for (int tile = blockIdx.x; tile < n_tiles && ok; tile += gridDim.x, first = false)
+                for (int job = 0; job < n_jobs && ok; job++) {
+                    const uint32_t dcol = tmem + (uint32_t)job_col0(job, depth);
+                    const uint32_t idesc = instr_desc_n(job_cols(job, depth));
+                    for (int kb = 0; kb < 4; kb++, it++) {
+                        const uint32_t s = it % kB2Stages, ph = (it / kB2Stages) & 1u;
+                        if (!mbar_wait(&full_bar[s], ph, ab)) { ok = false; break; }
+                        tc_fence_after();
+                        const uint32_t sb = smem_u32(stages + (size_t)s * kB2StageBytes);
+                        for (int ks = 0; ks < 4; ks++) {
+                            const uint64_t a_hi = make_b_desc(sb + ks * 32), a_lo = make_b_desc(sb + kHalfStage + ks * 32);
+                            const uint64_t b_hi = make_b_desc(sb + kB2BOff + ks * 32), b_lo = make_b_desc(sb + kB2BLoOff + ks * 32);
+                            mma_tf32_ss(dcol, a_lo, b_hi, idesc, !(first && kb == 0 && ks == 0));
+                            mma_tf32_ss(dcol, a_hi, b_lo, idesc, 1u);
+                            mma_tf32_ss(dcol, a_hi, b_hi, idesc, 1u);
+                        }
+                        tc_commit(&empty_bar[s]);
+                    }
+                }
+            if (ok && has_work) tc_commit(&done_bar);
+        }
+    } else {
+        // dump the accumulators: partials[cta][column][row f], zeros for a CTA that had no tile
+        const int f = threadIdx.x;
+        float *dst = a.partials + (size_t)blockIdx.x * kPartialCols * kTileRows + f;
+        const int total = job_col0(depth, depth) + job_cols(depth, depth);
+        if (has_work) ok = mbar_wait(&done_bar, 0u, ab);
+        tc_fence_after();
+        const uint32_t tl = tmem + ((uint32_t)(warp * 32) << 16);
+#pragma unroll 1
+        for (int c0 = 0; c0 < total; c0 += 32) {
+            uint32_t z[32];
+            if (has_work && ok) { tmem_ld32(tl + c0, z); tmem_wait_ld(); }
+#pragma unroll
+            for (int j = 0; j < 32; j++)
+                if (c0 + j < total) dst[(size_t)(c0 + j) * kTileRows] = (has_work && ok) ? __uint_as_float(z[j]) : 0.f;
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x == 0 && abort_flag) atomicOr(a.status, kStatusTimeout);
+    if (warp == 0) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols) : "memory");
+    }
+}
+
+// sum the per-CTA partials in CTA order (deterministic) and scatter them into the gradient arrays; block 0 also sums dz_out
+__global__ void __launch_bounds__(128) k_shadow_bwd_reduce(ShadowDev a) {
+    const int depth = a.depth, f = threadIdx.x;
+    // blockIdx.x enumerates the accumulator columns that matter
+    int col = -1;
+    float *out = nullptr;
+    int b = blockIdx.x;
+    if (b < 1 + a.enc) {                                             // job 0: column 0 = db_in, 16 + e = dW_in[:, e]
+        col = (b == 0) ? 0 : 16 + (b - 1);
+        out = (b == 0) ? a.g_b_in + f : a.g_W_in + (size_t)f * a.enc + (b - 1);
+    } else {
+        b -= 1 + a.enc;
+        if (b < (depth - 1) * 129) {                                 // job l: column 0 = db, 16 + i = dW_l[:, i]
+            const int l = 1 + b / 129, c = b % 129;
+            col = job_col0(l, depth) + ((c == 0) ? 0 : 16 + (c - 1));
+            out = (c == 0) ? a.g_b_hid + (size_t)(l - 1) * kWidth + f
+                           : a.g_W_hid + (size_t)(l - 1) * kWidth * kWidth + (size_t)f * kWidth + (c - 1);
+        } else {                                                     // output job: column 16 = dw_out
+            col = job_col0(depth, depth) + 16;
+            out = a.g_w_out + f;
+        }
+    }
+    float s = 0.f;
+    for (int c = 0; c < a.n_ctas; c++) s += a.partials[((size_t)c * kPartialCols + col) * kTileRows + f];
+    *out = s;
+    if (blockIdx.x == 0 && f < 32) {                                 // db_out = sum of dz_out, fixed order
+        const int n_fg = a.n_fg[0];
+        const int n = min((n_fg + kTileRows - 1) / kTileRows, (int)(a.capacity / kTileRows)) * 4;
+        float t = 0.f;
+        for (int i = f; i < n; i += 32) t += a.dzo_sums[i];
+        t = warp_sum(t);
+        if (f == 0) a.g_b_out[0] = t;
+    }
+}
+
 }  // namespace
 
 extern "C" size_t gom_sizeof_shadow_mlp_args(void) { return sizeof(GomShadowMlpArgs); }
 extern "C" size_t gom_shadow_mlp_weight_image_bytes(int depth) {
-    return (depth >= 1 && depth <= kMaxDepth) ? (size_t)images_total(depth) * kStageBytes : 0;
+    return (depth >= 1 && depth <= kMaxDepth) ? (size_t)images_total_with_backward(depth) * kStageBytes : 0;
 }
+extern "C" size_t gom_shadow_mlp_tile_words(int depth, int which) {
+    if (depth < 1 || depth > kMaxDepth) return 0;
+    return which == 0 ? act_tile_words(depth) : dz_tile_words(depth);
+}
+extern "C" size_t gom_shadow_mlp_partial_floats(void) { return (size_t)kPartialCols * kTileRows; }
 
-extern "C" int gom_shadow_mlp_forward(const GomShadowMlpArgs *p, gom_stream_t stream_) {
+static int g_sm_count = 0;
+static int shadow_setup(void) {
+    if (g_sm_count) return GOM_OK;
+    int dev = 0, sms = 0;
+    GOM_CUDA(cudaGetDevice(&dev));
+    GOM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int dyn = kStages * kStageBytes + 1024, dyn2 = kB2Stages * kB2StageBytes + 1024;
+    GOM_CUDA(cudaFuncSetAttribute(k_shadow_fwd<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
+    GOM_CUDA(cudaFuncSetAttribute(k_shadow_fwd<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
+    GOM_CUDA(cudaFuncSetAttribute(k_shadow_bwd_data, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
+    GOM_CUDA(cudaFuncSetAttribute(k_shadow_bwd_weights, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn2));
+    g_sm_count = sms;
+    return GOM_OK;
+}
+extern "C" int gom_shadow_mlp_num_ctas(void) { return shadow_setup() == GOM_OK ? g_sm_count : 0; }
+
+static int shadow_fill(const GomShadowMlpArgs *p, ShadowDev &d, bool backward) {
     GOM_REQUIRE(p != nullptr, "args");
     GOM_REQUIRE(p->n_pixels > 0 && p->n_pixels < (1ll << 31) - 4096, "n_pixels");
     GOM_REQUIRE(p->width == kWidth, "width must be 128");
@@ -450,29 +952,36 @@ extern "C" int gom_shadow_mlp_forward(const GomShadowMlpArgs *p, gom_stream_t st
     GOM_REQUIRE(p->normals && p->W_in && p->b_in && p->W_out && p->b_out, "null input");
     GOM_REQUIRE(p->depth == 1 || (p->W_hid && p->b_hid), "null hidden weights");
     GOM_REQUIRE(p->block_count && p->fg_index && p->n_fg && p->w_images && p->bg_value && p->out && p->status, "null buffer");
-    GOM_REQUIRE(!p->save_hidden || (p->hidden && p->capacity > 0), "save_hidden needs hidden and capacity");
-    GOM_REQUIRE((reinterpret_cast<uintptr_t>(p->normals) & 15) == 0 && (reinterpret_cast<uintptr_t>(p->w_images) & 127) == 0,
-                "normals must be 16-byte and w_images 128-byte aligned");
-    cudaStream_t stream = (cudaStream_t)stream_;
-
-    ShadowDev d;
+    if (p->save_hidden || backward) {
+        GOM_REQUIRE(p->depth <= 3, "the backward pass supports depth <= 3 (tensor-memory columns of the weight-gradient accumulators)");
+        GOM_REQUIRE(p->act_img && p->capacity >= kTileRows && p->capacity % kTileRows == 0, "save_hidden needs act_img and a capacity that is a multiple of 128");
+    }
+    if (backward)
+        GOM_REQUIRE(p->g_out && p->dz_img && p->g_normals && p->dzo_sums && p->partials && p->g_W_in && p->g_b_in && p->g_w_out &&
+                    p->g_b_out && (p->depth == 1 || (p->g_W_hid && p->g_b_hid)), "null backward buffer");
+    GOM_REQUIRE((reinterpret_cast<uintptr_t>(p->normals) & 15) == 0 && (reinterpret_cast<uintptr_t>(p->w_images) & 127) == 0 &&
+                (reinterpret_cast<uintptr_t>(p->act_img) & 127) == 0 && (reinterpret_cast<uintptr_t>(p->dz_img) & 127) == 0,
+                "normals must be 16-byte, w_images / act_img / dz_img 128-byte aligned");
+    if (int rc = shadow_setup()) return rc;
     d.n_pixels = p->n_pixels; d.capacity = p->capacity;
-    d.multires = p->multires; d.enc = 3 + 6 * p->multires; d.depth = p->depth; d.save_hidden = p->save_hidden;
+    d.multires = p->multires; d.enc = 3 + 6 * p->multires; d.depth = p->depth; d.save_hidden = p->save_hidden; d.n_ctas = g_sm_count;
     d.normals = p->normals;
     d.W_in = p->W_in; d.b_in = p->b_in; d.W_hid = p->W_hid; d.b_hid = p->b_hid; d.W_out = p->W_out; d.b_out = p->b_out;
     d.block_count = p->block_count; d.fg_index = p->fg_index; d.n_fg = p->n_fg;
-    d.w_images = p->w_images; d.bg_value = p->bg_value; d.out = p->out; d.hidden = p->hidden; d.status = p->status;
+    d.w_images = p->w_images; d.bg_value = p->bg_value; d.out = p->out; d.status = p->status;
+    d.act_img = reinterpret_cast<uint32_t *>(p->act_img); d.dz_img = reinterpret_cast<uint32_t *>(p->dz_img);
+    d.g_out = p->g_out; d.g_normals = p->g_normals; d.dzo_sums = p->dzo_sums; d.partials = p->partials;
+    d.g_W_in = p->g_W_in; d.g_b_in = p->g_b_in; d.g_W_hid = p->g_W_hid; d.g_b_hid = p->g_b_hid; d.g_w_out = p->g_w_out; d.g_b_out = p->g_b_out;
+    return GOM_OK;
+}
 
-    static int sm_count = 0;
+extern "C" int gom_shadow_mlp_forward(const GomShadowMlpArgs *p, gom_stream_t stream_) {
+    ShadowDev d;
+    if (int rc = shadow_fill(p, d, false)) return rc;
+    cudaStream_t stream = (cudaStream_t)stream_;
     const size_t dyn_smem = (size_t)kStages * kStageBytes + 1024;
-    if (sm_count == 0) {
-        int dev = 0;
-        GOM_CUDA(cudaGetDevice(&dev));
-        GOM_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
-        GOM_CUDA(cudaFuncSetAttribute(k_shadow_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem));
-    }
     const int nblk = gom_div_up(p->n_pixels, 1024);
-    const int n_img = images_total(p->depth);
+    const int n_img = p->save_hidden ? images_total_with_backward(p->depth) : images_total(p->depth);
 
     gom_prof_begin(GOM_PROF_SHADOW_COMPACT, stream);
     k_shadow_prep<<<gom_div_up((int64_t)n_img * 4096, 256) + 1, 256, 0, stream>>>(d);
@@ -486,8 +995,27 @@ extern "C" int gom_shadow_mlp_forward(const GomShadowMlpArgs *p, gom_stream_t st
     gom_prof_end(GOM_PROF_SHADOW_COMPACT, stream);
 
     gom_prof_begin(GOM_PROF_SHADOW_FWD, stream);
-    k_shadow_fwd<<<sm_count, kThreads, dyn_smem, stream>>>(d);
+    if (p->save_hidden) k_shadow_fwd<true><<<g_sm_count, kThreads, dyn_smem, stream>>>(d);
+    else k_shadow_fwd<false><<<g_sm_count, kThreads, dyn_smem, stream>>>(d);
     GOM_LAUNCH_CHECK();
     gom_prof_end(GOM_PROF_SHADOW_FWD, stream);
+    return GOM_OK;
+}
+
+// Backward of a forward call made with save_hidden = 1 on the SAME buffers (fg_index, n_fg, out, w_images, act_img).
+extern "C" int gom_shadow_mlp_backward(const GomShadowMlpArgs *p, gom_stream_t stream_) {
+    ShadowDev d;
+    if (int rc = shadow_fill(p, d, true)) return rc;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    gom_prof_begin(GOM_PROF_SHADOW_BWD_DATA, stream);
+    k_shadow_bwd_data<<<g_sm_count, kThreads, (size_t)kStages * kStageBytes + 1024, stream>>>(d);
+    GOM_LAUNCH_CHECK();
+    gom_prof_end(GOM_PROF_SHADOW_BWD_DATA, stream);
+    gom_prof_begin(GOM_PROF_SHADOW_BWD_WEIGHTS, stream);
+    k_shadow_bwd_weights<<<g_sm_count, kThreads, (size_t)kB2Stages * kB2StageBytes + 1024, stream>>>(d);
+    GOM_LAUNCH_CHECK();
+    k_shadow_bwd_reduce<<<1 + d.enc + (d.depth - 1) * 129 + 1, 128, 0, stream>>>(d);
+    GOM_LAUNCH_CHECK();
+    gom_prof_end(GOM_PROF_SHADOW_BWD_WEIGHTS, stream);
     return GOM_OK;
 }

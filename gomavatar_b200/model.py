@@ -10,8 +10,9 @@ What differs from the reference, by design:
 * LBS -> face frame -> covariance -> splat is ~10 kernel launches with no host sync instead of ~150 launches and 6 syncs;
 * RGB and alpha are rendered in ONE 4-channel pass instead of the reference's two 3-channel passes
   (gaussian.py:77-94) — same values, same gradients (tests/test_model_gpu.py).
-The pose-refinement / non-rigid MLPs, the mesh normal renderer and the shadow MLP are NOT part of the hot path
-(SURVEY.md §8f "next" rows); they plug in as optional callables with the reference's call signatures.
+The pose-refinement / non-rigid MLPs are plain torch modules (modules.py); the mesh normal renderer (mesh_renderer.py,
+csrc/mesh_raster.cu) and the shadow MLP (shadow.py, csrc/shadow_mlp.cu: tcgen05) are the SURVEY.md §8f "next" rows and
+are built from the reference's cfg nodes; all of them can be replaced by callables with the reference's signatures.
 """
 from __future__ import annotations
 
@@ -76,6 +77,19 @@ def mesh_edges(faces, vertices):
     return length, conn
 
 
+def _shadow_module(sub):
+    """The tcgen05 shadow MLP (shadow.FusedShadowModule) for the configuration family the reference ships; the plain
+    torch module (cuBLAS) for anything else (other widths, skip connections inside the depth)."""
+    from . import modules, shadow
+    try:
+        m = shadow.FusedShadowModule(sub)
+        if len(m._linears()) - 1 > shadow.MAX_TRAIN_DEPTH:            # deeper MLPs: inference only on the fused path
+            raise NotImplementedError
+        return m
+    except NotImplementedError:
+        return modules.ShadowModule(sub)
+
+
 class AppearanceModule(nn.Module):
     """reference models/modules/appearance_module.py:6-23 — per-face RGB + zero background buffer."""
 
@@ -122,7 +136,7 @@ class Model(nn.Module):
         self.non_rigid_module = build(non_rigid_module, "non_rigid", modules.NonRigidModule)
         self.normal_renderer = build(normal_renderer, "normal_renderer", lambda sub: mesh_renderer.Renderer(
             sub, canonical_info, img_size=_get(model_cfg, "img_size", [512, 512])))
-        self.shadow_module = build(shadow_module, "shadow_module", modules.ShadowModule)
+        self.shadow_module = build(shadow_module, "shadow_module", _shadow_module)
         tel, conn = mesh_edges(faces.numpy(), verts.numpy().T)
         self.register_buffer("target_edge_length", torch.from_numpy(tel))       # reference model.py:58-60,127-134
         self.register_buffer("face_connectivity", torch.from_numpy(conn), persistent=False)

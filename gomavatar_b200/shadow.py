@@ -1,4 +1,4 @@
-"""``ShadowModule`` on the tcgen05 kernel of csrc/shadow_mlp.cu — drop-in for reference
+"""``ShadowModule`` on the tcgen05 kernels of csrc/shadow_mlp.cu — drop-in for reference
 ``models/modules/shadow_module.py::ShadowModule`` (constructor ``ShadowModule(module_cfg)``, ``forward(normals [B,N,3])
 -> [B,N,1]`` in (0,1), state-dict keys ``block_mlps.{0,2,..}.{weight,bias}``), SURVEY.md §8 f-2.
 
@@ -6,11 +6,12 @@ Forward: ``gom_shadow_mlp_forward`` — foreground compaction (the mesh renderer
 reference mesh.py:103-112, so those pixels share ONE value), weights split into TF32 hi/lo, and a persistent kernel that
 keeps the activations in tensor memory (3xTF32 products, fp32 accumulation: fp32-GEMM accuracy, see the kernel header).
 
-Backward: the kernel saved the post-ReLU activations of the foreground rows feature-major ``[depth,128,capacity]``; the
-gradient GEMMs (dW = dZ^T H, dH = dZ W, K = foreground rows) are plain fp32 cuBLAS calls on those fixed-capacity buffers
-— static shapes, no host sync, CUDA-graph capturable; padded rows carry zero gradient.  The background pixels are one
-extra row with normal 0 and the summed gradient of all background pixels (the reference evaluates the MLP on them too,
-so they contribute weight gradients).  There is no CPU path: inputs must be CUDA tensors and the library must be built.
+Backward: ``gom_shadow_mlp_backward`` — the forward saved its operands as TF32 hi/lo images; one tcgen05 kernel runs the
+chain backwards to dL/dnormal, a second one accumulates the weight/bias gradients as split-K GEMMs in tensor memory, a
+fixed-order reduction makes the result deterministic.  Static shapes, no host sync: CUDA-graph capturable.  The
+background pixels are ONE extra row with normal 0 carrying the summed gradient of all background pixels (the reference
+evaluates the MLP on them too, so they contribute weight gradients and receive a normal gradient): a handful of tiny torch
+ops (``background_row``).  There is no CPU path: inputs must be CUDA tensors and the library must be built.
 """
 from __future__ import annotations
 
@@ -20,6 +21,8 @@ from . import _lib
 from ._lib import GomShadowMlpArgs, call, ptr
 from .modules import ShadowModule as _TorchShadowModule
 from .modules import posenc
+
+MAX_TRAIN_DEPTH = 3          # tensor-memory columns of the weight-gradient accumulators (csrc/shadow_mlp.cu)
 
 
 def _posenc_backward(x, g_enc, multires):
@@ -32,88 +35,53 @@ def _posenc_backward(x, g_enc, multires):
     return g
 
 
-def _mlp_backward(enc, hidden_t, weights, w_out, dz_out):
-    """Backward of Linear/ReLU x depth + Linear(width,1) given the saved activations.
+def background_row(weights, biases, w_out, b_out, multires):
+    """The MLP at normal = 0 and its gradients for a unit upstream gradient (device-agnostic torch, one row).
 
-    enc [R,E] layer-0 input; hidden_t: list of [W,R] post-ReLU activations (feature-major); weights: list of [W,in];
-    w_out [W]; dz_out [R] gradient of the pre-sigmoid output.  Returns (g_enc [R,E], [dW_l], [db_l], dw_out [W], db_out)."""
-    depth = len(hidden_t)
-    dw_out = hidden_t[-1] @ dz_out
-    db_out = dz_out.sum()
-    dzt = (w_out[:, None] * dz_out[None, :]) * (hidden_t[-1] > 0)                # [W,R]
-    dWs, dbs = [None] * depth, [None] * depth
-    for l in range(depth - 1, 0, -1):
-        dWs[l] = dzt @ hidden_t[l - 1].t()                                       # [W,W]
-        dbs[l] = dzt.sum(dim=1)
-        dzt = (weights[l].t() @ dzt) * (hidden_t[l - 1] > 0)
-    dWs[0] = dzt @ enc                                                           # [W,E]
-    dbs[0] = dzt.sum(dim=1)
-    g_enc = dzt.t() @ weights[0]                                                 # [R,E]
-    return g_enc, dWs, dbs, dw_out, db_out
-
-
-def shadow_backward(normals, out, fg_index, n_fg, hidden, weights, biases, w_out, b_out, g_out, multires, cap):
-    """Gradients of sum(out * g_out) from what gom_shadow_mlp_forward left behind (device-agnostic torch, static shapes).
-
-    normals [N,3]; out [N] sigmoid outputs; fg_index [>=cap] foreground pixel ids; n_fg [1] their count (device tensor);
-    hidden [depth,W,cap] post-ReLU activations of foreground row r in column r.  Returns (g_normals [N,3], g_w_out [1,W],
-    g_b_out [1], [g_W0, g_b0, g_W1, g_b1, ...])."""
-    depth = len(weights)
-    dev = normals.device
-    g_out = g_out.contiguous().float()
-    rows = torch.arange(cap, device=dev)
-    valid = rows < n_fg.clamp(max=cap)                                            # device-side, no sync
-    idx = torch.where(valid, fg_index[:cap].long(), torch.zeros_like(rows))
-    y = out[idx]
-    gy = torch.where(valid, g_out[idx], torch.zeros_like(y))
-    dz_out = gy * y * (1.0 - y)
-    x = torch.where(valid[:, None], normals[idx], torch.zeros(1, 3, device=dev))
-    enc = posenc(x, multires, include_input=True)
-    # rows >= n_fg of `hidden` are stale but finite (the buffer starts as zeros) and their dz is exactly 0
-    hidden_t = [hidden[l] for l in range(depth)]
-    g_enc, dWs, dbs, dw_out, db_out = _mlp_backward(enc, hidden_t, weights, w_out, dz_out)
-    # the background: one row with normal 0 carrying the summed gradient of every background pixel (the reference
-    # evaluates the MLP there too); the MLP backward is linear in dz, so it is run for dz = y0 (1 - y0) and scaled
+    weights/biases: the Linear+ReLU layers; w_out [W], b_out [1].  Returns (y0 scalar tensor, g_x0 [1,3] = d out / d normal,
+    [dW_l], [db_l], dw_out [W], db_out scalar) — everything is linear in the upstream gradient, the caller scales it."""
+    dev = w_out.device
     x0 = torch.zeros(1, 3, device=dev)
     enc0 = posenc(x0, multires, include_input=True)
-    h, hid0 = enc0, []
-    for l in range(depth):
-        h = torch.relu(h @ weights[l].t() + biases[l])
-        hid0.append(h.t().contiguous())
-    y0 = torch.sigmoid(h @ w_out[:, None] + b_out)
-    g_bg = g_out.sum() - gy.sum()
-    g_enc0, dWs0, dbs0, dw_out0, db_out0 = _mlp_backward(enc0, hid0, weights, w_out, (y0 * (1.0 - y0)).reshape(1))
-    g_x0 = _posenc_backward(x0, g_enc0, multires)                                 # [1,3]: d out / d normal at normal = 0
-    is_bg = (normals == 0).all(dim=1, keepdim=True)
-    g_normals = torch.where(is_bg, g_out[:, None] * g_x0, torch.zeros_like(normals))
-    g_normals.index_add_(0, idx, _posenc_backward(x, g_enc, multires))
-    g_wb = []
-    for l in range(depth):
-        g_wb += [dWs[l] + g_bg * dWs0[l], dbs[l] + g_bg * dbs0[l]]
-    return g_normals, (dw_out + g_bg * dw_out0).reshape(1, -1), (db_out + g_bg * db_out0).reshape(1), g_wb
+    h, hid = enc0, []
+    for W, b in zip(weights, biases):
+        h = torch.relu(h @ W.t() + b)
+        hid.append(h)
+    y0 = torch.sigmoid(h @ w_out[:, None] + b_out).reshape(())
+    dz = y0 * (1.0 - y0)
+    dw_out, db_out = hid[-1][0] * dz, dz
+    dzl = (w_out * dz) * (hid[-1][0] > 0)                                         # [W]
+    dWs, dbs = [None] * len(weights), [None] * len(weights)
+    for l in range(len(weights) - 1, 0, -1):
+        dWs[l], dbs[l] = torch.outer(dzl, hid[l - 1][0]), dzl
+        dzl = (weights[l].t() @ dzl) * (hid[l - 1][0] > 0)
+    dWs[0], dbs[0] = torch.outer(dzl, enc0[0]), dzl
+    g_x0 = _posenc_backward(x0, (dzl @ weights[0])[None], multires)
+    return y0, g_x0, dWs, dbs, dw_out, db_out
 
 
 class _ShadowMlp(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, module, normals, w_out, b_out, *wb):
+    def forward(ctx, module, need_grad, normals, w_out, b_out, *wb):
         """normals [N,3] contiguous fp32 CUDA; wb = (W_0, b_0, W_1, b_1, ...) of the Linear+ReLU layers."""
         depth = len(wb) // 2
+        if need_grad and depth > MAX_TRAIN_DEPTH:
+            raise NotImplementedError(f"FusedShadowModule: the backward pass supports mlp_depth <= {MAX_TRAIN_DEPTH}")
         weights, biases = list(wb[0::2]), list(wb[1::2])
         N = normals.shape[0]
-        need_grad = any(ctx.needs_input_grad)            # (grad mode is off inside Function.forward; this accounts for it)
-        ws = module._workspace(N, depth, normals.device, need_grad)
         W_hid = torch.stack([w.detach() for w in weights[1:]]).contiguous() if depth > 1 else None
         b_hid = torch.stack([b.detach() for b in biases[1:]]).contiguous() if depth > 1 else None
         W_in, b_in = weights[0].detach().contiguous(), biases[0].detach().contiguous()
         wo, bo = w_out.detach().reshape(-1).contiguous(), b_out.detach().reshape(-1).contiguous()
         out = torch.empty(N, dtype=torch.float32, device=normals.device)
         while True:
+            ws = module._workspace(N, depth, normals.device, need_grad)
             a = GomShadowMlpArgs(n_pixels=N, capacity=ws["capacity"], multires=module.multires, width=module.width, depth=depth,
                                  save_hidden=int(need_grad), normals=ptr(normals), W_in=ptr(W_in), b_in=ptr(b_in),
                                  W_hid=ptr(W_hid), b_hid=ptr(b_hid), W_out=ptr(wo), b_out=ptr(bo),
                                  block_count=ptr(ws["block_count"]), fg_index=ptr(ws["fg_index"]), n_fg=ptr(ws["n_fg"]),
                                  w_images=ptr(ws["w_images"]), bg_value=ptr(ws["bg_value"]), out=ptr(out),
-                                 hidden=ptr(ws["hidden"]) if need_grad else None, status=ptr(ws["status"]))
+                                 act_img=ptr(ws["act_img"]) if need_grad else None, status=ptr(ws["status"]))
             call("gom_shadow_mlp_forward", a)
             if not module.strict or torch.cuda.is_current_stream_capturing():
                 break                                   # status stays on the device: FusedShadowModule.check_status()
@@ -122,29 +90,54 @@ class _ShadowMlp(torch.autograd.Function):
                 raise _lib.GomError("gom_shadow_mlp_forward: tcgen05 pipeline wait timed out (status TIMEOUT)")
             if status & _lib.STATUS_OVERFLOW:           # more foreground than rows kept for backward: regrow, rerun
                 n_fg = int(ws["n_fg"].item())
-                module.capacity = min(N, (int(n_fg * 1.25) + 127) // 128 * 128)
-                ws = module._workspace(N, depth, normals.device, need_grad)
+                module.capacity = (int(n_fg * 1.25) + 127) // 128 * 128
                 continue
             break
         if need_grad:
-            ctx.module, ctx.depth, ctx.capacity = module, depth, ws["capacity"]
-            ctx.save_for_backward(normals, out, ws["fg_index"], ws["n_fg"], ws["hidden"], wo, *weights)
+            ctx.module, ctx.depth, ctx.ws = module, depth, ws
+            ctx.fwd_args = (W_in, b_in, W_hid, b_hid, wo, bo)
+            ctx.save_for_backward(normals, out)
         return out
 
     @staticmethod
     def backward(ctx, g_out):
-        normals, out, fg_index, n_fg, hidden, wo = ctx.saved_tensors[:6]
-        weights = [w.detach() for w in ctx.saved_tensors[6:]]
-        m = ctx.module
-        g_normals, g_wo, g_bo, g_wb = shadow_backward(normals, out, fg_index, n_fg, hidden, weights, m._biases_detached(), wo,
-                                                      m._b_out_detached(), g_out, m.multires, ctx.capacity)
-        return (None, g_normals, g_wo, g_bo, *g_wb)
+        module, depth, ws = ctx.module, ctx.depth, ctx.ws
+        normals, out = ctx.saved_tensors
+        W_in, b_in, W_hid, b_hid, wo, bo = ctx.fwd_args
+        dev = normals.device
+        N = normals.shape[0]
+        g_out = g_out.contiguous().float()
+        weights = [W_in] + ([W_hid[l] for l in range(depth - 1)] if depth > 1 else [])
+        biases = [b_in] + ([b_hid[l] for l in range(depth - 1)] if depth > 1 else [])
+        # the background row (normal 0): value gradient for those pixels, parameter gradients scaled by their summed g_out
+        _, g_x0, dWs0, dbs0, dw_out0, db_out0 = background_row(weights, biases, wo, bo, module.multires)
+        is_bg = (normals == 0).all(dim=1)
+        g_bg = (g_out * is_bg).sum()
+        g_normals = torch.where(is_bg[:, None], g_out[:, None] * g_x0, torch.zeros((), device=dev))
+        e = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
+        gW_in, gb_in, gw_out, gb_out = e(module.width, W_in.shape[1]), e(module.width), e(module.width), e(1)
+        gW_hid = e(depth - 1, module.width, module.width) if depth > 1 else None
+        gb_hid = e(depth - 1, module.width) if depth > 1 else None
+        a = GomShadowMlpArgs(n_pixels=N, capacity=ws["capacity"], multires=module.multires, width=module.width, depth=depth,
+                             save_hidden=1, normals=ptr(normals), W_in=ptr(W_in), b_in=ptr(b_in), W_hid=ptr(W_hid), b_hid=ptr(b_hid),
+                             W_out=ptr(wo), b_out=ptr(bo), block_count=ptr(ws["block_count"]), fg_index=ptr(ws["fg_index"]),
+                             n_fg=ptr(ws["n_fg"]), w_images=ptr(ws["w_images"]), bg_value=ptr(ws["bg_value"]), out=ptr(out),
+                             act_img=ptr(ws["act_img"]), status=ptr(ws["status"]), g_out=ptr(g_out), dz_img=ptr(ws["dz_img"]),
+                             g_normals=ptr(g_normals), dzo_sums=ptr(ws["dzo_sums"]), partials=ptr(ws["partials"]),
+                             g_W_in=ptr(gW_in), g_b_in=ptr(gb_in), g_W_hid=ptr(gW_hid), g_b_hid=ptr(gb_hid),
+                             g_w_out=ptr(gw_out), g_b_out=ptr(gb_out))
+        call("gom_shadow_mlp_backward", a)
+        grads = [gW_in + g_bg * dWs0[0], gb_in + g_bg * dbs0[0]]
+        for l in range(1, depth):
+            grads += [gW_hid[l - 1] + g_bg * dWs0[l], gb_hid[l - 1] + g_bg * dbs0[l]]
+        return (None, None, g_normals, (gw_out + g_bg * dw_out0).reshape(1, -1), (gb_out + g_bg * db_out0).reshape(1), *grads)
 
 
 class FusedShadowModule(_TorchShadowModule):
     """Same parameters / state dict as ``modules.ShadowModule`` (and therefore as the reference's); forward on the
-    tcgen05 kernel.  ``capacity``: foreground rows kept for the backward pass (default: a quarter of the pixels, regrown
-    automatically when ``strict``); ``strict=False`` never reads the device status (for CUDA-graph capture)."""
+    tcgen05 kernels.  ``capacity``: foreground rows kept for the backward pass (default: a quarter of the pixels, regrown
+    automatically when ``strict``); ``strict=False`` never reads the device status (for CUDA-graph capture).  Training
+    needs ``mlp_depth <= 3`` (the reference's configs use 3); inference supports up to 8."""
 
     def __init__(self, module_cfg=None, capacity=None, strict=True, **kwargs):
         super().__init__(module_cfg, **kwargs)
@@ -160,26 +153,26 @@ class FusedShadowModule(_TorchShadowModule):
     def _linears(self):
         return [m for m in self.block_mlps if isinstance(m, torch.nn.Linear)]
 
-    def _biases_detached(self):
-        return [m.bias.detach() for m in self._linears()[:-1]]
-
-    def _b_out_detached(self):
-        return self._linears()[-1].bias.detach()
-
-    def _workspace(self, n_pixels, depth, device, need_hidden):
+    def _workspace(self, n_pixels, depth, device, need_backward):
         cap = self.capacity if self.capacity else max(128, (n_pixels // 4 + 127) // 128 * 128)
-        cap = min(cap, (n_pixels + 127) // 128 * 128)
+        cap = min((cap + 127) // 128 * 128, (n_pixels + 127) // 128 * 128)
         key = (n_pixels, depth, str(device), cap)
+        L = _lib.lib()
         if self._ws is None or self._ws["key"] != key:
-            img_bytes = int(_lib.lib().gom_shadow_mlp_weight_image_bytes(depth))
+            img_bytes = int(L.gom_shadow_mlp_weight_image_bytes(depth))
             e = lambda *s, dtype=torch.float32: torch.empty(*s, dtype=dtype, device=device)
             self._ws = dict(key=key, capacity=cap, block_count=e((n_pixels + 1023) // 1024 + 1, dtype=torch.int32),
-                            fg_index=torch.zeros(max(n_pixels, cap), dtype=torch.int32, device=device),
-                            n_fg=torch.zeros(1, dtype=torch.int32, device=device), w_images=e(img_bytes // 4),
-                            bg_value=e(1), status=torch.zeros(1, dtype=torch.int32, device=device), hidden=None)
-        if need_hidden and self._ws["hidden"] is None:
-            # zeros once: rows the kernel never writes must stay finite for the padded backward GEMMs
-            self._ws["hidden"] = torch.zeros(depth, self.width, cap, dtype=torch.float32, device=device)
+                            fg_index=e(n_pixels, dtype=torch.int32), n_fg=torch.zeros(1, dtype=torch.int32, device=device),
+                            w_images=e(img_bytes // 4), bg_value=e(1), status=torch.zeros(1, dtype=torch.int32, device=device),
+                            act_img=None)
+        if need_backward and self._ws["act_img"] is None:
+            tiles = cap // 128
+            e = lambda *s, dtype=torch.float32: torch.empty(*s, dtype=dtype, device=device)
+            self._ws.update(
+                act_img=e(tiles * int(L.gom_shadow_mlp_tile_words(depth, 0)), dtype=torch.int32),
+                # zeros once: rows 1..15 of the dz_out images are never written and must stay 0
+                dz_img=torch.zeros(tiles * int(L.gom_shadow_mlp_tile_words(depth, 1)), dtype=torch.int32, device=device),
+                dzo_sums=e(tiles * 4), partials=e(int(L.gom_shadow_mlp_num_ctas()) * int(L.gom_shadow_mlp_partial_floats())))
         return self._ws
 
     def check_status(self):
@@ -202,5 +195,8 @@ class FusedShadowModule(_TorchShadowModule):
         wb = []
         for m in lin[:-1]:
             wb += [m.weight, m.bias]
-        out = _ShadowMlp.apply(self, flat, lin[-1].weight, lin[-1].bias, *wb)
+        # grad mode is off inside Function.forward and ctx.needs_input_grad ignores torch.no_grad(): decide here whether
+        # the kernel has to keep the hidden activations for a backward pass
+        need_grad = torch.is_grad_enabled() and (flat.requires_grad or any(p.requires_grad for p in self.parameters()))
+        out = _ShadowMlp.apply(self, need_grad, flat, lin[-1].weight, lin[-1].bias, *wb)
         return out.reshape(*shape, 1)

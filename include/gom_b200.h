@@ -429,12 +429,17 @@ int gom_adam_step(const GomAdamArgs *a, gom_stream_t stream);
  * One call = pixel compaction (normal != 0; the background gets sigmoid(MLP(posenc(0))) as a constant), weight
  * preparation and one persistent tcgen05 kernel (3xTF32 split products, fp32 accumulation in tensor memory).
  * out[p] is the sigmoid output for EVERY pixel (the caller multiplies by 2, model.py:283).
- * For a backward pass set save_hidden: hidden[l][j][r] = post-ReLU activation j of layer l of foreground row r
- * (row r is pixel fg_index[r]; rows >= capacity are dropped and GOM_STATUS_OVERFLOW is set in status[0]).
+ * Backward (depth <= 3): call forward with save_hidden = 1 — it then also writes every matrix operand it formed as
+ * TF32 hi/lo "activation images" into act_img (private layout, gom_shadow_mlp_tile_words(depth, 0) words per tile of 128
+ * foreground rows; rows >= capacity are dropped and GOM_STATUS_OVERFLOW is set in status[0]) — and later
+ * gom_shadow_mlp_backward with the SAME struct plus g_out: it writes dL/dnormal of every FOREGROUND pixel into g_normals
+ * (background entries are left untouched) and the parameter gradients of the foreground rows into g_W_in ... g_b_out.
+ * The background pixels share one row (normal 0); their contribution is the caller's (one row, see shadow.py).
+ * Two tcgen05 kernels (data gradients; split-K weight gradients with per-CTA partials) + a fixed-order reduction.
  */
 typedef struct {
     int64_t n_pixels;            /* B*H*W */
-    int64_t capacity;            /* rows of `hidden` (save_hidden only) */
+    int64_t capacity;            /* foreground rows act_img / dz_img hold (save_hidden / backward): a multiple of 128 */
     int32_t multires;            /* positional-encoding octaves (6): encoding width 3 + 6*multires <= 63 */
     int32_t width;               /* must be 128 */
     int32_t depth;               /* number of Linear+ReLU layers (mlp_depth, 3); 1..8 */
@@ -449,11 +454,24 @@ typedef struct {
     float *w_images;             /* scratch, gom_shadow_mlp_weight_image_bytes(depth) bytes, 128-byte aligned */
     float *bg_value;             /* [1] out: the background constant */
     float *out;                  /* [n_pixels] out */
-    float *hidden;               /* [depth, width, capacity] out (save_hidden), else NULL */
+    void *act_img;               /* [capacity/128 tiles, gom_shadow_mlp_tile_words(depth,0)] u32 out (save_hidden), else NULL */
     uint32_t *status;            /* [1] out: GOM_STATUS_OVERFLOW | GOM_STATUS_TIMEOUT */
+    /* ---- backward only */
+    const float *g_out;          /* [n_pixels] dL/dout */
+    void *dz_img;                /* [capacity/128, gom_shadow_mlp_tile_words(depth,1)] u32 scratch, ZERO-INITIALISED once by the caller */
+    float *g_normals;            /* [n_pixels,3]: foreground rows are written */
+    float *dzo_sums;             /* scratch [capacity/128 * 4] */
+    float *partials;             /* scratch [gom_shadow_mlp_num_ctas(), gom_shadow_mlp_partial_floats()] */
+    float *g_W_in, *g_b_in;      /* [width, 3+6*multires], [width] out */
+    float *g_W_hid, *g_b_hid;    /* [depth-1, width, width], [depth-1, width] out */
+    float *g_w_out, *g_b_out;    /* [width], [1] out */
 } GomShadowMlpArgs;
 int gom_shadow_mlp_forward(const GomShadowMlpArgs *a, gom_stream_t stream);
+int gom_shadow_mlp_backward(const GomShadowMlpArgs *a, gom_stream_t stream);
 size_t gom_shadow_mlp_weight_image_bytes(int depth);
+size_t gom_shadow_mlp_tile_words(int depth, int which);     /* which: 0 = act_img, 1 = dz_img */
+size_t gom_shadow_mlp_partial_floats(void);
+int gom_shadow_mlp_num_ctas(void);                          /* CTAs of the persistent kernels = SMs of the current device */
 
 /* struct sizes, so that a foreign-language binding can assert its mirror of the structs */
 size_t gom_sizeof_camera_args(void);

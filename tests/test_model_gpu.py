@@ -116,7 +116,8 @@ def test_state_dict_keys_match_reference_checkpoint_layout(golden_dir):
     assert m.vertices.shape[0] == 3 and m.so3.shape[0] == 3 and m.lbs_weights.shape[0] == 25
 
 
-def test_full_model_with_all_reference_modules_matches_oracle_composition():
+@pytest.mark.parametrize("shadow_width", [64, 128])        # 128: the tcgen05 FusedShadowModule; 64: the torch module
+def test_full_model_with_all_reference_modules_matches_oracle_composition(shadow_width):
     """Model built from a reference-shaped cfg (pose refinement, non-rigid, mesh normal renderer, shadow MLP all on):
     rgbs = albedo * shading, masks, normal map and soft normal mask against the CPU composition of the oracles, and the
     backward reaches every parameter group (reference models/model.py:184-303)."""
@@ -132,7 +133,7 @@ def test_full_model_with_all_reference_modules_matches_oracle_composition():
            "non_rigid": {"name": "basic", "condition_code_size": 69, "mlp_width": 64, "mlp_depth": 3, "skips": [4], "multires": 6,
                          "i_embed": 0, "kick_in_iter": 0, "full_band_iter": 10},
            "normal_renderer": {"name": "mesh", "soft_mask": True, "sigma": 1e-5},
-           "shadow_module": {"name": "basic", "mlp_width": 64, "mlp_depth": 3, "skips": [4], "multires": 6}}
+           "shadow_module": {"name": "basic", "mlp_width": shadow_width, "mlp_depth": 3, "skips": [4], "multires": 6}}
     sc = S.make_humanoid(2000, seed=0)
     fr = S.make_frames(sc, 1, img_size=(W, H), seed=3)
     pr = S.make_params(sc, seed=1)
@@ -144,7 +145,12 @@ def test_full_model_with_all_reference_modules_matches_oracle_composition():
         m.pose_refinement_module.block_mlps[-1].weight.normal_(0, 2e-3)          # a visible pose correction
         m.non_rigid_module.block_mlps[-1].weight.normal_(0, 2e-4)                # a visible (sub-centimetre) offset
         m.shadow_module.block_mlps[-1].weight.normal_(0, 0.3)
+    from gomavatar_b200.modules import ShadowModule
+    from gomavatar_b200.shadow import FusedShadowModule
+    assert isinstance(m.shadow_module, FusedShadowModule) == (shadow_width == 128)
     cpu = copy.deepcopy(m)                                                       # same weights for the CPU composition
+    cpu.shadow_module = ShadowModule(cfg["shadow_module"])                       # (the fused module has no CPU path)
+    cpu.shadow_module.load_state_dict(m.shadow_module.state_dict())
     m = m.to(DEV).train()
     d = {k: t(v).to(DEV) for k, v in fr.items()}
     rgbs, masks, out = m(d["K"], d["E"], d["cnl_gtfms"], d["dst_Rs"], d["dst_Ts"], dst_posevec=d["dst_posevec"], i_iter=7)

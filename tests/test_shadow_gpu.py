@@ -85,9 +85,12 @@ def test_many_tiles_per_cta_full_frame_batch():
     assert np.abs(out - ref).max() <= 1e-5
 
 
-@pytest.mark.parametrize("n,fg_frac", [(3000, 0.6), (50_000, 0.2)])
-def test_backward_matches_oracle(n, fg_frac):
-    m = _trained_like(FusedShadowModule(_cfg()), seed=2).to(DEV)
+@pytest.mark.parametrize("n,fg_frac,depth", [(3000, 0.6, 3), (50_000, 0.2, 3), (2 * 512 * 512, 0.3, 3), (4000, 0.5, 1), (4000, 0.5, 2),
+                                             (100, 0.0, 3)])
+def test_backward_matches_oracle(n, fg_frac, depth):
+    """data gradients (k_shadow_bwd_data), weight/bias gradients (k_shadow_bwd_weights: split-K in tensor memory over up to
+    ~8 tiles per CTA at the largest size) and the background row"""
+    m = _trained_like(FusedShadowModule(_cfg(depth)), seed=2).to(DEV)
     x = _normals(n, fg_frac, seed=n + 1)
     g_out = torch.randn(n, generator=torch.Generator().manual_seed(4))
     xg = x.to(DEV).requires_grad_(True)
@@ -100,11 +103,38 @@ def test_backward_matches_oracle(n, fg_frac):
     def close(a, ref, what):
         err = np.abs(a.detach().cpu().numpy().astype(np.float64) - ref).max()
         assert err <= 1e-3 * np.abs(ref).max() + 1e-9, (what, err, np.abs(ref).max())
-    close(xg.grad, r_n, "normals")
+    # dL/dnormal is per pixel: a hidden unit whose pre-activation is within rounding of 0 has its ReLU decided by the last
+    # bit (fp32 here, float64 in the oracle) and moves that ONE pixel's gradient by up to ~1e-2 of the maximum (seen: 1 unit
+    # in 6e7 at the largest size, tools/shadow_debug.py).  Strict bound on all but 1e-4 of the pixels, loose bound on the rest.
+    e_n = np.abs(xg.grad.detach().cpu().numpy().astype(np.float64) - r_n).max(axis=1)
+    assert (e_n > 1e-3 * np.abs(r_n).max()).mean() <= 1e-4 and e_n.max() <= 5e-2 * np.abs(r_n).max(), (e_n.max(), np.abs(r_n).max())
     lin = [t for t in m.block_mlps if isinstance(t, torch.nn.Linear)]
     for l, layer in enumerate(lin):
         close(layer.weight.grad, r_W[l], f"W{l}")
         close(layer.bias.grad, r_b[l], f"b{l}")
+
+
+def test_backward_is_deterministic():
+    m = _trained_like(FusedShadowModule(_cfg()), seed=2).to(DEV)
+    x = _normals(300_000, 0.4, seed=12).to(DEV)
+    g_out = torch.randn(300_000, device=DEV, generator=torch.Generator(device=DEV).manual_seed(4))
+    res = []
+    for _ in range(2):
+        for p in m.parameters():
+            p.grad = None
+        xg = x.clone().requires_grad_(True)
+        (m(xg[None])[0, :, 0] * g_out).sum().backward()
+        res.append([xg.grad.clone()] + [p.grad.clone() for p in m.parameters()])
+    for a, b in zip(*res):
+        assert torch.equal(a, b)
+
+
+def test_training_deeper_than_three_layers_is_refused():
+    m = FusedShadowModule(_cfg(5)).to(DEV)
+    with pytest.raises(NotImplementedError):
+        m(_normals(1000, 0.5, seed=1).to(DEV)[None])                  # parameters require grad -> a backward would follow
+    with torch.no_grad():
+        assert m(_normals(1000, 0.5, seed=1).to(DEV)[None]).shape == (1, 1000, 1)
 
 
 def test_capacity_overflow_regrows_when_strict_and_is_flagged_otherwise():

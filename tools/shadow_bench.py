@@ -77,7 +77,13 @@ def main():
     for k in ("shadow_compact", "shadow_mlp_fwd"):
         if k in prof:
             res[k + "_ms"] = prof[k][0] / prof[k][1]
+    _lib.profile_enable(True)
     res["fused_fwd_bwd_ms"] = timed(lambda: fwd_bwd(fused), args.iters, flush)
+    prof = _lib.profile_read()
+    _lib.profile_enable(False)
+    for k in ("shadow_mlp_fwd", "shadow_mlp_bwd_data", "shadow_mlp_bwd_weights"):
+        if k in prof:
+            res["train_" + k + "_ms"] = prof[k][0] / prof[k][1]
     fused.strict = True
     fused.check_status()
     res["torch_fwd_ms"] = timed(lambda: fwd(ref), args.iters, flush)
