@@ -56,6 +56,10 @@ def parse():
     ap.add_argument("--no-cuda-graph", dest="cuda_graph", action="store_false",
                     help="default: zero_grad + forward + losses + backward are captured once per input buffer set in a CUDA graph "
                          "and replayed (all-reduce and the Adam launch stay eager): +5 %% at 8 frames/step, +50 %% at 1 (launch-bound)")
+    ap.add_argument("--full-model", action="store_true",
+                    help="NOT the headline metric: the whole reference-shaped step of exps/zju-mocap_377.yaml — pose-refinement and "
+                         "non-rigid MLPs, mesh normal map + soft silhouette (csrc/mesh_raster.cu), tcgen05 shadow MLP "
+                         "(csrc/shadow_mlp.cu), rgb = albedo * shading, and the Laplacian / normal / colour regularisers")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-frames", type=int, default=2, help="frames in the bounded CPU-baseline sample")
     return ap.parse_args()
@@ -151,7 +155,31 @@ class Trainer:
         H = W = args.img
         scene = S.make_humanoid(args.faces, seed=0)
         self.scene = scene
-        self.model = Model(default_model_cfg(img_size=(W, H)), scene.canonical_info(), strict_raster=False).to(device)
+        if args.full_model:           # the module nodes of reference exps/zju-mocap_377.yaml:63-98, all active (kick_in_iter 0)
+            cfg = {"img_size": [W, H], "eval_mode": False,
+                   "canonical_geometry": {"sigma": 1e-3, "radius_scale": 1.0, "deform_scale": True, "deform_so3": True},
+                   "appearance": {"color_init": 0.5},
+                   "non_rigid": {"name": "basic", "condition_code_size": 69, "mlp_width": 128, "mlp_depth": 6, "skips": [4],
+                                 "multires": 6, "i_embed": 0, "kick_in_iter": 0, "full_band_iter": 50000},
+                   "pose_refinement": {"name": "basic", "embedding_size": 69, "total_bones": 24, "mlp_width": 256, "mlp_depth": 4,
+                                       "refine_root": False, "refine_t": False, "kick_in_iter": 0},
+                   "normal_renderer": {"name": "mesh", "soft_mask": True, "sigma": 1e-5},
+                   "shadow_module": {"name": "basic", "mlp_width": 128, "mlp_depth": 3, "skips": [4], "multires": 6, "i_embed": 0}}
+            self.loss_cfg = {"rgb": {"coeff": 1.0}, "mask": {"coeff": 5.0}, "lpips": {"coeff": 1.0},       # configs/default.yaml:101-121
+                             "laplacian": {"coeff_canonical": 0.0, "coeff_observation": 10.0},             # + exps/zju-mocap_377.yaml:101-112
+                             "normal": {"mask_dilate": True, "kernel_size": 7, "coeff_mask": 1.0, "coeff_consist": 0.10},
+                             "color_consist": {"coeff": 0.050}}
+            self.model = Model(cfg, scene.canonical_info(), strict_raster=False).to(device)
+            self.model.normal_renderer.strict = False             # overflow flags stay on the device (graph capture)
+            self.model.normal_renderer.capacity = 16 * args.faces
+            self.model.shadow_module.strict = False
+            with torch.no_grad():                                 # the reference's 1e-5 last layers would make the MLPs invisible
+                g = torch.Generator(device="cpu").manual_seed(5)
+                self.model.shadow_module.block_mlps[-1].weight.copy_(torch.randn(1, 128, generator=g) * 0.15)
+                self.model.non_rigid_module.block_mlps[-1].weight.copy_(torch.randn(3, 128, generator=g) * 2e-4)
+                self.model.pose_refinement_module.block_mlps[-1].weight.copy_(torch.randn(69, 256, generator=g) * 2e-3)
+        else:
+            self.model = Model(default_model_cfg(img_size=(W, H)), scene.canonical_info(), strict_raster=False).to(device)
         pr = S.make_params(scene, seed=1)
         with torch.no_grad():
             self.model.so3.copy_(torch.from_numpy(pr["so3"]))
@@ -172,7 +200,8 @@ class Trainer:
         self.arena = FlatArena(self.model)
         self.arena.broadcast_params()
         groups = self.model.get_param_groups(type("C", (), {"lr": {"appearance": 5e-4, "canonical_geometry": 5e-4,
-                                                                "canonical_geometry_xyz": 5e-4}})())
+                                                                "canonical_geometry_xyz": 5e-4, "non_rigid": 5e-4,
+                                                                "pose_refinement": 5e-5, "shadow": 5e-4}})())
         from gomavatar_b200.dist import ArenaAdam
         self.opt = ArenaAdam(self.arena, groups)            # one launch over the flat arena (csrc/adam.cu)
         self.h2d_bytes = sum(v[: self.B].numel() * v.element_size() for v in self.host.values()) + \
@@ -199,9 +228,13 @@ class Trainer:
     def _fwd_bwd(self, d, tgt_rgb, tgt_mask):
         from gomavatar_b200.losses import compute_loss
         self.arena.zero_grad()
-        rgb, mask, _ = self.model(d["K"], d["E"], d["cnl_gtfms"], d["dst_Rs"], d["dst_Ts"], dst_posevec=d["dst_posevec"],
-                                  bgcolor=d["bgcolor"])
-        loss, terms, _ = compute_loss(rgb, mask, d["bgcolor"], tgt_rgb, tgt_mask, lpips_func=self.lpips)
+        rgb, mask, outputs = self.model(d["K"], d["E"], d["cnl_gtfms"], d["dst_Rs"], d["dst_Ts"], dst_posevec=d["dst_posevec"],
+                                        bgcolor=d["bgcolor"])
+        if self.args.full_model:
+            from gomavatar_b200.regularizers import compute_loss as full_loss
+            loss, _ = full_loss(rgb, mask, d["bgcolor"], tgt_rgb, tgt_mask, outputs, self.model, self.loss_cfg, lpips_func=self.lpips)
+        else:
+            loss, terms, _ = compute_loss(rgb, mask, d["bgcolor"], tgt_rgb, tgt_mask, lpips_func=self.lpips)
         loss.backward()
         return loss.detach()
 
@@ -412,7 +445,8 @@ def run_b200(args):
         kernels[name] = {"ms_per_step": ms_step, "launches_per_step": per_step, "ms_per_launch": tot_ms / max(n, 1),
                          "share_of_step": ms_step / (ms_prof / K), "alg_bytes_per_launch": byt_step / max(per_step, 1e-9),
                          "gbs": byt_step / (ms_step * 1e-3) / 1e9 if ms_step > 0 else None}
-    dom = max(kernels, key=lambda k: kernels[k]["ms_per_step"]) if kernels else None
+    hbm_kernels = [k for k in kernels if alg_bytes_per_frame.get(k, 0.0) > 0]
+    dom = max(hbm_kernels, key=lambda k: kernels[k]["ms_per_step"]) if hbm_kernels else None
     roofline = None
     if dom:
         k = kernels[dom]
@@ -423,17 +457,33 @@ def run_b200(args):
                     "blend_pass": {kk: {"gbs": kernels[kk]["gbs"], "frac": kernels[kk]["gbs"] / peak, "ms_per_launch": kernels[kk]["ms_per_launch"]}
                                    for kk in ("sort_blend_fwd", "blend_bwd") if kk in kernels}}
 
+    if args.full_model and roofline is not None and "shadow_mlp_fwd" in kernels:
+        sm = tr.model.shadow_module
+        n_fg = int(sm._ws["n_fg"].item())
+        flops = 2.0 * n_fg * (39 * 128 + 2 * 128 * 128 + 128)           # one pass over the MLP (fp32-equivalent FLOPs)
+        tpeak = float(peaks.get("bf16_tflops_sustained", 1400.0)) / 2.0     # TF32 = half the bf16 tensor rate
+        roofline["shadow_mlp"] = {"bound": "tensor", "unit": "TFLOP/s", "peak": tpeak, "n_fg_per_step": n_fg,
+                                  "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained / 2 (TF32)",
+                                  "note": "achieved = algorithmic fp32-equivalent FLOPs / time; every product is issued as 3 TF32 MMAs"}
+        for kk, mult in (("shadow_mlp_fwd", 1.0), ("shadow_mlp_bwd_data", 1.0), ("shadow_mlp_bwd_weights", 1.0)):
+            if kk in kernels:
+                ach = flops * mult / (kernels[kk]["ms_per_launch"] * 1e-3) / 1e12
+                roofline["shadow_mlp"][kk] = {"achieved": ach, "frac": ach / tpeak, "frac_issued": 3 * ach / tpeak,
+                                              "ms_per_launch": kernels[kk]["ms_per_launch"]}
     line = None
     if rank == 0:
         value = frames_total / (ms * 1e-3)
         e2e_value = frames_total / (ms_e2e * 1e-3)
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": max(W_, 3),
+            "metric": ("full_model_" + METRIC) if args.full_model else METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": max(W_, 3),
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (all hand-written kernels fp32; LPIPS VGG convs in cuDNN at %s)" % args.lpips_precision,
             "data": "synthetic (seeded SMPL-topology humanoid, poses, ZJU-like cameras; LPIPS trunk = seeded random VGG16, "
                     "no ImageNet weights offline)",
-            "config": {"workload": "ZJU-MoCap-377-like train step (LBS+face frame+splat raster+L1/LPIPS losses+backward+Adam), "
-                                   "512x512, 30k Gaussians (BASELINE configs[2])",
+            "config": {"workload": ("FULL reference-shaped train step of exps/zju-mocap_377.yaml (hot path + pose-refinement / non-rigid "
+                                    "MLPs + mesh normal map + tcgen05 shadow MLP + Laplacian / normal / colour regularisers + Adam), "
+                                    "512x512, 30k Gaussians" if args.full_model else
+                                    "ZJU-MoCap-377-like train step (LBS+face frame+splat raster+L1/LPIPS losses+backward+Adam), "
+                                    "512x512, 30k Gaussians (BASELINE configs[2])"),
                        "img": args.img, "n_gaussians": F, "n_vertices": V, "frames_per_step_per_gpu": B,
                        "global_batch": B * world, "parallelism": f"frame-sharded dp{world}, 1 NCCL all-reduce of the flat grad arena/step",
                        "lpips_conv_precision": args.lpips_precision + (" (cuDNN default; the reference never disables TF32)" if args.lpips_precision == "tf32" else ""), "raster_overflow": overflow,
@@ -444,7 +494,7 @@ def run_b200(args):
                     "d2h_bytes_per_step": 4},
             "gpu_launches": launches_timed, "clocks": clocks, "roofline": roofline, "kernels": kernels,
         }
-        if not args.no_cpu_baseline and world == 1:
+        if not args.no_cpu_baseline and world == 1 and not args.full_model:
             line["cpu_baseline"] = cpu_path(args, n_frames=args.cpu_frames, gpu_trainer=tr)
         emit(line)
     if world > 1:

@@ -9,9 +9,10 @@
 //   * faces are binned to 16x16-pixel tiles by their blur-padded bounding boxes (count -> scan -> emit, no host sync,
 //     fixed capacity + overflow flag exactly like the splat rasterizer), so a pixel only meets the faces of its tile;
 //   * ONE pass renders the hard result (nearest inside face -> pix_to_face, summed vertex normals) and the soft
-//     silhouette alpha = 1 - prod(1 - sigmoid(-d/1e-4)); no K = 50 queue is materialised: the product does not depend
-//     on order, and only a pixel with MORE than K candidates (rare) takes the exact slow path that selects its K
-//     nearest by (z, face id) and records the cut for the backward;
+//     silhouette alpha = 1 - prod(1 - sigmoid(-d/1e-4)).  The product does not depend on order, so a pixel with at most
+//     K candidates needs no queue; beyond K (common at 30 k faces: the 2.4-pixel blur disc meets ~15 faces per surface
+//     layer) the K nearest by (z, face id) are tracked in a thread-local queue (replace-the-maximum, O(K) per
+//     replacement) and the cut is recorded for the backward;
 //   * backward: d alpha / d d_k = -(1 - alpha) p_k / sigma (the (1 - p_k) factor cancels), chained through the
 //     squared point-segment distance to the two vertices of the nearest edge; normal-map gradient scattered to the
 //     hit face's three vertex normals.  A batch of B frames per launch.
@@ -22,6 +23,7 @@
 namespace {
 
 constexpr int kThreads = 256;
+constexpr int kMaxK = 64;                  // thread-local K-nearest queue of the soft silhouette (reference: K = 50)
 constexpr float kEpsArea = 1e-8f;          // PyTorch3D kEpsilon
 constexpr float kBlendSigma = 1e-4f;       // BlendParams().sigma (SoftSilhouetteShader default, mesh.py:107-112)
 
@@ -214,6 +216,12 @@ __global__ void __launch_bounds__(kThreads) k_mesh_raster_fwd(MeshDev a) {
 
     float best_z = INFINITY; int best_f = -1;
     float prod = 1.f; int cand = 0;
+    // the K candidates of smallest (z, face id) seen so far (thread-local arrays: local memory, L1-resident) and the
+    // largest of them (mz, mf at slot mi); only consulted once a pixel has more than K candidates
+    float hz[kMaxK], hp[kMaxK]; int hf[kMaxK];
+    float mz = -INFINITY; int mf = -1, mi = 0;
+    const int K = a.K;
+    const bool keep = a.soft && K <= kMaxK;
     for (int base = 0; base < n; base += kThreads) {
         __syncthreads();
         if (base + tid < n) {
@@ -228,10 +236,22 @@ __global__ void __launch_bounds__(kThreads) k_mesh_raster_fwd(MeshDev a) {
         for (int j = 0; j < m; j++) {
             float pz, dist, tt; bool inside, deg; int edge;
             if (!pixel_face(s_rec[j], px, py, a.blur, br, pz, inside, dist, edge, tt, deg)) continue;
-            if (inside && zid_less(pz, s_fid[j], best_z, best_f < 0 ? 0x7fffffff : best_f)) { best_z = pz; best_f = s_fid[j]; }
+            const int f = s_fid[j];
+            if (inside && zid_less(pz, f, best_z, best_f < 0 ? 0x7fffffff : best_f)) { best_z = pz; best_f = f; }
             if (a.soft) {
                 const float p = 1.f / (1.f + __expf((inside ? -dist : dist) / kBlendSigma));     // sigmoid(-d / sigma)
                 prod *= 1.f - p;
+                if (keep) {
+                    if (cand < K) {
+                        hz[cand] = pz; hf[cand] = f; hp[cand] = p;
+                        if (zid_less(mz, mf, pz, f)) { mz = pz; mf = f; mi = cand; }
+                    } else if (zid_less(pz, f, mz, mf)) {                       // replaces the current K-th nearest
+                        hz[mi] = pz; hf[mi] = f; hp[mi] = p;
+                        mz = hz[0]; mf = hf[0]; mi = 0;
+                        for (int i = 1; i < K; i++)
+                            if (zid_less(mz, mf, hz[i], hf[i])) { mz = hz[i]; mf = hf[i]; mi = i; }
+                    }
+                }
                 cand++;
             }
         }
@@ -250,13 +270,19 @@ __global__ void __launch_bounds__(kThreads) k_mesh_raster_fwd(MeshDev a) {
     a.normal[3 * pix] = nx; a.normal[3 * pix + 1] = ny; a.normal[3 * pix + 2] = nz;
     if (!a.soft) return;
     float zc = INFINITY; int ic = 0x7fffffff;
-    if (cand > a.K) {
-        // exact slow path: keep the K candidates of smallest (z, id); walk the list K times, each time taking the
-        // smallest key above the previous one
+    if (cand > K && keep) {
+        // more than K candidates: the silhouette is the product over the K nearest only (PyTorch3D's per-pixel queue);
+        // the cut (z, id) of the K-th nearest is recorded for the backward
+        prod = 1.f;
+        for (int i = 0; i < K; i++) prod *= 1.f - hp[i];
+        zc = mz; ic = mf;
+    } else if (cand > K) {
+        // K beyond the thread-local queue: exact selection by K passes over the list, each taking the smallest key
+        // above the previous one
         float lz = -INFINITY; int lf = -1;
         prod = 1.f;
-        for (int k = 0; k < a.K; k++) {
-            float mz = INFINITY; int mf = 0x7fffffff; float mp = 0.f;
+        for (int k = 0; k < K; k++) {
+            float sz = INFINITY; int sf = 0x7fffffff; float sp = 0.f;
             for (int i = 0; i < n; i++) {
                 int3 id;
                 const int f = (int)list[i];
@@ -264,10 +290,10 @@ __global__ void __launch_bounds__(kThreads) k_mesh_raster_fwd(MeshDev a) {
                 float pz, dist, tt; bool inside, deg; int edge;
                 if (!pixel_face(r, px, py, a.blur, br, pz, inside, dist, edge, tt, deg)) continue;
                 if (!zid_less(lz, lf, pz, f)) continue;                       // already taken
-                if (zid_less(pz, f, mz, mf)) { mz = pz; mf = f; mp = 1.f / (1.f + __expf((inside ? -dist : dist) / kBlendSigma)); }
+                if (zid_less(pz, f, sz, sf)) { sz = pz; sf = f; sp = 1.f / (1.f + __expf((inside ? -dist : dist) / kBlendSigma)); }
             }
-            prod *= 1.f - mp;
-            lz = mz; lf = mf;
+            prod *= 1.f - sp;
+            lz = sz; lf = sf;
         }
         zc = lz; ic = lf;
     }

@@ -690,16 +690,18 @@ __global__ void __launch_bounds__(kThreads, 1) k_shadow_bwd_data(ShadowDev a) {
             for (int st = 0; st < depth; st++, g++) {
                 const bool last = (st == depth - 1);
                 const uint32_t dcol = tl + kColD + (g & 1u) * kWidth;
+                const int slot = depth - 1 - st;                        // (not last) the product is dL/dH_slot
+                uint32_t m[32];
+                if (!last) load_mask(tile, slot, 0, m);                 // in flight while the MMAs of this step run
                 if (!mbar_wait(&z_ready, g & 1u, ab)) { ok = false; break; }
                 tc_fence_after();
                 if (!last) {
-                    const int slot = depth - 1 - st;                    // the product is dL/dH_slot
 #pragma unroll 1
                     for (int fb = 0; fb < 4; fb++) {
-                        uint32_t z[32], m[32];
+                        uint32_t z[32], mn[32];
                         float v[32];
-                        load_mask(tile, slot, fb, m);
                         tmem_ld32(dcol + fb * 32, z);
+                        if (fb < 3) load_mask(tile, slot, fb + 1, mn);  // next block's mask behind this block's work
                         tmem_wait_ld();
 #pragma unroll
                         for (int j = 0; j < 32; j++) v[j] = (__uint_as_float(m[j]) > 0.f) ? __uint_as_float(z[j]) : 0.f;
@@ -707,6 +709,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_shadow_bwd_data(ShadowDev a) {
                         tmem_wait_st();
                         tc_fence_before();
                         mbar_arrive(&a_ready[fb]);
+#pragma unroll
+                        for (int j = 0; j < 32; j++) m[j] = mn[j];
                     }
                 } else {
                     if (tile_n < n_tiles) publish_first(tile_n, dzo_n);     // A is free: start the next tile

@@ -37,7 +37,7 @@ def ndc_T_world(xyzs_world, K, E, H, W):
 def vertex_normals(verts_bv3, faces):
     """PyTorch3D ``Meshes.verts_normals_padded``: area-weighted face normals accumulated on the vertices, eps 1e-6."""
     f = faces.long()
-    v0, v1, v2 = verts_bv3[:, f[:, 0]], verts_bv3[:, f[:, 1]], verts_bv3[:, f[:, 2]]
+    v0, v1, v2 = (verts_bv3.index_select(1, f[:, k]) for k in range(3))      # backward = index_add, no sort
     n = torch.zeros_like(verts_bv3)
     n = n.index_add(1, f[:, 1], torch.cross(v2 - v1, v0 - v1, dim=-1))
     n = n.index_add(1, f[:, 2], torch.cross(v0 - v2, v1 - v2, dim=-1))
@@ -51,7 +51,7 @@ def default_list_capacity(n_faces):
 
 class _MeshRaster(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, verts_ndc, vert_normals, faces, H, W, soft, blur_radius, faces_per_pixel, capacity, aux):
+    def forward(ctx, verts_ndc, vert_normals, faces, H, W, soft, blur_radius, faces_per_pixel, capacity, aux, strict=True):
         if verts_ndc.device.type != "cuda":
             raise _lib.GomError("mesh renderer: inputs must live on a CUDA device (no CPU path exists)")
         B, V, _ = verts_ndc.shape
@@ -75,6 +75,8 @@ class _MeshRaster(torch.autograd.Function):
                                   list_capacity=cap, verts_ndc=ptr(vn), faces=ptr(fc), vert_normals=ptr(nn_),
                                   **{k: ptr(v) for k, v in st.items()})
             call("gom_mesh_raster_forward", a)
+            if not strict or torch.cuda.is_current_stream_capturing():      # no host sync: overflow stays a device flag in aux["status"]
+                break
             if int(st["status"].max().item()) & _lib.STATUS_OVERFLOW:       # binning lists too small: regrow, like the splat path
                 need = int(st["tile_offset"][:, T].to(torch.int64).bitwise_and(0xFFFFFFFF).max().item())
                 cap = int(need * 1.25) + 1024
@@ -110,15 +112,15 @@ class _MeshRaster(torch.autograd.Function):
                               normal_map=ptr(nmap), alpha=ptr(alpha), zcut=ptr(zcut), idcut=ptr(idcut), dL_dnormal_map=ptr(gn),
                               dL_dalpha=ptr(ga), dL_dverts_ndc=ptr(d_verts), dL_dvert_normals=ptr(d_vn))
         call("gom_mesh_raster_backward", a)
-        return d_verts, d_vn, None, None, None, None, None, None, None, None
+        return d_verts, d_vn, None, None, None, None, None, None, None, None, None
 
 
 def rasterize_mesh(verts_ndc, vert_normals, faces, image_height, image_width, soft=False, blur_radius=0.0,
-                   faces_per_pixel=50, capacity=None, aux=None):
+                   faces_per_pixel=50, capacity=None, aux=None, strict=True):
     """verts_ndc [B,V,3], vert_normals [B,V,3], faces [F,3] -> (normal_map [B,H,W,3] with 0 on the background,
     alpha [B,H,W] (empty unless soft), pix_to_face [B,H,W] int32)."""
     return _MeshRaster.apply(verts_ndc, vert_normals, faces, int(image_height), int(image_width), bool(soft),
-                             float(blur_radius), int(faces_per_pixel), capacity, aux)
+                             float(blur_radius), int(faces_per_pixel), capacity, aux, bool(strict))
 
 
 class Renderer(nn.Module):
@@ -133,6 +135,7 @@ class Renderer(nn.Module):
         self.sigma = float(sigma if sigma is not None else get("sigma", 1e-4))
         self.blur_radius = math.log(1. / 1e-4 - 1.) * self.sigma
         self.faces_per_pixel = int(faces_per_pixel)
+        self.strict, self.capacity = True, None      # strict=False: never read the overflow flag back (CUDA-graph capture)
         self.last_aux = None
 
     def forward(self, xyzs_observation, vertex_normals, K, E, faces, **kwargs):
@@ -144,7 +147,7 @@ class Renderer(nn.Module):
             vn = vn.expand(B, -1, -1)
         aux = {}
         normal, alpha, _ = rasterize_mesh(xyzs_ndc, vn, faces, H, W, soft=self.training, blur_radius=self.blur_radius,
-                                          faces_per_pixel=self.faces_per_pixel, aux=aux)
+                                          faces_per_pixel=self.faces_per_pixel, aux=aux, capacity=self.capacity, strict=self.strict)
         self.last_aux = aux
         if not self.training:
             return normal, None

@@ -74,11 +74,12 @@ def posenc(x, multires, include_input=True, window=None):
     return torch.cat([x, sc], dim=-1) if include_input else sc
 
 
-def hann_window(multires, i_iter, kick_in_iter, full_band_iter):
-    """reference non_rigid_module.py:33-43: w_k = (1 - cos(pi clamp(alpha - k, 0, 1))) / 2, alpha = m t / N."""
+def hann_window(multires, i_iter, kick_in_iter, full_band_iter, device=None):
+    """reference non_rigid_module.py:33-43: w_k = (1 - cos(pi clamp(alpha - k, 0, 1))) / 2, alpha = m t / N.  Built on
+    `device` from Python scalars only (no host-to-device tensor copy: the step stays CUDA-graph capturable)."""
     t = max(float(i_iter) - float(kick_in_iter), 0.0)
     alpha = multires * t / (float(full_band_iter) - float(kick_in_iter))
-    k = torch.arange(multires, dtype=torch.float32)
+    k = torch.arange(multires, dtype=torch.float32, device=device)
     return (1.0 - torch.cos(math.pi * torch.clamp(alpha - k, min=0.0, max=1.0))) / 2.0
 
 
@@ -118,7 +119,7 @@ class NonRigidModule(nn.Module):
             xyzs = xyzs.expand(dst_posevec.shape[0], -1, -1)
             B = dst_posevec.shape[0]
         enc = posenc(xyzs, self.multires, include_input=False,
-                     window=hann_window(self.multires, i_iter, self.kick_in_iter, self.full_band_iter))
+                     window=hann_window(self.multires, i_iter, self.kick_in_iter, self.full_band_iter, device=xyzs.device))
         h = torch.cat([dst_posevec[:, None, :].expand(B, N, -1), enc], dim=-1)
         offset = _run(self.block_mlps, self.layers_to_cat_inputs, h, enc)
         return xyzs_skeleton + offset.permute(0, 2, 1), R, S

@@ -32,33 +32,41 @@ def laplacian_smoothing(verts, faces, edges=None):
     """verts [V,3] -> scalar."""
     V = verts.shape[0]
     e = unique_edges(faces, V) if edges is None else edges
-    nbr = torch.zeros_like(verts).index_add(0, e[:, 0], verts[e[:, 1]]).index_add(0, e[:, 1], verts[e[:, 0]])
+    # index_select (backward = atomic index_add) instead of advanced indexing (backward = a radix sort per gather)
+    nbr = torch.zeros_like(verts).index_add(0, e[:, 0], verts.index_select(0, e[:, 1])).index_add(0, e[:, 1], verts.index_select(0, e[:, 0]))
     deg = torch.zeros(V, dtype=verts.dtype, device=verts.device).index_add(
         0, e.reshape(-1), torch.ones(e.numel(), dtype=verts.dtype, device=verts.device))
     lv = torch.where(deg[:, None] > 0, nbr / deg.clamp(min=1)[:, None] - verts, torch.zeros_like(verts))
     return (lv.norm(dim=1) ** 2).mean()
 
 
-def normal_consistency(verts, faces, face_connectivity):
-    """face_connectivity [P,2]: pairs of faces sharing an edge (``Model.face_connectivity``)."""
+def normal_consistency_indices(faces, face_connectivity):
+    """(v0, v1, other_a, other_b) per pair of faces sharing an edge: the shared edge in a fixed order (smaller vertex index
+    first, as PyTorch3D's edges_packed stores it) and the one unshared vertex of each face.  Topology only: cacheable."""
     f = faces.long()
     fa, fb = f[face_connectivity[:, 0]], f[face_connectivity[:, 1]]                     # [P,3] each
     shared = (fa[:, :, None] == fb[:, None, :]).any(dim=2)                              # which corners of fa are shared
     other_a = (fa * (~shared)).sum(dim=1)                                               # the one unshared vertex of each face
     shared_b = (fb[:, :, None] == fa[:, None, :]).any(dim=2)
     other_b = (fb * (~shared_b)).sum(dim=1)
-    # the shared edge, in a fixed order (smaller vertex index first), as PyTorch3D's edges_packed stores it
     big = torch.iinfo(torch.int64).max
     v0 = torch.where(shared, fa, torch.full_like(fa, big)).min(dim=1).values
     v1 = torch.where(shared, fa, torch.full_like(fa, -1)).max(dim=1).values
-    e = verts[v1] - verts[v0]
-    n0 = torch.cross(e, verts[other_a] - verts[v0], dim=1)
-    n1 = -torch.cross(e, verts[other_b] - verts[v0], dim=1)
+    return v0, v1, other_a, other_b
+
+
+def normal_consistency(verts, faces, face_connectivity, indices=None):
+    """face_connectivity [P,2]: pairs of faces sharing an edge (``Model.face_connectivity``)."""
+    v0, v1, other_a, other_b = indices if indices is not None else normal_consistency_indices(faces, face_connectivity)
+    p0 = verts.index_select(0, v0)
+    e = verts.index_select(0, v1) - p0
+    n0 = torch.cross(e, verts.index_select(0, other_a) - p0, dim=1)
+    n1 = -torch.cross(e, verts.index_select(0, other_b) - p0, dim=1)
     return (1.0 - F.cosine_similarity(n0, n1, dim=1)).mean()
 
 
 def color_consistency(color, face_connectivity):
-    return (color[face_connectivity[:, 0]] - color[face_connectivity[:, 1]]).abs().mean()
+    return (color.index_select(0, face_connectivity[:, 0]) - color.index_select(0, face_connectivity[:, 1])).abs().mean()
 
 
 def normal_mask_loss(normal_mask, mask_gt, kernel_size=7, dilate=True):
@@ -92,18 +100,25 @@ def compute_loss(rgbs, masks, bgcolors, rgb_gt, mask_gt, outputs, model, loss_cf
         total = total + value * coeff
 
     faces = model.faces
+    edges = getattr(model, "_unique_edges", None)                  # topology is fixed between subdivisions: computed once
+    if edges is None or edges.device != faces.device or getattr(model, "_unique_edges_faces", None) is not faces:
+        edges = unique_edges(faces, model.vertices.shape[1])       # (torch.unique syncs: keep it out of the steady-state step)
+        model._unique_edges, model._unique_edges_faces = edges, faces
     if _c(loss_cfg, "laplacian.coeff_canonical") > 0:
-        add("laplacian_canonical", laplacian_smoothing(model.vertices.T, faces), _c(loss_cfg, "laplacian.coeff_canonical"))
+        add("laplacian_canonical", laplacian_smoothing(model.vertices.T, faces, edges), _c(loss_cfg, "laplacian.coeff_canonical"))
     if _c(loss_cfg, "laplacian.coeff_observation") > 0:
         vo = outputs["vertices_observation"]                       # [B,3,V]; the reference is batch 1
-        lap = torch.stack([laplacian_smoothing(v.T, faces) for v in vo]).mean()
+        lap = torch.stack([laplacian_smoothing(v.T, faces, edges) for v in vo]).mean()
         add("laplacian_observation", lap, _c(loss_cfg, "laplacian.coeff_observation"))
     if _c(loss_cfg, "normal.coeff_mask") > 0 and outputs.get("normal_mask") is not None:
         add("normal_mask", normal_mask_loss(outputs["normal_mask"], mask_gt, int(_c(loss_cfg, "normal.kernel_size", 7)),
                                             bool(_c(loss_cfg, "normal.mask_dilate", True))), _c(loss_cfg, "normal.coeff_mask"))
     if _c(loss_cfg, "normal.coeff_consist") > 0:
         vo = outputs["vertices_observation"]
-        nc = torch.stack([normal_consistency(v.T, faces, outputs["face_connectivity"]) for v in vo]).mean()
+        conn = outputs["face_connectivity"]
+        if getattr(model, "_nc_indices_key", None) is not conn:            # topology only: once per (sub)division
+            model._nc_indices, model._nc_indices_key = normal_consistency_indices(faces, conn), conn
+        nc = torch.stack([normal_consistency(v.T, faces, conn, model._nc_indices) for v in vo]).mean()
         add("normal_consist", nc, _c(loss_cfg, "normal.coeff_consist"))
     if _c(loss_cfg, "color_consist.coeff") > 0:
         add("color_consist", color_consistency(outputs["colors"], outputs["face_connectivity"]), _c(loss_cfg, "color_consist.coeff"))
