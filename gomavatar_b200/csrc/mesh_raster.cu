@@ -11,8 +11,8 @@
 //   * ONE pass renders the hard result (nearest inside face -> pix_to_face, summed vertex normals) and the soft
 //     silhouette alpha = 1 - prod(1 - sigmoid(-d/1e-4)).  The product does not depend on order, so a pixel with at most
 //     K candidates needs no queue; beyond K (common at 30 k faces: the 2.4-pixel blur disc meets ~15 faces per surface
-//     layer) the K nearest by (z, face id) are tracked in a thread-local queue (replace-the-maximum, O(K) per
-//     replacement) and the cut is recorded for the backward;
+//     layer) the K nearest by (z, face id) are tracked in a thread-local queue (replace-the-maximum with per-group
+//     maxima: ~15 comparisons per replacement) and the cut is recorded for the backward;
 //   * backward: d alpha / d d_k = -(1 - alpha) p_k / sigma (the (1 - p_k) factor cancels), chained through the
 //     squared point-segment distance to the two vertices of the nearest edge; normal-map gradient scattered to the
 //     hit face's three vertex normals.  A batch of B frames per launch.
@@ -219,6 +219,7 @@ __global__ void __launch_bounds__(kThreads) k_mesh_raster_fwd(MeshDev a) {
     // the K candidates of smallest (z, face id) seen so far (thread-local arrays: local memory, L1-resident) and the
     // largest of them (mz, mf at slot mi); only consulted once a pixel has more than K candidates
     float hz[kMaxK], hp[kMaxK]; int hf[kMaxK];
+    float gz[kMaxK / 8]; int gf[kMaxK / 8], gi[kMaxK / 8];       // per group of 8 slots: its largest key and where it sits
     float mz = -INFINITY; int mf = -1, mi = 0;
     const int K = a.K;
     const bool keep = a.soft && K <= kMaxK;
@@ -244,12 +245,19 @@ __global__ void __launch_bounds__(kThreads) k_mesh_raster_fwd(MeshDev a) {
                 if (keep) {
                     if (cand < K) {
                         hz[cand] = pz; hf[cand] = f; hp[cand] = p;
+                        const int g = cand >> 3;
+                        if ((cand & 7) == 0 || zid_less(gz[g], gf[g], pz, f)) { gz[g] = pz; gf[g] = f; gi[g] = cand; }
                         if (zid_less(mz, mf, pz, f)) { mz = pz; mf = f; mi = cand; }
                     } else if (zid_less(pz, f, mz, mf)) {                       // replaces the current K-th nearest
                         hz[mi] = pz; hf[mi] = f; hp[mi] = p;
-                        mz = hz[0]; mf = hf[0]; mi = 0;
-                        for (int i = 1; i < K; i++)
-                            if (zid_less(mz, mf, hz[i], hf[i])) { mz = hz[i]; mf = hf[i]; mi = i; }
+                        const int g = mi >> 3, lo = g << 3, hi = min(lo + 8, K);
+                        float tz = hz[lo]; int tf = hf[lo], ti = lo;            // new maximum of the touched group ...
+                        for (int i = lo + 1; i < hi; i++)
+                            if (zid_less(tz, tf, hz[i], hf[i])) { tz = hz[i]; tf = hf[i]; ti = i; }
+                        gz[g] = tz; gf[g] = tf; gi[g] = ti;
+                        mz = gz[0]; mf = gf[0]; mi = gi[0];                     // ... then of the group maxima
+                        for (int gg = 1; gg < ((K + 7) >> 3); gg++)
+                            if (zid_less(mz, mf, gz[gg], gf[gg])) { mz = gz[gg]; mf = gf[gg]; mi = gi[gg]; }
                     }
                 }
                 cand++;
