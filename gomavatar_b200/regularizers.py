@@ -28,16 +28,23 @@ def unique_edges(faces, n_verts):
     return torch.stack([key // n_verts, key % n_verts], dim=1)
 
 
-def laplacian_smoothing(verts, faces, edges=None):
-    """verts [V,3] -> scalar."""
-    V = verts.shape[0]
+def laplacian_smoothing(verts, faces, edges=None, degree=None):
+    """verts [V,3] -> scalar, or [B,V,3] -> scalar mean over the B meshes (one set of launches for the whole batch).
+    ``edges`` / ``degree`` (``vertex_degree``) are topology only and can be cached by the caller."""
+    batched = verts.dim() == 3
+    v = verts if batched else verts[None]
+    V = v.shape[1]
     e = unique_edges(faces, V) if edges is None else edges
+    deg = vertex_degree(e, V, v.dtype) if degree is None else degree
     # index_select (backward = atomic index_add) instead of advanced indexing (backward = a radix sort per gather)
-    nbr = torch.zeros_like(verts).index_add(0, e[:, 0], verts.index_select(0, e[:, 1])).index_add(0, e[:, 1], verts.index_select(0, e[:, 0]))
-    deg = torch.zeros(V, dtype=verts.dtype, device=verts.device).index_add(
-        0, e.reshape(-1), torch.ones(e.numel(), dtype=verts.dtype, device=verts.device))
-    lv = torch.where(deg[:, None] > 0, nbr / deg.clamp(min=1)[:, None] - verts, torch.zeros_like(verts))
-    return (lv.norm(dim=1) ** 2).mean()
+    nbr = torch.zeros_like(v).index_add(1, e[:, 0], v.index_select(1, e[:, 1])).index_add(1, e[:, 1], v.index_select(1, e[:, 0]))
+    lv = torch.where(deg[None, :, None] > 0, nbr / deg.clamp(min=1)[None, :, None] - v, torch.zeros_like(v))
+    return (lv.norm(dim=2) ** 2).mean()
+
+
+def vertex_degree(edges, n_verts, dtype=torch.float32):
+    return torch.zeros(n_verts, dtype=dtype, device=edges.device).index_add(
+        0, edges.reshape(-1), torch.ones(edges.numel(), dtype=dtype, device=edges.device))
 
 
 def normal_consistency_indices(faces, face_connectivity):
@@ -56,13 +63,15 @@ def normal_consistency_indices(faces, face_connectivity):
 
 
 def normal_consistency(verts, faces, face_connectivity, indices=None):
-    """face_connectivity [P,2]: pairs of faces sharing an edge (``Model.face_connectivity``)."""
+    """face_connectivity [P,2]: pairs of faces sharing an edge (``Model.face_connectivity``).  verts [V,3] or [B,V,3]
+    (mean over the B meshes: they share the topology, so it is the mean over all pairs of all meshes)."""
     v0, v1, other_a, other_b = indices if indices is not None else normal_consistency_indices(faces, face_connectivity)
-    p0 = verts.index_select(0, v0)
-    e = verts.index_select(0, v1) - p0
-    n0 = torch.cross(e, verts.index_select(0, other_a) - p0, dim=1)
-    n1 = -torch.cross(e, verts.index_select(0, other_b) - p0, dim=1)
-    return (1.0 - F.cosine_similarity(n0, n1, dim=1)).mean()
+    d = verts.dim() - 2
+    p0 = verts.index_select(d, v0)
+    e = verts.index_select(d, v1) - p0
+    n0 = torch.cross(e, verts.index_select(d, other_a) - p0, dim=-1)
+    n1 = -torch.cross(e, verts.index_select(d, other_b) - p0, dim=-1)
+    return (1.0 - F.cosine_similarity(n0, n1, dim=-1)).mean()
 
 
 def color_consistency(color, face_connectivity):
@@ -104,11 +113,13 @@ def compute_loss(rgbs, masks, bgcolors, rgb_gt, mask_gt, outputs, model, loss_cf
     if edges is None or edges.device != faces.device or getattr(model, "_unique_edges_faces", None) is not faces:
         edges = unique_edges(faces, model.vertices.shape[1])       # (torch.unique syncs: keep it out of the steady-state step)
         model._unique_edges, model._unique_edges_faces = edges, faces
+        model._vertex_degree = vertex_degree(edges, model.vertices.shape[1])
+    deg = model._vertex_degree
     if _c(loss_cfg, "laplacian.coeff_canonical") > 0:
-        add("laplacian_canonical", laplacian_smoothing(model.vertices.T, faces, edges), _c(loss_cfg, "laplacian.coeff_canonical"))
+        add("laplacian_canonical", laplacian_smoothing(model.vertices.T, faces, edges, deg), _c(loss_cfg, "laplacian.coeff_canonical"))
     if _c(loss_cfg, "laplacian.coeff_observation") > 0:
-        vo = outputs["vertices_observation"]                       # [B,3,V]; the reference is batch 1
-        lap = torch.stack([laplacian_smoothing(v.T, faces, edges) for v in vo]).mean()
+        vo = outputs["vertices_observation"]                       # [B,3,V]; the reference is batch 1: mean over the frames
+        lap = laplacian_smoothing(vo.permute(0, 2, 1), faces, edges, deg)
         add("laplacian_observation", lap, _c(loss_cfg, "laplacian.coeff_observation"))
     if _c(loss_cfg, "normal.coeff_mask") > 0 and outputs.get("normal_mask") is not None:
         add("normal_mask", normal_mask_loss(outputs["normal_mask"], mask_gt, int(_c(loss_cfg, "normal.kernel_size", 7)),
@@ -118,7 +129,7 @@ def compute_loss(rgbs, masks, bgcolors, rgb_gt, mask_gt, outputs, model, loss_cf
         conn = outputs["face_connectivity"]
         if getattr(model, "_nc_indices_key", None) is not conn:            # topology only: once per (sub)division
             model._nc_indices, model._nc_indices_key = normal_consistency_indices(faces, conn), conn
-        nc = torch.stack([normal_consistency(v.T, faces, conn, model._nc_indices) for v in vo]).mean()
+        nc = normal_consistency(vo.permute(0, 2, 1), faces, conn, model._nc_indices)
         add("normal_consist", nc, _c(loss_cfg, "normal.coeff_consist"))
     if _c(loss_cfg, "color_consist.coeff") > 0:
         add("color_consist", color_consistency(outputs["colors"], outputs["face_connectivity"]), _c(loss_cfg, "color_consist.coeff"))

@@ -32,6 +32,16 @@ def test_uniform_laplacian_matches_dense_matrix():
     assert torch.isfinite(vg.grad).all() and float(vg.grad.abs().max()) > 0
 
 
+def test_batched_regularisers_equal_the_mean_over_meshes():
+    sc, v, f, conn = _scene()
+    g = torch.Generator().manual_seed(5)
+    vb = torch.stack([v + 0.002 * torch.randn(v.shape, dtype=torch.float64, generator=g) for _ in range(3)])
+    lap = torch.stack([RG.laplacian_smoothing(x, f) for x in vb]).mean()
+    assert abs(float(RG.laplacian_smoothing(vb, f)) - float(lap)) < 1e-14
+    nc = torch.stack([RG.normal_consistency(x, f, conn) for x in vb]).mean()
+    assert abs(float(RG.normal_consistency(vb, f, conn)) - float(nc)) < 1e-14
+
+
 def test_normal_consistency_matches_face_normal_formulation():
     sc, v, f, conn = _scene()
     n = torch.cross(v[f[:, 1]] - v[f[:, 0]], v[f[:, 2]] - v[f[:, 0]], dim=1)     # consistently oriented closed mesh

@@ -23,6 +23,11 @@ def _cfg(depth=3, multires=6):
     return {"multires": multires, "mlp_width": 128, "mlp_depth": depth, "skips": [depth + 1]}
 
 
+@pytest.fixture(autouse=True)
+def _seed():
+    torch.manual_seed(1234)            # module construction draws its Xavier weights from the global generator
+
+
 def _trained_like(m, seed):
     """the reference initialises the last layer at 1e-5 (output == 0.5 everywhere): perturb the hidden layers and give
     the output layer weights that spread the pre-sigmoid value over a few units, so every layer matters"""
@@ -107,7 +112,8 @@ def test_backward_matches_oracle(n, fg_frac, depth):
     # bit (fp32 here, float64 in the oracle) and moves that ONE pixel's gradient by up to ~1e-2 of the maximum (seen: 1 unit
     # in 6e7 at the largest size, tools/shadow_debug.py).  Strict bound on all but 1e-4 of the pixels, loose bound on the rest.
     e_n = np.abs(xg.grad.detach().cpu().numpy().astype(np.float64) - r_n).max(axis=1)
-    assert (e_n > 1e-3 * np.abs(r_n).max()).mean() <= 1e-4 and e_n.max() <= 5e-2 * np.abs(r_n).max(), (e_n.max(), np.abs(r_n).max())
+    n_bad = int((e_n > 1e-3 * np.abs(r_n).max()).sum())
+    assert n_bad <= max(2, 1e-4 * n) and e_n.max() <= 5e-2 * np.abs(r_n).max(), (n_bad, e_n.max(), np.abs(r_n).max())
     lin = [t for t in m.block_mlps if isinstance(t, torch.nn.Linear)]
     for l, layer in enumerate(lin):
         close(layer.weight.grad, r_W[l], f"W{l}")
@@ -163,3 +169,43 @@ def test_same_values_as_the_torch_module():
             assert (m(x[None]) - t(x[None])).abs().max().item() <= 1e-5
     finally:
         torch.backends.cuda.matmul.allow_tf32 = prev
+
+
+def test_forward_and_backward_replay_from_a_cuda_graph():
+    """strict=False keeps every status on the device: forward + backward captured once, replayed on new inputs"""
+    m = _trained_like(FusedShadowModule(_cfg(), strict=False, capacity=4096), seed=6).to(DEV)
+    n = 10_000
+    x_static = _normals(n, 0.3, seed=21).to(DEV).requires_grad_(True)
+    g_static = torch.randn(n, device=DEV)
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        for _ in range(2):                                            # warm-up: workspaces, cuBLAS-free path
+            for p in m.parameters():
+                p.grad = None
+            x_static.grad = None
+            (m(x_static[None])[0, :, 0] * g_static).sum().backward()
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        for p in m.parameters():
+            p.grad = None
+        x_static.grad = None
+        with torch.cuda.graph(graph, stream=side):
+            out_static = m(x_static[None])[0, :, 0]
+            (out_static * g_static).sum().backward()
+    torch.cuda.synchronize()
+    x_new, g_new = _normals(n, 0.35, seed=22).to(DEV), torch.randn(n, device=DEV)
+    with torch.no_grad():
+        x_static.copy_(x_new)
+        g_static.copy_(g_new)
+    graph.replay()
+    torch.cuda.synchronize()
+    got = [out_static.clone(), x_static.grad.clone()] + [p.grad.clone() for p in m.parameters()]
+    m.check_status()
+    e = FusedShadowModule(_cfg()).to(DEV)
+    e.load_state_dict(m.state_dict())
+    xe = x_new.clone().requires_grad_(True)
+    oe = e(xe[None])[0, :, 0]
+    (oe * g_new).sum().backward()
+    ref = [oe.detach(), xe.grad] + [p.grad for p in e.parameters()]
+    for a, b in zip(got, ref):
+        assert torch.equal(a, b)
