@@ -79,10 +79,13 @@ __device__ __forceinline__ int swz(int j, int q) { return j * 32 + ((((q >> 2) ^
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// x = hi + lo with hi a TF32 number (10 explicit mantissa bits), rounded to nearest with ties away from zero exactly like
+// cvt.rna.tf32.f32 but on the integer pipe (add half an ulp to the magnitude bits, clear the 13 low bits): the conversion
+// instruction issues at a quarter of the rate and the epilogue does two of these per accumulator element.  lo = x - hi is
+// exact in fp32 and has at most 14 significant bits; the tensor core ignores its 13 low mantissa bits (error <= 2^-24 |x|).
 __device__ __forceinline__ void split_tf32(float x, uint32_t &hi, uint32_t &lo) {
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
-    const float r = x - __uint_as_float(hi);
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
+    hi = (__float_as_uint(x) + 0x1000u) & 0xFFFFE000u;
+    lo = __float_as_uint(x - __uint_as_float(hi));
 }
 
 // number of 32-column K-blocks of layer l and the images before it
@@ -317,14 +320,26 @@ __device__ __forceinline__ void encode_normal(float nx, float ny, float nz, int 
 #pragma unroll
     for (int c = 0; c < kEncPad; c++) enc[c] = 0.f;
     enc[0] = nx; enc[1] = ny; enc[2] = nz;
+    // sincosf at every third octave, two angle doublings in between (sin 2a = 2 s c, cos 2a = 1 - 2 s^2): the absolute
+    // error at most quadruples (~2.5e-7), a third of the transcendental work
+    float s[3], c[3];
 #pragma unroll
     for (int k = 0; k < 10; k++) {
         if (k < multires) {
-            const float f = (float)(1 << k);
-            float s, c;
-            sincosf(nx * f, &s, &c); enc[3 + 6 * k + 0] = s; enc[3 + 6 * k + 3] = c;
-            sincosf(ny * f, &s, &c); enc[3 + 6 * k + 1] = s; enc[3 + 6 * k + 4] = c;
-            sincosf(nz * f, &s, &c); enc[3 + 6 * k + 2] = s; enc[3 + 6 * k + 5] = c;
+            if (k % 3 == 0) {
+                const float f = (float)(1 << k);
+                sincosf(nx * f, &s[0], &c[0]);
+                sincosf(ny * f, &s[1], &c[1]);
+                sincosf(nz * f, &s[2], &c[2]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 3; j++) {
+                    const float s2 = 2.f * s[j] * c[j], c2 = 1.f - 2.f * s[j] * s[j];
+                    s[j] = s2; c[j] = c2;
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 3; j++) { enc[3 + 6 * k + j] = s[j]; enc[3 + 6 * k + 3 + j] = c[j]; }
         }
     }
 }
@@ -722,17 +737,22 @@ __global__ void __launch_bounds__(kThreads, 1) k_shadow_bwd_data(ShadowDev a) {
                     float dx[kEncPad];
 #pragma unroll
                     for (int j = 0; j < 32; j++) { dx[j] = __uint_as_float(z0[j]); dx[32 + j] = __uint_as_float(z1[j]); }
-                    float gx = dx[0], gy = dx[1], gz = dx[2];
+                    float gn[3] = {dx[0], dx[1], dx[2]};
+                    const float nn[3] = {nx, ny, nz};
+                    float sn[3], cs[3];
 #pragma unroll
                     for (int k = 0; k < 10; k++) {
                         if (k < a.multires) {
                             const float f = (float)(1 << k);
-                            float sn, cs;
-                            sincosf(nx * f, &sn, &cs); gx += f * (cs * dx[3 + 6 * k + 0] - sn * dx[3 + 6 * k + 3]);
-                            sincosf(ny * f, &sn, &cs); gy += f * (cs * dx[3 + 6 * k + 1] - sn * dx[3 + 6 * k + 4]);
-                            sincosf(nz * f, &sn, &cs); gz += f * (cs * dx[3 + 6 * k + 2] - sn * dx[3 + 6 * k + 5]);
+#pragma unroll
+                            for (int j = 0; j < 3; j++) {
+                                if (k % 3 == 0) sincosf(nn[j] * f, &sn[j], &cs[j]);          // same octave scheme as encode_normal
+                                else { const float s2 = 2.f * sn[j] * cs[j], c2 = 1.f - 2.f * sn[j] * sn[j]; sn[j] = s2; cs[j] = c2; }
+                                gn[j] += f * (cs[j] * dx[3 + 6 * k + j] - sn[j] * dx[3 + 6 * k + 3 + j]);
+                            }
                         }
                     }
+                    const float gx = gn[0], gy = gn[1], gz = gn[2];
                     if (pix >= 0) { float *q = a.g_normals + 3ll * pix; q[0] = gx; q[1] = gy; q[2] = gz; }
                     tc_fence_before();
                 }
