@@ -504,14 +504,15 @@ __global__ void __launch_bounds__(kThreads, 1) k_shadow_fwd(ShadowDev a) {
                 if (!last) {
                     if (!mbar_wait(&z_ready, g & 1u, ab)) { ok = false; break; }
                     tc_fence_after();
+                    uint32_t z[32];
+                    tmem_ld32(dcol, z);
 #pragma unroll 1
                     for (int fb = 0; fb < 4; fb++) {
-                        uint32_t z[32];
                         float h[32];
-                        tmem_ld32(dcol + fb * 32, z);
                         tmem_wait_ld();
 #pragma unroll
                         for (int j = 0; j < 32; j++) h[j] = fmaxf(__uint_as_float(z[j]) + s_bias[l * kWidth + fb * 32 + j], 0.f);
+                        if (fb < 3) tmem_ld32(dcol + (fb + 1) * 32, z);      // next block's accumulator behind this block's work
                         store_block(h, fb, true, img, act_slot_half(1));
                         tmem_wait_st();
                         tc_fence_before();
@@ -524,17 +525,18 @@ __global__ void __launch_bounds__(kThreads, 1) k_shadow_fwd(ShadowDev a) {
                     tc_fence_after();
                     if (tile_n < n_tiles) publish_encoding(encn, tile_n);   // every MMA that read A has completed: start the next tile
                     float acc = 0.f;
+                    uint32_t z[32];
+                    tmem_ld32(dcol, z);
 #pragma unroll 1
                     for (int fb = 0; fb < 4; fb++) {
-                        uint32_t z[32];
                         float h[32];
-                        tmem_ld32(dcol + fb * 32, z);
                         tmem_wait_ld();
 #pragma unroll
                         for (int j = 0; j < 32; j++) {
                             h[j] = fmaxf(__uint_as_float(z[j]) + s_bias[l * kWidth + fb * 32 + j], 0.f);
                             acc = fmaf(h[j], s_wout[fb * 32 + j], acc);
                         }
+                        if (fb < 3) tmem_ld32(dcol + (fb + 1) * 32, z);
                         if (SAVE) store_block(h, fb, false, img, act_slot_half(1));
                     }
                     if (valid) a.out[pix] = 1.f / (1.f + expf(-(acc + s_bout)));
