@@ -6,7 +6,8 @@
 // `bin_size = 0`, i.e. PyTorch3D's NAIVE kernel that tests every pixel against every face (3.6 .. 14 G point-in-triangle
 // tests per call).  Semantics follow PyTorch3D's `CheckPixelInsideFace` / geometry_utils (App. B;
 // parity unpinned, oracle/mesh_raster.py).  B200-first design:
-//   * faces are binned to 16x16-pixel tiles by their blur-padded bounding boxes (count -> scan -> emit, no host sync,
+//   * faces are binned to 8x8-pixel tiles (a face with its 2.4-pixel blur margin spans ~6.5 pixels: 16x16 tiles made every
+//     pixel test 4x more faces than necessary) by their blur-padded bounding boxes (count -> scan -> emit, no host sync,
 //     fixed capacity + overflow flag exactly like the splat rasterizer), so a pixel only meets the faces of its tile;
 //   * ONE pass renders the hard result (nearest inside face -> pix_to_face, summed vertex normals) and the soft
 //     silhouette alpha = 1 - prod(1 - sigmoid(-d/1e-4)).  The product does not depend on order, so a pixel with at most
@@ -22,7 +23,9 @@
 
 namespace {
 
-constexpr int kThreads = 256;
+constexpr int kThreads = 256;                // face-parallel kernels (count, emit)
+constexpr int kBin = 8, kBinShift = 3;       // faces are binned to 8x8-pixel tiles; one 64-thread block rasterises one tile
+constexpr int kPix = kBin * kBin;
 constexpr int kMaxK = 64;                  // thread-local K-nearest queue of the soft silhouette (reference: K = 50)
 constexpr float kEpsArea = 1e-8f;          // PyTorch3D kEpsilon
 constexpr float kBlendSigma = 1e-4f;       // BlendParams().sigma (SoftSilhouetteShader default, mesh.py:107-112)
@@ -72,7 +75,7 @@ __device__ __forceinline__ bool face_tiles(const MeshDev &a, int b, int f, int4 
     ndc_to_pixel_range(fminf(fminf(ax, bx), cx) - br, fmaxf(fmaxf(ax, bx), cx) + br, a.sx, a.S, a.W, x0, x1);
     ndc_to_pixel_range(fminf(fminf(ay, by), cy) - br, fmaxf(fmaxf(ay, by), cy) + br, a.sy, a.S, a.H, y0, y1);
     if (x1 <= x0 || y1 <= y0) return false;
-    rc = make_int4(x0 >> 4, y0 >> 4, (x1 + 15) >> 4, (y1 + 15) >> 4);
+    rc = make_int4(x0 >> kBinShift, y0 >> kBinShift, (x1 + kBin - 1) >> kBinShift, (y1 + kBin - 1) >> kBinShift);
     return true;
 }
 
@@ -199,17 +202,17 @@ __device__ __forceinline__ FaceRec fetch_face(const MeshDev &a, int b, int f, in
 __device__ __forceinline__ bool zid_less(float z0, int f0, float z1, int f1) { return z0 < z1 || (z0 == z1 && f0 < f1); }
 
 // ------------------------------------------------------------------------------------------------------- forward
-__global__ void __launch_bounds__(kThreads) k_mesh_raster_fwd(MeshDev a) {
-    __shared__ FaceRec s_rec[kThreads];
-    __shared__ int s_fid[kThreads];
-    const int b = blockIdx.z, tile = blockIdx.y * a.gx + blockIdx.x, tid = threadIdx.y * 16 + threadIdx.x;
+__global__ void __launch_bounds__(kPix) k_mesh_raster_fwd(MeshDev a) {
+    __shared__ FaceRec s_rec[kPix];
+    __shared__ int s_fid[kPix];
+    const int b = blockIdx.z, tile = blockIdx.y * a.gx + blockIdx.x, tid = threadIdx.y * kBin + threadIdx.x;
     const uint32_t *off = a.tile_offset + (long long)b * (a.T + 1);
     long long start = off[tile], end = off[tile + 1];
     if (start > a.cap) start = a.cap;
     if (end > a.cap) end = a.cap;
     const int n = (int)(end - start);
     const uint32_t *list = a.face_list + (long long)b * a.cap + start;
-    const int x = blockIdx.x * 16 + threadIdx.x, y = blockIdx.y * 16 + threadIdx.y;
+    const int x = blockIdx.x * kBin + threadIdx.x, y = blockIdx.y * kBin + threadIdx.y;
     const bool in_img = x < a.W && y < a.H;
     const float px = a.sx - (2.0f * x + 1.0f) / a.S, py = a.sy - (2.0f * y + 1.0f) / a.S;
     const float br = sqrtf(a.blur);
@@ -223,7 +226,7 @@ __global__ void __launch_bounds__(kThreads) k_mesh_raster_fwd(MeshDev a) {
     float mz = -INFINITY; int mf = -1, mi = 0;
     const int K = a.K;
     const bool keep = a.soft && K <= kMaxK;
-    for (int base = 0; base < n; base += kThreads) {
+    for (int base = 0; base < n; base += kPix) {
         __syncthreads();
         if (base + tid < n) {
             int3 id;
@@ -232,7 +235,7 @@ __global__ void __launch_bounds__(kThreads) k_mesh_raster_fwd(MeshDev a) {
             s_fid[tid] = f;
         }
         __syncthreads();
-        const int m = min(kThreads, n - base);
+        const int m = min(kPix, n - base);
         if (!in_img) continue;
         for (int j = 0; j < m; j++) {
             float pz, dist, tt; bool inside, deg; int edge;
@@ -311,19 +314,19 @@ __global__ void __launch_bounds__(kThreads) k_mesh_raster_fwd(MeshDev a) {
 }
 
 // ------------------------------------------------------------------------------------------------------- backward
-__global__ void __launch_bounds__(kThreads) k_mesh_raster_bwd(MeshDev a) {
-    __shared__ FaceRec s_rec[kThreads];
-    __shared__ int s_fid[kThreads];
-    __shared__ int3 s_vid[kThreads];
+__global__ void __launch_bounds__(kPix) k_mesh_raster_bwd(MeshDev a) {
+    __shared__ FaceRec s_rec[kPix];
+    __shared__ int s_fid[kPix];
+    __shared__ int3 s_vid[kPix];
     __shared__ int s_any;
-    const int b = blockIdx.z, tile = blockIdx.y * a.gx + blockIdx.x, tid = threadIdx.y * 16 + threadIdx.x;
+    const int b = blockIdx.z, tile = blockIdx.y * a.gx + blockIdx.x, tid = threadIdx.y * kBin + threadIdx.x;
     const uint32_t *off = a.tile_offset + (long long)b * (a.T + 1);
     long long start = off[tile], end = off[tile + 1];
     if (start > a.cap) start = a.cap;
     if (end > a.cap) end = a.cap;
     const int n = (int)(end - start);
     const uint32_t *list = a.face_list + (long long)b * a.cap + start;
-    const int x = blockIdx.x * 16 + threadIdx.x, y = blockIdx.y * 16 + threadIdx.y;
+    const int x = blockIdx.x * kBin + threadIdx.x, y = blockIdx.y * kBin + threadIdx.y;
     const bool in_img = x < a.W && y < a.H;
     const long long pix = ((long long)b * a.H + y) * a.W + x;
     const float px = a.sx - (2.0f * x + 1.0f) / a.S, py = a.sy - (2.0f * y + 1.0f) / a.S;
@@ -358,7 +361,7 @@ __global__ void __launch_bounds__(kThreads) k_mesh_raster_bwd(MeshDev a) {
     __syncthreads();
     if (!s_any) return;                                        // interior / empty tiles: alpha saturated, nothing flows
     float *gv = a.d_verts + (long long)b * a.V * 3;
-    for (int base = 0; base < n; base += kThreads) {
+    for (int base = 0; base < n; base += kPix) {
         __syncthreads();
         if (base + tid < n) {
             int3 id;
@@ -368,7 +371,7 @@ __global__ void __launch_bounds__(kThreads) k_mesh_raster_bwd(MeshDev a) {
             s_vid[tid] = id;
         }
         __syncthreads();
-        const int m = min(kThreads, n - base);
+        const int m = min(kPix, n - base);
         if (coef == 0.f) continue;
         for (int j = 0; j < m; j++) {
             float pz, dist, tt; bool inside, deg; int edge;
@@ -407,7 +410,7 @@ int fill_dev(const GomMeshRasterArgs *p, MeshDev &a) {
     GOM_REQUIRE(p->pix_to_face && p->normal_map, "null output");
     GOM_REQUIRE(!p->soft || (p->alpha && p->zcut && p->idcut), "soft silhouette outputs");
     a.B = p->n_frames; a.V = p->n_verts; a.F = p->n_faces; a.H = p->height; a.W = p->width;
-    a.gx = (a.W + 15) / 16; a.gy = (a.H + 15) / 16; a.T = a.gx * a.gy;
+    a.gx = (a.W + kBin - 1) / kBin; a.gy = (a.H + kBin - 1) / kBin; a.T = a.gx * a.gy;
     GOM_REQUIRE(a.gy <= 65535, "image too tall");
     a.K = p->faces_per_pixel; a.faces_int64 = p->faces_int64; a.soft = p->soft; a.cap = p->list_capacity;
     a.blur = p->soft ? p->blur_radius : 0.f;
@@ -441,7 +444,7 @@ extern "C" int gom_mesh_raster_forward(const GomMeshRasterArgs *p, gom_stream_t 
         GOM_LAUNCH_CHECK();
     }
     gom_prof_end(GOM_PROF_MESH_BIN, stream);
-    dim3 bgrid(a.gx, a.gy, a.B), bblock(16, 16);
+    dim3 bgrid(a.gx, a.gy, a.B), bblock(kBin, kBin);
     gom_prof_begin(GOM_PROF_MESH_FWD, stream);
     k_mesh_raster_fwd<<<bgrid, bblock, 0, stream>>>(a);
     GOM_LAUNCH_CHECK();
@@ -457,7 +460,7 @@ extern "C" int gom_mesh_raster_backward(const GomMeshRasterArgs *p, gom_stream_t
     const size_t n = sizeof(float) * 3 * (size_t)a.B * a.V;
     GOM_CUDA(cudaMemsetAsync(a.d_verts, 0, n, stream));
     GOM_CUDA(cudaMemsetAsync(a.d_vnormals, 0, n, stream));
-    dim3 bgrid(a.gx, a.gy, a.B), bblock(16, 16);
+    dim3 bgrid(a.gx, a.gy, a.B), bblock(kBin, kBin);
     gom_prof_begin(GOM_PROF_MESH_BWD, stream);
     k_mesh_raster_bwd<<<bgrid, bblock, 0, stream>>>(a);
     GOM_LAUNCH_CHECK();

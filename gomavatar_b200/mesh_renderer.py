@@ -45,6 +45,9 @@ def vertex_normals(verts_bv3, faces):
     return torch.nn.functional.normalize(n, eps=1e-6, dim=-1)
 
 
+MESH_BIN = 8                 # pixels per side of a binning tile (csrc/mesh_raster.cu kBin)
+
+
 def default_list_capacity(n_faces):
     return max(8 * int(n_faces), 1 << 16)
 
@@ -61,7 +64,7 @@ class _MeshRaster(torch.autograd.Function):
         fc = faces.contiguous()
         if fc.dtype not in (torch.int32, torch.int64):
             fc = fc.long()
-        T = ((W + 15) // 16) * ((H + 15) // 16)
+        T = ((W + MESH_BIN - 1) // MESH_BIN) * ((H + MESH_BIN - 1) // MESH_BIN)
         cap = int(capacity) if capacity else default_list_capacity(F)
         e = lambda *s, dtype=torch.float32: torch.empty(*s, dtype=dtype, device=dev)
         while True:

@@ -367,7 +367,7 @@ int gom_eval_metrics(const GomEvalMetricsArgs *a, gom_stream_t stream);
  *   alpha = 1 - prod_k (1 - sigmoid(-d_k / 1e-4)) over the K faces of smallest interpolated z whose signed squared
  *   NDC distance d_k to the pixel centre is negative (inside) or below blur_radius.
  * verts_ndc are the output of the reference's ndc_T_world (utils/pc_util.py:30-46): x, y in NDC (+X left, +Y up, the
- * shorter image side spans [-1,1]), z = camera depth.  Faces are binned to 16x16 tiles into caller-owned lists of
+ * shorter image side spans [-1,1]), z = camera depth.  Faces are binned to 8x8-pixel tiles (T = ceil(W/8) ceil(H/8)) into caller-owned lists of
  * fixed capacity (overflow -> GOM_STATUS_OVERFLOW in status[b]).
  * backward: dL_dvert_normals from dL_dnormal_map, dL_dverts_ndc (x, y; z gets 0) from dL_dalpha; both zeroed first.
  */
