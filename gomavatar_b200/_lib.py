@@ -161,6 +161,13 @@ class GomShadowMlpArgs(ctypes.Structure):
                 ("g_b_hid", c_void_p), ("g_w_out", c_void_p), ("g_b_out", c_void_p)]
 
 
+class GomMeshRegArgs(ctypes.Structure):
+    _fields_ = [("n_frames", c_int32), ("n_verts", c_int32), ("n_pairs", c_int32), ("n_faces", c_int32), ("do_laplacian", c_int32),
+                ("do_normal", c_int32), ("do_color", c_int32), ("_pad", c_int32), ("verts", c_void_p), ("row_ptr", c_void_p),
+                ("col", c_void_p), ("pair_vid", c_void_p), ("pair_face", c_void_p), ("colors", c_void_p), ("lap", c_void_p),
+                ("sums", c_void_p), ("g_verts_lap", c_void_p), ("g_verts_nc", c_void_p), ("g_colors", c_void_p)]
+
+
 # every symbol include/gom_b200.h declares (tests check the .so exports all of them)
 EXPORTS = [
     "gom_abi_version", "gom_last_error", "gom_launch_count", "gom_profile_enable", "gom_profile_num_slots",
@@ -178,6 +185,7 @@ EXPORTS = [
     "gom_mesh_raster_forward", "gom_mesh_raster_backward", "gom_sizeof_mesh_raster_args",
     "gom_shadow_mlp_forward", "gom_shadow_mlp_backward", "gom_shadow_mlp_weight_image_bytes", "gom_shadow_mlp_tile_words",
     "gom_shadow_mlp_partial_floats", "gom_shadow_mlp_num_ctas", "gom_sizeof_shadow_mlp_args",
+    "gom_mesh_regularizers", "gom_sizeof_mesh_reg_args",
 ]
 
 _STRUCTS = {
@@ -187,7 +195,7 @@ _STRUCTS = {
     "lpips_input": GomLpipsInputArgs, "bias_relu": GomBiasReluArgs, "relu_bwd": GomReluBwdArgs,
     "lpips_tap": GomLpipsTapArgs, "eval_metrics": GomEvalMetricsArgs,
     "conv_first": GomConvFirstArgs, "adam": GomAdamArgs,
-    "mesh_raster": GomMeshRasterArgs, "shadow_mlp": GomShadowMlpArgs,
+    "mesh_raster": GomMeshRasterArgs, "shadow_mlp": GomShadowMlpArgs, "mesh_reg": GomMeshRegArgs,
 }
 _ENTRY_POINTS = ["gom_camera_from_KE", "gom_raster_forward", "gom_raster_backward", "gom_joint_transforms_forward",
                  "gom_joint_transforms_backward", "gom_lbs_forward", "gom_lbs_backward", "gom_face_gaussians_forward",
@@ -195,7 +203,8 @@ _ENTRY_POINTS = ["gom_camera_from_KE", "gom_raster_forward", "gom_raster_backwar
                  "gom_lpips_input_forward", "gom_lpips_input_backward", "gom_bias_relu", "gom_relu_backward",
                  "gom_lpips_tap_forward", "gom_lpips_tap_backward", "gom_eval_metrics",
                  "gom_conv_first_forward", "gom_conv_first_backward", "gom_adam_step",
-                 "gom_mesh_raster_forward", "gom_mesh_raster_backward", "gom_shadow_mlp_forward", "gom_shadow_mlp_backward"]
+                 "gom_mesh_raster_forward", "gom_mesh_raster_backward", "gom_shadow_mlp_forward", "gom_shadow_mlp_backward",
+                 "gom_mesh_regularizers"]
 
 _lib = None
 

@@ -1,0 +1,189 @@
+// regularizers.cu — the three mesh regularisers of reference train.py:123-160 as fused kernels, values
+// AND unit gradients in one call, for a batch of B posed meshes that share one topology:
+//   * uniform Laplacian smoothing     reference utils/network_util.py:669-792 ("uniform"; PyTorch3D laplacian_packed):
+//                                     mean_{b,v} | mean_{j in N(v)} x_j - x_v |^2
+//   * normal consistency              pytorch3d.loss.mesh_normal_consistency (train.py:149):
+//                                     mean_{b,p} 1 - cos(n0, n1) over the pairs p of faces sharing an edge
+//   * colour consistency              reference utils/network_util.py:795-799: mean_{p,c} | col[a_p, c] - col[b_p, c] |
+// The reference builds them from ~60 small torch launches per mesh (gathers, index_add, cross, norms) plus as many again in
+// autograd.  Here: the Laplacian is two gather kernels over a CSR adjacency (deterministic, no atomics), the pair terms are
+// one kernel that scatters its four vertex gradients with atomics (as torch's index_add backward does).  Topology
+// (adjacency, pair indices) is static between subdivisions and built once by the caller.  Vertices arrive in the model's
+// SoA layout [B,3,V] (vertices_observation), so no transposed copy is made.  Losses are accumulated in fp64 partials
+// (one atomicAdd per block).
+#include "gom_common.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+
+struct RegDev {
+    int B, V, P, F;
+    const float *verts;        // [B,3,V]
+    const int *row_ptr, *col;  // CSR adjacency [V+1], [2E]
+    const int *pair_vid;       // [P,4]: v0, v1 (shared edge), other_a, other_b
+    const int *pair_face;      // [P,2]: the two faces (colour term)
+    const float *colors;       // [F,3]
+    float *lap;                // [B,3,V] scratch: Laplacian coordinates
+    double *sums;              // [3]: laplacian, normal consistency, colour consistency (sums, not means)
+    float *g_verts_lap, *g_verts_nc;   // [B,3,V] unit gradients of the two MEANS
+    float *g_colors;           // [F,3]
+};
+
+__device__ __forceinline__ void block_add(double v, double *dst) {
+    __shared__ double s[kThreads / 32];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int i = 0; i < kThreads / 32; i++) t += s[i];
+        atomicAdd(dst, t);
+    }
+    __syncthreads();
+}
+
+// lap[b,:,v] = mean over neighbours - x_v  (0 for an isolated vertex); sums[0] += |lap|^2
+__global__ void __launch_bounds__(kThreads) k_reg_laplacian(RegDev a) {
+    const int v = blockIdx.x * kThreads + threadIdx.x, b = blockIdx.y;
+    double sq = 0.0;
+    if (v < a.V) {
+        const float *x = a.verts + (size_t)b * 3 * a.V;
+        const int lo = a.row_ptr[v], hi = a.row_ptr[v + 1];
+        float sx = 0.f, sy = 0.f, sz = 0.f;
+        for (int i = lo; i < hi; i++) {
+            const int j = a.col[i];
+            sx += x[j]; sy += x[a.V + j]; sz += x[2 * a.V + j];
+        }
+        float lx = 0.f, ly = 0.f, lz = 0.f;
+        if (hi > lo) {
+            const float d = (float)(hi - lo);
+            lx = sx / d - x[v]; ly = sy / d - x[a.V + v]; lz = sz / d - x[2 * a.V + v];
+        }
+        float *l = a.lap + (size_t)b * 3 * a.V;
+        l[v] = lx; l[a.V + v] = ly; l[2 * a.V + v] = lz;
+        sq = (double)lx * lx + (double)ly * ly + (double)lz * lz;
+    }
+    block_add(sq, a.sums + 0);
+}
+
+// d mean|lap|^2 / d x_v = 2/(B V) ( sum_{j in N(v)} lap_j / deg_j - lap_v )     (the adjacency is symmetric)
+__global__ void __launch_bounds__(kThreads) k_reg_laplacian_grad(RegDev a) {
+    const int v = blockIdx.x * kThreads + threadIdx.x, b = blockIdx.y;
+    if (v >= a.V) return;
+    const float *l = a.lap + (size_t)b * 3 * a.V;
+    const int lo = a.row_ptr[v], hi = a.row_ptr[v + 1];
+    float sx = 0.f, sy = 0.f, sz = 0.f;
+    for (int i = lo; i < hi; i++) {
+        const int j = a.col[i];
+        const float dj = (float)(a.row_ptr[j + 1] - a.row_ptr[j]);
+        sx += l[j] / dj; sy += l[a.V + j] / dj; sz += l[2 * a.V + j] / dj;
+    }
+    const float s = 2.0f / ((float)a.B * (float)a.V);
+    float *g = a.g_verts_lap + (size_t)b * 3 * a.V;
+    const bool has = hi > lo;                       // an isolated vertex has lap = 0 and no dependence on itself
+    g[v] = s * (sx - (has ? l[v] : 0.f));
+    g[a.V + v] = s * (sy - (has ? l[a.V + v] : 0.f));
+    g[2 * a.V + v] = s * (sz - (has ? l[2 * a.V + v] : 0.f));
+}
+
+__device__ __forceinline__ float3 cross3(float3 u, float3 w) {
+    return make_float3(u.y * w.z - u.z * w.y, u.z * w.x - u.x * w.z, u.x * w.y - u.y * w.x);
+}
+__device__ __forceinline__ float3 sub3(float3 u, float3 w) { return make_float3(u.x - w.x, u.y - w.y, u.z - w.z); }
+__device__ __forceinline__ float3 add3(float3 u, float3 w) { return make_float3(u.x + w.x, u.y + w.y, u.z + w.z); }
+__device__ __forceinline__ float3 mul3(float3 u, float s) { return make_float3(u.x * s, u.y * s, u.z * s); }
+__device__ __forceinline__ float dot3(float3 u, float3 w) { return u.x * w.x + u.y * w.y + u.z * w.z; }
+__device__ __forceinline__ float3 ldv(const float *x, int V, int v) { return make_float3(x[v], x[V + v], x[2 * V + v]); }
+__device__ __forceinline__ void atomic_add3(float *g, int V, int v, float3 w) {
+    atomicAdd(g + v, w.x); atomicAdd(g + V + v, w.y); atomicAdd(g + 2 * V + v, w.z);
+}
+
+// pair p of mesh b: n0 = e x (a - p0), n1 = -(e x (b - p0)), e = p1 - p0; term = 1 - n0.n1 / (max(|n0|,eps) max(|n1|,eps))
+// (torch.nn.functional.cosine_similarity, eps 1e-8); unit gradient of the MEAN over B P pairs scattered to the 4 vertices
+__global__ void __launch_bounds__(kThreads) k_reg_normal_consistency(RegDev a) {
+    const int p = blockIdx.x * kThreads + threadIdx.x, b = blockIdx.y;
+    double term = 0.0;
+    if (p < a.P) {
+        const float *x = a.verts + (size_t)b * 3 * a.V;
+        const int i0 = a.pair_vid[4 * p], i1 = a.pair_vid[4 * p + 1], ia = a.pair_vid[4 * p + 2], ib = a.pair_vid[4 * p + 3];
+        const float3 p0 = ldv(x, a.V, i0), e = sub3(ldv(x, a.V, i1), p0);
+        const float3 ap = sub3(ldv(x, a.V, ia), p0), bp = sub3(ldv(x, a.V, ib), p0);
+        const float3 n0 = cross3(e, ap), n1 = mul3(cross3(e, bp), -1.f);
+        const float l0 = fmaxf(sqrtf(dot3(n0, n0)), 1e-8f), l1 = fmaxf(sqrtf(dot3(n1, n1)), 1e-8f);
+        const float c = dot3(n0, n1) / (l0 * l1);
+        term = 1.0 - (double)c;
+        const float s = -1.0f / ((float)a.B * (float)a.P);                     // d mean / d cos
+        const float3 w0 = mul3(sub3(mul3(n1, 1.f / l1), mul3(n0, c / l0)), s / l0);   // dL/dn0
+        const float3 w1 = mul3(sub3(mul3(n0, 1.f / l0), mul3(n1, c / l1)), s / l1);   // dL/dn1
+        const float3 de = sub3(cross3(ap, w0), cross3(bp, w1));
+        const float3 dap = cross3(w0, e), dbp = cross3(mul3(w1, -1.f), e);
+        float *g = a.g_verts_nc + (size_t)b * 3 * a.V;
+        atomic_add3(g, a.V, i1, de);
+        atomic_add3(g, a.V, i0, mul3(add3(add3(de, dap), dbp), -1.f));
+        atomic_add3(g, a.V, ia, dap);
+        atomic_add3(g, a.V, ib, dbp);
+    }
+    block_add(term, a.sums + 1);
+}
+
+// mean_{p,c} |col[fa,c] - col[fb,c]| and its unit gradient sign / (3 P)
+__global__ void __launch_bounds__(kThreads) k_reg_color_consistency(RegDev a) {
+    const int p = blockIdx.x * kThreads + threadIdx.x;
+    double term = 0.0;
+    if (p < a.P) {
+        const int fa = a.pair_face[2 * p], fb = a.pair_face[2 * p + 1];
+        const float s = 1.0f / (3.0f * (float)a.P);
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            const float d = a.colors[3 * fa + c] - a.colors[3 * fb + c];
+            term += (double)fabsf(d);
+            const float sg = (d > 0.f) ? s : (d < 0.f ? -s : 0.f);
+            if (sg != 0.f) { atomicAdd(a.g_colors + 3 * fa + c, sg); atomicAdd(a.g_colors + 3 * fb + c, -sg); }
+        }
+    }
+    block_add(term, a.sums + 2);
+}
+
+}  // namespace
+
+extern "C" size_t gom_sizeof_mesh_reg_args(void) { return sizeof(GomMeshRegArgs); }
+
+extern "C" int gom_mesh_regularizers(const GomMeshRegArgs *p, gom_stream_t stream_) {
+    GOM_REQUIRE(p != nullptr, "args");
+    GOM_REQUIRE(p->n_frames > 0 && p->n_verts > 0 && p->n_pairs >= 0 && p->n_faces >= 0, "sizes");
+    GOM_REQUIRE(p->n_frames <= 65535, "n_frames");
+    GOM_REQUIRE(p->verts && p->sums, "null pointer");
+    GOM_REQUIRE(!p->do_laplacian || (p->row_ptr && p->col && p->lap && p->g_verts_lap), "laplacian buffers");
+    GOM_REQUIRE(!p->do_normal || (p->pair_vid && p->g_verts_nc), "normal-consistency buffers");
+    GOM_REQUIRE(!p->do_color || (p->pair_face && p->colors && p->g_colors), "colour-consistency buffers");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    RegDev a;
+    a.B = p->n_frames; a.V = p->n_verts; a.P = p->n_pairs; a.F = p->n_faces;
+    a.verts = p->verts; a.row_ptr = p->row_ptr; a.col = p->col; a.pair_vid = p->pair_vid; a.pair_face = p->pair_face;
+    a.colors = p->colors; a.lap = p->lap; a.sums = p->sums;
+    a.g_verts_lap = p->g_verts_lap; a.g_verts_nc = p->g_verts_nc; a.g_colors = p->g_colors;
+    gom_prof_begin(GOM_PROF_MESH_REG, stream);
+    GOM_CUDA(cudaMemsetAsync(a.sums, 0, 3 * sizeof(double), stream));
+    if (p->do_laplacian) {
+        dim3 grid(gom_div_up(a.V, kThreads), a.B);
+        k_reg_laplacian<<<grid, kThreads, 0, stream>>>(a);
+        GOM_LAUNCH_CHECK();
+        k_reg_laplacian_grad<<<grid, kThreads, 0, stream>>>(a);
+        GOM_LAUNCH_CHECK();
+    }
+    if (p->do_normal && a.P > 0) {
+        GOM_CUDA(cudaMemsetAsync(a.g_verts_nc, 0, sizeof(float) * 3 * (size_t)a.B * a.V, stream));
+        dim3 grid(gom_div_up(a.P, kThreads), a.B);
+        k_reg_normal_consistency<<<grid, kThreads, 0, stream>>>(a);
+        GOM_LAUNCH_CHECK();
+    }
+    if (p->do_color && a.P > 0) {
+        GOM_CUDA(cudaMemsetAsync(a.g_colors, 0, sizeof(float) * 3 * (size_t)a.F, stream));
+        k_reg_color_consistency<<<gom_div_up(a.P, kThreads), kThreads, 0, stream>>>(a);
+        GOM_LAUNCH_CHECK();
+    }
+    gom_prof_end(GOM_PROF_MESH_REG, stream);
+    return GOM_OK;
+}

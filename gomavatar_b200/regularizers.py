@@ -9,7 +9,10 @@
 * ``color_consistency``     reference utils/network_util.py:795-799
 * ``normal_mask_loss``      reference train.py:137-146: L1 between the soft mesh silhouette and the 7x7-dilated gt mask
 
-They are small sparse / elementwise torch ops on [V,3] / [F,3] tensors, not kernels.
+The torch functions below are the readable definition (CPU-testable against dense restatements:
+tests/test_regularizers_cpu.py).  On a CUDA device ``compute_loss`` evaluates the three geometry terms for all frames of
+the batch with the fused kernels of csrc/regularizers.cu (``gom_mesh_regularizers``: values and gradients in 4 launches
+instead of ~150 small ones), checked against these functions in tests/test_regularizers_gpu.py.
 """
 from __future__ import annotations
 
@@ -84,6 +87,70 @@ def normal_mask_loss(normal_mask, mask_gt, kernel_size=7, dilate=True):
     return (normal_mask - mask_gt).abs().mean()
 
 
+def mesh_topology(faces, face_connectivity, n_verts):
+    """Static index tables of ``gom_mesh_regularizers`` (int32, on the device of ``faces``): CSR adjacency of the unique
+    edges, per pair of faces sharing an edge its (v0, v1, opposite a, opposite b) and the two face ids."""
+    e = unique_edges(faces, n_verts)
+    rows, cols = torch.cat([e[:, 0], e[:, 1]]), torch.cat([e[:, 1], e[:, 0]])
+    order = torch.argsort(rows, stable=True)
+    counts = torch.bincount(rows, minlength=n_verts)
+    row_ptr = torch.zeros(n_verts + 1, dtype=torch.int64, device=faces.device)
+    row_ptr[1:] = torch.cumsum(counts, 0)
+    v0, v1, oa, ob = normal_consistency_indices(faces, face_connectivity)
+    return {"row_ptr": row_ptr.int().contiguous(), "col": cols[order].int().contiguous(),
+            "pair_vid": torch.stack([v0, v1, oa, ob], dim=1).int().contiguous(),
+            "pair_face": face_connectivity.int().contiguous(), "n_verts": int(n_verts), "n_faces": int(faces.shape[0])}
+
+
+class _FusedMeshReg(torch.autograd.Function):
+    """(verts [B,3,V], colors [F,3]) -> (laplacian, normal consistency, colour consistency) means, one library call."""
+
+    @staticmethod
+    def forward(ctx, verts, colors, topo, flags):
+        from . import _lib
+        from ._lib import GomMeshRegArgs, call, ptr
+        if verts.device.type != "cuda":
+            raise _lib.GomError("fused mesh regularisers: inputs must live on a CUDA device")
+        B, _, V = verts.shape
+        P, Fn = topo["pair_vid"].shape[0], topo["n_faces"]
+        do_lap, do_nc, do_cc = flags
+        vb = verts.detach().contiguous().float()
+        cb = colors.detach().contiguous().float() if do_cc else None
+        dev = verts.device
+        e = lambda *s_: torch.empty(*s_, dtype=torch.float32, device=dev)
+        sums = torch.empty(3, dtype=torch.float64, device=dev)
+        g_lap = e(B, 3, V) if do_lap else None
+        g_nc = e(B, 3, V) if do_nc else None
+        g_col = e(Fn, 3) if do_cc else None
+        lap_scratch = e(B, 3, V) if do_lap else None
+        a = GomMeshRegArgs(n_frames=B, n_verts=V, n_pairs=P, n_faces=Fn, do_laplacian=int(do_lap), do_normal=int(do_nc),
+                           do_color=int(do_cc), verts=ptr(vb), row_ptr=ptr(topo["row_ptr"]), col=ptr(topo["col"]),
+                           pair_vid=ptr(topo["pair_vid"]), pair_face=ptr(topo["pair_face"]), colors=ptr(cb),
+                           lap=ptr(lap_scratch), sums=ptr(sums), g_verts_lap=ptr(g_lap), g_verts_nc=ptr(g_nc),
+                           g_colors=ptr(g_col))
+        call("gom_mesh_regularizers", a)
+        ctx.grads = (g_lap, g_nc, g_col)
+        # Python scalars only (no host tensor -> device copy: the step stays CUDA-graph capturable)
+        means = torch.stack([sums[0] / (B * V), sums[1] / max(B * P, 1), sums[2] / max(3 * P, 1)]).float()
+        return means[0], means[1], means[2]
+
+    @staticmethod
+    def backward(ctx, g0, g1, g2):
+        g_lap, g_nc, g_col = ctx.grads
+        gv = None
+        if g_lap is not None:
+            gv = g0 * g_lap
+        if g_nc is not None:
+            gv = g1 * g_nc if gv is None else gv + g1 * g_nc
+        gc = g2 * g_col if g_col is not None else None
+        return gv, gc, None, None
+
+
+def fused_mesh_regularizers(verts_b3v, colors_f3, topo, laplacian=True, normal=True, color=True):
+    """(laplacian_smoothing, normal_consistency, color_consistency) of B meshes [B,3,V] sharing ``topo`` (``mesh_topology``)."""
+    return _FusedMeshReg.apply(verts_b3v, colors_f3, topo, (bool(laplacian), bool(normal), bool(color)))
+
+
 def _c(cfg, path, default=0.0):
     cur = cfg
     for k in path.split("."):
@@ -109,28 +176,35 @@ def compute_loss(rgbs, masks, bgcolors, rgb_gt, mask_gt, outputs, model, loss_cf
         total = total + value * coeff
 
     faces = model.faces
-    edges = getattr(model, "_unique_edges", None)                  # topology is fixed between subdivisions: computed once
-    if edges is None or edges.device != faces.device or getattr(model, "_unique_edges_faces", None) is not faces:
-        edges = unique_edges(faces, model.vertices.shape[1])       # (torch.unique syncs: keep it out of the steady-state step)
-        model._unique_edges, model._unique_edges_faces = edges, faces
-        model._vertex_degree = vertex_degree(edges, model.vertices.shape[1])
-    deg = model._vertex_degree
-    if _c(loss_cfg, "laplacian.coeff_canonical") > 0:
-        add("laplacian_canonical", laplacian_smoothing(model.vertices.T, faces, edges, deg), _c(loss_cfg, "laplacian.coeff_canonical"))
-    if _c(loss_cfg, "laplacian.coeff_observation") > 0:
-        vo = outputs["vertices_observation"]                       # [B,3,V]; the reference is batch 1: mean over the frames
-        lap = laplacian_smoothing(vo.permute(0, 2, 1), faces, edges, deg)
-        add("laplacian_observation", lap, _c(loss_cfg, "laplacian.coeff_observation"))
-    if _c(loss_cfg, "normal.coeff_mask") > 0 and outputs.get("normal_mask") is not None:
-        add("normal_mask", normal_mask_loss(outputs["normal_mask"], mask_gt, int(_c(loss_cfg, "normal.kernel_size", 7)),
-                                            bool(_c(loss_cfg, "normal.mask_dilate", True))), _c(loss_cfg, "normal.coeff_mask"))
-    if _c(loss_cfg, "normal.coeff_consist") > 0:
-        vo = outputs["vertices_observation"]
+    c_lap_c, c_lap_o = _c(loss_cfg, "laplacian.coeff_canonical"), _c(loss_cfg, "laplacian.coeff_observation")
+    c_nm, c_nc, c_cc = _c(loss_cfg, "normal.coeff_mask"), _c(loss_cfg, "normal.coeff_consist"), _c(loss_cfg, "color_consist.coeff")
+    vo = outputs.get("vertices_observation")                        # [B,3,V]; the reference is batch 1: mean over the frames
+    fused = vo is not None and vo.is_cuda and (c_lap_o > 0 or c_nc > 0 or c_cc > 0)
+    if fused:                                                       # csrc/regularizers.cu: all three terms in one call
         conn = outputs["face_connectivity"]
-        if getattr(model, "_nc_indices_key", None) is not conn:            # topology only: once per (sub)division
-            model._nc_indices, model._nc_indices_key = normal_consistency_indices(faces, conn), conn
-        nc = normal_consistency(vo.permute(0, 2, 1), faces, conn, model._nc_indices)
-        add("normal_consist", nc, _c(loss_cfg, "normal.coeff_consist"))
-    if _c(loss_cfg, "color_consist.coeff") > 0:
-        add("color_consist", color_consistency(outputs["colors"], outputs["face_connectivity"]), _c(loss_cfg, "color_consist.coeff"))
+        if getattr(model, "_mesh_topology_key", None) is not conn:  # topology only: once per (sub)division
+            model._mesh_topology, model._mesh_topology_key = mesh_topology(faces, conn, model.vertices.shape[1]), conn
+        lap, nc, cc = fused_mesh_regularizers(vo, outputs["colors"], model._mesh_topology, c_lap_o > 0, c_nc > 0, c_cc > 0)
+    else:
+        edges = getattr(model, "_unique_edges", None)               # topology is fixed between subdivisions: computed once
+        if edges is None or edges.device != faces.device or getattr(model, "_unique_edges_faces", None) is not faces:
+            edges = unique_edges(faces, model.vertices.shape[1])    # (torch.unique syncs: keep it out of the steady-state step)
+            model._unique_edges, model._unique_edges_faces = edges, faces
+            model._vertex_degree = vertex_degree(edges, model.vertices.shape[1])
+    if c_lap_c > 0:
+        add("laplacian_canonical", laplacian_smoothing(model.vertices.T, faces), c_lap_c)
+    if c_lap_o > 0:
+        add("laplacian_observation", lap if fused else laplacian_smoothing(vo.permute(0, 2, 1), faces, edges, model._vertex_degree), c_lap_o)
+    if c_nm > 0 and outputs.get("normal_mask") is not None:
+        add("normal_mask", normal_mask_loss(outputs["normal_mask"], mask_gt, int(_c(loss_cfg, "normal.kernel_size", 7)),
+                                            bool(_c(loss_cfg, "normal.mask_dilate", True))), c_nm)
+    if c_nc > 0:
+        if not fused:
+            conn = outputs["face_connectivity"]
+            if getattr(model, "_nc_indices_key", None) is not conn:
+                model._nc_indices, model._nc_indices_key = normal_consistency_indices(faces, conn), conn
+            nc = normal_consistency(vo.permute(0, 2, 1), faces, conn, model._nc_indices)
+        add("normal_consist", nc, c_nc)
+    if c_cc > 0:
+        add("color_consist", cc if fused else color_consistency(outputs["colors"], outputs["face_connectivity"]), c_cc)
     return total, losses

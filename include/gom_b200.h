@@ -473,6 +473,31 @@ size_t gom_shadow_mlp_tile_words(int depth, int which);     /* which: 0 = act_im
 size_t gom_shadow_mlp_partial_floats(void);
 int gom_shadow_mlp_num_ctas(void);                          /* CTAs of the persistent kernels = SMs of the current device */
 
+/* --------------------------------------------------------------------------------------------------------------
+ * Mesh regularisers of reference train.py:123-160 for B posed meshes of one topology: uniform Laplacian smoothing
+ * (utils/network_util.py:669-792, method "uniform"), normal consistency (pytorch3d.loss.mesh_normal_consistency,
+ * train.py:149) and colour consistency (utils/network_util.py:795-799).  One call writes the three SUMS (the caller
+ * divides: B*V, B*P, 3*P) and the unit gradients of the three MEANS; the caller scales them by the loss coefficients.
+ * Topology (CSR adjacency of the unique edges, per pair the shared edge and the two opposite vertices) is static between
+ * subdivisions and supplied by the caller (regularizers.py builds it once).
+ */
+typedef struct {
+    int32_t n_frames, n_verts, n_pairs, n_faces;
+    int32_t do_laplacian, do_normal, do_color, _pad;
+    const float *verts;          /* [B,3,V] (the model's vertices_observation layout) */
+    const int32_t *row_ptr;      /* [V+1] CSR adjacency */
+    const int32_t *col;          /* [2E] */
+    const int32_t *pair_vid;     /* [P,4] v0, v1 (shared edge, v0 < v1), opposite vertex of face a, of face b */
+    const int32_t *pair_face;    /* [P,2] the two faces (colour term) */
+    const float *colors;         /* [F,3] */
+    float *lap;                  /* [B,3,V] scratch */
+    double *sums;                /* [3] out: sum |lap|^2, sum (1 - cos), sum |dcol| */
+    float *g_verts_lap;          /* [B,3,V] out: d mean|lap|^2 / d verts */
+    float *g_verts_nc;           /* [B,3,V] out: d mean(1 - cos) / d verts */
+    float *g_colors;             /* [F,3]   out: d mean|dcol| / d colors */
+} GomMeshRegArgs;
+int gom_mesh_regularizers(const GomMeshRegArgs *a, gom_stream_t stream);
+
 /* struct sizes, so that a foreign-language binding can assert its mirror of the structs */
 size_t gom_sizeof_camera_args(void);
 size_t gom_sizeof_raster_fwd_args(void);
@@ -493,6 +518,7 @@ size_t gom_sizeof_conv_first_args(void);
 size_t gom_sizeof_adam_args(void);
 size_t gom_sizeof_mesh_raster_args(void);
 size_t gom_sizeof_shadow_mlp_args(void);
+size_t gom_sizeof_mesh_reg_args(void);
 
 #ifdef __cplusplus
 }
