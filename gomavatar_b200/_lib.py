@@ -13,7 +13,7 @@ from ctypes import c_int, c_int32, c_int64, c_size_t, c_void_p, c_float, c_char_
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libgom_b200.so")
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 STATUS_OVERFLOW = 1
 STATUS_TIMEOUT = 2
 
@@ -127,8 +127,9 @@ class GomEvalMetricsArgs(ctypes.Structure):
 
 
 class GomConvFirstArgs(ctypes.Structure):
-    _fields_ = [("n_images", c_int32), ("height", c_int32), ("width", c_int32), ("_pad", c_int32), ("x", c_void_p),
-                ("weight", c_void_p), ("bias", c_void_p), ("out", c_void_p), ("dL_dout", c_void_p), ("dL_dx", c_void_p)]
+    _fields_ = [("n_images", c_int32), ("height", c_int32), ("width", c_int32), ("use_tensor_cores", c_int32), ("x", c_void_p),
+                ("weight", c_void_p), ("bias", c_void_p), ("out", c_void_p), ("dL_dout", c_void_p), ("dL_dx", c_void_p),
+                ("scratch", c_void_p)]
 
 
 ADAM_MAX_SEGMENTS = 16

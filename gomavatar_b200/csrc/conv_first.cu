@@ -212,10 +212,14 @@ __global__ void __launch_bounds__(kBwdThreads) k_conv_first_bwd(ConvBwdDev a) {
 
 }  // namespace
 
+int gom_conv_first_forward_tc(const GomConvFirstArgs *p, cudaStream_t stream);      // conv_first_tc.cu
+int gom_conv_first_backward_tc(const GomConvFirstArgs *p, cudaStream_t stream);
+
 extern "C" int gom_conv_first_forward(const GomConvFirstArgs *p, gom_stream_t stream_) {
     GOM_REQUIRE(p != nullptr, "args");
     GOM_REQUIRE(p->n_images > 0 && p->n_images <= 65535 && p->height > 0 && p->width > 0, "sizes");
     GOM_REQUIRE(p->x && p->weight && p->bias && p->out, "null pointer");
+    if (p->use_tensor_cores) return gom_conv_first_forward_tc(p, (cudaStream_t)stream_);
     GOM_REQUIRE(((uintptr_t)p->out % 8) == 0, "out must be 8-byte aligned");
     cudaStream_t stream = (cudaStream_t)stream_;
     ConvFwdDev a{p->n_images, p->height, p->width, p->x, p->weight, p->bias, p->out};
@@ -231,6 +235,7 @@ extern "C" int gom_conv_first_backward(const GomConvFirstArgs *p, gom_stream_t s
     GOM_REQUIRE(p != nullptr, "args");
     GOM_REQUIRE(p->n_images > 0 && p->n_images <= 65535 && p->height > 0 && p->width > 0, "sizes");
     GOM_REQUIRE(p->dL_dout && p->weight && p->dL_dx, "null pointer");
+    if (p->use_tensor_cores) return gom_conv_first_backward_tc(p, (cudaStream_t)stream_);
     cudaStream_t stream = (cudaStream_t)stream_;
     ConvBwdDev a{p->n_images, p->height, p->width, p->dL_dout, p->weight, p->dL_dx};
     dim3 grid(gom_div_up(a.W, kBwdCols), gom_div_up(a.H, kBwdRows), a.N);

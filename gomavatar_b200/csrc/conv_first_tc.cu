@@ -1,0 +1,298 @@
+// conv_first_tc.cu — the first VGG16 convolution of LPIPS (3 -> 64, 3x3, pad 1, + bias + ReLU) and its input gradient as
+// tcgen05 GEMMs over pixel rows, behind the same entry points as the FFMA kernels of conv_first.cu
+// (gom_conv_first_forward / gom_conv_first_backward with use_tensor_cores = 1).
+//
+// Both are far too thin for the tensor core to matter (K = 27 resp. N = 27): the point is to take the 1728 FMAs per
+// pixel off the FP32 pipe, which bound the FFMA kernels at 0.38 ms each, so that the kernels run at the speed of their
+// HBM traffic (forward: write 256 B per pixel; backward: read 256 B per pixel).  Products are formed as 3xTF32
+// (lo*hi + hi*lo + hi*hi, fp32 accumulate), i.e. with fp32-GEMM accuracy like the FFMA kernels they replace.
+//
+//   forward   out[p, k]  = relu( sum_{r,s,c} x[p + (r-1, s-1), c] W[k,c,r,s] + b[k] )
+//             A[p, (r,s,c)] = the 27 neighbourhood values of pixel p (zero padded, gathered by the pixel's thread straight
+//             into tensor memory), B[k, (r,s,c)] = W, one 128 x 64 x 32 product per 128 pixels.
+//   backward  T[p, (r,s,c)] = sum_k dY[p,k] W[k,c,r,s]      (128 x 32 x 64 product, A = the pixel's 64 gradients)
+//             dX[q, c] = sum_{r,s} T[q - (r-1, s-1), (r,s,c)]   (k_conv1_stencil: 9 coalesced float4 loads per pixel from the
+//             9 tap planes the GEMM epilogue writes)
+//
+// One persistent CTA per SM running several independent producer/MMA/epilogue groups (see k_conv1_gemm).
+// The weight images (TF32 hi/lo, K-major SWIZZLE_128B) are built by each CTA in its own shared memory at start-up.
+#include "gom_common.cuh"
+#include "gom_tcgen05.cuh"
+
+namespace {
+
+using namespace gomtc;
+
+constexpr uint32_t kTmemCols = 512;
+
+struct Conv1Dev {
+    int N, H, W;
+    long long rows;                      // N*H*W
+    const float *x, *weight, *bias, *dY;
+    float *out, *T, *dX;
+    uint32_t *status;
+};
+
+__device__ __forceinline__ int swz(int j, int q) { return j * 32 + ((((q >> 2) ^ (j & 7)) << 2) | (q & 3)); }
+
+// MODE 0: forward (K = 32 = one k-block, N = 64).  MODE 1: backward GEMM (K = 64 = two k-blocks, N = 32).
+// A CTA runs G independent groups (4 producer/epilogue warps + 1 MMA warp each, one tile in flight per group, own TMEM
+// columns and barriers): the per-tile chain gather -> split -> tcgen05.st -> MMA -> tcgen05.ld -> store is latency bound,
+// so several chains per SM are interleaved instead of deepening one.  Warps 0..4G-1 are the producers (group = warp / 4;
+// warp % 4 is the TMEM lane quarter a warp may access), warps 4G..5G-1 the MMA issuers.
+template <int MODE> struct Conv1Cfg {
+    static constexpr int KB = MODE == 0 ? 1 : 2;          // k-blocks of 32 columns
+    static constexpr int NOUT = MODE == 0 ? 64 : 32;      // accumulator columns
+    static constexpr int G = MODE == 0 ? 4 : 3;           // groups per CTA: G * (NOUT + 2 * KB * 32) <= 512 TMEM columns
+    static constexpr int COLS = NOUT + 2 * KB * 32;
+    static constexpr int THREADS = G * 160;
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(Conv1Cfg<MODE>::THREADS, 1) k_conv1_gemm(Conv1Dev a) {
+    using Cfg = Conv1Cfg<MODE>;
+    constexpr int KB = Cfg::KB, NOUT = Cfg::NOUT, G = Cfg::G, kThreads = Cfg::THREADS;
+    __shared__ __align__(1024) uint32_t s_b[KB][2][NOUT * 32];    // [k-block][hi|lo][row n][32 swizzled words]
+    extern __shared__ float4 s_stage[];                           // [producer warp][32 rows][16 float4]: row <-> lane transposition
+    __shared__ uint64_t a_ready[G], z_ready[G];
+    __shared__ uint32_t tmem_slot;
+    __shared__ int abort_flag;
+    __shared__ float s_bias[64];
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (threadIdx.x == 32) {
+        for (int i = 0; i < G; i++) { mbar_init(&a_ready[i], kTileRows); mbar_init(&z_ready[i], 1); }
+        abort_flag = 0;
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    // weight images.  forward: row n = output channel k, column kk = (r*3+s)*3+c.  backward: row n = (r*3+s)*3+c, column = k.
+    for (int e = threadIdx.x; e < KB * NOUT * 32; e += kThreads) {
+        const int kb = e / (NOUT * 32), n = (e / 32) % NOUT, kl = e % 32;
+        float w = 0.f;
+        if (MODE == 0) {
+            if (kl < 27) { const int tap = kl / 3, c = kl % 3; w = a.weight[(n * 3 + c) * 9 + tap]; }
+        } else {
+            if (n < 27) { const int tap = n / 3, c = n % 3, k = kb * 32 + kl; w = a.weight[(k * 3 + c) * 9 + tap]; }
+        }
+        uint32_t hi, lo;
+        split_tf32(w, hi, lo);
+        s_b[kb][0][swz(n, kl)] = hi;
+        s_b[kb][1][swz(n, kl)] = lo;
+    }
+    if (MODE == 0) for (int i = threadIdx.x; i < 64; i += kThreads) s_bias[i] = a.bias[i];
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+    const long long n_tiles = (a.rows + kTileRows - 1) / kTileRows;
+    const long long stride = (long long)gridDim.x * G;
+    volatile int *ab = &abort_flag;
+    bool ok = true;
+
+    if (warp >= 4 * G) {
+        const int g = warp - 4 * G;
+        if (lane == 0) {
+            const uint32_t idesc = instr_desc_n(NOUT);
+            const uint32_t d = tmem + g * Cfg::COLS, a_hi = d + NOUT, a_lo = a_hi + KB * 32;
+            uint32_t it = 0;
+            for (long long tile = (long long)blockIdx.x * G + g; tile < n_tiles && ok; tile += stride, it++) {
+                if (!mbar_wait(&a_ready[g], it & 1u, ab)) { ok = false; break; }
+                tc_fence_after();
+#pragma unroll
+                for (int kb = 0; kb < KB; kb++)
+#pragma unroll
+                    for (int ks = 0; ks < 4; ks++) {
+                        const uint32_t kcol = (uint32_t)(kb * 32 + ks * 8);
+                        const uint64_t b_hi = make_b_desc(smem_u32(&s_b[kb][0][0]) + ks * 32);
+                        const uint64_t b_lo = make_b_desc(smem_u32(&s_b[kb][1][0]) + ks * 32);
+                        mma_tf32_ts(d, a_lo + kcol, b_hi, idesc, (kb | ks) != 0);
+                        mma_tf32_ts(d, a_hi + kcol, b_lo, idesc, 1u);
+                        mma_tf32_ts(d, a_hi + kcol, b_hi, idesc, 1u);
+                    }
+                tc_commit(&z_ready[g]);
+            }
+        }
+    } else {
+        const int g = warp >> 2, quarter = warp & 3;
+        const int r = quarter * 32 + lane;
+        const uint32_t d = tmem + ((uint32_t)(quarter * 32) << 16) + g * Cfg::COLS, a_hi = d + NOUT, a_lo = a_hi + KB * 32;
+        const long long HW = (long long)a.H * a.W;
+        // Global rows of 64 floats are read / written by the WARP, 512 contiguous bytes per instruction (lane l: float4
+        // l & 15 of row 2 i + (l >> 4)), and cross to / from the row-per-thread view through this warp's 8 KB of shared
+        // memory; float4 j of row q sits at column j ^ (q & 15), so both views are bank-conflict free per quarter warp.
+        // (One thread writing its own 256-byte row costs 32 half-filled sectors per instruction: 2.5 TB/s instead of 6.)
+        float4 *stg = s_stage + (size_t)warp * 512;
+        uint32_t it = 0;
+        for (long long tile = (long long)blockIdx.x * G + g; tile < n_tiles && ok; tile += stride, it++) {
+            const long long p = tile * kTileRows + r;
+            const long long p_warp = tile * kTileRows + quarter * 32;       // first row of this warp
+            {   // this thread's row of the A operand -> tensor memory
+                float v[KB * 32];
+                if (MODE == 0) {
+#pragma unroll
+                    for (int i = 0; i < 32; i++) v[i] = 0.f;
+                    if (p < a.rows) {
+                        const long long n = p / HW, yx = p - n * HW;
+                        const int y = (int)(yx / a.W), x = (int)(yx - (long long)y * a.W);
+                        const float *img = a.x + n * HW * 3;
+#pragma unroll
+                        for (int dy = -1; dy <= 1; dy++)
+#pragma unroll
+                            for (int dx = -1; dx <= 1; dx++) {
+                                const int yy = y + dy, xx = x + dx;
+                                if (yy >= 0 && yy < a.H && xx >= 0 && xx < a.W) {
+                                    const float *q = img + ((long long)yy * a.W + xx) * 3;
+                                    const int t = ((dy + 1) * 3 + (dx + 1)) * 3;
+                                    v[t] = __ldg(q); v[t + 1] = __ldg(q + 1); v[t + 2] = __ldg(q + 2);
+                                }
+                            }
+                    }
+                } else {
+                    __syncwarp();
+#pragma unroll
+                    for (int i = 0; i < 16; i++) {
+                        const int q = 2 * i + (lane >> 4), j = lane & 15;
+                        float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (p_warp + q < a.rows) f = __ldg(reinterpret_cast<const float4 *>(a.dY + (p_warp + q) * 64) + j);
+                        stg[q * 16 + (j ^ (q & 15))] = f;
+                    }
+                    __syncwarp();
+#pragma unroll
+                    for (int i = 0; i < 16; i++) {
+                        const float4 f = stg[lane * 16 + (i ^ (lane & 15))];
+                        v[4 * i] = f.x; v[4 * i + 1] = f.y; v[4 * i + 2] = f.z; v[4 * i + 3] = f.w;
+                    }
+                }
+#pragma unroll
+                for (int c = 0; c < KB * 2; c++) {
+                    uint32_t hi[16], lo[16];
+#pragma unroll
+                    for (int j = 0; j < 16; j++) split_tf32(v[c * 16 + j], hi[j], lo[j]);
+                    tmem_st16(a_hi + c * 16, hi);
+                    tmem_st16(a_lo + c * 16, lo);
+                }
+                tmem_wait_st();
+                tc_fence_before();
+                mbar_arrive(&a_ready[g]);
+            }
+            if (!mbar_wait(&z_ready[g], it & 1u, ab)) { ok = false; break; }
+            tc_fence_after();
+            if (MODE == 0) {
+                __syncwarp();
+#pragma unroll
+                for (int c = 0; c < 2; c++) {
+                    uint32_t z[32];
+                    tmem_ld32(d + c * 32, z);
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int j = 0; j < 8; j++)
+                        stg[lane * 16 + ((c * 8 + j) ^ (lane & 15))] =
+                            make_float4(fmaxf(__uint_as_float(z[4 * j]) + s_bias[c * 32 + 4 * j], 0.f),
+                                        fmaxf(__uint_as_float(z[4 * j + 1]) + s_bias[c * 32 + 4 * j + 1], 0.f),
+                                        fmaxf(__uint_as_float(z[4 * j + 2]) + s_bias[c * 32 + 4 * j + 2], 0.f),
+                                        fmaxf(__uint_as_float(z[4 * j + 3]) + s_bias[c * 32 + 4 * j + 3], 0.f));
+                }
+                __syncwarp();
+#pragma unroll
+                for (int i = 0; i < 16; i++) {
+                    const int q = 2 * i + (lane >> 4), j = lane & 15;
+                    if (p_warp + q < a.rows)
+                        reinterpret_cast<float4 *>(a.out + (p_warp + q) * 64)[j] = stg[q * 16 + (j ^ (q & 15))];
+                }
+            } else {
+                // T as 9 planes [tap][pixel] of float4 (dX channels 0..2 of that tap, pad): a warp's 32 consecutive pixels
+                // are 512 contiguous bytes per plane, for this store and for the stencil's loads
+                uint32_t z[32];
+                tmem_ld32(d, z);
+                tmem_wait_ld();
+                if (p < a.rows) {
+                    float4 *tp = reinterpret_cast<float4 *>(a.T) + p;
+#pragma unroll
+                    for (int t = 0; t < 9; t++)
+                        tp[(size_t)t * a.rows] = make_float4(__uint_as_float(z[3 * t]), __uint_as_float(z[3 * t + 1]),
+                                                             __uint_as_float(z[3 * t + 2]), 0.f);
+                }
+            }
+            tc_fence_before();      // these tcgen05.ld are ordered before the next a_ready arrive (the next MMA overwrites D)
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x == 0 && abort_flag && a.status) atomicOr(a.status, GOM_STATUS_TIMEOUT);
+    if (warp == 0) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols) : "memory");
+    }
+}
+
+// dX[q, c] = sum over the 9 taps (r,s) of T[(r,s)][q - (r-1, s-1)].c   (pixels outside the image contribute nothing)
+__global__ void __launch_bounds__(256) k_conv1_stencil(Conv1Dev a) {
+    const long long q = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (q >= a.rows) return;
+    const long long HW = (long long)a.H * a.W;
+    const long long n = q / HW, yx = q - n * HW;
+    const int y = (int)(yx / a.W), x = (int)(yx - (long long)y * a.W);
+    const float4 *T = reinterpret_cast<const float4 *>(a.T);
+    float g0 = 0.f, g1 = 0.f, g2 = 0.f;
+#pragma unroll
+    for (int r = 0; r < 3; r++)
+#pragma unroll
+        for (int s = 0; s < 3; s++) {
+            const int yy = y - (r - 1), xx = x - (s - 1);
+            if (yy >= 0 && yy < a.H && xx >= 0 && xx < a.W) {
+                const float4 f = __ldg(T + (size_t)(r * 3 + s) * a.rows + n * HW + (long long)yy * a.W + xx);
+                g0 += f.x; g1 += f.y; g2 += f.z;
+            }
+        }
+    float *o = a.dX + q * 3;
+    o[0] = g0; o[1] = g1; o[2] = g2;
+}
+
+int g_conv1_sms = 0;
+int conv1_setup(void) {
+    if (g_conv1_sms) return GOM_OK;
+    int dev = 0, sms = 0;
+    GOM_CUDA(cudaGetDevice(&dev));
+    GOM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    GOM_CUDA(cudaFuncSetAttribute(k_conv1_gemm<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv1Cfg<0>::G * 4 * 8192));
+    GOM_CUDA(cudaFuncSetAttribute(k_conv1_gemm<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv1Cfg<1>::G * 4 * 8192));
+    g_conv1_sms = sms;
+    return GOM_OK;
+}
+
+}  // namespace
+
+// called by gom_conv_first_forward / gom_conv_first_backward (conv_first.cu) when use_tensor_cores is set
+int gom_conv_first_forward_tc(const GomConvFirstArgs *p, cudaStream_t stream) {
+    GOM_REQUIRE(((uintptr_t)p->out % 16) == 0, "out must be 16-byte aligned");
+    if (int rc = conv1_setup()) return rc;
+    Conv1Dev a{};
+    a.N = p->n_images; a.H = p->height; a.W = p->width; a.rows = (long long)a.N * a.H * a.W;
+    a.x = p->x; a.weight = p->weight; a.bias = p->bias; a.out = p->out; a.status = nullptr;
+    gom_prof_begin(GOM_PROF_CONV_FIRST_FWD, stream);
+    k_conv1_gemm<0><<<g_conv1_sms, Conv1Cfg<0>::THREADS, Conv1Cfg<0>::G * 4 * 8192, stream>>>(a);
+    GOM_LAUNCH_CHECK();
+    gom_prof_end(GOM_PROF_CONV_FIRST_FWD, stream);
+    return GOM_OK;
+}
+
+int gom_conv_first_backward_tc(const GomConvFirstArgs *p, cudaStream_t stream) {
+    GOM_REQUIRE(p->scratch != nullptr, "the tensor-core backward needs scratch [9, N*H*W, 4] floats");
+    GOM_REQUIRE(((uintptr_t)p->dL_dout % 16) == 0 && ((uintptr_t)p->scratch % 16) == 0, "dL_dout / scratch must be 16-byte aligned");
+    if (int rc = conv1_setup()) return rc;
+    Conv1Dev a{};
+    a.N = p->n_images; a.H = p->height; a.W = p->width; a.rows = (long long)a.N * a.H * a.W;
+    a.weight = p->weight; a.dY = p->dL_dout; a.T = p->scratch; a.dX = p->dL_dx; a.status = nullptr;
+    gom_prof_begin(GOM_PROF_CONV_FIRST_BWD, stream);
+    k_conv1_gemm<1><<<g_conv1_sms, Conv1Cfg<1>::THREADS, Conv1Cfg<1>::G * 4 * 8192, stream>>>(a);
+    GOM_LAUNCH_CHECK();
+    k_conv1_stencil<<<gom_div_up(a.rows, 256), 256, 0, stream>>>(a);
+    GOM_LAUNCH_CHECK();
+    gom_prof_end(GOM_PROF_CONV_FIRST_BWD, stream);
+    return GOM_OK;
+}

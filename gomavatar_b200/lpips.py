@@ -207,6 +207,7 @@ class LPIPS(nn.Module):
         self._no_cudnn_epilogue = set()
         # conv1_1 (3 -> 64) runs in csrc/conv_first.cu: torch-contiguous [64,3,3,3] copy of its weight
         self.own_first_conv = True
+        self.first_conv_tc = True      # csrc/conv_first_tc.cu (tcgen05, HBM-bound) instead of csrc/conv_first.cu (FFMA-bound)
         self.register_buffer("w_first", self._convs[0].weight.detach().clone(memory_format=torch.contiguous_format),
                              persistent=False)
 
@@ -224,8 +225,8 @@ class LPIPS(nn.Module):
             if not x.is_contiguous():
                 x = x.contiguous()
             y = torch.empty(N, hh, ww, 64, dtype=torch.float32, device=h.device)
-            call("gom_conv_first_forward", GomConvFirstArgs(n_images=N, height=hh, width=ww, x=ptr(x), weight=ptr(self.w_first),
-                                                            bias=ptr(conv.bias), out=ptr(y)))
+            call("gom_conv_first_forward", GomConvFirstArgs(n_images=N, height=hh, width=ww, use_tensor_cores=int(self.first_conv_tc),
+                                                            x=ptr(x), weight=ptr(self.w_first), bias=ptr(conv.bias), out=ptr(y)))
             return y.permute(0, 3, 1, 2)
         if self.conv_epilogue == "cudnn" and ci not in self._no_cudnn_epilogue:
             # cuDNN's fused conv + bias + activation: measured on B200 at the same time as the bare convolution
@@ -248,8 +249,9 @@ class LPIPS(nn.Module):
             if not g.is_contiguous():
                 g = g.contiguous()
             dx = torch.empty(N, hh, ww, 3, dtype=torch.float32, device=g.device)
-            call("gom_conv_first_backward", GomConvFirstArgs(n_images=N, height=hh, width=ww, weight=ptr(self.w_first),
-                                                             dL_dout=ptr(g), dL_dx=ptr(dx)))
+            scratch = torch.empty(9, N * hh * ww, 4, dtype=torch.float32, device=g.device) if self.first_conv_tc else None
+            call("gom_conv_first_backward", GomConvFirstArgs(n_images=N, height=hh, width=ww, use_tensor_cores=int(self.first_conv_tc),
+                                                             weight=ptr(self.w_first), dL_dout=ptr(g), dL_dx=ptr(dx), scratch=ptr(scratch)))
             return dx.permute(0, 3, 1, 2)
         w = self._convs[ci].weight
         return torch.ops.aten.convolution_backward(g_out, inp, w, None, (1, 1), (1, 1), (1, 1), False, (0, 0), 1,

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define GOM_ABI_VERSION 3
+#define GOM_ABI_VERSION 4
 #define GOM_TILE 16              /* 16x16-pixel tiles, as upstream's BLOCK_X/BLOCK_Y */
 #define GOM_MAX_CHANNELS 4
 #define GOM_MAX_JOINTS 64
@@ -325,17 +325,20 @@ int gom_lpips_tap_forward(const GomLpipsTapArgs *a, gom_stream_t stream);
 int gom_lpips_tap_backward(const GomLpipsTapArgs *a, gom_stream_t stream);
 
 /* First VGG16 convolution of LPIPS (3 -> 64 channels, 3x3, stride 1, zero padding 1) fused with bias + ReLU, and its
- * input gradient, in exact fp32 (csrc/conv_first.cu).  Replaces `features[0:2]` of reference
- * utils/lpips/pretrained_networks.py:96-134.  NHWC activations; weight is torch's contiguous [64,3,3,3].
- * forward : out = relu(conv(x) + bias)          backward: dL_dx = conv_transpose(dL_dout)  (dL_dout already ReLU-masked) */
+ * input gradient, with fp32 accuracy.  Replaces `features[0:2]` of reference utils/lpips/pretrained_networks.py:96-134.
+ * NHWC activations; weight is torch's contiguous [64,3,3,3].
+ * forward : out = relu(conv(x) + bias)          backward: dL_dx = conv_transpose(dL_dout)  (dL_dout already ReLU-masked)
+ * use_tensor_cores = 0: FP32-FMA kernels (csrc/conv_first.cu, FMA-pipe bound); 1: tcgen05 GEMMs over pixel rows with
+ * 3xTF32 products (csrc/conv_first_tc.cu, HBM bound); the backward then needs `scratch`. */
 typedef struct {
-    int32_t n_images, height, width, _pad;
+    int32_t n_images, height, width, use_tensor_cores;
     const float *x;              /* [N,H,W,3]  (forward) */
     const float *weight;         /* [64,3,3,3] */
     const float *bias;           /* [64]       (forward) */
     float *out;                  /* [N,H,W,64] (forward) */
     const float *dL_dout;        /* [N,H,W,64] (backward) */
     float *dL_dx;                /* [N,H,W,3]  (backward) */
+    float *scratch;              /* [9, N*H*W, 4] floats (backward with use_tensor_cores), 16-byte aligned; else NULL */
 } GomConvFirstArgs;
 int gom_conv_first_forward(const GomConvFirstArgs *a, gom_stream_t stream);
 int gom_conv_first_backward(const GomConvFirstArgs *a, gom_stream_t stream);

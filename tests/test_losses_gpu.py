@@ -223,10 +223,12 @@ def test_fused_lpips_matches_oracle(hw, epilogue, golden_dir):
     np.testing.assert_allclose(v2.reshape(B).cpu().numpy(), kv.detach().cpu().numpy(), rtol=1e-5)
 
 
-@pytest.mark.parametrize("hw", [(5, 3), (70, 54), (64, 130), (9, 200)])
-def test_first_convolution_kernels_match_torch_fp32(hw):
-    """csrc/conv_first.cu (3 -> 64, 3x3, pad 1, + bias + ReLU; and its input gradient) against torch's strict-fp32
-    convolution.  Sizes cover single / multiple / ragged 8x64 tiles."""
+@pytest.mark.parametrize("tc", [0, 1])        # 0: FP32-FMA kernels (csrc/conv_first.cu), 1: tcgen05 3xTF32 GEMMs (csrc/conv_first_tc.cu)
+@pytest.mark.parametrize("hw", [(5, 3), (70, 54), (64, 130), (9, 200), (300, 301)])
+def test_first_convolution_kernels_match_torch_fp32(hw, tc):
+    """First LPIPS convolution (3 -> 64, 3x3, pad 1, + bias + ReLU; and its input gradient) against torch's strict-fp32
+    convolution.  Sizes cover single / multiple / ragged tiles (8x64 pixel tiles of the FMA kernels, 128-pixel row tiles
+    that straddle image rows and images, several tiles per CTA for the tcgen05 kernels)."""
     import torch.nn.functional as F
     from gomavatar_b200._lib import GomConvFirstArgs, call, ptr
     H, W = hw
@@ -245,10 +247,15 @@ def test_first_convolution_kernels_match_torch_fp32(hw):
     finally:
         torch.backends.cudnn.allow_tf32 = prev
     out = torch.full((N, H, W, 64), float("nan"), device=DEV)
-    call("gom_conv_first_forward", GomConvFirstArgs(n_images=N, height=H, width=W, x=ptr(x), weight=ptr(w), bias=ptr(b), out=ptr(out)))
+    call("gom_conv_first_forward", GomConvFirstArgs(n_images=N, height=H, width=W, use_tensor_cores=tc, x=ptr(x), weight=ptr(w),
+                                                    bias=ptr(b), out=ptr(out)))
     np.testing.assert_allclose(out.cpu().numpy(), ref.permute(0, 2, 3, 1).detach().float().cpu().numpy(), rtol=1e-5, atol=2e-5)
-    gm = (go * (out > 0)).contiguous()                       # the fused path hands over a ReLU-masked gradient
+    # the fused path hands over a ReLU-masked gradient; the mask is taken from the float64 reference so that an output
+    # within rounding of 0 (a few in 10^6) does not flip it
+    gm = (go * (ref.permute(0, 2, 3, 1) > 0)).float().contiguous()
     dx = torch.full((N, H, W, 3), float("nan"), device=DEV)
-    call("gom_conv_first_backward", GomConvFirstArgs(n_images=N, height=H, width=W, weight=ptr(w), dL_dout=ptr(gm), dL_dx=ptr(dx)))
+    scratch = torch.empty(9, N * H * W, 4, device=DEV) if tc else None
+    call("gom_conv_first_backward", GomConvFirstArgs(n_images=N, height=H, width=W, use_tensor_cores=tc, weight=ptr(w), dL_dout=ptr(gm),
+                                                     dL_dx=ptr(dx), scratch=ptr(scratch)))
     refg = xr.grad.permute(0, 2, 3, 1).float().cpu().numpy()
     np.testing.assert_allclose(dx.cpu().numpy(), refg, rtol=1e-4, atol=1e-5 * np.abs(refg).max())
