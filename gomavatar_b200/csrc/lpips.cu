@@ -145,8 +145,35 @@ __global__ void __launch_bounds__(kThreads) k_lpips_tap_fwd(TapDev a) {
     const int q0 = blockIdx.x * kWarps + wid, qstride = gridDim.x * kWarps;
     const int dqy = qstride / qw, dqx = qstride - dqy * qw;
     int qy = q0 / qw, qx = q0 - qy * qw;
+    // For the wide-image levels (C <= 128: 16 registers per pixel pair) the NEXT quad's features are requested before the
+    // current quad is reduced, so that every warp always has a full set of loads in flight (the kernel is HBM-bound and
+    // otherwise alternates between a load phase and a shuffle/reduce phase).
+    constexpr bool kPrefetch = (L::CPL * L::NIT <= 16);
+    float c0[kPrefetch ? L::NIT : 1][L::CPL], c1[kPrefetch ? L::NIT : 1][L::CPL];
+    auto load_quad = [&](int qy_, int qx_, float (&g0)[kPrefetch ? L::NIT : 1][L::CPL], float (&g1)[kPrefetch ? L::NIT : 1][L::CPL]) {
+#pragma unroll
+        for (int it = 0; it < (kPrefetch ? L::NIT : 1); it++) {
+            const int s_ = it * L::PPW + grp;
+            const int y = 2 * qy_ + (s_ >> 1), x = 2 * qx_ + (s_ & 1);
+            if (y < a.h && x < a.w) {
+                const long long o = ((long long)y * a.w + x) * C;
+                load_px<C>(F0 + o, sl, g0[it]);
+                load_px<C>(F1 + o, sl, g1[it]);
+            } else {
+#pragma unroll
+                for (int r = 0; r < L::CPL; r++) { g0[it][r] = 0.f; g1[it][r] = 0.f; }
+            }
+        }
+    };
+    if (kPrefetch && q0 < nq) load_quad(qy, qx, c0, c1);
     for (int q = q0; q < nq; q += qstride, qy += dqy, qx += dqx) {
         if (qx >= qw) { qx -= qw; qy++; }
+        float n0_[kPrefetch ? L::NIT : 1][L::CPL], n1_[kPrefetch ? L::NIT : 1][L::CPL];
+        if (kPrefetch && q + qstride < nq) {
+            int nqy = qy + dqy, nqx = qx + dqx;
+            if (nqx >= qw) { nqx -= qw; nqy++; }
+            load_quad(nqy, nqx, n0_, n1_);
+        }
         float m0[L::CPL], m1[L::CPL];
 #pragma unroll
         for (int r = 0; r < L::CPL; r++) { m0[r] = -INFINITY; m1[r] = -INFINITY; }
@@ -157,7 +184,10 @@ __global__ void __launch_bounds__(kThreads) k_lpips_tap_fwd(TapDev a) {
             const bool ok = y < a.h && x < a.w;
             const long long o = ((long long)y * a.w + x) * C;
             float f0[L::CPL], f1[L::CPL];
-            if (ok) {
+            if (kPrefetch) {
+#pragma unroll
+                for (int r = 0; r < L::CPL; r++) { f0[r] = c0[kPrefetch ? it : 0][r]; f1[r] = c1[kPrefetch ? it : 0][r]; }
+            } else if (ok) {
                 load_px<C>(F0 + o, sl, f0);
                 load_px<C>(F1 + o, sl, f1);
             } else {
@@ -195,6 +225,12 @@ __global__ void __launch_bounds__(kThreads) k_lpips_tap_fwd(TapDev a) {
                 store_px<C>(a.pooled + (long long)b * pimg + po, sl, m0);
                 store_px<C>(a.pooled + (long long)(b + a.B) * pimg + po, sl, m1);
             }
+        }
+        if (kPrefetch) {
+#pragma unroll
+            for (int it = 0; it < L::NIT; it++)
+#pragma unroll
+                for (int r = 0; r < L::CPL; r++) { c0[kPrefetch ? it : 0][r] = n0_[kPrefetch ? it : 0][r]; c1[kPrefetch ? it : 0][r] = n1_[kPrefetch ? it : 0][r]; }
         }
     }
     __shared__ float sh[kWarps];
@@ -311,6 +347,136 @@ __global__ void __launch_bounds__(kThreads) k_lpips_tap_bwd(TapDev a) {
     }
 }
 
+// The same kernel for the wide-image levels (C <= 128), with the NEXT quad's operands (both feature halves and the pooled
+// gradient) requested before the current quad is processed — see k_lpips_tap_fwd.
+// Backward: gradient wrt the PRE-ReLU convolution output of the prediction half:
+//   [ dval_b * d(mean d)/df0  +  max-pool backward of d_pooled (first maximum in scan order, as torch) ] * (f0 > 0)
+template <int C>
+__global__ void __launch_bounds__(kThreads) k_lpips_tap_bwd_pf(TapDev a) {
+    using L = TL<C>;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int grp = lane / L::LPP, sl = lane % L::LPP;
+    const int b = blockIdx.y;
+    const int qw = (a.w + 1) >> 1, qh = (a.h + 1) >> 1, nq = qw * qh;
+    const int ph = a.h >> 1, pw = a.w >> 1;
+    const long long img = (long long)a.h * a.w * C;
+    const float *F0 = a.feats + (long long)b * img, *F1 = a.feats + (long long)(b + a.B) * img;
+    float *G = a.d_pre + (long long)b * img;
+    const float kscale = 2.f * a.dval[b] / (float)((long long)a.h * a.w);
+    float lin[L::CPL];
+    load_lin<C>(a.lin, sl, lin);
+    const int q0 = blockIdx.x * kWarps + wid, qstride = gridDim.x * kWarps;
+    const int dqy = qstride / qw, dqx = qstride - dqy * qw;
+    int qy = q0 / qw, qx = q0 - qy * qw;
+    float c0[L::NIT][L::CPL], c1[L::NIT][L::CPL], cgp[L::CPL];
+    auto load_quad = [&](int qy_, int qx_, float (&g0)[L::NIT][L::CPL], float (&g1)[L::NIT][L::CPL], float (&ggp)[L::CPL]) {
+#pragma unroll
+        for (int it = 0; it < L::NIT; it++) {
+            const int s_ = it * L::PPW + grp;
+            const int y = 2 * qy_ + (s_ >> 1), x = 2 * qx_ + (s_ & 1);
+            if (y < a.h && x < a.w) {
+                const long long o = ((long long)y * a.w + x) * C;
+                load_px<C>(F0 + o, sl, g0[it]);
+                load_px<C>(F1 + o, sl, g1[it]);
+            } else {
+#pragma unroll
+                for (int r = 0; r < L::CPL; r++) { g0[it][r] = 0.f; g1[it][r] = 0.f; }
+            }
+        }
+        if (a.pool && a.d_pooled && qy_ < ph && qx_ < pw)
+            load_px<C>(a.d_pooled + ((long long)b * ph * pw + (long long)qy_ * pw + qx_) * C, sl, ggp);
+    };
+    if (q0 < nq) load_quad(qy, qx, c0, c1, cgp);
+    for (int q = q0; q < nq; q += qstride, qy += dqy, qx += dqx) {
+        if (qx >= qw) { qx -= qw; qy++; }
+        const bool pooled = a.pool && a.d_pooled && qy < ph && qx < pw;      // warp-uniform; quad complete
+        float n0_[L::NIT][L::CPL], n1_[L::NIT][L::CPL], ngp[L::CPL];
+        if (q + qstride < nq) {
+            int nqy = qy + dqy, nqx = qx + dqx;
+            if (nqx >= qw) { nqx -= qw; nqy++; }
+            load_quad(nqy, nqx, n0_, n1_, ngp);
+        }
+        float f0[L::NIT][L::CPL];
+        bool ok[L::NIT];
+#pragma unroll
+        for (int it = 0; it < L::NIT; it++) {
+            const int s = it * L::PPW + grp;
+            const int y = 2 * qy + (s >> 1), x = 2 * qx + (s & 1);
+            ok[it] = y < a.h && x < a.w;
+#pragma unroll
+            for (int r = 0; r < L::CPL; r++) f0[it][r] = c0[it][r];
+        }
+        // which of the quad's four pixels (scan order s = 0..3) holds the FIRST maximum of each channel
+        float gp[L::CPL];
+        uint32_t am = 0;                                                     // 2 bits per register
+        if (pooled) {
+#pragma unroll
+            for (int r = 0; r < L::CPL; r++) gp[r] = cgp[r];
+#pragma unroll
+            for (int r = 0; r < L::CPL; r++) {
+                float v4[4];                                                 // the quad's four values of this channel
+                if constexpr (L::PPW == 1) {
+#pragma unroll
+                    for (int s = 0; s < 4; s++) v4[s] = f0[s][r];
+                } else if constexpr (L::PPW == 2) {                          // s = 2 it + group: own or the partner group's
+#pragma unroll
+                    for (int it = 0; it < 2; it++) {
+                        const float own = f0[it][r], oth = __shfl_xor_sync(0xffffffffu, own, L::LPP);
+                        v4[2 * it] = grp ? oth : own;                        // group 0's pixel comes first in scan order
+                        v4[2 * it + 1] = grp ? own : oth;
+                    }
+                } else {
+#pragma unroll
+                    for (int s = 0; s < 4; s++) v4[s] = __shfl_sync(0xffffffffu, f0[0][r], s * L::LPP + sl);
+                }
+                float best = v4[0];
+                uint32_t arg = 0;
+#pragma unroll
+                for (int s = 1; s < 4; s++)
+                    if (v4[s] > best || v4[s] != v4[s]) { best = v4[s]; arg = s; }   // strict: the first maximum wins
+                am |= arg << (2 * r);
+            }
+        }
+#pragma unroll
+        for (int it = 0; it < L::NIT; it++) {
+            const int s = it * L::PPW + grp;
+            const int y = 2 * qy + (s >> 1), x = 2 * qx + (s & 1);
+            const long long o = ((long long)y * a.w + x) * C;
+            float f1[L::CPL];
+#pragma unroll
+            for (int r = 0; r < L::CPL; r++) f1[r] = c1[it][r];
+            float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+            for (int r = 0; r < L::CPL; r++) { s0 += f0[it][r] * f0[it][r]; s1 += f1[r] * f1[r]; }
+            group_sum2<L::LPP>(s0, s1);
+            float n0, n1;
+            const float i0 = inv_norm(s0, n0), i1 = inv_norm(s1, n1);
+            float e[L::CPL], dot = 0.f;
+#pragma unroll
+            for (int r = 0; r < L::CPL; r++) {
+                e[r] = kscale * lin[r] * (f0[it][r] * i0 - f1[r] * i1);
+                dot += e[r] * f0[it][r];
+            }
+            dot = group_sum<L::LPP>(dot);
+            const float k2 = __fdividef(dot * i0 * i0, n0);
+            float g[L::CPL];
+#pragma unroll
+            for (int r = 0; r < L::CPL; r++) {
+                float v = e[r] * i0 - k2 * f0[it][r];
+                if (pooled && ((am >> (2 * r)) & 3u) == (uint32_t)s) v += gp[r];
+                g[r] = f0[it][r] > 0.f ? v : 0.f;
+            }
+            if (ok[it]) store_px<C>(G + o, sl, g);
+        }
+#pragma unroll
+        for (int it = 0; it < L::NIT; it++)
+#pragma unroll
+            for (int r = 0; r < L::CPL; r++) { c0[it][r] = n0_[it][r]; c1[it][r] = n1_[it][r]; }
+#pragma unroll
+        for (int r = 0; r < L::CPL; r++) cgp[r] = ngp[r];
+    }
+}
+
 int grid_for(long long work_items, int per_block) {
     long long g = (work_items + per_block - 1) / per_block;
     const long long cap = 148LL * 16;            // 148 SMs x resident blocks; grid-stride loops cover the rest
@@ -326,7 +492,10 @@ template <int C> int launch_tap(const TapDev &d, bool bwd, cudaStream_t stream) 
     if (gx > cap) gx = cap;
     if (gx < 1) gx = 1;
     dim3 grid(gx, d.B);
-    if (bwd) k_lpips_tap_bwd<C><<<grid, kThreads, 0, stream>>>(d);
+    if (bwd) {
+        if constexpr (TL<C>::CPL * TL<C>::NIT <= 16) k_lpips_tap_bwd_pf<C><<<grid, kThreads, 0, stream>>>(d);
+        else k_lpips_tap_bwd<C><<<grid, kThreads, 0, stream>>>(d);
+    }
     else k_lpips_tap_fwd<C><<<grid, kThreads, 0, stream>>>(d);
     GOM_LAUNCH_CHECK();
     return GOM_OK;
