@@ -236,6 +236,7 @@ extern "C" int gom_conv_first_backward(const GomConvFirstArgs *p, gom_stream_t s
     GOM_REQUIRE(p->n_images > 0 && p->n_images <= 65535 && p->height > 0 && p->width > 0, "sizes");
     GOM_REQUIRE(p->dL_dout && p->weight && p->dL_dx, "null pointer");
     if (p->use_tensor_cores) return gom_conv_first_backward_tc(p, (cudaStream_t)stream_);
+    GOM_REQUIRE(p->act == nullptr, "the fused ReLU backward (act) needs use_tensor_cores");
     cudaStream_t stream = (cudaStream_t)stream_;
     ConvBwdDev a{p->n_images, p->height, p->width, p->dL_dout, p->weight, p->dL_dx};
     dim3 grid(gom_div_up(a.W, kBwdCols), gom_div_up(a.H, kBwdRows), a.N);

@@ -28,11 +28,14 @@ constexpr uint32_t kTmemCols = 512;
 struct Conv1Dev {
     int N, H, W;
     long long rows;                      // N*H*W
-    const float *x, *weight, *bias, *dY;
+    const float *x, *weight, *bias, *dY, *act;
     float *out, *T, *dX;
     uint32_t *status;
 };
 
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
 __device__ __forceinline__ int swz(int j, int q) { return j * 32 + ((((q >> 2) ^ (j & 7)) << 2) | (q & 3)); }
 
 // MODE 0: forward (K = 32 = one k-block, N = 64).  MODE 1: backward GEMM (K = 64 = two k-blocks, N = 32).
@@ -46,6 +49,8 @@ template <int MODE> struct Conv1Cfg {
     static constexpr int G = MODE == 0 ? 4 : 3;           // groups per CTA: G * (NOUT + 2 * KB * 32) <= 512 TMEM columns
     static constexpr int COLS = NOUT + 2 * KB * 32;
     static constexpr int THREADS = G * 160;
+    static constexpr int STAGE = MODE == 0 ? 512 : 1024;  // float4 of staging per producer warp (backward: gradient rows + ReLU rows)
+    static constexpr int DYN_SMEM = G * 4 * STAGE * 16;
 };
 
 template <int MODE>
@@ -126,7 +131,7 @@ __global__ void __launch_bounds__(Conv1Cfg<MODE>::THREADS, 1) k_conv1_gemm(Conv1
         // l & 15 of row 2 i + (l >> 4)), and cross to / from the row-per-thread view through this warp's 8 KB of shared
         // memory; float4 j of row q sits at column j ^ (q & 15), so both views are bank-conflict free per quarter warp.
         // (One thread writing its own 256-byte row costs 32 half-filled sectors per instruction: 2.5 TB/s instead of 6.)
-        float4 *stg = s_stage + (size_t)warp * 512;
+        float4 *stg = s_stage + (size_t)warp * Cfg::STAGE;
         uint32_t it = 0;
         for (long long tile = (long long)blockIdx.x * G + g; tile < n_tiles && ok; tile += stride, it++) {
             const long long p = tile * kTileRows + r;
@@ -153,18 +158,32 @@ __global__ void __launch_bounds__(Conv1Cfg<MODE>::THREADS, 1) k_conv1_gemm(Conv1
                             }
                     }
                 } else {
+                    // the warp's 32 gradient rows (and, for the fused ReLU backward, the 32 rows of this convolution's own
+                    // output) go global -> shared memory with cp.async: no registers are tied up by the 32 loads in flight
                     __syncwarp();
 #pragma unroll
                     for (int i = 0; i < 16; i++) {
                         const int q = 2 * i + (lane >> 4), j = lane & 15;
-                        float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (p_warp + q < a.rows) f = __ldg(reinterpret_cast<const float4 *>(a.dY + (p_warp + q) * 64) + j);
-                        stg[q * 16 + (j ^ (q & 15))] = f;
+                        float4 *dst = &stg[q * 16 + (j ^ (q & 15))];
+                        if (p_warp + q < a.rows) {
+                            cp_async16(dst, reinterpret_cast<const float4 *>(a.dY + (p_warp + q) * 64) + j);
+                            if (a.act) cp_async16(dst + 512, reinterpret_cast<const float4 *>(a.act + (p_warp + q) * 64) + j);
+                        } else {
+                            *dst = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (a.act) dst[512] = make_float4(1.f, 1.f, 1.f, 1.f);
+                        }
                     }
+                    asm volatile("cp.async.commit_group;" ::: "memory");
+                    asm volatile("cp.async.wait_group 0;" ::: "memory");
                     __syncwarp();
 #pragma unroll
                     for (int i = 0; i < 16; i++) {
-                        const float4 f = stg[lane * 16 + (i ^ (lane & 15))];
+                        float4 f = stg[lane * 16 + (i ^ (lane & 15))];
+                        if (a.act) {                                // fused ReLU backward of this convolution's own output
+                            const float4 y = stg[512 + lane * 16 + (i ^ (lane & 15))];
+                            f.x = y.x > 0.f ? f.x : 0.f; f.y = y.y > 0.f ? f.y : 0.f;
+                            f.z = y.z > 0.f ? f.z : 0.f; f.w = y.w > 0.f ? f.w : 0.f;
+                        }
                         v[4 * i] = f.x; v[4 * i + 1] = f.y; v[4 * i + 2] = f.z; v[4 * i + 3] = f.w;
                     }
                 }
@@ -259,8 +278,8 @@ int conv1_setup(void) {
     int dev = 0, sms = 0;
     GOM_CUDA(cudaGetDevice(&dev));
     GOM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    GOM_CUDA(cudaFuncSetAttribute(k_conv1_gemm<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv1Cfg<0>::G * 4 * 8192));
-    GOM_CUDA(cudaFuncSetAttribute(k_conv1_gemm<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv1Cfg<1>::G * 4 * 8192));
+    GOM_CUDA(cudaFuncSetAttribute(k_conv1_gemm<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv1Cfg<0>::DYN_SMEM));
+    GOM_CUDA(cudaFuncSetAttribute(k_conv1_gemm<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv1Cfg<1>::DYN_SMEM));
     g_conv1_sms = sms;
     return GOM_OK;
 }
@@ -275,7 +294,7 @@ int gom_conv_first_forward_tc(const GomConvFirstArgs *p, cudaStream_t stream) {
     a.N = p->n_images; a.H = p->height; a.W = p->width; a.rows = (long long)a.N * a.H * a.W;
     a.x = p->x; a.weight = p->weight; a.bias = p->bias; a.out = p->out; a.status = nullptr;
     gom_prof_begin(GOM_PROF_CONV_FIRST_FWD, stream);
-    k_conv1_gemm<0><<<g_conv1_sms, Conv1Cfg<0>::THREADS, Conv1Cfg<0>::G * 4 * 8192, stream>>>(a);
+    k_conv1_gemm<0><<<g_conv1_sms, Conv1Cfg<0>::THREADS, Conv1Cfg<0>::DYN_SMEM, stream>>>(a);
     GOM_LAUNCH_CHECK();
     gom_prof_end(GOM_PROF_CONV_FIRST_FWD, stream);
     return GOM_OK;
@@ -287,9 +306,10 @@ int gom_conv_first_backward_tc(const GomConvFirstArgs *p, cudaStream_t stream) {
     if (int rc = conv1_setup()) return rc;
     Conv1Dev a{};
     a.N = p->n_images; a.H = p->height; a.W = p->width; a.rows = (long long)a.N * a.H * a.W;
-    a.weight = p->weight; a.dY = p->dL_dout; a.T = p->scratch; a.dX = p->dL_dx; a.status = nullptr;
+    a.weight = p->weight; a.dY = p->dL_dout; a.act = p->act; a.T = p->scratch; a.dX = p->dL_dx; a.status = nullptr;
+    GOM_REQUIRE(((uintptr_t)p->act % 16) == 0, "act must be 16-byte aligned");
     gom_prof_begin(GOM_PROF_CONV_FIRST_BWD, stream);
-    k_conv1_gemm<1><<<g_conv1_sms, Conv1Cfg<1>::THREADS, Conv1Cfg<1>::G * 4 * 8192, stream>>>(a);
+    k_conv1_gemm<1><<<g_conv1_sms, Conv1Cfg<1>::THREADS, Conv1Cfg<1>::DYN_SMEM, stream>>>(a);
     GOM_LAUNCH_CHECK();
     k_conv1_stencil<<<gom_div_up(a.rows, 256), 256, 0, stream>>>(a);
     GOM_LAUNCH_CHECK();

@@ -154,7 +154,7 @@ class _FusedLpips(torch.autograd.Function):
         prev = torch.backends.cudnn.allow_tf32
         torch.backends.cudnn.allow_tf32 = net.conv_precision != "fp32"
         try:
-            g_pooled, ci = None, len(conv_in)
+            g_pooled, ci, fuse_act = None, len(conv_in), None
             for level in reversed(range(len(_LEVELS))):
                 ci_last = ci - 1
                 a = acts[conv_out[ci_last]]
@@ -166,10 +166,16 @@ class _FusedLpips(torch.autograd.Function):
                 for j in reversed(range(_LEVELS[level])):
                     ci -= 1
                     inp = acts[conv_in[ci]][:B]
-                    g_in = net._conv_dgrad(g_pre.permute(0, 3, 1, 2), inp, ci)
+                    g_in = net._conv_dgrad(g_pre.permute(0, 3, 1, 2), inp, ci, act=fuse_act)
+                    fuse_act = None
                     g_in = _nhwc(g_in.contiguous(memory_format=torch.channels_last))
                     if j > 0:                                # the input was itself a ReLU output of this block
-                        call("gom_relu_backward", GomReluBwdArgs(n=g_in.numel(), act=ptr(inp), grad=ptr(g_in)))
+                        if ci == 1 and net.own_first_conv and net.first_conv_tc:
+                            # conv1_1's output: its ReLU backward is fused into the tcgen05 dgrad that consumes this gradient
+                            # next (one read + one write of the largest gradient tensor and a launch less)
+                            fuse_act = _nhwc(inp) if _nhwc(inp).is_contiguous() else None
+                        if fuse_act is None:
+                            call("gom_relu_backward", GomReluBwdArgs(n=g_in.numel(), act=ptr(inp), grad=ptr(g_in)))
                         g_pre = g_in
                     else:                                    # the input was the pooled previous block (or the image)
                         g_pooled = g_in
@@ -242,7 +248,8 @@ class LPIPS(nn.Module):
         call("gom_bias_relu", GomBiasReluArgs(n_pixels=N * hh * ww, channels=C, x=ptr(y), bias=ptr(conv.bias)))
         return y
 
-    def _conv_dgrad(self, g_out, inp, ci):
+    def _conv_dgrad(self, g_out, inp, ci, act=None):
+        """``act``: (first convolution, tensor-core kernel only) its own ReLU output; g_out is then the unmasked gradient."""
         if ci == 0 and self.own_first_conv:
             N, _, hh, ww = g_out.shape
             g = g_out.permute(0, 2, 3, 1)
@@ -251,7 +258,8 @@ class LPIPS(nn.Module):
             dx = torch.empty(N, hh, ww, 3, dtype=torch.float32, device=g.device)
             scratch = torch.empty(9, N * hh * ww, 4, dtype=torch.float32, device=g.device) if self.first_conv_tc else None
             call("gom_conv_first_backward", GomConvFirstArgs(n_images=N, height=hh, width=ww, use_tensor_cores=int(self.first_conv_tc),
-                                                             weight=ptr(self.w_first), dL_dout=ptr(g), dL_dx=ptr(dx), scratch=ptr(scratch)))
+                                                             weight=ptr(self.w_first), dL_dout=ptr(g), dL_dx=ptr(dx), scratch=ptr(scratch),
+                                                             act=ptr(act)))
             return dx.permute(0, 3, 1, 2)
         w = self._convs[ci].weight
         return torch.ops.aten.convolution_backward(g_out, inp, w, None, (1, 1), (1, 1), (1, 1), False, (0, 0), 1,

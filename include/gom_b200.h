@@ -339,6 +339,8 @@ typedef struct {
     const float *dL_dout;        /* [N,H,W,64] (backward) */
     float *dL_dx;                /* [N,H,W,3]  (backward) */
     float *scratch;              /* [9, N*H*W, 4] floats (backward with use_tensor_cores), 16-byte aligned; else NULL */
+    const float *act;            /* optional [N,H,W,64] (backward with use_tensor_cores): this convolution's ReLU output; when given,
+                                    dL_dout is the UNMASKED gradient and the ReLU backward (dL_dout * [act > 0]) is fused in */
 } GomConvFirstArgs;
 int gom_conv_first_forward(const GomConvFirstArgs *a, gom_stream_t stream);
 int gom_conv_first_backward(const GomConvFirstArgs *a, gom_stream_t stream);

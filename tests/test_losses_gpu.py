@@ -259,3 +259,9 @@ def test_first_convolution_kernels_match_torch_fp32(hw, tc):
                                                      dL_dx=ptr(dx), scratch=ptr(scratch)))
     refg = xr.grad.permute(0, 2, 3, 1).float().cpu().numpy()
     np.testing.assert_allclose(dx.cpu().numpy(), refg, rtol=1e-4, atol=1e-5 * np.abs(refg).max())
+    if tc:          # fused ReLU backward: unmasked gradient + the convolution's own output
+        act = torch.relu(ref).permute(0, 2, 3, 1).float().contiguous()
+        dx2 = torch.full((N, H, W, 3), float("nan"), device=DEV)
+        call("gom_conv_first_backward", GomConvFirstArgs(n_images=N, height=H, width=W, use_tensor_cores=1, weight=ptr(w), dL_dout=ptr(go),
+                                                         dL_dx=ptr(dx2), scratch=ptr(scratch), act=ptr(act)))
+        assert torch.equal(dx2, dx)
