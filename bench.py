@@ -112,27 +112,30 @@ class ClockSampler:
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed `ncu --set full`
 # capture of this same command (profiles/); filled in by hand after each capture, None = not captured yet.
-NCU_TRAFFIC_BYTES = {      # profiles/r1s_ncu_full_summary.md (8 frames, 512x512): mean over the kernel's launches in one step,
-    # like `achieved` (tap_bwd 5 launches 3201.5 MB, tap_fwd 5 launches 2497.0 MB, relu_bwd 8 launches 3418.0 MB)
-    "lpips_tap_bwd": 640.3e6, "lpips_tap_fwd": 499.4e6, "relu_bwd": 427.2e6, "conv_first_fwd": 1079.0e6,
-    "conv_first_bwd": 581.1e6, "blend_bwd": 16.4e6, "sort_blend_fwd": 16.8e6}
+NCU_TRAFFIC_BYTES = {      # profiles/r2_ncu_full_summary.md (8 frames, 512x512): mean over the kernel's launches in one step,
+    # like `achieved` (tap_bwd 5 launches 3199.5 MB, tap_fwd 5 launches 2494.3 MB, relu_bwd 7 launches 1854.0 MB,
+    # conv_first_bwd = k_conv1_gemm<1> 1357.2 MB + k_conv1_stencil 323.4 MB)
+    "lpips_tap_bwd": 639.9e6, "lpips_tap_fwd": 498.9e6, "relu_bwd": 264.9e6, "conv_first_fwd": 1064.6e6,
+    "conv_first_bwd": 1680.6e6, "blend_bwd": 16.4e6, "sort_blend_fwd": 17.0e6}
 
 _VGG_LEVELS = ((64, 2), (128, 2), (256, 3), (512, 3), (512, 3))      # (channels, convolutions) per VGG16 block
 
 
-def lpips_alg_bytes_per_frame(H, W, own_kernel_epilogue=False):
+def lpips_alg_bytes_per_frame(H, W, own_kernel_epilogue=False, fused_first_relu=True):
     """Algorithmic HBM bytes per FRAME (= one prediction + one target image) of the hand-written LPIPS kernels, summed
     over the layers each kernel serves (csrc/lpips.cu; formulas in DESIGN.md §4).  fp32 NHWC."""
     out = {"lpips_input": (2 * 2 + 2) * 3 * H * W * 4.0, "bias_relu": 0.0, "relu_bwd": 0.0, "lpips_tap_fwd": 0.0,
            "lpips_tap_bwd": 0.0,
-           # conv1_1 in csrc/conv_first.cu (fp32-FMA-bound, 1728 FMA per pixel; bytes listed for completeness)
-           "conv_first_fwd": 2 * H * W * (3 + 64) * 4.0, "conv_first_bwd": H * W * (64 + 3) * 4.0}
+           # conv1_1 in csrc/conv_first_tc.cu: forward for prediction + target; backward reads the gradient (and, with the
+           # fused ReLU backward, the layer's own output) and writes 3 channels
+           "conv_first_fwd": 2 * H * W * (3 + 64) * 4.0, "conv_first_bwd": H * W * (64 + 3 + (64 if fused_first_relu else 0)) * 4.0}
     h, w, cin = H, W, 3
     for level, (C, n_conv) in enumerate(_VGG_LEVELS):
         px = h * w
         if own_kernel_epilogue:
             out["bias_relu"] += n_conv * 2 * (2 * px * C * 4.0)          # read + write, pred and gt
-        out["relu_bwd"] += (n_conv - 1) * 3 * (px * C * 4.0)             # act read, grad read + write (pred half)
+        n_relu = n_conv - 1 - (1 if (level == 0 and fused_first_relu) else 0)   # conv1_1's ReLU backward lives in its dgrad kernel
+        out["relu_bwd"] += n_relu * 3 * (px * C * 4.0)                   # act read, grad read + write (pred half)
         pooled = (h // 2) * (w // 2) * C * 4.0 if level < 4 else 0.0
         out["lpips_tap_fwd"] += 2 * px * C * 4.0 + 2 * pooled
         out["lpips_tap_bwd"] += 2 * px * C * 4.0 + pooled + px * C * 4.0
