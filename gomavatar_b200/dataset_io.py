@@ -1,0 +1,298 @@
+"""On-disk compatibility with the reference's processed-dataset format.
+
+* ``write_dataset``   writes what reference ``scripts/prepare_zju-mocap/prepare_dataset.py:143-197`` writes:
+                      ``images/<name>.png``, ``masks/<name>.png`` (3-channel), ``cameras.pkl`` {name: intrinsics, extrinsics,
+                      distortions}, ``mesh_infos.pkl`` {name: Rh, Th, poses[72], joints[24,3], tpose_joints[24,3]},
+                      ``canonical_joints.pkl`` {vertex, joints, weights, edges, faces}, ``avg_betas.npy``.
+* ``Dataset``         reads it back with the constructor, ``__getitem__`` keys and ``get_canonical_info()`` of reference
+                      ``dataset/train.py::Dataset`` (:18-310), so its items feed ``Model.forward`` / ``compute_loss`` exactly like
+                      the reference's (train.py:300-330) and reference-prepared ZJU / Snapshot folders load unchanged.
+* ``write_synthetic_dataset``  the synthetic scene of ``gomavatar_b200.synthetic`` in that format (teacher renders as images).
+
+Pinned by the reference's own reader run on a folder this module wrote (tests/golden/golden_dataset.npz, made by
+oracle/make_golden.py::dataset_golden with OpenCV stubbed out): every item field agrees.  What OpenCV does to pixels is not
+reproduced bit for bit: images are resampled with Pillow (LANCZOS / BILINEAR) when ``target_size`` differs from the file size,
+and non-zero lens distortion is rejected (ZJU-MoCap's processed folders carry the raw distortion coefficients; Snapshot's
+are zero) — both are stated in DESIGN.md as unpinned.  Pure numpy / Pillow: this is host-side I/O, not the hot path.
+"""
+from __future__ import annotations
+
+import os
+import pickle
+
+import numpy as np
+
+from .synthetic import SMPL_PARENTS, body_pose_to_body_RTs, canonical_global_tfms, rvec_to_rmtx
+
+
+# ------------------------------------------------------------------------------------------------------------ helpers
+def _rodrigues(rvec):
+    """cv2.Rodrigues(rvec)[0] (exact axis-angle, no regularisation) in float64."""
+    v = np.asarray(rvec, dtype=np.float64).reshape(3)
+    th = float(np.linalg.norm(v))
+    if th < 1e-12:
+        return np.eye(3)
+    k = v / th
+    K = np.array([[0, -k[2], k[1]], [k[2], 0, -k[0]], [-k[1], k[0], 0]])
+    return np.cos(th) * np.eye(3) + np.sin(th) * K + (1 - np.cos(th)) * np.outer(k, k)
+
+
+def apply_global_tfm_to_camera(E, Rh, Th, return_global_tfms=False):
+    """reference utils/camera_util.py:111-131."""
+    g = np.eye(4)
+    rot = _rodrigues(Rh).T
+    g[:3, :3] = rot
+    g[:3, 3] = -rot.dot(np.asarray(Th, dtype=np.float64))
+    out = np.asarray(E).dot(np.linalg.inv(g))
+    return (out, g) if return_global_tfms else out
+
+
+def get_joints_from_pose(poses, tpose_joints):
+    """reference utils/body_util.py:553-582 (fp32 forward kinematics of the 24 joints)."""
+    N = tpose_joints.shape[0]
+    poses = np.asarray(poses).reshape(N, -1)
+    T = np.eye(4, dtype=np.float32)[None].repeat(N, axis=0)
+    for i in range(N):
+        T[i, :3, :3] = rvec_to_rmtx(poses[i]).astype(np.float32)
+        T[i, :3, 3] = tpose_joints[i] if i == 0 else tpose_joints[i] - tpose_joints[SMPL_PARENTS[i]]
+    joints = np.zeros((N, 4), dtype=np.float32)
+    joints[0] = T[0] @ np.array([0, 0, 0, 1], dtype=np.float32)
+    for i in range(1, N):
+        T[i] = T[SMPL_PARENTS[i]] @ T[i]
+        joints[i] = T[i] @ np.array([0, 0, 0, 1], dtype=np.float32)
+    return joints[:, :3] / joints[:, 3:]
+
+
+def unique_edges(faces):
+    """trimesh.Trimesh(...).edges of the reference writer is every directed face edge; readers only use it as an index
+    list, so the [3F,2] directed edges in face order are written (same content as trimesh's ``edges``)."""
+    f = np.asarray(faces)
+    return np.concatenate([f[:, [0, 1]], f[:, [1, 2]], f[:, [2, 0]]], axis=1).reshape(-1, 2)
+
+
+def _save_png(array_u8, path):
+    from PIL import Image
+    Image.fromarray(array_u8).save(path)
+
+
+def _load_rgb(path):
+    from PIL import Image
+    return np.array(Image.open(path).convert("RGB"))
+
+
+# ------------------------------------------------------------------------------------------------------------- writer
+def write_dataset(path, canonical, frames):
+    """canonical: dict(vertex [V,3], joints [24,3], weights [V,24], faces [F,3]); frames: iterable of dicts with keys
+    name, image (uint8 [H,W,3]), mask (uint8 [H,W] or [H,W,3], 255 = subject), K [3,3], E [4,4], optional D [5], Rh [3],
+    Th [3], poses [72], tpose_joints [24,3], optional joints [24,3] (posed joints; forward kinematics if absent)."""
+    os.makedirs(os.path.join(path, "images"), exist_ok=True)
+    os.makedirs(os.path.join(path, "masks"), exist_ok=True)
+    cameras, mesh_infos = {}, {}
+    for fr in frames:
+        name = fr["name"]
+        mask = np.asarray(fr["mask"], dtype=np.uint8)
+        if mask.ndim == 2:
+            mask = np.stack([mask] * 3, axis=-1)
+        _save_png(np.asarray(fr["image"], dtype=np.uint8), os.path.join(path, "images", f"{name}.png"))
+        _save_png(mask, os.path.join(path, "masks", f"{name}.png"))
+        cameras[name] = {"intrinsics": np.asarray(fr["K"], dtype=np.float64), "extrinsics": np.asarray(fr["E"], dtype=np.float64),
+                         "distortions": np.asarray(fr.get("D", np.zeros(5)), dtype=np.float64)}
+        poses = np.asarray(fr["poses"], dtype=np.float64).reshape(-1)
+        tpose = np.asarray(fr["tpose_joints"], dtype=np.float64)
+        joints = fr.get("joints")
+        if joints is None:
+            joints = get_joints_from_pose(poses.astype(np.float32), tpose.astype(np.float32))
+        mesh_infos[name] = {"Rh": np.asarray(fr.get("Rh", np.zeros(3)), dtype=np.float64),
+                            "Th": np.asarray(fr.get("Th", np.zeros(3)), dtype=np.float64), "poses": poses,
+                            "joints": np.asarray(joints, dtype=np.float64), "tpose_joints": tpose}
+    with open(os.path.join(path, "cameras.pkl"), "wb") as f:
+        pickle.dump(cameras, f)
+    with open(os.path.join(path, "mesh_infos.pkl"), "wb") as f:
+        pickle.dump(mesh_infos, f)
+    np.save(os.path.join(path, "avg_betas.npy"), np.zeros(10))
+    faces = np.asarray(canonical["faces"])
+    with open(os.path.join(path, "canonical_joints.pkl"), "wb") as f:
+        pickle.dump({"vertex": np.asarray(canonical["vertex"], dtype=np.float64),
+                     "joints": np.asarray(canonical["joints"], dtype=np.float64),
+                     "weights": np.asarray(canonical["weights"], dtype=np.float64), "edges": unique_edges(faces), "faces": faces}, f)
+
+
+def write_synthetic_dataset(path, scene, poses72, cameras, images, masks, Rh=None, Th=None):
+    """``scene``: synthetic.Scene; poses72 [N,72]; cameras: list of (K [3,3], E [4,4]) as the MODEL sees them (i.e. after the
+    global transform); images uint8 [N,H,W,3], masks uint8 [N,H,W].  With Rh/Th [N,3] the stored extrinsics are E G so
+    that the reader's apply_global_tfm_to_camera recovers E."""
+    frames = []
+    for i, (K, E) in enumerate(cameras):
+        rh = np.zeros(3) if Rh is None else np.asarray(Rh[i], dtype=np.float64)
+        th = np.zeros(3) if Th is None else np.asarray(Th[i], dtype=np.float64)
+        _, g = apply_global_tfm_to_camera(np.eye(4), rh, th, return_global_tfms=True)
+        frames.append({"name": f"frame_{i:06d}", "image": images[i], "mask": masks[i], "K": K, "E": np.asarray(E, dtype=np.float64) @ g,
+                       "Rh": rh, "Th": th, "poses": poses72[i], "tpose_joints": scene.joints})
+    canonical = {"vertex": scene.vertices, "joints": scene.joints, "weights": scene.lbs_weights[:24].T, "faces": scene.faces}
+    write_dataset(path, canonical, frames)
+
+
+# ------------------------------------------------------------------------------------------------------------- reader
+class Dataset:
+    """Mirror of reference ``dataset/train.py::Dataset`` (same constructor arguments, item keys and dtypes).  Works as a
+    ``torch.utils.data.Dataset`` (``__len__`` / ``__getitem__``); it does not import torch."""
+
+    def __init__(self, dataset_path, keyfilter=None, maxframes=-1, bgcolor=None, skip=1, target_size=None,
+                 crop_size=(-1, -1), prefetch=False, split_for_pose=False):
+        self.cfg = {"bbox_offset": 0.3, "resize_img_scale": [0.5, 0.5]}
+        self.dataset_path = dataset_path
+        self.image_dir = os.path.join(dataset_path, "images")
+        with open(os.path.join(dataset_path, "canonical_joints.pkl"), "rb") as f:
+            cj = pickle.load(f)
+        self.canonical_joints = cj["joints"].astype("float32")
+        self.canonical_bbox = self.skeleton_to_bbox(self.canonical_joints)
+        self.canonical_vertex = cj["vertex"].astype("float32")
+        self.canonical_lbs_weights = cj["weights"].astype("float32")
+        self.edges = cj["edges"].astype(int) if "edges" in cj else None
+        self.faces = cj.get("faces")
+        with open(os.path.join(dataset_path, "cameras.pkl"), "rb") as f:
+            self.cameras = pickle.load(f)
+        with open(os.path.join(dataset_path, "mesh_infos.pkl"), "rb") as f:
+            self.mesh_infos = pickle.load(f)
+        for name in self.mesh_infos:
+            self.mesh_infos[name]["bbox"] = self.skeleton_to_bbox(self.mesh_infos[name]["joints"])
+        names = sorted(os.path.splitext(n)[0] for n in os.listdir(self.image_dir) if n.endswith(".png"))
+        self.framelist = names[::skip]
+        if maxframes > 0:
+            self.framelist = self.framelist[:maxframes]
+        if split_for_pose:
+            self.framelist = self.framelist[:-(len(self.framelist) // 5)]
+        self.keyfilter, self.bgcolor = keyfilter, bgcolor
+        if target_size is not None:
+            self.cfg["target_size"] = target_size
+        self.cfg["crop_size"] = list(crop_size)
+        self.prefetch = prefetch
+        if prefetch:
+            self.preload = {n: list(self.load_image(n, np.zeros(3, dtype="float32"))) for n in self.framelist}
+
+    def skeleton_to_bbox(self, skeleton):
+        return {"min_xyz": np.min(skeleton, axis=0) - self.cfg["bbox_offset"], "max_xyz": np.max(skeleton, axis=0) + self.cfg["bbox_offset"]}
+
+    def _resize(self, arr, size, lanczos):
+        from PIL import Image
+        w, h = size
+        if arr.shape[1] == w and arr.shape[0] == h:
+            return arr
+        mode = Image.LANCZOS if lanczos else Image.BILINEAR
+        chans = [np.asarray(Image.fromarray(arr[..., c].astype(np.float32), mode="F").resize((w, h), mode)) for c in range(arr.shape[2])]
+        return np.stack(chans, axis=-1).astype(arr.dtype)
+
+    def load_image(self, frame_name, bg_color):
+        orig = _load_rgb(os.path.join(self.image_dir, f"{frame_name}.png"))
+        orig_H, orig_W, _ = orig.shape
+        alpha = _load_rgb(os.path.join(self.dataset_path, "masks", f"{frame_name}.png"))
+        cam = self.cameras.get(frame_name, {})
+        if "distortions" in cam and np.any(np.asarray(cam["distortions"]) != 0):
+            raise NotImplementedError("lens undistortion (cv2.undistort in the reference) is not reproduced: undistort the folder first")
+        alpha = alpha / 255.0
+        img = alpha * orig + (1.0 - alpha) * np.asarray(bg_color)[None, None, :]
+        if "target_size" in self.cfg:
+            img, alpha = self._resize(img, self.cfg["target_size"], True), self._resize(alpha, self.cfg["target_size"], False)
+        elif self.cfg["resize_img_scale"] != 1.0:
+            sx, sy = self.cfg["resize_img_scale"]
+            size = (int(round(orig_W * sx)), int(round(orig_H * sy)))
+            img, alpha = self._resize(img, size, True), self._resize(alpha, size, False)
+        return img, alpha, orig_W, orig_H
+
+    def crop_image(self, img, mask, K):
+        """reference dataset/train.py:176-200 (random crop around the mask's centre, same np.random call sequence)."""
+        crop_w, crop_h = self.cfg["crop_size"]
+        h, w, _ = img.shape
+        h_center, w_center, _ = np.stack(np.nonzero(mask), axis=-1).mean(axis=0).astype(int)
+        h_center = min(h_center, h - (crop_h + 1) // 2) if h_center + (crop_h + 1) // 2 > h else h_center
+        h_center = crop_h // 2 if h_center - crop_h // 2 < 0 else h_center
+        w_center = min(w_center, w - (crop_w + 1) // 2) if w_center + (crop_w + 1) // 2 > w else w_center
+        w_center = crop_w // 2 if w_center - crop_w // 2 < 0 else w_center
+        h_left, w_left = h_center - crop_h // 2, w_center - crop_w // 2
+        while True:
+            rand_w = np.random.randint(max(0, w_left - 50), min(w_left + 50, w - crop_w + 1))
+            rand_h = np.random.randint(max(0, h_left - 50), min(h_left + 50, h - crop_h + 1))
+            crop_mask = mask[rand_h:rand_h + crop_h, rand_w:rand_w + crop_w]
+            if np.sum(crop_mask) < 20:
+                continue
+            K_new = K.copy()
+            K_new[0, 2] -= rand_w
+            K_new[1, 2] -= rand_h
+            return img[rand_h:rand_h + crop_h, rand_w:rand_w + crop_w], crop_mask, K_new
+
+    def get_total_frames(self):
+        return len(self.framelist)
+
+    def __len__(self):
+        return len(self.framelist)
+
+    def __getitem__(self, idx):
+        name = self.framelist[idx]
+        res = {"frame_name": name}
+        bgcolor = (np.random.rand(3) * 255.0).astype("float32") if self.bgcolor is None else np.array(self.bgcolor, dtype="float32")
+        res["bgcolor"] = bgcolor / 255.0
+        if self.prefetch:
+            img, alpha, orig_W, orig_H = self.preload[name]
+            img = alpha * img + (1.0 - alpha) * bgcolor[None, None, :]
+        else:
+            img, alpha, orig_W, orig_H = self.load_image(name, bgcolor)
+        img = (img / 255.0).astype("float32")
+        info = self.mesh_infos[name]
+        dst_poses, tpose = info["poses"].astype("float32"), info["tpose_joints"].astype("float32")
+        K = self.cameras[name]["intrinsics"][:3, :3].copy()
+        if "target_size" in self.cfg:
+            scale_w, scale_h = self.cfg["target_size"][0] / orig_W, self.cfg["target_size"][1] / orig_H
+        else:
+            scale_w, scale_h = self.cfg["resize_img_scale"]
+        K[:1] *= scale_w
+        K[1:2] *= scale_h
+        E, global_tfms = apply_global_tfm_to_camera(self.cameras[name]["extrinsics"], info["Rh"].astype("float32"),
+                                                    info["Th"].astype("float32"), return_global_tfms=True)
+        res["global_tfms"] = global_tfms
+        if list(self.cfg["crop_size"]) != [-1, -1]:
+            img, alpha, K = self.crop_image(img, alpha, K)
+        res.update({"K": K.astype(np.float32), "E": E.astype(np.float32), "target_rgbs": img,
+                    "target_masks": alpha[:, :, 0].astype(np.float32)})
+        dst_Rs, dst_Ts = body_pose_to_body_RTs(dst_poses, tpose)
+        res.update({"dst_poses": dst_poses, "dst_Rs": dst_Rs, "dst_Ts": dst_Ts, "cnl_gtfms": canonical_global_tfms(self.canonical_joints),
+                    "dst_posevec": dst_poses.reshape(-1)[3:] + 1e-2, "joints": get_joints_from_pose(dst_poses, tpose),
+                    "dst_tpose_joints": tpose})
+        return res
+
+    def get_canonical_info(self):
+        """reference dataset/train.py:286-300: what ``Model(model_cfg, canonical_info)`` is built from."""
+        return {"canonical_joints": self.canonical_joints,
+                "canonical_bbox": {"min_xyz": self.canonical_bbox["min_xyz"], "max_xyz": self.canonical_bbox["max_xyz"],
+                                   "scale_xyz": self.canonical_bbox["max_xyz"] - self.canonical_bbox["min_xyz"]},
+                "canonical_vertex": self.canonical_vertex, "canonical_lbs_weights": self.canonical_lbs_weights,
+                "edges": self.edges, "faces": self.faces}
+
+
+# -------------------------------------------------------------------------------------------------------- checkpoints
+def save_checkpoint(path, model, optimizer_state=None, n_iter=0):
+    """The reference's checkpoint file (train.py:289-294, :372-376): {'iter', 'network': state_dict, 'optimizer'}."""
+    import torch
+    torch.save({"iter": int(n_iter), "network": model.state_dict(), "optimizer": optimizer_state if optimizer_state is not None else {}}, path)
+
+
+def model_from_checkpoint(model_cfg, ckpt, map_location="cpu", **model_kwargs):
+    """Build ``gomavatar_b200.model.Model`` from a reference checkpoint (a path or the loaded dict) and load it.
+
+    The reference resumes by REPLAYING its mesh subdivisions (``model.subdivide()`` for every ``subdivide_iters`` entry passed,
+    train.py:275-279; trimesh-based) so that the parameter shapes match before ``load_state_dict``.  The subdivided topology
+    is itself part of the checkpoint — ``faces``, ``lbs_weights`` and ``vertices`` are registered buffers / parameters
+    (models/model.py:58-85, :151-170) — so the model is constructed from those tensors directly, whatever number of
+    subdivisions produced them.  Returns (model, iteration)."""
+    import torch
+    from .model import Model
+    if isinstance(ckpt, (str, os.PathLike)):
+        ckpt = torch.load(ckpt, map_location=map_location, weights_only=False)
+    sd = ckpt["network"] if "network" in ckpt else ckpt
+    info = {"canonical_vertex": sd["vertices"].detach().cpu().numpy().T.copy(),
+            "canonical_lbs_weights": sd["lbs_weights"].detach().cpu().numpy()[:-1].T.copy(),
+            "faces": sd["faces"].detach().cpu().numpy()}
+    model = Model(model_cfg, info, **model_kwargs)
+    missing, unexpected = model.load_state_dict(sd, strict=False)
+    if missing or unexpected:
+        raise KeyError(f"checkpoint does not match the model built from cfg: missing {list(missing)}, unexpected {list(unexpected)}")
+    return model, int(ckpt.get("iter", 0)) if isinstance(ckpt, dict) else 0

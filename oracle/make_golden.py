@@ -300,3 +300,68 @@ def modules_golden():
 
 if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "modules":
     modules_golden()
+
+
+def dataset_golden():
+    """``golden_dataset.npz``: the reference's OWN reader (``dataset/train.py::Dataset``, imported unchanged) run on the folder
+    that ``gomavatar_b200.dataset_io.write_synthetic_dataset`` wrote (oracle/dataset_fixture.py).  OpenCV is absent offline:
+    ``cv2`` is a stub whose Rodrigues is exact axis-angle, whose undistort is the identity (the fixture has zero
+    distortion) and whose resize refuses to resample (the fixture is read at its native size) — none of them changes a
+    value.  ``termcolor`` (imported by utils/image_util.py for log colouring) is an empty stub."""
+    import tempfile
+    from oracle import dataset_fixture as DF
+
+    def rodrigues(rvec):
+        v = np.asarray(rvec, dtype=np.float64).reshape(3)
+        th = float(np.linalg.norm(v))
+        if th < 1e-12:
+            return (np.eye(3), None)
+        k = v / th
+        K = np.array([[0, -k[2], k[1]], [k[2], 0, -k[0]], [-k[1], k[0], 0]])
+        return (np.cos(th) * np.eye(3) + np.sin(th) * K + (1 - np.cos(th)) * np.outer(k, k), None)
+
+    def undistort(img, K, D):
+        assert not np.any(np.asarray(D) != 0)
+        return img
+
+    def resize(img, size, **kw):
+        assert size is not None and tuple(size) == (img.shape[1], img.shape[0]), "the fixture is read at its native size"
+        return img
+
+    _stub_module("cv2", Rodrigues=rodrigues, undistort=undistort, resize=resize, INTER_LANCZOS4=4, INTER_LINEAR=1)
+    _stub_module("termcolor", colored=lambda s, *a, **k: s)
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    import importlib
+    ref_train = importlib.import_module("dataset.train")
+    out = {}
+    with tempfile.TemporaryDirectory() as tmp:
+        DF.build(tmp)
+        ds = ref_train.Dataset(tmp, bgcolor=[255.0, 128.0, 0.0], target_size=[DF.W, DF.H])
+        assert len(ds) == DF.N_FRAMES
+        for i in range(len(ds)):
+            item = ds[i]
+            for k, v in item.items():
+                if k == "frame_name":
+                    out[f"item{i}.frame_name"] = np.array(v)
+                else:
+                    out[f"item{i}.{k}"] = np.asarray(v)
+        info = ds.get_canonical_info()
+        for k, v in info.items():
+            if isinstance(v, dict):
+                for kk, vv in v.items():
+                    out[f"info.{k}.{kk}"] = np.asarray(vv)
+            elif v is not None:
+                out[f"info.{k}"] = np.asarray(v)
+        # the random-crop branch, under a fixed numpy seed
+        np.random.seed(3)
+        dc = ref_train.Dataset(tmp, bgcolor=[0.0, 0.0, 0.0], target_size=[DF.W, DF.H], crop_size=[32, 24])
+        item = dc[1]
+        for k in ("K", "target_rgbs", "target_masks"):
+            out[f"crop.{k}"] = np.asarray(item[k])
+    np.savez_compressed(os.path.join(OUT, "golden_dataset.npz"), **out)
+    print("golden_dataset.npz:", len(out), "arrays")
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "dataset":
+    dataset_golden()

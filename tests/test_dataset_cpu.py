@@ -1,0 +1,133 @@
+"""CPU: on-disk compatibility (gomavatar_b200/dataset_io.py).
+
+tests/golden/golden_dataset.npz holds what the reference's OWN reader (dataset/train.py::Dataset, run by
+oracle/make_golden.py::dataset_golden) returned for the folder that ``write_synthetic_dataset`` wrote from the seeded
+fixture of oracle/dataset_fixture.py.  Here the same folder is written again and read with ``dataset_io.Dataset``: every item
+field, the canonical info and the random-crop branch must agree; and the items must feed ``Model`` (shapes / dtypes)."""
+import os
+import pickle
+
+import numpy as np
+import pytest
+
+from gomavatar_b200 import dataset_io as IO
+from oracle import dataset_fixture as DF
+
+
+@pytest.fixture(scope="module")
+def folder(tmp_path_factory):
+    path = str(tmp_path_factory.mktemp("dataset"))
+    fixture = DF.build(path)
+    return path, fixture
+
+
+@pytest.fixture(scope="module")
+def gold(golden_dir):
+    return np.load(os.path.join(golden_dir, "golden_dataset.npz"))
+
+
+def test_folder_has_the_reference_layout(folder):
+    path, (scene, poses, cams, images, masks) = folder
+    assert sorted(os.listdir(path)) == ["avg_betas.npy", "cameras.pkl", "canonical_joints.pkl", "images", "masks", "mesh_infos.pkl"]
+    cams_pkl = pickle.load(open(os.path.join(path, "cameras.pkl"), "rb"))
+    mesh_pkl = pickle.load(open(os.path.join(path, "mesh_infos.pkl"), "rb"))
+    cj = pickle.load(open(os.path.join(path, "canonical_joints.pkl"), "rb"))
+    names = sorted(cams_pkl)
+    assert names == sorted(mesh_pkl) == [f"frame_{i:06d}" for i in range(DF.N_FRAMES)]
+    assert set(cams_pkl[names[0]]) == {"intrinsics", "extrinsics", "distortions"}          # prepare_dataset.py:143-147
+    assert set(mesh_pkl[names[0]]) == {"Rh", "Th", "poses", "joints", "tpose_joints"}      # :152-158
+    assert set(cj) == {"vertex", "joints", "weights", "edges", "faces"}                    # :188-196
+    assert cj["weights"].shape == (scene.n_vertices, 24) and mesh_pkl[names[0]]["poses"].shape == (72,)
+
+
+def test_items_equal_the_reference_reader(folder, gold):
+    path, _ = folder
+    ds = IO.Dataset(path, bgcolor=[255.0, 128.0, 0.0], target_size=[DF.W, DF.H])
+    assert len(ds) == DF.N_FRAMES
+    for i in range(len(ds)):
+        item = ds[i]
+        keys = {k[len(f"item{i}."):] for k in gold.files if k.startswith(f"item{i}.")}
+        assert set(item) == keys, (set(item) ^ keys)
+        assert item["frame_name"] == str(gold[f"item{i}.frame_name"])
+        for k in keys - {"frame_name"}:
+            ref, got = gold[f"item{i}.{k}"], np.asarray(item[k])
+            assert got.shape == ref.shape and got.dtype == ref.dtype, (k, got.shape, ref.shape, got.dtype, ref.dtype)
+            tol = 0 if k in ("target_rgbs", "target_masks", "bgcolor", "dst_poses", "dst_tpose_joints", "dst_posevec") else 2e-6
+            assert np.abs(got.astype(np.float64) - ref.astype(np.float64)).max() <= tol, (k, np.abs(got - ref).max())
+    # the model's inputs come out in the shapes train.py batches (then [1, ...] after the DataLoader)
+    item = ds[0]
+    assert item["K"].shape == (3, 3) and item["E"].shape == (4, 4) and item["cnl_gtfms"].shape == (24, 4, 4)
+    assert item["dst_Rs"].shape == (24, 3, 3) and item["dst_Ts"].shape == (24, 3) and item["dst_posevec"].shape == (69,)
+    assert item["target_rgbs"].shape == (DF.H, DF.W, 3) and item["target_masks"].shape == (DF.H, DF.W)
+
+
+def test_stored_extrinsics_round_trip_through_the_global_transform(folder):
+    path, (scene, poses, cams, images, masks) = folder
+    ds = IO.Dataset(path, bgcolor=[0.0, 0.0, 0.0], target_size=[DF.W, DF.H])
+    for i in range(len(ds)):                              # the writer stored E G; the reader's E inv(G) gives the model's E back
+        np.testing.assert_allclose(ds[i]["E"], cams[i][1], atol=2e-6)
+        np.testing.assert_allclose(ds[i]["K"], cams[i][0], atol=1e-6)
+
+
+def test_canonical_info_and_crop_branch_equal_the_reference_reader(folder, gold):
+    path, (scene, *_rest) = folder
+    ds = IO.Dataset(path, bgcolor=[0.0, 0.0, 0.0], target_size=[DF.W, DF.H], crop_size=[32, 24])
+    info = ds.get_canonical_info()
+    for k in gold.files:
+        if not k.startswith("info."):
+            continue
+        parts = k.split(".")[1:]
+        got = info[parts[0]] if len(parts) == 1 else info[parts[0]][parts[1]]
+        np.testing.assert_allclose(np.asarray(got, dtype=np.float64), gold[k].astype(np.float64), atol=1e-7)
+    np.random.seed(3)                                     # same seed as the golden run: same crop window
+    item = ds[1]
+    for k in ("K", "target_rgbs", "target_masks"):
+        assert item[k].shape == gold[f"crop.{k}"].shape
+        assert np.abs(np.asarray(item[k], dtype=np.float64) - gold[f"crop.{k}"]).max() <= 1e-6, k
+    # the canonical info builds the model (CPU construction only; the kernels need a GPU)
+    from gomavatar_b200.model import Model, default_model_cfg
+    m = Model(default_model_cfg(img_size=(DF.W, DF.H)), info)
+    assert m.vertices.shape == (3, scene.n_vertices) and m.lbs_weights.shape == (25, scene.n_vertices)
+
+
+def test_distorted_cameras_are_refused_not_silently_ignored(folder, tmp_path):
+    import shutil
+    path, _ = folder
+    p2 = str(tmp_path / "d")
+    shutil.copytree(path, p2)
+    cams = pickle.load(open(os.path.join(p2, "cameras.pkl"), "rb"))
+    cams["frame_000000"]["distortions"] = np.array([0.1, 0, 0, 0, 0.0])
+    pickle.dump(cams, open(os.path.join(p2, "cameras.pkl"), "wb"))
+    ds = IO.Dataset(p2, bgcolor=[0.0, 0.0, 0.0], target_size=[DF.W, DF.H])
+    with pytest.raises(NotImplementedError):
+        ds[0]
+    ds[1]
+
+
+def test_checkpoint_round_trip_in_the_reference_format_including_a_subdivided_mesh(tmp_path):
+    """{'iter', 'network', 'optimizer'} like train.py:289-294; a checkpoint taken after a subdivision (4x the faces) is
+    restored from its own faces / lbs_weights / vertices tensors, no subdivision replay."""
+    import torch
+    from gomavatar_b200 import synthetic as S
+    from gomavatar_b200.model import Model
+    cfg = {"img_size": [64, 64], "canonical_geometry": {"sigma": 1e-3, "radius_scale": 1.0, "deform_scale": True, "deform_so3": True},
+           "appearance": {"color_init": 0.5},
+           "shadow_module": {"name": "basic", "mlp_width": 128, "mlp_depth": 3, "skips": [4], "multires": 6},
+           "normal_renderer": {"name": "mesh", "soft_mask": True, "sigma": 1e-5}}
+    for n_faces in (2000, 8000):                           # 8000 stands for "after one subdivision of the 2000-face mesh"
+        scene = S.make_humanoid(n_faces, seed=0)
+        torch.manual_seed(n_faces)
+        m = Model(cfg, scene.canonical_info())
+        with torch.no_grad():
+            m.so3.normal_(0, 0.1)
+            m.appearance_module.appearance.uniform_(0, 1)
+        path = str(tmp_path / f"iter_{n_faces}.pt")
+        IO.save_checkpoint(path, m, optimizer_state={"state": {}, "param_groups": []}, n_iter=1234)
+        raw = torch.load(path, weights_only=False)
+        assert set(raw) == {"iter", "network", "optimizer"} and raw["iter"] == 1234
+        m2, it = IO.model_from_checkpoint(cfg, path)
+        assert it == 1234 and m2.faces.shape[0] == n_faces
+        sd, sd2 = m.state_dict(), m2.state_dict()
+        assert set(sd) == set(sd2)
+        for k in sd:
+            assert torch.equal(sd[k], sd2[k]), k
