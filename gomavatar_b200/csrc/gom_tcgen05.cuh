@@ -45,7 +45,7 @@ __device__ __forceinline__ bool mbar_wait(uint64_t *bar, uint32_t parity, volati
         if (mbar_try_wait(bar, parity)) return true;
         if ((spin & 255u) == 0u) {
             if (*abort_flag) return false;
-            if (clock64() - t0 > 400000000ll) { *abort_flag = 1; return false; }
+            if (clock64() - t0 > 2000000000ll) { *abort_flag = 1; return false; }     // ~1 s: far beyond any legitimate wait
         }
     }
 }

@@ -94,6 +94,8 @@ class _ShadowMlp(torch.autograd.Function):
                 continue
             break
         if need_grad:
+            ws["generation"] = ws.get("generation", 0) + 1          # the saved operand images live in the shared workspace
+            ctx.generation = ws["generation"]
             ctx.module, ctx.depth, ctx.ws = module, depth, ws
             ctx.fwd_args = (W_in, b_in, W_hid, b_hid, wo, bo)
             ctx.save_for_backward(normals, out)
@@ -102,6 +104,9 @@ class _ShadowMlp(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_out):
         module, depth, ws = ctx.module, ctx.depth, ctx.ws
+        if ws.get("generation") != ctx.generation:
+            raise _lib.GomError("FusedShadowModule: another forward pass with gradients ran on this module before this backward; "
+                                "its saved activations were overwritten (use one module instance per concurrent graph)")
         normals, out = ctx.saved_tensors
         W_in, b_in, W_hid, b_hid, wo, bo = ctx.fwd_args
         dev = normals.device

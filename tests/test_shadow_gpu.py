@@ -209,3 +209,15 @@ def test_forward_and_backward_replay_from_a_cuda_graph():
     ref = [oe.detach(), xe.grad] + [p.grad for p in e.parameters()]
     for a, b in zip(got, ref):
         assert torch.equal(a, b)
+
+
+def test_backward_after_a_second_forward_is_refused():
+    """the saved operand images live in the module's workspace: a stale backward must fail loudly, not return wrong gradients"""
+    m = _trained_like(FusedShadowModule(_cfg()), seed=3).to(DEV)
+    x1 = _normals(2000, 0.5, seed=1).to(DEV).requires_grad_(True)
+    x2 = _normals(2000, 0.5, seed=2).to(DEV).requires_grad_(True)
+    o1 = m(x1[None]).sum()
+    o2 = m(x2[None]).sum()
+    o2.backward()
+    with pytest.raises(_lib.GomError):
+        o1.backward()
