@@ -16,8 +16,8 @@
 //                  TF32 tensor rate instead of the FFMA rate.  The last layer (128 -> 1) and the sigmoid are done in
 //                  registers.
 //   backward:   4. when a backward pass will follow, the forward also writes every operand it formed (encoding and
-//                  post-ReLU activations, already split into hi/lo) as ready-made K-major SWIZZLE_128B "activation
-//                  images" [feature][pixel row] per 32-row block, so that later kernels consume them with 1-D TMA;
+//                  post-ReLU activations, fp32) as ready-made K-major SWIZZLE_128B "activation images"
+//                  [feature][pixel row] per 32-row block, so that later kernels consume them with 1-D TMA;
 //               5. k_shadow_bwd_data: the same pipeline run backwards (dZ_l = (dZ_{l+1} W_{l+1}) * [H_l > 0], transposed
 //                  weight images), ending in the positional-encoding backward -> dL/dnormal; it writes dZ_l images;
 //               6. k_shadow_bwd_weights: split-K GEMMs dW_l = dZ_l^T H_{l-1} (both operands are the saved images, both
@@ -66,17 +66,17 @@ struct ShadowDev {
 // ------------------------------------------------------------------------------------------- activation images
 // One tile (128 pixel rows) of saved operands, in 32-bit words.  Row block kb = rows 32 kb .. 32 kb + 31 of the tile
 // (= the epilogue warp kb); inside an image, element (feature j, row-in-block q) sits at word swz(j, q): row j of a
-// K-major SWIZZLE_128B matrix whose K index is the pixel row.
-//   act tile: [slot 0 (encoding, 64 features): 4 blocks x (hi 2048 | lo 2048)] [slot s = 1..depth (H_s, 128 features):
-//             4 blocks x (hi 4096 | lo 4096)]
-//   dz tile:  [layer l = 0..depth-1 (dZ_l, 128 features): 4 blocks x (hi 4096 | lo 4096)] [dz_out, 16 rows of which row 0
-//             is used: 4 blocks x (hi 512 | lo 512)]
-__host__ __device__ __forceinline__ size_t act_tile_words(int depth) { return 16384 + (size_t)depth * 32768; }
-__host__ __device__ __forceinline__ size_t dz_tile_words(int depth) { return (size_t)depth * 32768 + 4096; }
+// K-major SWIZZLE_128B matrix whose K index is the pixel row.  Images hold the fp32 VALUES (one copy): the tensor core
+// ignores the 13 low mantissa bits of a TF32 operand, so an image is its own "hi" part and k_shadow_bwd_weights forms
+// lo = v - trunc(v) in shared memory next to it (storing hi and lo separately doubled the HBM bytes of three kernels).
+//   act tile: [slot 0 (encoding, 64 features): 4 blocks x 2048] [slot s = 1..depth (H_s, 128 features): 4 blocks x 4096]
+//   dz tile:  [layer l = 0..depth-1 (dZ_l, 128 features): 4 blocks x 4096] [dz_out, 16 rows of which row 0 is used: 4 x 512]
+__host__ __device__ __forceinline__ size_t act_tile_words(int depth) { return 8192 + (size_t)depth * 16384; }
+__host__ __device__ __forceinline__ size_t dz_tile_words(int depth) { return (size_t)depth * 16384 + 2048; }
 __host__ __device__ __forceinline__ size_t act_slot_block(int slot, int kb) {       // word offset of (slot, kb) in an act tile
-    return slot == 0 ? (size_t)kb * 4096 : 16384 + (size_t)(slot - 1) * 32768 + (size_t)kb * 8192;
+    return slot == 0 ? (size_t)kb * 2048 : 8192 + (size_t)(slot - 1) * 16384 + (size_t)kb * 4096;
 }
-__host__ __device__ __forceinline__ size_t act_slot_half(int slot) { return slot == 0 ? 2048 : 4096; }   // hi -> lo distance
+__host__ __device__ __forceinline__ size_t act_slot_words(int slot) { return slot == 0 ? 2048 : 4096; }   // words of one image
 __device__ __forceinline__ int swz(int j, int q) { return j * 32 + ((((q >> 2) ^ (j & 7)) << 2) | (q & 3)); }
 
 // number of 32-column K-blocks of layer l and the images before it
@@ -367,14 +367,14 @@ __global__ void __launch_bounds__(kThreads, 1) k_shadow_fwd(ShadowDev a) {
         const size_t act_words = act_tile_words(depth);
         uint32_t g = 0;
 
-        // Split one feature block (32 columns) of `v` into TF32 hi/lo; store it as A operand columns [32 fb, 32 fb + 32)
-        // (to_tmem) and, when a backward pass will follow, into the activation image `img` (word pointer to the hi part
-        // of (slot, row block = this warp); the lo part is `half` words further).
-        auto store_block = [&](const float *v, int fb, bool to_tmem, uint32_t *img, size_t half) {
-            uint32_t hi[32], lo[32];
-#pragma unroll
-            for (int j = 0; j < 32; j++) split_tf32(v[j], hi[j], lo[j]);
+        // Split one feature block (32 columns) of `v` into TF32 hi/lo and store it as A operand columns [32 fb, 32 fb + 32)
+        // (to_tmem); when a backward pass will follow, also store the fp32 values into the activation image `img` of
+        // (slot, row block = this warp).
+        auto store_block = [&](const float *v, int fb, bool to_tmem, uint32_t *img) {
             if (to_tmem) {
+                uint32_t hi[32], lo[32];
+#pragma unroll
+                for (int j = 0; j < 32; j++) split_tf32(v[j], hi[j], lo[j]);
                 tmem_st16(tl + kColAhi + fb * 32, hi);
                 tmem_st16(tl + kColAhi + fb * 32 + 16, hi + 16);
                 tmem_st16(tl + kColAlo + fb * 32, lo);
@@ -382,11 +382,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_shadow_fwd(ShadowDev a) {
             }
             if (SAVE && img) {
 #pragma unroll
-                for (int j = 0; j < 32; j++) {
-                    const int w = swz(fb * 32 + j, lane);
-                    img[w] = hi[j];
-                    img[half + w] = lo[j];
-                }
+                for (int j = 0; j < 32; j++) img[swz(fb * 32 + j, lane)] = __float_as_uint(v[j]);
             }
         };
         auto act_img_ptr = [&](int t, int slot) -> uint32_t * {        // image of (tile t, slot, row block = this warp)
@@ -395,8 +391,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_shadow_fwd(ShadowDev a) {
         };
         auto publish_encoding = [&](const float *enc, int t) {          // layer-0 operand of tile t, then release all four
             uint32_t *img = act_img_ptr(t, 0);
-            store_block(enc, 0, true, img, act_slot_half(0));
-            store_block(enc + 32, 1, true, img, act_slot_half(0));
+            store_block(enc, 0, true, img);
+            store_block(enc + 32, 1, true, img);
             tmem_wait_st();
             tc_fence_before();
 #pragma unroll
@@ -439,7 +435,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_shadow_fwd(ShadowDev a) {
 #pragma unroll
                         for (int j = 0; j < 32; j++) h[j] = fmaxf(__uint_as_float(z[j]) + s_bias[l * kWidth + fb * 32 + j], 0.f);
                         if (fb < 3) tmem_ld32(dcol + (fb + 1) * 32, z);      // next block's accumulator behind this block's work
-                        store_block(h, fb, true, img, act_slot_half(1));
+                        store_block(h, fb, true, img);
                         tmem_wait_st();
                         tc_fence_before();
                         mbar_arrive(&a_ready[fb]);
@@ -463,7 +459,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_shadow_fwd(ShadowDev a) {
                             acc = fmaf(h[j], s_wout[fb * 32 + j], acc);
                         }
                         if (fb < 3) tmem_ld32(dcol + (fb + 1) * 32, z);
-                        if (SAVE) store_block(h, fb, false, img, act_slot_half(1));
+                        if (SAVE) store_block(h, fb, false, img);
                     }
                     if (valid) a.out[pix] = 1.f / (1.f + expf(-(acc + s_bout)));
                     tc_fence_before();      // orders these tcgen05.ld before the a_ready arrivals of the next tile's layer 0
@@ -572,15 +568,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_shadow_bwd_data(ShadowDev a) {
             tmem_st16(tl + kColAhi + fb * 32 + 16, hi + 16);
             tmem_st16(tl + kColAlo + fb * 32, lo);
             tmem_st16(tl + kColAlo + fb * 32 + 16, lo + 16);
-            uint32_t *img = a.dz_img + (size_t)t * dz_words + (size_t)layer * 32768 + (size_t)warp * 8192;
+            uint32_t *img = a.dz_img + (size_t)t * dz_words + (size_t)layer * 16384 + (size_t)warp * 4096;
 #pragma unroll
-            for (int j = 0; j < 32; j++) {
-                const int w = swz(fb * 32 + j, lane);
-                img[w] = hi[j];
-                img[4096 + w] = lo[j];
-            }
+            for (int j = 0; j < 32; j++) img[swz(fb * 32 + j, lane)] = __float_as_uint(v[j]);
         };
-        // [H_slot > 0] of this row, features [32 fb, 32 fb + 32): hi words of the forward's activation image (hi > 0 <=> H > 0)
+        // [H_slot > 0] of this row, features [32 fb, 32 fb + 32), from the forward's activation image
         auto load_mask = [&](int t, int slot, int fb, uint32_t m[32]) {
             const uint32_t *img = a.act_img + (size_t)t * act_words + act_slot_block(slot, warp);
 #pragma unroll
@@ -588,11 +580,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_shadow_bwd_data(ShadowDev a) {
         };
         // first operand of a tile: dZ_{depth-1} = dz_out * w_out * [H_depth > 0]; also the dz_out image + its warp sum
         auto publish_first = [&](int t, float dzo) {
-            uint32_t dh, dl;
-            split_tf32(dzo, dh, dl);
-            uint32_t *dimg = a.dz_img + (size_t)t * dz_words + (size_t)depth * 32768 + (size_t)warp * 1024;
-            dimg[lane] = dh;                                   // row 0 of a 16-row image: swz(0, lane) = lane
-            dimg[512 + lane] = dl;
+            uint32_t *dimg = a.dz_img + (size_t)t * dz_words + (size_t)depth * 16384 + (size_t)warp * 512;
+            dimg[lane] = __float_as_uint(dzo);                 // row 0 of a 16-row image: swz(0, lane) = lane
             const float ws = warp_sum(dzo);
             if (lane == 0) a.dzo_sums[(size_t)t * 4 + warp] = ws;
 #pragma unroll 1
@@ -700,9 +689,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_shadow_bwd_data(ShadowDev a) {
 // ========================================================================================= backward: weight gradients
 // Job j < depth:  D_j[f, 16 + i] += sum_r dZ_j[r, f] * A_j[r, i]   (A_0 = encoding, A_j = H_j), D_j[f, 0] += sum_r dZ_j[r, f]
 // Job depth:      D[f, 16]       += sum_r H_depth[r, f] * dz_out[r]                                  (-> dL/dw_out)
-// Both operands of every job are saved images (K = pixel row), streamed with 1-D TMA; 16 constant rows in front of the B
-// image (row 0 = ones) give the bias gradients.  One accumulator per job lives in tensor memory for the whole kernel.
-constexpr int kB2StageBytes = 32768 + 36864;     // A image | [ones 2 KB | B hi 16 KB | zeros 2 KB | B lo 16 KB]
+// Both operands of every job are saved fp32 images (K = pixel row), streamed with 1-D TMA; the four otherwise idle epilogue
+// warps form the TF32 lo parts in shared memory; 16 constant rows in front of the B image (row 0 = ones) give the bias
+// gradients.  One accumulator per job lives in tensor memory for the whole kernel.
+constexpr int kB2StageBytes = 32768 + 36864;     // A v 16 KB | A lo 16 KB | [ones 2 KB | B v 16 KB | zeros 2 KB | B lo 16 KB]
 constexpr int kB2Stages = 3;
 constexpr int kB2BOff = 32768, kB2BLoOff = 32768 + 18432;
 constexpr int kPartialCols = 512;
@@ -711,7 +701,7 @@ __host__ __device__ __forceinline__ int job_cols(int job, int depth) { return jo
 __host__ __device__ __forceinline__ int job_col0(int job, int depth) { return job == 0 ? 0 : 80 + (job - 1) * 144; }
 __global__ void __launch_bounds__(kThreads, 1) k_shadow_bwd_weights(ShadowDev a) {
     extern __shared__ uint8_t smem_raw[];
-    __shared__ uint64_t full_bar[kB2Stages], empty_bar[kB2Stages], done_bar;
+    __shared__ uint64_t full_bar[kB2Stages], split_bar[kB2Stages], empty_bar[kB2Stages], done_bar;
     __shared__ uint32_t tmem_slot;
     __shared__ int abort_flag;
 
@@ -723,7 +713,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_shadow_bwd_weights(ShadowDev a)
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (threadIdx.x == 32) {
-        for (int s = 0; s < kB2Stages; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < kB2Stages; s++) { mbar_init(&full_bar[s], 1); mbar_init(&split_bar[s], kTileRows); mbar_init(&empty_bar[s], 1); }
         mbar_init(&done_bar, 1);
         abort_flag = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -758,17 +748,16 @@ __global__ void __launch_bounds__(kThreads, 1) k_shadow_bwd_weights(ShadowDev a)
                     for (int kb = 0; kb < 4; kb++, it++) {
                         const uint32_t s = it % kB2Stages, ph = (it / kB2Stages) & 1u;
                         if (!mbar_wait(&empty_bar[s], ph ^ 1u, ab)) { ok = false; break; }
-                        const uint32_t *A = (job < depth) ? dz + (size_t)job * 32768 + (size_t)kb * 8192
+                        const uint32_t *A = (job < depth) ? dz + (size_t)job * 16384 + (size_t)kb * 4096
                                                           : act + act_slot_block(depth, kb);
-                        const uint32_t *Bh;
-                        uint32_t part_words;                 // words of one part (hi or lo) of the B image
-                        if (job < depth) { Bh = act + act_slot_block(job, kb); part_words = (uint32_t)act_slot_half(job); }
-                        else { Bh = dz + (size_t)depth * 32768 + (size_t)kb * 1024; part_words = 512; }
+                        const uint32_t *B;
+                        uint32_t b_words;                    // words of the B image
+                        if (job < depth) { B = act + act_slot_block(job, kb); b_words = (uint32_t)act_slot_words(job); }
+                        else { B = dz + (size_t)depth * 16384 + (size_t)kb * 512; b_words = 512; }
                         const uint32_t sb = smem_u32(stages + (size_t)s * kB2StageBytes);
-                        mbar_expect_tx(&full_bar[s], 32768 + 8 * part_words);
-                        tma_bulk_g2s(sb, A, 32768, &full_bar[s]);
-                        tma_bulk_g2s(sb + kB2BOff + 2048, Bh, 4 * part_words, &full_bar[s]);
-                        tma_bulk_g2s(sb + kB2BLoOff + 2048, Bh + part_words, 4 * part_words, &full_bar[s]);
+                        mbar_expect_tx(&full_bar[s], 16384 + 4 * b_words);
+                        tma_bulk_g2s(sb, A, 16384, &full_bar[s]);
+                        tma_bulk_g2s(sb + kB2BOff + 2048, B, 4 * b_words, &full_bar[s]);
                     }
             }
         }
@@ -782,7 +771,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_shadow_bwd_weights(ShadowDev a)
                     const uint32_t idesc = instr_desc_n(job_cols(job, depth));
                     for (int kb = 0; kb < 4; kb++, it++) {
                         const uint32_t s = it % kB2Stages, ph = (it / kB2Stages) & 1u;
-                        if (!mbar_wait(&full_bar[s], ph, ab)) { ok = false; break; }
+                        if (!mbar_wait(&split_bar[s], ph, ab)) { ok = false; break; }      // images landed AND lo parts formed
                         tc_fence_after();
                         const uint32_t sb = smem_u32(stages + (size_t)s * kB2StageBytes);
                         for (int ks = 0; ks < 4; ks++) {
@@ -798,6 +787,37 @@ __global__ void __launch_bounds__(kThreads, 1) k_shadow_bwd_weights(ShadowDev a)
             if (ok && has_work) tc_commit(&done_bar);
         }
     } else {
+        // splitters: the TMA delivered fp32 images, which the tensor core reads as their own TF32 "hi" part (it ignores the
+        // 13 low mantissa bits); lo = v - trunc(v) is formed here, element for element at the same swizzled position, in
+        // the lo halves of the stage (exact: <= 13 significant bits)
+        {
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < n_tiles && ok; tile += gridDim.x)
+                for (int job = 0; job < n_jobs && ok; job++) {
+                    const int b_vec = (job < depth ? (int)act_slot_words(job) : 512) / 4;      // float4 of the B image
+                    for (int kb = 0; kb < 4; kb++, it++) {
+                        const uint32_t s = it % kB2Stages, ph = (it / kB2Stages) & 1u;
+                        if (!mbar_wait(&full_bar[s], ph, ab)) { ok = false; break; }
+                        uint8_t *st = stages + (size_t)s * kB2StageBytes;
+                        const uint4 *av = reinterpret_cast<const uint4 *>(st);
+                        uint4 *al = reinterpret_cast<uint4 *>(st + kHalfStage);
+                        const uint4 *bv = reinterpret_cast<const uint4 *>(st + kB2BOff + 2048);
+                        uint4 *bl = reinterpret_cast<uint4 *>(st + kB2BLoOff + 2048);
+                        auto lo_of = [](uint32_t v) { return __float_as_uint(__uint_as_float(v) - __uint_as_float(v & 0xFFFFE000u)); };
+#pragma unroll
+                        for (int i = 0; i < 8; i++) {                                           // 1024 float4 of A
+                            const uint4 v = av[i * kTileRows + threadIdx.x];
+                            al[i * kTileRows + threadIdx.x] = make_uint4(lo_of(v.x), lo_of(v.y), lo_of(v.z), lo_of(v.w));
+                        }
+                        for (int i = threadIdx.x; i < b_vec; i += kTileRows) {
+                            const uint4 v = bv[i];
+                            bl[i] = make_uint4(lo_of(v.x), lo_of(v.y), lo_of(v.z), lo_of(v.w));
+                        }
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                        mbar_arrive(&split_bar[s]);
+                    }
+                }
+        }
         // dump the accumulators: partials[cta][column][row f], zeros for a CTA that had no tile
         const int f = threadIdx.x;
         float *dst = a.partials + (size_t)blockIdx.x * kPartialCols * kTileRows + f;
