@@ -192,7 +192,7 @@ def compute_loss(rgbs, masks, bgcolors, rgb_gt, mask_gt, outputs, model, loss_cf
             model._unique_edges, model._unique_edges_faces = edges, faces
             model._vertex_degree = vertex_degree(edges, model.vertices.shape[1])
     if c_lap_c > 0:
-        add("laplacian_canonical", laplacian_smoothing(model.vertices.T, faces), c_lap_c)
+        add("laplacian_canoincal", laplacian_smoothing(model.vertices.T, faces), c_lap_c)      # (sic: the reference's key, train.py:125)
     if c_lap_o > 0:
         add("laplacian_observation", lap if fused else laplacian_smoothing(vo.permute(0, 2, 1), faces, edges, model._vertex_degree), c_lap_o)
     if c_nm > 0 and outputs.get("normal_mask") is not None:

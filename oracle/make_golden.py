@@ -365,3 +365,112 @@ def dataset_golden():
 
 if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "dataset":
     dataset_golden()
+
+
+def _extract_functions(path, names):
+    """Source text of the top-level functions `names` of a reference file, compiled in a namespace the caller fills —
+    the reference's own code is EXECUTED from where it lies (nothing is copied into this repository) without importing
+    the file's unsatisfiable module-level dependencies (tensorboard, pytorch3d, seaborn, skimage ...)."""
+    import ast
+    src = open(path).read()
+    tree = ast.parse(src)
+    out = {}
+    for node in tree.body:
+        if isinstance(node, ast.FunctionDef) and node.name in names:
+            out[node.name] = ast.get_source_segment(src, node)
+    assert set(out) == set(names), (set(names) - set(out))
+    return out
+
+
+class _LossMeshes(_Meshes):
+    """+ what reference utils/network_util.py::mesh_laplacian_smoothing asks of pytorch3d Meshes (uniform Laplacian
+    L = D^-1 A - I as a sparse matrix: pytorch3d/structures/meshes.py::laplacian_packed, restated)."""
+    device = torch.device("cpu")
+
+    def isempty(self):
+        return False
+
+    def __len__(self):
+        return 1
+
+    def num_verts_per_mesh(self):
+        return torch.tensor([self.v.shape[0]])
+
+    def verts_packed_to_mesh_idx(self):
+        return torch.zeros(self.v.shape[0], dtype=torch.long)
+
+    def laplacian_packed(self):
+        e = self.edges_packed()
+        V = self.v.shape[0]
+        idx = torch.cat([e.t(), e.flip(1).t()], dim=1)                        # both directions
+        A = torch.sparse_coo_tensor(idx, torch.ones(idx.shape[1]), (V, V)).coalesce()
+        deg = torch.sparse.sum(A, dim=1).to_dense()
+        w = 1.0 / deg[idx[0]]
+        L = torch.sparse_coo_tensor(idx, w, (V, V))
+        L = L - torch.sparse_coo_tensor(torch.arange(V).repeat(2, 1), torch.ones(V), (V, V))
+        return L.coalesce()
+
+
+def loss_golden():
+    """``golden_loss.npz``: the reference's OWN ``unpack`` + ``compute_loss`` (train.py:53-55, :98-163), its own
+    ``mesh_laplacian_smoothing`` / ``mesh_color_consistency`` (utils/network_util.py:669-799) and its own LPIPS (random trunk
+    under seed 0, in-tree heads) on seeded inputs, with the loss coefficients of exps/zju-mocap_377.yaml.  Stand-ins: the
+    Meshes object (stub above) and ``pytorch3d.loss.mesh_normal_consistency`` (absent offline; the torch definition of
+    gomavatar_b200/regularizers.py, i.e. that ONE term is circular and says so)."""
+    import types as _t
+    import torch.nn.functional as F
+    from gomavatar_b200 import regularizers as RG
+    from gomavatar_b200 import synthetic as S
+    from gomavatar_b200.model import mesh_edges
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    src_train = _extract_functions(os.path.join(REF, "train.py"), ["unpack", "compute_loss"])
+    src_net = _extract_functions(os.path.join(REF, "utils", "network_util.py"), ["mesh_laplacian_smoothing", "mesh_color_consistency"])
+    ns = {"torch": torch, "F": F}
+    for s_ in src_net.values():
+        exec(s_, ns)
+    ns["mesh_normal_consistency"] = lambda mesh: RG.normal_consistency(mesh.verts_packed(), mesh.faces_packed(), mesh.conn)
+    for s_ in src_train.values():
+        exec(s_, ns)
+    from utils import lpips as ref_lpips
+    torch.manual_seed(0)
+    lp = ref_lpips.LPIPS(net="vgg", pnet_rand=True, verbose=False)
+
+    H = W = 64
+    scene = S.make_humanoid(2000, seed=0)
+    g = torch.Generator().manual_seed(21)
+    verts = torch.from_numpy(scene.vertices) + 0.004 * torch.randn(scene.n_vertices, 3, generator=g)
+    faces = torch.from_numpy(scene.faces).long()
+    _, conn = mesh_edges(scene.faces.astype(np.int64), scene.vertices)
+    conn = torch.from_numpy(conn)
+    mesh = _LossMeshes(verts[None], faces[None])
+    mesh.conn = conn
+    yy, xx = torch.meshgrid(torch.arange(H), torch.arange(W), indexing="ij")
+    blob = (((xx - 30) ** 2 / 1.5 + (yy - 34) ** 2) < 18 ** 2).float()
+    rgb_raw = torch.rand(1, H, W, 3, generator=g) * blob[None, ..., None]
+    mask_pred = (blob[None] * (0.6 + 0.4 * torch.rand(1, H, W, generator=g))).clamp(0, 1)
+    bgcolor = torch.rand(1, 3, generator=g)
+    rgb_gt = torch.rand(1, H, W, 3, generator=g)
+    mask_gt = (((xx - 32) ** 2 + (yy - 32) ** 2) < 17 ** 2).float()[None]
+    normal_mask = (blob[None] * torch.rand(1, H, W, generator=g)).clamp(0, 1)
+    colors = torch.rand(scene.n_faces, 3, generator=g)
+    cfgl = _t.SimpleNamespace(rgb=_t.SimpleNamespace(coeff=1.0), mask=_t.SimpleNamespace(coeff=5.0), lpips=_t.SimpleNamespace(coeff=1.0),
+                              laplacian=_t.SimpleNamespace(coeff_canonical=0.0, coeff_observation=10.0),
+                              normal=_t.SimpleNamespace(mask_dilate=True, kernel_size=7, coeff_mask=1.0, coeff_consist=0.10),
+                              color_consist=_t.SimpleNamespace(coeff=0.050))
+    outputs = {"mesh": mesh, "mesh_canonical": mesh, "normal_mask": normal_mask, "colors": colors, "face_connectivity": conn}
+    with torch.no_grad():
+        rgb = ns["unpack"](rgb_raw, mask_pred, bgcolor)
+        total, losses = ns["compute_loss"](rgb, mask_pred, outputs, rgb_gt, mask_gt, cfgl, None, 0, lpips_func=lp)
+    out = {"verts": verts.numpy(), "faces": scene.faces.astype(np.int64), "face_connectivity": conn.numpy(), "rgb_raw": rgb_raw.numpy(),
+           "mask_pred": mask_pred.numpy(), "bgcolor": bgcolor.numpy(), "rgb_gt": rgb_gt.numpy(), "mask_gt": mask_gt.numpy(),
+           "normal_mask": normal_mask.numpy(), "colors": colors.numpy(), "total": np.float64(total)}
+    for k, v in losses.items():
+        out[f"unscaled.{k}"] = np.float64(v["unscaled"])
+        out[f"scaled.{k}"] = np.float64(v["scaled"])
+    np.savez_compressed(os.path.join(OUT, "golden_loss.npz"), **out)
+    print("golden_loss.npz:", {k: float(v["unscaled"]) for k, v in losses.items()}, "total", float(total))
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "loss":
+    loss_golden()

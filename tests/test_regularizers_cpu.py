@@ -63,3 +63,17 @@ def test_color_consistency_and_normal_mask():
     nm = torch.zeros(1, 16, 16)
     assert abs(float(RG.normal_mask_loss(nm, m, 7)) - 49 / 256) < 1e-7               # a point dilates to 7x7
     assert abs(float(RG.normal_mask_loss(nm, m, 7, dilate=False)) - 1 / 256) < 1e-7
+
+
+def test_torch_definitions_equal_the_reference_functions(golden_dir):
+    """tests/golden/golden_loss.npz holds what the reference's OWN mesh_laplacian_smoothing / mesh_color_consistency
+    (utils/network_util.py:669-799, executed by oracle/make_golden.py::loss_golden) and the normal-mask term of its
+    compute_loss (train.py:137-146) returned on seeded inputs."""
+    import os
+    g = np.load(os.path.join(golden_dir, "golden_loss.npz"))
+    v, f, conn = t(g["verts"]), t(g["faces"]), t(g["face_connectivity"])
+    assert abs(float(RG.laplacian_smoothing(v, f)) - float(g["unscaled.laplacian_observation"])) <= 2e-6 * float(g["unscaled.laplacian_observation"])
+    assert abs(float(RG.color_consistency(t(g["colors"]), conn)) - float(g["unscaled.color_consist"])) <= 1e-6
+    assert abs(float(RG.normal_mask_loss(t(g["normal_mask"]), t(g["mask_gt"]), 7, True)) - float(g["unscaled.normal_mask"])) <= 1e-6
+    # (normal_consist in that file comes from RG.normal_consistency itself: PyTorch3D's loss is absent offline)
+    assert abs(float(RG.normal_consistency(v, f, conn)) - float(g["unscaled.normal_consist"])) <= 1e-6

@@ -59,3 +59,33 @@ def test_single_terms_and_compute_loss_route():
     assert float(nc) == 0.0 and float(cc) == 0.0
     ref = RG.laplacian_smoothing(x[0].t().double(), faces)
     assert abs(float(lap) - float(ref)) <= 2e-5 * float(ref)
+
+
+def test_compute_loss_equals_the_reference_compute_loss(golden_dir):
+    """regularizers.compute_loss (unpack + L1 rgb / mask kernels + LPIPS + fused regulariser kernels + dilated normal-mask L1)
+    against the reference's own unpack + compute_loss (train.py:53-55, :98-163) run by oracle/make_golden.py::loss_golden
+    with the coefficients of exps/zju-mocap_377.yaml: every term, its scaling and the total."""
+    import os
+    import types
+    from gomavatar_b200.lpips import LPIPS, seeded_random_trunk
+    g = np.load(os.path.join(golden_dir, "golden_loss.npz"))
+    heads = np.load(os.path.join(golden_dir, "golden_lpips.npz"))
+    lp = LPIPS(seeded_random_trunk(0), [heads[f"lin{k}"] for k in range(5)], conv_precision="fp32").to(DEV)
+    d = lambda k: t(g[k]).to(DEV)
+    verts = d("verts").float()
+    model = types.SimpleNamespace(faces=d("faces").long(), vertices=verts.t().contiguous())
+    outputs = {"vertices_observation": verts.t()[None].contiguous(), "colors": d("colors").float(),
+               "face_connectivity": d("face_connectivity").long(), "normal_mask": d("normal_mask").float()}
+    cfg = {"rgb": {"coeff": 1.0}, "mask": {"coeff": 5.0}, "lpips": {"coeff": 1.0},
+           "laplacian": {"coeff_canonical": 0.0, "coeff_observation": 10.0},
+           "normal": {"mask_dilate": True, "kernel_size": 7, "coeff_mask": 1.0, "coeff_consist": 0.10}, "color_consist": {"coeff": 0.050}}
+    total, losses = RG.compute_loss(d("rgb_raw").float(), d("mask_pred").float(), d("bgcolor").float(), d("rgb_gt").float(),
+                                    d("mask_gt").float(), outputs, model, cfg, lpips_func=lp)
+    names = {k[len("unscaled."):] for k in g.files if k.startswith("unscaled.")}
+    assert set(losses) == names, set(losses) ^ names
+    for k in names:
+        for kind in ("unscaled", "scaled"):
+            ref, got = float(g[f"{kind}.{k}"]), float(losses[k][kind])
+            tol = 2e-4 if k == "lpips" else 2e-5                      # LPIPS: different convolution implementations
+            assert abs(got - ref) <= tol * abs(ref) + 1e-8, (k, kind, got, ref)
+    assert abs(float(total) - float(g["total"])) <= 5e-5 * float(g["total"])
