@@ -44,11 +44,14 @@ def make_problem(n_faces, img, n_frames, device, seed=0):
     return scene, model, frames, tgt_rgb, tgt_mask
 
 
-def train(model, frames, tgt_rgb, tgt_mask, iters, lpips=None, lr=5e-3, lr_decay=0.1, decay_steps=None, log=None):
-    arena = FlatArena(model)
-    groups = model.get_param_groups({"lr": {"appearance": lr, "canonical_geometry": lr, "canonical_geometry_xyz": lr * 0.1}})
-    opt = ArenaAdam(arena, groups)
-    base = [g["lr"] for g in opt.param_groups]
+def train(model, frames, tgt_rgb, tgt_mask, iters, lpips=None, lr=5e-3, lr_decay=0.1, decay_steps=None, log=None,
+          subdivide_iters=()):
+    def make_optimizer():                                         # also after every subdivision (reference train.py:343-346)
+        arena = FlatArena(model)
+        groups = model.get_param_groups({"lr": {"appearance": lr, "canonical_geometry": lr, "canonical_geometry_xyz": lr * 0.1}})
+        opt = ArenaAdam(arena, groups)
+        return arena, opt, [g["lr"] for g in opt.param_groups]
+    arena, opt, base = make_optimizer()
     history = []
     for it in range(iters):
         arena.zero_grad()
@@ -57,6 +60,11 @@ def train(model, frames, tgt_rgb, tgt_mask, iters, lpips=None, lr=5e-3, lr_decay
         loss, terms, rgb_u = compute_loss(rgb, mask, frames["bgcolor"], tgt_rgb, tgt_mask, lpips_func=lpips)
         loss.backward()
         opt.step(grad_scale=arena.all_reduce_sum())
+        if it in subdivide_iters:                                 # reference train.py:341-346 (cfg.model.subdivide_iters)
+            model.subdivide()
+            arena, opt, base = make_optimizer()
+            if log:
+                log(f"iter {it:5d}  subdivided: {model.vertices.shape[1]} vertices, {model.faces.shape[0]} faces")
         if decay_steps:                                           # reference train.py:166-175
             for g, b in zip(opt.param_groups, base):
                 g["lr"] = b * lr_decay ** (it / decay_steps)
@@ -77,6 +85,7 @@ if __name__ == "__main__":
     ap.add_argument("--img", type=int, default=256)
     ap.add_argument("--frames", type=int, default=4)
     ap.add_argument("--no-lpips", action="store_true")
+    ap.add_argument("--subdivide-iters", type=int, nargs="*", default=[])
     a = ap.parse_args()
     dev = torch.device("cuda:0")
     scene, model, frames, tgt_rgb, tgt_mask = make_problem(a.faces, a.img, a.frames, dev)
@@ -84,4 +93,5 @@ if __name__ == "__main__":
     if not a.no_lpips:
         heads = np.load(os.path.join(ROOT, "tests", "golden", "golden_lpips.npz"))
         lp = LPIPS(seeded_random_trunk(0), [heads[f"lin{k}"] for k in range(5)]).to(dev)
-    train(model.train(), frames, tgt_rgb, tgt_mask, a.iters, lpips=lp, decay_steps=a.iters, log=print)
+    train(model.train(), frames, tgt_rgb, tgt_mask, a.iters, lpips=lp, decay_steps=a.iters, log=print,
+          subdivide_iters=tuple(a.subdivide_iters))

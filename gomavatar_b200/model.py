@@ -101,6 +101,10 @@ class AppearanceModule(nn.Module):
     def forward(self, **kwargs):
         return self.appearance, self.bg_col
 
+    def set(self, appearance):
+        """reference appearance_module.py:22-23 — used by ``Model.subdivide``."""
+        self.appearance = nn.Parameter(appearance)
+
 
 class Model(nn.Module):
     def __init__(self, model_cfg, canonical_info, pose_refinement_module=None, non_rigid_module=None,
@@ -201,6 +205,35 @@ class Model(nn.Module):
             if normal is not None:
                 outputs["normal"], outputs["normal_mask"], outputs["shadow"] = normal, normal_mask[..., 0], shadings
         return rgbs, masks, outputs
+
+    def subdivide(self, need_face_connectivity=True):
+        """reference models/model.py:136-179: split every face into 4 at its edge midpoints (subdivision.py mirrors
+        utils/pc_util.py::subdivide).  New vertices take the mean position and the mean LBS weights of their edge's end
+        points; per-face parameters (so3, scale, colour) are repeated for the 4 children; ``target_edge_length`` and
+        ``face_connectivity`` are rebuilt (``need_face_connectivity=False``, eval.py:305, leaves zeros like the
+        reference).  Every trainable tensor is a NEW ``nn.Parameter`` afterwards, so the caller re-creates its optimizer
+        (train.py:343-346) — and its ``dist.FlatArena`` — exactly as with the reference.  Deterministic host code: all
+        ranks of a frame-sharded run call it at the same iteration and stay identical without communication.
+        One deviation: the reference's ``target_edge_length`` turns float64 here (``torch.tensor`` of trimesh's float64
+        vertices, model.py:174-177); it stays float32 like before the subdivision."""
+        from .subdivision import subdivide_mesh
+        dev = self.vertices.device
+        v_new, f_new, attrs, _ = subdivide_mesh(self.vertices.detach().T.cpu().numpy(), self.faces.cpu().numpy(),
+                                                {"weights": self.lbs_weights.detach().T.cpu().numpy()})
+        rep4 = lambda t: t.detach()[..., None].repeat(1, 1, 4).reshape(t.shape[0], -1).contiguous()
+        appearance, so3, scale = rep4(self.appearance_module.appearance), rep4(self.so3), rep4(self.scale)
+        f_new = f_new.astype(np.int64)
+        self.vertices = nn.Parameter(torch.from_numpy(v_new).float().T.contiguous().to(dev))
+        self.faces = torch.from_numpy(f_new).to(dev)
+        self.lbs_weights = torch.from_numpy(attrs["weights"]).float().T.contiguous().to(dev)
+        self.appearance_module.set(appearance)
+        self.so3 = nn.Parameter(so3) if isinstance(self.so3, nn.Parameter) else so3
+        self.scale = nn.Parameter(scale) if isinstance(self.scale, nn.Parameter) else scale
+        tel, conn = mesh_edges(f_new, v_new)
+        self.target_edge_length = torch.from_numpy(tel).to(dev)
+        self.face_connectivity = torch.from_numpy(conn).to(dev) if need_face_connectivity else \
+            torch.zeros(tel.shape[0], 2, dtype=torch.int64, device=dev)
+        self.last_raster_aux = None
 
     def _vertex_normals(self, verts_b3v):
         """PyTorch3D ``Meshes.verts_normals_padded`` semantics: area-weighted face normals

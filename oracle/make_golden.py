@@ -474,3 +474,107 @@ def loss_golden():
 
 if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "loss":
     loss_golden()
+
+
+# ------------------------------------------------------------------------------------------------ mesh subdivision
+def _tm_faces_to_edges(faces, return_index=False):
+    """trimesh.geometry.faces_to_edges (third party, absent offline; restated from its published source)."""
+    faces = np.asanyarray(faces)
+    return faces[:, [0, 1, 1, 2, 2, 0]].reshape((-1, 2))
+
+
+class _tm_grouping:
+    """trimesh.grouping.hashable_rows / unique_rows for small integer rows (restated; trimesh is unpinned in
+    requirements.txt:9 and this row hash is the same in 3.x and 4.x)."""
+
+    @staticmethod
+    def hashable_rows(data, digits=None):
+        as_int = np.asanyarray(data).astype(np.int64)
+        precision = int(np.floor(64 / as_int.shape[1]))
+        assert np.abs(as_int).max() < 2 ** (precision - 1)
+        hashable = np.zeros(len(as_int), dtype=np.int64)
+        for offset, column in enumerate(as_int.T):
+            np.bitwise_xor(hashable, column << (offset * precision), out=hashable)
+        return hashable
+
+    @staticmethod
+    def unique_rows(data, digits=None):
+        rows = _tm_grouping.hashable_rows(data, digits=digits)
+        _, unique, inverse = np.unique(rows, return_index=True, return_inverse=True)
+        return unique, inverse
+
+
+class _Trimesh:
+    """What utils/pc_util.py::subdivide asks of trimesh.Trimesh (process=True merges coincident vertices: none here)."""
+
+    def __init__(self, vertices, faces, vertex_attributes=None):
+        self.vertices = np.asanyarray(vertices, dtype=np.float64)
+        self.faces = np.asanyarray(faces, dtype=np.int64)
+        self.vertex_attributes = dict(vertex_attributes or {})
+
+    @property
+    def edges(self):
+        return _tm_faces_to_edges(self.faces)
+
+
+def subdivide_golden():
+    """``golden_subdivide.npz``: the reference's OWN ``Model.subdivide`` (models/model.py:136-179, module imported
+    unchanged) calling its OWN ``utils/pc_util.py::subdivide`` / ``_subdivide``, on a seeded 2000-face humanoid with random
+    per-face parameters: the complete state dict after one subdivision, after a second one with
+    ``need_face_connectivity=False`` (eval.py:305; stored as SHA-256 digests of the arrays, the comparison is bit-exact
+    anyway), and the face connectivity.  Stand-ins: PyTorch3D ``Meshes`` (stub
+    above) and the three trimesh pieces restated above."""
+    assert os.path.isdir(REF)
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, REF)
+    from gomavatar_b200 import synthetic as S
+    _install_stubs()
+    tm = sys.modules["trimesh"]
+    tm.Trimesh = _Trimesh
+    tm.remesh.faces_to_edges, tm.remesh.grouping = _tm_faces_to_edges, _tm_grouping
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    cwd = os.getcwd()
+    os.chdir(REF)
+    try:
+        from configs import make_cfg
+        import models.model as ref_model
+        cfg = make_cfg("exps/zju-mocap_377.yaml")
+    finally:
+        os.chdir(cwd)
+    cfg.model.img_size = [64, 64]
+    cfg.model.normal_renderer.name = "none"
+    cfg.model.shadow_module.name = "none"
+    cfg.model.non_rigid.name = "none"
+    cfg.model.pose_refinement.name = "none"
+    if "eval_mode" not in cfg.model:
+        cfg.model.eval_mode = False
+    scene = S.make_humanoid(2000, seed=4)
+    model = ref_model.Model(cfg.model, scene.canonical_info())
+    g = torch.Generator().manual_seed(11)
+    with torch.no_grad():
+        model.so3.copy_(0.1 * torch.randn(model.so3.shape, generator=g))
+        model.scale.copy_(0.7 + 0.6 * torch.rand(model.scale.shape, generator=g))
+        model.appearance_module.appearance.copy_(torch.rand(model.so3.shape, generator=g))
+        model.vertices.add_(1e-3 * torch.randn(model.vertices.shape, generator=g))
+    out = {"seed_scene": np.int64(4), "n_faces": np.int64(2000),
+           "in.faces": model.faces.numpy().copy(), "in.face_connectivity": model.face_connectivity.numpy().copy()}
+    for k, v in model.state_dict().items():
+        out[f"in.{k}"] = v.numpy().copy()
+    model.subdivide()
+    for k, v in model.state_dict().items():
+        out[f"s1.{k}"] = v.detach().numpy().copy()
+    out["s1.face_connectivity"] = model.face_connectivity.numpy().copy()
+    model.subdivide(need_face_connectivity=False)
+    import hashlib
+    for k in ("vertices", "faces", "lbs_weights"):
+        a = np.ascontiguousarray(model.state_dict()[k].detach().numpy())
+        out[f"s2.{k}.shape"] = np.asarray(a.shape, np.int64)
+        out[f"s2.{k}.dtype"] = np.asarray(str(a.dtype))
+        out[f"s2.{k}.sha256"] = np.asarray(hashlib.sha256(a.tobytes()).hexdigest())
+    out["s2.face_connectivity_shape"] = np.asarray(model.face_connectivity.shape, np.int64)
+    np.savez_compressed(os.path.join(OUT, "golden_subdivide.npz"), **out)
+    print("golden_subdivide.npz:", {k: (v.shape, str(v.dtype)) for k, v in out.items() if k.startswith("s1.")})
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "subdivide":
+    subdivide_golden()
