@@ -64,7 +64,7 @@ def collate(items):
     return {k: torch.from_numpy(np.stack([np.asarray(it[k], dtype=np.float32) for it in items])) for k in keys}
 
 
-def train(data, iters, img, device, batch=2, lr=5e-4, ckpt_dir=None, save_freq=0, lpips=None, log=None):
+def train(data, iters, img, device, batch=2, lr=5e-4, ckpt_dir=None, save_freq=0, lpips=None, log=None, subdivide_iters=()):
     ds = IO.Dataset(data, target_size=[img, img])
     loader = torch.utils.data.DataLoader(ds, batch_size=batch, shuffle=True, drop_last=True, collate_fn=collate,
                                          generator=torch.Generator().manual_seed(0))
@@ -75,10 +75,12 @@ def train(data, iters, img, device, batch=2, lr=5e-4, ckpt_dir=None, save_freq=0
     if model is None:
         model = Model(model_cfg(img), ds.get_canonical_info(), strict_raster=False)
     model = model.to(device).train()
-    arena = FlatArena(model)
-    groups = model.get_param_groups({"lr": {"appearance": lr, "canonical_geometry": lr, "canonical_geometry_xyz": lr, "shadow": lr}})
-    opt = ArenaAdam(arena, groups)
-    base = [g["lr"] for g in opt.param_groups]
+    def make_optimizer():
+        arena = FlatArena(model)
+        groups = model.get_param_groups({"lr": {"appearance": lr, "canonical_geometry": lr, "canonical_geometry_xyz": lr, "shadow": lr}})
+        opt = ArenaAdam(arena, groups)
+        return arena, opt, [g["lr"] for g in opt.param_groups]
+    arena, opt, base = make_optimizer()
     history = []
     while n_iter < iters:
         for b in loader:
@@ -92,6 +94,11 @@ def train(data, iters, img, device, batch=2, lr=5e-4, ckpt_dir=None, save_freq=0
             loss.backward()
             opt.step(grad_scale=arena.all_reduce_sum())
             n_iter += 1
+            if n_iter in subdivide_iters:                                                  # train.py:341-346: every face -> 4,
+                model.subdivide()                                                          # new Parameters -> new optimizer
+                arena, opt, base = make_optimizer()
+                if log:
+                    log(f"iter {n_iter:6d}  subdivided: {model.vertices.shape[1]} vertices, {model.faces.shape[0]} faces")
             for g, b0 in zip(opt.param_groups, base):                                      # train.py:166-175
                 g["lr"] = b0 * 0.1 ** (n_iter / 100000)
             history.append(float(loss.detach()))
@@ -110,9 +117,11 @@ if __name__ == "__main__":
     ap.add_argument("--faces", type=int, default=2000)
     ap.add_argument("--img", type=int, default=128)
     ap.add_argument("--frames", type=int, default=8)
+    ap.add_argument("--subdivide-iters", type=int, nargs="*", default=[])
     a = ap.parse_args()
     dev = torch.device("cuda:0")
     if not os.path.exists(os.path.join(a.data, "cameras.pkl")):
         write_synthetic_subject(a.data, a.faces, a.img, a.frames, dev)
         print(f"wrote a synthetic subject in the reference's format to {a.data}")
-    train(a.data, a.iters, a.img, dev, ckpt_dir=os.path.join(a.data, "checkpoints"), save_freq=max(1, a.iters // 2), log=print)
+    train(a.data, a.iters, a.img, dev, ckpt_dir=os.path.join(a.data, "checkpoints"), save_freq=max(1, a.iters // 2), log=print,
+          subdivide_iters=tuple(a.subdivide_iters))

@@ -86,3 +86,21 @@ def test_training_continues_across_a_subdivision():
     assert int(model.last_raster_aux["status"].max()) == 0
     for p in model.parameters():
         assert torch.isfinite(p).all()
+
+
+def test_full_model_training_with_a_subdivision_then_resume(tmp_path):
+    """examples/train_from_folder.py with ``subdivide_iters``: the mesh normal renderer, the tcgen05 shadow MLP and the
+    regulariser kernels run on the subdivided mesh; a checkpoint taken AFTER the subdivision resumes."""
+    import train_from_folder as TF
+    dev = torch.device("cuda:0")
+    data = str(tmp_path / "subject")
+    torch.manual_seed(0)
+    TF.write_synthetic_subject(data, 2000, 64, 4, dev)
+    ck = os.path.join(data, "checkpoints")
+    model, hist = TF.train(data, 24, 64, dev, ckpt_dir=ck, save_freq=24, lr=5e-3, subdivide_iters=(12,))
+    assert model.faces.shape[0] == 8000 and len(hist) == 24 and all(np.isfinite(hist))
+    assert np.mean(hist[-6:]) < 1.25 * np.mean(hist[6:12]), hist                           # no blow-up across the event
+    assert os.listdir(ck) == ["iter_24.pt"]
+    model2, hist2 = TF.train(data, 30, 64, dev, ckpt_dir=ck, save_freq=0, lr=5e-3, subdivide_iters=(12,))
+    assert model2.faces.shape[0] == 8000 and len(hist2) == 6 and all(np.isfinite(hist2))
+    assert np.mean(hist2) < 1.25 * np.mean(hist[-6:]), (hist2, hist[-6:])
