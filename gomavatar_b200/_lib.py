@@ -13,7 +13,7 @@ from ctypes import c_int, c_int32, c_int64, c_size_t, c_void_p, c_float, c_char_
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libgom_b200.so")
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 STATUS_OVERFLOW = 1
 STATUS_TIMEOUT = 2
 
@@ -164,7 +164,7 @@ class GomShadowMlpArgs(ctypes.Structure):
 
 class GomMeshRegArgs(ctypes.Structure):
     _fields_ = [("n_frames", c_int32), ("n_verts", c_int32), ("n_pairs", c_int32), ("n_faces", c_int32), ("do_laplacian", c_int32),
-                ("do_normal", c_int32), ("do_color", c_int32), ("_pad", c_int32), ("verts", c_void_p), ("row_ptr", c_void_p),
+                ("do_normal", c_int32), ("do_color", c_int32), ("n_color_pairs", c_int32), ("verts", c_void_p), ("row_ptr", c_void_p),
                 ("col", c_void_p), ("pair_vid", c_void_p), ("pair_face", c_void_p), ("colors", c_void_p), ("lap", c_void_p),
                 ("sums", c_void_p), ("g_verts_lap", c_void_p), ("g_verts_nc", c_void_p), ("g_colors", c_void_p)]
 

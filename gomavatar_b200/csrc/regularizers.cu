@@ -18,11 +18,11 @@ namespace {
 constexpr int kThreads = 256;
 
 struct RegDev {
-    int B, V, P, F;
+    int B, V, P, Pc, F;        // P pairs for the normal term, Pc for the colour term
     const float *verts;        // [B,3,V]
     const int *row_ptr, *col;  // CSR adjacency [V+1], [2E]
     const int *pair_vid;       // [P,4]: v0, v1 (shared edge), other_a, other_b
-    const int *pair_face;      // [P,2]: the two faces (colour term)
+    const int *pair_face;      // [Pc,2]: the two faces (colour term)
     const float *colors;       // [F,3]
     float *lap;                // [B,3,V] scratch: Laplacian coordinates
     double *sums;              // [3]: laplacian, normal consistency, colour consistency (sums, not means)
@@ -128,13 +128,13 @@ __global__ void __launch_bounds__(kThreads) k_reg_normal_consistency(RegDev a) {
     block_add(term, a.sums + 1);
 }
 
-// mean_{p,c} |col[fa,c] - col[fb,c]| and its unit gradient sign / (3 P)
+// mean_{p,c} |col[fa,c] - col[fb,c]| and its unit gradient sign / (3 Pc)
 __global__ void __launch_bounds__(kThreads) k_reg_color_consistency(RegDev a) {
     const int p = blockIdx.x * kThreads + threadIdx.x;
     double term = 0.0;
-    if (p < a.P) {
+    if (p < a.Pc) {
         const int fa = a.pair_face[2 * p], fb = a.pair_face[2 * p + 1];
-        const float s = 1.0f / (3.0f * (float)a.P);
+        const float s = 1.0f / (3.0f * (float)a.Pc);
 #pragma unroll
         for (int c = 0; c < 3; c++) {
             const float d = a.colors[3 * fa + c] - a.colors[3 * fb + c];
@@ -152,7 +152,7 @@ extern "C" size_t gom_sizeof_mesh_reg_args(void) { return sizeof(GomMeshRegArgs)
 
 extern "C" int gom_mesh_regularizers(const GomMeshRegArgs *p, gom_stream_t stream_) {
     GOM_REQUIRE(p != nullptr, "args");
-    GOM_REQUIRE(p->n_frames > 0 && p->n_verts > 0 && p->n_pairs >= 0 && p->n_faces >= 0, "sizes");
+    GOM_REQUIRE(p->n_frames > 0 && p->n_verts > 0 && p->n_pairs >= 0 && p->n_color_pairs >= 0 && p->n_faces >= 0, "sizes");
     GOM_REQUIRE(p->n_frames <= 65535, "n_frames");
     GOM_REQUIRE(p->verts && p->sums, "null pointer");
     GOM_REQUIRE(!p->do_laplacian || (p->row_ptr && p->col && p->lap && p->g_verts_lap), "laplacian buffers");
@@ -160,7 +160,7 @@ extern "C" int gom_mesh_regularizers(const GomMeshRegArgs *p, gom_stream_t strea
     GOM_REQUIRE(!p->do_color || (p->pair_face && p->colors && p->g_colors), "colour-consistency buffers");
     cudaStream_t stream = (cudaStream_t)stream_;
     RegDev a;
-    a.B = p->n_frames; a.V = p->n_verts; a.P = p->n_pairs; a.F = p->n_faces;
+    a.B = p->n_frames; a.V = p->n_verts; a.P = p->n_pairs; a.Pc = p->n_color_pairs; a.F = p->n_faces;
     a.verts = p->verts; a.row_ptr = p->row_ptr; a.col = p->col; a.pair_vid = p->pair_vid; a.pair_face = p->pair_face;
     a.colors = p->colors; a.lap = p->lap; a.sums = p->sums;
     a.g_verts_lap = p->g_verts_lap; a.g_verts_nc = p->g_verts_nc; a.g_colors = p->g_colors;
@@ -173,15 +173,17 @@ extern "C" int gom_mesh_regularizers(const GomMeshRegArgs *p, gom_stream_t strea
         k_reg_laplacian_grad<<<grid, kThreads, 0, stream>>>(a);
         GOM_LAUNCH_CHECK();
     }
-    if (p->do_normal && a.P > 0) {
+    if (p->do_normal)                                      // also with no pair at all: the gradient is defined (zero)
         GOM_CUDA(cudaMemsetAsync(a.g_verts_nc, 0, sizeof(float) * 3 * (size_t)a.B * a.V, stream));
+    if (p->do_color)
+        GOM_CUDA(cudaMemsetAsync(a.g_colors, 0, sizeof(float) * 3 * (size_t)a.F, stream));
+    if (p->do_normal && a.P > 0) {
         dim3 grid(gom_div_up(a.P, kThreads), a.B);
         k_reg_normal_consistency<<<grid, kThreads, 0, stream>>>(a);
         GOM_LAUNCH_CHECK();
     }
-    if (p->do_color && a.P > 0) {
-        GOM_CUDA(cudaMemsetAsync(a.g_colors, 0, sizeof(float) * 3 * (size_t)a.F, stream));
-        k_reg_color_consistency<<<gom_div_up(a.P, kThreads), kThreads, 0, stream>>>(a);
+    if (p->do_color && a.Pc > 0) {
+        k_reg_color_consistency<<<gom_div_up(a.Pc, kThreads), kThreads, 0, stream>>>(a);
         GOM_LAUNCH_CHECK();
     }
     gom_prof_end(GOM_PROF_MESH_REG, stream);

@@ -50,6 +50,30 @@ def vertex_degree(edges, n_verts, dtype=torch.float32):
         0, edges.reshape(-1), torch.ones(edges.numel(), dtype=dtype, device=edges.device))
 
 
+def all_face_pairs(faces, n_verts):
+    """[P,2] (lower face index first) for EVERY edge shared by exactly two faces, in ``edges_packed`` order: the pairs
+    ``pytorch3d.loss.mesh_normal_consistency`` averages over (it derives them from the mesh itself).  The model's
+    ``face_connectivity`` (reference models/model.py:115-125) is this list WITHOUT the pair of the last edge — its
+    ``range(max_edge_id)`` loop stops one short — and is what the reference's own colour term uses
+    (utils/network_util.py:795-799); the two terms therefore count P and P - 1 pairs on a closed mesh, as in the
+    reference.  Edges with more than two faces (non-manifold; PyTorch3D would take all their pairs) do not occur in SMPL
+    meshes or their subdivisions and are skipped.  Topology only: cacheable."""
+    f = faces.long()
+    Fn = f.shape[0]
+    e = torch.cat([f[:, [1, 2]], f[:, [2, 0]], f[:, [0, 1]]], dim=0)
+    e, _ = torch.sort(e, dim=1)
+    key = e[:, 0] * n_verts + e[:, 1]
+    face_of = torch.arange(Fn, device=f.device).repeat(3)
+    order = torch.argsort(key * Fn + face_of)                                            # by edge id, then face index
+    k, fo = key[order], face_of[order]
+    first = torch.ones_like(k, dtype=torch.bool)
+    first[1:] = k[1:] != k[:-1]
+    idx = torch.nonzero(first)[:, 0]
+    count = torch.diff(torch.cat([idx, idx.new_tensor([k.numel()])]))
+    sel = idx[count == 2]
+    return torch.stack([fo[sel], fo[sel + 1]], dim=1)
+
+
 def normal_consistency_indices(faces, face_connectivity):
     """(v0, v1, other_a, other_b) per pair of faces sharing an edge: the shared edge in a fixed order (smaller vertex index
     first, as PyTorch3D's edges_packed stores it) and the one unshared vertex of each face.  Topology only: cacheable."""
@@ -65,9 +89,12 @@ def normal_consistency_indices(faces, face_connectivity):
     return v0, v1, other_a, other_b
 
 
-def normal_consistency(verts, faces, face_connectivity, indices=None):
-    """face_connectivity [P,2]: pairs of faces sharing an edge (``Model.face_connectivity``).  verts [V,3] or [B,V,3]
-    (mean over the B meshes: they share the topology, so it is the mean over all pairs of all meshes)."""
+def normal_consistency(verts, faces, face_connectivity=None, indices=None):
+    """face_connectivity [P,2]: pairs of faces sharing an edge; None = all of them (``all_face_pairs``: PyTorch3D's
+    definition, what ``compute_loss`` uses).  verts [V,3] or [B,V,3] (mean over the B meshes: they share the topology, so
+    it is the mean over all pairs of all meshes)."""
+    if face_connectivity is None and indices is None:
+        face_connectivity = all_face_pairs(faces, verts.shape[-2])
     v0, v1, other_a, other_b = indices if indices is not None else normal_consistency_indices(faces, face_connectivity)
     d = verts.dim() - 2
     p0 = verts.index_select(d, v0)
@@ -87,16 +114,17 @@ def normal_mask_loss(normal_mask, mask_gt, kernel_size=7, dilate=True):
     return (normal_mask - mask_gt).abs().mean()
 
 
-def mesh_topology(faces, face_connectivity, n_verts):
+def mesh_topology(faces, face_connectivity, n_verts, normal_pairs=None):
     """Static index tables of ``gom_mesh_regularizers`` (int32, on the device of ``faces``): CSR adjacency of the unique
-    edges, per pair of faces sharing an edge its (v0, v1, opposite a, opposite b) and the two face ids."""
+    edges; (v0, v1, opposite a, opposite b) per pair of the NORMAL term (``normal_pairs``, default ``all_face_pairs``);
+    the two face ids per pair of the COLOUR term (``face_connectivity``, the model's buffer)."""
     e = unique_edges(faces, n_verts)
     rows, cols = torch.cat([e[:, 0], e[:, 1]]), torch.cat([e[:, 1], e[:, 0]])
     order = torch.argsort(rows, stable=True)
     counts = torch.bincount(rows, minlength=n_verts)
     row_ptr = torch.zeros(n_verts + 1, dtype=torch.int64, device=faces.device)
     row_ptr[1:] = torch.cumsum(counts, 0)
-    v0, v1, oa, ob = normal_consistency_indices(faces, face_connectivity)
+    v0, v1, oa, ob = normal_consistency_indices(faces, all_face_pairs(faces, n_verts) if normal_pairs is None else normal_pairs)
     return {"row_ptr": row_ptr.int().contiguous(), "col": cols[order].int().contiguous(),
             "pair_vid": torch.stack([v0, v1, oa, ob], dim=1).int().contiguous(),
             "pair_face": face_connectivity.int().contiguous(), "n_verts": int(n_verts), "n_faces": int(faces.shape[0])}
@@ -112,7 +140,7 @@ class _FusedMeshReg(torch.autograd.Function):
         if verts.device.type != "cuda":
             raise _lib.GomError("fused mesh regularisers: inputs must live on a CUDA device")
         B, _, V = verts.shape
-        P, Fn = topo["pair_vid"].shape[0], topo["n_faces"]
+        P, Pc, Fn = topo["pair_vid"].shape[0], topo["pair_face"].shape[0], topo["n_faces"]
         do_lap, do_nc, do_cc = flags
         vb = verts.detach().contiguous().float()
         cb = colors.detach().contiguous().float() if do_cc else None
@@ -123,7 +151,7 @@ class _FusedMeshReg(torch.autograd.Function):
         g_nc = e(B, 3, V) if do_nc else None
         g_col = e(Fn, 3) if do_cc else None
         lap_scratch = e(B, 3, V) if do_lap else None
-        a = GomMeshRegArgs(n_frames=B, n_verts=V, n_pairs=P, n_faces=Fn, do_laplacian=int(do_lap), do_normal=int(do_nc),
+        a = GomMeshRegArgs(n_frames=B, n_verts=V, n_pairs=P, n_color_pairs=Pc, n_faces=Fn, do_laplacian=int(do_lap), do_normal=int(do_nc),
                            do_color=int(do_cc), verts=ptr(vb), row_ptr=ptr(topo["row_ptr"]), col=ptr(topo["col"]),
                            pair_vid=ptr(topo["pair_vid"]), pair_face=ptr(topo["pair_face"]), colors=ptr(cb),
                            lap=ptr(lap_scratch), sums=ptr(sums), g_verts_lap=ptr(g_lap), g_verts_nc=ptr(g_nc),
@@ -131,7 +159,7 @@ class _FusedMeshReg(torch.autograd.Function):
         call("gom_mesh_regularizers", a)
         ctx.grads = (g_lap, g_nc, g_col)
         # Python scalars only (no host tensor -> device copy: the step stays CUDA-graph capturable)
-        means = torch.stack([sums[0] / (B * V), sums[1] / max(B * P, 1), sums[2] / max(3 * P, 1)]).float()
+        means = torch.stack([sums[0] / (B * V), sums[1] / max(B * P, 1), sums[2] / max(3 * Pc, 1)]).float()
         return means[0], means[1], means[2]
 
     @staticmethod
@@ -200,10 +228,10 @@ def compute_loss(rgbs, masks, bgcolors, rgb_gt, mask_gt, outputs, model, loss_cf
                                             bool(_c(loss_cfg, "normal.mask_dilate", True))), c_nm)
     if c_nc > 0:
         if not fused:
-            conn = outputs["face_connectivity"]
-            if getattr(model, "_nc_indices_key", None) is not conn:
-                model._nc_indices, model._nc_indices_key = normal_consistency_indices(faces, conn), conn
-            nc = normal_consistency(vo.permute(0, 2, 1), faces, conn, model._nc_indices)
+            if getattr(model, "_nc_indices_key", None) is not faces:
+                pairs = all_face_pairs(faces, model.vertices.shape[1])
+                model._nc_indices, model._nc_indices_key = normal_consistency_indices(faces, pairs), faces
+            nc = normal_consistency(vo.permute(0, 2, 1), faces, None, model._nc_indices)
         add("normal_consist", nc, c_nc)
     if c_cc > 0:
         add("color_consist", cc if fused else color_consistency(outputs["colors"], outputs["face_connectivity"]), c_cc)

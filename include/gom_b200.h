@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define GOM_ABI_VERSION 4
+#define GOM_ABI_VERSION 5
 #define GOM_TILE 16              /* 16x16-pixel tiles, as upstream's BLOCK_X/BLOCK_Y */
 #define GOM_MAX_CHANNELS 4
 #define GOM_MAX_JOINTS 64
@@ -482,18 +482,21 @@ int gom_shadow_mlp_num_ctas(void);                          /* CTAs of the persi
  * Mesh regularisers of reference train.py:123-160 for B posed meshes of one topology: uniform Laplacian smoothing
  * (utils/network_util.py:669-792, method "uniform"), normal consistency (pytorch3d.loss.mesh_normal_consistency,
  * train.py:149) and colour consistency (utils/network_util.py:795-799).  One call writes the three SUMS (the caller
- * divides: B*V, B*P, 3*P) and the unit gradients of the three MEANS; the caller scales them by the loss coefficients.
+ * divides: B*V, B*P, 3*Pc) and the unit gradients of the three MEANS; the caller scales them by the loss coefficients.
  * Topology (CSR adjacency of the unique edges, per pair the shared edge and the two opposite vertices) is static between
  * subdivisions and supplied by the caller (regularizers.py builds it once).
  */
 typedef struct {
-    int32_t n_frames, n_verts, n_pairs, n_faces;
-    int32_t do_laplacian, do_normal, do_color, _pad;
+    int32_t n_frames, n_verts, n_pairs, n_faces;   /* n_pairs = P: rows of pair_vid (normal consistency) */
+    int32_t do_laplacian, do_normal, do_color;
+    int32_t n_color_pairs;                          /* Pc: rows of pair_face (colour consistency; the reference's
+                                                       face_connectivity misses the pair of the last edge, so Pc = P - 1
+                                                       on a closed mesh: models/model.py:119-123) */
     const float *verts;          /* [B,3,V] (the model's vertices_observation layout) */
     const int32_t *row_ptr;      /* [V+1] CSR adjacency */
     const int32_t *col;          /* [2E] */
     const int32_t *pair_vid;     /* [P,4] v0, v1 (shared edge, v0 < v1), opposite vertex of face a, of face b */
-    const int32_t *pair_face;    /* [P,2] the two faces (colour term) */
+    const int32_t *pair_face;    /* [Pc,2] the two faces (colour term) */
     const float *colors;         /* [F,3] */
     float *lap;                  /* [B,3,V] scratch */
     double *sums;                /* [3] out: sum |lap|^2, sum (1 - cos), sum |dcol| */

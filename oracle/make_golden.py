@@ -411,12 +411,41 @@ class _LossMeshes(_Meshes):
         return L.coalesce()
 
 
+def _p3d_mesh_normal_consistency(meshes):
+    """pytorch3d.loss.mesh_normal_consistency (0.7.0, absent offline) restated step by step from its published source,
+    independently of gomavatar_b200/regularizers.py: every edge gathers the faces that use it (``faces_packed_to_edges_packed``
+    sorted by edge), ``mesh_normal_consistency_find_verts`` lists all pairs (i < j) of those faces per edge, the normal of a
+    face relative to the edge (v0, v1) is (v1 - v0) x (its opposite vertex - v0) — obtained as the sum over the face's three
+    corners, two of which give zero — and the loss is the mean of 1 - cos(n_i, -n_j) over the pairs."""
+    verts, faces = meshes.verts_packed(), meshes.faces_packed()
+    edges, face_to_edge = meshes.edges_packed(), meshes.faces_packed_to_edges_packed()
+    E, Fn = edges.shape[0], faces.shape[0]
+    with torch.no_grad():
+        edge_idx = face_to_edge.reshape(Fn * 3)
+        vert_idx = faces.view(1, Fn, 3).expand(3, Fn, 3).transpose(0, 1).reshape(3 * Fn, 3)
+        edge_idx, sort_idx = edge_idx.sort()
+        vert_idx = vert_idx[sort_idx]
+        edge_num = edge_idx.bincount(minlength=E)
+        pairs, start = [], 0
+        for n in edge_num.tolist():                              # mesh_normal_consistency_find_verts (C++)
+            for i in range(n):
+                for j in range(i + 1, n):
+                    pairs.append((start + i, start + j))
+            start += n
+        pair_idx = torch.tensor(pairs, dtype=torch.int64)
+    v0, v1 = verts[edges[edge_idx, 0]], verts[edges[edge_idx, 1]]
+    n = sum(torch.cross(v1 - v0, verts[vert_idx[:, k]] - v0, dim=1) for k in range(3))
+    n0, n1 = n[pair_idx[:, 0]], -n[pair_idx[:, 1]]
+    loss = 1 - torch.cosine_similarity(n0, n1, dim=1)
+    return loss.sum() / loss.numel()                             # one mesh: weights = 1 / number of pairs
+
+
 def loss_golden():
     """``golden_loss.npz``: the reference's OWN ``unpack`` + ``compute_loss`` (train.py:53-55, :98-163), its own
     ``mesh_laplacian_smoothing`` / ``mesh_color_consistency`` (utils/network_util.py:669-799) and its own LPIPS (random trunk
     under seed 0, in-tree heads) on seeded inputs, with the loss coefficients of exps/zju-mocap_377.yaml.  Stand-ins: the
-    Meshes object (stub above) and ``pytorch3d.loss.mesh_normal_consistency`` (absent offline; the torch definition of
-    gomavatar_b200/regularizers.py, i.e. that ONE term is circular and says so)."""
+    Meshes object (stub above) and ``pytorch3d.loss.mesh_normal_consistency`` (absent offline; restated above from
+    PyTorch3D's published source, independently of the product — that ONE term stays unpinned against PyTorch3D itself)."""
     import types as _t
     import torch.nn.functional as F
     from gomavatar_b200 import regularizers as RG
@@ -429,7 +458,7 @@ def loss_golden():
     ns = {"torch": torch, "F": F}
     for s_ in src_net.values():
         exec(s_, ns)
-    ns["mesh_normal_consistency"] = lambda mesh: RG.normal_consistency(mesh.verts_packed(), mesh.faces_packed(), mesh.conn)
+    ns["mesh_normal_consistency"] = _p3d_mesh_normal_consistency
     for s_ in src_train.values():
         exec(s_, ns)
     from utils import lpips as ref_lpips

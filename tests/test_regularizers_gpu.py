@@ -25,7 +25,9 @@ def test_fused_regularisers_match_torch_definitions(n_faces, B):
     col = torch.rand(sc.n_faces, 3, generator=g)
     V = v.shape[0]
     topo = RG.mesh_topology(faces, conn, V)
-    assert int(topo["row_ptr"][-1]) == topo["col"].numel() and topo["pair_vid"].shape == (conn.shape[0], 4)
+    assert int(topo["row_ptr"][-1]) == topo["col"].numel()
+    # normal term: every edge-sharing pair (PyTorch3D); colour term: the model's connectivity (one pair short, model.py:119-123)
+    assert topo["pair_vid"].shape == (conn.shape[0] + 1, 4) and topo["pair_face"].shape == (conn.shape[0], 2)
 
     x = vb.permute(0, 2, 1).contiguous().to(DEV).requires_grad_(True)                                 # [B,3,V] like the model
     c = col.to(DEV).requires_grad_(True)
@@ -36,7 +38,7 @@ def test_fused_regularisers_match_torch_definitions(n_faces, B):
     xr = vb.double().to(DEV).requires_grad_(True)
     cr = col.double().to(DEV).requires_grad_(True)
     r_lap = RG.laplacian_smoothing(xr, faces)
-    r_nc = RG.normal_consistency(xr, faces, conn)
+    r_nc = RG.normal_consistency(xr, faces)
     r_cc = RG.color_consistency(cr, conn)
     (10.0 * r_lap + 0.1 * r_nc + 0.05 * r_cc).backward()
     for got, ref, what in ((lap, r_lap, "laplacian"), (nc, r_nc, "normal"), (cc, r_cc, "colour")):

@@ -64,7 +64,7 @@ def test_regulariser_kernels_follow_the_new_topology():
         vo = out["vertices_observation"].permute(0, 2, 1).double()
         with torch.no_grad():
             lap = RG.laplacian_smoothing(vo, model.faces)
-            nc = RG.normal_consistency(vo, model.faces, model.face_connectivity)
+            nc = RG.normal_consistency(vo, model.faces)
             cc = RG.color_consistency(out["colors"].double(), model.face_connectivity)
         for name, ref in (("laplacian_observation", lap), ("normal_consist", nc), ("color_consist", cc)):
             got = float(losses[name]["unscaled"])
