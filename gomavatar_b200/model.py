@@ -200,6 +200,11 @@ class Model(nn.Module):
             outputs["face_connectivity"] = self.face_connectivity
             outputs["target_edge_length"] = self.target_edge_length
             outputs["vertices_observation"] = vertices_observation
+            # reference model.py:223-224,295-296: PyTorch3D Meshes for its loss function; here light torch views with the
+            # same accessors (meshes.py) — nothing is computed unless a caller asks (regularizers.compute_loss does not)
+            from .meshes import Meshes
+            outputs["mesh"] = Meshes(vertices_observation.permute(0, 2, 1), self.faces)
+            outputs["mesh_canonical"] = Meshes(vertices_canonical.permute(1, 0)[None], self.faces)
             outputs["albedo"] = albedos[0]
             outputs["radii"] = radii
             if normal is not None:
