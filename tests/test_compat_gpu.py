@@ -58,5 +58,5 @@ def test_skimage_stand_in_is_the_metric_kernel(shims):
     got = structural_similarity(pred, gt, multichannel=True)                      # eval.py:107
     dev = torch.device("cuda:0")
     m = eval_metrics(torch.from_numpy(pred).float().to(dev), torch.from_numpy(gt).float().to(dev), quantize=False)
-    assert got == float(m["ssim"][0])
+    assert abs(got - float(m["ssim"][0])) < 1e-12                 # same kernel; fp64 atomics make the last bit order-dependent
     assert abs(got - float(OL.ssim(pred, gt))) < 1e-9
