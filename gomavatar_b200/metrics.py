@@ -54,8 +54,29 @@ class Evaluator:
                 v = self.lpips_model(p.permute(0, 3, 1, 2) * 2. - 1., g.permute(0, 3, 1, 2) * 2. - 1.)
             self.lpips.append(float(v.mean()) * 1000)
 
-    def summarize(self):
+    def evaluate_batch(self, rgb_pred, rgb_gt, return_8b=False):
+        """The batched form of the loop at eval.py:346-366: raw network outputs / targets ``[B,H,W,3]`` on the device;
+        ``to_8b_image`` of both (eval.py:355,361), mse / psnr / ssim of every frame in ONE launch, LPIPS on the quantised
+        images.  Returns the quantised predictions (uint8, what eval.py writes to PNG) on request."""
+        p, g = rgb_pred.to(self.device).float(), rgb_gt.to(self.device).float()
+        m = eval_metrics(p, g, quantize=True, return_8b=True)
+        self.mse += m["mse"].tolist(); self.psnr += m["psnr"].tolist(); self.ssim += m["ssim"].tolist()
+        if self.lpips_model is not None:
+            g8 = (255.0 * g.clamp(0, 1)).to(torch.uint8)
+            with torch.no_grad():
+                v = self.lpips_model((m["pred_8b"].float() / 255.0).permute(0, 3, 1, 2) * 2. - 1., (g8.float() / 255.0).permute(0, 3, 1, 2) * 2. - 1.)
+            self.lpips += (v.reshape(-1) * 1000).tolist()
+        return m["pred_8b"] if return_8b else None
+
+    def summarize(self, path=None):
+        """Means of the collected metrics; with ``path`` also the reference's result file (eval.py:131-143: ``np.save`` of
+        ``{'mse': [...], 'psnr': [...], 'ssim': [...], 'lpips': [...]}``, read back with ``allow_pickle=True``)."""
         mean = lambda v: float(sum(v) / len(v)) if v else float("nan")
+        if path is not None:
+            import os
+            import numpy as np
+            os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
+            np.save(path, {"mse": list(self.mse), "psnr": list(self.psnr), "ssim": list(self.ssim), "lpips": list(self.lpips)})
         out = {"mse": mean(self.mse), "psnr": mean(self.psnr), "ssim": mean(self.ssim), "lpips": mean(self.lpips)}
         self.mse, self.psnr, self.ssim, self.lpips = [], [], [], []
         return out
