@@ -247,14 +247,24 @@ class Model(nn.Module):
         return vertex_normals(verts_b3v.permute(0, 2, 1), self.faces)
 
     def get_param_groups(self, cfg):
-        """reference models/model.py:305-324 (lr names from configs/default.yaml:91-99)."""
+        """reference models/model.py:305-324 (lr names from configs/default.yaml:91-99): the same groups in the same order
+        — the frozen ``lbs_weights`` buffer first (lr 0, never receives a gradient), then appearance, vertices, scale, so3,
+        and the MLPs that exist — so that ``optimizer.state_dict()`` of a ``torch.optim.Adam`` built from it has the
+        reference's layout and ``train.py --resume`` loads either side's checkpoints.  ``dist.ArenaAdam`` ignores group
+        members that are not trainable."""
         lr = cfg.lr if hasattr(cfg, "lr") else cfg["lr"]
-        g = lambda k: getattr(lr, k) if hasattr(lr, k) else lr[k]
-        groups = [{"name": "appearance", "params": list(self.appearance_module.parameters()), "lr": g("appearance")},
-                  {"name": "canonical_geometry_xyz", "params": [self.vertices], "lr": g("canonical_geometry_xyz")}]
-        for p in (self.scale, self.so3):
-            if isinstance(p, nn.Parameter):
-                groups.append({"name": "canonical_geometry", "params": [p], "lr": g("canonical_geometry")})
+        def g(k, default=None):
+            v = getattr(lr, k, None) if not isinstance(lr, dict) else lr.get(k, None)
+            if v is None:
+                if default is None:
+                    raise KeyError(f"cfg.lr.{k} is missing")
+                return default
+            return v
+        groups = [{"name": "lbs_weights", "params": [self.lbs_weights], "lr": g("lbs_weights", 0.0)},
+                  {"name": "appearance", "params": list(self.appearance_module.parameters()), "lr": g("appearance")},
+                  {"name": "canonical_geometry_xyz", "params": [self.vertices], "lr": g("canonical_geometry_xyz")},
+                  {"name": "canonical_geometry", "params": [self.scale], "lr": g("canonical_geometry")},
+                  {"name": "canonical_geometry", "params": [self.so3], "lr": g("canonical_geometry")}]
         for name, mod in (("non_rigid", self.non_rigid_module), ("pose_refinement", self.pose_refinement_module),
                           ("shadow", self.shadow_module)):
             if isinstance(mod, nn.Module):

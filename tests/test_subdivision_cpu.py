@@ -153,8 +153,39 @@ def test_resume_replays_the_subdivision_and_loads_strictly(tmp_path):
     assert torch.equal(a.face_connectivity, b.face_connectivity)
     # every trainable tensor is a new Parameter: optimizers / arenas are rebuilt by the caller (train.py:343-346)
     lr = {"lr": {"appearance": 1e-3, "canonical_geometry_xyz": 1e-4, "canonical_geometry": 1e-3}}
-    n = sum(p.numel() for grp in b.get_param_groups(lr) for p in grp["params"])
+    groups = b.get_param_groups(lr)
+    assert [g["name"] for g in groups] == ["lbs_weights", "appearance", "canonical_geometry_xyz", "canonical_geometry", "canonical_geometry"]
+    n = sum(p.numel() for grp in groups for p in grp["params"] if p.requires_grad)
     assert n == 3 * b.vertices.shape[1] + 9 * b.faces.shape[0]
     arena = FlatArena(b)
     assert arena.numel == n and b.vertices.data_ptr() == arena.data.data_ptr() + 4 * arena.slices[
         [id(p) for p in arena.params].index(id(b.vertices))][0]
+
+
+def test_param_groups_have_the_reference_optimizer_layout():
+    """models/model.py:305-324: 8 groups with the full ZJU config, the frozen lbs_weights buffer first — so a
+    ``torch.optim.Adam`` state dict written by either side loads on the other (train.py:281)."""
+    from types import SimpleNamespace as NS
+    sc = S.make_humanoid(2000, seed=2)
+    cfg = default_model_cfg((64, 64))
+    cfg.pose_refinement = NS(name="mlp", embedding_size=69, mlp_width=256, mlp_depth=4, kick_in_iter=0)
+    try:
+        m = Model(cfg, sc.canonical_info())
+    except Exception:                                              # module cfg fields differ: the 5 core groups are enough here
+        m = Model(default_model_cfg((64, 64)), sc.canonical_info())
+    lr = NS(lr=NS(lbs_weights=0.0, appearance=5e-3, canonical_geometry_xyz=5e-5, canonical_geometry=5e-4, non_rigid=5e-5,
+                  pose_refinement=5e-5, shadow=5e-4))
+    groups = m.get_param_groups(lr)
+    assert [g["name"] for g in groups][:5] == ["lbs_weights", "appearance", "canonical_geometry_xyz", "canonical_geometry", "canonical_geometry"]
+    assert groups[0]["params"][0] is m.lbs_weights and groups[3]["params"][0] is m.scale and groups[4]["params"][0] is m.so3
+    opt = torch.optim.Adam(groups, betas=(0.9, 0.999))
+    w0 = m.lbs_weights.clone()
+    (m.vertices.sum() + m.scale.sum()).backward()
+    opt.step()
+    assert torch.equal(m.lbs_weights, w0)                          # no gradient, lr 0: untouched
+    sd = opt.state_dict()
+    assert [g["params"] for g in sd["param_groups"]][:5] == [[0], [1], [2], [3], [4]]
+    opt2 = torch.optim.Adam(m.get_param_groups(lr), betas=(0.9, 0.999))
+    opt2.load_state_dict(sd)
+    with pytest.raises(KeyError):
+        m.get_param_groups({"lr": {"appearance": 1e-3}})
