@@ -240,6 +240,14 @@ class Model(nn.Module):
             torch.zeros(tel.shape[0], 2, dtype=torch.int64, device=dev)
         self.last_raster_aux = None
 
+    def print_info(self):
+        """reference models/model.py:181-182."""
+        import logging
+        logging.info(f"the number of effective points is {self.vertices.shape[1]}")
+
+    def get_lbs_weights(self):
+        return self.lbs_weights
+
     def _vertex_normals(self, verts_b3v):
         """PyTorch3D ``Meshes.verts_normals_padded`` semantics: area-weighted face normals
         accumulated on vertices, normalised with eps 1e-6.  Only used when a normal renderer is plugged in."""
