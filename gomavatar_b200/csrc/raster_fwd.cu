@@ -14,10 +14,14 @@
 namespace {
 
 constexpr int kThreads = 256;
-constexpr int kSortCap = 4096;   // tile lists up to this length are sorted in shared memory (32 KB)
+constexpr int kSortCap = 4096;      // tile lists up to this length are sorted in shared memory (32 KB of dynamic smem) ...
+constexpr int kSortCapBig = 8192;   // ... or this one (64 KB, 3 blocks per SM) when the frame has more than kBigP Gaussians:
+constexpr int kBigP = 40000;        // at 55 104 Gaussians / 512^2 the busiest tile holds ~5 000 entries, and a list sorted
+                                    // in global memory made its block the straggler the whole launch waited for
 
 struct FwdDev {
     int B, P, H, W, C, interleaved, gx, gy, T;
+    int sort_cap;                    // entries of dynamic shared memory k_sort_blend was launched with
     long long cap;
     const float *means3D; long long means3D_stride;
     const float *cov3D; long long cov3D_stride;
@@ -168,24 +172,70 @@ __device__ __forceinline__ void cmpxchg(unsigned long long *k, int i, int j) {
     if (x > y) { k[i] = y; k[j] = x; }
 }
 
+// One stage = `half` independent compare-exchanges; a caller walks a range of them.
+__device__ __forceinline__ void flip_pairs(unsigned long long *k, int n, int lsize, int t_begin, int t_end, int t_step) {
+    const int size = 1 << lsize, hs = size >> 1, lhs = lsize - 1;
+    for (int t = t_begin; t < t_end; t += t_step) {
+        const int blk = t >> lhs, w = t & (hs - 1);
+        const int i = (blk << lsize) + w, j = (blk << lsize) + (size - 1 - w);
+        if (j < n) cmpxchg(k, i, j);
+    }
+}
+__device__ __forceinline__ void disperse_pairs(unsigned long long *k, int n, int lstep, int t_begin, int t_end, int t_step) {
+    const int step = 1 << lstep;
+    for (int t = t_begin; t < t_end; t += t_step) {
+        const int i = ((t >> lstep) << (lstep + 1)) + (t & (step - 1)), j = i + step;
+        if (j < n) cmpxchg(k, i, j);
+    }
+}
+
+// Block-wide sort (kThreads = 8 warps).  Warp w owns the `chunk` = npad / 8 consecutive elements [w chunk, (w+1) chunk):
+// every stage whose pairs stay inside a chunk — merges of size <= chunk entirely, and the disperse steps <= chunk / 2 of
+// the larger merges — is done by that warp alone behind __syncwarp(); only the stages that cross chunks pay a block
+// barrier (10 instead of 66 at 2 048 entries).  Same compare-exchange network as before, so the result is identical.
 __device__ void block_sort(unsigned long long *k, int n, int tid) {
     if (n < 2) return;
-    int npad = 2;
-    while (npad < n) npad <<= 1;
-    const int half = npad >> 1;
-    for (int lsize = 1; (1 << lsize) <= npad; lsize++) {               // sizes are powers of two: shifts, no divisions
-        const int size = 1 << lsize, hs = size >> 1, lhs = lsize - 1;
-        for (int t = tid; t < half; t += kThreads) {                  // flip
-            const int blk = t >> lhs, w = t & (hs - 1);
-            const int i = (blk << lsize) + w, j = (blk << lsize) + (size - 1 - w);
-            if (j < n) cmpxchg(k, i, j);
+    int lpad = 1;
+    while ((1 << lpad) < n) lpad++;
+    const int half = 1 << (lpad - 1);                                  // pairs per stage
+    const int lane = tid & 31, warp = tid >> 5;
+    if (lpad <= 6) {                                                   // <= 64 entries: one warp, one pair per lane
+        if (warp == 0) {
+            for (int lsize = 1; lsize <= lpad; lsize++) {
+                flip_pairs(k, n, lsize, lane, half, 32);
+                __syncwarp();
+                for (int lstep = lsize - 2; lstep >= 0; lstep--) {
+                    disperse_pairs(k, n, lstep, lane, half, 32);
+                    __syncwarp();
+                }
+            }
         }
         __syncthreads();
-        for (int lstep = lhs - 1; lstep >= 0; lstep--) {               // disperse
-            const int step = 1 << lstep;
-            for (int t = tid; t < half; t += kThreads) {
-                const int i = ((t >> lstep) << (lstep + 1)) + (t & (step - 1)), j = i + step;
-                if (j < n) cmpxchg(k, i, j);
+        return;
+    }
+    const int lchunk = lpad - 3;                                       // log2(chunk), >= 4
+    const int cp = 1 << (lchunk - 1);                                  // pairs per chunk
+    const int w_begin = warp * cp + lane, w_end = (warp + 1) * cp;
+    for (int lsize = 1; lsize <= lpad; lsize++) {
+        if (lsize <= lchunk) {                                         // the whole merge stays inside the chunks
+            flip_pairs(k, n, lsize, w_begin, w_end, 32);
+            __syncwarp();
+            for (int lstep = lsize - 2; lstep >= 0; lstep--) {
+                disperse_pairs(k, n, lstep, w_begin, w_end, 32);
+                __syncwarp();
+            }
+            if (lsize == lchunk) __syncthreads();                      // the next merge crosses chunks
+        } else {
+            flip_pairs(k, n, lsize, tid, half, kThreads);
+            __syncthreads();
+            int lstep = lsize - 2;
+            for (; lstep >= lchunk; lstep--) {                         // pairs (i, i + step) with 2 step > chunk
+                disperse_pairs(k, n, lstep, tid, half, kThreads);
+                __syncthreads();
+            }
+            for (; lstep >= 0; lstep--) {
+                disperse_pairs(k, n, lstep, w_begin, w_end, 32);
+                __syncwarp();
             }
             __syncthreads();
         }
@@ -201,7 +251,7 @@ __device__ void block_sort(unsigned long long *k, int n, int tid) {
 template <int C>
 __global__ void __launch_bounds__(kThreads) k_sort_blend(FwdDev a) {
     constexpr int kWarps = kThreads / 32;
-    __shared__ unsigned long long skeys[kSortCap];
+    extern __shared__ __align__(16) unsigned long long skeys[];       // a.sort_cap entries
     __shared__ float2 s_xy[kWarps][32];
     __shared__ float4 s_co[kWarps][32];
     __shared__ __align__(16) float s_col[kWarps][32 * C];
@@ -217,7 +267,7 @@ __global__ void __launch_bounds__(kThreads) k_sort_blend(FwdDev a) {
 
     unsigned long long *gkeys = a.inst_keys + (long long)b * a.cap + start;
     unsigned long long *sk = gkeys;
-    if (n <= kSortCap) {
+    if (n <= a.sort_cap) {
         for (int i = tid; i < n; i += kThreads) skeys[i] = gkeys[i];
         sk = skeys;
         __syncthreads();
@@ -362,9 +412,19 @@ extern "C" int gom_raster_forward(const GomRasterFwdArgs *p, gom_stream_t stream
         gom_prof_end(GOM_PROF_EMIT, stream);
     }
     dim3 bgrid(a.gx, a.gy, a.B), bblock(16, 16);
+    a.sort_cap = a.P > kBigP ? kSortCapBig : kSortCap;
+    const size_t sort_bytes = sizeof(unsigned long long) * (size_t)a.sort_cap;
+    {
+        static bool big_smem_enabled = false;           // > 48 KB of dynamic shared memory is an opt-in per function
+        if (!big_smem_enabled) {
+            GOM_CUDA(cudaFuncSetAttribute(k_sort_blend<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(unsigned long long) * kSortCapBig)));
+            GOM_CUDA(cudaFuncSetAttribute(k_sort_blend<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(unsigned long long) * kSortCapBig)));
+            big_smem_enabled = true;
+        }
+    }
     gom_prof_begin(GOM_PROF_BLEND_FWD, stream);
-    if (a.C == 3) k_sort_blend<3><<<bgrid, bblock, 0, stream>>>(a);
-    else k_sort_blend<4><<<bgrid, bblock, 0, stream>>>(a);
+    if (a.C == 3) k_sort_blend<3><<<bgrid, bblock, sort_bytes, stream>>>(a);
+    else k_sort_blend<4><<<bgrid, bblock, sort_bytes, stream>>>(a);
     GOM_LAUNCH_CHECK();
     gom_prof_end(GOM_PROF_BLEND_FWD, stream);
     return GOM_OK;
