@@ -47,12 +47,38 @@ out["loss"] = {k: float(v["unscaled"]) for k, v in losses.items()}
 out["loss_golden"] = {k[len("unscaled."):]: float(g[k]) for k in g.files if k.startswith("unscaled.")}
 out["total"], out["total_golden"] = float(total), float(g["total"])
 
+# ---- this package's Model built from the reference's REAL config node (yacs CfgNode of exps/zju-mocap_377.yaml) + the
+#      reference's own optimizer recipe (train.py:264-266) and update_lr (train.py:166-175) on its param groups
+from configs import make_cfg  # noqa: E402
+
+s = np.load(os.path.join(golden, "golden_subdivide.npz"))
+info = {"faces": s["in.faces"], "canonical_vertex": s["in.vertices"].T.copy(), "canonical_lbs_weights": s["in.lbs_weights"][:-1].T.copy(),
+        "edges": np.zeros((0, 2), np.int64)}
+cfg = make_cfg("exps/zju-mocap_377.yaml")
+ours = train.Model(cfg.model, info)
+out["ours_modules"] = {k: type(getattr(ours, k)).__name__ for k in ("pose_refinement_module", "non_rigid_module", "normal_renderer", "shadow_module")}
+out["ours_state"] = {k: list(v.shape) for k, v in ours.state_dict().items()}
+opt = torch.optim.Adam(ours.get_param_groups(cfg.train), betas=(0.9, 0.999))
+train.update_lr(opt, 1000, cfg.train)
+out["ours_groups"] = [[g["name"], float(g["lr"]), sum(int(p.numel()) for p in g["params"])] for g in opt.param_groups]
+out["subdivide_iters"] = list(cfg.model.subdivide_iters)
+
 # ---- the reference's own Model (models/model.py, unchanged) + its own subdivide() on the trimesh / Meshes stand-ins
 compat.install(ref, b200_model=False)
 sys.modules.pop("models.model", None)
 torch.Tensor.cuda = lambda self, *a, **k: self              # model.py:58,60 call .cuda() in the constructor
 import models.model as ref_model  # noqa: E402
-from configs import make_cfg  # noqa: E402
+
+# full ZJU config except the PyTorch3D mesh renderer (no parameters of its own): state-dict keys / shapes, param groups
+cfg_full = make_cfg("exps/zju-mocap_377.yaml")
+cfg_full.model.normal_renderer.name = "none"
+import contextlib, io  # noqa: E402
+with contextlib.redirect_stdout(io.StringIO()):                 # get_param_groups prints every tensor (model.py:322)
+    ref_full = ref_model.Model(cfg_full.model, info)
+    ropt = torch.optim.Adam(ref_full.get_param_groups(cfg_full.train), betas=(0.9, 0.999))
+train.update_lr(ropt, 1000, cfg_full.train)
+out["ref_state"] = {k: list(v.shape) for k, v in ref_full.state_dict().items()}
+out["ref_groups"] = [[g["name"], float(g["lr"]), sum(int(p.numel()) for p in g["params"])] for g in ropt.param_groups]
 
 cfg = make_cfg("exps/zju-mocap_377.yaml")
 cfg.model.img_size = [64, 64]
@@ -60,8 +86,6 @@ for node in ("normal_renderer", "shadow_module", "non_rigid", "pose_refinement")
     getattr(cfg.model, node).name = "none"
 if "eval_mode" not in cfg.model:
     cfg.model.eval_mode = False
-s = np.load(os.path.join(golden, "golden_subdivide.npz"))
-info = {"faces": s["in.faces"], "canonical_vertex": s["in.vertices"].T.copy(), "canonical_lbs_weights": s["in.lbs_weights"][:-1].T.copy()}
 m = ref_model.Model(cfg.model, info)
 out["ref_model_class"] = f"{type(m).__module__}.{type(m).__name__}"
 out["conn_equal"] = bool(np.array_equal(m.face_connectivity.numpy(), s["in.face_connectivity"]))

@@ -30,6 +30,14 @@ def test_reference_scripts_import_and_run_their_own_code_on_the_stand_ins(golden
     for k, ref in out["loss_golden"].items():
         assert abs(out["loss"][k] - ref) <= 1e-6 * abs(ref) + 1e-9, (k, out["loss"][k], ref)
     assert abs(out["total"] - out["total_golden"]) <= 1e-6 * out["total_golden"]
+    # this package's Model built from the reference's real CfgNode (exps/zju-mocap_377.yaml) == the reference's own Model:
+    # every module present, the same state-dict keys and shapes (checkpoints interchange), the same Adam param groups
+    # (names, sizes, learning rates after the reference's update_lr) — train.py:262-266, :166-175
+    assert out["ours_modules"] == {"pose_refinement_module": "PoseRefinementModule", "non_rigid_module": "NonRigidModule",
+                                   "normal_renderer": "Renderer", "shadow_module": "FusedShadowModule"}
+    assert out["ours_state"] == out["ref_state"] and len(out["ours_state"]) > 20
+    assert out["ours_groups"] == out["ref_groups"] and [g[0] for g in out["ours_groups"]][0] == "lbs_weights"
+    assert out["subdivide_iters"] == [50001]
     assert out["conn_equal"] and out["subdivide_conn_equal"] and out["edge_length_close"]
     assert all(out["subdivide_equal"].values()), out["subdivide_equal"]
 
