@@ -197,3 +197,20 @@ def test_install_is_idempotent_and_real_packages_win():
         assert os.path.abspath(importlib.util.find_spec(name).origin).startswith(compat.SHIM_DIR)
     compat.uninstall()
     assert compat.SHIM_DIR not in sys.path
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference checkout not present")
+def test_reference_train_main_runs_unchanged_up_to_the_first_kernel_call(tmp_path):
+    """tests/host_harness/compat_train_main_check.py: the reference's own ``train.main`` on the stand-ins, in this GPU-less
+    container — config, logger, TensorBoard, its three Dataset objects on a folder dataset_io wrote, this package's Model
+    from its cfg node, param groups, Adam, ``iter_0.pt`` — then the first iteration's ``model(...)`` (train.py:317) must
+    stop at the first kernel call with GomError: there is no CPU path to fall back to."""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "host_harness", "compat_train_main_check.py"), REF, str(tmp_path)],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-3000:]
+    out = json.loads([l for l in r.stdout.splitlines() if l.startswith("RESULT ")][-1][len("RESULT "):])
+    assert out["stopped"] is not None and "no CPU path" in out["stopped"]
+    assert "train.py:main" in out["frames"] and out["frames"][-3:] == ["function.py:apply", "skinning.py:forward", "skinning.py:_need_cuda"]
+    assert out["files"] == ["checkpoints", "config.yaml", "log.txt", "tb"]
+    assert out["ckpt_keys"] == ["iter", "network", "optimizer"] and out["n_param_groups"] == 7     # lbs, app, xyz, scale, so3, pose, shadow
+    assert out["reload"] == ["gomavatar_b200.model", 1, 2000]
