@@ -80,4 +80,21 @@ out["ckpt_keys"] = sorted(ck)
 out["n_param_groups"] = len(ck["optimizer"]["param_groups"])
 model, it = IO.model_from_checkpoint(train.make_cfg(yaml_path).model, ck)
 out["reload"] = [type(model).__module__, it, int(model.faces.shape[0])]
+
+# ---- the reference's own eval.main (eval.py:183-366, unchanged) on a checkpoint taken AFTER the subdivision: dataset,
+#      Model + subdivide(need_face_connectivity=False) replay (eval.py:300-305), load_state_dict(strict=False), then the
+#      first model(...) call (eval.py:341) must stop at the first kernel
+model.subdivide()
+IO.save_checkpoint(os.path.join(log, "checkpoints", "iter_5.pt"), model, n_iter=5)
+import eval as ref_eval  # noqa: E402
+
+ref_eval.LPIPS = _NoLpips
+out["eval_stopped"] = None
+try:
+    ref_eval.main(argparse.Namespace(cfg=yaml_path, type="view", iter=None, frame_idx=0, n_frames=1, bgcolor=None, pose_path=None))
+except GomError as e:
+    import traceback
+    out["eval_stopped"] = str(e)
+    out["eval_frames"] = [f"{os.path.basename(fr.filename)}:{fr.name}" for fr in traceback.extract_tb(e.__traceback__)]
+out["eval_dir"] = sorted(os.listdir(os.path.join(log, "eval")))
 print("RESULT " + json.dumps(out))

@@ -200,7 +200,7 @@ def test_install_is_idempotent_and_real_packages_win():
 
 
 @pytest.mark.skipif(not os.path.isdir(REF), reason="reference checkout not present")
-def test_reference_train_main_runs_unchanged_up_to_the_first_kernel_call(tmp_path):
+def test_reference_train_and_eval_main_run_unchanged_up_to_the_first_kernel_call(tmp_path):
     """tests/host_harness/compat_train_main_check.py: the reference's own ``train.main`` on the stand-ins, in this GPU-less
     container — config, logger, TensorBoard, its three Dataset objects on a folder dataset_io wrote, this package's Model
     from its cfg node, param groups, Adam, ``iter_0.pt`` — then the first iteration's ``model(...)`` (train.py:317) must
@@ -214,3 +214,8 @@ def test_reference_train_main_runs_unchanged_up_to_the_first_kernel_call(tmp_pat
     assert out["files"] == ["checkpoints", "config.yaml", "log.txt", "tb"]
     assert out["ckpt_keys"] == ["iter", "network", "optimizer"] and out["n_param_groups"] == 7     # lbs, app, xyz, scale, so3, pose, shadow
     assert out["reload"] == ["gomavatar_b200.model", 1, 2000]
+    # and the reference's own eval.main on a post-subdivision checkpoint: dataset, Model + subdivide replay (eval.py:300-305),
+    # load_state_dict, then the first model(...) (eval.py:341) stops at the same place
+    assert out["eval_stopped"] is not None and "no CPU path" in out["eval_stopped"]
+    assert "eval.py:main" in out["eval_frames"] and out["eval_frames"][-1] == "skinning.py:_need_cuda"
+    assert out["eval_dir"] == ["log_view.txt", "view"]
