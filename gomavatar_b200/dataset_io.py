@@ -9,11 +9,12 @@
                       the reference's (train.py:300-330) and reference-prepared ZJU / Snapshot folders load unchanged.
 * ``write_synthetic_dataset``  the synthetic scene of ``gomavatar_b200.synthetic`` in that format (teacher renders as images).
 
-Pinned by the reference's own reader run on a folder this module wrote (tests/golden/golden_dataset.npz, made by
-oracle/make_golden.py::dataset_golden with OpenCV stubbed out): every item field agrees.  What OpenCV does to pixels is not
-reproduced bit for bit: images are resampled with Pillow (LANCZOS / BILINEAR) when ``target_size`` differs from the file size,
-and non-zero lens distortion is rejected (ZJU-MoCap's processed folders carry the raw distortion coefficients; Snapshot's
-are zero) — both are stated in DESIGN.md as unpinned.  Pure numpy / Pillow: this is host-side I/O, not the hot path.
+Pinned by the reference's own reader run on folders this module wrote: tests/golden/golden_dataset.npz (every item field,
+OpenCV stubbed out) and tests/golden/golden_dataset_cv2.npz (the reference reader with the real OpenCV: lens undistortion —
+ZJU-MoCap's processed folders carry the raw coefficients —, LANCZOS4 / LINEAR resampling to a ``target_size``, the
+``resize_img_scale`` branch).  Where OpenCV is installed this reader makes the reference's own ``cv2.undistort`` /
+``cv2.resize`` calls and the pixels are identical; where it is not, images are resampled with Pillow (close, not identical:
+unpinned) and non-zero distortion is refused.  Host-side I/O, not the hot path.
 """
 from __future__ import annotations
 
@@ -173,8 +174,27 @@ class Dataset:
     def skeleton_to_bbox(self, skeleton):
         return {"min_xyz": np.min(skeleton, axis=0) - self.cfg["bbox_offset"], "max_xyz": np.max(skeleton, axis=0) + self.cfg["bbox_offset"]}
 
-    def _resize(self, arr, size, lanczos):
+    @staticmethod
+    def _cv2():
+        """OpenCV if it is installed (then pixels are produced by the very calls the reference makes), else None."""
+        try:
+            import cv2
+            return cv2
+        except Exception:
+            return None
+
+    def _resize(self, arr, size, lanczos, scale=None):
+        """reference dataset/train.py:157-173: ``cv2.resize`` with INTER_LANCZOS4 (image) / INTER_LINEAR (mask), to
+        ``size`` = (w, h) or by ``scale`` = (fx, fy).  Without OpenCV: Pillow's LANCZOS / BILINEAR (close, not identical)."""
+        cv2 = self._cv2()
+        if cv2 is not None:
+            interp = cv2.INTER_LANCZOS4 if lanczos else cv2.INTER_LINEAR
+            if scale is not None:
+                return cv2.resize(arr, None, fx=scale[0], fy=scale[1], interpolation=interp)
+            return cv2.resize(arr, [int(size[0]), int(size[1])], interpolation=interp)
         from PIL import Image
+        if scale is not None:
+            size = (int(round(arr.shape[1] * scale[0])), int(round(arr.shape[0] * scale[1])))
         w, h = size
         if arr.shape[1] == w and arr.shape[0] == h:
             return arr
@@ -187,16 +207,21 @@ class Dataset:
         orig_H, orig_W, _ = orig.shape
         alpha = _load_rgb(os.path.join(self.dataset_path, "masks", f"{frame_name}.png"))
         cam = self.cameras.get(frame_name, {})
-        if "distortions" in cam and np.any(np.asarray(cam["distortions"]) != 0):
-            raise NotImplementedError("lens undistortion (cv2.undistort in the reference) is not reproduced: undistort the folder first")
+        if "distortions" in cam:                                        # reference dataset/train.py:149-153
+            cv2 = self._cv2()
+            if cv2 is not None:
+                K, D = cam["intrinsics"], cam["distortions"]
+                orig, alpha = cv2.undistort(orig, K, D), cv2.undistort(alpha, K, D)
+            elif np.any(np.asarray(cam["distortions"]) != 0):
+                raise NotImplementedError("lens undistortion needs OpenCV (cv2.undistort, as in the reference): install it or "
+                                          "undistort the folder first")
         alpha = alpha / 255.0
         img = alpha * orig + (1.0 - alpha) * np.asarray(bg_color)[None, None, :]
         if "target_size" in self.cfg:
             img, alpha = self._resize(img, self.cfg["target_size"], True), self._resize(alpha, self.cfg["target_size"], False)
         elif self.cfg["resize_img_scale"] != 1.0:
-            sx, sy = self.cfg["resize_img_scale"]
-            size = (int(round(orig_W * sx)), int(round(orig_H * sy)))
-            img, alpha = self._resize(img, size, True), self._resize(alpha, size, False)
+            sc = self.cfg["resize_img_scale"]
+            img, alpha = self._resize(img, None, True, scale=sc), self._resize(alpha, None, False, scale=sc)
         return img, alpha, orig_W, orig_H
 
     def crop_image(self, img, mask, K):

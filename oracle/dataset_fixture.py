@@ -23,3 +23,19 @@ def build(path):
     Th = rng.normal(0, 0.2, (N_FRAMES, 3))
     write_synthetic_dataset(path, scene, poses, cams, images, masks, Rh=Rh, Th=Th)
     return scene, poses, cams, images, masks
+
+
+DISTORTION = np.array([[0.0, 0.0, 0.0, 0.0, 0.0], [-0.12, 0.05, 0.002, -0.001, 0.01], [0.2, -0.08, -0.003, 0.002, 0.0]])
+
+
+def add_distortion(path):
+    """Rewrites cameras.pkl with non-zero lens distortion for frames 1 and 2 (ZJU-MoCap's processed folders carry the raw
+    coefficients; the reader undistorts with them: reference dataset/train.py:149-153)."""
+    import os
+    import pickle
+    with open(os.path.join(path, "cameras.pkl"), "rb") as f:
+        cams = pickle.load(f)
+    for i, name in enumerate(sorted(cams)):
+        cams[name]["distortions"] = DISTORTION[i % len(DISTORTION)].copy()
+    with open(os.path.join(path, "cameras.pkl"), "wb") as f:
+        pickle.dump(cams, f)

@@ -607,3 +607,35 @@ def subdivide_golden():
 
 if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "subdivide":
     subdivide_golden()
+
+
+def dataset_cv2_golden():
+    """``golden_dataset_cv2.npz``: the reference's OWN reader with the REAL OpenCV (importable in this container: cv2
+    4.13) on the fixture folder, for what the stubbed run above cannot pin — ``cv2.undistort`` with non-zero lens
+    distortion (frames 1, 2), ``cv2.resize`` INTER_LANCZOS4 / INTER_LINEAR to a ``target_size`` different from the files',
+    and the ``resize_img_scale`` (0.5, 0.5) branch taken without ``target_size``.  Only ``termcolor`` is a stub."""
+    import pickle
+    import tempfile
+    import cv2  # noqa: F401  (the real one)
+    from oracle import dataset_fixture as DF
+    _stub_module("termcolor", colored=lambda s, *a, **k: s)
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    import importlib
+    ref_train = importlib.import_module("dataset.train")
+    out = {"cv2_version": np.array(cv2.__version__)}
+    with tempfile.TemporaryDirectory() as tmp:
+        DF.build(tmp)
+        DF.add_distortion(tmp)
+        for tag, kw in (("resized", dict(target_size=[64, 56])), ("halved", dict())):
+            ds = ref_train.Dataset(tmp, bgcolor=[255.0, 128.0, 0.0], **kw)
+            for i in range(len(ds)):
+                item = ds[i]
+                for k in ("K", "E", "target_rgbs", "target_masks", "bgcolor"):
+                    out[f"{tag}.item{i}.{k}"] = np.asarray(item[k])
+    np.savez_compressed(os.path.join(OUT, "golden_dataset_cv2.npz"), **out)
+    print("golden_dataset_cv2.npz:", len(out), "arrays;", {k: out[k].shape for k in ("resized.item1.target_rgbs", "halved.item1.target_rgbs")})
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "dataset_cv2":
+    dataset_cv2_golden()

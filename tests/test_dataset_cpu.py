@@ -90,20 +90,6 @@ def test_canonical_info_and_crop_branch_equal_the_reference_reader(folder, gold)
     assert m.vertices.shape == (3, scene.n_vertices) and m.lbs_weights.shape == (25, scene.n_vertices)
 
 
-def test_distorted_cameras_are_refused_not_silently_ignored(folder, tmp_path):
-    import shutil
-    path, _ = folder
-    p2 = str(tmp_path / "d")
-    shutil.copytree(path, p2)
-    cams = pickle.load(open(os.path.join(p2, "cameras.pkl"), "rb"))
-    cams["frame_000000"]["distortions"] = np.array([0.1, 0, 0, 0, 0.0])
-    pickle.dump(cams, open(os.path.join(p2, "cameras.pkl"), "wb"))
-    ds = IO.Dataset(p2, bgcolor=[0.0, 0.0, 0.0], target_size=[DF.W, DF.H])
-    with pytest.raises(NotImplementedError):
-        ds[0]
-    ds[1]
-
-
 def test_checkpoint_round_trip_in_the_reference_format_including_a_subdivided_mesh(tmp_path):
     """{'iter', 'network', 'optimizer'} like train.py:289-294; a checkpoint taken after a subdivision (4x the faces) is
     restored from its own faces / lbs_weights / vertices tensors, no subdivision replay."""
@@ -131,3 +117,44 @@ def test_checkpoint_round_trip_in_the_reference_format_including_a_subdivided_me
         assert set(sd) == set(sd2)
         for k in sd:
             assert torch.equal(sd[k], sd2[k]), k
+
+
+def test_opencv_pixel_path_equals_the_reference_reader(tmp_path, golden_dir):
+    """tests/golden/golden_dataset_cv2.npz: the reference's own reader with the REAL OpenCV on the fixture folder with lens
+    distortion (``cv2.undistort``), a ``target_size`` that differs from the files' (``cv2.resize`` LANCZOS4 / LINEAR) and the
+    ``resize_img_scale`` branch.  With OpenCV installed ``dataset_io.Dataset`` makes the same calls: the pixels agree."""
+    cv2 = pytest.importorskip("cv2")
+    gold = np.load(os.path.join(golden_dir, "golden_dataset_cv2.npz"))
+    path = str(tmp_path / "distorted")
+    DF.build(path)
+    DF.add_distortion(path)
+    same_build = str(gold["cv2_version"]) == cv2.__version__
+    for tag, kw in (("resized", dict(target_size=[64, 56])), ("halved", dict())):
+        ds = IO.Dataset(path, bgcolor=[255.0, 128.0, 0.0], **kw)
+        for i in range(len(ds)):
+            item = ds[i]
+            for k in ("K", "E", "target_rgbs", "target_masks", "bgcolor"):
+                ref, got = gold[f"{tag}.item{i}.{k}"], np.asarray(item[k])
+                assert got.shape == ref.shape and got.dtype == ref.dtype, (tag, i, k, got.shape, ref.shape, got.dtype, ref.dtype)
+                tol = 2e-6 if k in ("K", "E") else (0.0 if same_build else 1e-5)      # pixels: the same library calls
+                assert np.abs(got.astype(np.float64) - ref.astype(np.float64)).max() <= tol, (tag, i, k, np.abs(got - ref).max())
+    # distortion did change the picture (the test is not vacuous): frame 1 differs from the undistorted read of the same file
+    clean = str(tmp_path / "clean")
+    DF.build(clean)
+    a = IO.Dataset(clean, bgcolor=[255.0, 128.0, 0.0], target_size=[64, 56])[1]["target_rgbs"]
+    b = IO.Dataset(path, bgcolor=[255.0, 128.0, 0.0], target_size=[64, 56])[1]["target_rgbs"]
+    assert np.abs(a - b).max() > 0.05
+
+
+def test_without_opencv_distortion_is_refused_and_pillow_resamples(tmp_path, monkeypatch):
+    path = str(tmp_path / "distorted")
+    DF.build(path)
+    monkeypatch.setattr(IO.Dataset, "_cv2", staticmethod(lambda: None))
+    ds = IO.Dataset(path, bgcolor=[0.0, 0.0, 0.0], target_size=[64, 56])             # zero distortion: fine without OpenCV
+    item = ds[0]
+    assert item["target_rgbs"].shape == (56, 64, 3) and item["target_masks"].shape == (56, 64)
+    assert 0.0 <= item["target_rgbs"].min() and item["target_rgbs"].max() <= 1.0 + 1e-3
+    DF.add_distortion(path)
+    ds = IO.Dataset(path, bgcolor=[0.0, 0.0, 0.0], target_size=[64, 56])
+    with pytest.raises(NotImplementedError, match="OpenCV"):
+        ds[1]
