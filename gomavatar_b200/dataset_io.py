@@ -186,6 +186,8 @@ class Dataset:
     def _resize(self, arr, size, lanczos, scale=None):
         """reference dataset/train.py:157-173: ``cv2.resize`` with INTER_LANCZOS4 (image) / INTER_LINEAR (mask), to
         ``size`` = (w, h) or by ``scale`` = (fx, fy).  Without OpenCV: Pillow's LANCZOS / BILINEAR (close, not identical)."""
+        if scale is None and arr.shape[1] == int(size[0]) and arr.shape[0] == int(size[1]):
+            return arr                           # cv2.resize to the same size is an exact copy: skip the library entirely
         cv2 = self._cv2()
         if cv2 is not None:
             interp = cv2.INTER_LANCZOS4 if lanczos else cv2.INTER_LINEAR
@@ -207,12 +209,14 @@ class Dataset:
         orig_H, orig_W, _ = orig.shape
         alpha = _load_rgb(os.path.join(self.dataset_path, "masks", f"{frame_name}.png"))
         cam = self.cameras.get(frame_name, {})
-        if "distortions" in cam:                                        # reference dataset/train.py:149-153
+        # reference dataset/train.py:149-153; cv2.undistort with all-zero coefficients returns its input bit for bit
+        # (tests/test_dataset_cpu.py), so OpenCV is only touched — and imported — when there is something to undo
+        if "distortions" in cam and np.any(np.asarray(cam["distortions"]) != 0):
             cv2 = self._cv2()
             if cv2 is not None:
                 K, D = cam["intrinsics"], cam["distortions"]
                 orig, alpha = cv2.undistort(orig, K, D), cv2.undistort(alpha, K, D)
-            elif np.any(np.asarray(cam["distortions"]) != 0):
+            else:
                 raise NotImplementedError("lens undistortion needs OpenCV (cv2.undistort, as in the reference): install it or "
                                           "undistort the folder first")
         alpha = alpha / 255.0

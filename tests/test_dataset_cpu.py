@@ -146,6 +146,28 @@ def test_opencv_pixel_path_equals_the_reference_reader(tmp_path, golden_dir):
     assert np.abs(a - b).max() > 0.05
 
 
+def test_identity_operations_never_touch_opencv(tmp_path, monkeypatch):
+    """cv2.undistort with zero coefficients and cv2.resize to the same size return their input bit for bit, so the reader
+    skips them (and never imports OpenCV) for folders that need neither — every synthetic folder of the GPU tests."""
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(0)
+    for _ in range(20):
+        H, W = int(rng.integers(20, 200)), int(rng.integers(20, 200))
+        img = rng.integers(0, 256, (H, W, 3)).astype(np.uint8)
+        K = np.array([[rng.uniform(50, 2000), 0, rng.uniform(0, W)], [0, rng.uniform(50, 2000), rng.uniform(0, H)], [0, 0, 1]])
+        assert np.array_equal(cv2.undistort(img, K, np.zeros(5)), img)
+        f = rng.random((H, W, 3))
+        assert np.array_equal(cv2.resize(f, [W, H], interpolation=cv2.INTER_LANCZOS4), f)
+        assert np.array_equal(cv2.resize(f, [W, H], interpolation=cv2.INTER_LINEAR), f)
+    path = str(tmp_path / "clean")
+    DF.build(path)
+
+    def boom():
+        raise AssertionError("OpenCV must not be needed here")
+    monkeypatch.setattr(IO.Dataset, "_cv2", staticmethod(boom))
+    IO.Dataset(path, bgcolor=[0.0, 0.0, 0.0], target_size=[DF.W, DF.H])[0]
+
+
 def test_without_opencv_distortion_is_refused_and_pillow_resamples(tmp_path, monkeypatch):
     path = str(tmp_path / "distorted")
     DF.build(path)
