@@ -297,6 +297,86 @@ class Dataset:
                 "edges": self.edges, "faces": self.faces}
 
 
+class NovelViewDataset(Dataset):
+    """Mirror of reference ``dataset/test.py::Dataset`` (:28-283) — the ZJU-MoCap novel-view / novel-pose evaluation reader
+    of ``eval.py --type view|pose`` (eval.py:214-247) and of train.py's periodic evaluation (train.py:211-220).  Poses and
+    the canonical mesh come from the processed folder (``dataset_path``), cameras and pictures from the RAW ZJU-MoCap
+    capture (``raw_dataset_path``): ``annots.npy`` (``cams`` K / R / T in millimetres / D per view),
+    ``Camera_B<v+1>/<frame:06d>.jpg``, ``mask/…png`` OR-ed with ``mask_cihp/…png``.  Items are ordered frame-major,
+    view-minor; every picture is undistorted and halved (LANCZOS4 / LINEAR) like the reference's.  Same constructor
+    arguments and item keys.  Pinned by the reference's own reader run with the real OpenCV on a synthetic capture
+    (tests/golden/golden_dataset_zju_views.npz)."""
+
+    RESIZE = 0.5                                                        # dataset/test.py:21-24
+
+    def __init__(self, raw_dataset_path, dataset_path, test_type="view", bgcolor=None, exclude_training_view=True,
+                 exclude_view=0, skip=30, **_):
+        super().__init__(dataset_path, bgcolor=bgcolor)
+        self.raw_dataset_path = raw_dataset_path
+        annots = np.load(os.path.join(raw_dataset_path, "annots.npy"), allow_pickle=True).item()
+        cams = annots["cams"]
+        self.cameras = {}
+        for view_id in range(len(cams["K"])):
+            if exclude_training_view and view_id == exclude_view:
+                continue
+            E = np.eye(4)
+            E[:3, :3] = np.array(cams["R"])[view_id].astype("float32")
+            E[:3, 3] = (np.array(cams["T"])[view_id].astype("float32") / 1000.0)[:3, 0]
+            self.cameras[view_id] = {"intrinsics": np.array(cams["K"])[view_id].astype("float32"), "extrinsics": E,
+                                     "distortions": np.array(cams["D"])[view_id].astype("float32")[:, 0]}
+        names = sorted(os.path.splitext(n)[0] for n in os.listdir(self.image_dir) if n.endswith(".png"))
+        if test_type == "view":                                          # monohuman's split
+            names = names[:-(len(names) // 5)]
+        elif test_type == "pose":
+            names = names[-(len(names) // 5):]
+        else:
+            raise NotImplementedError(f"unknown test_type {test_type}")
+        self.framelist = names[::skip]
+
+    def __len__(self):
+        return len(self.framelist) * len(self.cameras)
+
+    def load_mask(self, rel_png):
+        def binary(folder):
+            return (_load_rgb(os.path.join(self.raw_dataset_path, folder, rel_png))[:, :, 0] != 0).astype(np.uint8)
+        msk = (binary("mask") | binary("mask_cihp")).astype(np.uint8)
+        msk[msk == 1] = 255
+        return msk
+
+    def load_view_image(self, view_id, frame_id, bg_color):
+        cam_dir = f"Camera_B{view_id + 1}"
+        orig = _load_rgb(os.path.join(self.raw_dataset_path, cam_dir, f"{frame_id:06d}.jpg"))
+        alpha = self.load_mask(os.path.join(cam_dir, f"{frame_id:06d}.png"))
+        cam = self.cameras[view_id]
+        if np.any(np.asarray(cam["distortions"]) != 0):
+            cv2 = self._cv2()
+            if cv2 is None:
+                raise NotImplementedError("lens undistortion needs OpenCV (cv2.undistort, as in the reference)")
+            orig, alpha = cv2.undistort(orig, cam["intrinsics"], cam["distortions"]), cv2.undistort(alpha, cam["intrinsics"], cam["distortions"])
+        alpha = (alpha / 255.0)[:, :, None]
+        img = alpha * orig + (1.0 - alpha) * np.asarray(bg_color)[None, None, :]
+        sc = (self.RESIZE, self.RESIZE)
+        img, alpha = self._resize(img, None, True, scale=sc), self._resize(alpha, None, False, scale=sc)
+        return img, alpha.reshape(alpha.shape[0], alpha.shape[1])        # cv2.resize drops the single channel
+
+    def __getitem__(self, idx):
+        view_id = sorted(self.cameras)[idx % len(self.cameras)]
+        name = self.framelist[idx // len(self.cameras)]
+        frame_id = int(name.split("_")[1])
+        bgcolor = (np.random.rand(3) * 255.0).astype("float32") if self.bgcolor is None else np.array(self.bgcolor, dtype="float32")
+        img, alpha = self.load_view_image(view_id, frame_id, bgcolor)
+        info = self.mesh_infos[name]
+        dst_poses, tpose = info["poses"].astype("float32"), info["tpose_joints"].astype("float32")
+        K = self.cameras[view_id]["intrinsics"][:3, :3].copy()
+        K[:2] *= self.RESIZE
+        E = apply_global_tfm_to_camera(self.cameras[view_id]["extrinsics"], info["Rh"].astype("float32"), info["Th"].astype("float32"))
+        dst_Rs, dst_Ts = body_pose_to_body_RTs(dst_poses, tpose)
+        return {"frame_name": f"Camera_B{view_id + 1}_{name}", "K": K.astype(np.float32), "E": E.astype(np.float32),
+                "target_rgbs": (img / 255.0).astype("float32"), "target_masks": alpha.astype(np.float32),
+                "dst_Rs": dst_Rs, "dst_Ts": dst_Ts, "cnl_gtfms": canonical_global_tfms(self.canonical_joints),
+                "dst_posevec": dst_poses.reshape(-1)[3:] + 1e-2}
+
+
 # -------------------------------------------------------------------------------------------------------- checkpoints
 def save_checkpoint(path, model, optimizer_state=None, n_iter=0):
     """The reference's checkpoint file (train.py:289-294, :372-376): {'iter', 'network': state_dict, 'optimizer'}."""

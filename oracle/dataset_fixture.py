@@ -39,3 +39,42 @@ def add_distortion(path):
         cams[name]["distortions"] = DISTORTION[i % len(DISTORTION)].copy()
     with open(os.path.join(path, "cameras.pkl"), "wb") as f:
         pickle.dump(cams, f)
+
+
+N_VIEWS, RAW_W, RAW_H = 3, 96, 80
+
+
+def build_raw_zju(raw_path, processed_path, n_frames=10):
+    """A synthetic RAW ZJU-MoCap capture (what reference dataset/test.py reads next to the processed folder):
+    ``annots.npy`` {'cams': {'K','R','T' (mm),'D'}}, ``Camera_B<v>/<frame:06d>.jpg``, ``mask/Camera_B<v>/<frame:06d>.png``
+    and ``mask_cihp/…`` — plus a processed folder with ``n_frames`` frames for the poses (so the 1/5 novel-pose split is
+    not empty)."""
+    import os
+    from PIL import Image
+    from gomavatar_b200 import synthetic as S
+    from gomavatar_b200.dataset_io import write_synthetic_dataset
+    scene = S.make_humanoid(2000, seed=0)
+    rng = np.random.default_rng(23)
+    poses = S.make_poses(n_frames, seed=7)
+    cams = [S.make_camera(azimuth=0.5 * i, img_size=(W, H), focal=60.0, base_size=W) for i in range(n_frames)]
+    write_synthetic_dataset(processed_path, scene, poses, cams, (rng.random((n_frames, H, W, 3)) * 255).astype(np.uint8),
+                            np.full((n_frames, H, W), 255, np.uint8), Rh=rng.normal(0, 0.3, (n_frames, 3)), Th=rng.normal(0, 0.2, (n_frames, 3)))
+    Ks, Rs, Ts, Ds = [], [], [], []
+    for v in range(N_VIEWS):
+        K, E = S.make_camera(azimuth=2.1 * v + 0.3, img_size=(RAW_W, RAW_H), focal=110.0 + 7 * v, base_size=RAW_W)
+        Ks.append(np.asarray(K, np.float64)); Rs.append(np.asarray(E, np.float64)[:3, :3])
+        Ts.append(np.asarray(E, np.float64)[:3, 3:4] * 1000.0)                               # millimetres
+        Ds.append(DISTORTION[v % len(DISTORTION)].reshape(5, 1))
+    np.save(os.path.join(raw_path, "annots.npy"), {"cams": {"K": Ks, "R": Rs, "T": Ts, "D": Ds}}, allow_pickle=True)
+    yy, xx = np.mgrid[0:RAW_H, 0:RAW_W]
+    smooth = lambda a, b, c: 127 + 120 * np.sin(xx / a + c) * np.cos(yy / b)
+    for v in range(N_VIEWS):
+        for sub in ("", "mask", "mask_cihp"):
+            os.makedirs(os.path.join(raw_path, sub, f"Camera_B{v + 1}"), exist_ok=True)
+        for fr in range(n_frames):
+            img = np.stack([smooth(7 + v, 9, fr), smooth(11, 5 + v, 2 * fr), smooth(6, 13, v)], -1).clip(0, 255).astype(np.uint8)
+            Image.fromarray(img).save(os.path.join(raw_path, f"Camera_B{v + 1}", f"{fr:06d}.jpg"), quality=95)
+            m1 = ((xx - 48 - 3 * v) ** 2 / 2 + (yy - 40) ** 2 < (22 + fr) ** 2).astype(np.uint8)
+            m2 = ((xx - 40) ** 2 + (yy - 44 - 2 * v) ** 2 < 15 ** 2).astype(np.uint8) * 7        # any non-zero label counts
+            Image.fromarray(np.stack([m1] * 3, -1)).save(os.path.join(raw_path, "mask", f"Camera_B{v + 1}", f"{fr:06d}.png"))
+            Image.fromarray(np.stack([m2] * 3, -1)).save(os.path.join(raw_path, "mask_cihp", f"Camera_B{v + 1}", f"{fr:06d}.png"))

@@ -639,3 +639,37 @@ def dataset_cv2_golden():
 
 if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "dataset_cv2":
     dataset_cv2_golden()
+
+
+def dataset_zju_views_golden():
+    """``golden_dataset_zju_views.npz``: the reference's OWN novel-view / novel-pose reader (``dataset/test.py::Dataset``,
+    imported unchanged, real OpenCV) on the synthetic raw ZJU-MoCap capture of oracle/dataset_fixture.py::build_raw_zju."""
+    import tempfile
+    import cv2
+    from oracle import dataset_fixture as DF
+    _stub_module("termcolor", colored=lambda s, *a, **k: s)
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    import importlib
+    ref_test = importlib.import_module("dataset.test")
+    out = {"cv2_version": np.array(cv2.__version__)}
+    with tempfile.TemporaryDirectory() as tmp:
+        raw, proc = os.path.join(tmp, "raw"), os.path.join(tmp, "processed")
+        os.makedirs(raw)
+        DF.build_raw_zju(raw, proc)
+        for tag, kw in (("view", dict(test_type="view", skip=3, exclude_view=0)),
+                        ("pose", dict(test_type="pose", skip=1, exclude_training_view=False))):
+            ds = ref_test.Dataset(raw, proc, bgcolor=[10.0, 200.0, 90.0], **kw)
+            out[f"{tag}.len"] = np.int64(len(ds))
+            for i in range(len(ds)):
+                item = ds[i]
+                for k, v in item.items():
+                    out[f"{tag}.item{i}.{k}"] = np.array(v) if k == "frame_name" else np.asarray(v)
+        info = ds.get_canonical_info()
+        out["info.canonical_vertex"] = np.asarray(info["canonical_vertex"])
+    np.savez_compressed(os.path.join(OUT, "golden_dataset_zju_views.npz"), **out)
+    print("golden_dataset_zju_views.npz:", len(out), "arrays; view items", int(out["view.len"]), "pose items", int(out["pose.len"]))
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "dataset_zju_views":
+    dataset_zju_views_golden()

@@ -180,3 +180,32 @@ def test_without_opencv_distortion_is_refused_and_pillow_resamples(tmp_path, mon
     ds = IO.Dataset(path, bgcolor=[0.0, 0.0, 0.0], target_size=[64, 56])
     with pytest.raises(NotImplementedError, match="OpenCV"):
         ds[1]
+
+
+def test_novel_view_reader_equals_the_reference_test_reader(tmp_path, golden_dir):
+    """tests/golden/golden_dataset_zju_views.npz: the reference's own ``dataset/test.py::Dataset`` (eval.py --type view /
+    pose on ZJU-MoCap, real OpenCV) on a synthetic RAW capture — annots.npy cameras in millimetres with lens distortion,
+    jpg pictures, mask OR mask_cihp, the monohuman frame splits, frame-major / view-minor order, the excluded training view."""
+    cv2 = pytest.importorskip("cv2")
+    gold = np.load(os.path.join(golden_dir, "golden_dataset_zju_views.npz"))
+    raw, proc = str(tmp_path / "raw"), str(tmp_path / "processed")
+    os.makedirs(raw)
+    DF.build_raw_zju(raw, proc)
+    same_build = str(gold["cv2_version"]) == cv2.__version__
+    for tag, kw in (("view", dict(test_type="view", skip=3, exclude_view=0)),
+                    ("pose", dict(test_type="pose", skip=1, exclude_training_view=False))):
+        ds = IO.NovelViewDataset(raw, proc, bgcolor=[10.0, 200.0, 90.0], **kw)
+        assert len(ds) == int(gold[f"{tag}.len"]) > 0
+        for i in range(len(ds)):
+            item = ds[i]
+            keys = {k[len(f"{tag}.item{i}."):] for k in gold.files if k.startswith(f"{tag}.item{i}.")}
+            assert set(item) == keys, set(item) ^ keys
+            assert item["frame_name"] == str(gold[f"{tag}.item{i}.frame_name"])
+            for k in keys - {"frame_name"}:
+                ref, got = gold[f"{tag}.item{i}.{k}"], np.asarray(item[k])
+                assert got.shape == ref.shape and got.dtype == ref.dtype, (tag, i, k, got.shape, ref.shape, got.dtype, ref.dtype)
+                tol = (0.0 if same_build else 1e-5) if k in ("target_rgbs", "target_masks", "dst_posevec") else 2e-6
+                assert np.abs(got.astype(np.float64) - ref.astype(np.float64)).max() <= tol, (tag, i, k, np.abs(got - ref).max())
+    assert np.array_equal(ds.get_canonical_info()["canonical_vertex"], gold["info.canonical_vertex"])
+    with pytest.raises(NotImplementedError):
+        IO.NovelViewDataset(raw, proc, test_type="tpose")
