@@ -415,11 +415,14 @@ extern "C" int gom_raster_forward(const GomRasterFwdArgs *p, gom_stream_t stream
     a.sort_cap = a.P > kBigP ? kSortCapBig : kSortCap;
     const size_t sort_bytes = sizeof(unsigned long long) * (size_t)a.sort_cap;
     {
-        static bool big_smem_enabled = false;           // > 48 KB of dynamic shared memory is an opt-in per function
-        if (!big_smem_enabled) {
+        // > 48 KB of dynamic shared memory is an opt-in per function AND per device (a process may drive several)
+        static bool big_smem_enabled[64] = {};
+        int dev = 0;
+        GOM_CUDA(cudaGetDevice(&dev));
+        if (dev < 0 || dev >= 64 || !big_smem_enabled[dev]) {
             GOM_CUDA(cudaFuncSetAttribute(k_sort_blend<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(unsigned long long) * kSortCapBig)));
             GOM_CUDA(cudaFuncSetAttribute(k_sort_blend<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(unsigned long long) * kSortCapBig)));
-            big_smem_enabled = true;
+            if (dev >= 0 && dev < 64) big_smem_enabled[dev] = true;
         }
     }
     gom_prof_begin(GOM_PROF_BLEND_FWD, stream);
