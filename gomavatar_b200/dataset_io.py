@@ -377,6 +377,71 @@ class NovelViewDataset(Dataset):
                 "dst_posevec": dst_poses.reshape(-1)[3:] + 1e-2}
 
 
+def rotate_camera_by_frame_idx(extrinsics, frame_idx, trans=None, rotate_axis="y", period=196, inv_angle=False):
+    """reference utils/camera_util.py:5-109 (``rotate_camera_by_frame_idx`` -> ``_update_extrinsics``): the camera of
+    ``extrinsics`` turned by 2 pi frame_idx / period about a world axis through ``trans``."""
+    angle = 2 * np.pi * (frame_idx / period)
+    if inv_angle:
+        angle = -angle
+    inv_E = np.linalg.inv(np.asarray(extrinsics))
+    camrot, campos = inv_E[:3, :3], inv_E[:3, 3].copy()
+    if trans is not None:
+        campos = campos - trans
+    if camrot.T[1, 1] < 0.0:
+        angle = -angle
+    vec = np.zeros(3)
+    vec[{"x": 0, "y": 1, "z": 2}[rotate_axis]] = angle
+    grot = _rodrigues(vec).astype("float32")
+    rot_campos, rot_camrot = grot.dot(campos), grot.dot(camrot)
+    if trans is not None:
+        rot_campos = rot_campos + trans
+    E = np.identity(4)
+    E[:3, :3] = rot_camrot.T
+    E[:3, 3] = -rot_camrot.T.dot(rot_campos)
+    return E
+
+
+class FreeviewDataset(Dataset):
+    """Mirror of reference ``dataset/freeview.py::Dataset`` (``eval.py --type freeview``, eval.py:262-277): one training
+    frame's pose seen from ``total_frames`` cameras on a circle around the subject.  Same constructor and item keys."""
+
+    ROT_CAM_PARAMS = {"zju_mocap": {"rotate_axis": "z", "inv_angle": True}, "wild": {"rotate_axis": "y", "inv_angle": False}}
+
+    def __init__(self, dataset_path, frame_idx=0, total_frames=100, keyfilter=None, bgcolor=None, src_type="zju_mocap",
+                 target_size=None, **_):
+        super().__init__(dataset_path, keyfilter=keyfilter, bgcolor=bgcolor if bgcolor is not None else [255.0, 255.0, 255.0],
+                         target_size=target_size)
+        self.train_frame_idx, self.total_frames, self.src_type = frame_idx, total_frames, src_type
+        self.train_frame_name = self.framelist[frame_idx]
+        self.train_camera = self.cameras[self.train_frame_name]
+        self.train_mesh_info = self.mesh_infos[self.train_frame_name]
+
+    def __len__(self):
+        return self.total_frames
+
+    def get_freeview_camera(self, E, frame_idx, total_frames, trans=None):
+        E = rotate_camera_by_frame_idx(E, frame_idx, period=total_frames, trans=trans, **self.ROT_CAM_PARAMS[self.src_type])
+        return self.train_camera["intrinsics"].copy(), E
+
+    def __getitem__(self, idx):
+        img, alpha, orig_W, orig_H = self.load_image(self.train_frame_name, np.array(self.bgcolor, dtype="float32"))
+        info = self.train_mesh_info
+        dst_poses, tpose = info["poses"].astype("float32").reshape(-1), info["tpose_joints"].astype("float32")
+        Rh, Th = info["Rh"].astype("float32"), info["Th"].astype("float32")
+        K, E = self.get_freeview_camera(self.train_camera["extrinsics"], idx, self.total_frames, trans=Th)
+        if "target_size" in self.cfg:
+            scale_w, scale_h = self.cfg["target_size"][0] / orig_W, self.cfg["target_size"][1] / orig_H
+        else:
+            scale_w, scale_h = self.cfg["resize_img_scale"]
+        K[:1] *= scale_w
+        K[1:2] *= scale_h
+        E = apply_global_tfm_to_camera(E, Rh, Th)
+        dst_Rs, dst_Ts = body_pose_to_body_RTs(dst_poses, tpose)
+        return {"frame_name": self.train_frame_name + f"_v{idx:04d}", "K": K.astype(np.float32), "E": E.astype(np.float32),
+                "target_rgbs": (img / 255.0).astype("float32"), "dst_Rs": dst_Rs, "dst_Ts": dst_Ts,
+                "cnl_gtfms": canonical_global_tfms(self.canonical_joints), "dst_posevec": dst_poses[3:] + 1e-2}
+
+
 # -------------------------------------------------------------------------------------------------------- checkpoints
 def save_checkpoint(path, model, optimizer_state=None, n_iter=0):
     """The reference's checkpoint file (train.py:289-294, :372-376): {'iter', 'network': state_dict, 'optimizer'}."""

@@ -673,3 +673,31 @@ def dataset_zju_views_golden():
 
 if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "dataset_zju_views":
     dataset_zju_views_golden()
+
+
+def dataset_freeview_golden():
+    """``golden_dataset_freeview.npz``: the reference's OWN free-view reader (``dataset/freeview.py::Dataset``, imported
+    unchanged, real OpenCV) on the fixture folder: 7 cameras on a circle for frame 1, both rotation conventions."""
+    import tempfile
+    import cv2  # noqa: F401
+    from oracle import dataset_fixture as DF
+    _stub_module("termcolor", colored=lambda s, *a, **k: s)
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    import importlib
+    ref_fv = importlib.import_module("dataset.freeview")
+    out = {}
+    with tempfile.TemporaryDirectory() as tmp:
+        DF.build(tmp)
+        for tag, kw in (("zju", dict(src_type="zju_mocap", target_size=[DF.W, DF.H])), ("wild", dict(src_type="wild", bgcolor=[0.0, 64.0, 255.0]))):
+            ds = ref_fv.Dataset(tmp, 1, total_frames=7, **kw)
+            out[f"{tag}.len"] = np.int64(len(ds))
+            for i in range(len(ds)):
+                for k, v in ds[i].items():
+                    out[f"{tag}.item{i}.{k}"] = np.array(v) if k == "frame_name" else np.asarray(v)
+    np.savez_compressed(os.path.join(OUT, "golden_dataset_freeview.npz"), **out)
+    print("golden_dataset_freeview.npz:", len(out), "arrays")
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "dataset_freeview":
+    dataset_freeview_golden()

@@ -209,3 +209,27 @@ def test_novel_view_reader_equals_the_reference_test_reader(tmp_path, golden_dir
     assert np.array_equal(ds.get_canonical_info()["canonical_vertex"], gold["info.canonical_vertex"])
     with pytest.raises(NotImplementedError):
         IO.NovelViewDataset(raw, proc, test_type="tpose")
+
+
+def test_freeview_reader_equals_the_reference_freeview_reader(folder, golden_dir):
+    """tests/golden/golden_dataset_freeview.npz: the reference's own ``dataset/freeview.py::Dataset`` (eval.py --type
+    freeview) on the fixture folder — the camera circle (``rotate_camera_by_frame_idx``) in both conventions."""
+    pytest.importorskip("cv2")                       # the 'wild' case resamples by 0.5: OpenCV's LANCZOS4, like the reference
+    gold = np.load(os.path.join(golden_dir, "golden_dataset_freeview.npz"))
+    path, _ = folder
+    for tag, kw in (("zju", dict(src_type="zju_mocap", target_size=[DF.W, DF.H])), ("wild", dict(src_type="wild", bgcolor=[0.0, 64.0, 255.0]))):
+        ds = IO.FreeviewDataset(path, 1, total_frames=7, **kw)
+        assert len(ds) == int(gold[f"{tag}.len"]) == 7
+        Es = []
+        for i in range(len(ds)):
+            item = ds[i]
+            keys = {k[len(f"{tag}.item{i}."):] for k in gold.files if k.startswith(f"{tag}.item{i}.")}
+            assert set(item) == keys, set(item) ^ keys
+            assert item["frame_name"] == str(gold[f"{tag}.item{i}.frame_name"])
+            for k in keys - {"frame_name"}:
+                ref, got = gold[f"{tag}.item{i}.{k}"], np.asarray(item[k])
+                assert got.shape == ref.shape and got.dtype == ref.dtype, (tag, i, k)
+                tol = 1e-6 if k == "target_rgbs" else 3e-6
+                assert np.abs(got.astype(np.float64) - ref.astype(np.float64)).max() <= tol, (tag, i, k, np.abs(got - ref).max())
+            Es.append(item["E"])
+        assert np.abs(Es[0] - Es[3]).max() > 0.1                          # the camera does move
