@@ -442,6 +442,81 @@ class FreeviewDataset(Dataset):
                 "cnl_gtfms": canonical_global_tfms(self.canonical_joints), "dst_posevec": dst_poses[3:] + 1e-2}
 
 
+def get_camrot(campos, lookat=None, up=None, inv_camera=False):
+    """reference utils/camera_util.py:52-83: rows right / up / forward of a camera at ``campos`` looking at ``lookat``."""
+    lookat = np.array([0.0, 0.0, 0.0], dtype=np.float32) if lookat is None else lookat
+    if up is None:
+        up = np.array([0.0, 1.0, 0.0], dtype=np.float32)
+        if inv_camera:
+            up[1] *= -1.0
+    forward = lookat - campos
+    forward = forward / np.linalg.norm(forward)
+    right = np.cross(up, forward)
+    right = right / np.linalg.norm(right)
+    up = np.cross(forward, right)
+    up = up / np.linalg.norm(up)
+    return np.array([right, up, forward], dtype=np.float32)
+
+
+class NewPoseDataset(Dataset):
+    """Mirror of reference ``dataset/newpose.py::Dataset`` (``eval.py --type pose_mdm``, eval.py:248-261): the avatar driven
+    by a motion file — an ``.npy`` dictionary with ``thetas_ori`` ``[24,3,N]`` (axis-angle per joint; a torch tensor in the
+    files MDM writes, an array is accepted too) and ``root_translation`` ``[3,N]`` — seen from one fixed 512 x 512 camera
+    (radius 8, focal 1250, height 1.2).  Targets are zero images, as in the reference.  Unlike the reference it does not
+    open (and then discard) ``images/frame_<idx>.png`` for every pose, so the motion may be longer than the training set."""
+
+    RENDER_SIZE = 512
+    CAM_PARAMS = {"radius": 8.0, "focal": 1250.0}
+
+    def __init__(self, dataset_path, pose_path, keyfilter=None, bgcolor=(0.0, 0.0, 0.0), debug=False, src_type="wild", **_):
+        super().__init__(dataset_path, keyfilter=keyfilter, bgcolor=list(bgcolor) if bgcolor is not None else None)
+        self.pose_path, self.src_type = pose_path, src_type
+        self.pose_infos = self.load_mdm_pose_infos(pose_path)
+        self.total_frames = len(self.pose_infos["Rh"])
+        K, E = self.setup_camera(self.RENDER_SIZE, **self.CAM_PARAMS)
+        self.camera = {"K": [K] * self.total_frames, "E": [E] * self.total_frames}
+
+    @staticmethod
+    def setup_camera(img_size, radius, focal):
+        y = 1.2
+        campos = np.array([0.0, y, radius], dtype="float32")
+        camrot = get_camrot(campos, lookat=np.array([0, y, 0.0]), inv_camera=True)
+        E = np.eye(4, dtype="float32")
+        E[:3, :3] = camrot
+        E[:3, 3] = -camrot.dot(campos)
+        K = np.eye(3, dtype="float32")
+        K[0, 0] = K[1, 1] = focal
+        K[:2, 2] = img_size / 2.0
+        return K, E
+
+    @staticmethod
+    def load_mdm_pose_infos(path):
+        data = dict(np.load(path, allow_pickle=True).item())
+        thetas = data["thetas_ori"]
+        thetas = thetas.cpu().numpy() if hasattr(thetas, "cpu") else np.asarray(thetas)
+        poses = np.transpose(thetas, (2, 0, 1)).copy()
+        Rh = poses[:, 0].copy()
+        Th = np.transpose(np.asarray(data["root_translation"]), (1, 0))
+        poses[:, 0] = 0.0
+        return {"poses": poses.reshape(poses.shape[0], -1), "Rh": Rh, "Th": Th}
+
+    def __len__(self):
+        return self.total_frames
+
+    def __getitem__(self, idx):
+        dst_poses = self.pose_infos["poses"][idx].astype("float32")
+        tpose = self.canonical_joints
+        Rh, Th = self.pose_infos["Rh"][idx].astype("float32"), self.pose_infos["Th"][0].astype("float32")
+        E = apply_global_tfm_to_camera(self.camera["E"][idx], Rh, Th - self.canonical_joints[0])
+        dst_Rs, dst_Ts = body_pose_to_body_RTs(dst_poses, tpose)
+        H = W = self.RENDER_SIZE
+        return {"frame_name": f"frame_{idx:06d}", "dst_poses": dst_poses, "dst_tpose_joints": tpose,
+                "K": self.camera["K"][idx].copy().astype(np.float32), "E": E.astype(np.float32),
+                "target_rgbs": np.zeros([H, W, 3], dtype=np.float32), "target_masks": np.zeros([H, W], dtype=np.float32),
+                "dst_Rs": dst_Rs, "dst_Ts": dst_Ts, "cnl_gtfms": canonical_global_tfms(self.canonical_joints),
+                "dst_posevec": dst_poses[3:] + 1e-2, "joints": get_joints_from_pose(dst_poses, tpose)}
+
+
 # -------------------------------------------------------------------------------------------------------- checkpoints
 def save_checkpoint(path, model, optimizer_state=None, n_iter=0):
     """The reference's checkpoint file (train.py:289-294, :372-376): {'iter', 'network': state_dict, 'optimizer'}."""

@@ -78,3 +78,14 @@ def build_raw_zju(raw_path, processed_path, n_frames=10):
             m2 = ((xx - 40) ** 2 + (yy - 44 - 2 * v) ** 2 < 15 ** 2).astype(np.uint8) * 7        # any non-zero label counts
             Image.fromarray(np.stack([m1] * 3, -1)).save(os.path.join(raw_path, "mask", f"Camera_B{v + 1}", f"{fr:06d}.png"))
             Image.fromarray(np.stack([m2] * 3, -1)).save(os.path.join(raw_path, "mask_cihp", f"Camera_B{v + 1}", f"{fr:06d}.png"))
+
+
+def write_mdm_motion(path, n_poses, as_torch=True):
+    """An MDM-format motion file as reference dataset/newpose.py:152-164 reads it: np.save of a dict with 'thetas_ori'
+    [24,3,N] (a torch tensor, as MDM's SMPL export stores it) and 'root_translation' [3,N]."""
+    import torch
+    rng = np.random.default_rng(31)
+    thetas = (rng.normal(0, 0.25, (24, 3, n_poses))).astype(np.float32)
+    root = rng.normal(0, 0.3, (3, n_poses)).astype(np.float32)
+    np.save(path, {"thetas_ori": torch.from_numpy(thetas) if as_torch else thetas, "root_translation": root}, allow_pickle=True)
+    return path

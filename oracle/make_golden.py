@@ -701,3 +701,35 @@ def dataset_freeview_golden():
 
 if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "dataset_freeview":
     dataset_freeview_golden()
+
+
+def dataset_newpose_golden():
+    """``golden_dataset_newpose.npz``: the reference's OWN motion-file reader (``dataset/newpose.py::Dataset``, imported
+    unchanged; eval.py --type pose_mdm) on the fixture folder with a seeded 3-pose MDM-format file (the reference opens
+    images/frame_<idx>.png for every pose, so the motion cannot be longer than the fixture)."""
+    import tempfile
+    from oracle import dataset_fixture as DF
+    _stub_module("termcolor", colored=lambda s, *a, **k: s)
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    import importlib
+    ref_np = importlib.import_module("dataset.newpose")
+    out = {}
+    with tempfile.TemporaryDirectory() as tmp:
+        DF.build(tmp)
+        pose_file = DF.write_mdm_motion(os.path.join(tmp, "motion.npy"), DF.N_FRAMES)
+        ds = ref_np.Dataset(tmp, pose_file)
+        out["len"] = np.int64(len(ds))
+        for i in range(len(ds)):
+            for k, v in ds[i].items():
+                if k in ("target_rgbs", "target_masks"):
+                    out[f"item{i}.{k}.shape"] = np.asarray(np.asarray(v).shape)
+                    assert not np.any(v)
+                else:
+                    out[f"item{i}.{k}"] = np.array(v) if k == "frame_name" else np.asarray(v)
+    np.savez_compressed(os.path.join(OUT, "golden_dataset_newpose.npz"), **out)
+    print("golden_dataset_newpose.npz:", len(out), "arrays")
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "dataset_newpose":
+    dataset_newpose_golden()

@@ -233,3 +233,27 @@ def test_freeview_reader_equals_the_reference_freeview_reader(folder, golden_dir
                 assert np.abs(got.astype(np.float64) - ref.astype(np.float64)).max() <= tol, (tag, i, k, np.abs(got - ref).max())
             Es.append(item["E"])
         assert np.abs(Es[0] - Es[3]).max() > 0.1                          # the camera does move
+
+
+def test_new_pose_reader_equals_the_reference_newpose_reader(folder, tmp_path, golden_dir):
+    """tests/golden/golden_dataset_newpose.npz: the reference's own ``dataset/newpose.py::Dataset`` (eval.py --type
+    pose_mdm) on the fixture folder and a seeded MDM-format motion file: the fixed camera, the root handling, every key."""
+    gold = np.load(os.path.join(golden_dir, "golden_dataset_newpose.npz"))
+    path, _ = folder
+    motion = DF.write_mdm_motion(str(tmp_path / "motion.npy"), DF.N_FRAMES)
+    ds = IO.NewPoseDataset(path, motion)
+    assert len(ds) == int(gold["len"]) == DF.N_FRAMES
+    for i in range(len(ds)):
+        item = ds[i]
+        keys = {k[len(f"item{i}."):].replace(".shape", "") for k in gold.files if k.startswith(f"item{i}.")}
+        assert set(item) == keys, set(item) ^ keys
+        assert item["frame_name"] == str(gold[f"item{i}.frame_name"])
+        for k in ("target_rgbs", "target_masks"):
+            assert list(item[k].shape) == list(gold[f"item{i}.{k}.shape"]) and item[k].dtype == np.float32 and not item[k].any()
+        for k in keys - {"frame_name", "target_rgbs", "target_masks"}:
+            ref, got = gold[f"item{i}.{k}"], np.asarray(item[k])
+            assert got.shape == ref.shape and got.dtype == ref.dtype, (i, k, got.shape, ref.shape, got.dtype, ref.dtype)
+            assert np.abs(got.astype(np.float64) - ref.astype(np.float64)).max() <= 3e-6, (i, k, np.abs(got - ref).max())
+    # a plain-array motion file (no torch tensor inside) and a motion longer than the training set both work here
+    longer = DF.write_mdm_motion(str(tmp_path / "longer.npy"), DF.N_FRAMES + 4, as_torch=False)
+    assert len(IO.NewPoseDataset(path, longer)) == DF.N_FRAMES + 4 and IO.NewPoseDataset(path, longer)[DF.N_FRAMES + 3]["K"][0, 0] == 1250.0
