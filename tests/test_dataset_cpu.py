@@ -257,3 +257,39 @@ def test_new_pose_reader_equals_the_reference_newpose_reader(folder, tmp_path, g
     # a plain-array motion file (no torch tensor inside) and a motion longer than the training set both work here
     longer = DF.write_mdm_motion(str(tmp_path / "longer.npy"), DF.N_FRAMES + 4, as_torch=False)
     assert len(IO.NewPoseDataset(path, longer)) == DF.N_FRAMES + 4 and IO.NewPoseDataset(path, longer)[DF.N_FRAMES + 3]["K"][0, 0] == 1250.0
+
+
+def test_eval_example_selects_every_reader_and_reaches_the_kernels(folder, tmp_path):
+    """examples/eval_from_folder.py::render — eval.py's ``--type`` switch (train / view / pose / freeview / pose_mdm): the
+    reader, the model at the reader's image size, the checkpoint with its subdivision replay, pose refinement off for
+    unseen poses; on this GPU-less machine each run must then stop at the first kernel call (no CPU path)."""
+    import sys
+    import torch
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "examples"))
+    import eval_from_folder as EF
+    from gomavatar_b200._lib import GomError
+    from gomavatar_b200.model import Model
+    path, _ = folder
+    raw, proc = str(tmp_path / "raw"), str(tmp_path / "processed")
+    os.makedirs(raw)
+    DF.build_raw_zju(raw, proc)
+    motion = DF.write_mdm_motion(str(tmp_path / "motion.npy"), 5, as_torch=False)
+    ds, gt = EF.make_dataset("view", proc, 64, (0.0, 0.0, 0.0), raw=raw, skip=3)
+    assert isinstance(ds, IO.NovelViewDataset) and gt and ds[0]["target_rgbs"].shape == (DF.RAW_H // 2, DF.RAW_W // 2, 3)
+    assert isinstance(EF.make_dataset("freeview", path, 64, (0.0,) * 3, frame_idx=1, n_frames=5)[0], IO.FreeviewDataset)
+    assert isinstance(EF.make_dataset("pose_mdm", path, 64, (0.0,) * 3, pose_path=motion)[0], IO.NewPoseDataset)
+    with pytest.raises(ValueError):
+        EF.make_dataset("tpose", path, 64, (0.0,) * 3)
+    if torch.cuda.is_available():
+        pytest.skip("the rest checks the no-CPU-path behaviour")
+    # a checkpoint of a once-subdivided model, in the reference's format
+    m = Model(EF.model_cfg(64), IO.Dataset(proc).get_canonical_info())
+    m.subdivide()
+    ck = str(tmp_path / "iter_9.pt")
+    IO.save_checkpoint(ck, m, n_iter=9)
+    dev = torch.device("cpu")
+    for eval_type, kw in (("view", dict(raw=raw, skip=3)), ("pose", dict(raw=raw, skip=1)), ("freeview", dict(frame_idx=1, n_frames=3)),
+                          ("pose_mdm", dict(pose_path=motion)), ("train", dict())):
+        with pytest.raises(GomError, match="no CPU path"):
+            EF.render(eval_type, proc, ck, 64, dev, str(tmp_path / "out"), n_subdivisions=1, batch=2, **kw)
+        assert os.path.isdir(os.path.join(str(tmp_path / "out"), "eval", eval_type))
