@@ -98,3 +98,40 @@ def test_two_rank_step_equals_single_rank_step():
         torch.testing.assert_close(grad, arena.grad, rtol=1e-5, atol=1e-6)
         torch.testing.assert_close(data, arena.data, rtol=1e-5, atol=1e-6)
     torch.testing.assert_close(out[0][0], out[1][0], rtol=0, atol=0)       # replicas stay bit-identical
+
+
+def _subdivide_worker(rank, world, port, out):
+    """a subdivision is a deterministic host event every rank executes at the same step — no communication.
+    The real ``Model`` (host side only: no forward), a rank-dependent pseudo-gradient, one all-reduce before and one after."""
+    os.environ.update(RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    init_from_env("gloo")
+    from gomavatar_b200 import synthetic as S
+    from gomavatar_b200.model import Model, default_model_cfg
+    model = Model(default_model_cfg((64, 64)), S.make_humanoid(2000, seed=0).canonical_info())
+    log = []
+    for phase in range(2):
+        arena = FlatArena(model)                                   # re-created after the subdivision, like the optimizer
+        arena.broadcast_params(src=0)
+        g = torch.Generator().manual_seed(10 * phase + rank)
+        arena.grad.copy_(torch.randn(arena.numel, generator=g))
+        arena.all_reduce_mean()
+        with torch.no_grad():
+            arena.data.add_(arena.grad, alpha=-1e-3)               # a plain SGD step stands in for the Adam kernel
+        log.append((arena.numel, arena.data.clone(), model.faces.clone(), model.lbs_weights.clone()))
+        if phase == 0:
+            model.subdivide()
+    out[rank] = log
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(180)
+def test_replicas_stay_identical_across_a_subdivision():
+    world = 2
+    out = mp.Manager().dict()
+    mp.spawn(_subdivide_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    (n0, d0, f0, w0), (n1, d1, f1, w1) = out[0]
+    assert n1 == 3 * (1034 + 3000) + 9 * 8000 and n0 == 3 * 1034 + 9 * 2000 and f1.shape[0] == 4 * f0.shape[0]
+    for phase in range(2):
+        for a, b in zip(out[0][phase][1:], out[1][phase][1:]):
+            assert torch.equal(a, b)                               # parameters, faces, LBS weights: bit-identical on both ranks
