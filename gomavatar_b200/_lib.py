@@ -13,7 +13,7 @@ from ctypes import c_int, c_int32, c_int64, c_size_t, c_void_p, c_float, c_char_
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libgom_b200.so")
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 STATUS_OVERFLOW = 1
 STATUS_TIMEOUT = 2
 
@@ -132,6 +132,21 @@ class GomConvFirstArgs(ctypes.Structure):
                 ("scratch", c_void_p), ("act", c_void_p)]
 
 
+class GomConvPackArgs(ctypes.Structure):
+    _fields_ = [("c_out", c_int32), ("c_in", c_int32), ("transpose", c_int32), ("split", c_int32), ("weight", c_void_p),
+                ("packed", c_void_p)]
+
+
+class GomConv3x3Args(ctypes.Structure):
+    _fields_ = [("n_images", c_int32), ("height", c_int32), ("width", c_int32), ("c_in", c_int32), ("c_out", c_int32),
+                ("relu", c_int32), ("precision", c_int32), ("tma_round", c_int32), ("x", c_void_p), ("x_lo", c_void_p),
+                ("w_packed", c_void_p), ("bias", c_void_p), ("act", c_void_p), ("out", c_void_p), ("status", c_void_p)]
+
+
+class GomTf32SplitArgs(ctypes.Structure):
+    _fields_ = [("n", c_int64), ("x", c_void_p), ("hi", c_void_p), ("lo", c_void_p)]
+
+
 ADAM_MAX_SEGMENTS = 16
 
 
@@ -182,6 +197,8 @@ EXPORTS = [
     "gom_lpips_tap_forward", "gom_lpips_tap_backward", "gom_sizeof_lpips_input_args", "gom_sizeof_bias_relu_args",
     "gom_sizeof_relu_bwd_args", "gom_sizeof_lpips_tap_args", "gom_eval_metrics", "gom_sizeof_eval_metrics_args",
     "gom_conv_first_forward", "gom_conv_first_backward", "gom_sizeof_conv_first_args",
+    "gom_conv3x3", "gom_conv3x3_pack_weights", "gom_tf32_split", "gom_sizeof_conv3x3_args", "gom_sizeof_conv_pack_args",
+    "gom_sizeof_tf32_split_args",
     "gom_adam_step", "gom_sizeof_adam_args",
     "gom_mesh_raster_forward", "gom_mesh_raster_backward", "gom_sizeof_mesh_raster_args",
     "gom_shadow_mlp_forward", "gom_shadow_mlp_backward", "gom_shadow_mlp_weight_image_bytes", "gom_shadow_mlp_tile_words",
@@ -196,6 +213,7 @@ _STRUCTS = {
     "lpips_input": GomLpipsInputArgs, "bias_relu": GomBiasReluArgs, "relu_bwd": GomReluBwdArgs,
     "lpips_tap": GomLpipsTapArgs, "eval_metrics": GomEvalMetricsArgs,
     "conv_first": GomConvFirstArgs, "adam": GomAdamArgs,
+    "conv3x3": GomConv3x3Args, "conv_pack": GomConvPackArgs, "tf32_split": GomTf32SplitArgs,
     "mesh_raster": GomMeshRasterArgs, "shadow_mlp": GomShadowMlpArgs, "mesh_reg": GomMeshRegArgs,
 }
 _ENTRY_POINTS = ["gom_camera_from_KE", "gom_raster_forward", "gom_raster_backward", "gom_joint_transforms_forward",
@@ -204,6 +222,7 @@ _ENTRY_POINTS = ["gom_camera_from_KE", "gom_raster_forward", "gom_raster_backwar
                  "gom_lpips_input_forward", "gom_lpips_input_backward", "gom_bias_relu", "gom_relu_backward",
                  "gom_lpips_tap_forward", "gom_lpips_tap_backward", "gom_eval_metrics",
                  "gom_conv_first_forward", "gom_conv_first_backward", "gom_adam_step",
+                 "gom_conv3x3", "gom_conv3x3_pack_weights", "gom_tf32_split",
                  "gom_mesh_raster_forward", "gom_mesh_raster_backward", "gom_shadow_mlp_forward", "gom_shadow_mlp_backward",
                  "gom_mesh_regularizers"]
 

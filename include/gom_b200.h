@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define GOM_ABI_VERSION 5
+#define GOM_ABI_VERSION 6
 #define GOM_TILE 16              /* 16x16-pixel tiles, as upstream's BLOCK_X/BLOCK_Y */
 #define GOM_MAX_CHANNELS 4
 #define GOM_MAX_JOINTS 64
@@ -345,6 +345,54 @@ typedef struct {
 int gom_conv_first_forward(const GomConvFirstArgs *a, gom_stream_t stream);
 int gom_conv_first_backward(const GomConvFirstArgs *a, gom_stream_t stream);
 
+/* The other twelve VGG16 convolutions of LPIPS (conv1_2 ... conv5_3: 3x3, stride 1, zero padding 1, channel counts that
+ * are multiples of 32) as tcgen05 implicit GEMMs: forward with bias + ReLU fused, input gradient with the ReLU backward
+ * of the layer below fused.  Replaces `features[2:30]` of reference utils/lpips/pretrained_networks.py:96-134 and their
+ * autograd (cuDNN in the reference).  TF32 products, fp32 accumulation — the reference's stock cuDNN setting
+ * (torch.backends.cudnn.allow_tf32 is never touched by it); precision = 1 selects 3xTF32 (fp32-GEMM accuracy).
+ *
+ * Both directions are the same GEMM  out[p, n] = sum_{tap, c} x[p + tap - (1,1), c] * w_packed[tap][n][c]  over NHWC
+ * activations; what differs is the packed weight (gom_conv3x3_pack_weights) and the epilogue:
+ *   forward : x = layer input  [N,H,W,C],  w_packed = fwd pack [9][K][C],  out = relu(. + bias)          [N,H,W,K]
+ *   dgrad   : x = dL/dout      [N,H,W,K],  w_packed = bwd pack [9][C][K] (taps flipped),  out = dL/dx    [N,H,W,C],
+ *             multiplied by [act > 0] when `act` (the ReLU output that was this layer's input) is given.
+ * The operand tiles travel global -> shared memory as TMA tensor tiles (an 8 x 16-pixel x 32-channel box per tap and
+ * channel block, shifted by the tap, zero-filled outside the image: no im2col buffer), the accumulators live in
+ * tensor memory, the result leaves through TMA tensor stores. */
+typedef struct {
+    int32_t c_out, c_in;         /* K, C of the torch weight [K,C,3,3] */
+    int32_t transpose;           /* 0: forward pack [9][K][C];  1: dgrad pack [9][C][K] with the taps flipped */
+    int32_t split;               /* 0: one TF32-rounded image; 1: two images [hi | lo] for precision = 1 */
+    const float *weight;         /* [K,C,3,3] contiguous */
+    float *packed;               /* 9*K*C floats (x2 when split) */
+} GomConvPackArgs;
+int gom_conv3x3_pack_weights(const GomConvPackArgs *a, gom_stream_t stream);
+
+typedef struct {
+    int32_t n_images, height, width;
+    int32_t c_in, c_out;         /* channels of x and of out (dgrad: c_in = K, c_out = C) */
+    int32_t relu;                /* forward: apply ReLU after the bias */
+    int32_t precision;           /* 0: TF32;  1: 3xTF32 (needs x_lo and a split weight pack) */
+    int32_t tma_round;           /* 1: the TMA engine rounds x to TF32 (round-to-nearest) on its way to shared memory;
+                                    0: the tensor core truncates the fp32 words it reads */
+    const float *x;              /* [N,H,W,c_in] */
+    const float *x_lo;           /* precision = 1: x - tf32(x), same shape (gom_tf32_split); else NULL */
+    const float *w_packed;       /* from gom_conv3x3_pack_weights */
+    const float *bias;           /* [c_out] or NULL */
+    const float *act;            /* [N,H,W,c_out] or NULL: out *= [act > 0] */
+    float *out;                  /* [N,H,W,c_out] */
+    uint32_t *status;            /* [1] nullable: GOM_STATUS_TIMEOUT */
+} GomConv3x3Args;
+int gom_conv3x3(const GomConv3x3Args *a, gom_stream_t stream);
+
+/* hi = x rounded to TF32 (nearest, ties away), lo = x - hi; n a multiple of 4 */
+typedef struct {
+    int64_t n;
+    const float *x;
+    float *hi, *lo;
+} GomTf32SplitArgs;
+int gom_tf32_split(const GomTf32SplitArgs *a, gom_stream_t stream);
+
 /* --------------------------------------------------------------------------------------------------------------
  * Evaluation metrics.  Replaces reference eval.py:101-108 (Evaluator.psnr_metric / ssim_metric: skimage 0.18
  * structural_similarity defaults — 7x7 uniform window, sample covariance, K1 .01, K2 .03, data_range 2, 3-px crop)
@@ -523,6 +571,9 @@ size_t gom_sizeof_relu_bwd_args(void);
 size_t gom_sizeof_lpips_tap_args(void);
 size_t gom_sizeof_eval_metrics_args(void);
 size_t gom_sizeof_conv_first_args(void);
+size_t gom_sizeof_conv3x3_args(void);
+size_t gom_sizeof_conv_pack_args(void);
+size_t gom_sizeof_tf32_split_args(void);
 size_t gom_sizeof_adam_args(void);
 size_t gom_sizeof_mesh_raster_args(void);
 size_t gom_sizeof_shadow_mlp_args(void);

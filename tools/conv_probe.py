@@ -1,48 +1,174 @@
-"""Development tool: time the VGG16 convolutions of the LPIPS trunk on the GPU (cuDNN through torch), per layer, for
-the three ways the fused path can call them.  Decides LPIPS.conv_epilogue and the cudnn.benchmark setting."""
-import os, sys, json
-_R = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, _R)
+"""GPU probe of csrc/conv3x3_tc.cu: correctness against torch (fp64 on small shapes, cuDNN fp32 on the VGG shapes) and
+timing of every VGG16 layer shape of the LPIPS trunk next to cuDNN's TF32 kernels on the same box.
+
+    python tools/conv_probe.py [--quick] [--out gpurun_out/conv_probe.json]
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
 import torch
 import torch.nn.functional as F
 
-def timeit(fn, n=10):
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from gomavatar_b200 import conv as gconv  # noqa: E402
+
+LAYERS = [(64, 64, 512), (64, 128, 256), (128, 128, 256), (128, 256, 128), (256, 256, 128), (256, 512, 64),
+          (512, 512, 64), (512, 512, 32)]
+
+
+def ref_conv(x, w, b, relu, dtype=torch.float64):
+    y = F.conv2d(x.permute(0, 3, 1, 2).to(dtype), w.to(dtype), None if b is None else b.to(dtype), padding=1)
+    if relu:
+        y = y.relu()
+    return y.permute(0, 2, 3, 1).contiguous()
+
+
+def ref_dgrad(g, w, dtype=torch.float64):
+    y = F.conv_transpose2d(g.permute(0, 3, 1, 2).to(dtype), w.to(dtype), None, padding=1)
+    return y.permute(0, 2, 3, 1).contiguous()
+
+
+def rel_err(a, b):
+    a, b = a.double(), b.double()
+    return ((a - b).abs().max() / b.abs().max().clamp_min(1e-30)).item(), ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+def check_small(report):
+    torch.manual_seed(0)
+    dev = "cuda"
+    status = torch.zeros(1, dtype=torch.int32, device=dev)
+    cases = [(2, 20, 24, 64, 64), (1, 8, 16, 32, 32), (3, 17, 33, 64, 128), (1, 40, 48, 128, 256), (2, 9, 50, 96, 160),
+             (1, 32, 32, 256, 512)]
+    for (N, H, W, C, K) in cases:
+        x = torch.randn(N, H, W, C, device=dev).relu()
+        w = torch.randn(K, C, 3, 3, device=dev) / (3 * C ** 0.5)
+        b = torch.randn(K, device=dev) * 0.1
+        yr = ref_conv(x, w, b, True)
+        for prec in ("tf32", "3xtf32"):
+            wp = gconv.pack_weights(w, split=prec != "tf32")
+            y = gconv.conv3x3(x, wp, bias=b, relu=True, precision=prec, status=status)
+            torch.cuda.synchronize()
+            e = rel_err(y, yr)
+            report["small"].append({"case": [N, H, W, C, K], "dir": "fwd", "precision": prec, "max_rel": e[0], "l2_rel": e[1],
+                                    "status": int(status.item())})
+        y = gconv.conv3x3(x, gconv.pack_weights(w), bias=b, relu=True, tma_round=True, status=status)
+        e = rel_err(y, yr)
+        report["small"].append({"case": [N, H, W, C, K], "dir": "fwd", "precision": "tf32+tma_round", "max_rel": e[0], "l2_rel": e[1],
+                                "status": int(status.item())})
+        # cuDNN TF32 for scale
+        torch.backends.cudnn.allow_tf32 = True
+        yc = ref_conv(x, w, b, True, torch.float32)
+        e = rel_err(yc, yr)
+        report["small"].append({"case": [N, H, W, C, K], "dir": "fwd", "precision": "cudnn-tf32", "max_rel": e[0], "l2_rel": e[1]})
+        # dgrad with the fused mask
+        g = torch.randn(N, H, W, K, device=dev)
+        gr = ref_dgrad(g, w) * (x > 0)
+        for prec in ("tf32", "3xtf32"):
+            wp = gconv.pack_weights(w, transpose=True, split=prec != "tf32")
+            gx = gconv.conv3x3(g, wp, act=x, precision=prec, status=status)
+            torch.cuda.synchronize()
+            e = rel_err(gx, gr)
+            report["small"].append({"case": [N, H, W, C, K], "dir": "dgrad+mask", "precision": prec, "max_rel": e[0], "l2_rel": e[1],
+                                    "status": int(status.item())})
+
+
+def time_it(fn, iters):
     for _ in range(3):
         fn()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(n):
+    for _ in range(iters):
         fn()
     e1.record()
     torch.cuda.synchronize()
-    return e0.elapsed_time(e1) / n
+    return e0.elapsed_time(e1) / iters
+
+
+def bench_layers(report, iters, n_fwd=16, n_bwd=8):
+    dev = "cuda"
+    torch.backends.cudnn.allow_tf32 = True
+    torch.backends.cudnn.benchmark = False
+    status = torch.zeros(1, dtype=torch.int32, device=dev)
+    for (C, K, S) in LAYERS:
+        torch.manual_seed(1)
+        x = torch.randn(n_fwd, S, S, C, device=dev).relu()
+        w = torch.randn(K, C, 3, 3, device=dev) / (3 * C ** 0.5)
+        b = torch.randn(K, device=dev) * 0.1
+        wcl = w.contiguous(memory_format=torch.channels_last)
+        xn = x.permute(0, 3, 1, 2)                       # channels_last view
+        wp = gconv.pack_weights(w)
+        out = torch.empty(n_fwd, S, S, K, device=dev)
+        y = gconv.conv3x3(x, wp, bias=b, relu=True, out=out, status=status)
+        yc = torch.cudnn_convolution_relu(xn, wcl, b, (1, 1), (1, 1), (1, 1), 1).permute(0, 2, 3, 1)
+        torch.backends.cudnn.allow_tf32 = False
+        y32 = torch.cudnn_convolution_relu(xn, wcl, b, (1, 1), (1, 1), (1, 1), 1).permute(0, 2, 3, 1)
+        torch.backends.cudnn.allow_tf32 = True
+        e_own, e_cudnn = rel_err(y, y32), rel_err(yc, y32)
+        t_own = time_it(lambda: gconv.conv3x3(x, wp, bias=b, relu=True, out=out), iters)
+        t_cudnn = time_it(lambda: torch.cudnn_convolution_relu(xn, wcl, b, (1, 1), (1, 1), (1, 1), 1), iters)
+        flops = 2.0 * n_fwd * S * S * C * K * 9
+        row = {"layer": f"{C}->{K}@{S}", "fwd_ms": t_own, "fwd_cudnn_ms": t_cudnn, "fwd_tflops": flops / t_own / 1e9,
+               "fwd_cudnn_tflops": flops / t_cudnn / 1e9, "fwd_err_vs_fp32": e_own, "cudnn_err_vs_fp32": e_cudnn,
+               "status": int(status.item())}
+        # dgrad: gradient [n_bwd,S,S,K] -> [n_bwd,S,S,C], with the fused ReLU mask of the input activation
+        g = torch.randn(n_bwd, S, S, K, device=dev)
+        xa = x[:n_bwd].contiguous()
+        wpt = gconv.pack_weights(w, transpose=True)
+        gout = torch.empty(n_bwd, S, S, C, device=dev)
+        gx = gconv.conv3x3(g, wpt, act=xa, out=gout, status=status)
+        gn = g.permute(0, 3, 1, 2)
+        xin = xa.permute(0, 3, 1, 2)
+
+        def cudnn_dgrad():
+            return torch.ops.aten.convolution_backward(gn, xin, wcl, None, (1, 1), (1, 1), (1, 1), False, (0, 0), 1,
+                                                       (True, False, False))[0]
+        torch.backends.cudnn.allow_tf32 = False
+        g32 = cudnn_dgrad().permute(0, 2, 3, 1) * (xa > 0)
+        torch.backends.cudnn.allow_tf32 = True
+        gc = cudnn_dgrad().permute(0, 2, 3, 1) * (xa > 0)
+        row["dgrad_err_vs_fp32"], row["cudnn_dgrad_err_vs_fp32"] = rel_err(gx, g32), rel_err(gc, g32)
+        t_own = time_it(lambda: gconv.conv3x3(g, wpt, act=xa, out=gout), iters)
+        t_cudnn = time_it(cudnn_dgrad, iters)
+        flops = 2.0 * n_bwd * S * S * C * K * 9
+        row.update({"dgrad_ms": t_own, "dgrad_cudnn_ms": t_cudnn, "dgrad_tflops": flops / t_own / 1e9,
+                    "dgrad_cudnn_tflops": flops / t_cudnn / 1e9, "status_bwd": int(status.item())})
+        report["layers"].append(row)
+        print("%-13s fwd %.3f ms (cudnn %.3f) %4.0f TF/s | dgrad %.3f ms (cudnn %.3f) %4.0f TF/s | l2 err %.1e / %.1e | status %d %d" % (
+            row["layer"], row["fwd_ms"], row["fwd_cudnn_ms"], row["fwd_tflops"], row["dgrad_ms"], row["dgrad_cudnn_ms"],
+            row["dgrad_tflops"], row["fwd_err_vs_fp32"][1], row["dgrad_err_vs_fp32"][1], row["status"], row["status_bwd"]), flush=True)
+        del x, out, y, yc, y32, g, gout, gx, g32, gc
+        torch.cuda.empty_cache()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--iters", type=int, default=10)
+    ap.add_argument("--out", default="gpurun_out/conv_probe.json")
+    a = ap.parse_args()
+    report = {"small": [], "layers": [], "gpu": torch.cuda.get_device_name(0)}
+    t0 = time.time()
+    check_small(report)
+    worst = {}
+    for r in report["small"]:
+        k = r["precision"]
+        worst[k] = max(worst.get(k, 0.0), r["l2_rel"])
+    print("small shapes: worst l2 error per precision", worst, "status bits", sorted({r.get("status", 0) for r in report["small"]}), flush=True)
+    if not a.quick:
+        bench_layers(report, a.iters)
+    tot_own = sum(r["fwd_ms"] for r in report["layers"]), sum(r["dgrad_ms"] for r in report["layers"])
+    tot_cudnn = sum(r["fwd_cudnn_ms"] for r in report["layers"]), sum(r["dgrad_cudnn_ms"] for r in report["layers"])
+    report["totals_ms"] = {"own_fwd": tot_own[0], "own_dgrad": tot_own[1], "cudnn_fwd": tot_cudnn[0], "cudnn_dgrad": tot_cudnn[1]}
+    report["seconds"] = time.time() - t0
+    print(json.dumps(report["totals_ms"]))
+    os.makedirs(os.path.dirname(a.out) or ".", exist_ok=True)
+    with open(a.out, "w") as f:
+        json.dump(report, f, indent=1)
+
 
 if __name__ == "__main__":
-    B2 = int(sys.argv[1]) if len(sys.argv) > 1 else 16
-    dev = "cuda:0"
-    layers = [(3, 64, 512), (64, 64, 512), (64, 128, 256), (128, 128, 256), (128, 256, 128), (256, 256, 128),
-              (256, 512, 64), (512, 512, 64), (512, 512, 32)]
-    for bench_mode in (False, True):
-        torch.backends.cudnn.benchmark = bench_mode
-        for tf32 in (True, False):
-            torch.backends.cudnn.allow_tf32 = tf32
-            tot = {"conv": 0.0, "conv_relu": 0.0, "dgrad": 0.0}
-            mult = {0: 1, 1: 1, 2: 1, 3: 1, 4: 1, 5: 2, 6: 1, 7: 2, 8: 3}
-            for li, (ci, co, s) in enumerate(layers):
-                x = torch.randn(B2, ci, s, s, device=dev).contiguous(memory_format=torch.channels_last)
-                w = torch.randn(co, ci, 3, 3, device=dev).contiguous(memory_format=torch.channels_last) * 0.05
-                b = torch.randn(co, device=dev)
-                g = torch.randn(B2 // 2, co, s, s, device=dev).contiguous(memory_format=torch.channels_last)
-                xi = x[: B2 // 2]
-                t_conv = timeit(lambda: F.conv2d(x, w, None, padding=1))
-                try:
-                    t_cr = timeit(lambda: torch.cudnn_convolution_relu(x, w, b, (1, 1), (1, 1), (1, 1), 1))
-                except Exception as e:
-                    t_cr = float("nan")
-                t_dg = timeit(lambda: torch.ops.aten.convolution_backward(g, xi, w, None, (1, 1), (1, 1), (1, 1), False, (0, 0), 1, (True, False, False)))
-                fl = 2 * 9 * ci * co * s * s * B2 / 1e12
-                print(f"bench={bench_mode} tf32={tf32} {ci:4d}->{co:4d} @{s:3d}: conv {t_conv:7.3f} ms ({fl / t_conv * 1e3:6.0f} TF/s)  "
-                      f"conv+bias+relu(cudnn) {t_cr:7.3f} ms  dgrad(B={B2 // 2}) {t_dg:7.3f} ms ({fl / 2 / t_dg * 1e3:6.0f} TF/s)", flush=True)
-                tot["conv"] += t_conv * mult[li]; tot["conv_relu"] += t_cr * mult[li]; tot["dgrad"] += t_dg * mult[li]
-            print(f"== bench={bench_mode} tf32={tf32} trunk totals (13 convs): {json.dumps(tot)}", flush=True)
+    main()
