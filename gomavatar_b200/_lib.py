@@ -140,7 +140,8 @@ class GomConvPackArgs(ctypes.Structure):
 class GomConv3x3Args(ctypes.Structure):
     _fields_ = [("n_images", c_int32), ("height", c_int32), ("width", c_int32), ("c_in", c_int32), ("c_out", c_int32),
                 ("relu", c_int32), ("precision", c_int32), ("tma_round", c_int32), ("x", c_void_p), ("x_lo", c_void_p),
-                ("w_packed", c_void_p), ("bias", c_void_p), ("act", c_void_p), ("out", c_void_p), ("status", c_void_p)]
+                ("w_packed", c_void_p), ("bias", c_void_p), ("mask_in", c_void_p), ("mask_out", c_void_p), ("out", c_void_p),
+                ("status", c_void_p)]
 
 
 class GomTf32SplitArgs(ctypes.Structure):

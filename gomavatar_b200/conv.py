@@ -39,8 +39,12 @@ def tf32_low_part(x):
     return lo
 
 
-def conv3x3(x, w_packed, bias=None, relu=False, act=None, precision="tf32", tma_round=False, out=None, status=None):
-    """x: contiguous [N,H,W,C_in]; w_packed from ``pack_weights``; returns [N,H,W,C_out] = conv (+ bias) (ReLU) (* [act > 0])."""
+def conv3x3(x, w_packed, bias=None, relu=False, mask_in=None, mask_out=None, precision="tf32", tma_round=True, out=None,
+            status=None):
+    """x: contiguous [N,H,W,C_in]; w_packed from ``pack_weights``; returns [N,H,W,C_out] = conv (+ bias) (ReLU) (masked).
+
+    ``mask_out`` (int32 [N,H,W,C_out/32]) receives the ReLU bit mask of the result; ``mask_in`` (same shape) zeroes the
+    result where its bits are 0 (the fused ReLU backward of the dgrad)."""
     _need_cuda(x, "conv3x3")
     if not x.is_contiguous():
         raise _lib.GomError("conv3x3: x must be a contiguous NHWC tensor")
@@ -54,9 +58,15 @@ def conv3x3(x, w_packed, bias=None, relu=False, act=None, precision="tf32", tma_
     if out is None:
         out = torch.empty(N, H, W, c_out, dtype=torch.float32, device=x.device)
     x_lo = tf32_low_part(x) if strict else None
-    if act is not None and (tuple(act.shape) != tuple(out.shape) or not act.is_contiguous()):
-        raise _lib.GomError("conv3x3: act must be contiguous and shaped like the output")
+    for mk in (mask_in, mask_out):
+        if mk is not None and (tuple(mk.shape) != (N, H, W, c_out // 32) or mk.dtype != torch.int32 or not mk.is_contiguous()):
+            raise _lib.GomError("conv3x3: masks must be contiguous int32 [N,H,W,C_out/32]")
     call("gom_conv3x3", GomConv3x3Args(n_images=N, height=H, width=W, c_in=C, c_out=c_out, relu=int(relu), precision=int(strict),
-                                       tma_round=int(tma_round), x=ptr(x), x_lo=ptr(x_lo), w_packed=ptr(w_packed), bias=ptr(bias),
-                                       act=ptr(act), out=ptr(out), status=ptr(status)))
+                                       tma_round=int(tma_round and not strict), x=ptr(x), x_lo=ptr(x_lo), w_packed=ptr(w_packed),
+                                       bias=ptr(bias), mask_in=ptr(mask_in), mask_out=ptr(mask_out), out=ptr(out), status=ptr(status)))
     return out
+
+
+def new_mask(n, h, w, c, device):
+    """storage for the ReLU bit mask of an [n,h,w,c] activation"""
+    return torch.empty(n, h, w, c // 32, dtype=torch.int32, device=device)

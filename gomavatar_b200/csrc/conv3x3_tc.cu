@@ -1,20 +1,29 @@
 // conv3x3_tc.cu — 3x3 / stride 1 / pad 1 convolutions over NHWC fp32 activations as tcgen05 implicit GEMMs
-// (gom_conv3x3, include/gom_b200.h): the twelve VGG16 layers conv1_2 ... conv5_3 of LPIPS, forward (bias + ReLU fused)
-// and input gradient (ReLU backward of the layer below fused).  Reference: utils/lpips/pretrained_networks.py:96-134
-// (torchvision VGG16 `features`, executed by cuDNN there).
+// (gom_conv3x3, include/gom_b200.h): the twelve VGG16 layers conv1_2 ... conv5_3 of LPIPS, forward (bias + ReLU fused, ReLU
+// bit mask emitted) and input gradient (ReLU backward of the layer below fused through that bit mask).
+// Reference: utils/lpips/pretrained_networks.py:96-134 (torchvision VGG16 `features`, executed by cuDNN there).
 //
 // GEMM view:  out[p, n] = sum_{tap = (r,s)} sum_c x[p + (r-1, s-1), c] * Wp[tap][n][c],   M = pixels, N = c_out, K = 9 c_in.
-//   * M tile = 8 x 16 pixels of one image = 128 rows = the 128 lanes of tensor memory.
-//   * A operand of one k-step (tap, 32-channel block): the 8 x 16 x 32 box of x shifted by the tap, fetched by ONE TMA tensor
-//     copy (cp.async.bulk.tensor.4d) — the tensor map's bounds check zero-fills the padding ring, its 128-byte swizzle writes
-//     the K-major SWIZZLE_128B layout tcgen05.mma reads.  No im2col buffer exists anywhere.
-//   * B operand: the [n0 : n0 + NT] x 32 slab of the packed weight of that tap (3-D tensor map), same layout.
-//   * D: NT fp32 columns of tensor memory, double buffered (2 NT <= 512) so the epilogue of tile i overlaps the MMAs of tile i+1.
-//   * epilogue: tcgen05.ld 32 columns at a time, bias / ReLU / mask in registers, 32 rows x 128 B per warp into swizzled shared
-//     memory, one TMA tensor store per warp and chunk (the store clips at the image border).
-// Warp roles (192 threads, one persistent CTA per SM): warp 0 TMA producer, warp 1 MMA issuer (+ TMEM allocation), warps 2-5
-// epilogue (TMEM lane quarter = warp % 4).  Every mbarrier wait is bounded (gomtc::mbar_wait) and reports GOM_STATUS_TIMEOUT.
+// The kernel is bound by operand traffic L2 -> shared memory (measured: ~58 B/clk/SM whatever the tile shape), so the tiling
+// is chosen to move as few bytes per MMA as possible:
+//   * A CTA tile is 16 x 16 output pixels of one image = TWO M = 128 sub-tiles (left / right 8 columns; tensor-memory lane =
+//     16 rows x 8 columns) sharing every weight tile.
+//   * A operand: ONE TMA tensor copy per 32-channel block fetches the 18 x PITCH-pixel halo of the CTA tile (zero-filled outside
+//     the image by the tensor map's bounds check, 128-byte swizzle).  The nine taps are nine shifted VIEWS of that halo: the
+//     shared-memory matrix descriptor of tap (r,s), sub-tile m starts at pixel (r, s + 8 m) of the halo, its 8-row groups (one
+//     image row of 8 pixels each) are PITCH * 128 B apart (SBO).  9x fewer activation bytes than one shifted box per tap, no
+//     im2col buffer anywhere.
+//   * B operand: the [n0 : n0 + NT] x 32 slab of the packed weight of (tap, channel block), a ring of small stages.
+//   * D: 2 sub-tiles x NT fp32 columns of tensor memory, double buffered (4 NT <= 512): the epilogue of tile i overlaps the MMAs
+//     of tile i + 1.
+//   * epilogue (8 warps, two per TMEM lane quarter, one sub-tile each): tcgen05.ld 32 columns at a time, bias / ReLU / mask in
+//     registers, 32 pixels x 128 B per warp into swizzled shared memory, one TMA tensor store per warp and chunk (clipped at the
+//     image border); the forward also writes one ReLU mask word per pixel and chunk, which the dgrad of the layer above reads
+//     back instead of the activation itself (1/32 of the bytes, no shared-memory staging).
+// Warp roles (320 threads, one persistent CTA per SM): warp 0 TMA producer, warp 1 MMA issuer (+ TMEM allocation), warps 2-9
+// epilogue.  Every mbarrier wait is bounded (gomtc::mbar_wait) and reports GOM_STATUS_TIMEOUT.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "gom_common.cuh"
 #include "gom_tcgen05.cuh"
@@ -23,26 +32,34 @@ namespace {
 
 using namespace gomtc;
 
-constexpr int kTileH = 8, kTileW = 16;
-constexpr int kABytes = 128 * 128;                 // one A k-block: 128 pixel rows x 32 fp32 channels
-constexpr int kEpiWarpBytes = 4 * 4096;            // per epilogue warp: 2 store staging + 2 mask buffers of 32 rows x 128 B
-constexpr int kThreads = 192;
+constexpr int kTile = 16;                          // CTA tile: 16 x 16 output pixels
+constexpr int kHaloH = kTile + 2;
+constexpr int kThreads = 320;
+constexpr int kEpiWarps = 8;
+constexpr int kEpiWarpBytes = 4096;                // store staging of one epilogue warp: 32 pixels x 32 channels
 
-template <int NT, int KBLK, int STAGES> struct ConvCfg {
+template <int NT, int PITCH, int BST> struct ConvCfg {
+    static constexpr int A_BYTES = ((kHaloH * PITCH * 128 + 1023) / 1024) * 1024;
+    static constexpr int A_BUFS = 2;
     static constexpr int B_BYTES = NT * 128;
-    static constexpr int STAGE_BYTES = KBLK * (kABytes + B_BYTES);
-    static constexpr int SMEM = STAGES * STAGE_BYTES + 4 * kEpiWarpBytes + 1024;
-    static constexpr uint32_t TMEM_COLS = 2 * NT <= 32 ? 32 : 2 * NT <= 64 ? 64 : 2 * NT <= 128 ? 128 : 2 * NT <= 256 ? 256 : 512;
-    static_assert(2 * NT <= 512, "two accumulators must fit tensor memory");
+    static constexpr int SMEM = A_BUFS * A_BYTES + BST * B_BYTES + kEpiWarps * kEpiWarpBytes + 1024;
+    static constexpr uint32_t TMEM_COLS = 4 * NT <= 32 ? 32 : 4 * NT <= 64 ? 64 : 4 * NT <= 128 ? 128 : 4 * NT <= 256 ? 256 : 512;
+    static_assert(4 * NT <= 512, "two double-buffered accumulators must fit tensor memory");
+    static_assert(PITCH >= kTile + 2, "halo pitch");
     static_assert(SMEM <= 232448, "shared memory budget");
 };
 
 struct ConvDev {
     int n_tiles, n_tiles_n, tiles_w, tiles_h;
-    int c_blocks;                // c_in / (32 * KBLK)
+    int H, W;
+    int c_blocks;                // c_in / 32
     int n_pass;                  // 1 (TF32) or 3 (3xTF32: x*w_hi, x_lo*w_hi, x*w_lo)
-    int relu, has_act;
+    int relu;
+    int mask_words;              // c_out / 32: mask words per pixel
+    int base_offset_mode;        // debug: 1 = put the swizzle phase of the tap's start address into the descriptor's base-offset field
     const float *bias;
+    const uint32_t *mask_in;
+    uint32_t *mask_out;
     uint32_t *status;
 };
 
@@ -68,18 +85,20 @@ __device__ __forceinline__ bool elect_one() {
     asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
     return pred != 0;
 }
-// tcgen05.mma kind::tf32, A and B from shared memory; descriptors are passed as their low words (start address, LBO): the high
-// word (SBO = 1024 B, descriptor version, SWIZZLE_128B) is the constant 0x40004040 for every operand tile of this kernel
-constexpr uint32_t kDescHi = 0x40004040u;
-__device__ __forceinline__ void mma_tf32_ss_lo(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t acc) {
-    asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %4, 0;\n\tmov.b64 da, {%1, %5};\n\tmov.b64 db, {%2, %5};\n\t"
-                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %3, p;\n\t}"
-                 ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(acc), "r"(kDescHi) : "memory");
+// tcgen05.mma kind::tf32, A and B from shared memory, descriptors given as (low word, high word) pairs.
+__device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc, uint32_t acc) {
+    asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %6, 0;\n\tmov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
+                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %5, p;\n\t}"
+                 ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(acc) : "memory");
 }
-__device__ __forceinline__ void mma_tf32_ss_acc(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc) {
-    asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.eq.b32 p, 0, 0;\n\tmov.b64 da, {%1, %4};\n\tmov.b64 db, {%2, %4};\n\t"
-                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %3, p;\n\t}"
-                 ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(kDescHi) : "memory");
+__device__ __forceinline__ void mma_tf32_acc(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc) {
+    asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.eq.b32 p, 0, 0;\n\tmov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
+                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %5, p;\n\t}"
+                 ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc) : "memory");
+}
+// high word of a K-major SWIZZLE_128B descriptor: SBO (bytes >> 4) | version 1 (bit 46) | base offset (bits 49-51) | layout 2 (bits 61-63)
+__host__ __device__ constexpr uint32_t desc_hi(uint32_t sbo_bytes, uint32_t base_offset) {
+    return (sbo_bytes >> 4) | (1u << 14) | (base_offset << 17) | (2u << 29);
 }
 
 struct TileCoord { int n0, w0, h0, img; };
@@ -88,32 +107,32 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvDev &p, int tile, int
     const int ni = tile % p.n_tiles_n;
     int m = tile / p.n_tiles_n;
     t.n0 = ni * nt;
-    t.w0 = (m % p.tiles_w) * kTileW;
+    t.w0 = (m % p.tiles_w) * kTile;
     m /= p.tiles_w;
-    t.h0 = (m % p.tiles_h) * kTileH;
+    t.h0 = (m % p.tiles_h) * kTile;
     t.img = m / p.tiles_h;
     return t;
 }
 
-template <int NT, int KBLK, int STAGES>
+template <int NT, int PITCH, int BST>
 __global__ void __launch_bounds__(kThreads, 1)
 k_conv3x3(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_a_lo,
-          const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_out,
-          const __grid_constant__ CUtensorMap map_act, const ConvDev p) {
-    using Cfg = ConvCfg<NT, KBLK, STAGES>;
+          const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_out, const ConvDev p) {
+    using Cfg = ConvCfg<NT, PITCH, BST>;
     extern __shared__ uint8_t smem_raw[];
-    __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], tfull_bar[2], tempty_bar[2], act_bar[4][2];
+    __shared__ uint64_t afull_bar[Cfg::A_BUFS], aempty_bar[Cfg::A_BUFS], bfull_bar[BST], bempty_bar[BST], tfull_bar[2], tempty_bar[2];
     __shared__ uint32_t tmem_slot;
     __shared__ int abort_flag;
 
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t epi_base = smem_base + STAGES * Cfg::STAGE_BYTES;
+    const uint32_t b_base = smem_base + Cfg::A_BUFS * Cfg::A_BYTES;
+    const uint32_t epi_base = b_base + BST * Cfg::B_BYTES;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < STAGES; i++) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-        for (int i = 0; i < 2; i++) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 4); }
-        for (int i = 0; i < 4; i++) { mbar_init(&act_bar[i][0], 1); mbar_init(&act_bar[i][1], 1); }
+        for (int i = 0; i < Cfg::A_BUFS; i++) { mbar_init(&afull_bar[i], 1); mbar_init(&aempty_bar[i], 1); }
+        for (int i = 0; i < BST; i++) { mbar_init(&bfull_bar[i], 1); mbar_init(&bempty_bar[i], 1); }
+        for (int i = 0; i < 2; i++) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], kEpiWarps); }
         abort_flag = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -126,109 +145,130 @@ k_conv3x3(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
     tc_fence_after();
     const uint32_t tmem = tmem_slot;
     volatile int *ab = &abort_flag;
-    const int k_steps = p.n_pass * 9 * p.c_blocks;
+    const int items_per_tile = p.n_pass * p.c_blocks;             // halo loads per tile; each is followed by 9 weight tiles
 
     if (warp == 0) {
         // ------------------------------------------------------------------------------------------- TMA producer
-        // The whole warp walks the loop (warp-uniform control flow keeps addresses in uniform registers); one elected lane
-        // issues.  The barrier of the NEXT stage is probed before the copies of the current one are issued, so its ~90-cycle
-        // answer arrives while they are being queued.
+        // One elected lane issues; the loop itself is warp-uniform.  Halo i + 1 is requested after the sixth weight tile of
+        // halo i: by then the MMA warp has released the buffer it goes into (it is at most BST weight tiles behind).
         if (elect_one()) {
             asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
             asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
         }
-        uint32_t st = 0, ph = 0;
+        uint32_t bst = 0, bph = 0, a_count = 0;
         bool ok = true;
-        bool ready = mbar_test_wait(&empty_bar[0], 1u);
+        // iterator over halo items (tile, pass, channel block), one ahead of the weight stream
+        int a_tile = blockIdx.x, a_item = 0;
+        auto issue_halo = [&]() -> bool {
+            if (a_tile >= p.n_tiles) return true;
+            const TileCoord t = decode_tile(p, a_tile, NT);
+            const int pass = a_item / p.c_blocks, cb = a_item - pass * p.c_blocks;
+            const uint32_t buf = a_count & 1u, ph = (a_count >> 1) & 1u;
+            if (!mbar_wait(&aempty_bar[buf], ph ^ 1u, ab)) return false;
+            if (elect_one()) {
+                mbar_expect_tx(&afull_bar[buf], kHaloH * PITCH * 128);
+                tma_load_4d(smem_base + buf * Cfg::A_BYTES, pass == 1 ? &map_a_lo : &map_a, cb * 32, t.w0 - 1, t.h0 - 1, t.img, &afull_bar[buf]);
+            }
+            __syncwarp();
+            a_count++;
+            if (++a_item == items_per_tile) { a_item = 0; a_tile += gridDim.x; }
+            return true;
+        };
+        ok = issue_halo();
+        bool ready = mbar_test_wait(&bempty_bar[0], 1u);
         for (int tile = blockIdx.x; tile < p.n_tiles && ok; tile += gridDim.x) {
             const TileCoord t = decode_tile(p, tile, NT);
-            for (int pass = 0; pass < p.n_pass && ok; pass++) {
-                const CUtensorMap *ma = pass == 1 ? &map_a_lo : &map_a;
+            for (int item = 0; item < items_per_tile && ok; item++) {
+                const int pass = item / p.c_blocks, cb = item - pass * p.c_blocks;
                 const int tap_off = pass == 2 ? 9 : 0;                  // the lo weight image follows the hi image
-                for (int tap = 0; tap < 9 && ok; tap++) {
-                    const int r = tap / 3, s = tap - 3 * r;
-                    for (int cb = 0; cb < p.c_blocks; cb++) {
-                        if (!ready && !mbar_wait(&empty_bar[st], ph ^ 1u, ab)) { ok = false; break; }
-                        const uint32_t a_dst = smem_base + st * Cfg::STAGE_BYTES, b_dst = a_dst + KBLK * kABytes;
-                        uint64_t *fb = &full_bar[st];
-                        if (++st == STAGES) { st = 0; ph ^= 1u; }
-                        ready = mbar_test_wait(&empty_bar[st], ph ^ 1u);
-                        if (elect_one()) {
-                            mbar_expect_tx(fb, Cfg::STAGE_BYTES);
-#pragma unroll
-                            for (int kb = 0; kb < KBLK; kb++) {
-                                const int c0 = (cb * KBLK + kb) * 32;
-                                tma_load_4d(a_dst + kb * kABytes, ma, c0, t.w0 + s - 1, t.h0 + r - 1, t.img, fb);
-                                tma_load_3d(b_dst + kb * Cfg::B_BYTES, &map_b, c0, t.n0, tap_off + tap, fb);
-                            }
-                        }
-                        __syncwarp();
+                for (int tap = 0; tap < 9; tap++) {
+                    if (tap == 5 && !issue_halo()) { ok = false; break; }
+                    if (!ready && !mbar_wait(&bempty_bar[bst], bph ^ 1u, ab)) { ok = false; break; }
+                    const uint32_t dst = b_base + bst * Cfg::B_BYTES;
+                    uint64_t *fb = &bfull_bar[bst];
+                    if (++bst == BST) { bst = 0; bph ^= 1u; }
+                    ready = mbar_test_wait(&bempty_bar[bst], bph ^ 1u);
+                    if (elect_one()) {
+                        mbar_expect_tx(fb, Cfg::B_BYTES);
+                        tma_load_3d(dst, &map_b, cb * 32, t.n0, tap_off + tap, fb);
                     }
+                    __syncwarp();
                 }
             }
         }
     } else if (warp == 1) {
         // --------------------------------------------------------------------------------------------- MMA issuer
         const uint32_t idesc = instr_desc_n(NT);
-        const uint32_t desc_base = ((smem_base & 0x3FFFFu) >> 4) | (1u << 16);      // low word of the descriptor of stage 0
-        uint32_t st = 0, ph = 0, tcount = 0;
+        const uint32_t a_desc0 = ((smem_base & 0x3FFFFu) >> 4) | (1u << 16);        // low descriptor word of halo buffer 0, pixel (0,0)
+        const uint32_t b_desc0 = ((b_base & 0x3FFFFu) >> 4) | (1u << 16);
+        constexpr uint32_t kBHi = desc_hi(1024, 0);
+        uint32_t bst = 0, bph = 0, a_count = 0, tcount = 0;
         bool ok = true;
-        bool ready = mbar_test_wait(&full_bar[0], 0u);
+        bool ready = mbar_test_wait(&bfull_bar[0], 0u);
         for (int tile = blockIdx.x; tile < p.n_tiles && ok; tile += gridDim.x, tcount++) {
             const uint32_t acc = tcount & 1u, aph = (tcount >> 1) & 1u;
             if (!mbar_wait(&tempty_bar[acc], aph ^ 1u, ab)) { ok = false; break; }
-            tc_fence_after();
-            const uint32_t d = tmem + acc * NT;
-            for (int ks = 0; ks < k_steps; ks++) {
-                if (!ready && !mbar_wait(&full_bar[st], ph, ab)) { ok = false; break; }
-                const uint32_t a_lo = desc_base + st * (Cfg::STAGE_BYTES >> 4), b_lo = a_lo + ((KBLK * kABytes) >> 4);
-                uint64_t *eb = &empty_bar[st];
-                if (++st == STAGES) { st = 0; ph ^= 1u; }
-                ready = mbar_test_wait(&full_bar[st], ph);
-                tc_fence_after();
-                if (elect_one()) {
+            const uint32_t d0 = tmem + acc * (2 * NT);
+            for (int item = 0; item < items_per_tile && ok; item++, a_count++) {
+                const uint32_t abuf = a_count & 1u;
+                if (!mbar_wait(&afull_bar[abuf], (a_count >> 1) & 1u, ab)) { ok = false; break; }
+                const uint32_t a_buf_lo = a_desc0 + abuf * (Cfg::A_BYTES >> 4);
 #pragma unroll
-                    for (int kb = 0; kb < KBLK; kb++)
+                for (int tap = 0; tap < 9; tap++) {
+                    const int r = tap / 3, s = tap % 3;
+                    if (!ready && !mbar_wait(&bfull_bar[bst], bph, ab)) { ok = false; break; }
+                    const uint32_t b_lo = b_desc0 + bst * (Cfg::B_BYTES >> 4);
+                    uint64_t *eb = &bempty_bar[bst];
+                    if (++bst == BST) { bst = 0; bph ^= 1u; }
+                    ready = mbar_test_wait(&bfull_bar[bst], bph);
+                    tc_fence_after();
+                    if (elect_one()) {
+                        const uint32_t a_hi = desc_hi(PITCH * 128, p.base_offset_mode ? (uint32_t)s : 0u);
 #pragma unroll
-                        for (int k = 0; k < 4; k++) {
-                            const uint32_t al = a_lo + ((kb * kABytes + k * 32) >> 4), bl = b_lo + ((kb * Cfg::B_BYTES + k * 32) >> 4);
-                            if (kb == 0 && k == 0) mma_tf32_ss_lo(d, al, bl, idesc, (uint32_t)(ks != 0));
-                            else mma_tf32_ss_acc(d, al, bl, idesc);
+                        for (int m = 0; m < 2; m++)
+#pragma unroll
+                            for (int k = 0; k < 4; k++) {
+                                const uint32_t al = a_buf_lo + (((r * PITCH + s + 8 * m) * 128 + k * 32) >> 4);
+                                const uint32_t bl = b_lo + ((k * 32) >> 4);
+                                if (k == 0 && tap == 0) mma_tf32(d0 + m * NT, al, a_hi, bl, kBHi, idesc, (uint32_t)(item != 0));
+                                else mma_tf32_acc(d0 + m * NT, al, a_hi, bl, kBHi, idesc);
+                            }
+                        tc_commit(eb);
+                        if (tap == 8) {
+                            tc_commit(&aempty_bar[abuf]);
+                            if (item == items_per_tile - 1) tc_commit(&tfull_bar[acc]);
                         }
-                    tc_commit(eb);
-                    if (ks == k_steps - 1) tc_commit(&tfull_bar[acc]);
+                    }
+                    __syncwarp();
                 }
-                __syncwarp();
             }
         }
     } else {
         // ----------------------------------------------------------------------------------------------- epilogue
-        const int q = warp & 3;                                   // TMEM lane quarter this warp may access
-        const uint32_t wbase = epi_base + (warp - 2) * kEpiWarpBytes;   // [stage 0 | stage 1 | act 0 | act 1], 4 KB each
+        const int e = warp - 2;
+        const int m = e >> 2;                                     // sub-tile (left / right 8 columns)
+        const int q = warp & 3;                                   // TMEM lane quarter this warp may access = tile rows 4q .. 4q + 3
+        const uint32_t sbuf = epi_base + e * kEpiWarpBytes;
         const uint32_t row_off = lane * 128;
         const int sw = lane & 7;
-        uint32_t tcount = 0, g = 0;                               // g: running 32-column chunk counter (buffer / parity selector)
+        uint32_t tcount = 0;
         bool ok = true;
         for (int tile = blockIdx.x; tile < p.n_tiles && ok; tile += gridDim.x, tcount++) {
             const TileCoord t = decode_tile(p, tile, NT);
-            const int hq = t.h0 + 2 * q;                          // this warp's two pixel rows of the tile
+            const int hw = t.h0 + 4 * q, ww = t.w0 + 8 * m;       // this warp's 4 x 8 pixels
+            const int ph_ = hw + (lane >> 3), pw = ww + (lane & 7);
+            const bool inside = ph_ < p.H && pw < p.W;
+            const long long mask_idx = (((long long)t.img * p.H + ph_) * p.W + pw) * p.mask_words + (t.n0 >> 5);
             const uint32_t acc = tcount & 1u, aph = (tcount >> 1) & 1u;
-            if (p.has_act && lane == 0) {
-                mbar_expect_tx(&act_bar[q][g & 1u], 4096);
-                tma_load_4d(wbase + 8192 + (g & 1u) * 4096, &map_act, t.n0, t.w0, hq, t.img, &act_bar[q][g & 1u]);
-            }
             if (!mbar_wait(&tfull_bar[acc], aph, ab)) { ok = false; break; }
             tc_fence_after();
             constexpr int kChunks = NT / 32;
 #pragma unroll 1
-            for (int ch = 0; ch < kChunks; ch++, g++) {
-                if (p.has_act && ch + 1 < kChunks && lane == 0) {
-                    const uint32_t nb = (g + 1) & 1u;
-                    mbar_expect_tx(&act_bar[q][nb], 4096);
-                    tma_load_4d(wbase + 8192 + nb * 4096, &map_act, t.n0 + (ch + 1) * 32, t.w0, hq, t.img, &act_bar[q][nb]);
-                }
+            for (int ch = 0; ch < kChunks; ch++) {
                 uint32_t v[32];
-                tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + acc * NT + ch * 32, v);
+                tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + acc * (2 * NT) + m * NT + ch * 32, v);
+                uint32_t mword = 0xFFFFFFFFu;
+                if (p.mask_in && inside) mword = __ldg(p.mask_in + mask_idx + ch);
                 tmem_wait_ld();
                 if (ch == kChunks - 1) {                          // accumulator drained: hand it back before the stores
                     tc_fence_before();
@@ -250,24 +290,19 @@ k_conv3x3(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
 #pragma unroll
                     for (int j = 0; j < 32; j++) f[j] = fmaxf(f[j], 0.f);
                 }
-                if (p.has_act) {
-                    const uint32_t b = g & 1u;
-                    if (!mbar_wait(&act_bar[q][b], (g >> 1) & 1u, ab)) { ok = false; break; }
-                    const uint32_t abuf = wbase + 8192 + b * 4096 + row_off;
+                if (p.mask_in) {
 #pragma unroll
-                    for (int j = 0; j < 8; j++) {
-                        float4 y;
-                        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(y.x), "=f"(y.y), "=f"(y.z), "=f"(y.w) : "r"(abuf + ((j ^ sw) << 4)));
-                        f[4 * j] = y.x > 0.f ? f[4 * j] : 0.f;
-                        f[4 * j + 1] = y.y > 0.f ? f[4 * j + 1] : 0.f;
-                        f[4 * j + 2] = y.z > 0.f ? f[4 * j + 2] : 0.f;
-                        f[4 * j + 3] = y.w > 0.f ? f[4 * j + 3] : 0.f;
-                    }
+                    for (int j = 0; j < 32; j++) f[j] = (mword >> j) & 1u ? f[j] : 0.f;
                 }
-                // the staging buffer about to be written was handed to a TMA store two chunks ago: wait until it has been read
-                if (lane == 0) bulk_wait_read<1>();
+                if (p.mask_out) {
+                    uint32_t w = 0;
+#pragma unroll
+                    for (int j = 0; j < 32; j++) w |= (f[j] > 0.f ? 1u : 0u) << j;
+                    if (inside) p.mask_out[mask_idx + ch] = w;
+                }
+                // the staging buffer was handed to a TMA store one chunk ago: wait until it has been read
+                if (lane == 0) bulk_wait_read<0>();
                 __syncwarp();
-                const uint32_t sbuf = wbase + (g & 1u) * 4096;
 #pragma unroll
                 for (int j = 0; j < 8; j++)
                     asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(sbuf + row_off + ((j ^ sw) << 4)), "f"(f[4 * j]), "f"(f[4 * j + 1]),
@@ -275,7 +310,7 @@ k_conv3x3(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
                 fence_async_smem();
                 __syncwarp();
                 if (lane == 0) {
-                    tma_store_4d(&map_out, sbuf, t.n0 + ch * 32, t.w0, hq, t.img);
+                    tma_store_4d(&map_out, sbuf, t.n0 + ch * 32, ww, hw, t.img);
                     bulk_commit();
                 }
             }
@@ -349,11 +384,11 @@ int conv_setup(void) {
     return GOM_OK;
 }
 
-// NHWC activation [N,H,W,C] as a 4-D tensor (C, W, H, N) with a (32, 16, box_h, 1) box, 128-byte swizzle, zero fill
-int make_act_map(CUtensorMap *m, const float *base, int N, int H, int W, int C, int box_h, bool tf32_round) {
+// NHWC activation [N,H,W,C] as a 4-D tensor (C, W, H, N) with a (32, box_w, box_h, 1) box, 128-byte swizzle, zero fill
+int make_act_map(CUtensorMap *m, const float *base, int N, int H, int W, int C, int box_w, int box_h, bool tf32_round) {
     const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
     const cuuint64_t strides[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4};
-    const cuuint32_t box[4] = {32, (cuuint32_t)kTileW, (cuuint32_t)box_h, 1};
+    const cuuint32_t box[4] = {32, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
     const cuuint32_t estr[4] = {1, 1, 1, 1};
     const CUresult r = g_encode(m, tf32_round ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void *)base, dims,
                                 strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -373,17 +408,26 @@ int make_weight_map(CUtensorMap *m, const float *base, int taps, int c_out, int 
     return GOM_OK;
 }
 
-template <int NT, int KBLK, int STAGES>
-int launch_conv(const CUtensorMap &ma, const CUtensorMap &malo, const CUtensorMap &mb, const CUtensorMap &mo, const CUtensorMap &mact,
-                const ConvDev &d, cudaStream_t stream) {
-    using Cfg = ConvCfg<NT, KBLK, STAGES>;
+template <int NT, int PITCH, int BST>
+int launch_conv(const GomConv3x3Args *p, ConvDev &d, cudaStream_t stream) {
+    using Cfg = ConvCfg<NT, PITCH, BST>;
     static bool configured = false;
     if (!configured) {
-        GOM_CUDA(cudaFuncSetAttribute(k_conv3x3<NT, KBLK, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+        GOM_CUDA(cudaFuncSetAttribute(k_conv3x3<NT, PITCH, BST>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
         configured = true;
     }
+    d.n_tiles_n = p->c_out / NT;
+    const long long n_tiles = (long long)p->n_images * d.tiles_h * d.tiles_w * d.n_tiles_n;
+    GOM_REQUIRE(n_tiles < (1ll << 30), "too many tiles");
+    d.n_tiles = (int)n_tiles;
+    CUtensorMap ma, malo, mb, mo;
+    const bool round = p->tma_round && p->precision == 0;
+    if (int rc = make_act_map(&ma, p->x, p->n_images, p->height, p->width, p->c_in, PITCH, kHaloH, round)) return rc;
+    if (int rc = make_act_map(&malo, p->precision == 1 ? p->x_lo : p->x, p->n_images, p->height, p->width, p->c_in, PITCH, kHaloH, false)) return rc;
+    if (int rc = make_weight_map(&mb, p->w_packed, p->precision == 1 ? 18 : 9, p->c_out, p->c_in, NT)) return rc;
+    if (int rc = make_act_map(&mo, p->out, p->n_images, p->height, p->width, p->c_out, 8, 4, false)) return rc;
     const int grid = d.n_tiles < g_sms ? d.n_tiles : g_sms;
-    k_conv3x3<NT, KBLK, STAGES><<<grid, kThreads, Cfg::SMEM, stream>>>(ma, malo, mb, mo, mact, d);
+    k_conv3x3<NT, PITCH, BST><<<grid, kThreads, Cfg::SMEM, stream>>>(ma, malo, mb, mo, d);
     GOM_LAUNCH_CHECK();
     return GOM_OK;
 }
@@ -421,43 +465,35 @@ extern "C" int gom_conv3x3(const GomConv3x3Args *p, gom_stream_t stream_) {
     GOM_REQUIRE(p->x && p->w_packed && p->out, "null pointer");
     GOM_REQUIRE(p->precision == 0 || (p->precision == 1 && p->x_lo), "precision = 1 needs x_lo");
     GOM_REQUIRE(((uintptr_t)p->x % 16) == 0 && ((uintptr_t)p->out % 16) == 0 && ((uintptr_t)p->w_packed % 16) == 0 &&
-                ((uintptr_t)p->act % 16) == 0 && ((uintptr_t)p->x_lo % 16) == 0 && ((uintptr_t)p->bias % 16) == 0, "16-byte alignment");
+                ((uintptr_t)p->x_lo % 16) == 0 && ((uintptr_t)p->bias % 16) == 0, "16-byte alignment");
     if (int rc = conv_setup()) return rc;
     cudaStream_t stream = (cudaStream_t)stream_;
-    const int nt = p->c_out % 256 == 0 ? 256 : p->c_out % 128 == 0 ? 128 : p->c_out % 64 == 0 ? 64 : 32;
-    const int kblk = (nt <= 64 && p->c_in % 64 == 0) ? 2 : 1;
 
     ConvDev d{};
-    d.tiles_w = gom_div_up(p->width, kTileW);
-    d.tiles_h = gom_div_up(p->height, kTileH);
-    d.n_tiles_n = p->c_out / nt;
-    const long long n_tiles = (long long)p->n_images * d.tiles_h * d.tiles_w * d.n_tiles_n;
-    GOM_REQUIRE(n_tiles < (1ll << 30), "too many tiles");
-    d.n_tiles = (int)n_tiles;
-    d.c_blocks = p->c_in / (32 * kblk);
+    d.H = p->height; d.W = p->width;
+    d.tiles_w = gom_div_up(p->width, kTile);
+    d.tiles_h = gom_div_up(p->height, kTile);
+    d.c_blocks = p->c_in / 32;
     d.n_pass = p->precision == 1 ? 3 : 1;
     d.relu = p->relu;
-    d.has_act = p->act != nullptr;
+    d.mask_words = p->c_out / 32;
     d.bias = p->bias;
+    d.mask_in = p->mask_in;
+    d.mask_out = p->mask_out;
     d.status = p->status;
+    static int bo_mode = -1, pitch18 = -1;
+    if (bo_mode < 0) { const char *e = getenv("GOM_CONV_BASE_OFFSET"); bo_mode = e ? atoi(e) : 0; }
+    if (pitch18 < 0) { const char *e = getenv("GOM_CONV_PITCH18"); pitch18 = e ? atoi(e) : 0; }
+    d.base_offset_mode = bo_mode;
 
-    CUtensorMap ma, malo, mb, mo, mact;
-    const bool round = p->tma_round && p->precision == 0;
-    if (int rc = make_act_map(&ma, p->x, p->n_images, p->height, p->width, p->c_in, kTileH, round)) return rc;
-    if (int rc = make_act_map(&malo, p->precision == 1 ? p->x_lo : p->x, p->n_images, p->height, p->width, p->c_in, kTileH, false)) return rc;
-    if (int rc = make_weight_map(&mb, p->w_packed, p->precision == 1 ? 18 : 9, p->c_out, p->c_in, nt)) return rc;
-    if (int rc = make_act_map(&mo, p->out, p->n_images, p->height, p->width, p->c_out, 2, false)) return rc;
-    if (int rc = make_act_map(&mact, p->act ? p->act : p->out, p->n_images, p->height, p->width, p->c_out, 2, false)) return rc;
-
-    gom_prof_begin(p->act || !p->relu ? GOM_PROF_CONV3X3_DGRAD : GOM_PROF_CONV3X3_FWD, stream);
+    const int slot = p->relu ? GOM_PROF_CONV3X3_FWD : GOM_PROF_CONV3X3_DGRAD;
+    gom_prof_begin(slot, stream);
     int rc;
-    if (nt == 256) rc = launch_conv<256, 1, 3>(ma, malo, mb, mo, mact, d, stream);
-    else if (nt == 128) rc = launch_conv<128, 1, 4>(ma, malo, mb, mo, mact, d, stream);
-    else if (nt == 64 && kblk == 2) rc = launch_conv<64, 2, 3>(ma, malo, mb, mo, mact, d, stream);
-    else if (nt == 64) rc = launch_conv<64, 1, 6>(ma, malo, mb, mo, mact, d, stream);
-    else rc = launch_conv<32, 1, 6>(ma, malo, mb, mo, mact, d, stream);
+    if (p->c_out % 128 == 0) rc = pitch18 ? launch_conv<128, 18, 5>(p, d, stream) : launch_conv<128, 24, 5>(p, d, stream);
+    else if (p->c_out % 64 == 0) rc = pitch18 ? launch_conv<64, 18, 8>(p, d, stream) : launch_conv<64, 24, 8>(p, d, stream);
+    else rc = pitch18 ? launch_conv<32, 18, 8>(p, d, stream) : launch_conv<32, 24, 8>(p, d, stream);
     if (rc) return rc;
-    gom_prof_end(p->act || !p->relu ? GOM_PROF_CONV3X3_DGRAD : GOM_PROF_CONV3X3_FWD, stream);
+    gom_prof_end(slot, stream);
     return GOM_OK;
 }
 

@@ -353,12 +353,14 @@ int gom_conv_first_backward(const GomConvFirstArgs *a, gom_stream_t stream);
  *
  * Both directions are the same GEMM  out[p, n] = sum_{tap, c} x[p + tap - (1,1), c] * w_packed[tap][n][c]  over NHWC
  * activations; what differs is the packed weight (gom_conv3x3_pack_weights) and the epilogue:
- *   forward : x = layer input  [N,H,W,C],  w_packed = fwd pack [9][K][C],  out = relu(. + bias)          [N,H,W,K]
+ *   forward : x = layer input  [N,H,W,C],  w_packed = fwd pack [9][K][C],  out = relu(. + bias)          [N,H,W,K];
+ *             mask_out (optional) receives one word per pixel and 32 output channels, bit j = [out channel 32 w + j > 0];
  *   dgrad   : x = dL/dout      [N,H,W,K],  w_packed = bwd pack [9][C][K] (taps flipped),  out = dL/dx    [N,H,W,C],
- *             multiplied by [act > 0] when `act` (the ReLU output that was this layer's input) is given.
- * The operand tiles travel global -> shared memory as TMA tensor tiles (an 8 x 16-pixel x 32-channel box per tap and
- * channel block, shifted by the tap, zero-filled outside the image: no im2col buffer), the accumulators live in
- * tensor memory, the result leaves through TMA tensor stores. */
+ *             multiplied by the ReLU mask of the activation that was this layer's input when mask_in (the mask_out of
+ *             the forward call that produced that activation) is given.
+ * The activations travel global -> shared memory as TMA tensor tiles (the 18 x 18-pixel halo of a 16 x 16-pixel output
+ * tile per 32-channel block, zero-filled outside the image; the nine taps are shifted views of it: no im2col buffer),
+ * the accumulators live in tensor memory, the result leaves through TMA tensor stores. */
 typedef struct {
     int32_t c_out, c_in;         /* K, C of the torch weight [K,C,3,3] */
     int32_t transpose;           /* 0: forward pack [9][K][C];  1: dgrad pack [9][C][K] with the taps flipped */
@@ -376,16 +378,17 @@ typedef struct {
     int32_t tma_round;           /* 1: the TMA engine rounds x to TF32 (round-to-nearest) on its way to shared memory;
                                     0: the tensor core truncates the fp32 words it reads */
     const float *x;              /* [N,H,W,c_in] */
-    const float *x_lo;           /* precision = 1: x - tf32(x), same shape (gom_tf32_split); else NULL */
+    const float *x_lo;           /* precision = 1: x - trunc_tf32(x), same shape (gom_tf32_split); else NULL */
     const float *w_packed;       /* from gom_conv3x3_pack_weights */
     const float *bias;           /* [c_out] or NULL */
-    const float *act;            /* [N,H,W,c_out] or NULL: out *= [act > 0] */
+    const uint32_t *mask_in;     /* [N,H,W,c_out/32] or NULL: out is zeroed where the bit is 0 */
+    uint32_t *mask_out;          /* [N,H,W,c_out/32] or NULL: bit = [out > 0] */
     float *out;                  /* [N,H,W,c_out] */
     uint32_t *status;            /* [1] nullable: GOM_STATUS_TIMEOUT */
 } GomConv3x3Args;
 int gom_conv3x3(const GomConv3x3Args *a, gom_stream_t stream);
 
-/* hi = x rounded to TF32 (nearest, ties away), lo = x - hi; n a multiple of 4 */
+/* hi = x truncated to TF32 (what the tensor core reads from an fp32 word; nullable), lo = x - hi; n a multiple of 4 */
 typedef struct {
     int64_t n;
     const float *x;
