@@ -51,8 +51,10 @@ def parse():
     ap.add_argument("--lpips-precision", default="tf32", choices=["tf32", "fp32", "bf16"],
                     help="cuDNN conv precision of the LPIPS VGG trunk; tf32 = torch/cuDNN default = the reference's stock path")
     ap.add_argument("--lpips-torch", action="store_true", help="A/B: plain torch LPIPS glue instead of csrc/lpips.cu")
+    ap.add_argument("--lpips-conv", default="tcgen05", choices=["tcgen05", "cudnn"],
+                    help="VGG convolutions conv1_2..conv5_3: csrc/conv3x3_tc.cu (default, the product path) or the cuDNN A/B baseline")
     ap.add_argument("--lpips-epilogue", default="cudnn", choices=["kernel", "cudnn"],
-                    help="bias+ReLU after each VGG convolution: own kernel, or cuDNN's fused conv-bias-activation")
+                    help="(--lpips-conv cudnn only) bias+ReLU after each VGG convolution: own kernel, or cuDNN's fused conv-bias-activation")
     ap.add_argument("--no-cuda-graph", dest="cuda_graph", action="store_false",
                     help="default: zero_grad + forward + losses + backward are captured once per input buffer set in a CUDA graph "
                          "and replayed (all-reduce and the Adam launch stay eager): +5 %% at 8 frames/step, +50 %% at 1 (launch-bound)")
@@ -191,7 +193,7 @@ class Trainer:
         self.model.train()
         heads = np.load(os.path.join(ROOT, "tests", "golden", "golden_lpips.npz"))
         self.lpips = LPIPS(seeded_random_trunk(0), [heads[f"lin{k}"] for k in range(5)], conv_precision=args.lpips_precision,
-                           fused=not args.lpips_torch, conv_epilogue=args.lpips_epilogue).to(device)
+                           fused=not args.lpips_torch, conv_epilogue=args.lpips_epilogue, conv_impl=args.lpips_conv).to(device)
         # pool of frames: different poses / cameras / backgrounds per rank
         n_pool = self.B * args.pool_steps
         fr = S.make_frames(scene, n_pool, img_size=(W, H), seed=100 + rank)

@@ -1,18 +1,21 @@
 """LPIPS-VGG v0.1 perceptual loss (reference utils/lpips/lpips.py:81-123, pretrained_networks.py:96-134,
 __init__.py:40-42; used at train.py:113-121 and eval.py:110-116).
 
-The VGG16 3x3 convolutions are dense GEMM-shaped work and stay in cuDNN (library tensor-core kernels, as SURVEY.md
-§8a-12 prescribes).  EVERYTHING ELSE of the loss — input scaling, bias + ReLU, max-pooling, channel normalisation,
-squared difference, the 1x1 heads, the spatial mean, and all of their backward passes — runs in the hand-written
-kernels of csrc/lpips.cu (``fused=True``, the default; one HBM pass per layer each way instead of ~25), driven by
-the hand-rolled backward in ``_FusedLpips``: prediction and target go through the trunk as ONE batch [B pred | B gt],
-only the prediction half is back-propagated, and the gradient arrives at each convolution's dgrad already masked by
-the ReLU and merged with the pooled / tapped contributions.  ``fused=False`` keeps the plain torch formulation (the
-A/B reference for the kernels' tests).  Numerics switch ``conv_precision``:
-  "tf32" (default) — cuDNN may use TF32 tensor-core convolutions.  This IS the reference's stock behaviour: it never
+Every operation of the loss runs in hand-written kernels of libgom_b200.so (``fused=True``, the default):
+  * the VGG16 3x3 convolutions: conv1_1 in csrc/conv_first_tc.cu, conv1_2 ... conv5_3 in csrc/conv3x3_tc.cu (tcgen05
+    implicit GEMMs fed by TMA, bias + ReLU fused into the forward epilogue, the ReLU backward of the layer below fused
+    into the dgrad epilogue through a bit mask the forward wrote);
+  * input scaling, max-pooling, channel normalisation, squared difference, the 1x1 heads, the spatial mean and all of
+    their backward passes in csrc/lpips.cu (one HBM pass per tapped layer each way instead of ~25),
+driven by the hand-rolled backward in ``_FusedLpips``: prediction and target go through the trunk as ONE batch
+[B pred | B gt], only the prediction half is back-propagated.  ``conv_impl="cudnn"`` keeps the library convolutions
+(the A/B baseline of tools/conv_probe.py and of the tests; not the product path); ``fused=False`` keeps the plain
+torch formulation (the A/B reference for the kernels' tests).  Numerics switch ``conv_precision``:
+  "tf32" (default) — TF32 tensor-core products, fp32 accumulation.  This IS the reference's stock behaviour: it never
           touches ``torch.backends.cudnn.allow_tf32``, whose default is True in the torch 1.13 it pins (README.md:19-20);
-  "fp32"  — strict IEEE fp32 convolutions (what the CPU oracle computes; used by the parity tests);
-  "bf16"  — autocast to bfloat16 (fastest, below the 1e-3 gradient tolerance: opt-in only).
+          operands are rounded to TF32 to nearest (weights when packed, activations by the TMA engine), like cuDNN's;
+  "fp32"  — 3xTF32 products (fp32-GEMM accuracy; what the CPU oracle computes; used by the parity tests);
+  "bf16"  — autocast to bfloat16 on the torch path (below the 1e-3 gradient tolerance: opt-in only).
 
 Weights: the trunk is torchvision's VGG16 ``features[:30]`` (same state-dict keys); ImageNet weights are not
 downloadable offline, so ``trunk_state`` must be given (or ``seeded_random_trunk`` used for tests/benchmarks, like the
@@ -26,6 +29,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import _lib
+from . import conv as _conv
 from ._lib import GomBiasReluArgs, GomConvFirstArgs, GomLpipsInputArgs, GomLpipsTapArgs, GomReluBwdArgs, call, ptr
 
 _VGG_CFG = [64, 64, "M", 128, 128, "M", 256, 256, 256, "M", 512, 512, 512, "M", 512, 512, 512]
@@ -99,7 +103,8 @@ def _nhwc(t):
 
 
 class _FusedLpips(torch.autograd.Function):
-    """pred, gt: contiguous [B,H,W,3] fp32 -> per-image LPIPS value [B].  Only ``pred`` receives a gradient."""
+    """pred, gt: contiguous [B,H,W,3] fp32 -> per-image LPIPS value [B].  Only ``pred`` receives a gradient.
+    Activations are contiguous NHWC tensors [2B,h,w,C] throughout."""
 
     @staticmethod
     def forward(ctx, pred, gt, net, from_unit_range):
@@ -112,35 +117,39 @@ class _FusedLpips(torch.autograd.Function):
         call("gom_lpips_input_forward", GomLpipsInputArgs(n_frames=B, height=H, width=W, from_unit_range=int(from_unit_range),
                                                           pred=ptr(pred), gt=ptr(gt), out=ptr(x)))
         vals = torch.zeros(B, dtype=torch.float32, device=dev)
-        acts = [x.permute(0, 3, 1, 2)]                      # NCHW-shaped views of NHWC storage
-        h = acts[0]
+        acts, masks = [x], {}
+        h = x
         prev = torch.backends.cudnn.allow_tf32
         torch.backends.cudnn.allow_tf32 = net.conv_precision != "fp32"
         try:
             ci = 0
             for level, n_conv in enumerate(_LEVELS):
-                for _ in range(n_conv):
-                    h = net._conv_bias_relu(h, ci)
+                for j in range(n_conv):
+                    # the ReLU mask of an activation that feeds another convolution of the same block is what that
+                    # convolution's dgrad needs (the block's last activation is tapped: csrc/lpips.cu masks there)
+                    h, m = net._conv_bias_relu(h, ci, want_mask=j < n_conv - 1)
+                    if m is not None:
+                        masks[len(acts)] = m
                     acts.append(h)
                     ci += 1
-                N2, C, hh, ww = h.shape
+                N2, hh, ww, C = h.shape
                 pool = level < len(_LEVELS) - 1
                 pooled = torch.empty(N2, hh // 2, ww // 2, C, dtype=torch.float32, device=dev) if pool else None
                 call("gom_lpips_tap_forward", GomLpipsTapArgs(
                     n_frames=B, height=hh, width=ww, channels=C, pool=int(pool), feats=ptr(h), lin=ptr(net._lin(level)),
                     layer_sums=ptr(vals), pooled=ptr(pooled)))
                 if pool:
-                    h = pooled.permute(0, 3, 1, 2)
+                    h = pooled
                     acts.append(h)
         finally:
             torch.backends.cudnn.allow_tf32 = prev
-        ctx.net, ctx.acts, ctx.from_unit_range = net, acts, bool(from_unit_range)
+        ctx.net, ctx.acts, ctx.masks, ctx.from_unit_range = net, acts, masks, bool(from_unit_range)
         ctx.dims = (B, H, W)
         return vals
 
     @staticmethod
     def backward(ctx, g_vals):
-        net, acts = ctx.net, ctx.acts
+        net, acts, masks = ctx.net, ctx.acts, ctx.masks
         B, H, W = ctx.dims
         dev = g_vals.device
         dval = g_vals.contiguous().float()
@@ -158,7 +167,7 @@ class _FusedLpips(torch.autograd.Function):
             for level in reversed(range(len(_LEVELS))):
                 ci_last = ci - 1
                 a = acts[conv_out[ci_last]]
-                N2, C, hh, ww = a.shape
+                N2, hh, ww, C = a.shape
                 g_pre = torch.empty(B, hh, ww, C, dtype=torch.float32, device=dev)
                 call("gom_lpips_tap_backward", GomLpipsTapArgs(
                     n_frames=B, height=hh, width=ww, channels=C, pool=int(g_pooled is not None), feats=ptr(a),
@@ -166,16 +175,17 @@ class _FusedLpips(torch.autograd.Function):
                 for j in reversed(range(_LEVELS[level])):
                     ci -= 1
                     inp = acts[conv_in[ci]][:B]
-                    g_in = net._conv_dgrad(g_pre.permute(0, 3, 1, 2), inp, ci, act=fuse_act)
+                    mask = masks.get(conv_in[ci]) if j > 0 else None       # fused ReLU backward of the layer below
+                    g_in = net._conv_dgrad(g_pre, inp, ci, act=fuse_act, mask_in=None if mask is None else mask[:B])
                     fuse_act = None
-                    g_in = _nhwc(g_in.contiguous(memory_format=torch.channels_last))
                     if j > 0:                                # the input was itself a ReLU output of this block
-                        if ci == 1 and net.own_first_conv and net.first_conv_tc:
-                            # conv1_1's output: its ReLU backward is fused into the tcgen05 dgrad that consumes this gradient
-                            # next (one read + one write of the largest gradient tensor and a launch less)
-                            fuse_act = _nhwc(inp) if _nhwc(inp).is_contiguous() else None
-                        if fuse_act is None:
-                            call("gom_relu_backward", GomReluBwdArgs(n=g_in.numel(), act=ptr(inp), grad=ptr(g_in)))
+                        if mask is None:
+                            if ci == 1 and net.own_first_conv and net.first_conv_tc:
+                                # conv1_1's output: its ReLU backward is fused into the tcgen05 dgrad that consumes this
+                                # gradient next (one read + one write of the largest gradient tensor and a launch less)
+                                fuse_act = inp
+                            else:
+                                call("gom_relu_backward", GomReluBwdArgs(n=g_in.numel(), act=ptr(inp), grad=ptr(g_in)))
                         g_pre = g_in
                     else:                                    # the input was the pooled previous block (or the image)
                         g_pooled = g_in
@@ -184,17 +194,20 @@ class _FusedLpips(torch.autograd.Function):
         d_pred = torch.empty(B, H, W, 3, dtype=torch.float32, device=dev)
         call("gom_lpips_input_backward", GomLpipsInputArgs(n_frames=B, height=H, width=W, from_unit_range=int(ctx.from_unit_range),
                                                            dL_dout=ptr(g_pooled), dL_dpred=ptr(d_pred)))
-        ctx.acts = None
+        ctx.acts = ctx.masks = None
         return d_pred, None, None, None
 
 
 class LPIPS(nn.Module):
     def __init__(self, trunk_state, head_weights, conv_precision="tf32", channels_last=True, fused=True,
-                 conv_epilogue="cudnn"):
+                 conv_epilogue="cudnn", conv_impl="tcgen05"):
         super().__init__()
         self.fused = bool(fused) and conv_precision != "bf16"      # the fused kernels are fp32-only
         assert conv_epilogue in ("kernel", "cudnn")
-        self.conv_epilogue = conv_epilogue
+        assert conv_impl in ("tcgen05", "cudnn")
+        self.conv_epilogue = conv_epilogue       # cuDNN baseline only: its fused bias + ReLU epilogue, or csrc/lpips.cu's
+        self.conv_impl = conv_impl
+        self._packs = {}
         self.features = make_vgg16_features()
         self.features.load_state_dict(trunk_state)
         self.register_buffer("shift", torch.tensor([-.030, -.088, -.188])[None, :, None, None])
@@ -221,49 +234,59 @@ class LPIPS(nn.Module):
     def _lin(self, level):
         return getattr(self, f"lin{level}").reshape(-1)
 
-    def _conv_bias_relu(self, h, ci):
-        """3x3 convolution (cuDNN) + bias + ReLU on a channels_last batch."""
+    def _packed(self, ci, transpose):
+        """packed weight image of convolution ``ci`` for csrc/conv3x3_tc.cu (built once per device and precision)"""
+        w = self._convs[ci].weight
+        strict = self.conv_precision == "fp32"
+        key = (ci, transpose, strict, w.device)
+        if key not in self._packs:
+            self._packs[key] = _conv.pack_weights(w, transpose=transpose, split=strict)
+        return self._packs[key]
+
+    def _conv_bias_relu(self, h, ci, want_mask=False):
+        """3x3 convolution + bias + ReLU on a contiguous NHWC batch -> (activation, ReLU bit mask or None)."""
         conv = self._convs[ci]
-        w = conv.weight
+        N, hh, ww, _ = h.shape
         if ci == 0 and self.own_first_conv:
-            N, _, hh, ww = h.shape
-            x = h.permute(0, 2, 3, 1)
-            if not x.is_contiguous():
-                x = x.contiguous()
             y = torch.empty(N, hh, ww, 64, dtype=torch.float32, device=h.device)
             call("gom_conv_first_forward", GomConvFirstArgs(n_images=N, height=hh, width=ww, use_tensor_cores=int(self.first_conv_tc),
-                                                            x=ptr(x), weight=ptr(self.w_first), bias=ptr(conv.bias), out=ptr(y)))
-            return y.permute(0, 3, 1, 2)
+                                                            x=ptr(h), weight=ptr(self.w_first), bias=ptr(conv.bias), out=ptr(y)))
+            return y, None
+        if self.conv_impl == "tcgen05" and ci > 0:
+            mask = _conv.new_mask(N, hh, ww, conv.out_channels, h.device) if want_mask else None
+            y = _conv.conv3x3(h, self._packed(ci, False), bias=conv.bias, relu=True, mask_out=mask, precision=self.conv_precision)
+            return y, mask
+        # cuDNN baseline (channels_last views of the same NHWC storage)
+        w = conv.weight
+        hn = h.permute(0, 3, 1, 2)
         if self.conv_epilogue == "cudnn" and ci not in self._no_cudnn_epilogue:
-            # cuDNN's fused conv + bias + activation: measured on B200 at the same time as the bare convolution
-            # (profiles/r1_conv_probe.md), so the epilogue costs no extra HBM pass.
             try:
-                y = torch.cudnn_convolution_relu(h, w, conv.bias, (1, 1), (1, 1), (1, 1), 1)
-                return y.contiguous(memory_format=torch.channels_last)
+                y = torch.cudnn_convolution_relu(hn, w, conv.bias, (1, 1), (1, 1), (1, 1), 1)
+                return y.contiguous(memory_format=torch.channels_last).permute(0, 2, 3, 1), None
             except RuntimeError:
                 self._no_cudnn_epilogue.add(ci)          # unsupported shape: use the kernel epilogue for this layer
-        y = F.conv2d(h, w, None, padding=1)
-        y = y.contiguous(memory_format=torch.channels_last)
-        N, C, hh, ww = y.shape
-        call("gom_bias_relu", GomBiasReluArgs(n_pixels=N * hh * ww, channels=C, x=ptr(y), bias=ptr(conv.bias)))
-        return y
+        y = F.conv2d(hn, w, None, padding=1)
+        y = y.contiguous(memory_format=torch.channels_last).permute(0, 2, 3, 1)
+        call("gom_bias_relu", GomBiasReluArgs(n_pixels=N * hh * ww, channels=conv.out_channels, x=ptr(y), bias=ptr(conv.bias)))
+        return y, None
 
-    def _conv_dgrad(self, g_out, inp, ci, act=None):
-        """``act``: (first convolution, tensor-core kernel only) its own ReLU output; g_out is then the unmasked gradient."""
+    def _conv_dgrad(self, g_out, inp, ci, act=None, mask_in=None):
+        """Input gradient of convolution ``ci`` (NHWC in, NHWC out).  ``act``: (first convolution, tensor-core kernel only) its
+        own ReLU output; g_out is then the unmasked gradient.  ``mask_in``: ReLU bit mask of ``inp`` (tcgen05 path)."""
+        N, hh, ww, _ = g_out.shape
         if ci == 0 and self.own_first_conv:
-            N, _, hh, ww = g_out.shape
-            g = g_out.permute(0, 2, 3, 1)
-            if not g.is_contiguous():
-                g = g.contiguous()
-            dx = torch.empty(N, hh, ww, 3, dtype=torch.float32, device=g.device)
-            scratch = torch.empty(9, N * hh * ww, 4, dtype=torch.float32, device=g.device) if self.first_conv_tc else None
+            dx = torch.empty(N, hh, ww, 3, dtype=torch.float32, device=g_out.device)
+            scratch = torch.empty(9, N * hh * ww, 4, dtype=torch.float32, device=g_out.device) if self.first_conv_tc else None
             call("gom_conv_first_backward", GomConvFirstArgs(n_images=N, height=hh, width=ww, use_tensor_cores=int(self.first_conv_tc),
-                                                             weight=ptr(self.w_first), dL_dout=ptr(g), dL_dx=ptr(dx), scratch=ptr(scratch),
+                                                             weight=ptr(self.w_first), dL_dout=ptr(g_out), dL_dx=ptr(dx), scratch=ptr(scratch),
                                                              act=ptr(act)))
-            return dx.permute(0, 3, 1, 2)
+            return dx
+        if self.conv_impl == "tcgen05" and ci > 0:
+            return _conv.conv3x3(g_out, self._packed(ci, True), mask_in=mask_in, precision=self.conv_precision)
         w = self._convs[ci].weight
-        return torch.ops.aten.convolution_backward(g_out, inp, w, None, (1, 1), (1, 1), (1, 1), False, (0, 0), 1,
-                                                   (True, False, False))[0]
+        g = torch.ops.aten.convolution_backward(g_out.permute(0, 3, 1, 2), inp.permute(0, 3, 1, 2), w, None, (1, 1), (1, 1), (1, 1),
+                                                False, (0, 0), 1, (True, False, False))[0]
+        return g.contiguous(memory_format=torch.channels_last).permute(0, 2, 3, 1)
 
     def per_image(self, pred_nhwc, gt_nhwc, from_unit_range=True):
         """pred / gt contiguous [B,H,W,3] (in [0,1] when from_unit_range, else already in [-1,1]) -> LPIPS values [B]."""

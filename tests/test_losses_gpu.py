@@ -87,7 +87,8 @@ def test_fused_lpips_gradient_matches_torch_autograd_on_same_activations(golden_
     from gomavatar_b200.lpips import LPIPS, seeded_random_trunk, _TAPS
     g = np.load(os.path.join(golden_dir, "golden_lpips.npz"))
     trunk = seeded_random_trunk(0)
-    net = LPIPS(trunk, [g[f"lin{k}"] for k in range(5)], conv_precision="fp32", fused=True, conv_epilogue="kernel").to(DEV)
+    net = LPIPS(trunk, [g[f"lin{k}"] for k in range(5)], conv_precision="fp32", fused=True, conv_epilogue="kernel",
+                conv_impl="cudnn").to(DEV)
     net.own_first_conv = False          # same cuDNN convolution as the torch side, so activations are bit-identical
     B = 2
     x1 = t(g["x1"]).to(DEV).permute(0, 2, 3, 1).contiguous()
@@ -194,10 +195,11 @@ def test_bias_relu_and_relu_backward_kernels():
 
 
 @pytest.mark.parametrize("hw", [(64, 48), (70, 54)])
-@pytest.mark.parametrize("epilogue", ["kernel", "cudnn"])
-def test_fused_lpips_matches_oracle(hw, epilogue, golden_dir):
-    """Whole loss through the fused path (cuDNN convolutions + csrc/lpips.cu) against the CPU oracle, which is itself
-    pinned to the reference's LPIPS by tests/test_oracle_golden.py.  Odd sizes exercise the ragged pooling edge."""
+@pytest.mark.parametrize("impl", ["tcgen05", "cudnn-kernel", "cudnn-cudnn"])
+def test_fused_lpips_matches_oracle(hw, impl, golden_dir):
+    """Whole loss through the fused path (csrc/conv_first_tc.cu + csrc/conv3x3_tc.cu with 3xTF32 products + csrc/lpips.cu; and,
+    as the A/B baseline, cuDNN convolutions with either epilogue) against the CPU oracle, which is itself pinned to the
+    reference's LPIPS by tests/test_oracle_golden.py.  Odd sizes exercise ragged convolution tiles and the ragged pooling edge."""
     from gomavatar_b200.lpips import LPIPS, seeded_random_trunk
     H, W = hw
     B = 2
@@ -211,7 +213,8 @@ def test_fused_lpips_matches_oracle(hw, epilogue, golden_dir):
     ov = oracle(2 * o0.permute(0, 3, 1, 2) - 1, 2 * t(x1).permute(0, 3, 1, 2) - 1).reshape(B)
     wts = t(np.array([1.0, -0.5], np.float32))
     (ov * wts).sum().backward()
-    net = LPIPS(trunk, _heads(golden_dir), conv_precision="fp32", fused=True, conv_epilogue=epilogue).to(DEV)
+    conv_impl, _, epilogue = impl.partition("-")
+    net = LPIPS(trunk, _heads(golden_dir), conv_precision="fp32", fused=True, conv_epilogue=epilogue or "cudnn", conv_impl=conv_impl).to(DEV)
     k0 = t(x0).to(DEV).requires_grad_(True)
     kv = net.per_image(k0, t(x1).to(DEV), from_unit_range=True)
     np.testing.assert_allclose(kv.detach().cpu().numpy(), ov.detach().numpy(), rtol=1e-4)
