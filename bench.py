@@ -14,6 +14,7 @@ from __future__ import annotations
 import argparse
 import json
 import os
+import re
 import subprocess
 import sys
 import threading
@@ -63,6 +64,7 @@ def parse():
                          "non-rigid MLPs, mesh normal map + soft silhouette (csrc/mesh_raster.cu), tcgen05 shadow MLP "
                          "(csrc/shadow_mlp.cu), rgb = albedo * shading, and the Laplacian / normal / colour regularisers")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the extra keys b1 / full_model / strong_scaling")
     ap.add_argument("--cpu-frames", type=int, default=2, help="frames in the bounded CPU-baseline sample")
     return ap.parse_args()
 
@@ -115,10 +117,13 @@ class ClockSampler:
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed `ncu --set full`
 # capture of this same command (profiles/); filled in by hand after each capture, None = not captured yet.
 NCU_TRAFFIC_BYTES = {      # profiles/r2_ncu_full_summary.md (8 frames, 512x512): mean over the kernel's launches in one step,
-    # like `achieved` (tap_bwd 5 launches 3199.5 MB, tap_fwd 5 launches 2494.3 MB, relu_bwd 7 launches 1854.0 MB,
+    # like `achieved` (tap_bwd 5 launches 3199.5 MB, tap_fwd 5 launches 2494.3 MB,
     # conv_first_bwd = k_conv1_gemm<1> 1357.2 MB + k_conv1_stencil 323.4 MB)
-    "lpips_tap_bwd": 639.9e6, "lpips_tap_fwd": 498.9e6, "relu_bwd": 264.9e6, "conv_first_fwd": 1064.6e6,
-    "conv_first_bwd": 1680.6e6, "blend_bwd": 16.4e6, "sort_blend_fwd": 17.0e6}
+    "lpips_tap_bwd": 639.9e6, "lpips_tap_fwd": 498.9e6, "conv_first_fwd": 1064.6e6, "conv_first_bwd": 1680.6e6}
+# smsp__inst_executed.sum per launch (warp instructions) of the rasterizer's list kernels at the DEFAULT workload (8 frames,
+# 30 000 Gaussians, 512x512, seeds of this file), from the committed ncu capture; None = not captured for this build.
+NCU_WARP_INSTS = {}
+NCU_WARP_INSTS_SOURCE = None
 
 _VGG_LEVELS = ((64, 2), (128, 2), (256, 3), (512, 3), (512, 3))      # (channels, convolutions) per VGG16 block
 
@@ -153,7 +158,7 @@ class Trainer:
         from gomavatar_b200.lpips import LPIPS, seeded_random_trunk
         from gomavatar_b200.model import Model, default_model_cfg
         self.args, self.rank, self.world, self.dev = args, rank, world, device
-        self.graphs, self.replays, self.graph_launches = {}, 0, 0
+        self.graphs, self.replays, self.graph_launches, self.graph_scope = {}, 0, 0, None
         if args.cuda_graph:          # everything off the legacy default stream: autograd's AccumulateGrad nodes keep the
             torch.cuda.set_stream(torch.cuda.Stream(device=device))     # stream they were created on, and capture needs one
         self.B = args.frames_per_step
@@ -208,7 +213,10 @@ class Trainer:
                                                                 "canonical_geometry_xyz": 5e-4, "non_rigid": 5e-4,
                                                                 "pose_refinement": 5e-5, "shadow": 5e-4}})())
         from gomavatar_b200.dist import ArenaAdam
-        self.opt = ArenaAdam(self.arena, groups)            # one launch over the flat arena (csrc/adam.cu)
+        # one launch over the flat arena (csrc/adam.cu); step counters on the device and the reference's exponential
+        # learning-rate decay (train.py:166-175: lr * 0.1^(iter / 100 000)) evaluated there: nothing step-dependent is a
+        # kernel argument, so the optimizer step is part of the captured graph
+        self.opt = ArenaAdam(self.arena, groups, device_state=True, lr_decay=(0.1, 100000.0))
         self.h2d_bytes = sum(v[: self.B].numel() * v.element_size() for v in self.host.values()) + \
             self.host_tgt_rgb[: self.B].numel() * 4 + self.host_tgt_mask[: self.B].numel() * 4
 
@@ -230,7 +238,7 @@ class Trainer:
         self.tgt_rgb, self.tgt_mask = torch.cat(rgbs).contiguous(), torch.cat(masks).contiguous()
         self.host_tgt_rgb, self.host_tgt_mask = self.tgt_rgb.cpu().pin_memory(), self.tgt_mask.cpu().pin_memory()
 
-    def _fwd_bwd(self, d, tgt_rgb, tgt_mask):
+    def _fwd_bwd(self, d, tgt_rgb, tgt_mask, with_optimizer=False):
         from gomavatar_b200.losses import compute_loss
         self.arena.zero_grad()
         rgb, mask, outputs = self.model(d["K"], d["E"], d["cnl_gtfms"], d["dst_Rs"], d["dst_Ts"], dst_posevec=d["dst_posevec"],
@@ -241,37 +249,45 @@ class Trainer:
         else:
             loss, terms, _ = compute_loss(rgb, mask, d["bgcolor"], tgt_rgb, tgt_mask, lpips_func=self.lpips)
         loss.backward()
+        if with_optimizer:
+            self.opt.step(grad_scale=self.arena.all_reduce_sum())  # 1/world folded into the Adam launch
         return loss.detach()
 
     def _train(self, d, tgt_rgb, tgt_mask, graph_key=None):
-        """graph_key: identity of a STATIC (d, tgt_rgb, tgt_mask) buffer set; with --cuda-graph its forward/backward is
-        captured on first use and replayed afterwards."""
-        if self.args.cuda_graph and graph_key is not None:
-            if graph_key not in self.graphs:
-                from gomavatar_b200 import _lib
-                was_on = _lib.profile_enable  # noqa: F841  (profiling events cannot be recorded inside a capture)
-                _lib.profile_enable(False)
-                for _ in range(2):                                   # warm-up on the capture stream (allocator, cuDNN plans)
-                    self._fwd_bwd(d, tgt_rgb, tgt_mask)
-                torch.cuda.synchronize(self.dev)
-                n0 = _lib.launch_count()
+        """graph_key: identity of a STATIC (d, tgt_rgb, tgt_mask) buffer set; with --cuda-graph the step is captured on first
+        use and replayed afterwards.  Scope of the graph: "step" = zero_grad + forward + losses + backward + NCCL all-reduce +
+        Adam (first choice); "fwd_bwd" = without the last two, which then stay eager (fallback if the collective cannot be
+        captured); eager if that fails too."""
+        if self.args.cuda_graph and graph_key is not None and graph_key not in self.graphs:
+            from gomavatar_b200 import _lib
+            _lib.profile_enable(False)                           # profiling events cannot be recorded inside a capture
+            for scope in (("step", "fwd_bwd") if self.graph_scope is None else (self.graph_scope,)):
                 try:
+                    for _ in range(2):                           # warm-up on the capture stream (allocator, NCCL channels)
+                        self._fwd_bwd(d, tgt_rgb, tgt_mask, with_optimizer=True)
+                    torch.cuda.synchronize(self.dev)
+                    n0 = _lib.launch_count()
                     g = torch.cuda.CUDAGraph()
                     with torch.cuda.graph(g, stream=torch.cuda.current_stream(self.dev)):
-                        loss = self._fwd_bwd(d, tgt_rgb, tgt_mask)
+                        loss = self._fwd_bwd(d, tgt_rgb, tgt_mask, with_optimizer=scope == "step")
                     self.graphs[graph_key] = (g, loss)
                     self.graph_launches = _lib.launch_count() - n0
-                except Exception as e:                               # never lose the run to a capture problem: go eager
-                    print(f"# CUDA-graph capture failed ({type(e).__name__}: {e}); continuing eagerly", file=sys.stderr)
-                    self.args.cuda_graph, self.graph_error = False, f"{type(e).__name__}: {e}"[:200]
+                    self.graph_scope = scope
+                    break
+                except Exception as e:
+                    print(f"# CUDA-graph capture of scope '{scope}' failed ({type(e).__name__}: {e})", file=sys.stderr)
+                    self.graph_error = f"{scope}: {type(e).__name__}: {e}"[:200]
                     torch.cuda.synchronize(self.dev)
+            else:                                                # never lose the run to a capture problem: go eager
+                self.args.cuda_graph = False
         if self.args.cuda_graph and graph_key is not None:
             g, loss = self.graphs[graph_key]
             g.replay()
             self.replays += 1
+            if self.graph_scope != "step":
+                self.opt.step(grad_scale=self.arena.all_reduce_sum())
         else:
-            loss = self._fwd_bwd(d, tgt_rgb, tgt_mask)
-        self.opt.step(grad_scale=self.arena.all_reduce_sum())      # 1/world folded into the Adam launch
+            loss = self._fwd_bwd(d, tgt_rgb, tgt_mask, with_optimizer=True)
         return loss
 
     def step_device(self, i):
@@ -374,8 +390,98 @@ def timed_region(fn, steps, warmup, world, device, flush=None):
     return float(ms.item())
 
 
-def run_b200(args):
+def vgg_conv_flops(H, W, n_images, skip_first=True):
+    """2 * MACs of the VGG16 convolutions conv1_2 ... conv5_3 (conv1_1 too unless skip_first) over n_images H x W images"""
+    total, h, w, cin, first = 0.0, H, W, 3, True
+    for C, n_conv in _VGG_LEVELS:
+        for _ in range(n_conv):
+            if not (first and skip_first):
+                total += 2.0 * 9 * cin * C * h * w * n_images
+            first, cin = False, C
+        h, w = h // 2, w // 2
+    return total
+
+
+def library_share(tr, steps=2):
+    """Which kernels the step runs, by owner, from a short torch.profiler (CUPTI) trace of EAGER steps on rank 0: this repo's
+    kernels (names from libgom_b200.so) / NCCL / memcpy+memset / anything else (torch ATen, cuDNN, cuBLAS, CUTLASS =
+    "library").  Shares of the summed kernel time; the trace itself is not part of any timed region."""
+    try:
+        from torch.profiler import ProfilerActivity, profile
+        was = tr.args.cuda_graph
+        tr.args.cuda_graph = False
+        tr.step_device(0)
+        torch.cuda.synchronize(tr.dev)
+        with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+            for i in range(steps):
+                tr.step_device(i)
+            torch.cuda.synchronize(tr.dev)
+        tr.args.cuda_graph = was
+        own = lib = nccl = mem = 0.0
+        lib_names = {}
+        for e in prof.events():
+            if "cuda" not in str(getattr(e, "device_type", "")).lower():
+                continue
+            t = float(getattr(e, "device_time_total", 0.0) or getattr(e, "cuda_time_total", 0.0) or 0.0)
+            n = e.name
+            if re.search(r"(^|[\s:])k_[a-z0-9_]+", n):           # every kernel of libgom_b200.so is named k_*
+                own += t
+            elif "nccl" in n.lower():
+                nccl += t
+            elif n.lower().startswith("memcpy") or n.lower().startswith("memset"):
+                mem += t
+            else:
+                lib += t
+                lib_names[n[:60]] = lib_names.get(n[:60], 0.0) + t
+        tot = own + lib + nccl + mem
+        if tot <= 0:
+            return {"unavailable": "the profiler returned no device events"}
+        top = sorted(lib_names.items(), key=lambda kv: -kv[1])[:5]
+        return {"own_kernels": own / tot, "library_kernels": lib / tot, "nccl": nccl / tot, "memcpy_memset": mem / tot,
+                "device_us_per_step": tot / steps, "top_library_kernels": [[k, v / steps] for k, v in top],
+                "how": "torch.profiler CUDA activity over %d eager steps, shares of summed device time" % steps}
+    except Exception as e:                                    # CUPTI may be unavailable: report, never fail the bench
+        return {"unavailable": f"{type(e).__name__}: {e}"[:160]}
+
+
+def measure(args, rank, local, world, device, detailed):
+    """Build the trainer for `args`, time the e2e and the device-resident step; with `detailed` also the per-kernel eager
+    region, the rooflines and the clock samples."""
     from gomavatar_b200 import _lib
+    tr = Trainer(args, rank, world, device)
+    B, K, W_ = args.frames_per_step, args.steps, max(args.warmup, 3)
+    frames_total = K * B * world
+    ms_e2e = timed_region(tr.step_e2e, K, W_, world, device, flush=tr.flush_e2e)
+    assert tr.losses_read == K + W_, "every e2e step must deliver its loss to the host"
+    sampler = ClockSampler(local)
+    if rank == 0 and detailed:
+        sampler.start()
+    r0, n0 = tr.replays, _lib.launch_count()
+    ms = timed_region(tr.step_device, K, W_, world, device)
+    used_graph = bool(args.cuda_graph)                           # False if the capture fell back to eager
+    if used_graph:
+        per_replay = tr.graph_launches + (0 if tr.graph_scope == "step" else 1)
+        launches_timed = int(round((tr.replays - r0) * K / (K + W_))) * per_replay
+    else:
+        launches_timed = int(round((_lib.launch_count() - n0) * K / (K + W_)))
+    clocks = sampler.stop() if (rank == 0 and detailed) else None
+    out = {"value": frames_total / (ms * 1e-3), "ms_per_step": ms / K, "e2e_value": frames_total / (ms_e2e * 1e-3),
+           "e2e_ms_per_step": ms_e2e / K, "gpu_launches": launches_timed, "clocks": clocks, "h2d": int(tr.h2d_bytes),
+           "cuda_graph": (tr.graph_scope if used_graph else (getattr(tr, "graph_error", None) or False)), "trainer": tr}
+    if not detailed:
+        return out
+    args.cuda_graph = False                                      # per-kernel CUDA-event timers need eager launches:
+    _lib.profile_enable(True)                                    # a second, eager region feeds `kernels` / the rooflines
+    ms_prof = timed_region(tr.step_device, K, W_, world, device)
+    prof = _lib.profile_read()
+    _lib.profile_enable(False)
+    args.cuda_graph = used_graph
+    out.update({"prof": prof, "ms_prof": ms_prof})
+    return out
+
+
+def run_b200(args):
+    import copy
     from gomavatar_b200.dist import init_from_env
     rank, local, world = init_from_env("nccl")
     if world != args.gpus and rank == 0:
@@ -384,56 +490,26 @@ def run_b200(args):
         raise SystemExit("bench.py: no CUDA device — the hot path has no CPU fallback (use --impl reference for the CPU arm)")
     device = torch.device("cuda", local)
     torch.cuda.set_device(device)
-    tr = Trainer(args, rank, world, device)
-    B, K, W_ = args.frames_per_step, args.steps, args.warmup
-    frames_total = K * B * world
+    B, K, W_ = args.frames_per_step, args.steps, max(args.warmup, 3)
+    m = measure(args, rank, local, world, device, detailed=True)
+    tr, prof, ms_prof, ms = m["trainer"], m["prof"], m["ms_prof"], m["ms_per_step"] * K
 
-    # ---- e2e first (host buffers in, loss out every step), then the device-resident number with per-kernel timers
-    ms_e2e = timed_region(tr.step_e2e, K, max(W_, 3), world, device, flush=tr.flush_e2e)
-    assert tr.losses_read == K + max(W_, 3), "every e2e step must deliver its loss to the host"
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    used_graph = bool(args.cuda_graph)
-    if args.cuda_graph:
-        r0, n0 = tr.replays, _lib.launch_count()
-        ms = timed_region(tr.step_device, K, max(W_, 3), world, device)          # graph replays (kernels are not re-issued by the host)
-        used_graph = bool(args.cuda_graph)                                       # False if the capture fell back to eager
-        if used_graph:
-            launches_timed = int(round((tr.replays - r0) * K / (K + max(W_, 3)))) * (tr.graph_launches + 1)
-        else:
-            launches_timed = int(round((_lib.launch_count() - n0) * K / (K + max(W_, 3))))
-        clocks = sampler.stop() if rank == 0 else None
-        args.cuda_graph = False                                                  # per-kernel CUDA-event timers need eager launches:
-        _lib.profile_enable(True)                                                # a second, eager region feeds `kernels` / `roofline`
-        ms_prof = timed_region(tr.step_device, K, max(W_, 3), world, device)
-        prof = _lib.profile_read()
-        _lib.profile_enable(False)
-        args.cuda_graph = used_graph
-    else:
-        _lib.profile_enable(True)
-        n0 = _lib.launch_count()
-        ms = timed_region(tr.step_device, K, max(W_, 3), world, device)
-        launches = _lib.launch_count() - n0
-        prof = _lib.profile_read()
-        _lib.profile_enable(False)
-        clocks = sampler.stop() if rank == 0 else None
-        launches_timed = int(round(launches * K / (K + max(W_, 3))))
-        ms_prof = ms
-
-    # ---- roofline of the dominant hand-written kernel (by measured time inside the timed region)
+    # ---- per-kernel table (eager region, CUDA events on the launching stream) and the rooflines
     aux = tr.model.last_raster_aux
     T = ((args.img + 15) // 16) ** 2
     n_dup = float(aux["tile_offset"][:, T].to(torch.int64).bitwise_and(0xFFFFFFFF).float().mean().item())
     overflow = int(aux["status"].max().item())
     HW, F, V = args.img * args.img, tr.scene.n_faces, tr.scene.n_vertices
     alg_bytes_per_frame = {      # SURVEY.md §8d algorithmic bytes per frame (DESIGN.md §4 lists every formula)
-        "sort_blend_fwd": 40 * n_dup + 24 * HW, "blend_bwd": 80 * n_dup + 44 * HW, "preprocess": 76 * F,
-        "preprocess_bwd": 76 * F + 36 * F, "emit": 12 * n_dup + 20 * F, "scan_tiles": 12 * T,
+        "blend_fwd": 40 * n_dup + 24 * HW, "blend_bwd": 80 * n_dup + 44 * HW, "tile_sort": 12 * n_dup, "preprocess": 76 * F,
+        "preprocess_bwd": 76 * F + 36 * F, "emit": 12 * n_dup + 20 * F, "scan_tiles": 12 * T, "worklist": 12 * T,
         "lbs_fwd": 120 * V, "lbs_bwd": 120 * V, "face_fwd": 72 * F, "face_bwd": 72 * F + 36 * F,
         "photo_fwd": 44 * HW, "photo_bwd": 60 * HW}
-    alg_bytes_per_frame.update(lpips_alg_bytes_per_frame(args.img, args.img, args.lpips_epilogue == "kernel"))
+    alg_bytes_per_frame.update(lpips_alg_bytes_per_frame(args.img, args.img, args.lpips_conv == "cudnn" and args.lpips_epilogue == "kernel"))
+    if args.lpips_conv == "tcgen05":
+        alg_bytes_per_frame["relu_bwd"] = 0.0                            # fused into the dgrad epilogues (bit masks)
     alg_bytes_per_frame["adam"] = 28.0 * tr.arena.numel / B          # param r/w, grad r, two moments r/w: per STEP
+    alg_flops_per_frame = {"conv3x3_fwd": vgg_conv_flops(args.img, args.img, 2), "conv3x3_dgrad": vgg_conv_flops(args.img, args.img, 1)}
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -441,47 +517,107 @@ def run_b200(args):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "6650 GB/s (of fallback)"
+    tpeak = float(peaks.get("bf16_tflops_sustained", 1400.0)) / 2.0      # TF32 runs at half the bf16 tensor rate
+    tpeak_src = ("MEASURED_PEAKS.json bf16_tflops_sustained / 2 = dense TF32 (of measured)" if "bf16_tflops_sustained" in peaks
+                 else "1400 / 2 TFLOP/s (of fallback)")
     kernels = {}
-    n_timed_steps = K + max(W_, 3)
+    n_timed_steps = K + W_
     for name, (tot_ms, n) in prof.items():
         ms_step = tot_ms / n_timed_steps                     # all launches of this kernel in one step
-        byt_step = alg_bytes_per_frame.get(name, 0.0) * B    # algorithmic bytes of all those launches
         per_step = n / n_timed_steps
-        kernels[name] = {"ms_per_step": ms_step, "launches_per_step": per_step, "ms_per_launch": tot_ms / max(n, 1),
-                         "share_of_step": ms_step / (ms_prof / K), "alg_bytes_per_launch": byt_step / max(per_step, 1e-9),
-                         "gbs": byt_step / (ms_step * 1e-3) / 1e9 if ms_step > 0 else None}
-    hbm_kernels = [k for k in kernels if alg_bytes_per_frame.get(k, 0.0) > 0]
-    dom = max(hbm_kernels, key=lambda k: kernels[k]["ms_per_step"]) if hbm_kernels else None
+        k = {"ms_per_step": ms_step, "launches_per_step": per_step, "ms_per_launch": tot_ms / max(n, 1),
+             "share_of_step": ms_step / (ms_prof / K)}
+        if name in alg_flops_per_frame:
+            fl = alg_flops_per_frame[name] * B
+            k.update({"alg_flops_per_launch": fl / max(per_step, 1e-9), "tflops": fl / (ms_step * 1e-3) / 1e12 if ms_step > 0 else None})
+        else:
+            byt_step = alg_bytes_per_frame.get(name, 0.0) * B    # algorithmic bytes of all those launches
+            k.update({"alg_bytes_per_launch": byt_step / max(per_step, 1e-9), "gbs": byt_step / (ms_step * 1e-3) / 1e9 if ms_step > 0 else None})
+        kernels[name] = k
+    bounded = [k for k in kernels if alg_bytes_per_frame.get(k, 0.0) > 0 or k in alg_flops_per_frame]
+    dom = max(bounded, key=lambda k: kernels[k]["ms_per_step"]) if bounded else None
     roofline = None
     if dom:
         k = kernels[dom]
-        roofline = {"kernel": dom, "bound": "hbm", "achieved": k["gbs"], "peak": peak, "unit": "GB/s", "frac": k["gbs"] / peak,
-                    "traffic": NCU_TRAFFIC_BYTES.get(dom), "peak_source": peak_src, "ms_per_launch": k["ms_per_launch"],
-                    "alg_bytes_per_launch": k["alg_bytes_per_launch"], "launches_per_step": k["launches_per_step"],
-                    "n_dup_per_frame": n_dup,
-                    "blend_pass": {kk: {"gbs": kernels[kk]["gbs"], "frac": kernels[kk]["gbs"] / peak, "ms_per_launch": kernels[kk]["ms_per_launch"]}
-                                   for kk in ("sort_blend_fwd", "blend_bwd") if kk in kernels}}
+        if dom in alg_flops_per_frame:
+            roofline = {"kernel": dom, "bound": "tensor", "achieved": k["tflops"], "peak": tpeak, "unit": "TFLOP/s",
+                        "frac": k["tflops"] / tpeak, "traffic": None, "peak_source": tpeak_src, "ms_per_launch": k["ms_per_launch"],
+                        "alg_flops_per_launch": k["alg_flops_per_launch"], "launches_per_step": k["launches_per_step"],
+                        "note": "TF32 tcgen05 implicit-GEMM convolutions (12 VGG layers per step, mean over the launches); "
+                                "achieved = 2 * MACs / CUDA-event time"}
+        else:
+            roofline = {"kernel": dom, "bound": "hbm", "achieved": k["gbs"], "peak": peak, "unit": "GB/s", "frac": k["gbs"] / peak,
+                        "traffic": NCU_TRAFFIC_BYTES.get(dom), "peak_source": peak_src, "ms_per_launch": k["ms_per_launch"],
+                        "alg_bytes_per_launch": k["alg_bytes_per_launch"], "launches_per_step": k["launches_per_step"]}
+    # the rasterizer's list kernels: the north star's ">= 60 % of HBM" target next to the bound that actually binds them
+    sm_mhz = (m["clocks"] or {}).get("sm_mhz") or float(peaks.get("sm_max_mhz", 1965.0))
+    default_workload = (args.faces == 30000 and args.img == 512 and B == 8 and not args.full_model)
+    roofline_blend = {"n_dup_per_frame": n_dup, "peak_hbm_gbs": peak, "peak_source": peak_src,
+                      "issue_peak": "148 SMs x 4 schedulers x SM clock (median under load: %.0f MHz) warp instructions / s" % sm_mhz,
+                      "warp_insts_source": NCU_WARP_INSTS_SOURCE if default_workload else None, "kernels": {}}
+    for kk in ("tile_sort", "blend_fwd", "blend_bwd"):
+        if kk in kernels:
+            e = {"ms_per_launch": kernels[kk]["ms_per_launch"], "alg_bytes_per_launch": kernels[kk]["alg_bytes_per_launch"],
+                 "gbs": kernels[kk]["gbs"], "frac_hbm": kernels[kk]["gbs"] / peak}
+            wi = NCU_WARP_INSTS.get(kk) if default_workload else None
+            if wi:
+                e["warp_insts_per_launch"] = wi
+                e["frac_issue"] = wi / (148 * 4 * sm_mhz * 1e6 * kernels[kk]["ms_per_launch"] * 1e-3)
+            roofline_blend["kernels"][kk] = e
+    roofline_conv = None
+    if "conv3x3_fwd" in kernels:
+        roofline_conv = {"bound": "tensor", "unit": "TFLOP/s", "peak": tpeak, "peak_source": tpeak_src,
+                         "kernels": {kk: {"tflops": kernels[kk]["tflops"], "frac": kernels[kk]["tflops"] / tpeak,
+                                          "ms_per_step": kernels[kk]["ms_per_step"], "launches_per_step": kernels[kk]["launches_per_step"]}
+                                     for kk in ("conv3x3_fwd", "conv3x3_dgrad") if kk in kernels}}
 
     if args.full_model and roofline is not None and "shadow_mlp_fwd" in kernels:
         sm = tr.model.shadow_module
         n_fg = int(sm._ws["n_fg"].item())
         flops = 2.0 * n_fg * (39 * 128 + 2 * 128 * 128 + 128)           # one pass over the MLP (fp32-equivalent FLOPs)
-        tpeak = float(peaks.get("bf16_tflops_sustained", 1400.0)) / 2.0     # TF32 = half the bf16 tensor rate
         roofline["shadow_mlp"] = {"bound": "tensor", "unit": "TFLOP/s", "peak": tpeak, "n_fg_per_step": n_fg,
-                                  "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained / 2 (TF32)",
+                                  "peak_source": tpeak_src,
                                   "note": "achieved = algorithmic fp32-equivalent FLOPs / time; every product is issued as 3 TF32 MMAs"}
         for kk, mult in (("shadow_mlp_fwd", 1.0), ("shadow_mlp_bwd_data", 1.0), ("shadow_mlp_bwd_weights", 1.0)):
             if kk in kernels:
                 ach = flops * mult / (kernels[kk]["ms_per_launch"] * 1e-3) / 1e12
                 roofline["shadow_mlp"][kk] = {"achieved": ach, "frac": ach / tpeak, "frac_issued": 3 * ach / tpeak,
                                               "ms_per_launch": kernels[kk]["ms_per_launch"]}
+    lib = library_share(tr) if (rank == 0 and world == 1) else None
+
+    # ---- extra measurements of the same step (extra keys; the headline above is untouched)
+    extras = {}
+    del m["trainer"], tr
+    torch.cuda.empty_cache()
+
+    def extra(**kw):
+        a2 = copy.copy(args)
+        for k_, v_ in kw.items():
+            setattr(a2, k_, v_)
+        a2.steps, a2.warmup = max(5, K // 2), 3
+        r = measure(a2, rank, local, world, device, detailed=False)
+        del r["trainer"]
+        torch.cuda.empty_cache()
+        return {"value": r["value"], "unit": UNIT, "ms_per_step": r["ms_per_step"], "e2e_value": r["e2e_value"],
+                "frames_per_step_per_gpu": a2.frames_per_step, "global_batch": a2.frames_per_step * world, "steps": a2.steps,
+                "cuda_graph": r["cuda_graph"], "gpu_launches": r["gpu_launches"]}
+    if not args.no_extras and not args.full_model:
+        if world == 1:
+            if B != 1:        # the reference's own batch size (configs/default.yaml:10, gaussian.py:24): one Adam step per frame
+                extras["b1"] = extra(frames_per_step=1)
+            extras["full_model"] = extra(full_model=True)
+            extras["full_model"]["note"] = "whole reference-shaped step of exps/zju-mocap_377.yaml (bench.py --full-model)"
+        elif B % world == 0:  # fixed global batch of B frames split over the ranks (the headline keeps B frames per GPU)
+            extras["strong_scaling"] = extra(frames_per_step=B // world)
+
     line = None
     if rank == 0:
-        value = frames_total / (ms * 1e-3)
-        e2e_value = frames_total / (ms_e2e * 1e-3)
         line = {
-            "metric": ("full_model_" + METRIC) if args.full_model else METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": max(W_, 3),
-            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (all hand-written kernels fp32; LPIPS VGG convs in cuDNN at %s)" % args.lpips_precision,
+            "metric": ("full_model_" + METRIC) if args.full_model else METRIC, "value": m["value"], "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W_,
+            "ms_per_step": m["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32 (every kernel hand-written; VGG convolutions of LPIPS: %s products on tcgen05, fp32 accumulation)"
+                     % ("TF32" if args.lpips_precision == "tf32" else args.lpips_precision) if args.lpips_conv == "tcgen05" else
+                     "f32 (LPIPS VGG convs in cuDNN at %s: A/B baseline, not the product path)" % args.lpips_precision,
             "data": "synthetic (seeded SMPL-topology humanoid, poses, ZJU-like cameras; LPIPS trunk = seeded random VGG16, "
                     "no ImageNet weights offline)",
             "config": {"workload": ("FULL reference-shaped train step of exps/zju-mocap_377.yaml (hot path + pose-refinement / non-rigid "
@@ -491,16 +627,18 @@ def run_b200(args):
                                     "512x512, 30k Gaussians (BASELINE configs[2])"),
                        "img": args.img, "n_gaussians": F, "n_vertices": V, "frames_per_step_per_gpu": B,
                        "global_batch": B * world, "parallelism": f"frame-sharded dp{world}, 1 NCCL all-reduce of the flat grad arena/step",
-                       "lpips_conv_precision": args.lpips_precision + (" (cuDNN default; the reference never disables TF32)" if args.lpips_precision == "tf32" else ""), "raster_overflow": overflow,
-                       "cuda_graph": used_graph if used_graph else (getattr(tr, "graph_error", None) or False),
+                       "lpips_conv": args.lpips_conv, "lpips_conv_precision": args.lpips_precision + (" (the reference's stock cuDNN setting: it never disables TF32)" if args.lpips_precision == "tf32" else ""),
+                       "raster_overflow": overflow, "cuda_graph": m["cuda_graph"],
                        "l2": "per-step working set (LPIPS activations, ~%d MB) exceeds the 126 MB L2; batches cycle through a pool"
                              % int(B * 2 * 32e6 * 4 / 1e6)},
-            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / K, "h2d_bytes_per_step": int(tr.h2d_bytes),
+            "e2e": {"value": m["e2e_value"], "unit": UNIT, "ms_per_step": m["e2e_ms_per_step"], "h2d_bytes_per_step": m["h2d"],
                     "d2h_bytes_per_step": 4},
-            "gpu_launches": launches_timed, "clocks": clocks, "roofline": roofline, "kernels": kernels,
+            "gpu_launches": m["gpu_launches"], "clocks": m["clocks"], "roofline": roofline, "roofline_blend": roofline_blend,
+            "roofline_conv": roofline_conv, "library_share_of_step": lib, "kernels": kernels,
         }
+        line.update(extras)
         if not args.no_cpu_baseline and world == 1 and not args.full_model:
-            line["cpu_baseline"] = cpu_path(args, n_frames=args.cpu_frames, gpu_trainer=tr)
+            line["cpu_baseline"] = cpu_path(args, n_frames=args.cpu_frames, gpu_device=device)
         emit(line)
     if world > 1:
         import torch.distributed as dist
@@ -510,7 +648,7 @@ def run_b200(args):
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm (oracle)
-def cpu_path(args, n_frames, gpu_trainer=None, steps=1, warmup=0):
+def cpu_path(args, n_frames, gpu_device=None, steps=1, warmup=0):
     """The reference's path on the host cores: its PyTorch ops restated (oracle/geometry.py, losses.py) + the C
     restatement of the un-vendored CUDA rasterizer (oracle/raster_oracle.c, OpenMP), forward + backward, n_frames frames
     per step, batch 1 per frame like the reference.  The ONLY place bench.py touches oracle/."""
@@ -549,12 +687,12 @@ def cpu_path(args, n_frames, gpu_trainer=None, steps=1, warmup=0):
         loss.backward()
         g = R.backward(f, img.grad[0].permute(2, 0, 1).contiguous().numpy())
         ((xyz * t(g["means3D"])).sum() + (cov6 * t(g["cov6"])).sum()).backward()
-        if gpu_trainer is not None and psnr is None:      # PSNR of the B200 render against the oracle render, same frame
+        if gpu_device is not None and psnr is None:      # PSNR of the B200 render against the oracle render, same frame
             from gomavatar_b200.model import Model, default_model_cfg
-            m = Model(default_model_cfg(img_size=(W, H)), scene.canonical_info()).to(gpu_trainer.dev)   # same initial params
+            m = Model(default_model_cfg(img_size=(W, H)), scene.canonical_info()).to(gpu_device)   # same initial params
             with torch.no_grad():
                 m.so3.copy_(t(pr["so3"])); m.scale.copy_(t(pr["scale"])); m.appearance_module.appearance.copy_(t(pr["appearance"]))
-                d = {k: t(fr[k][b:b + 1]).to(gpu_trainer.dev) for k in ("K", "E", "cnl_gtfms", "dst_Rs", "dst_Ts")}
+                d = {k: t(fr[k][b:b + 1]).to(gpu_device) for k in ("K", "E", "cnl_gtfms", "dst_Rs", "dst_Ts")}
                 rgb, mask, _ = m(d["K"], d["E"], d["cnl_gtfms"], d["dst_Rs"], d["dst_Ts"])
             mse = float(((rgb[0].cpu().double() - img.detach()[0, ..., :3].double()) ** 2).mean())
             psnr = float("inf") if mse == 0 else -10.0 * np.log10(mse)

@@ -68,10 +68,12 @@ def train(data, iters, img, device, batch=2, lr=5e-4, ckpt_dir=None, save_freq=0
     ds = IO.Dataset(data, target_size=[img, img])
     loader = torch.utils.data.DataLoader(ds, batch_size=batch, shuffle=True, drop_last=True, collate_fn=collate,
                                          generator=torch.Generator().manual_seed(0))
-    n_iter, model = 0, None
+    n_iter, model, opt_state = 0, None, None
     if ckpt_dir and os.path.isdir(ckpt_dir) and os.listdir(ckpt_dir):                     # train.py:269-286 (--resume)
         last = max(int(f.split("_")[-1][:-3]) for f in os.listdir(ckpt_dir))
-        model, n_iter = IO.model_from_checkpoint(model_cfg(img), os.path.join(ckpt_dir, f"iter_{last}.pt"), strict_raster=False)
+        ckpt = torch.load(os.path.join(ckpt_dir, f"iter_{last}.pt"), map_location="cpu", weights_only=False)
+        model, n_iter = IO.model_from_checkpoint(model_cfg(img), ckpt, strict_raster=False)
+        opt_state = ckpt.get("optimizer") or None                                          # train.py:281
     if model is None:
         model = Model(model_cfg(img), ds.get_canonical_info(), strict_raster=False)
     model = model.to(device).train()
@@ -81,6 +83,9 @@ def train(data, iters, img, device, batch=2, lr=5e-4, ckpt_dir=None, save_freq=0
         opt = ArenaAdam(arena, groups)
         return arena, opt, [g["lr"] for g in opt.param_groups]
     arena, opt, base = make_optimizer()
+    if opt_state is not None:                  # Adam moments and per-parameter step counts continue where they stopped
+        opt.load_state_dict(opt_state)
+        base = [g["lr"] / 0.1 ** (n_iter / 100000) for g in opt.param_groups]
     history = []
     while n_iter < iters:
         for b in loader:
@@ -92,7 +97,7 @@ def train(data, iters, img, device, batch=2, lr=5e-4, ckpt_dir=None, save_freq=0
                                          i_iter=n_iter, bgcolor=b["bgcolor"])
             loss, terms = compute_loss(rgbs, masks, b["bgcolor"], b["target_rgbs"], b["target_masks"], outputs, model, LOSSES, lpips_func=lpips)
             loss.backward()
-            opt.step(grad_scale=arena.all_reduce_sum())
+            opt.step(grad_scale=arena.all_reduce_sum(), active=model.active_param_groups(n_iter))
             n_iter += 1
             if n_iter in subdivide_iters:                                                  # train.py:341-346: every face -> 4,
                 model.subdivide()                                                          # new Parameters -> new optimizer
@@ -102,11 +107,16 @@ def train(data, iters, img, device, batch=2, lr=5e-4, ckpt_dir=None, save_freq=0
             for g, b0 in zip(opt.param_groups, base):                                      # train.py:166-175
                 g["lr"] = b0 * 0.1 ** (n_iter / 100000)
             history.append(float(loss.detach()))
+            if n_iter % max(1, iters // 10) == 0:                                          # one sync per log interval
+                st = int(model.last_raster_aux["status"].max().item())
+                if st:     # k_emit dropped (Gaussian, tile) instances: the tile lists of those frames were truncated
+                    raise RuntimeError(f"rasterizer status {st} at iteration {n_iter}: instance capacity "
+                                       f"{model.last_raster_aux['inst_capacity']} exceeded; rebuild the Model with a larger raster_capacity")
             if log and (n_iter % max(1, iters // 10) == 0):
                 log(f"iter {n_iter:6d}  loss {history[-1]:.5f}  " + "  ".join(f"{k} {float(v['scaled']):.5f}" for k, v in terms.items()))
             if ckpt_dir and save_freq and n_iter % save_freq == 0:
                 os.makedirs(ckpt_dir, exist_ok=True)
-                IO.save_checkpoint(os.path.join(ckpt_dir, f"iter_{n_iter}.pt"), model, n_iter=n_iter)
+                IO.save_checkpoint(os.path.join(ckpt_dir, f"iter_{n_iter}.pt"), model, optimizer_state=opt.state_dict(), n_iter=n_iter)
     return model, history
 
 

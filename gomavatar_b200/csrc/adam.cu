@@ -11,18 +11,36 @@
 
 namespace {
 __global__ void __launch_bounds__(256) k_adam(GomAdamArgs a) {
-    const float bc2_sqrt = sqrtf(a.bias_correction2);
+    __shared__ float s_step_size[GOM_ADAM_MAX_SEGMENTS], s_bc2_sqrt[GOM_ADAM_MAX_SEGMENTS];
+    if (threadIdx.x < a.n_segments) {                       // per-segment scalars (double: 1 - beta^t loses digits in fp32)
+        const int s = threadIdx.x;
+        const long long t = a.dev_steps ? a.dev_steps[s] + 1 : a.seg_step[s];
+        const long long iter = a.dev_steps ? a.dev_steps[GOM_ADAM_MAX_SEGMENTS] : a.iter;
+        double lr = a.seg_lr[s];
+        if (a.lr_decay_steps > 0.f) lr *= pow((double)a.lr_decay_rate, (double)iter / (double)a.lr_decay_steps);
+        const double bc1 = 1.0 - pow((double)a.beta1, (double)t), bc2 = 1.0 - pow((double)a.beta2, (double)t);
+        s_step_size[s] = (float)(lr / bc1);
+        s_bc2_sqrt[s] = (float)sqrt(bc2);
+    }
+    __syncthreads();
     for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < a.n; i += (long long)gridDim.x * 256) {
         int s = 0;
         while (s + 1 < a.n_segments && i >= a.seg_end[s]) s++;
+        if (!a.seg_active[s]) continue;
         const float g = a.grad[i] * a.grad_scale;
         const float m = a.beta1 * a.exp_avg[i] + (1.f - a.beta1) * g;
         const float v = a.beta2 * a.exp_avg_sq[i] + (1.f - a.beta2) * g * g;
         a.exp_avg[i] = m;
         a.exp_avg_sq[i] = v;
-        const float denom = sqrtf(v) / bc2_sqrt + a.eps;
-        a.param[i] -= (a.seg_lr[s] / a.bias_correction1) * (m / denom);
+        const float denom = sqrtf(v) / s_bc2_sqrt[s] + a.eps;
+        a.param[i] -= s_step_size[s] * (m / denom);
     }
+}
+// device-resident counters: runs after k_adam on the same stream
+__global__ void k_adam_tick(GomAdamArgs a) {
+    const int s = threadIdx.x;
+    if (s < a.n_segments && a.seg_active[s]) a.dev_steps[s] += 1;
+    if (s == GOM_ADAM_MAX_SEGMENTS) a.dev_steps[s] += 1;
 }
 }  // namespace
 
@@ -31,13 +49,18 @@ extern "C" int gom_adam_step(const GomAdamArgs *p, gom_stream_t stream_) {
     GOM_REQUIRE(p->n > 0 && p->param && p->grad && p->exp_avg && p->exp_avg_sq, "null pointer / empty arena");
     GOM_REQUIRE(p->n_segments >= 1 && p->n_segments <= GOM_ADAM_MAX_SEGMENTS, "n_segments");
     GOM_REQUIRE(p->seg_end[p->n_segments - 1] >= p->n, "the last segment must end at or after n");
-    GOM_REQUIRE(p->bias_correction1 > 0.f && p->bias_correction2 > 0.f, "bias corrections must be positive (step >= 1)");
+    if (!p->dev_steps)
+        for (int s = 0; s < p->n_segments; s++) GOM_REQUIRE(!p->seg_active[s] || p->seg_step[s] >= 1, "seg_step must be >= 1 for active segments");
     cudaStream_t stream = (cudaStream_t)stream_;
     long long blocks = (p->n + 255) / 256;
     if (blocks > 148 * 8) blocks = 148 * 8;
     gom_prof_begin(GOM_PROF_ADAM, stream);
     k_adam<<<(unsigned)blocks, 256, 0, stream>>>(*p);
     GOM_LAUNCH_CHECK();
+    if (p->dev_steps) {
+        k_adam_tick<<<1, 32, 0, stream>>>(*p);
+        GOM_LAUNCH_CHECK();
+    }
     gom_prof_end(GOM_PROF_ADAM, stream);
     return GOM_OK;
 }

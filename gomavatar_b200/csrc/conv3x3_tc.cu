@@ -7,7 +7,8 @@
 // The kernel is bound by operand traffic L2 -> shared memory (measured: ~58 B/clk/SM whatever the tile shape), so the tiling
 // is chosen to move as few bytes per MMA as possible:
 //   * A CTA tile is 16 x 16 output pixels of one image = TWO M = 128 sub-tiles (left / right 8 columns; tensor-memory lane =
-//     16 rows x 8 columns) sharing every weight tile.
+//     16 rows x 8 columns) sharing every weight tile.  (Layers with too few such tiles to fill the 148 SMs — the deep layers
+//     at the reference's batch size of one frame — use ONE sub-tile and / or 64 output channels per tile: SUB, NT.)
 //   * A operand: ONE TMA tensor copy per 32-channel block fetches the 18 x PITCH-pixel halo of the CTA tile (zero-filled outside
 //     the image by the tensor map's bounds check, 128-byte swizzle).  The nine taps are nine shifted VIEWS of that halo: the
 //     shared-memory matrix descriptor of tap (r,s), sub-tile m starts at pixel (r, s + 8 m) of the halo, its 8-row groups (one
@@ -32,21 +33,29 @@ namespace {
 
 using namespace gomtc;
 
-constexpr int kTile = 16;                          // CTA tile: 16 x 16 output pixels
-constexpr int kHaloH = kTile + 2;
-constexpr int kThreads = 320;
-constexpr int kEpiWarps = 8;
+constexpr int kTileH = 16;                         // CTA tile: 16 rows x (8 SUB) columns of output pixels
+constexpr int kHaloH = kTileH + 2;
 constexpr int kEpiWarpBytes = 4096;                // store staging of one epilogue warp: 32 pixels x 32 channels
 
-template <int NT, int PITCH, int BST> struct ConvCfg {
+// NT: output channels per tile; SUB: M = 128 sub-tiles per tile (1 or 2); TPS: taps per weight stage (1 or 3 — a stage must
+// hold enough MMA work, >= ~500 cycles, to cover the issuing warp's per-stage barrier round trip); BST: weight ring depth
+template <int NT, int SUB, int TPS, int BST> struct ConvCfg {
+    static constexpr int TILE_W = 8 * SUB;
+    static constexpr int PITCH = TILE_W + 2;        // halo pitch in pixels: exactly the columns a tile needs (see gom_conv3x3)
     static constexpr int A_BYTES = ((kHaloH * PITCH * 128 + 1023) / 1024) * 1024;
     static constexpr int A_BUFS = 2;
-    static constexpr int B_BYTES = NT * 128;
-    static constexpr int SMEM = A_BUFS * A_BYTES + BST * B_BYTES + kEpiWarps * kEpiWarpBytes + 1024;
-    static constexpr uint32_t TMEM_COLS = 4 * NT <= 32 ? 32 : 4 * NT <= 64 ? 64 : 4 * NT <= 128 ? 128 : 4 * NT <= 256 ? 256 : 512;
-    static_assert(4 * NT <= 512, "two double-buffered accumulators must fit tensor memory");
-    static_assert(PITCH >= kTile + 2, "halo pitch");
+    static constexpr int B_TAP_BYTES = NT * 128;
+    static constexpr int B_BYTES = TPS * B_TAP_BYTES;
+    static constexpr int GROUPS = 9 / TPS;           // weight stages per halo
+    static constexpr int HALO_AT = TPS == 1 ? 5 : 1; // the next halo is requested before this weight stage of the current one
+    static constexpr int EPI_WARPS = 4 * SUB;
+    static constexpr int THREADS = 64 + 32 * EPI_WARPS;
+    static constexpr int ACC_COLS = SUB * NT;       // one accumulator stage
+    static constexpr int SMEM = A_BUFS * A_BYTES + BST * B_BYTES + EPI_WARPS * kEpiWarpBytes + 1024;
+    static constexpr uint32_t TMEM_COLS = 2 * ACC_COLS <= 32 ? 32 : 2 * ACC_COLS <= 64 ? 64 : 2 * ACC_COLS <= 128 ? 128 : 2 * ACC_COLS <= 256 ? 256 : 512;
+    static_assert(2 * ACC_COLS <= 512, "two accumulator stages must fit tensor memory");
     static_assert(SMEM <= 232448, "shared memory budget");
+    static_assert(TPS == 1 || TPS == 3, "taps per stage");
 };
 
 struct ConvDev {
@@ -56,7 +65,6 @@ struct ConvDev {
     int n_pass;                  // 1 (TF32) or 3 (3xTF32: x*w_hi, x_lo*w_hi, x*w_lo)
     int relu;
     int mask_words;              // c_out / 32: mask words per pixel
-    int base_offset_mode;        // debug: 1 = put the swizzle phase of the tap's start address into the descriptor's base-offset field
     const float *bias;
     const uint32_t *mask_in;
     uint32_t *mask_out;
@@ -102,23 +110,24 @@ __host__ __device__ constexpr uint32_t desc_hi(uint32_t sbo_bytes, uint32_t base
 }
 
 struct TileCoord { int n0, w0, h0, img; };
-__device__ __forceinline__ TileCoord decode_tile(const ConvDev &p, int tile, int nt) {
+__device__ __forceinline__ TileCoord decode_tile(const ConvDev &p, int tile, int nt, int tile_w) {
     TileCoord t;
     const int ni = tile % p.n_tiles_n;
     int m = tile / p.n_tiles_n;
     t.n0 = ni * nt;
-    t.w0 = (m % p.tiles_w) * kTile;
+    t.w0 = (m % p.tiles_w) * tile_w;
     m /= p.tiles_w;
-    t.h0 = (m % p.tiles_h) * kTile;
+    t.h0 = (m % p.tiles_h) * kTileH;
     t.img = m / p.tiles_h;
     return t;
 }
 
-template <int NT, int PITCH, int BST>
-__global__ void __launch_bounds__(kThreads, 1)
+template <int NT, int SUB, int TPS, int BST>
+__global__ void __launch_bounds__(ConvCfg<NT, SUB, TPS, BST>::THREADS, 1)
 k_conv3x3(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_a_lo,
           const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_out, const ConvDev p) {
-    using Cfg = ConvCfg<NT, PITCH, BST>;
+    using Cfg = ConvCfg<NT, SUB, TPS, BST>;
+    constexpr int PITCH = Cfg::PITCH;
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint64_t afull_bar[Cfg::A_BUFS], aempty_bar[Cfg::A_BUFS], bfull_bar[BST], bempty_bar[BST], tfull_bar[2], tempty_bar[2];
     __shared__ uint32_t tmem_slot;
@@ -132,7 +141,7 @@ k_conv3x3(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
     if (threadIdx.x == 0) {
         for (int i = 0; i < Cfg::A_BUFS; i++) { mbar_init(&afull_bar[i], 1); mbar_init(&aempty_bar[i], 1); }
         for (int i = 0; i < BST; i++) { mbar_init(&bfull_bar[i], 1); mbar_init(&bempty_bar[i], 1); }
-        for (int i = 0; i < 2; i++) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], kEpiWarps); }
+        for (int i = 0; i < 2; i++) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], Cfg::EPI_WARPS); }
         abort_flag = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -149,8 +158,9 @@ k_conv3x3(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
 
     if (warp == 0) {
         // ------------------------------------------------------------------------------------------- TMA producer
-        // One elected lane issues; the loop itself is warp-uniform.  Halo i + 1 is requested after the sixth weight tile of
-        // halo i: by then the MMA warp has released the buffer it goes into (it is at most BST weight tiles behind).
+        // One elected lane issues; the loop itself is warp-uniform.  Halo i + 1 is requested in the middle of the weight stages
+        // of halo i: the MMA warp is then about to release (or has released) the buffer it goes into, and the weight ring
+        // still holds work for it while the producer waits for that.
         if (elect_one()) {
             asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
             asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
@@ -161,7 +171,7 @@ k_conv3x3(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
         int a_tile = blockIdx.x, a_item = 0;
         auto issue_halo = [&]() -> bool {
             if (a_tile >= p.n_tiles) return true;
-            const TileCoord t = decode_tile(p, a_tile, NT);
+            const TileCoord t = decode_tile(p, a_tile, NT, Cfg::TILE_W);
             const int pass = a_item / p.c_blocks, cb = a_item - pass * p.c_blocks;
             const uint32_t buf = a_count & 1u, ph = (a_count >> 1) & 1u;
             if (!mbar_wait(&aempty_bar[buf], ph ^ 1u, ab)) return false;
@@ -177,12 +187,12 @@ k_conv3x3(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
         ok = issue_halo();
         bool ready = mbar_test_wait(&bempty_bar[0], 1u);
         for (int tile = blockIdx.x; tile < p.n_tiles && ok; tile += gridDim.x) {
-            const TileCoord t = decode_tile(p, tile, NT);
+            const TileCoord t = decode_tile(p, tile, NT, Cfg::TILE_W);
             for (int item = 0; item < items_per_tile && ok; item++) {
                 const int pass = item / p.c_blocks, cb = item - pass * p.c_blocks;
                 const int tap_off = pass == 2 ? 9 : 0;                  // the lo weight image follows the hi image
-                for (int tap = 0; tap < 9; tap++) {
-                    if (tap == 5 && !issue_halo()) { ok = false; break; }
+                for (int grp = 0; grp < Cfg::GROUPS; grp++) {
+                    if (grp == Cfg::HALO_AT && !issue_halo()) { ok = false; break; }
                     if (!ready && !mbar_wait(&bempty_bar[bst], bph ^ 1u, ab)) { ok = false; break; }
                     const uint32_t dst = b_base + bst * Cfg::B_BYTES;
                     uint64_t *fb = &bfull_bar[bst];
@@ -190,7 +200,7 @@ k_conv3x3(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
                     ready = mbar_test_wait(&bempty_bar[bst], bph ^ 1u);
                     if (elect_one()) {
                         mbar_expect_tx(fb, Cfg::B_BYTES);
-                        tma_load_3d(dst, &map_b, cb * 32, t.n0, tap_off + tap, fb);
+                        tma_load_3d(dst, &map_b, cb * 32, t.n0, tap_off + grp * TPS, fb);       // TPS taps in one box
                     }
                     __syncwarp();
                 }
@@ -208,14 +218,13 @@ k_conv3x3(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
         for (int tile = blockIdx.x; tile < p.n_tiles && ok; tile += gridDim.x, tcount++) {
             const uint32_t acc = tcount & 1u, aph = (tcount >> 1) & 1u;
             if (!mbar_wait(&tempty_bar[acc], aph ^ 1u, ab)) { ok = false; break; }
-            const uint32_t d0 = tmem + acc * (2 * NT);
+            const uint32_t d0 = tmem + acc * Cfg::ACC_COLS;
             for (int item = 0; item < items_per_tile && ok; item++, a_count++) {
                 const uint32_t abuf = a_count & 1u;
                 if (!mbar_wait(&afull_bar[abuf], (a_count >> 1) & 1u, ab)) { ok = false; break; }
                 const uint32_t a_buf_lo = a_desc0 + abuf * (Cfg::A_BYTES >> 4);
 #pragma unroll
-                for (int tap = 0; tap < 9; tap++) {
-                    const int r = tap / 3, s = tap % 3;
+                for (int grp = 0; grp < Cfg::GROUPS; grp++) {
                     if (!ready && !mbar_wait(&bfull_bar[bst], bph, ab)) { ok = false; break; }
                     const uint32_t b_lo = b_desc0 + bst * (Cfg::B_BYTES >> 4);
                     uint64_t *eb = &bempty_bar[bst];
@@ -223,18 +232,22 @@ k_conv3x3(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
                     ready = mbar_test_wait(&bfull_bar[bst], bph);
                     tc_fence_after();
                     if (elect_one()) {
-                        const uint32_t a_hi = desc_hi(PITCH * 128, p.base_offset_mode ? (uint32_t)s : 0u);
+                        constexpr uint32_t a_hi = desc_hi(PITCH * 128, 0);
 #pragma unroll
-                        for (int m = 0; m < 2; m++)
+                        for (int ti = 0; ti < TPS; ti++) {
+                            const int tap = grp * TPS + ti, r = tap / 3, s = tap % 3;
 #pragma unroll
-                            for (int k = 0; k < 4; k++) {
-                                const uint32_t al = a_buf_lo + (((r * PITCH + s + 8 * m) * 128 + k * 32) >> 4);
-                                const uint32_t bl = b_lo + ((k * 32) >> 4);
-                                if (k == 0 && tap == 0) mma_tf32(d0 + m * NT, al, a_hi, bl, kBHi, idesc, (uint32_t)(item != 0));
-                                else mma_tf32_acc(d0 + m * NT, al, a_hi, bl, kBHi, idesc);
-                            }
+                            for (int m = 0; m < SUB; m++)
+#pragma unroll
+                                for (int k = 0; k < 4; k++) {
+                                    const uint32_t al = a_buf_lo + (((r * PITCH + s + 8 * m) * 128 + k * 32) >> 4);
+                                    const uint32_t bl = b_lo + ((ti * Cfg::B_TAP_BYTES + k * 32) >> 4);
+                                    if (k == 0 && tap == 0) mma_tf32(d0 + m * NT, al, a_hi, bl, kBHi, idesc, (uint32_t)(item != 0));
+                                    else mma_tf32_acc(d0 + m * NT, al, a_hi, bl, kBHi, idesc);
+                                }
+                        }
                         tc_commit(eb);
-                        if (tap == 8) {
+                        if (grp == Cfg::GROUPS - 1) {
                             tc_commit(&aempty_bar[abuf]);
                             if (item == items_per_tile - 1) tc_commit(&tfull_bar[acc]);
                         }
@@ -254,7 +267,7 @@ k_conv3x3(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
         uint32_t tcount = 0;
         bool ok = true;
         for (int tile = blockIdx.x; tile < p.n_tiles && ok; tile += gridDim.x, tcount++) {
-            const TileCoord t = decode_tile(p, tile, NT);
+            const TileCoord t = decode_tile(p, tile, NT, Cfg::TILE_W);
             const int hw = t.h0 + 4 * q, ww = t.w0 + 8 * m;       // this warp's 4 x 8 pixels
             const int ph_ = hw + (lane >> 3), pw = ww + (lane & 7);
             const bool inside = ph_ < p.H && pw < p.W;
@@ -266,7 +279,7 @@ k_conv3x3(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
 #pragma unroll 1
             for (int ch = 0; ch < kChunks; ch++) {
                 uint32_t v[32];
-                tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + acc * (2 * NT) + m * NT + ch * 32, v);
+                tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + acc * Cfg::ACC_COLS + m * NT + ch * 32, v);
                 uint32_t mword = 0xFFFFFFFFu;
                 if (p.mask_in && inside) mword = __ldg(p.mask_in + mask_idx + ch);
                 tmem_wait_ld();
@@ -396,11 +409,11 @@ int make_act_map(CUtensorMap *m, const float *base, int N, int H, int W, int C, 
     if (r != CUDA_SUCCESS) { gom_set_error("gom_conv3x3: cuTensorMapEncodeTiled (activation) failed: %d", (int)r); return GOM_ERR_CUDA; }
     return GOM_OK;
 }
-// packed weight [taps][c_out][c_in] as a 3-D tensor (c_in, c_out, taps) with a (32, nt, 1) box
-int make_weight_map(CUtensorMap *m, const float *base, int taps, int c_out, int c_in, int nt) {
+// packed weight [taps][c_out][c_in] as a 3-D tensor (c_in, c_out, taps) with a (32, nt, taps_per_box) box
+int make_weight_map(CUtensorMap *m, const float *base, int taps, int c_out, int c_in, int nt, int taps_per_box) {
     const cuuint64_t dims[3] = {(cuuint64_t)c_in, (cuuint64_t)c_out, (cuuint64_t)taps};
     const cuuint64_t strides[2] = {(cuuint64_t)c_in * 4, (cuuint64_t)c_out * c_in * 4};
-    const cuuint32_t box[3] = {32, (cuuint32_t)nt, 1};
+    const cuuint32_t box[3] = {32, (cuuint32_t)nt, (cuuint32_t)taps_per_box};
     const cuuint32_t estr[3] = {1, 1, 1};
     const CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void *)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                 CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -408,14 +421,17 @@ int make_weight_map(CUtensorMap *m, const float *base, int taps, int c_out, int 
     return GOM_OK;
 }
 
-template <int NT, int PITCH, int BST>
+template <int NT, int SUB, int TPS, int BST>
 int launch_conv(const GomConv3x3Args *p, ConvDev &d, cudaStream_t stream) {
-    using Cfg = ConvCfg<NT, PITCH, BST>;
+    using Cfg = ConvCfg<NT, SUB, TPS, BST>;
+    constexpr int PITCH = Cfg::PITCH;
     static bool configured = false;
     if (!configured) {
-        GOM_CUDA(cudaFuncSetAttribute(k_conv3x3<NT, PITCH, BST>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+        GOM_CUDA(cudaFuncSetAttribute(k_conv3x3<NT, SUB, TPS, BST>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
         configured = true;
     }
+    d.tiles_w = gom_div_up(p->width, Cfg::TILE_W);
+    d.tiles_h = gom_div_up(p->height, kTileH);
     d.n_tiles_n = p->c_out / NT;
     const long long n_tiles = (long long)p->n_images * d.tiles_h * d.tiles_w * d.n_tiles_n;
     GOM_REQUIRE(n_tiles < (1ll << 30), "too many tiles");
@@ -424,10 +440,10 @@ int launch_conv(const GomConv3x3Args *p, ConvDev &d, cudaStream_t stream) {
     const bool round = p->tma_round && p->precision == 0;
     if (int rc = make_act_map(&ma, p->x, p->n_images, p->height, p->width, p->c_in, PITCH, kHaloH, round)) return rc;
     if (int rc = make_act_map(&malo, p->precision == 1 ? p->x_lo : p->x, p->n_images, p->height, p->width, p->c_in, PITCH, kHaloH, false)) return rc;
-    if (int rc = make_weight_map(&mb, p->w_packed, p->precision == 1 ? 18 : 9, p->c_out, p->c_in, NT)) return rc;
+    if (int rc = make_weight_map(&mb, p->w_packed, p->precision == 1 ? 18 : 9, p->c_out, p->c_in, NT, TPS)) return rc;
     if (int rc = make_act_map(&mo, p->out, p->n_images, p->height, p->width, p->c_out, 8, 4, false)) return rc;
     const int grid = d.n_tiles < g_sms ? d.n_tiles : g_sms;
-    k_conv3x3<NT, PITCH, BST><<<grid, kThreads, Cfg::SMEM, stream>>>(ma, malo, mb, mo, d);
+    k_conv3x3<NT, SUB, TPS, BST><<<grid, Cfg::THREADS, Cfg::SMEM, stream>>>(ma, malo, mb, mo, d);
     GOM_LAUNCH_CHECK();
     return GOM_OK;
 }
@@ -471,8 +487,6 @@ extern "C" int gom_conv3x3(const GomConv3x3Args *p, gom_stream_t stream_) {
 
     ConvDev d{};
     d.H = p->height; d.W = p->width;
-    d.tiles_w = gom_div_up(p->width, kTile);
-    d.tiles_h = gom_div_up(p->height, kTile);
     d.c_blocks = p->c_in / 32;
     d.n_pass = p->precision == 1 ? 3 : 1;
     d.relu = p->relu;
@@ -481,17 +495,41 @@ extern "C" int gom_conv3x3(const GomConv3x3Args *p, gom_stream_t stream_) {
     d.mask_in = p->mask_in;
     d.mask_out = p->mask_out;
     d.status = p->status;
-    static int bo_mode = -1, pitch18 = -1;
-    if (bo_mode < 0) { const char *e = getenv("GOM_CONV_BASE_OFFSET"); bo_mode = e ? atoi(e) : 0; }
-    if (pitch18 < 0) { const char *e = getenv("GOM_CONV_PITCH18"); pitch18 = e ? atoi(e) : 0; }
-    d.base_offset_mode = bo_mode;
 
     const int slot = p->relu ? GOM_PROF_CONV3X3_FWD : GOM_PROF_CONV3X3_DGRAD;
     gom_prof_begin(slot, stream);
     int rc;
-    if (p->c_out % 128 == 0) rc = pitch18 ? launch_conv<128, 18, 5>(p, d, stream) : launch_conv<128, 24, 5>(p, d, stream);
-    else if (p->c_out % 64 == 0) rc = pitch18 ? launch_conv<64, 18, 8>(p, d, stream) : launch_conv<64, 24, 8>(p, d, stream);
-    else rc = pitch18 ? launch_conv<32, 18, 8>(p, d, stream) : launch_conv<32, 24, 8>(p, d, stream);
+    // The halo pitch is exactly the tile width + 2 columns, so the 8-row groups of a tap's view start at arbitrary multiples of
+    // 128 B inside the 1024-byte swizzle pattern.  The tensor core handles that because the SWIZZLE_128B XOR is a function of
+    // the shared-memory ADDRESS bits (measured on B200: results identical to a 1024-byte-aligned pitch of 24 pixels, and wrong
+    // if the start phase is additionally written into the descriptor's base-offset field: profiles/r5_conv_probe_*.json).
+    //
+    // Tile shape: the largest one that still gives the 148 SMs about two waves of tiles; cost model = waves x MMA cycles of one
+    // tile (128 x NT x 8 TF32 MMA: NT / 2 cycles, but at least 48 — below NT = 128 the operand reads from shared memory bind;
+    // a single sub-tile does not share its weight tile, measured ~25 % slower per MMA).
+    struct Shape { int nt, sub; };
+    const Shape shapes[4] = {{128, 2}, {128, 1}, {64, 2}, {64, 1}};
+    Shape best = {p->c_out % 128 == 0 ? 128 : p->c_out % 64 == 0 ? 64 : 32, 2};
+    if (best.nt >= 64) {
+        double best_cost = 1e30;
+        for (const Shape &sh : shapes) {
+            if (p->c_out % sh.nt) continue;
+            const long long tiles = (long long)p->n_images * gom_div_up(p->height, kTileH) * gom_div_up(p->width, 8 * sh.sub) * (p->c_out / sh.nt);
+            const long long waves = (tiles + g_sms - 1) / g_sms;
+            const double mma = (sh.nt >= 128 ? 64.0 : 48.0) * (sh.sub == 1 ? 1.2 : 1.0);
+            const double cost = (double)waves * ((double)d.c_blocks * 9 * sh.sub * 4 * mma + 4000.0);
+            if (cost < best_cost * 0.97) { best_cost = cost; best = sh; }     // prefer the earlier (larger) shape on near ties
+        }
+    }
+    if (const char *force = getenv("GOM_CONV_SHAPE")) {            // tests: "NT,SUB" pins the tile shape (ignored if it does not divide c_out)
+        int nt = 0, sub = 0;
+        if (sscanf(force, "%d,%d", &nt, &sub) == 2 && (nt == 64 || nt == 128) && (sub == 1 || sub == 2) && p->c_out % nt == 0) best = {nt, sub};
+    }
+    if (best.nt == 128 && best.sub == 2) rc = launch_conv<128, 2, 1, 5>(p, d, stream);
+    else if (best.nt == 128) rc = launch_conv<128, 1, 3, 3>(p, d, stream);
+    else if (best.nt == 64 && best.sub == 2) rc = launch_conv<64, 2, 3, 4>(p, d, stream);
+    else if (best.nt == 64) rc = launch_conv<64, 1, 3, 5>(p, d, stream);
+    else rc = launch_conv<32, 2, 3, 6>(p, d, stream);
     if (rc) return rc;
     gom_prof_end(slot, stream);
     return GOM_OK;

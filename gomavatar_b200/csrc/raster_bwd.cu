@@ -18,7 +18,7 @@ struct BwdDev {
     const float *colors; long long colors_stride;
     const float *view, *proj, *tanfov, *bg;
     const float *final_T; const uint32_t *n_contrib; const int32_t *radii;
-    const float2 *xy; const float4 *conic_opacity; const uint32_t *tile_offset, *point_list;
+    const float2 *xy; const float4 *conic_opacity; const uint32_t *tile_offset, *point_list, *worklist;
     const float *dL_dout;
     float *dL_dmeans3D, *dL_dcov3D, *dL_dcolors; long long dL_dcolors_stride;
     float *dL_dopacity; float *dL_dmean2D; float *dL_dconic;
@@ -68,9 +68,10 @@ __global__ void __launch_bounds__(kBwdThreads) k_blend_bwd(BwdDev a) {
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const long long gw = (long long)blockIdx.x * kBwdWarps + wib;      // global warp = (frame, tile, sub-block)
     const int sub = (int)(gw & 7);
-    const long long ft = gw >> 3;
+    const long long wi = gw >> 3;
+    if (wi >= (long long)a.B * a.T) return;
+    const long long ft = a.worklist ? (long long)a.worklist[wi] : wi;      // longest lists first (the forward's order)
     const int tile = (int)(ft % a.T), b = (int)(ft / a.T);
-    if (b >= a.B) return;
     const uint32_t *off = a.tile_offset + (long long)b * (a.T + 1);
     long long start = off[tile], end = off[tile + 1];
     if (start > a.cap) start = a.cap;
@@ -317,7 +318,7 @@ extern "C" int gom_raster_backward(const GomRasterBwdArgs *p, gom_stream_t strea
     a.final_T = p->final_T; a.n_contrib = p->n_contrib; a.radii = p->radii;
     a.xy = reinterpret_cast<const float2 *>(p->xy);
     a.conic_opacity = reinterpret_cast<const float4 *>(p->conic_opacity);
-    a.tile_offset = p->tile_offset; a.point_list = p->point_list; a.dL_dout = p->dL_dout;
+    a.tile_offset = p->tile_offset; a.point_list = p->point_list; a.worklist = p->worklist; a.dL_dout = p->dL_dout;
     a.dL_dmeans3D = p->dL_dmeans3D; a.dL_dcov3D = p->dL_dcov3D;
     a.dL_dcolors = p->dL_dcolors; a.dL_dcolors_stride = p->dL_dcolors_stride;
     a.dL_dopacity = p->dL_dopacity; a.dL_dmean2D = p->dL_dmeans2D; a.dL_dconic = p->dL_dconic;

@@ -6,22 +6,26 @@
 //     do not leave most of the 148 SMs idle;
 //   * no host synchronisation: upstream's D2H read of num_rendered is replaced by fixed-capacity instance buffers
 //     and a device status flag, which also makes the whole forward CUDA-graph capturable;
-//   * binning is count -> scan -> scatter into per-tile segments, and the depth sort is a per-tile bitonic sort in
-//     shared memory fused into the blend kernel, instead of a global 64-bit radix sort (6+ passes over HBM);
+//   * binning is count -> scan -> scatter into per-tile segments, and the depth sort is a per-tile COUNTING sort in shared
+//     memory (k_tile_sort: depth bits bucketed over the tile's own depth range, exact (depth, id) order restored inside the
+//     few multi-entry buckets) instead of a global 64-bit radix sort (6+ passes over HBM);
+//   * tiles are processed longest list first (k_worklist orders all B*T tiles by list length on the device), so the launch
+//     tail is made of the short lists, and the blend runs as independent warps (8x4-pixel sub-blocks) in small blocks;
 //   * one fused pass renders 3 (reference layout) or 4 (RGB + alpha) channels.
 #include "gom_common.cuh"
 
 namespace {
 
 constexpr int kThreads = 256;
-constexpr int kSortCap = 4096;      // tile lists up to this length are sorted in shared memory (32 KB of dynamic smem) ...
-constexpr int kSortCapBig = 8192;   // ... or this one (64 KB, 3 blocks per SM) when the frame has more than kBigP Gaussians:
-constexpr int kBigP = 40000;        // at 55 104 Gaussians / 512^2 the busiest tile holds ~5 000 entries, and a list sorted
-                                    // in global memory made its block the straggler the whole launch waited for
+constexpr int kSortCap = 4096;      // entries of one counting-sort pass (32 KB of keys + 16 KB of bucket counters in shared memory);
+                                    // longer lists are sorted in several passes over consecutive bucket ranges
+constexpr int kBuckets = 4096;      // depth buckets of the counting sort
+constexpr int kLogBuckets = 12;
+constexpr int kMaxRun = 48;         // longest same-bucket run a single thread orders by insertion
+constexpr int kBlendThreads = 128;  // 4 independent warps per blend block
 
 struct FwdDev {
     int B, P, H, W, C, interleaved, gx, gy, T;
-    int sort_cap;                    // entries of dynamic shared memory k_sort_blend was launched with
     long long cap;
     const float *means3D; long long means3D_stride;
     const float *cov3D; long long cov3D_stride;
@@ -32,6 +36,7 @@ struct FwdDev {
     float *depth; float2 *xy; float4 *conic_opacity; int4 *rect;
     uint32_t *tile_count, *tile_offset, *tile_cursor; unsigned long long *inst_keys; uint32_t *point_list;
     uint32_t *status;
+    uint32_t *worklist;              // [B*T] (frame * T + tile), longest list first; nullptr: identity order
 };
 
 // ------------------------------------------------------------------------------------------- App. A.3 preprocess
@@ -242,42 +247,175 @@ __device__ void block_sort(unsigned long long *k, int n, int tid) {
     }
 }
 
-// ------------------------------------------------------------------------ App. A.5: per-tile depth sort + blend
-// One 256-thread block per tile sorts the tile's keys (shared memory), then its 8 warps blend INDEPENDENTLY: warp w
-// owns the 8x4-pixel sub-block (w & 1, w >> 1) and walks the sorted list in chunks of 32 entries — one entry per lane
-// is fetched and tested against the sub-block (entry_reaches_rect), survivors are staged in the warp's own shared
-// memory slots and visited through the ballot mask.  No block barrier after the sort: a warp whose 32 pixels are
-// saturated stops, the next chunk's records are prefetched while the current one is blended.
-template <int C>
-__global__ void __launch_bounds__(kThreads) k_sort_blend(FwdDev a) {
-    constexpr int kWarps = kThreads / 32;
-    extern __shared__ __align__(16) unsigned long long skeys[];       // a.sort_cap entries
-    __shared__ float2 s_xy[kWarps][32];
-    __shared__ float4 s_co[kWarps][32];
-    __shared__ __align__(16) float s_col[kWarps][32 * C];
+// ------------------------------------------------------------------ all B*T tiles ordered by list length, longest first
+// One block.  Key = bit length of the list length and its next two bits (132 classes); order inside a class is arbitrary
+// (it only decides which SM runs which tile, never a result).
+__global__ void __launch_bounds__(1024) k_worklist(FwdDev a) {
+    constexpr int kBins = 33 * 4;
+    __shared__ uint32_t hist[kBins];
+    const int total = a.B * a.T;
+    for (int i = threadIdx.x; i < kBins; i += blockDim.x) hist[i] = 0;
+    __syncthreads();
+    auto bin_of = [&](int e) {
+        const int b = e / a.T, t = e - b * a.T;
+        const uint32_t *off = a.tile_offset + (long long)b * (a.T + 1);
+        const uint32_t n = off[t + 1] - off[t];
+        if (n == 0) return kBins - 1;
+        const int len = 32 - __clz(n);                                   // 1 .. 32
+        const uint32_t frac = len >= 3 ? (n >> (len - 3)) & 3u : (n << (3 - len)) & 3u;
+        return (32 - len) * 4 + (3 - (int)frac);
+    };
+    for (int e = threadIdx.x; e < total; e += blockDim.x) atomicAdd(&hist[bin_of(e)], 1u);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t run = 0;
+        for (int i = 0; i < kBins; i++) { const uint32_t c = hist[i]; hist[i] = run; run += c; }
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < total; e += blockDim.x) a.worklist[atomicAdd(&hist[bin_of(e)], 1u)] = (uint32_t)e;
+}
 
-    const int b = blockIdx.z;
-    const int tile = blockIdx.y * a.gx + blockIdx.x;
-    const int tid = threadIdx.y * 16 + threadIdx.x;
+// ------------------------------------------------------------------------------------ App. A.4: per-tile depth sort
+// Sorts one tile's (depth bits << 32 | id) keys ascending — exactly the order of upstream's stable radix sort of
+// (tile | depth) keys over instances emitted in id order — and writes the ids to point_list.
+//   1. min / max of the depth bits over the list; bucket = (bits - min) >> shift, shift chosen so that the tile's own depth
+//      range spans the kBuckets buckets (positive floats order like their bit patterns);
+//   2. histogram + exclusive scan of the bucket counters;
+//   3. scatter into shared memory at bucket base + arrival order (arrival order is arbitrary, hence:)
+//   4. every bucket holding more than one key is put in exact key order by one thread (insertion; buckets are a fraction of a
+//      millimetre deep, so runs are 1-3 keys).  A bucket with more than kMaxRun keys (flat geometry, degenerate range) sends the
+//      pass to the block-wide bitonic network instead.
+// Lists longer than kSortCap are processed as consecutive bucket ranges of at most kSortCap keys each, re-reading the list
+// once per range; only a single bucket with more than kSortCap keys falls back to the bitonic network in global memory.
+__global__ void __launch_bounds__(kThreads) k_tile_sort(FwdDev a) {
+    extern __shared__ __align__(16) unsigned long long skeys[];          // kSortCap keys, then kBuckets counters
+    uint32_t *cnt = reinterpret_cast<uint32_t *>(skeys + kSortCap);
+    __shared__ uint32_t s_red[2][kThreads / 32];
+    __shared__ uint32_t s_scan[kThreads / 32];
+    __shared__ int s_flag;
+
+    const uint32_t entry = a.worklist ? a.worklist[blockIdx.x] : blockIdx.x;
+    const int b = (int)(entry / a.T), tile = (int)(entry % a.T);
     const uint32_t *off = a.tile_offset + (long long)b * (a.T + 1);
     long long start = off[tile], end = off[tile + 1];
     if (start > a.cap) start = a.cap;                      // overflowed frame: stay in bounds, result is flagged
     if (end > a.cap) end = a.cap;
     const int n = (int)(end - start);
-
+    if (n == 0) return;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     unsigned long long *gkeys = a.inst_keys + (long long)b * a.cap + start;
-    unsigned long long *sk = gkeys;
-    if (n <= a.sort_cap) {
-        for (int i = tid; i < n; i += kThreads) skeys[i] = gkeys[i];
-        sk = skeys;
-        __syncthreads();
-    }
-    block_sort(sk, n, tid);
     uint32_t *plist = a.point_list + (long long)b * a.cap + start;
-    for (int i = tid; i < n; i += kThreads) plist[i] = (uint32_t)sk[i];
+    if (n == 1) { if (tid == 0) plist[0] = (uint32_t)gkeys[0]; return; }
 
-    const int lane = tid & 31, wib = tid >> 5;
-    const int x0 = blockIdx.x * 16 + (wib & 1) * 8, y0 = blockIdx.y * 16 + (wib >> 1) * 4;
+    // 1. depth range
+    uint32_t lo = 0xffffffffu, hi = 0u;
+    for (int i = tid; i < n; i += kThreads) { const uint32_t d = (uint32_t)(gkeys[i] >> 32); lo = min(lo, d); hi = max(hi, d); }
+    lo = __reduce_min_sync(0xffffffffu, lo); hi = __reduce_max_sync(0xffffffffu, hi);
+    if (lane == 0) { s_red[0][warp] = lo; s_red[1][warp] = hi; }
+    for (int i = tid; i < kBuckets; i += kThreads) cnt[i] = 0;
+    if (tid == 0) s_flag = 0;
+    __syncthreads();
+    lo = s_red[0][0]; hi = s_red[1][0];
+#pragma unroll
+    for (int w = 1; w < kThreads / 32; w++) { lo = min(lo, s_red[0][w]); hi = max(hi, s_red[1][w]); }
+    const uint32_t range = hi - lo;
+    const int shift = range ? max(0, (32 - __clz(range)) - kLogBuckets) : 0;
+    // 2. histogram, exclusive scan (16 consecutive buckets per thread)
+    for (int i = tid; i < n; i += kThreads) atomicAdd(&cnt[((uint32_t)(gkeys[i] >> 32) - lo) >> shift], 1u);
+    __syncthreads();
+    {
+        constexpr int kPer = kBuckets / kThreads;
+        uint32_t v[kPer], sum = 0;
+#pragma unroll
+        for (int k = 0; k < kPer; k++) { v[k] = cnt[tid * kPer + k]; sum += v[k]; }
+        uint32_t incl = sum;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += y; }
+        if (lane == 31) s_scan[warp] = incl;
+        __syncthreads();
+        uint32_t base = incl - sum;
+        for (int w = 0; w < warp; w++) base += s_scan[w];
+#pragma unroll
+        for (int k = 0; k < kPer; k++) { cnt[tid * kPer + k] = base; base += v[k]; }
+    }
+    __syncthreads();
+    // 3./4. one pass per bucket range of at most kSortCap keys.  cnt[k] is the exclusive base of bucket k until the bucket has
+    // been scattered, its end afterwards (= the base of bucket k + 1).
+    int lo_b = 0;
+    while (lo_b < kBuckets) {
+        const uint32_t base_lo = cnt[lo_b];
+        if (base_lo >= (uint32_t)n) break;                               // only empty buckets are left
+        int hi_b;                                                        // largest hi_b with base(hi_b) - base_lo <= kSortCap
+        if ((uint32_t)n - base_lo <= (uint32_t)kSortCap) hi_b = kBuckets;
+        else {
+            int l = lo_b, r = kBuckets - 1;                              // invariant: base(l) fits, base(r + 1) may not
+            while (l < r) { const int m = (l + r + 1) >> 1; if (cnt[m] - base_lo <= (uint32_t)kSortCap) l = m; else r = m - 1; }
+            hi_b = l;
+        }
+        if (hi_b == lo_b) {                                              // one bucket alone exceeds a pass: global-memory bitonic
+            __syncthreads();
+            block_sort(gkeys, n, tid);
+            for (int i = tid; i < n; i += kThreads) plist[i] = (uint32_t)gkeys[i];
+            return;
+        }
+        const uint32_t count = (hi_b == kBuckets ? (uint32_t)n : cnt[hi_b]) - base_lo;
+        __syncthreads();                                                 // everyone has read the bases of this range
+        for (int i = tid; i < n; i += kThreads) {
+            const unsigned long long key = gkeys[i];
+            const int bk = (int)(((uint32_t)(key >> 32) - lo) >> shift);
+            if (bk >= lo_b && bk < hi_b) skeys[atomicAdd(&cnt[bk], 1u) - base_lo] = key;
+        }
+        __syncthreads();
+        for (int bk = lo_b + tid; bk < hi_b; bk += kThreads) {
+            const int rb = (int)((bk == lo_b ? base_lo : cnt[bk - 1]) - base_lo), re = (int)(cnt[bk] - base_lo);
+            if (re - rb > kMaxRun) { s_flag = 1; continue; }
+            for (int i = rb + 1; i < re; i++) {
+                const unsigned long long key = skeys[i];
+                int j = i - 1;
+                while (j >= rb && skeys[j] > key) { skeys[j + 1] = skeys[j]; j--; }
+                skeys[j + 1] = key;
+            }
+        }
+        __syncthreads();
+        if (s_flag) {                                                    // a long run: order the whole pass with the network
+            block_sort(skeys, (int)count, tid);
+            __syncthreads();
+            if (tid == 0) s_flag = 0;
+        }
+        for (int i = tid; i < (int)count; i += kThreads) plist[base_lo + i] = (uint32_t)skeys[i];
+        __syncthreads();
+        lo_b = hi_b;
+    }
+}
+
+// ------------------------------------------------------------------------------------------ App. A.5: alpha blending
+// Every warp is independent: it owns one 8x4-pixel sub-block of one tile (global warp index -> worklist entry, sub-block) and
+// walks the tile's sorted list front to back in chunks of 32 entries — one entry per lane is fetched and tested against the
+// sub-block (entry_reaches_rect), survivors are staged in the warp's own shared-memory slots and visited through the ballot
+// mask.  A warp whose 32 pixels are saturated stops; the next chunk's records are prefetched while the current one is blended.
+template <int C>
+__global__ void __launch_bounds__(kBlendThreads) k_blend(FwdDev a) {
+    constexpr int kWarps = kBlendThreads / 32;
+    __shared__ float2 s_xy[kWarps][32];
+    __shared__ float4 s_co[kWarps][32];
+    __shared__ __align__(16) float s_col[kWarps][32 * C];
+
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const long long gw = (long long)blockIdx.x * kWarps + wib;
+    const int sub = (int)(gw & 7);
+    const long long wi = gw >> 3;
+    if (wi >= (long long)a.B * a.T) return;
+    const uint32_t entry = a.worklist ? a.worklist[wi] : (uint32_t)wi;
+    const int b = (int)(entry / a.T), tile = (int)(entry % a.T);
+    const uint32_t *off = a.tile_offset + (long long)b * (a.T + 1);
+    long long start = off[tile], end = off[tile + 1];
+    if (start > a.cap) start = a.cap;
+    if (end > a.cap) end = a.cap;
+    const int n = (int)(end - start);
+    const uint32_t *plist = a.point_list + (long long)b * a.cap + start;
+
+    const int tx = tile % a.gx, ty = tile / a.gx;
+    const int x0 = tx * 16 + (sub & 1) * 8, y0 = ty * 16 + (sub >> 1) * 4;
     const int x = x0 + (lane & 7), y = y0 + (lane >> 3);
     const bool inside = x < a.W && y < a.H;
     const float pxf = (float)x, pyf = (float)y;
@@ -294,7 +432,7 @@ __global__ void __launch_bounds__(kThreads) k_sort_blend(FwdDev a) {
     uint32_t last = 0;
 
     uint32_t id_c = 0; float2 xy_c = make_float2(0.f, 0.f); float4 co_c = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (lane < n) { id_c = (uint32_t)sk[lane]; xy_c = __ldg(gxy + id_c); co_c = __ldg(gco + id_c); }
+    if (lane < n) { id_c = plist[lane]; xy_c = __ldg(gxy + id_c); co_c = __ldg(gco + id_c); }
     for (int base = 0; base < n; base += 32) {
         if (__all_sync(0xffffffffu, done)) break;
         const bool rel = (base + lane < n) && entry_reaches_rect(xy_c, co_c, rcx, rcy, 3.5f, 1.5f);
@@ -310,7 +448,7 @@ __global__ void __launch_bounds__(kThreads) k_sort_blend(FwdDev a) {
             }
         }
         const int nidx = base + 32 + lane;                 // prefetch the next chunk while this one is blended
-        if (nidx < n) { id_c = (uint32_t)sk[nidx]; xy_c = __ldg(gxy + id_c); co_c = __ldg(gco + id_c); }
+        if (nidx < n) { id_c = plist[nidx]; xy_c = __ldg(gxy + id_c); co_c = __ldg(gco + id_c); }
         __syncwarp();
         while (mask) {
             const int j = __ffs(mask) - 1;
@@ -376,7 +514,7 @@ extern "C" int gom_raster_forward(const GomRasterFwdArgs *p, gom_stream_t stream
     a.B = p->n_frames; a.P = p->n_gauss; a.H = p->height; a.W = p->width; a.C = p->n_channels;
     a.interleaved = p->interleaved;
     a.gx = (a.W + GOM_TILE - 1) / GOM_TILE; a.gy = (a.H + GOM_TILE - 1) / GOM_TILE; a.T = a.gx * a.gy;
-    GOM_REQUIRE(a.gy <= 65535, "image too tall");
+    GOM_REQUIRE((long long)a.B * a.T * 8 < 0x7fffffffLL, "too many tiles");
     a.cap = p->inst_capacity;
     a.means3D = p->means3D; a.means3D_stride = p->means3D_stride;
     a.cov3D = p->cov3D; a.cov3D_stride = p->cov3D_stride;
@@ -389,6 +527,7 @@ extern "C" int gom_raster_forward(const GomRasterFwdArgs *p, gom_stream_t stream
     a.tile_count = p->tile_count; a.tile_offset = p->tile_offset; a.tile_cursor = p->tile_cursor;
     a.inst_keys = reinterpret_cast<unsigned long long *>(p->inst_keys); a.point_list = p->point_list;
     a.status = p->status;
+    a.worklist = p->worklist;
     GOM_REQUIRE(((uintptr_t)p->xy % 8) == 0 && ((uintptr_t)p->conic_opacity % 16) == 0 && ((uintptr_t)p->rect % 16) == 0 &&
                     ((uintptr_t)p->inst_keys % 8) == 0, "state alignment");
 
@@ -411,23 +550,32 @@ extern "C" int gom_raster_forward(const GomRasterFwdArgs *p, gom_stream_t stream
         GOM_LAUNCH_CHECK();
         gom_prof_end(GOM_PROF_EMIT, stream);
     }
-    dim3 bgrid(a.gx, a.gy, a.B), bblock(16, 16);
-    a.sort_cap = a.P > kBigP ? kSortCapBig : kSortCap;
-    const size_t sort_bytes = sizeof(unsigned long long) * (size_t)a.sort_cap;
+    const int n_tiles = a.B * a.T;
+    if (a.worklist) {
+        gom_prof_begin(GOM_PROF_WORKLIST, stream);
+        k_worklist<<<1, 1024, 0, stream>>>(a);
+        GOM_LAUNCH_CHECK();
+        gom_prof_end(GOM_PROF_WORKLIST, stream);
+    }
+    constexpr size_t kSortSmem = sizeof(unsigned long long) * kSortCap + sizeof(uint32_t) * kBuckets;
     {
         // > 48 KB of dynamic shared memory is an opt-in per function AND per device (a process may drive several)
         static bool big_smem_enabled[64] = {};
         int dev = 0;
         GOM_CUDA(cudaGetDevice(&dev));
         if (dev < 0 || dev >= 64 || !big_smem_enabled[dev]) {
-            GOM_CUDA(cudaFuncSetAttribute(k_sort_blend<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(unsigned long long) * kSortCapBig)));
-            GOM_CUDA(cudaFuncSetAttribute(k_sort_blend<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(unsigned long long) * kSortCapBig)));
+            GOM_CUDA(cudaFuncSetAttribute(k_tile_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSortSmem));
             if (dev >= 0 && dev < 64) big_smem_enabled[dev] = true;
         }
     }
+    gom_prof_begin(GOM_PROF_TILE_SORT, stream);
+    k_tile_sort<<<n_tiles, kThreads, kSortSmem, stream>>>(a);
+    GOM_LAUNCH_CHECK();
+    gom_prof_end(GOM_PROF_TILE_SORT, stream);
+    const unsigned bgrid = (unsigned)(((long long)n_tiles * 8 + kBlendThreads / 32 - 1) / (kBlendThreads / 32));
     gom_prof_begin(GOM_PROF_BLEND_FWD, stream);
-    if (a.C == 3) k_sort_blend<3><<<bgrid, bblock, sort_bytes, stream>>>(a);
-    else k_sort_blend<4><<<bgrid, bblock, sort_bytes, stream>>>(a);
+    if (a.C == 3) k_blend<3><<<bgrid, kBlendThreads, 0, stream>>>(a);
+    else k_blend<4><<<bgrid, kBlendThreads, 0, stream>>>(a);
     GOM_LAUNCH_CHECK();
     gom_prof_end(GOM_PROF_BLEND_FWD, stream);
     return GOM_OK;

@@ -145,7 +145,8 @@ class Model(nn.Module):
         self.register_buffer("target_edge_length", torch.from_numpy(tel))       # reference model.py:58-60,127-134
         self.register_buffer("face_connectivity", torch.from_numpy(conn), persistent=False)
         self.strict_raster = strict_raster
-        self.last_raster_aux = None
+        self.last_raster_aux = None             # {'status', 'tile_offset', 'inst_capacity'} of the latest forward
+        self.keep_raster_aux = False            # True: keep every intermediate raster buffer there (tests / debugging)
 
     def forward(self, K, E, cnl_gtfms, dst_Rs, dst_Ts, dst_posevec=None, canonical_joints=None,
                 i_iter=1e7, bgcolor=None, global_R=None, global_T=None, tb=None):
@@ -181,7 +182,8 @@ class Model(nn.Module):
         rgba, radii, final_T, _ = rasterize_gaussians(means3D, cov3D, colors, opacity, view, proj, tanfov, bg, H, W,
                                                       interleaved=True, strict=self.strict_raster, aux=aux,
                                                       color_grad_channels=3)
-        self.last_raster_aux = aux
+        # what a training loop checks lazily (overflow flag, N_dup); everything else would only pin ~100 MB until the next call
+        self.last_raster_aux = aux if self.keep_raster_aux else {k: aux[k] for k in ("status", "tile_offset", "inst_capacity")}
         albedos, masks = rgba[..., :3], rgba[..., 3]
 
         normal = normal_mask = shadings = None
@@ -210,6 +212,17 @@ class Model(nn.Module):
             if normal is not None:
                 outputs["normal"], outputs["normal_mask"], outputs["shadow"] = normal, normal_mask[..., 0], shadings
         return rgbs, masks, outputs
+
+    def active_param_groups(self, i_iter):
+        """Names of the ``get_param_groups`` groups whose parameters take part in ``forward(..., i_iter=i_iter)`` — what
+        ``dist.ArenaAdam.step(active=...)`` needs to reproduce torch.optim.Adam, which skips parameters whose ``.grad`` is
+        None: the pose-refinement and non-rigid MLPs before their kick_in_iter (reference models/model.py:193-210)."""
+        names = ["appearance", "canonical_geometry_xyz", "canonical_geometry", "shadow"]
+        if self.pose_refinement_module is not None and i_iter >= _get(self.cfg, "pose_refinement.kick_in_iter", 0):
+            names.append("pose_refinement")
+        if self.non_rigid_module is not None and i_iter >= _get(self.cfg, "non_rigid.kick_in_iter", 0):
+            names.append("non_rigid")
+        return names
 
     def subdivide(self, need_face_connectivity=True):
         """reference models/model.py:136-179: split every face into 4 at its edge midpoints (subdivision.py mirrors

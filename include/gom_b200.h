@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define GOM_ABI_VERSION 6
+#define GOM_ABI_VERSION 7
 #define GOM_TILE 16              /* 16x16-pixel tiles, as upstream's BLOCK_X/BLOCK_Y */
 #define GOM_MAX_CHANNELS 4
 #define GOM_MAX_JOINTS 64
@@ -112,6 +112,8 @@ typedef struct {
     uint64_t *inst_keys;         /* [B,cap] (depth bits << 32 | gaussian id), grouped by tile, unsorted */
     uint32_t *point_list;        /* [B,cap] gaussian ids grouped by tile, sorted by (depth, id) */
     uint32_t *status;            /* [B]     GOM_STATUS_* bits */
+    uint32_t *worklist;          /* [B*T]   out, nullable: (frame * T + tile) of every tile, longest list first — the order the
+                                    sort / blend kernels (and the backward, if handed over) walk the tiles in */
 } GomRasterFwdArgs;
 int gom_raster_forward(const GomRasterFwdArgs *a, gom_stream_t stream);
 
@@ -138,6 +140,7 @@ typedef struct {
     const float *conic_opacity;
     const uint32_t *tile_offset;
     const uint32_t *point_list;
+    const uint32_t *worklist;    /* [B*T] nullable: the forward's tile order (longest list first) */
     /* upstream gradient */
     const float *dL_dout;        /* same layout as out_color */
     /* outputs */
@@ -460,7 +463,16 @@ int gom_mesh_raster_backward(const GomMeshRasterArgs *a, gom_stream_t stream);
  * Adam over the flat parameter arena, one launch.  Replaces `optimizer.step()` of reference train.py:339 for the
  * parameter groups of models/model.py:305-324 (torch.optim.Adam semantics, amsgrad off, weight decay 0).  Segment s
  * covers arena elements [seg_end[s-1], seg_end[s]) with learning rate seg_lr[s]; grad_scale multiplies the gradient
- * first (1 / world_size after the summing all-reduce).  The host owns the step counter and passes 1 - beta^step.
+ * first (1 / world_size after the summing all-reduce).
+ * torch.optim.Adam keeps one step counter per PARAMETER and skips parameters whose .grad is None (the reference's
+ * non-rigid / pose-refinement MLPs before their kick_in_iter): a segment with seg_active[s] = 0 is left untouched
+ * (parameter, both moments and its counter), and the bias corrections 1 - beta^t use the segment's own t.
+ * Step counters live on the host (dev_steps = NULL: the caller passes seg_step[s] = t of THIS step) or on the device
+ * (dev_steps != NULL: int64 [GOM_ADAM_MAX_SEGMENTS + 1], counters of the COMPLETED steps per segment and, last, of the whole
+ * optimizer; the call reads t = dev_steps[s] + 1 and a second tiny launch increments the counters of the active segments
+ * afterwards) — the second form has no step-dependent kernel argument, so the step can sit inside a CUDA graph.  With
+ * lr_decay_steps > 0 the learning rate is seg_lr[s] * lr_decay_rate^(iter / lr_decay_steps), iter = the optimizer-wide
+ * counter (reference train.py:166-175: update_lr, exponential decay), evaluated on the device in the second form.
  */
 #define GOM_ADAM_MAX_SEGMENTS 16
 typedef struct {
@@ -470,10 +482,14 @@ typedef struct {
     float *exp_avg;              /* [n] */
     float *exp_avg_sq;           /* [n] */
     float beta1, beta2, eps, grad_scale;
-    float bias_correction1, bias_correction2;
+    float lr_decay_rate, lr_decay_steps;     /* lr_decay_steps <= 0: constant learning rates */
     int32_t n_segments, _pad;
+    int64_t *dev_steps;          /* nullable, see above */
+    int64_t iter;                /* host form: optimizer-wide step index of this step (0-based) for the decay */
     int64_t seg_end[GOM_ADAM_MAX_SEGMENTS];
+    int64_t seg_step[GOM_ADAM_MAX_SEGMENTS]; /* host form: t (>= 1) of this step for the segment */
     float seg_lr[GOM_ADAM_MAX_SEGMENTS];
+    int32_t seg_active[GOM_ADAM_MAX_SEGMENTS];
 } GomAdamArgs;
 int gom_adam_step(const GomAdamArgs *a, gom_stream_t stream);
 

@@ -37,6 +37,7 @@ def test_model_forward_backward_at_baseline_configs(name, n_faces, size, focal, 
     with torch.no_grad():
         m.so3.copy_(t(pr["so3"])); m.scale.copy_(t(pr["scale"])); m.appearance_module.appearance.copy_(t(pr["appearance"]))
     m.train()
+    m.keep_raster_aux = True
     d = {k: t(v).to(DEV) for k, v in fr.items()}
     rgb, mask, out = m(d["K"], d["E"], d["cnl_gtfms"], d["dst_Rs"], d["dst_Ts"], dst_posevec=d["dst_posevec"])
     aux = m.last_raster_aux

@@ -177,3 +177,71 @@ def test_arena_adam_matches_torch_adam():
         opt2.step()
     for p1, p2 in zip(m1.parameters(), m2.parameters()):
         np.testing.assert_allclose(p1.detach().cpu().numpy(), p2.detach().cpu().numpy(), rtol=2e-6, atol=2e-7)
+
+
+def test_arena_adam_skips_inactive_groups_like_torch_and_round_trips_torch_state():
+    """torch.optim.Adam keeps a step counter per parameter and skips parameters whose .grad is None (the reference's
+    non-rigid / pose-refinement MLPs before their kick_in_iter, models/model.py:193-210).  ArenaAdam.step(active=...) must
+    reproduce that — first update of a late group is 1.0 x lr, not 3.2 x — with the counters on the host or on the device,
+    and its state_dict must be loadable by torch.optim.Adam (train.py:281) and vice versa."""
+    from gomavatar_b200.dist import ArenaAdam, FlatArena
+
+    class M(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            g = torch.Generator().manual_seed(4)
+            self.frozen = torch.nn.Parameter(torch.randn(7, generator=g), requires_grad=False)
+            self.a = torch.nn.Parameter(torch.randn(2, 513, generator=g))
+            self.late = torch.nn.Parameter(torch.randn(300, generator=g))
+
+    def groups(m):
+        return [{"name": "frozen", "params": [m.frozen], "lr": 0.0}, {"name": "a", "params": [m.a], "lr": 1e-2},
+                {"name": "late", "params": [m.late], "lr": 5e-3}]
+
+    for device_state in (False, True):
+        m1, m2 = M().to(DEV), M().to(DEV)
+        arena = FlatArena(m1)
+        opt1 = ArenaAdam(arena, groups(m1), device_state=device_state)
+        opt2 = torch.optim.Adam([{k: v for k, v in g.items() if k != "name"} for g in groups(m2)])
+        gen = torch.Generator(device=DEV).manual_seed(1)
+        kick_in = 4
+        for step in range(8):
+            arena.zero_grad()
+            opt2.zero_grad(set_to_none=True)
+            ga = torch.randn(m1.a.shape, generator=gen, device=DEV)
+            m1.a.grad.copy_(ga); m2.a.grad = ga.clone()
+            active = ["a"]
+            if step >= kick_in:
+                gl = torch.randn(m1.late.shape, generator=gen, device=DEV)
+                m1.late.grad.copy_(gl); m2.late.grad = gl.clone()
+                active.append("late")
+            opt1.step(active=active)
+            opt2.step()
+            if step == kick_in:         # the late group's first update: |delta| = lr (bias-corrected m / sqrt(v) = sign(g))
+                d = (m1.late.detach() - M().late.detach().to(DEV)).abs()
+                np.testing.assert_allclose(d.cpu().numpy(), 5e-3, rtol=1e-3)
+        for p1, p2 in zip((m1.a, m1.late), (m2.a, m2.late)):
+            np.testing.assert_allclose(p1.detach().cpu().numpy(), p2.detach().cpu().numpy(), rtol=2e-6, atol=2e-7)
+        # torch reads our state ...
+        sd = opt1.state_dict()
+        assert [len(g["params"]) for g in sd["param_groups"]] == [1, 1, 1] and sorted(sd["state"]) == [1, 2]
+        assert float(sd["state"][1]["step"]) == 8 and float(sd["state"][2]["step"]) == 8 - kick_in
+        m3 = M().to(DEV)
+        opt3 = torch.optim.Adam([{k: v for k, v in g.items() if k != "name"} for g in groups(m3)])
+        opt3.load_state_dict(sd)
+        for k in ("exp_avg", "exp_avg_sq"):
+            torch.testing.assert_close(opt3.state[m3.late][k], opt2.state[m2.late][k], rtol=5e-5, atol=1e-7)
+        # ... and we read torch's, and continue identically
+        m4 = M().to(DEV)
+        with torch.no_grad():
+            m4.a.copy_(m2.a); m4.late.copy_(m2.late)
+        arena4 = FlatArena(m4)
+        opt4 = ArenaAdam(arena4, groups(m4), device_state=device_state)
+        opt4.load_state_dict(opt2.state_dict())
+        ga, gl = torch.randn(m1.a.shape, generator=gen, device=DEV), torch.randn(m1.late.shape, generator=gen, device=DEV)
+        m4.a.grad.copy_(ga); m4.late.grad.copy_(gl); m2.a.grad = ga.clone(); m2.late.grad = gl.clone()
+        opt4.step(active=["a", "late"]); opt2.step()
+        for p1, p2 in zip((m4.a, m4.late), (m2.a, m2.late)):
+            np.testing.assert_allclose(p1.detach().cpu().numpy(), p2.detach().cpu().numpy(), rtol=2e-6, atol=2e-7)
+    with pytest.raises(KeyError):
+        opt4.load_state_dict({})

@@ -161,6 +161,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--quick", action="store_true")
     ap.add_argument("--iters", type=int, default=10)
+    ap.add_argument("--n-fwd", type=int, default=16, help="images per forward call (2 x frames per step)")
+    ap.add_argument("--n-bwd", type=int, default=8, help="images per dgrad call (frames per step)")
     ap.add_argument("--out", default="gpurun_out/conv_probe.json")
     a = ap.parse_args()
     report = {"small": [], "layers": [], "gpu": torch.cuda.get_device_name(0)}
@@ -172,7 +174,7 @@ def main():
         worst[k] = max(worst.get(k, 0.0), r["l2_rel"])
     print("small shapes: worst l2 error per precision", worst, "status bits", sorted({r.get("status", 0) for r in report["small"]}), flush=True)
     if not a.quick:
-        bench_layers(report, a.iters)
+        bench_layers(report, a.iters, a.n_fwd, a.n_bwd)
     tot_own = sum(r["fwd_ms"] for r in report["layers"]), sum(r["dgrad_ms"] for r in report["layers"])
     tot_cudnn = sum(r["fwd_cudnn_ms"] for r in report["layers"]), sum(r["dgrad_cudnn_ms"] for r in report["layers"])
     report["totals_ms"] = {"own_fwd": tot_own[0], "own_dgrad": tot_own[1], "cudnn_fwd": tot_cudnn[0], "cudnn_dgrad": tot_cudnn[1]}
