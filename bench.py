@@ -263,8 +263,9 @@ class Trainer:
             _lib.profile_enable(False)                           # profiling events cannot be recorded inside a capture
             for scope in (("step", "fwd_bwd") if self.graph_scope is None else (self.graph_scope,)):
                 try:
-                    for _ in range(2):                           # warm-up on the capture stream (allocator, NCCL channels)
-                        self._fwd_bwd(d, tgt_rgb, tgt_mask, with_optimizer=True)
+                    for _ in range(2):                           # warm-up on the capture stream (allocator, NCCL channels);
+                        self._fwd_bwd(d, tgt_rgb, tgt_mask)      # no optimizer step: the parameters must not move here
+                        self.arena.all_reduce_sum()
                     torch.cuda.synchronize(self.dev)
                     n0 = _lib.launch_count()
                     g = torch.cuda.CUDAGraph()

@@ -107,11 +107,12 @@ def train(data, iters, img, device, batch=2, lr=5e-4, ckpt_dir=None, save_freq=0
             for g, b0 in zip(opt.param_groups, base):                                      # train.py:166-175
                 g["lr"] = b0 * 0.1 ** (n_iter / 100000)
             history.append(float(loss.detach()))
-            if n_iter % max(1, iters // 10) == 0:                                          # one sync per log interval
-                st = int(model.last_raster_aux["status"].max().item())
+            aux = model.last_raster_aux                                                    # None right after a subdivision
+            if aux is not None and n_iter % max(1, iters // 10) == 0:                      # one sync per log interval
+                st = int(aux["status"].max().item())
                 if st:     # k_emit dropped (Gaussian, tile) instances: the tile lists of those frames were truncated
                     raise RuntimeError(f"rasterizer status {st} at iteration {n_iter}: instance capacity "
-                                       f"{model.last_raster_aux['inst_capacity']} exceeded; rebuild the Model with a larger raster_capacity")
+                                       f"{aux['inst_capacity']} exceeded; rebuild the Model with a larger raster_capacity")
             if log and (n_iter % max(1, iters // 10) == 0):
                 log(f"iter {n_iter:6d}  loss {history[-1]:.5f}  " + "  ".join(f"{k} {float(v['scaled']):.5f}" for k, v in terms.items()))
             if ckpt_dir and save_freq and n_iter % save_freq == 0:

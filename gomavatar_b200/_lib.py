@@ -308,5 +308,14 @@ def call(name, args):
 
 
 def ptr(t):
-    """device pointer of a torch tensor (None -> NULL)"""
-    return None if t is None else c_void_p(t.data_ptr())
+    """device pointer of a torch tensor (None -> NULL).  Kernels are launched on the CURRENT device's current stream, so a
+    tensor living on another GPU (model.to('cuda:1') without torch.cuda.set_device(1)) is refused instead of being
+    dereferenced from the wrong device."""
+    if t is None:
+        return None
+    if t.is_cuda:
+        import torch
+        if t.device.index != torch.cuda.current_device():
+            raise GomError(f"tensor on {t.device} but the current CUDA device is cuda:{torch.cuda.current_device()}: "
+                           "call torch.cuda.set_device(...) (or use `with torch.cuda.device(...)`) before launching")
+    return c_void_p(t.data_ptr())

@@ -15,7 +15,7 @@ sys.path.insert(0, ROOT)
 
 def _args(**kw):
     a = dict(gpus=1, steps=2, warmup=1, impl="b200", frames_per_step=2, faces=2000, img=64, pool_steps=2, lpips_precision="tf32",
-             lpips_torch=False, lpips_epilogue="cudnn", cuda_graph=False, full_model=True, no_cpu_baseline=True, cpu_frames=1)
+             lpips_torch=False, lpips_epilogue="cudnn", lpips_conv="tcgen05", no_extras=True, cuda_graph=False, full_model=True, no_cpu_baseline=True, cpu_frames=1)
     a.update(kw)
     return types.SimpleNamespace(**a)
 
