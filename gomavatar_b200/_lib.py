@@ -13,7 +13,7 @@ from ctypes import c_int, c_int32, c_int64, c_size_t, c_void_p, c_float, c_char_
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libgom_b200.so")
 
-ABI_VERSION = 7
+ABI_VERSION = 8
 STATUS_OVERFLOW = 1
 STATUS_TIMEOUT = 2
 
@@ -35,7 +35,7 @@ class GomRasterFwdArgs(ctypes.Structure):
                 ("out_color", c_void_p), ("final_T", c_void_p), ("n_contrib", c_void_p), ("radii", c_void_p),
                 ("depth", c_void_p), ("xy", c_void_p), ("conic_opacity", c_void_p), ("rect", c_void_p),
                 ("tile_count", c_void_p), ("tile_offset", c_void_p), ("tile_cursor", c_void_p),
-                ("inst_keys", c_void_p), ("point_list", c_void_p), ("status", c_void_p), ("worklist", c_void_p)]
+                ("inst_keys", c_void_p), ("point_list", c_void_p), ("status", c_void_p), ("worklist", c_void_p), ("point_mask", c_void_p)]
 
 
 class GomRasterBwdArgs(ctypes.Structure):
@@ -47,7 +47,7 @@ class GomRasterBwdArgs(ctypes.Structure):
                 ("colors", c_void_p), ("colors_stride", c_int64),
                 ("viewmatrix", c_void_p), ("projmatrix", c_void_p), ("tanfov", c_void_p), ("bg", c_void_p),
                 ("final_T", c_void_p), ("n_contrib", c_void_p), ("radii", c_void_p), ("xy", c_void_p),
-                ("conic_opacity", c_void_p), ("tile_offset", c_void_p), ("point_list", c_void_p), ("worklist", c_void_p),
+                ("conic_opacity", c_void_p), ("tile_offset", c_void_p), ("point_list", c_void_p), ("worklist", c_void_p), ("point_mask", c_void_p),
                 ("dL_dout", c_void_p),
                 ("dL_dmeans3D", c_void_p), ("dL_dcov3D", c_void_p),
                 ("dL_dcolors", c_void_p), ("dL_dcolors_stride", c_int64),

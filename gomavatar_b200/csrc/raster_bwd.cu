@@ -18,7 +18,7 @@ struct BwdDev {
     const float *colors; long long colors_stride;
     const float *view, *proj, *tanfov, *bg;
     const float *final_T; const uint32_t *n_contrib; const int32_t *radii;
-    const float2 *xy; const float4 *conic_opacity; const uint32_t *tile_offset, *point_list, *worklist;
+    const float2 *xy; const float4 *conic_opacity; const uint32_t *tile_offset, *point_list, *worklist; const uint8_t *point_mask;
     const float *dL_dout;
     float *dL_dmeans3D, *dL_dcov3D, *dL_dcolors; long long dL_dcolors_stride;
     float *dL_dopacity; float *dL_dmean2D; float *dL_dconic;
@@ -129,10 +129,19 @@ __global__ void __launch_bounds__(kBwdThreads) k_blend_bwd(BwdDev a) {
         else { red_base = o_opac; red_stride = 1; }
     }
 
-    uint32_t id_c = 0; float2 xy_c = make_float2(0.f, 0.f); float4 co_c = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (n_eff - 1 - lane >= 0) { id_c = plist[n_eff - 1 - lane]; xy_c = __ldg(gxy + id_c); co_c = __ldg(gco + id_c); }
+    const uint8_t *pmask = a.point_mask ? a.point_mask + (long long)b * a.cap + start : nullptr;
+    // ids (+ sub-block masks) two chunks ahead, records of the reaching entries one chunk ahead (see k_blend)
+    uint32_t id_c = 0, id_n = 0; bool rel_c = false, rel_n = false;
+    float2 xy_c = make_float2(0.f, 0.f); float4 co_c = make_float4(0.f, 0.f, 0.f, 0.f);
+    auto fetch_id = [&](int idx, uint32_t &id, bool &rel) {
+        rel = false;
+        if (idx >= 0) { id = plist[idx]; rel = pmask ? ((pmask[idx] >> sub) & 1u) != 0u : true; }
+    };
+    fetch_id(n_eff - 1 - lane, id_c, rel_c);
+    fetch_id(n_eff - 33 - lane, id_n, rel_n);
+    if (rel_c) { xy_c = __ldg(gxy + id_c); co_c = __ldg(gco + id_c); }
     for (int hi = n_eff; hi > 0; hi -= 32) {               // lane j of a chunk holds list entry hi-1-j (back to front)
-        const bool rel = (hi - 1 - lane >= 0) && entry_reaches_rect(xy_c, co_c, rcx, rcy, 3.5f, 1.5f);
+        const bool rel = rel_c && (pmask != nullptr || entry_reaches_rect(xy_c, co_c, rcx, rcy, 3.5f, 1.5f));
         unsigned mask = __ballot_sync(0xffffffffu, rel);
         if (rel) {
             s_id[wib][lane] = id_c;
@@ -145,67 +154,90 @@ __global__ void __launch_bounds__(kBwdThreads) k_blend_bwd(BwdDev a) {
                 for (int ch = 0; ch < C; ch++) s_col[wib][lane * C + ch] = __ldg(gcol + (long long)id_c * C + ch);
             }
         }
-        const int nidx = hi - 32 - 1 - lane;                // prefetch the next chunk
-        if (nidx >= 0) { id_c = plist[nidx]; xy_c = __ldg(gxy + id_c); co_c = __ldg(gco + id_c); }
+        id_c = id_n; rel_c = rel_n;
+        if (rel_c) { xy_c = __ldg(gxy + id_c); co_c = __ldg(gco + id_c); }
+        fetch_id(hi - 65 - lane, id_n, rel_n);
         __syncwarp();
+        // Two survivors per round: their Gaussian values (shared-memory reads, exp) and, afterwards, their two butterfly
+        // reductions are independent and overlap; only the T / accumulated-colour recurrence between them is sequential.
+        constexpr int kU = 2;
+        constexpr int kNG = NG > 8 ? NG : 8;
         while (mask) {
-            const int j = __ffs(mask) - 1;
-            mask &= mask - 1;
-            const uint32_t k = (uint32_t)(hi - 1 - j);
-            bool valid = k < last_contributor;
-            float g[NG > 8 ? NG : 8];
+            int j[kU];
+            float g[kU][kNG];
+            bool valid[kU];
+            float G[kU], alpha[kU], dx[kU], dy[kU];
+            float4 co[kU];
 #pragma unroll
-            for (int c = 0; c < (NG > 8 ? NG : 8); c++) g[c] = 0.f;
-            if (valid) {
-                const float2 c = s_xy[wib][j];
-                const float4 co = s_co[wib][j];
-                const float dx = c.x - pxf, dy = c.y - pyf;
-                const float power = -0.5f * (co.x * dx * dx + co.z * dy * dy) - co.y * dx * dy;
-                const float G = __expf(power);
-                const float alpha = fminf(0.99f, co.w * G);
-                valid = (power <= 0.0f) && (alpha >= 1.0f / 255.0f);
-                if (valid) {
-                    const float inv1ma = __fdividef(1.f, 1.f - alpha);
+            for (int u = 0; u < kU; u++) {
+                const bool have = mask != 0u;
+                j[u] = have ? __ffs(mask) - 1 : 0;
+                mask &= mask - 1;
+                const uint32_t k = (uint32_t)(hi - 1 - j[u]);
+                const float2 c = s_xy[wib][j[u]];
+                co[u] = s_co[wib][j[u]];
+                dx[u] = c.x - pxf; dy[u] = c.y - pyf;
+                const float power = -0.5f * (co[u].x * dx[u] * dx[u] + co[u].z * dy[u] * dy[u]) - co[u].y * dx[u] * dy[u];
+                G[u] = __expf(power);
+                alpha[u] = fminf(0.99f, co[u].w * G[u]);
+                valid[u] = have && k < last_contributor && (power <= 0.0f) && (alpha[u] >= 1.0f / 255.0f);
+            }
+#pragma unroll
+            for (int u = 0; u < kU; u++) {
+#pragma unroll
+                for (int c = 0; c < kNG; c++) g[u][c] = 0.f;
+                if (valid[u]) {
+                    const float inv1ma = __fdividef(1.f, 1.f - alpha[u]);
                     T = T * inv1ma;
-                    const float dchannel_dcolor = alpha * T;
+                    const float dchannel_dcolor = alpha[u] * T;
                     float dL_dalpha = 0.f;
 #pragma unroll
                     for (int ch = 0; ch < C; ch++) {
-                        const float col = s_col[wib][j * C + ch];
+                        const float col = s_col[wib][j[u] * C + ch];
                         accum_rec[ch] = last_alpha * last_color[ch] + (1.f - last_alpha) * accum_rec[ch];
                         last_color[ch] = col;
                         dL_dalpha += (col - accum_rec[ch]) * dpix[ch];
-                        if (ch < CG) g[5 + ch] = dchannel_dcolor * dpix[ch];
+                        if (ch < CG) g[u][5 + ch] = dchannel_dcolor * dpix[ch];
                     }
                     dL_dalpha *= T;
-                    last_alpha = alpha;
+                    last_alpha = alpha[u];
                     dL_dalpha += (-T_final * inv1ma) * bg_dot;
-                    const float dL_dG = co.w * dL_dalpha;          // the 0.99 clamp is ignored, as upstream
-                    const float gdx = G * dx, gdy = G * dy;
-                    const float dG_ddelx = -gdx * co.x - gdy * co.y;
-                    const float dG_ddely = -gdy * co.z - gdx * co.y;
-                    g[0] = dL_dG * dG_ddelx * ddelx_dx;
-                    g[1] = dL_dG * dG_ddely * ddely_dy;
-                    g[2] = -0.5f * gdx * dx * dL_dG;
-                    g[3] = -0.5f * gdx * dy * dL_dG;
-                    g[4] = -0.5f * gdy * dy * dL_dG;
-                    if (OPAC) g[5 + CG] = G * dL_dalpha;
+                    const float dL_dG = co[u].w * dL_dalpha;          // the 0.99 clamp is ignored, as upstream
+                    const float gdx = G[u] * dx[u], gdy = G[u] * dy[u];
+                    const float dG_ddelx = -gdx * co[u].x - gdy * co[u].y;
+                    const float dG_ddely = -gdy * co[u].z - gdx * co[u].y;
+                    g[u][0] = dL_dG * dG_ddelx * ddelx_dx;
+                    g[u][1] = dL_dG * dG_ddely * ddely_dy;
+                    g[u][2] = -0.5f * gdx * dx[u] * dL_dG;
+                    g[u][3] = -0.5f * gdx * dy[u] * dL_dG;
+                    g[u][4] = -0.5f * gdy * dy[u] * dL_dG;
+                    if (OPAC) g[u][5 + CG] = G[u] * dL_dalpha;
                 }
             }
-            if (!__any_sync(0xffffffffu, valid)) continue;
-            const uint32_t id = s_id[wib][j];
+            bool any[kU];
+#pragma unroll
+            for (int u = 0; u < kU; u++) any[u] = __any_sync(0xffffffffu, valid[u]);
             if constexpr (NG <= 8) {
-                const float tot = butterfly8(g, lane);
-                if (red_base && tot != 0.f) atomicAdd(red_base + (long long)id * red_stride, tot);
+                float tot[kU];
+#pragma unroll
+                for (int u = 0; u < kU; u++) tot[u] = any[u] ? butterfly8(g[u], lane) : 0.f;
+#pragma unroll
+                for (int u = 0; u < kU; u++)
+                    if (any[u] && red_base && tot[u] != 0.f) atomicAdd(red_base + (long long)s_id[wib][j[u]] * red_stride, tot[u]);
             } else {
 #pragma unroll
-                for (int c = 0; c < NG; c++) {
-                    const float tot = warp_sum(g[c]);
-                    if (lane == 0 && tot != 0.f) {
-                        float *dst = c < 2 ? o_mean2D + 2LL * id + c
-                                   : c < 5 ? o_conic + 3LL * id + (c - 2)
-                                   : c < 5 + CG ? o_col + (long long)id * C + (c - 5) : o_opac + id;
-                        atomicAdd(dst, tot);
+                for (int u = 0; u < kU; u++) {
+                    if (!any[u]) continue;
+                    const uint32_t id = s_id[wib][j[u]];
+#pragma unroll
+                    for (int c = 0; c < NG; c++) {
+                        const float tot = warp_sum(g[u][c]);
+                        if (lane == 0 && tot != 0.f) {
+                            float *dst = c < 2 ? o_mean2D + 2LL * id + c
+                                       : c < 5 ? o_conic + 3LL * id + (c - 2)
+                                       : c < 5 + CG ? o_col + (long long)id * C + (c - 5) : o_opac + id;
+                            atomicAdd(dst, tot);
+                        }
                     }
                 }
             }
@@ -318,7 +350,7 @@ extern "C" int gom_raster_backward(const GomRasterBwdArgs *p, gom_stream_t strea
     a.final_T = p->final_T; a.n_contrib = p->n_contrib; a.radii = p->radii;
     a.xy = reinterpret_cast<const float2 *>(p->xy);
     a.conic_opacity = reinterpret_cast<const float4 *>(p->conic_opacity);
-    a.tile_offset = p->tile_offset; a.point_list = p->point_list; a.worklist = p->worklist; a.dL_dout = p->dL_dout;
+    a.tile_offset = p->tile_offset; a.point_list = p->point_list; a.worklist = p->worklist; a.point_mask = p->point_mask; a.dL_dout = p->dL_dout;
     a.dL_dmeans3D = p->dL_dmeans3D; a.dL_dcov3D = p->dL_dcov3D;
     a.dL_dcolors = p->dL_dcolors; a.dL_dcolors_stride = p->dL_dcolors_stride;
     a.dL_dopacity = p->dL_dopacity; a.dL_dmean2D = p->dL_dmeans2D; a.dL_dconic = p->dL_dconic;

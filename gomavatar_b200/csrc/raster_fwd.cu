@@ -37,6 +37,7 @@ struct FwdDev {
     uint32_t *tile_count, *tile_offset, *tile_cursor; unsigned long long *inst_keys; uint32_t *point_list;
     uint32_t *status;
     uint32_t *worklist;              // [B*T] (frame * T + tile), longest list first; nullptr: identity order
+    uint8_t *point_mask;             // [B,cap] per list entry: bit s = the entry can reach 8x4 sub-block s of its tile; nullptr: test in the blend
 };
 
 // ------------------------------------------------------------------------------------------- App. A.3 preprocess
@@ -287,6 +288,18 @@ __global__ void __launch_bounds__(1024) k_worklist(FwdDev a) {
 //      pass to the block-wide bitonic network instead.
 // Lists longer than kSortCap are processed as consecutive bucket ranges of at most kSortCap keys each, re-reading the list
 // once per range; only a single bucket with more than kSortCap keys falls back to the bitonic network in global memory.
+// bit s of the result: entry (xy, conic/opacity) passes the conservative alpha >= 1/255 test somewhere in sub-block s
+// (8 columns x 4 rows; s & 1 = left / right half, s >> 1 = row band) of the tile whose top-left pixel is (tx0, ty0)
+__device__ __forceinline__ uint32_t sub_block_mask(float2 c, float4 co, int tx0, int ty0) {
+    uint32_t m = 0;
+#pragma unroll
+    for (int sb = 0; sb < 8; sb++) {
+        const float rcx = (float)(tx0 + (sb & 1) * 8) + 3.5f, rcy = (float)(ty0 + (sb >> 1) * 4) + 1.5f;
+        m |= entry_reaches_rect(c, co, rcx, rcy, 3.5f, 1.5f) ? (1u << sb) : 0u;
+    }
+    return m;
+}
+
 __global__ void __launch_bounds__(kThreads) k_tile_sort(FwdDev a) {
     extern __shared__ __align__(16) unsigned long long skeys[];          // kSortCap keys, then kBuckets counters
     uint32_t *cnt = reinterpret_cast<uint32_t *>(skeys + kSortCap);
@@ -305,7 +318,17 @@ __global__ void __launch_bounds__(kThreads) k_tile_sort(FwdDev a) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     unsigned long long *gkeys = a.inst_keys + (long long)b * a.cap + start;
     uint32_t *plist = a.point_list + (long long)b * a.cap + start;
-    if (n == 1) { if (tid == 0) plist[0] = (uint32_t)gkeys[0]; return; }
+    // the sorted ids leave together with their sub-block masks: the cull test runs once per entry here (all lanes busy)
+    // instead of once per entry and sub-block warp in the forward AND the backward blend
+    uint8_t *pmask = a.point_mask ? a.point_mask + (long long)b * a.cap + start : nullptr;
+    const float2 *gxy = a.xy + (long long)b * a.P;
+    const float4 *gco = a.conic_opacity + (long long)b * a.P;
+    const int tx0 = (tile % a.gx) * 16, ty0 = (tile / a.gx) * 16;
+    auto emit = [&](int pos, uint32_t id) {
+        plist[pos] = id;
+        if (pmask) pmask[pos] = (uint8_t)sub_block_mask(__ldg(gxy + id), __ldg(gco + id), tx0, ty0);
+    };
+    if (n == 1) { if (tid == 0) emit(0, (uint32_t)gkeys[0]); return; }
 
     // 1. depth range
     uint32_t lo = 0xffffffffu, hi = 0u;
@@ -355,7 +378,7 @@ __global__ void __launch_bounds__(kThreads) k_tile_sort(FwdDev a) {
         if (hi_b == lo_b) {                                              // one bucket alone exceeds a pass: global-memory bitonic
             __syncthreads();
             block_sort(gkeys, n, tid);
-            for (int i = tid; i < n; i += kThreads) plist[i] = (uint32_t)gkeys[i];
+            for (int i = tid; i < n; i += kThreads) emit(i, (uint32_t)gkeys[i]);
             return;
         }
         const uint32_t count = (hi_b == kBuckets ? (uint32_t)n : cnt[hi_b]) - base_lo;
@@ -382,7 +405,7 @@ __global__ void __launch_bounds__(kThreads) k_tile_sort(FwdDev a) {
             __syncthreads();
             if (tid == 0) s_flag = 0;
         }
-        for (int i = tid; i < (int)count; i += kThreads) plist[base_lo + i] = (uint32_t)skeys[i];
+        for (int i = tid; i < (int)count; i += kThreads) emit((int)base_lo + i, (uint32_t)skeys[i]);
         __syncthreads();
         lo_b = hi_b;
     }
@@ -431,11 +454,21 @@ __global__ void __launch_bounds__(kBlendThreads) k_blend(FwdDev a) {
     for (int ch = 0; ch < C; ch++) acc[ch] = 0.f;
     uint32_t last = 0;
 
-    uint32_t id_c = 0; float2 xy_c = make_float2(0.f, 0.f); float4 co_c = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (lane < n) { id_c = plist[lane]; xy_c = __ldg(gxy + id_c); co_c = __ldg(gco + id_c); }
+    const uint8_t *pmask = a.point_mask ? a.point_mask + (long long)b * a.cap + start : nullptr;
+    // software pipeline: ids (+ masks) are fetched two chunks ahead, the records of the entries that reach this sub-block one
+    // chunk ahead, so neither latency sits in front of the blend of the current chunk
+    uint32_t id_c = 0, id_n = 0; bool rel_c = false, rel_n = false;
+    float2 xy_c = make_float2(0.f, 0.f); float4 co_c = make_float4(0.f, 0.f, 0.f, 0.f);
+    auto fetch_id = [&](int idx, uint32_t &id, bool &rel) {
+        rel = false;
+        if (idx < n) { id = plist[idx]; rel = pmask ? ((pmask[idx] >> sub) & 1u) != 0u : true; }
+    };
+    fetch_id(lane, id_c, rel_c);
+    fetch_id(32 + lane, id_n, rel_n);
+    if (rel_c) { xy_c = __ldg(gxy + id_c); co_c = __ldg(gco + id_c); }
     for (int base = 0; base < n; base += 32) {
         if (__all_sync(0xffffffffu, done)) break;
-        const bool rel = (base + lane < n) && entry_reaches_rect(xy_c, co_c, rcx, rcy, 3.5f, 1.5f);
+        const bool rel = rel_c && (pmask != nullptr || entry_reaches_rect(xy_c, co_c, rcx, rcy, 3.5f, 1.5f));
         unsigned mask = __ballot_sync(0xffffffffu, rel);
         if (rel) {
             s_xy[wib][lane] = xy_c;
@@ -447,27 +480,41 @@ __global__ void __launch_bounds__(kBlendThreads) k_blend(FwdDev a) {
                 for (int ch = 0; ch < C; ch++) s_col[wib][lane * C + ch] = __ldg(gcol + (long long)id_c * C + ch);
             }
         }
-        const int nidx = base + 32 + lane;                 // prefetch the next chunk while this one is blended
-        if (nidx < n) { id_c = plist[nidx]; xy_c = __ldg(gxy + id_c); co_c = __ldg(gco + id_c); }
+        id_c = id_n; rel_c = rel_n;                        // advance the pipeline
+        if (rel_c) { xy_c = __ldg(gxy + id_c); co_c = __ldg(gco + id_c); }
+        fetch_id(base + 64 + lane, id_n, rel_n);
         __syncwarp();
+        // The transmittance chain T <- T (1 - alpha) is the only true dependency between entries: alpha of the next kU
+        // survivors is evaluated first (independent shared-memory reads, FMAs and exp's that overlap), then the chain is
+        // walked.  Same operations in the same order per pixel as a one-by-one loop.
+        constexpr int kU = 4;
         while (mask) {
-            const int j = __ffs(mask) - 1;
-            mask &= mask - 1;
-            if (done) continue;
-            const float2 c = s_xy[wib][j];
-            const float4 co = s_co[wib][j];
-            const float dx = c.x - pxf, dy = c.y - pyf;
-            const float power = -0.5f * (co.x * dx * dx + co.z * dy * dy) - co.y * dx * dy;
-            if (power > 0.0f) continue;
-            const float alpha = fminf(0.99f, co.w * __expf(power));
-            if (alpha < 1.0f / 255.0f) continue;
-            const float test_T = T * (1.f - alpha);
-            if (test_T < 0.0001f) { done = true; continue; }
-            const float w = alpha * T;
+            int j[kU];
+            float alpha[kU];
+            bool ok[kU];
 #pragma unroll
-            for (int ch = 0; ch < C; ch++) acc[ch] += s_col[wib][j * C + ch] * w;
-            T = test_T;
-            last = (uint32_t)(base + j + 1);
+            for (int u = 0; u < kU; u++) {
+                const bool have = mask != 0u;
+                j[u] = have ? __ffs(mask) - 1 : 0;
+                mask &= mask - 1;
+                const float2 c = s_xy[wib][j[u]];
+                const float4 co = s_co[wib][j[u]];
+                const float dx = c.x - pxf, dy = c.y - pyf;
+                const float power = -0.5f * (co.x * dx * dx + co.z * dy * dy) - co.y * dx * dy;
+                alpha[u] = fminf(0.99f, co.w * __expf(power));
+                ok[u] = have && power <= 0.0f && alpha[u] >= 1.0f / 255.0f;
+            }
+#pragma unroll
+            for (int u = 0; u < kU; u++) {
+                if (!ok[u] || done) continue;
+                const float test_T = T * (1.f - alpha[u]);
+                if (test_T < 0.0001f) { done = true; continue; }
+                const float w = alpha[u] * T;
+#pragma unroll
+                for (int ch = 0; ch < C; ch++) acc[ch] += s_col[wib][j[u] * C + ch] * w;
+                T = test_T;
+                last = (uint32_t)(base + j[u] + 1);
+            }
         }
         __syncwarp();
     }
@@ -528,6 +575,7 @@ extern "C" int gom_raster_forward(const GomRasterFwdArgs *p, gom_stream_t stream
     a.inst_keys = reinterpret_cast<unsigned long long *>(p->inst_keys); a.point_list = p->point_list;
     a.status = p->status;
     a.worklist = p->worklist;
+    a.point_mask = p->point_mask;
     GOM_REQUIRE(((uintptr_t)p->xy % 8) == 0 && ((uintptr_t)p->conic_opacity % 16) == 0 && ((uintptr_t)p->rect % 16) == 0 &&
                     ((uintptr_t)p->inst_keys % 8) == 0, "state alignment");
 

@@ -64,7 +64,8 @@ class _Rasterize(torch.autograd.Function):
                 rect=e(B, P, 4, dtype=torch.int32), tile_count=e(B, T, dtype=torch.int32),
                 tile_offset=e(B, T + 1, dtype=torch.int32), tile_cursor=e(B, T, dtype=torch.int32),
                 inst_keys=e(B, cap, dtype=torch.int64), point_list=e(B, cap, dtype=torch.int32),
-                status=e(B, dtype=torch.int32), worklist=e(B * T, dtype=torch.int32))
+                status=e(B, dtype=torch.int32), worklist=e(B * T, dtype=torch.int32),
+                point_mask=e(B, cap, dtype=torch.uint8))
             a = GomRasterFwdArgs(
                 n_frames=B, n_gauss=P, height=H, width=W, n_channels=C, interleaved=int(bool(interleaved)),
                 inst_capacity=cap,
@@ -83,7 +84,7 @@ class _Rasterize(torch.autograd.Function):
         ctx.color_grad_channels = int(color_grad_channels or 0)
         ctx.has_means2D = means2D is not None
         ctx.save_for_backward(m3, c3, col, view, proj, tanfov, bg, st["final_T"], st["n_contrib"], st["radii"],
-                              st["xy"], st["conic_opacity"], st["tile_offset"], st["point_list"], st["worklist"])
+                              st["xy"], st["conic_opacity"], st["tile_offset"], st["point_list"], st["worklist"], st["point_mask"])
         if aux is not None:
             aux.update(st)
             aux["inst_capacity"] = cap
@@ -95,7 +96,7 @@ class _Rasterize(torch.autograd.Function):
         L = _lib.lib()
         B, P, H, W, C, interleaved, cap, shared_colors = ctx.dims
         (m3, c3, col, view, proj, tanfov, bg, final_T, n_contrib, radii, xy, conic_opacity, tile_offset,
-         point_list, worklist) = ctx.saved_tensors
+         point_list, worklist, point_mask) = ctx.saved_tensors
         dev = m3.device
         g_color = g_color.contiguous().float()
         e = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
@@ -112,7 +113,7 @@ class _Rasterize(torch.autograd.Function):
             viewmatrix=ptr(view), projmatrix=ptr(proj), tanfov=ptr(tanfov), bg=ptr(bg),
             final_T=ptr(final_T), n_contrib=ptr(n_contrib), radii=ptr(radii), xy=ptr(xy),
             conic_opacity=ptr(conic_opacity), tile_offset=ptr(tile_offset), point_list=ptr(point_list),
-            worklist=ptr(worklist), dL_dout=ptr(g_color), dL_dmeans3D=ptr(d_means3D), dL_dcov3D=ptr(d_cov3D),
+            worklist=ptr(worklist), point_mask=ptr(point_mask), dL_dout=ptr(g_color), dL_dmeans3D=ptr(d_means3D), dL_dcov3D=ptr(d_cov3D),
             dL_dcolors=ptr(d_colors), dL_dcolors_stride=0 if shared_colors else P * C,
             dL_dopacity=ptr(d_op), dL_dmeans2D=ptr(d_mean2D), dL_dconic=ptr(d_conic))
         check(L.gom_raster_backward(ctypes.byref(a), _stream()), "gom_raster_backward")

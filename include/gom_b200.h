@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define GOM_ABI_VERSION 7
+#define GOM_ABI_VERSION 8
 #define GOM_TILE 16              /* 16x16-pixel tiles, as upstream's BLOCK_X/BLOCK_Y */
 #define GOM_MAX_CHANNELS 4
 #define GOM_MAX_JOINTS 64
@@ -114,6 +114,8 @@ typedef struct {
     uint32_t *status;            /* [B]     GOM_STATUS_* bits */
     uint32_t *worklist;          /* [B*T]   out, nullable: (frame * T + tile) of every tile, longest list first — the order the
                                     sort / blend kernels (and the backward, if handed over) walk the tiles in */
+    uint8_t *point_mask;         /* [B,cap] out, nullable: per point_list entry, bit s = the entry can reach the 8x4-pixel sub-block s
+                                    of its tile (conservative alpha >= 1/255 test, done once in the sort instead of per blend warp) */
 } GomRasterFwdArgs;
 int gom_raster_forward(const GomRasterFwdArgs *a, gom_stream_t stream);
 
@@ -141,6 +143,7 @@ typedef struct {
     const uint32_t *tile_offset;
     const uint32_t *point_list;
     const uint32_t *worklist;    /* [B*T] nullable: the forward's tile order (longest list first) */
+    const uint8_t *point_mask;   /* [B,cap] nullable: the forward's sub-block masks */
     /* upstream gradient */
     const float *dL_dout;        /* same layout as out_color */
     /* outputs */

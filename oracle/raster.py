@@ -41,6 +41,8 @@ def lib():
         _lib.gor_blend_backward.argtypes = [c_int, c_int, c_int, c_int] + [c_void_p] * 13
         _lib.gor_preprocess_backward.restype = c_int
         _lib.gor_preprocess_backward.argtypes = [c_int, c_int, c_int] + [c_void_p] * 5 + [c_float, c_float] + [c_void_p] * 4
+        _lib.gor_blend_margins.restype = c_int
+        _lib.gor_blend_margins.argtypes = [c_int, c_int, c_int] + [c_void_p] * 4 + [c_float, c_void_p, c_void_p]
         _lib.gor_num_threads.restype = c_int
     return _lib
 
@@ -92,6 +94,23 @@ def forward(means3D, cov6, colors, opacity, view, proj, tanfovx, tanfovy, bg, H,
                 keys=keys[:n_dup], point_list=plist[:n_dup], ranges=ranges,
                 _in=dict(means3D=means3D, cov6=cov6, colors=colors, opacity=opacity, view=view, proj=proj,
                          tanfovx=float(tanfovx), tanfovy=float(tanfovy), bg=bg, H=H, W=W))
+
+
+def margins(fwd, thr=3e-5):
+    """Decision margins of the forward blend (see gor_blend_margins): (margin [H,W] float32 — smallest relative distance of
+    any alpha >= 1/255 / T < 1e-4 / power > 0 decision of the pixel to its threshold; fragile [P] bool — Gaussians that
+    contribute at a pixel whose margin is below ``thr``).  A CUDA kernel whose exp differs in the last bits may legitimately
+    differ from the oracle exactly there, and nowhere else."""
+    L = lib()
+    i = fwd["_in"]
+    P = i["colors"].shape[0]
+    H, W = i["H"], i["W"]
+    m = np.full((H, W), np.inf, np.float32)
+    fr = np.zeros(P, np.uint8)
+    plist = np.ascontiguousarray(fwd["point_list"]) if fwd["n_dup"] else np.zeros(1, np.uint32)
+    rc = L.gor_blend_margins(P, H, W, _p(plist), _p(fwd["ranges"]), _p(fwd["xy"]), _p(fwd["conic_opacity"]), float(thr), _p(m), _p(fr))
+    assert rc == 0, rc
+    return m, fr.astype(bool)
 
 
 def backward(fwd, dL_dcolor):

@@ -220,6 +220,58 @@ int gor_blend_forward(int H, int W, int C, const uint32_t *point_list, const uin
     return 0;
 }
 
+/* ------------------------------------------------------------------ decision margins of the forward blend */
+/* Test infrastructure for the parity tests (no upstream counterpart).  The blend takes three kinds of discontinuous decisions
+ * per (pixel, Gaussian): power > 0, alpha < 1/255, test_T < 1e-4.  An implementation whose exp() differs from libm's in the
+ * last bits (the CUDA kernels use ex2.approx) takes a DIFFERENT decision only where alpha or test_T sits within a few 1e-6
+ * (relative) of its threshold — and then the pixel legitimately moves by up to alpha * colour, and the gradients of every
+ * Gaussian blended at that pixel move with it.  This function reports, per pixel, the smallest relative distance of any decision
+ * taken for it to its threshold (margin [H,W]; +inf where nothing was decided), and flags every Gaussian that passes the
+ * alpha test at a pixel whose margin is below `thr` (fragile [P]).  The tests then demand that EVERY value outside the
+ * north-star tolerance belongs to such a pixel / Gaussian, instead of allowing a fraction of unexplained outliers. */
+int gor_blend_margins(int P, int H, int W, const uint32_t *point_list, const uint32_t *ranges, const float *xy,
+                      const float *conic_opacity, float thr, float *margin, uint8_t *fragile) {
+    const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
+    (void)P;
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int tile = 0; tile < gx * gy; tile++) {
+        const uint32_t start = ranges[2 * tile], end = ranges[2 * tile + 1];
+        const int tx = tile % gx, ty = tile / gx;
+        for (int ly = 0; ly < TILE; ly++)
+            for (int lx = 0; lx < TILE; lx++) {
+                const int x = tx * TILE + lx, y = ty * TILE + ly;
+                if (x >= W || y >= H) continue;
+                const float pxf = (float)x, pyf = (float)y;
+                float T = 1.0f, m = INFINITY;
+                for (uint32_t k = start; k < end; k++) {
+                    const uint32_t g = point_list[k];
+                    const float dx = xy[2 * g] - pxf, dy = xy[2 * g + 1] - pyf;
+                    const float *co = conic_opacity + 4 * g;
+                    const float power = -0.5f * (co[0] * dx * dx + co[2] * dy * dy) - co[1] * dx * dy;
+                    if (power > 0.0f) { m = fminf(m, fabsf(power)); continue; }
+                    const float alpha = fminf_(0.99f, co[3] * expf(power));
+                    m = fminf(m, fabsf(alpha - 1.0f / 255.0f) * 255.0f);
+                    if (alpha < 1.0f / 255.0f) continue;
+                    const float test_T = T * (1 - alpha);
+                    m = fminf(m, fabsf(test_T - 0.0001f) * 10000.0f);
+                    if (test_T < 0.0001f) break;
+                    T = test_T;
+                }
+                margin[(size_t)y * W + x] = m;
+                if (m < thr)                 /* every Gaussian that can contribute here inherits the pixel's fragility */
+                    for (uint32_t k = start; k < end; k++) {
+                        const uint32_t g = point_list[k];
+                        const float dx = xy[2 * g] - pxf, dy = xy[2 * g + 1] - pyf;
+                        const float *co = conic_opacity + 4 * g;
+                        const float power = -0.5f * (co[0] * dx * dx + co[2] * dy * dy) - co[1] * dx * dy;
+                        if (power > 0.0f) continue;
+                        if (fminf_(0.99f, co[3] * expf(power)) >= 0.5f / 255.0f) fragile[g] = 1;
+                    }
+            }
+    }
+    return 0;
+}
+
 /* ------------------------------------------------------------------ App. A.6 blend backward */
 /* dL_dpix [C,H,W] -> dL_dmean2D [P,2], dL_dconic [P,3] (A,B,C), dL_dopacity [P], dL_dcolors [P,C]. */
 int gor_blend_backward(int P, int H, int W, int C, const uint32_t *point_list, const uint32_t *ranges,

@@ -41,23 +41,56 @@ def test_model_forward_backward_at_baseline_configs(name, n_faces, size, focal, 
     d = {k: t(v).to(DEV) for k, v in fr.items()}
     rgb, mask, out = m(d["K"], d["E"], d["cnl_gtfms"], d["dst_Rs"], d["dst_Ts"], dst_posevec=d["dst_posevec"])
     aux = m.last_raster_aux
-    # oracle chain
+    # ---- (1) geometry: the kernels' Gaussians (the same three public calls Model.forward makes) against the oracle chain.
+    # Continuous functions: tight tolerances, no exceptions.
+    from gomavatar_b200.skinning import apply_lbs, face_gaussians, get_global_RTs
+    with torch.no_grad():
+        Rs, Ts = get_global_RTs(d["cnl_gtfms"], d["dst_Rs"], d["dst_Ts"])
+        vobs_k = apply_lbs(m.vertices[None], Rs, Ts, m.lbs_weights)
+        means_k, cov6_k = face_gaussians(vobs_k, m.faces, m.so3, m.scale, 1e-3)
     ov = t(pr["vertices"]).requires_grad_(True)
     ow, os_ = t(pr["so3"]).requires_grad_(True), t(pr["scale"]).requires_grad_(True)
     vobs_o, xyz, cov = G.pose_geometry(ov, t(scene.faces), t(scene.lbs_weights), ow, os_, t(fr["cnl_gtfms"][0]),
                                        t(fr["dst_Rs"][0]), t(fr["dst_Ts"][0]))
     cov6 = G.pack_cov6(cov)
+    means_k, cov6_k = means_k[0].cpu().numpy(), cov6_k[0].cpu().numpy()
+    assert np.abs(means_k - xyz.detach().numpy()).max() <= 2e-6 * np.abs(xyz.detach().numpy()).max()
+    # the covariance inherits the conditioning of the Steiner angle t0 = atan2(2 f1.f2, f1.f1 - f2.f2) / 2: away from its
+    # singularity (equilateral face: both arguments vanish) fp32 rounding gives ~1e-6; within 1 % of it the angle — and with it
+    # the frame of an anisotropic Gaussian — is decided by the last input bits (in the reference too: SURVEY.md §7)
+    cref = cov6.detach().numpy()
+    vo_ = vobs_o.detach().T
+    tri_ = vo_[t(scene.faces).reshape(-1)].reshape(-1, 3, 3)
+    f1_ = 0.5 * (tri_[:, 2] - tri_.mean(1)); f2_ = (tri_[:, 1] - tri_[:, 0]) / (2 * np.sqrt(3))
+    pp_, qq_ = 2 * (f1_ * f2_).sum(-1), (f1_ * f1_).sum(-1) - (f2_ * f2_).sum(-1)
+    ss_ = (f1_ * f1_).sum(-1) + (f2_ * f2_).sum(-1)
+    # ... or sits on atan2's branch cut (f1.f2 = 0 with |f1| < |f2|), where t0 jumps by pi / 2 and the frame's axes swap
+    ill = (((pp_.abs() < 1e-2 * ss_) & (qq_ < 0)) | (torch.hypot(pp_, qq_) < 1e-2 * ss_)).numpy()
+    assert ill.mean() < 0.03
+    face_err = np.abs(cov6_k - cref).max(1) / np.abs(cref).max(1)
+    assert face_err[~ill].max() <= 5e-3, (name, float(face_err[~ill].max()))              # worst well-conditioned face (slivers: ~1e-3)
+    assert np.median(face_err) <= 1e-5 and np.abs(cov6_k - cref).max() <= 2e-4 * np.abs(cref).max(), (name, float(np.median(face_err)))
+    # ---- (2) rasterizer: Model.forward's image against the oracle rasterizer fed with EXACTLY the Gaussians the kernels
+    # produced.  The sorted tile lists must then be identical, and every pixel beyond the north-star tolerance must be one where
+    # the oracle's own blend came within 3e-5 (relative) of flipping an alpha >= 1/255 / T < 1e-4 decision (the kernels'
+    # ex2.approx differs from libm's expf by ~1e-6 there; oracle.raster.margins).  Nothing is left unexplained.
     st = Cam.raster_settings_from_KE(fr["K"][0], fr["E"][0], (W, H))
     app = pr["appearance"].T
     feat = np.ascontiguousarray(np.concatenate([app, np.ones_like(app[:, :1])], 1), dtype=np.float32)
-    f = R.forward(xyz.detach().numpy(), cov6.detach().numpy(), feat, np.ones(scene.n_faces, np.float32), st.viewmatrix,
+    f = R.forward(means_k, cov6_k, feat, np.ones(scene.n_faces, np.float32), st.viewmatrix,
                   st.projmatrix, st.tanfovx, st.tanfovy, np.zeros(4, np.float32), H, W)
+    T_ = ((W + 15) // 16) * ((H + 15) // 16)
+    assert int(aux["tile_offset"][0, T_].item()) == f["n_dup"]
+    assert np.array_equal(aux["point_list"][0].cpu().numpy().view(np.uint32)[: f["n_dup"]], f["point_list"]), "sorted tile lists"
     ref = f["color"].transpose(1, 2, 0)
     got = torch.cat([rgb[0], mask[0][..., None]], -1).detach().cpu().numpy()
     err = np.abs(got - ref)
     assert ref[..., 3].max() > 0.9 and (ref[..., 3] > 0.5).mean() > 0.02, "the subject must be in view"
-    # the GPU geometry differs from the oracle's in the last bits, so a few borderline alpha/T tests may flip
-    assert (err > 1e-4 * np.abs(ref) + 1e-5).mean() <= 5e-4 and err.max() < 5e-2, (name, float(err.max()))
+    THR = 3e-5
+    margin, fragile = R.margins(f, THR)
+    bad = err > 1e-4 * np.abs(ref) + 1e-5
+    assert not (bad & (margin >= THR)[..., None]).any(), (name, int((bad & (margin >= THR)[..., None]).sum()), float(err.max()))
+    assert err.max() < 1.2e-2 and (margin < THR).mean() < 5e-3, (name, float(err.max()), float((margin < THR).mean()))
     mse = float((err.astype(np.float64)[..., :3] ** 2).mean())
     assert mse == 0 or -10 * np.log10(mse) > 80.0, "render PSNR vs oracle"
     # size-independent properties: alpha = 1 - final_T over the zero background; the lists cover every touched tile
@@ -85,13 +118,17 @@ def test_model_forward_backward_at_baseline_configs(name, n_faces, size, focal, 
     assert bad_face.mean() < 0.03
     bad_vert = np.zeros(scene.n_vertices, bool)
     bad_vert[scene.faces[bad_face].reshape(-1)] = True
+    # a Gaussian blended at a pixel with a borderline decision (see above) carries that pixel's flip in its gradient: those
+    # faces / their vertices may exceed 1e-3 (capped at 2e-2); every other entry must meet the north-star tolerance
+    frag_vert = np.zeros(scene.n_vertices, bool)
+    frag_vert[scene.faces[fragile].reshape(-1)] = True
     scale_v = None
-    for pname, gk, go, keep in (("vertices", m.vertices.grad, ov.grad, ~bad_vert), ("so3", m.so3.grad, ow.grad, ~bad_face),
-                                ("scale", m.scale.grad, os_.grad, ~bad_face),
-                                ("appearance", m.appearance_module.appearance.grad, t(gr["colors"][:, :3].T.copy()), None)):
+    for pname, gk, go, keep, frag in (("vertices", m.vertices.grad, ov.grad, ~bad_vert, frag_vert), ("so3", m.so3.grad, ow.grad, ~bad_face, fragile),
+                                      ("scale", m.scale.grad, os_.grad, ~bad_face, fragile),
+                                      ("appearance", m.appearance_module.appearance.grad, t(gr["colors"][:, :3].T.copy()), None, fragile)):
         gk, go = gk.cpu().numpy(), go.numpy()
         if keep is not None:
-            gk, go = gk[:, keep], go[:, keep]
+            gk, go, frag = gk[:, keep], go[:, keep], frag[keep]
         ref_max = np.abs(go).max()
         if pname == "vertices":
             scale_v = ref_max
@@ -99,4 +136,5 @@ def test_model_forward_backward_at_baseline_configs(name, n_faces, size, focal, 
             assert np.abs(gk).max() <= 1e-6 * scale_v, (name, pname)
             continue
         err = np.abs(gk - go) / ref_max
-        assert (err > 1e-3).mean() <= 1e-4 and err.max() < 2e-2, (name, pname, float(err.max()), float((err > 1e-3).mean()))
+        unexplained = (err > 1e-3) & ~frag[None, :]
+        assert not unexplained.any() and err.max() < 2e-2, (name, pname, int(unexplained.sum()), float(err.max()))

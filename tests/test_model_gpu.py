@@ -107,6 +107,44 @@ def test_gradients_match_oracle_chain(golden_dir):
         assert rel < 1e-3, (name, rel)
 
 
+def test_rigid_pose_gradients_match_oracle_chain(golden_dir):
+    """d(loss)/d(global_R, global_T) — the only reason those arguments exist: the reference's test-time pose fit optimises
+    exactly them (models/model.py:218-221, train_pose.py:247-254, RodriguesModule utils/network_util.py:66-92) — through
+    Rodrigues -> rigid transform -> face frame -> covariance -> splat, against the oracle chain (float32 torch restatement
+    + the C rasterizer's explicit backward).  Also d/d(vertices) on the same path, which now runs through the rotation."""
+    g = np.load(os.path.join(golden_dir, "golden_model.npz"))
+    m, sc = _model_from_golden(g)
+    b = 0
+    H = W = 64
+    rng = np.random.default_rng(9)
+    dL_rgb = rng.normal(size=(1, H, W, 3)).astype(np.float32)
+    dL_mask = rng.normal(size=(1, H, W)).astype(np.float32)
+    s = slice(b, b + 1)
+    c = lambda k: t(g[k][s]).to(DEV)
+    for gR0, gT0 in ((g["global_R"], g["global_T"]), (np.zeros(3, np.float32), np.zeros(3, np.float32))):   # theta -> sqrt(1e-5): the eps branch
+        m.zero_grad(set_to_none=True)
+        gR, gT = t(gR0.copy()).to(DEV).requires_grad_(True), t(gT0.copy()).to(DEV).requires_grad_(True)
+        rgbs, masks, _ = m(c("K"), c("E"), c("cnl_gtfms"), c("dst_Rs"), c("dst_Ts"), i_iter=0, global_R=gR, global_T=gT)
+        ((rgbs * t(dL_rgb).to(DEV)).sum() + (masks * t(dL_mask).to(DEV)).sum()).backward()
+        ov = t(sc.vertices.T.copy()).requires_grad_(True)
+        oR, oT = t(gR0.copy()).requires_grad_(True), t(gT0.copy()).requires_grad_(True)
+        _, xyz, cov = G.pose_geometry(ov, t(sc.faces), t(sc.lbs_weights), t(g["so3"]), t(g["scale"]), t(g["cnl_gtfms"][b]),
+                                      t(g["dst_Rs"][b]), t(g["dst_Ts"][b]), global_R=oR, global_T=oT)
+        cov6 = G.pack_cov6(cov)
+        st = Cam.raster_settings_from_KE(g["K"][b], g["E"][b], (W, H))
+        app = g["appearance"].T
+        feat = np.concatenate([app, np.ones_like(app[:, :1])], 1)
+        fwd = R.forward(xyz.detach().numpy(), cov6.detach().numpy(), feat, np.ones(len(app), np.float32), st.viewmatrix,
+                        st.projmatrix, st.tanfovx, st.tanfovy, np.zeros(4, np.float32), H, W)
+        gr = R.backward(fwd, np.concatenate([dL_rgb[0].transpose(2, 0, 1), dL_mask], 0))
+        ((xyz * t(gr["means3D"])).sum() + (cov6 * t(gr["cov6"])).sum()).backward()
+        assert float(oR.grad.abs().max()) > 0 and float(oT.grad.abs().max()) > 0
+        for name, got, ref in (("global_R", gR.grad, oR.grad), ("global_T", gT.grad, oT.grad), ("vertices", m.vertices.grad, ov.grad)):
+            got, ref = got.cpu().numpy(), ref.numpy()
+            rel = np.abs(got - ref).max() / np.abs(ref).max()
+            assert rel < 1e-3, (name, rel)
+
+
 def test_state_dict_keys_match_reference_checkpoint_layout(golden_dir):
     g = np.load(os.path.join(golden_dir, "golden_model.npz"))
     m, _ = _model_from_golden(g)

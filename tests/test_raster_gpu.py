@@ -26,12 +26,24 @@ def _oracle(d, b, C=None):
                      float(d["tanfov"][b, 0]), float(d["tanfov"][b, 1]), d["bg"][b, :C], d["H"], d["W"])
 
 
-def _assert_image_close(got, ref, what):
+MARGIN_THR = 3e-5      # relative distance of an alpha >= 1/255 / T < 1e-4 decision to its threshold below which ex2.approx
+                       # (the kernels' exp, relative error ~1e-6 at power = -5.5, accumulated over the T product) may flip it
+
+
+def _assert_image_close(got, ref, what, margin=None):
+    """North-star tolerance (1e-4 relative, +1e-5 absolute) on EVERY pixel whose blend took no borderline decision; a pixel
+    where the oracle itself was within MARGIN_THR of flipping an alpha / T test (oracle.raster.margins) may differ by what
+    one flipped Gaussian contributes: alpha T colour <= 0.99 * 1e-4 / 0.01 = 1e-2 at the T stop, <= 1/255 at the alpha test."""
     err = np.abs(got - ref)
-    ok = err <= 1e-4 * np.abs(ref) + 1e-5
-    frac_bad = 1.0 - ok.mean()
-    assert frac_bad <= 2e-4, f"{what}: {frac_bad:.2e} of values beyond 1e-4 tolerance"
-    assert err.max() < 2e-2, f"{what}: max abs err {err.max()}"
+    bad = err > 1e-4 * np.abs(ref) + 1e-5
+    if margin is None:
+        assert not bad.any(), f"{what}: {bad.mean():.2e} of values beyond 1e-4 tolerance (max {err.max():.2e})"
+        return
+    fragile = np.broadcast_to(margin < MARGIN_THR, bad.shape)
+    assert not (bad & ~fragile).any(), (f"{what}: {int((bad & ~fragile).sum())} values beyond 1e-4 tolerance at pixels without a "
+                                        f"borderline decision (max {err[bad & ~fragile].max():.2e})")
+    assert err.max() < 1.2e-2, f"{what}: max abs err {err.max()}"
+    assert fragile.mean() < 5e-3, f"{what}: {fragile.mean():.2e} of the pixels are borderline — threshold too generous"
 
 
 def _u32(x):
@@ -66,14 +78,15 @@ def _check_forward(d, interleaved=False, capacity=None, strict=True):
         assert np.array_equal(ranges, o["ranges"]), "tile ranges"
         assert np.array_equal(_u32(aux["point_list"][b])[:o["n_dup"]], o["point_list"]), "sorted (tile, depth, id) list"
         assert int(aux["status"][b]) == 0
-        # ---- image
+        # ---- image: every difference is attributed to a borderline decision of the oracle's own blend
+        margin, _ = R.margins(o, MARGIN_THR)
         img = color[b].cpu().numpy()
         if interleaved:
             img = img.transpose(2, 0, 1)
-        _assert_image_close(img, o["color"], f"color frame {b}")
-        _assert_image_close(final_T[b].cpu().numpy(), o["final_T"], f"final_T frame {b}")
+        _assert_image_close(img, o["color"], f"color frame {b}", margin)
+        _assert_image_close(final_T[b].cpu().numpy(), o["final_T"], f"final_T frame {b}", margin)
         nc = n_contrib[b].cpu().numpy().view(np.uint32)
-        assert (nc != o["n_contrib"]).mean() <= 2e-4, "n_contrib"
+        assert not ((nc != o["n_contrib"]) & (margin >= MARGIN_THR)).any(), "n_contrib differs at a pixel without a borderline decision"
     return aux
 
 
@@ -207,7 +220,7 @@ def test_reference_api_shim_matches_two_pass_reference_usage():
     pred = torch.cat(preds, 0)[:4].permute(1, 2, 0)
     dd = dict(d); dd["bg"] = np.zeros_like(d["bg"])
     o = _oracle(dd, 0)
-    _assert_image_close(pred.detach().cpu().numpy().transpose(2, 0, 1), o["color"], "two-pass shim")
+    _assert_image_close(pred.detach().cpu().numpy().transpose(2, 0, 1), o["color"], "two-pass shim", R.margins(o, MARGIN_THR)[0])
     assert radii.dtype == torch.int32 and np.array_equal(radii.cpu().numpy(), o["radii"])
     pred.sum().backward()
     assert means2D.grad is not None and means2D.grad.shape == xyz.shape and float(means2D.grad[:, 2].abs().max()) == 0

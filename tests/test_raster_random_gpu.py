@@ -57,9 +57,15 @@ def test_random_gaussians_forward_backward(seed, P, size, C, orange):
     T = ((W + 15) // 16) * ((H + 15) // 16)
     assert int(aux["tile_offset"][0, T]) == o["n_dup"]
     assert np.array_equal(aux["point_list"][0].cpu().numpy().view(np.uint32)[: o["n_dup"]], o["point_list"])
+    # every difference beyond the north-star tolerance sits at a pixel where the oracle's own blend took a borderline alpha / T
+    # decision (oracle.raster.margins), and every gradient beyond it belongs to a Gaussian blended at such a pixel
+    thr = 3e-5
+    margin, fragile = R.margins(o, thr)
     err = np.abs(color[0].detach().cpu().numpy() - o["color"])
-    assert (err > 1e-4 * np.abs(o["color"]) + 1e-5).mean() <= 5e-4 and err.max() < 2e-2, float(err.max())
-    assert (n_contrib[0].cpu().numpy().view(np.uint32) != o["n_contrib"]).mean() <= 1e-3
+    bad = err > 1e-4 * np.abs(o["color"]) + 1e-5
+    assert not (bad & (margin >= thr)[None]).any() and err.max() < 1.2e-2, (int((bad & (margin >= thr)[None]).sum()), float(err.max()))
+    assert not ((n_contrib[0].cpu().numpy().view(np.uint32) != o["n_contrib"]) & (margin >= thr)).any()
+    assert (margin < thr).mean() < 2e-2
     rng = np.random.default_rng(seed + 100)
     dL = rng.normal(size=(1, C, H, W)).astype(np.float32)
     (color * t(dL)).sum().backward()
@@ -69,5 +75,6 @@ def test_random_gaussians_forward_backward(seed, P, size, C, orange):
         got = got.cpu().numpy()
         scale = np.abs(ref).max()
         e = np.abs(got - ref) / scale
-        # a flipped alpha >= 1/255 or T < 1e-4 test (exp rounding) moves the few Gaussians of that pixel; everything else is tight
-        assert (e > 1e-3).mean() <= 2e-3 and e.max() < 5e-2, (name, float(e.max()), float((e > 1e-3).mean()))
+        # a flipped alpha >= 1/255 or T < 1e-4 test (exp rounding) moves the Gaussians blended at that pixel; everything else is tight
+        off = (e > 1e-3).reshape(len(ref), -1).any(1)
+        assert not (off & ~fragile).any() and e.max() < 5e-2, (name, int((off & ~fragile).sum()), float(e.max()))
