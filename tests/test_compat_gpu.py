@@ -60,3 +60,26 @@ def test_skimage_stand_in_is_the_metric_kernel(shims):
     m = eval_metrics(torch.from_numpy(pred).float().to(dev), torch.from_numpy(gt).float().to(dev), quantize=False)
     assert abs(got - float(m["ssim"][0])) < 1e-12                 # same kernel; fp64 atomics make the last bit order-dependent
     assert abs(got - float(OL.ssim(pred, gt))) < 1e-9
+
+
+def test_unchanged_reference_train_and_eval_run_on_the_gpu(tmp_path):
+    """SURVEY.md §8 f-4, end to end: the reference's own train.main (20 iterations incl. a mesh subdivision, the periodic
+    evaluate(), checkpoints), ``--resume`` and eval.main, all byte-unchanged, on ``gomavatar_b200.compat``
+    (tests/host_harness/compat_train_gpu_run.py).  Needs a reference checkout next to the GPU: /root/reference, or a copy in the
+    git-ignored ``_ref_scratch/`` of the snapshot (the tree is never committed); skipped otherwise.  Log of the run this was
+    developed with: profiles/r5_compat_unchanged_train_eval_gpu.log."""
+    import json
+    import subprocess
+    ref = next((p for p in ("/root/reference", os.path.join(ROOT, "_ref_scratch")) if os.path.exists(os.path.join(p, "train.py"))), None)
+    if ref is None:
+        pytest.skip("no reference checkout on this machine")
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "host_harness", "compat_train_gpu_run.py"), ref, str(tmp_path)],
+                         capture_output=True, text=True, timeout=900)
+    lines = [ln for ln in res.stdout.splitlines() if ln.startswith("RESULT ")]
+    assert res.returncode == 0 and lines, res.stdout[-3000:] + res.stderr[-3000:]
+    out = json.loads(lines[-1][7:])
+    assert out["model_module"] == "gomavatar_b200.model"
+    assert out["checkpoints"] == ["iter_0.pt", "iter_10.pt", "iter_20.pt"] and "iter_20.pt" in out["checkpoints_after_resume"]
+    assert out["ckpt_faces_after_subdivision"] == 4 * 4000 and out["ckpt_optimizer_groups"] >= 5
+    assert any("evaluate on test" in ln for ln in out["log_lines"]) and any("subdivide at iter 8" in ln for ln in out["log_lines"])
+    assert "view" in out["eval_dir"]
