@@ -13,7 +13,7 @@ from ctypes import c_int, c_int32, c_int64, c_size_t, c_void_p, c_float, c_char_
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libgom_b200.so")
 
-ABI_VERSION = 8
+ABI_VERSION = 9
 STATUS_OVERFLOW = 1
 STATUS_TIMEOUT = 2
 
@@ -133,13 +133,14 @@ class GomConvFirstArgs(ctypes.Structure):
 
 
 class GomConvPackArgs(ctypes.Structure):
-    _fields_ = [("c_out", c_int32), ("c_in", c_int32), ("transpose", c_int32), ("split", c_int32), ("weight", c_void_p),
-                ("packed", c_void_p)]
+    _fields_ = [("c_out", c_int32), ("c_in", c_int32), ("transpose", c_int32), ("split", c_int32), ("kernel_size", c_int32),
+                ("_pad", c_int32), ("weight", c_void_p), ("packed", c_void_p)]
 
 
 class GomConv3x3Args(ctypes.Structure):
     _fields_ = [("n_images", c_int32), ("height", c_int32), ("width", c_int32), ("c_in", c_int32), ("c_out", c_int32),
-                ("relu", c_int32), ("precision", c_int32), ("tma_round", c_int32), ("x", c_void_p), ("x_lo", c_void_p),
+                ("relu", c_int32), ("precision", c_int32), ("tma_round", c_int32), ("kernel_size", c_int32), ("_pad", c_int32),
+                ("x", c_void_p), ("x_lo", c_void_p),
                 ("w_packed", c_void_p), ("bias", c_void_p), ("mask_in", c_void_p), ("mask_out", c_void_p), ("out", c_void_p),
                 ("status", c_void_p)]
 

@@ -19,14 +19,16 @@ def _need_cuda(t, what):
 
 
 def pack_weights(weight, transpose=False, split=False):
-    """torch weight [K,C,3,3] -> the kernel's packed image: [9,K,C] (forward) or [9,C,K] with flipped taps (dgrad),
-    TF32-rounded; ``split`` appends the low parts (3xTF32)."""
+    """torch weight [K,C,3,3] (or [K,C]: a Linear layer) -> the kernel's packed image: [taps,K,C] (forward) or [taps,C,K]
+    with flipped taps (dgrad), TF32-rounded; ``split`` appends the low parts (3xTF32)."""
     _need_cuda(weight, "pack_weights")
     K, C = weight.shape[:2]
+    ks = 1 if weight.dim() == 2 else int(weight.shape[2])
+    taps = ks * ks
     w = weight.detach().float().contiguous()
-    packed = torch.empty((18 if split else 9), (C if transpose else K), (K if transpose else C), dtype=torch.float32,
+    packed = torch.empty((2 * taps if split else taps), (C if transpose else K), (K if transpose else C), dtype=torch.float32,
                          device=weight.device)
-    call("gom_conv3x3_pack_weights", GomConvPackArgs(c_out=K, c_in=C, transpose=int(transpose), split=int(split),
+    call("gom_conv3x3_pack_weights", GomConvPackArgs(c_out=K, c_in=C, transpose=int(transpose), split=int(split), kernel_size=ks,
                                                      weight=ptr(w), packed=ptr(packed)))
     return packed
 
@@ -40,7 +42,7 @@ def tf32_low_part(x):
 
 
 def conv3x3(x, w_packed, bias=None, relu=False, mask_in=None, mask_out=None, precision="tf32", tma_round=True, out=None,
-            status=None):
+            status=None, kernel_size=3):
     """x: contiguous [N,H,W,C_in]; w_packed from ``pack_weights``; returns [N,H,W,C_out] = conv (+ bias) (ReLU) (masked).
 
     ``mask_out`` (int32 [N,H,W,C_out/32]) receives the ReLU bit mask of the result; ``mask_in`` (same shape) zeroes the
@@ -53,7 +55,7 @@ def conv3x3(x, w_packed, bias=None, relu=False, mask_in=None, mask_out=None, pre
     if w_packed.shape[2] != C:
         raise _lib.GomError(f"conv3x3: packed weight expects {w_packed.shape[2]} input channels, x has {C}")
     strict = precision in ("fp32", "3xtf32")
-    if strict and w_packed.shape[0] != 18:
+    if strict and w_packed.shape[0] != 2 * kernel_size * kernel_size:
         raise _lib.GomError("conv3x3: 3xTF32 needs a weight packed with split=True")
     if out is None:
         out = torch.empty(N, H, W, c_out, dtype=torch.float32, device=x.device)
@@ -62,7 +64,7 @@ def conv3x3(x, w_packed, bias=None, relu=False, mask_in=None, mask_out=None, pre
         if mk is not None and (tuple(mk.shape) != (N, H, W, c_out // 32) or mk.dtype != torch.int32 or not mk.is_contiguous()):
             raise _lib.GomError("conv3x3: masks must be contiguous int32 [N,H,W,C_out/32]")
     call("gom_conv3x3", GomConv3x3Args(n_images=N, height=H, width=W, c_in=C, c_out=c_out, relu=int(relu), precision=int(strict),
-                                       tma_round=int(tma_round and not strict), x=ptr(x), x_lo=ptr(x_lo), w_packed=ptr(w_packed),
+                                       tma_round=int(tma_round and not strict), kernel_size=kernel_size, x=ptr(x), x_lo=ptr(x_lo), w_packed=ptr(w_packed),
                                        bias=ptr(bias), mask_in=ptr(mask_in), mask_out=ptr(mask_out), out=ptr(out), status=ptr(status)))
     return out
 
@@ -70,3 +72,20 @@ def conv3x3(x, w_packed, bias=None, relu=False, mask_in=None, mask_out=None, pre
 def new_mask(n, h, w, c, device):
     """storage for the ReLU bit mask of an [n,h,w,c] activation"""
     return torch.empty(n, h, w, c // 32, dtype=torch.int32, device=device)
+
+
+def linear(x, w_packed, bias=None, relu=False, mask_in=None, mask_out=None, precision="fp32", out=None):
+    """Linear layer over rows on the tensor cores: x [R, C_in] (R a multiple of 16, C_in a multiple of 32, contiguous) ->
+    [R, C_out] = x W^T (+ bias) (ReLU) (masked), C_out a multiple of 64; ``w_packed = pack_weights(W [C_out, C_in], ...)``.
+    The rows are handed to the convolution kernel as a 16-pixel-wide one-tap "image" (kernel_size 1).  Masks: int32
+    [R, C_out / 32] as in ``conv3x3``."""
+    R, C = x.shape
+    if R % 16 or C % 32:
+        raise _lib.GomError("linear: rows must be a multiple of 16 and input features a multiple of 32 (pad with zeros)")
+    c_out = w_packed.shape[1]
+    v4 = lambda t, c: None if t is None else t.view(1, R // 16, 16, c)
+    if out is None:
+        out = torch.empty(R, c_out, dtype=torch.float32, device=x.device)
+    conv3x3(x.view(1, R // 16, 16, C), w_packed, bias=bias, relu=relu, mask_in=v4(mask_in, c_out // 32), mask_out=v4(mask_out, c_out // 32),
+            precision=precision, out=out.view(1, R // 16, 16, c_out), kernel_size=1)
+    return out

@@ -34,19 +34,23 @@ namespace {
 using namespace gomtc;
 
 constexpr int kTileH = 16;                         // CTA tile: 16 rows x (8 SUB) columns of output pixels
-constexpr int kHaloH = kTileH + 2;
 constexpr int kEpiWarpBytes = 4096;                // store staging of one epilogue warp: 32 pixels x 32 channels
 
 // NT: output channels per tile; SUB: M = 128 sub-tiles per tile (1 or 2); TPS: taps per weight stage (1 or 3 — a stage must
 // hold enough MMA work, >= ~500 cycles, to cover the issuing warp's per-stage barrier round trip); BST: weight ring depth
-template <int NT, int SUB, int TPS, int BST> struct ConvCfg {
+// TAPS: 9 = 3x3 convolution (halo + shifted views); 1 = 1x1 convolution = plain GEMM over pixel rows (the MLP layers): no halo,
+// and the activation tile travels in the same stage ring as its weight tile (one barrier pair per k-block).
+template <int NT, int SUB, int TPS, int BST, int TAPS = 9> struct ConvCfg {
     static constexpr int TILE_W = 8 * SUB;
-    static constexpr int PITCH = TILE_W + 2;        // halo pitch in pixels: exactly the columns a tile needs (see gom_conv3x3)
-    static constexpr int A_BYTES = ((kHaloH * PITCH * 128 + 1023) / 1024) * 1024;
-    static constexpr int A_BUFS = 2;
+    static constexpr int HALO = TAPS == 9 ? 2 : 0;
+    static constexpr int PITCH = TILE_W + HALO;     // halo pitch in pixels: exactly the columns a tile needs (see gom_conv3x3)
+    static constexpr int HALO_H = kTileH + HALO;
+    static constexpr int A_TX_BYTES = HALO_H * PITCH * 128;
+    static constexpr int A_BYTES = ((A_TX_BYTES + 1023) / 1024) * 1024;
+    static constexpr int A_BUFS = TAPS == 9 ? 2 : BST;
     static constexpr int B_TAP_BYTES = NT * 128;
     static constexpr int B_BYTES = TPS * B_TAP_BYTES;
-    static constexpr int GROUPS = 9 / TPS;           // weight stages per halo
+    static constexpr int GROUPS = TAPS / TPS;        // weight stages per halo
     static constexpr int HALO_AT = TPS == 1 ? 5 : 1; // the next halo is requested before this weight stage of the current one
     static constexpr int EPI_WARPS = 4 * SUB;
     static constexpr int THREADS = 64 + 32 * EPI_WARPS;
@@ -56,6 +60,7 @@ template <int NT, int SUB, int TPS, int BST> struct ConvCfg {
     static_assert(2 * ACC_COLS <= 512, "two accumulator stages must fit tensor memory");
     static_assert(SMEM <= 232448, "shared memory budget");
     static_assert(TPS == 1 || TPS == 3, "taps per stage");
+    static_assert(TAPS == 9 || (TAPS == 1 && TPS == 1), "kernel size");
 };
 
 struct ConvDev {
@@ -122,11 +127,11 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvDev &p, int tile, int
     return t;
 }
 
-template <int NT, int SUB, int TPS, int BST>
-__global__ void __launch_bounds__(ConvCfg<NT, SUB, TPS, BST>::THREADS, 1)
+template <int NT, int SUB, int TPS, int BST, int TAPS>
+__global__ void __launch_bounds__(ConvCfg<NT, SUB, TPS, BST, TAPS>::THREADS, 1)
 k_conv3x3(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_a_lo,
           const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_out, const ConvDev p) {
-    using Cfg = ConvCfg<NT, SUB, TPS, BST>;
+    using Cfg = ConvCfg<NT, SUB, TPS, BST, TAPS>;
     constexpr int PITCH = Cfg::PITCH;
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint64_t afull_bar[Cfg::A_BUFS], aempty_bar[Cfg::A_BUFS], bfull_bar[BST], bempty_bar[BST], tfull_bar[2], tempty_bar[2];
@@ -167,6 +172,27 @@ k_conv3x3(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
         }
         uint32_t bst = 0, bph = 0, a_count = 0;
         bool ok = true;
+        if constexpr (TAPS == 1) {
+            // plain GEMM: k-block i = activation tile + weight tile in stage i % BST, one full / empty barrier pair
+            bool ready = mbar_test_wait(&bempty_bar[0], 1u);
+            for (int tile = blockIdx.x; tile < p.n_tiles && ok; tile += gridDim.x) {
+                const TileCoord t = decode_tile(p, tile, NT, Cfg::TILE_W);
+                for (int item = 0; item < items_per_tile; item++) {
+                    const int pass = item / p.c_blocks, cb = item - pass * p.c_blocks;
+                    if (!ready && !mbar_wait(&bempty_bar[bst], bph ^ 1u, ab)) { ok = false; break; }
+                    const uint32_t a_dst = smem_base + bst * Cfg::A_BYTES, b_dst = b_base + bst * Cfg::B_BYTES;
+                    uint64_t *fb = &bfull_bar[bst];
+                    if (++bst == BST) { bst = 0; bph ^= 1u; }
+                    ready = mbar_test_wait(&bempty_bar[bst], bph ^ 1u);
+                    if (elect_one()) {
+                        mbar_expect_tx(fb, Cfg::A_TX_BYTES + Cfg::B_BYTES);
+                        tma_load_4d(a_dst, pass == 1 ? &map_a_lo : &map_a, cb * 32, t.w0, t.h0, t.img, fb);
+                        tma_load_3d(b_dst, &map_b, cb * 32, t.n0, pass == 2 ? 1 : 0, fb);
+                    }
+                    __syncwarp();
+                }
+            }
+        } else {
         // iterator over halo items (tile, pass, channel block), one ahead of the weight stream
         int a_tile = blockIdx.x, a_item = 0;
         auto issue_halo = [&]() -> bool {
@@ -176,7 +202,7 @@ k_conv3x3(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
             const uint32_t buf = a_count & 1u, ph = (a_count >> 1) & 1u;
             if (!mbar_wait(&aempty_bar[buf], ph ^ 1u, ab)) return false;
             if (elect_one()) {
-                mbar_expect_tx(&afull_bar[buf], kHaloH * PITCH * 128);
+                mbar_expect_tx(&afull_bar[buf], Cfg::A_TX_BYTES);
                 tma_load_4d(smem_base + buf * Cfg::A_BYTES, pass == 1 ? &map_a_lo : &map_a, cb * 32, t.w0 - 1, t.h0 - 1, t.img, &afull_bar[buf]);
             }
             __syncwarp();
@@ -206,6 +232,7 @@ k_conv3x3(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
                 }
             }
         }
+        }
     } else if (warp == 1) {
         // --------------------------------------------------------------------------------------------- MMA issuer
         const uint32_t idesc = instr_desc_n(NT);
@@ -220,8 +247,8 @@ k_conv3x3(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
             if (!mbar_wait(&tempty_bar[acc], aph ^ 1u, ab)) { ok = false; break; }
             const uint32_t d0 = tmem + acc * Cfg::ACC_COLS;
             for (int item = 0; item < items_per_tile && ok; item++, a_count++) {
-                const uint32_t abuf = a_count & 1u;
-                if (!mbar_wait(&afull_bar[abuf], (a_count >> 1) & 1u, ab)) { ok = false; break; }
+                const uint32_t abuf = TAPS == 1 ? bst : (a_count & 1u);              // GEMM: the activation tile shares the weight stage
+                if (TAPS == 9 && !mbar_wait(&afull_bar[abuf], (a_count >> 1) & 1u, ab)) { ok = false; break; }
                 const uint32_t a_buf_lo = a_desc0 + abuf * (Cfg::A_BYTES >> 4);
 #pragma unroll
                 for (int grp = 0; grp < Cfg::GROUPS; grp++) {
@@ -235,7 +262,7 @@ k_conv3x3(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
                         constexpr uint32_t a_hi = desc_hi(PITCH * 128, 0);
 #pragma unroll
                         for (int ti = 0; ti < TPS; ti++) {
-                            const int tap = grp * TPS + ti, r = tap / 3, s = tap % 3;
+                            const int tap = grp * TPS + ti, r = TAPS == 9 ? tap / 3 : 0, s = TAPS == 9 ? tap % 3 : 0;
 #pragma unroll
                             for (int m = 0; m < SUB; m++)
 #pragma unroll
@@ -248,7 +275,7 @@ k_conv3x3(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
                         }
                         tc_commit(eb);
                         if (grp == Cfg::GROUPS - 1) {
-                            tc_commit(&aempty_bar[abuf]);
+                            if (TAPS == 9) tc_commit(&aempty_bar[abuf]);
                             if (item == items_per_tile - 1) tc_commit(&tfull_bar[acc]);
                         }
                     }
@@ -342,15 +369,16 @@ k_conv3x3(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
 // ------------------------------------------------------------------------------------------------------ helpers
 __global__ void k_pack_weights(GomConvPackArgs a) {
     const int K = a.c_out, C = a.c_in;
-    const long long total = 9ll * K * C;
+    const int taps = a.kernel_size == 1 ? 1 : 9;
+    const long long total = (long long)taps * K * C;
     for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
         float w;
         if (!a.transpose) {          // packed[tap][k][c] = W[k][c][tap]
             const int c = (int)(e % C), k = (int)((e / C) % K), tap = (int)(e / ((long long)C * K));
-            w = a.weight[((long long)k * C + c) * 9 + tap];
+            w = a.weight[((long long)k * C + c) * taps + tap];
         } else {                     // packed[tap][c][k] = W[k][c][8 - tap]
             const int k = (int)(e % K), c = (int)((e / K) % C), tap = (int)(e / ((long long)C * K));
-            w = a.weight[((long long)k * C + c) * 9 + (8 - tap)];
+            w = a.weight[((long long)k * C + c) * taps + (taps - 1 - tap)];
         }
         uint32_t hi, lo;
         split_tf32(w, hi, lo);
@@ -421,13 +449,13 @@ int make_weight_map(CUtensorMap *m, const float *base, int taps, int c_out, int 
     return GOM_OK;
 }
 
-template <int NT, int SUB, int TPS, int BST>
+template <int NT, int SUB, int TPS, int BST, int TAPS = 9>
 int launch_conv(const GomConv3x3Args *p, ConvDev &d, cudaStream_t stream) {
-    using Cfg = ConvCfg<NT, SUB, TPS, BST>;
+    using Cfg = ConvCfg<NT, SUB, TPS, BST, TAPS>;
     constexpr int PITCH = Cfg::PITCH;
     static bool configured = false;
     if (!configured) {
-        GOM_CUDA(cudaFuncSetAttribute(k_conv3x3<NT, SUB, TPS, BST>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+        GOM_CUDA(cudaFuncSetAttribute(k_conv3x3<NT, SUB, TPS, BST, TAPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
         configured = true;
     }
     d.tiles_w = gom_div_up(p->width, Cfg::TILE_W);
@@ -438,12 +466,12 @@ int launch_conv(const GomConv3x3Args *p, ConvDev &d, cudaStream_t stream) {
     d.n_tiles = (int)n_tiles;
     CUtensorMap ma, malo, mb, mo;
     const bool round = p->tma_round && p->precision == 0;
-    if (int rc = make_act_map(&ma, p->x, p->n_images, p->height, p->width, p->c_in, PITCH, kHaloH, round)) return rc;
-    if (int rc = make_act_map(&malo, p->precision == 1 ? p->x_lo : p->x, p->n_images, p->height, p->width, p->c_in, PITCH, kHaloH, false)) return rc;
-    if (int rc = make_weight_map(&mb, p->w_packed, p->precision == 1 ? 18 : 9, p->c_out, p->c_in, NT, TPS)) return rc;
+    if (int rc = make_act_map(&ma, p->x, p->n_images, p->height, p->width, p->c_in, PITCH, Cfg::HALO_H, round)) return rc;
+    if (int rc = make_act_map(&malo, p->precision == 1 ? p->x_lo : p->x, p->n_images, p->height, p->width, p->c_in, PITCH, Cfg::HALO_H, false)) return rc;
+    if (int rc = make_weight_map(&mb, p->w_packed, (p->precision == 1 ? 2 : 1) * TAPS, p->c_out, p->c_in, NT, TPS)) return rc;
     if (int rc = make_act_map(&mo, p->out, p->n_images, p->height, p->width, p->c_out, 8, 4, false)) return rc;
     const int grid = d.n_tiles < g_sms ? d.n_tiles : g_sms;
-    k_conv3x3<NT, SUB, TPS, BST><<<grid, Cfg::THREADS, Cfg::SMEM, stream>>>(ma, malo, mb, mo, d);
+    k_conv3x3<NT, SUB, TPS, BST, TAPS><<<grid, Cfg::THREADS, Cfg::SMEM, stream>>>(ma, malo, mb, mo, d);
     GOM_LAUNCH_CHECK();
     return GOM_OK;
 }
@@ -454,7 +482,8 @@ extern "C" int gom_conv3x3_pack_weights(const GomConvPackArgs *p, gom_stream_t s
     GOM_REQUIRE(p != nullptr, "args");
     GOM_REQUIRE(p->c_out > 0 && p->c_in > 0, "sizes");
     GOM_REQUIRE(p->weight && p->packed, "null pointer");
-    const long long total = 9ll * p->c_out * p->c_in;
+    GOM_REQUIRE(p->kernel_size == 3 || p->kernel_size == 1, "kernel_size must be 3 or 1");
+    const long long total = (p->kernel_size == 1 ? 1ll : 9ll) * p->c_out * p->c_in;
     int blocks = gom_div_up(total, 256);
     if (blocks > 2048) blocks = 2048;
     k_pack_weights<<<blocks, 256, 0, (cudaStream_t)stream>>>(*p);
@@ -480,6 +509,8 @@ extern "C" int gom_conv3x3(const GomConv3x3Args *p, gom_stream_t stream_) {
     GOM_REQUIRE(p->c_in > 0 && p->c_in % 32 == 0 && p->c_out > 0 && p->c_out % 32 == 0, "channel counts must be multiples of 32");
     GOM_REQUIRE(p->x && p->w_packed && p->out, "null pointer");
     GOM_REQUIRE(p->precision == 0 || (p->precision == 1 && p->x_lo), "precision = 1 needs x_lo");
+    GOM_REQUIRE(p->kernel_size == 3 || p->kernel_size == 1, "kernel_size must be 3 or 1");
+    GOM_REQUIRE(p->kernel_size == 3 || p->c_out % 64 == 0, "1x1: c_out must be a multiple of 64");
     GOM_REQUIRE(((uintptr_t)p->x % 16) == 0 && ((uintptr_t)p->out % 16) == 0 && ((uintptr_t)p->w_packed % 16) == 0 &&
                 ((uintptr_t)p->x_lo % 16) == 0 && ((uintptr_t)p->bias % 16) == 0, "16-byte alignment");
     if (int rc = conv_setup()) return rc;
@@ -496,6 +527,13 @@ extern "C" int gom_conv3x3(const GomConv3x3Args *p, gom_stream_t stream_) {
     d.mask_out = p->mask_out;
     d.status = p->status;
 
+    if (p->kernel_size == 1) {                  // plain GEMM over pixel rows (the MLP layers): no halo, no tile-shape search
+        gom_prof_begin(GOM_PROF_GEMM_TC, stream);
+        const int rc1 = p->c_out % 128 == 0 ? launch_conv<128, 2, 1, 4, 1>(p, d, stream) : launch_conv<64, 2, 1, 4, 1>(p, d, stream);
+        if (rc1) return rc1;
+        gom_prof_end(GOM_PROF_GEMM_TC, stream);
+        return GOM_OK;
+    }
     const int slot = p->relu ? GOM_PROF_CONV3X3_FWD : GOM_PROF_CONV3X3_DGRAD;
     gom_prof_begin(slot, stream);
     int rc;

@@ -29,6 +29,9 @@ def _get(cfg, key, default=None):
     return getattr(cfg, key, default)
 
 
+_TC_MLP = True          # False: plain torch (cuBLAS fp32) everywhere — the A/B reference of tests/test_modules_gpu.py
+
+
 def _init_linear(m, gain):
     nn.init.xavier_uniform_(m.weight, gain)
     nn.init.zeros_(m.bias)
@@ -91,7 +94,116 @@ def _linear(m, h):
     return m(h)
 
 
+def _pad_cols(t, mult):
+    """[R, C] -> contiguous [R16, Cm]: rows padded to a multiple of 16, columns to a multiple of ``mult``, with zeros"""
+    R, C = t.shape
+    R16, Cm = (R + 15) // 16 * 16, (C + mult - 1) // mult * mult
+    if R16 == R and Cm == C and t.is_contiguous():
+        return t
+    out = t.new_zeros(R16, Cm)
+    out[:R, :C] = t
+    return out
+
+
+class _TcMlpStack(torch.autograd.Function):
+    """The hidden Linear + ReLU layers of an MLP (reference models/modules/non_rigid_module.py:75-147: width 128, depth 6,
+    the encoding re-read by the layer in ``skips``) on the tcgen05 kernel of csrc/conv3x3_tc.cu (kernel_size 1: a GEMM over
+    rows, bias + ReLU fused, the ReLU bit mask written by the forward and consumed by the dgrad of the layer above) with 3xTF32
+    products = fp32-GEMM accuracy, what ``nn.Linear`` computes in the reference (torch never enables TF32 for matmul by
+    default).  Weight gradients are reductions over the ~1e5 rows and stay split-K batched GEMMs (see ``_Linear``).
+
+    forward(x0 [R, in0], enc [R, E], cat_layers, *weights_and_biases) -> last hidden activation [R, width]."""
+
+    @staticmethod
+    def forward(ctx, x0, enc, cat_layers, *params):
+        from . import conv as C
+        R = x0.shape[0]
+        ws, bs = params[0::2], params[1::2]
+        h = _pad_cols(x0.detach().float(), 32)
+        encd = enc.detach().float()
+        saved_in, masks = [], []
+        for i, (w, b) in enumerate(zip(ws, bs)):
+            if i in cat_layers:
+                h = _pad_cols(torch.cat([h[:R, :ws[i - 1].shape[0]], encd], dim=1), 32)
+            wp = w.detach().new_zeros(w.shape[0], h.shape[1])
+            wp[:, :w.shape[1]] = w.detach()
+            mask = C.new_mask(1, h.shape[0] // 16, 16, w.shape[0], h.device).view(h.shape[0], -1)
+            y = C.linear(h, C.pack_weights(wp, split=True), bias=b.detach().clone(), relu=True, mask_out=mask, precision="fp32")     # clone: 16-byte aligned (arena views are not)
+            saved_in.append(h)
+            masks.append(mask)
+            h = y
+        ctx.cat_layers, ctx.R, ctx.n = tuple(cat_layers), R, len(ws)
+        ctx.dims = (x0.shape[1], enc.shape[1])
+        ctx.save_for_backward(*saved_in, *masks, *ws)
+        ctx.last = h
+        return h[:R]
+
+    @staticmethod
+    def backward(ctx, g):
+        from . import conv as C
+        from ._lib import GomReluBwdArgs, call, ptr
+        n, R = ctx.n, ctx.R
+        t = ctx.saved_tensors
+        saved_in, masks, ws = t[:n], t[n:2 * n], t[2 * n:]
+        in0, E = ctx.dims
+        R16 = saved_in[0].shape[0]
+        gp = g.new_zeros(R16, g.shape[1])
+        gp[:R] = g
+        call("gom_relu_backward", GomReluBwdArgs(n=gp.numel(), act=ptr(ctx.last), grad=ptr(gp)))      # ReLU of the last hidden layer
+        g_enc = None
+        grads = [None] * (2 * n)
+        ones = torch.ones(1, R16, dtype=gp.dtype, device=gp.device)
+        for i in reversed(range(n)):
+            w, hin = ws[i], saved_in[i]
+            # weight / bias gradients: reductions over the rows (split-K batched GEMM, GEMV with ones)
+            S = 64
+            while S > 1 and R16 % S:
+                S //= 2
+            if S >= 8 and R16 // S >= 512:
+                gw = torch.bmm(gp.view(S, R16 // S, -1).transpose(1, 2), hin.view(S, R16 // S, -1)).sum(0)
+            else:
+                gw = gp.t() @ hin
+            grads[2 * i] = gw[:, :w.shape[1]]
+            grads[2 * i + 1] = (ones @ gp)[0]
+            if i == 0 and not (ctx.needs_input_grad[0] or ctx.needs_input_grad[1]):
+                break
+            # input gradient with the ReLU backward of the layer below fused (bit mask; the re-read encoding columns and the
+            # first layer's input have no ReLU: all-ones mask words)
+            wp = w.new_zeros(w.shape[0], hin.shape[1])
+            wp[:, :w.shape[1]] = w
+            c_out = hin.shape[1]
+            mask_in = None
+            if i > 0:
+                mask_in = torch.full((R16, c_out // 32), -1, dtype=torch.int32, device=gp.device)
+                mask_in[:, :masks[i - 1].shape[1]] = masks[i - 1]
+            if c_out % 64:                               # the kernel writes 64-column tiles: pad the transposed weight's rows
+                wp = torch.cat([wp, wp.new_zeros(wp.shape[0], 64 - c_out % 64)], dim=1)
+                if mask_in is not None:
+                    mask_in = torch.cat([mask_in, mask_in.new_full((R16, 1), -1)], dim=1).contiguous()
+            g_in = C.linear(gp, C.pack_weights(wp, transpose=True, split=True), mask_in=mask_in, precision="fp32")
+            if i in ctx.cat_layers:
+                wprev = ws[i - 1].shape[0]
+                g_enc = g_in[:R, wprev:wprev + E] if g_enc is None else g_enc + g_in[:R, wprev:wprev + E]
+                gp = g_in[:, :wprev].contiguous()
+            elif i > 0:
+                gp = g_in if g_in.shape[1] == ws[i - 1].shape[0] else g_in[:, :ws[i - 1].shape[0]].contiguous()
+            else:
+                gp = g_in
+        g_x0 = gp[:R, :in0] if ctx.needs_input_grad[0] else None
+        ctx.last = None
+        return (g_x0, g_enc if ctx.needs_input_grad[1] else None, None) + tuple(grads)
+
+
 def _run(mods, cat_at, h, enc):
+    # hidden stack on the tensor cores when it is tall enough to matter and shaped like the reference's (width % 64 == 0)
+    lin = [m for m in mods if isinstance(m, nn.Linear)]
+    if (h.is_cuda and h.dim() >= 2 and h.numel() // h.shape[-1] >= 4096 and len(lin) >= 2
+            and all(m.out_features % 64 == 0 for m in lin[:-1]) and _TC_MLP):
+        lead = h.shape[:-1]
+        cat_layers = tuple(sorted(i // 2 for i in cat_at))            # module index -> Linear index
+        params = [p for m in lin[:-1] for p in (m.weight, m.bias)]
+        hid = _TcMlpStack.apply(h.reshape(-1, h.shape[-1]), enc.reshape(-1, enc.shape[-1]), cat_layers, *params)
+        return _linear(lin[-1], hid).reshape(*lead, lin[-1].out_features)
     for i, m in enumerate(mods):
         if i in cat_at:
             h = torch.cat([h, enc], dim=-1)

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define GOM_ABI_VERSION 8
+#define GOM_ABI_VERSION 9
 #define GOM_TILE 16              /* 16x16-pixel tiles, as upstream's BLOCK_X/BLOCK_Y */
 #define GOM_MAX_CHANNELS 4
 #define GOM_MAX_JOINTS 64
@@ -371,8 +371,10 @@ typedef struct {
     int32_t c_out, c_in;         /* K, C of the torch weight [K,C,3,3] */
     int32_t transpose;           /* 0: forward pack [9][K][C];  1: dgrad pack [9][C][K] with the taps flipped */
     int32_t split;               /* 0: one TF32-rounded image; 1: two images [hi | lo] for precision = 1 */
-    const float *weight;         /* [K,C,3,3] contiguous */
-    float *packed;               /* 9*K*C floats (x2 when split) */
+    int32_t kernel_size;         /* 3: weight [K,C,3,3], nine taps;  1: weight [K,C] (a Linear layer), one tap */
+    int32_t _pad;
+    const float *weight;         /* [K,C,ks,ks] contiguous */
+    float *packed;               /* ks*ks*K*C floats (x2 when split) */
 } GomConvPackArgs;
 int gom_conv3x3_pack_weights(const GomConvPackArgs *a, gom_stream_t stream);
 
@@ -383,6 +385,11 @@ typedef struct {
     int32_t precision;           /* 0: TF32;  1: 3xTF32 (needs x_lo and a split weight pack) */
     int32_t tma_round;           /* 1: the TMA engine rounds x to TF32 (round-to-nearest) on its way to shared memory;
                                     0: the tensor core truncates the fp32 words it reads */
+    int32_t kernel_size;         /* 3 (the convolution described above) or 1: out[p, n] = sum_c x[p, c] w_packed[0][n][c], a plain
+                                    GEMM over pixel rows with the same epilogues — the Linear layers of the reference's MLPs
+                                    (models/modules/non_rigid_module.py:75-147) with rows laid out as an [N,H,W] "image";
+                                    c_out must then be a multiple of 64 */
+    int32_t _pad;
     const float *x;              /* [N,H,W,c_in] */
     const float *x_lo;           /* precision = 1: x - trunc_tf32(x), same shape (gom_tf32_split); else NULL */
     const float *w_packed;       /* from gom_conv3x3_pack_weights */
