@@ -119,11 +119,13 @@ class ClockSampler:
 NCU_TRAFFIC_BYTES = {      # profiles/r2_ncu_full_summary.md (8 frames, 512x512): mean over the kernel's launches in one step,
     # like `achieved` (tap_bwd 5 launches 3199.5 MB, tap_fwd 5 launches 2494.3 MB,
     # conv_first_bwd = k_conv1_gemm<1> 1357.2 MB + k_conv1_stencil 323.4 MB)
-    "lpips_tap_bwd": 639.9e6, "lpips_tap_fwd": 498.9e6, "conv_first_fwd": 1064.6e6, "conv_first_bwd": 1680.6e6}
+    "lpips_tap_bwd": 639.9e6, "lpips_tap_fwd": 498.9e6, "conv_first_fwd": 1064.6e6, "conv_first_bwd": 1680.6e6,
+    # profiles/r5_ncu_full_summary.md: sum over the 12 forward (6 014 MB) / 12 dgrad (2 910 MB) launches of one step, per launch
+    "conv3x3_fwd": 501.2e6, "conv3x3_dgrad": 242.5e6}
 # smsp__inst_executed.sum per launch (warp instructions) of the rasterizer's list kernels at the DEFAULT workload (8 frames,
 # 30 000 Gaussians, 512x512, seeds of this file), from the committed ncu capture; None = not captured for this build.
-NCU_WARP_INSTS = {}
-NCU_WARP_INSTS_SOURCE = None
+NCU_WARP_INSTS = {"blend_fwd": 5.768e7, "blend_bwd": 1.053e8, "tile_sort": 2.507e7}
+NCU_WARP_INSTS_SOURCE = "profiles/r5_ncu_full_summary.md (smsp__inst_executed.sum of k_blend<4>, k_blend_bwd<4,3,0>, k_tile_sort)"
 
 _VGG_LEVELS = ((64, 2), (128, 2), (256, 3), (512, 3), (512, 3))      # (channels, convolutions) per VGG16 block
 
@@ -542,7 +544,7 @@ def run_b200(args):
         k = kernels[dom]
         if dom in alg_flops_per_frame:
             roofline = {"kernel": dom, "bound": "tensor", "achieved": k["tflops"], "peak": tpeak, "unit": "TFLOP/s",
-                        "frac": k["tflops"] / tpeak, "traffic": None, "peak_source": tpeak_src, "ms_per_launch": k["ms_per_launch"],
+                        "frac": k["tflops"] / tpeak, "traffic": NCU_TRAFFIC_BYTES.get(dom), "peak_source": tpeak_src, "ms_per_launch": k["ms_per_launch"],
                         "alg_flops_per_launch": k["alg_flops_per_launch"], "launches_per_step": k["launches_per_step"],
                         "note": "TF32 tcgen05 implicit-GEMM convolutions (12 VGG layers per step, mean over the launches); "
                                 "achieved = 2 * MACs / CUDA-event time"}
