@@ -47,7 +47,9 @@ template <int NT, int SUB, int TPS, int BST, int TAPS = 9> struct ConvCfg {
     static constexpr int HALO_H = kTileH + HALO;
     static constexpr int A_TX_BYTES = HALO_H * PITCH * 128;
     static constexpr int A_BYTES = ((A_TX_BYTES + 1023) / 1024) * 1024;
-    static constexpr int A_BUFS = TAPS == 9 ? 2 : BST;
+    // halo ring: a halo must be requested a full L2 round trip (~2 500 cycles) before its first MMA; one halo of the smallest
+    // shape (NT 64, one sub-tile) is only ~1 700 cycles of MMA work, so that shape keeps three halos in flight
+    static constexpr int A_BUFS = TAPS == 1 ? BST : (SUB == 1 && NT <= 64) ? 4 : 2;
     static constexpr int B_TAP_BYTES = NT * 128;
     static constexpr int B_BYTES = TPS * B_TAP_BYTES;
     static constexpr int GROUPS = TAPS / TPS;        // weight stages per halo
@@ -66,7 +68,9 @@ template <int NT, int SUB, int TPS, int BST, int TAPS = 9> struct ConvCfg {
 struct ConvDev {
     int n_tiles, n_tiles_n, tiles_w, tiles_h;
     int H, W;
-    int c_blocks;                // c_in / 32
+    int k_splits;                // > 1: the channel blocks of a tile are shared out over k_splits CTAs whose partial sums meet in
+                                 // global memory (TMA reduce-add into a zeroed output; bias / ReLU / masks in k_conv_finish)
+    int c_blocks;                // channel blocks (of 32) PER SPLIT
     int n_pass;                  // 1 (TF32) or 3 (3xTF32: x*w_hi, x_lo*w_hi, x*w_lo)
     int relu;
     int mask_words;              // c_out / 32: mask words per pixel
@@ -86,6 +90,10 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map
 }
 __device__ __forceinline__ void tma_store_4d(const CUtensorMap *map, uint32_t src, int c0, int c1, int c2, int c3) {
     asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                 ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_4d(const CUtensorMap *map, uint32_t src, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.reduce.async.bulk.tensor.4d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
                  ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
@@ -114,9 +122,11 @@ __host__ __device__ constexpr uint32_t desc_hi(uint32_t sbo_bytes, uint32_t base
     return (sbo_bytes >> 4) | (1u << 14) | (base_offset << 17) | (2u << 29);
 }
 
-struct TileCoord { int n0, w0, h0, img; };
+struct TileCoord { int n0, w0, h0, img, cb0; };
 __device__ __forceinline__ TileCoord decode_tile(const ConvDev &p, int tile, int nt, int tile_w) {
     TileCoord t;
+    t.cb0 = (tile % p.k_splits) * p.c_blocks;                 // splits of one tile are neighbours: they run at the same time
+    tile /= p.k_splits;
     const int ni = tile % p.n_tiles_n;
     int m = tile / p.n_tiles_n;
     t.n0 = ni * nt;
@@ -186,8 +196,8 @@ k_conv3x3(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
                     ready = mbar_test_wait(&bempty_bar[bst], bph ^ 1u);
                     if (elect_one()) {
                         mbar_expect_tx(fb, Cfg::A_TX_BYTES + Cfg::B_BYTES);
-                        tma_load_4d(a_dst, pass == 1 ? &map_a_lo : &map_a, cb * 32, t.w0, t.h0, t.img, fb);
-                        tma_load_3d(b_dst, &map_b, cb * 32, t.n0, pass == 2 ? 1 : 0, fb);
+                        tma_load_4d(a_dst, pass == 1 ? &map_a_lo : &map_a, (t.cb0 + cb) * 32, t.w0, t.h0, t.img, fb);
+                        tma_load_3d(b_dst, &map_b, (t.cb0 + cb) * 32, t.n0, pass == 2 ? 1 : 0, fb);
                     }
                     __syncwarp();
                 }
@@ -199,18 +209,18 @@ k_conv3x3(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
             if (a_tile >= p.n_tiles) return true;
             const TileCoord t = decode_tile(p, a_tile, NT, Cfg::TILE_W);
             const int pass = a_item / p.c_blocks, cb = a_item - pass * p.c_blocks;
-            const uint32_t buf = a_count & 1u, ph = (a_count >> 1) & 1u;
+            const uint32_t buf = a_count % Cfg::A_BUFS, ph = (a_count / Cfg::A_BUFS) & 1u;
             if (!mbar_wait(&aempty_bar[buf], ph ^ 1u, ab)) return false;
             if (elect_one()) {
                 mbar_expect_tx(&afull_bar[buf], Cfg::A_TX_BYTES);
-                tma_load_4d(smem_base + buf * Cfg::A_BYTES, pass == 1 ? &map_a_lo : &map_a, cb * 32, t.w0 - 1, t.h0 - 1, t.img, &afull_bar[buf]);
+                tma_load_4d(smem_base + buf * Cfg::A_BYTES, pass == 1 ? &map_a_lo : &map_a, (t.cb0 + cb) * 32, t.w0 - 1, t.h0 - 1, t.img, &afull_bar[buf]);
             }
             __syncwarp();
             a_count++;
             if (++a_item == items_per_tile) { a_item = 0; a_tile += gridDim.x; }
             return true;
         };
-        ok = issue_halo();
+        for (int i = 0; i < Cfg::A_BUFS - 1 && ok; i++) ok = issue_halo();       // halos run A_BUFS - 1 items ahead of the weights
         bool ready = mbar_test_wait(&bempty_bar[0], 1u);
         for (int tile = blockIdx.x; tile < p.n_tiles && ok; tile += gridDim.x) {
             const TileCoord t = decode_tile(p, tile, NT, Cfg::TILE_W);
@@ -226,7 +236,7 @@ k_conv3x3(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
                     ready = mbar_test_wait(&bempty_bar[bst], bph ^ 1u);
                     if (elect_one()) {
                         mbar_expect_tx(fb, Cfg::B_BYTES);
-                        tma_load_3d(dst, &map_b, cb * 32, t.n0, tap_off + grp * TPS, fb);       // TPS taps in one box
+                        tma_load_3d(dst, &map_b, (t.cb0 + cb) * 32, t.n0, tap_off + grp * TPS, fb);       // TPS taps in one box
                     }
                     __syncwarp();
                 }
@@ -247,8 +257,8 @@ k_conv3x3(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
             if (!mbar_wait(&tempty_bar[acc], aph ^ 1u, ab)) { ok = false; break; }
             const uint32_t d0 = tmem + acc * Cfg::ACC_COLS;
             for (int item = 0; item < items_per_tile && ok; item++, a_count++) {
-                const uint32_t abuf = TAPS == 1 ? bst : (a_count & 1u);              // GEMM: the activation tile shares the weight stage
-                if (TAPS == 9 && !mbar_wait(&afull_bar[abuf], (a_count >> 1) & 1u, ab)) { ok = false; break; }
+                const uint32_t abuf = TAPS == 1 ? bst : (a_count % Cfg::A_BUFS);      // GEMM: the activation tile shares the weight stage
+                if (TAPS == 9 && !mbar_wait(&afull_bar[abuf], (a_count / Cfg::A_BUFS) & 1u, ab)) { ok = false; break; }
                 const uint32_t a_buf_lo = a_desc0 + abuf * (Cfg::A_BYTES >> 4);
 #pragma unroll
                 for (int grp = 0; grp < Cfg::GROUPS; grp++) {
@@ -308,7 +318,7 @@ k_conv3x3(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
                 uint32_t v[32];
                 tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + acc * Cfg::ACC_COLS + m * NT + ch * 32, v);
                 uint32_t mword = 0xFFFFFFFFu;
-                if (p.mask_in && inside) mword = __ldg(p.mask_in + mask_idx + ch);
+                if (p.mask_in && inside && p.k_splits == 1) mword = __ldg(p.mask_in + mask_idx + ch);
                 tmem_wait_ld();
                 if (ch == kChunks - 1) {                          // accumulator drained: hand it back before the stores
                     tc_fence_before();
@@ -318,7 +328,8 @@ k_conv3x3(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
                 float f[32];
 #pragma unroll
                 for (int j = 0; j < 32; j++) f[j] = __uint_as_float(v[j]);
-                if (p.bias) {
+                const bool partial = p.k_splits > 1;                  // a K-split's partial sum: epilogue math happens in k_conv_finish
+                if (p.bias && !partial) {
                     const float4 *bp = reinterpret_cast<const float4 *>(p.bias + t.n0 + ch * 32);
 #pragma unroll
                     for (int j = 0; j < 8; j++) {
@@ -326,15 +337,15 @@ k_conv3x3(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
                         f[4 * j] += b.x; f[4 * j + 1] += b.y; f[4 * j + 2] += b.z; f[4 * j + 3] += b.w;
                     }
                 }
-                if (p.relu) {
+                if (p.relu && !partial) {
 #pragma unroll
                     for (int j = 0; j < 32; j++) f[j] = fmaxf(f[j], 0.f);
                 }
-                if (p.mask_in) {
+                if (p.mask_in && !partial) {
 #pragma unroll
                     for (int j = 0; j < 32; j++) f[j] = (mword >> j) & 1u ? f[j] : 0.f;
                 }
-                if (p.mask_out) {
+                if (p.mask_out && !partial) {
                     uint32_t w = 0;
 #pragma unroll
                     for (int j = 0; j < 32; j++) w |= (f[j] > 0.f ? 1u : 0u) << j;
@@ -350,12 +361,14 @@ k_conv3x3(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
                 fence_async_smem();
                 __syncwarp();
                 if (lane == 0) {
-                    tma_store_4d(&map_out, sbuf, t.n0 + ch * 32, ww, hw, t.img);
+                    if (partial) tma_reduce_add_4d(&map_out, sbuf, t.n0 + ch * 32, ww, hw, t.img);
+                    else tma_store_4d(&map_out, sbuf, t.n0 + ch * 32, ww, hw, t.img);
                     bulk_commit();
                 }
             }
         }
-        if (lane == 0) bulk_wait_all();
+        // the staging buffer must outlive the store's READ of it; the writes themselves are complete (and visible) at kernel end
+        if (lane == 0) bulk_wait_read<0>();
     }
 
     tc_fence_before();
@@ -385,6 +398,28 @@ __global__ void k_pack_weights(GomConvPackArgs a) {
         a.packed[e] = __uint_as_float(hi);
         if (a.split) a.packed[total + e] = __uint_as_float(lo);
     }
+}
+
+// After a K-split convolution: out <- act(out + bias), ReLU bit mask written / applied.  One thread per pixel and 32 channels.
+struct FinishDev { long long n_words; int words_per_pixel, relu; float *out; const float *bias; const uint32_t *mask_in; uint32_t *mask_out; };
+__global__ void __launch_bounds__(256) k_conv_finish(FinishDev a) {
+    const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (i >= a.n_words) return;
+    const int wi = (int)(i % a.words_per_pixel);
+    float4 *o = reinterpret_cast<float4 *>(a.out + i * 32);
+    const uint32_t mw = a.mask_in ? __ldg(a.mask_in + i) : 0xFFFFFFFFu;
+    uint32_t w = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        float4 v = o[j];
+        if (a.bias) { const float4 b = __ldg(reinterpret_cast<const float4 *>(a.bias + wi * 32) + j); v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w; }
+        if (a.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+        v.x = (mw >> (4 * j)) & 1u ? v.x : 0.f; v.y = (mw >> (4 * j + 1)) & 1u ? v.y : 0.f;
+        v.z = (mw >> (4 * j + 2)) & 1u ? v.z : 0.f; v.w = (mw >> (4 * j + 3)) & 1u ? v.w : 0.f;
+        w |= (v.x > 0.f ? 1u : 0u) << (4 * j) | (v.y > 0.f ? 1u : 0u) << (4 * j + 1) | (v.z > 0.f ? 1u : 0u) << (4 * j + 2) | (v.w > 0.f ? 1u : 0u) << (4 * j + 3);
+        o[j] = v;
+    }
+    if (a.mask_out) a.mask_out[i] = w;
 }
 
 // lo = x - trunc_tf32(x): the part of x the tensor core drops when it reads the fp32 word x as a TF32 operand
@@ -461,7 +496,7 @@ int launch_conv(const GomConv3x3Args *p, ConvDev &d, cudaStream_t stream) {
     d.tiles_w = gom_div_up(p->width, Cfg::TILE_W);
     d.tiles_h = gom_div_up(p->height, kTileH);
     d.n_tiles_n = p->c_out / NT;
-    const long long n_tiles = (long long)p->n_images * d.tiles_h * d.tiles_w * d.n_tiles_n;
+    const long long n_tiles = (long long)p->n_images * d.tiles_h * d.tiles_w * d.n_tiles_n * d.k_splits;
     GOM_REQUIRE(n_tiles < (1ll << 30), "too many tiles");
     d.n_tiles = (int)n_tiles;
     CUtensorMap ma, malo, mb, mo;
@@ -471,8 +506,15 @@ int launch_conv(const GomConv3x3Args *p, ConvDev &d, cudaStream_t stream) {
     if (int rc = make_weight_map(&mb, p->w_packed, (p->precision == 1 ? 2 : 1) * TAPS, p->c_out, p->c_in, NT, TPS)) return rc;
     if (int rc = make_act_map(&mo, p->out, p->n_images, p->height, p->width, p->c_out, 8, 4, false)) return rc;
     const int grid = d.n_tiles < g_sms ? d.n_tiles : g_sms;
+    const size_t out_elems = (size_t)p->n_images * p->height * p->width * p->c_out;
+    if (d.k_splits > 1) GOM_CUDA(cudaMemsetAsync(p->out, 0, out_elems * sizeof(float), stream));
     k_conv3x3<NT, SUB, TPS, BST, TAPS><<<grid, Cfg::THREADS, Cfg::SMEM, stream>>>(ma, malo, mb, mo, d);
     GOM_LAUNCH_CHECK();
+    if (d.k_splits > 1) {
+        FinishDev f{(long long)(out_elems / 32), p->c_out / 32, p->relu, p->out, p->bias, p->mask_in, p->mask_out};
+        k_conv_finish<<<gom_div_up(f.n_words, 256), 256, 0, stream>>>(f);
+        GOM_LAUNCH_CHECK();
+    }
     return GOM_OK;
 }
 
@@ -519,6 +561,7 @@ extern "C" int gom_conv3x3(const GomConv3x3Args *p, gom_stream_t stream_) {
     ConvDev d{};
     d.H = p->height; d.W = p->width;
     d.c_blocks = p->c_in / 32;
+    d.k_splits = 1;
     d.n_pass = p->precision == 1 ? 3 : 1;
     d.relu = p->relu;
     d.mask_words = p->c_out / 32;
@@ -545,28 +588,46 @@ extern "C" int gom_conv3x3(const GomConv3x3Args *p, gom_stream_t stream_) {
     // Tile shape: the largest one that still gives the 148 SMs about two waves of tiles; cost model = waves x MMA cycles of one
     // tile (128 x NT x 8 TF32 MMA: NT / 2 cycles, but at least 48 — below NT = 128 the operand reads from shared memory bind;
     // a single sub-tile does not share its weight tile, measured ~25 % slower per MMA).
-    struct Shape { int nt, sub; };
-    const Shape shapes[4] = {{128, 2}, {128, 1}, {64, 2}, {64, 1}};
-    Shape best = {p->c_out % 128 == 0 ? 128 : p->c_out % 64 == 0 ? 64 : 32, 2};
+    // A layer with too few tiles even of the smallest shape (the 32 x 32 and 64 x 64 layers at one frame per step) additionally
+    // splits the channel blocks of a tile over KS CTAs (partial sums meet in global memory through TMA reduce-add stores; a
+    // small finishing kernel applies bias / ReLU / masks): KS x more tiles of 1 / KS the length.
+    struct Shape { int nt, sub, ks; };
+    const int total_cb = p->c_in / 32;
+    Shape best = {p->c_out % 128 == 0 ? 128 : p->c_out % 64 == 0 ? 64 : 32, 2, 1};
     if (best.nt >= 64) {
         double best_cost = 1e30;
-        for (const Shape &sh : shapes) {
-            if (p->c_out % sh.nt) continue;
-            const long long tiles = (long long)p->n_images * gom_div_up(p->height, kTileH) * gom_div_up(p->width, 8 * sh.sub) * (p->c_out / sh.nt);
-            const long long waves = (tiles + g_sms - 1) / g_sms;
-            const double mma = (sh.nt >= 128 ? 64.0 : 48.0) * (sh.sub == 1 ? 1.2 : 1.0);
-            const double cost = (double)waves * ((double)d.c_blocks * 9 * sh.sub * 4 * mma + 4000.0);
-            if (cost < best_cost * 0.97) { best_cost = cost; best = sh; }     // prefer the earlier (larger) shape on near ties
+        for (int nt = 128; nt >= 64; nt /= 2)
+            for (int sub = 2; sub >= 1; sub--)
+                for (int ks = 1; ks <= 8; ks *= 2) {
+                    if (p->c_out % nt || total_cb % ks || total_cb / ks < 2) continue;
+                    const long long tiles = (long long)p->n_images * gom_div_up(p->height, kTileH) * gom_div_up(p->width, 8 * sub) * (p->c_out / nt) * ks;
+                    const long long waves = (tiles + g_sms - 1) / g_sms;
+                    // measured on B200 (tools/conv_overhead.py, tools/conv_shape_sweep.py): a 128 x NT x 8 TF32 MMA takes NT / 2
+                    // cycles (64 at NT = 128; 48, not 32, at NT = 64: operand reads from shared memory bind), ~20 % more in the
+                    // stream of a real tile (barrier round trips), another ~25 % when a single sub-tile does not share its weight
+                    // tile; a launch costs ~7.5 us (14 000 cycles) before / after its MMAs, a K-split ~10 us more (memset,
+                    // finishing pass, two launches) plus three passes over the output
+                    const double mma = (nt >= 128 ? 64.0 : 48.0) * 1.2 * (sub == 1 ? 1.25 : 1.0);
+                    const double out_bytes = (double)p->n_images * p->height * p->width * p->c_out * 4.0;
+                    const double finish = ks > 1 ? 19000.0 + 3.0 * out_bytes / 3000.0 : 0.0;
+                    const double cost = (double)waves * ((double)(total_cb / ks) * 9 * sub * 4 * mma) + 14000.0 + finish;
+                    if (cost < best_cost * 0.97) { best_cost = cost; best = {nt, sub, ks}; }   // prefer the earlier (larger, unsplit) shape on near ties
+                }
+    }
+    if (const char *force = getenv("GOM_CONV_SHAPE")) {            // tests: "NT,SUB[,KS]" pins the tile shape (ignored if it does not divide)
+        int nt = 0, sub = 0, ks = 1;
+        const int got = sscanf(force, "%d,%d,%d", &nt, &sub, &ks);
+        if (got >= 2 && (nt == 64 || nt == 128) && (sub == 1 || sub == 2) && p->c_out % nt == 0) {
+            if (got < 3 || ks < 1 || total_cb % ks) ks = 1;
+            best = {nt, sub, ks};
         }
     }
-    if (const char *force = getenv("GOM_CONV_SHAPE")) {            // tests: "NT,SUB" pins the tile shape (ignored if it does not divide c_out)
-        int nt = 0, sub = 0;
-        if (sscanf(force, "%d,%d", &nt, &sub) == 2 && (nt == 64 || nt == 128) && (sub == 1 || sub == 2) && p->c_out % nt == 0) best = {nt, sub};
-    }
+    d.k_splits = best.ks;
+    d.c_blocks = total_cb / best.ks;
     if (best.nt == 128 && best.sub == 2) rc = launch_conv<128, 2, 1, 5>(p, d, stream);
     else if (best.nt == 128) rc = launch_conv<128, 1, 3, 3>(p, d, stream);
     else if (best.nt == 64 && best.sub == 2) rc = launch_conv<64, 2, 3, 4>(p, d, stream);
-    else if (best.nt == 64) rc = launch_conv<64, 1, 3, 5>(p, d, stream);
+    else if (best.nt == 64) rc = launch_conv<64, 1, 3, 4>(p, d, stream);
     else rc = launch_conv<32, 2, 3, 6>(p, d, stream);
     if (rc) return rc;
     gom_prof_end(slot, stream);
