@@ -147,8 +147,11 @@ class _TcMlpStack(torch.autograd.Function):
         saved_in, masks, ws = t[:n], t[n:2 * n], t[2 * n:]
         in0, E = ctx.dims
         R16 = saved_in[0].shape[0]
-        gp = g.new_zeros(R16, g.shape[1])
-        gp[:R] = g
+        if R16 == R:
+            gp = g.contiguous().clone()                   # masked in place below
+        else:
+            gp = g.new_zeros(R16, g.shape[1])
+            gp[:R] = g
         call("gom_relu_backward", GomReluBwdArgs(n=gp.numel(), act=ptr(ctx.last), grad=ptr(gp)))      # ReLU of the last hidden layer
         g_enc = None
         grads = [None] * (2 * n)
@@ -173,7 +176,9 @@ class _TcMlpStack(torch.autograd.Function):
             wp[:, :w.shape[1]] = w
             c_out = hin.shape[1]
             mask_in = None
-            if i > 0:
+            if i > 0 and masks[i - 1].shape[1] == c_out // 32:
+                mask_in = masks[i - 1]                    # the whole input is the previous layer's activation
+            elif i > 0:
                 mask_in = torch.full((R16, c_out // 32), -1, dtype=torch.int32, device=gp.device)
                 mask_in[:, :masks[i - 1].shape[1]] = masks[i - 1]
             if c_out % 64:                               # the kernel writes 64-column tiles: pad the transposed weight's rows
