@@ -13,7 +13,7 @@ from ctypes import c_int, c_int32, c_int64, c_size_t, c_void_p, c_float, c_char_
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libgom_b200.so")
 
-ABI_VERSION = 9
+ABI_VERSION = 10
 STATUS_OVERFLOW = 1
 STATUS_TIMEOUT = 2
 
@@ -166,7 +166,7 @@ class GomMeshRasterArgs(ctypes.Structure):
                 ("faces_int64", c_int32), ("soft", c_int32), ("faces_per_pixel", c_int32), ("blur_radius", c_float),
                 ("_pad", c_int32), ("list_capacity", c_int64), ("verts_ndc", c_void_p), ("faces", c_void_p),
                 ("vert_normals", c_void_p), ("tile_count", c_void_p), ("tile_offset", c_void_p), ("tile_cursor", c_void_p),
-                ("face_list", c_void_p), ("status", c_void_p), ("pix_to_face", c_void_p), ("normal_map", c_void_p),
+                ("face_list", c_void_p), ("status", c_void_p), ("worklist", c_void_p), ("pix_to_face", c_void_p), ("normal_map", c_void_p),
                 ("alpha", c_void_p), ("zcut", c_void_p), ("idcut", c_void_p), ("dL_dnormal_map", c_void_p),
                 ("dL_dalpha", c_void_p), ("dL_dverts_ndc", c_void_p), ("dL_dvert_normals", c_void_p)]
 

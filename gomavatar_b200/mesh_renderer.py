@@ -70,7 +70,8 @@ class _MeshRaster(torch.autograd.Function):
         while True:
             st = dict(tile_count=e(B, T, dtype=torch.int32), tile_offset=e(B, T + 1, dtype=torch.int32),
                       tile_cursor=e(B, T, dtype=torch.int32), face_list=e(B, cap, dtype=torch.int32),
-                      status=e(B, dtype=torch.int32), pix_to_face=e(B, H, W, dtype=torch.int32), normal_map=e(B, H, W, 3))
+                      status=e(B, dtype=torch.int32), worklist=e(B * T + 4, dtype=torch.int32),
+                      pix_to_face=e(B, H, W, dtype=torch.int32), normal_map=e(B, H, W, 3))
             if soft:
                 st.update(alpha=e(B, H, W), zcut=e(B, H, W), idcut=e(B, H, W, dtype=torch.int32))
             a = GomMeshRasterArgs(n_frames=B, n_verts=V, n_faces=F, height=H, width=W, faces_int64=int(fc.dtype == torch.int64),
@@ -87,7 +88,7 @@ class _MeshRaster(torch.autograd.Function):
             break
         ctx.meta = (B, V, F, H, W, bool(soft), float(blur_radius), int(faces_per_pixel), cap)
         saved = [vn, nn_, fc, st["tile_count"], st["tile_offset"], st["tile_cursor"], st["face_list"], st["status"],
-                 st["pix_to_face"], st["normal_map"]]
+                 st["pix_to_face"], st["normal_map"], st["worklist"]]
         if soft:
             saved += [st["alpha"], st["zcut"], st["idcut"]]
         ctx.save_for_backward(*saved)
@@ -101,8 +102,8 @@ class _MeshRaster(torch.autograd.Function):
     def backward(ctx, g_normal, g_alpha, _g_p2f):
         B, V, F, H, W, soft, blur, K, cap = ctx.meta
         t = ctx.saved_tensors
-        vn, nn_, fc, tile_count, tile_offset, tile_cursor, face_list, status, p2f, nmap = t[:10]
-        alpha, zcut, idcut = (t[10], t[11], t[12]) if soft else (None, None, None)
+        vn, nn_, fc, tile_count, tile_offset, tile_cursor, face_list, status, p2f, nmap, worklist = t[:11]
+        alpha, zcut, idcut = (t[11], t[12], t[13]) if soft else (None, None, None)
         dev = vn.device
         gn = None if g_normal is None else g_normal.contiguous().float()
         ga = None if (g_alpha is None or not soft) else g_alpha.contiguous().float()
@@ -111,7 +112,7 @@ class _MeshRaster(torch.autograd.Function):
         a = GomMeshRasterArgs(n_frames=B, n_verts=V, n_faces=F, height=H, width=W, faces_int64=int(fc.dtype == torch.int64),
                               soft=int(soft), faces_per_pixel=K, blur_radius=blur, list_capacity=cap, verts_ndc=ptr(vn),
                               faces=ptr(fc), vert_normals=ptr(nn_), tile_count=ptr(tile_count), tile_offset=ptr(tile_offset),
-                              tile_cursor=ptr(tile_cursor), face_list=ptr(face_list), status=ptr(status), pix_to_face=ptr(p2f),
+                              tile_cursor=ptr(tile_cursor), face_list=ptr(face_list), status=ptr(status), worklist=ptr(worklist), pix_to_face=ptr(p2f),
                               normal_map=ptr(nmap), alpha=ptr(alpha), zcut=ptr(zcut), idcut=ptr(idcut), dL_dnormal_map=ptr(gn),
                               dL_dalpha=ptr(ga), dL_dverts_ndc=ptr(d_verts), dL_dvert_normals=ptr(d_vn))
         call("gom_mesh_raster_backward", a)

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define GOM_ABI_VERSION 9
+#define GOM_ABI_VERSION 10
 #define GOM_TILE 16              /* 16x16-pixel tiles, as upstream's BLOCK_X/BLOCK_Y */
 #define GOM_MAX_CHANNELS 4
 #define GOM_MAX_JOINTS 64
@@ -456,6 +456,8 @@ typedef struct {
     uint32_t *tile_cursor;       /* [B,T]   */
     uint32_t *face_list;         /* [B,cap] face ids grouped by tile */
     uint32_t *status;            /* [B] */
+    uint32_t *worklist;          /* [B*T + 4] all tiles by decreasing list length (written by forward, read by backward), then
+                                    the number of non-empty tiles and the work counters of the persistent tile kernels */
     int32_t *pix_to_face;        /* [B,H,W] nearest inside face, -1 = none */
     float *normal_map;           /* [B,H,W,3] */
     float *alpha;                /* [B,H,W]   (soft) */
