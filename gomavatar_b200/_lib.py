@@ -146,7 +146,13 @@ class GomConv3x3Args(ctypes.Structure):
 
 
 class GomTf32SplitArgs(ctypes.Structure):
-    _fields_ = [("n", c_int64), ("x", c_void_p), ("hi", c_void_p), ("lo", c_void_p)]
+    _fields_ = [("n", c_int64), ("x", c_void_p), ("hi", c_void_p), ("lo", c_void_p), ("col_sum", c_void_p), ("n_cols", c_int32),
+                ("_pad", c_int32)]
+
+
+class GomLinearWgradArgs(ctypes.Structure):
+    _fields_ = [("rows", c_int64), ("m", c_int32), ("n", c_int32), ("zero_first", c_int32), ("_pad", c_int32), ("g", c_void_p),
+                ("g_lo", c_void_p), ("x", c_void_p), ("x_lo", c_void_p), ("out", c_void_p), ("status", c_void_p)]
 
 
 ADAM_MAX_SEGMENTS = 16
@@ -202,7 +208,7 @@ EXPORTS = [
     "gom_sizeof_relu_bwd_args", "gom_sizeof_lpips_tap_args", "gom_eval_metrics", "gom_sizeof_eval_metrics_args",
     "gom_conv_first_forward", "gom_conv_first_backward", "gom_sizeof_conv_first_args",
     "gom_conv3x3", "gom_conv3x3_pack_weights", "gom_tf32_split", "gom_sizeof_conv3x3_args", "gom_sizeof_conv_pack_args",
-    "gom_sizeof_tf32_split_args",
+    "gom_sizeof_tf32_split_args", "gom_linear_wgrad", "gom_sizeof_linear_wgrad_args",
     "gom_adam_step", "gom_sizeof_adam_args",
     "gom_mesh_raster_forward", "gom_mesh_raster_backward", "gom_sizeof_mesh_raster_args",
     "gom_shadow_mlp_forward", "gom_shadow_mlp_backward", "gom_shadow_mlp_weight_image_bytes", "gom_shadow_mlp_tile_words",
@@ -218,6 +224,7 @@ _STRUCTS = {
     "lpips_tap": GomLpipsTapArgs, "eval_metrics": GomEvalMetricsArgs,
     "conv_first": GomConvFirstArgs, "adam": GomAdamArgs,
     "conv3x3": GomConv3x3Args, "conv_pack": GomConvPackArgs, "tf32_split": GomTf32SplitArgs,
+    "linear_wgrad": GomLinearWgradArgs,
     "mesh_raster": GomMeshRasterArgs, "shadow_mlp": GomShadowMlpArgs, "mesh_reg": GomMeshRegArgs,
 }
 _ENTRY_POINTS = ["gom_camera_from_KE", "gom_raster_forward", "gom_raster_backward", "gom_joint_transforms_forward",
@@ -226,7 +233,7 @@ _ENTRY_POINTS = ["gom_camera_from_KE", "gom_raster_forward", "gom_raster_backwar
                  "gom_lpips_input_forward", "gom_lpips_input_backward", "gom_bias_relu", "gom_relu_backward",
                  "gom_lpips_tap_forward", "gom_lpips_tap_backward", "gom_eval_metrics",
                  "gom_conv_first_forward", "gom_conv_first_backward", "gom_adam_step",
-                 "gom_conv3x3", "gom_conv3x3_pack_weights", "gom_tf32_split",
+                 "gom_conv3x3", "gom_conv3x3_pack_weights", "gom_tf32_split", "gom_linear_wgrad",
                  "gom_mesh_raster_forward", "gom_mesh_raster_backward", "gom_shadow_mlp_forward", "gom_shadow_mlp_backward",
                  "gom_mesh_regularizers"]
 

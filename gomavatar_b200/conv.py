@@ -10,7 +10,7 @@ from __future__ import annotations
 import torch
 
 from . import _lib
-from ._lib import GomConv3x3Args, GomConvPackArgs, GomTf32SplitArgs, call, ptr
+from ._lib import GomConv3x3Args, GomConvPackArgs, GomLinearWgradArgs, GomTf32SplitArgs, call, ptr
 
 
 def _need_cuda(t, what):
@@ -33,16 +33,20 @@ def pack_weights(weight, transpose=False, split=False):
     return packed
 
 
-def tf32_low_part(x):
-    """x - trunc_tf32(x): what the tensor core drops when it reads x as a TF32 operand (second operand of 3xTF32)."""
+def tf32_low_part(x, col_sum=None):
+    """x - trunc_tf32(x): what the tensor core drops when it reads x as a TF32 operand (second operand of 3xTF32).
+    ``col_sum`` (fp32 [x.shape[-1]], a multiple of 4 dividing 1024) is incremented by the column sums of x in the same pass."""
     _need_cuda(x, "tf32_low_part")
+    if not x.is_contiguous():
+        raise _lib.GomError("tf32_low_part: x must be contiguous")
     lo = torch.empty_like(x)
-    call("gom_tf32_split", GomTf32SplitArgs(n=x.numel(), x=ptr(x), hi=None, lo=ptr(lo)))
+    call("gom_tf32_split", GomTf32SplitArgs(n=x.numel(), x=ptr(x), hi=None, lo=ptr(lo), col_sum=ptr(col_sum),
+                                            n_cols=0 if col_sum is None else int(x.shape[-1])))
     return lo
 
 
 def conv3x3(x, w_packed, bias=None, relu=False, mask_in=None, mask_out=None, precision="tf32", tma_round=True, out=None,
-            status=None, kernel_size=3):
+            status=None, kernel_size=3, x_lo=None):
     """x: contiguous [N,H,W,C_in]; w_packed from ``pack_weights``; returns [N,H,W,C_out] = conv (+ bias) (ReLU) (masked).
 
     ``mask_out`` (int32 [N,H,W,C_out/32]) receives the ReLU bit mask of the result; ``mask_in`` (same shape) zeroes the
@@ -59,7 +63,8 @@ def conv3x3(x, w_packed, bias=None, relu=False, mask_in=None, mask_out=None, pre
         raise _lib.GomError("conv3x3: 3xTF32 needs a weight packed with split=True")
     if out is None:
         out = torch.empty(N, H, W, c_out, dtype=torch.float32, device=x.device)
-    x_lo = tf32_low_part(x) if strict else None
+    if strict and x_lo is None:
+        x_lo = tf32_low_part(x)
     for mk in (mask_in, mask_out):
         if mk is not None and (tuple(mk.shape) != (N, H, W, c_out // 32) or mk.dtype != torch.int32 or not mk.is_contiguous()):
             raise _lib.GomError("conv3x3: masks must be contiguous int32 [N,H,W,C_out/32]")
@@ -74,7 +79,7 @@ def new_mask(n, h, w, c, device):
     return torch.empty(n, h, w, c // 32, dtype=torch.int32, device=device)
 
 
-def linear(x, w_packed, bias=None, relu=False, mask_in=None, mask_out=None, precision="fp32", out=None):
+def linear(x, w_packed, bias=None, relu=False, mask_in=None, mask_out=None, precision="fp32", out=None, x_lo=None):
     """Linear layer over rows on the tensor cores: x [R, C_in] (R a multiple of 16, C_in a multiple of 32, contiguous) ->
     [R, C_out] = x W^T (+ bias) (ReLU) (masked), C_out a multiple of 64; ``w_packed = pack_weights(W [C_out, C_in], ...)``.
     The rows are handed to the convolution kernel as a 16-pixel-wide one-tap "image" (kernel_size 1).  Masks: int32
@@ -87,5 +92,23 @@ def linear(x, w_packed, bias=None, relu=False, mask_in=None, mask_out=None, prec
     if out is None:
         out = torch.empty(R, c_out, dtype=torch.float32, device=x.device)
     conv3x3(x.view(1, R // 16, 16, C), w_packed, bias=bias, relu=relu, mask_in=v4(mask_in, c_out // 32), mask_out=v4(mask_out, c_out // 32),
-            precision=precision, out=out.view(1, R // 16, 16, c_out), kernel_size=1)
+            precision=precision, out=out.view(1, R // 16, 16, c_out), kernel_size=1,
+            x_lo=None if x_lo is None else x_lo.view(1, R // 16, 16, C))
+    return out
+
+
+def linear_wgrad(g, g_lo, x, x_lo, out=None, accumulate=False, status=None):
+    """Weight gradient of ``linear``: g [R, 128] (output gradient), x [R, C_in] (the layer's input, C_in a multiple of 32, at most
+    256), their TF32 low parts from ``tf32_low_part``  ->  [128, C_in] = g^T x with 3xTF32 products (csrc/wgrad_tc.cu)."""
+    _need_cuda(g, "linear_wgrad")
+    R, M = g.shape
+    N = x.shape[1]
+    for t in (g, g_lo, x, x_lo):
+        if not t.is_contiguous() or t.dtype != torch.float32 or t.shape[0] != R:
+            raise _lib.GomError("linear_wgrad: operands must be contiguous fp32 matrices with the same number of rows")
+    if out is None:
+        out = torch.empty(M, N, dtype=torch.float32, device=g.device)
+        accumulate = False
+    call("gom_linear_wgrad", GomLinearWgradArgs(rows=R, m=M, n=N, zero_first=int(not accumulate), g=ptr(g), g_lo=ptr(g_lo), x=ptr(x),
+                                               x_lo=ptr(x_lo), out=ptr(out), status=ptr(status)))
     return out

@@ -422,9 +422,15 @@ __global__ void __launch_bounds__(256) k_conv_finish(FinishDev a) {
     if (a.mask_out) a.mask_out[i] = w;
 }
 
-// lo = x - trunc_tf32(x): the part of x the tensor core drops when it reads the fp32 word x as a TF32 operand
-__global__ void k_tf32_split(GomTf32SplitArgs a) {
+// lo = x - trunc_tf32(x): the part of x the tensor core drops when it reads the fp32 word x as a TF32 operand.
+// With col_sum: x is a row-major matrix of n_cols columns (n_cols divides 1024 = the floats one block covers per step, and the
+// grid stride is a multiple of it, so a thread meets the same four columns every time); the column sums of x (the bias
+// gradient of the Linear layer whose output gradient x is) are accumulated in registers, reduced over the block's row groups
+// in shared memory and added to col_sum with one atomic per column and block.
+__global__ void __launch_bounds__(256) k_tf32_split(GomTf32SplitArgs a) {
+    __shared__ float4 s_sum[256];
     const long long n4 = a.n / 4;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
         const float4 x = __ldg(reinterpret_cast<const float4 *>(a.x) + i);
         float4 h, l;
@@ -434,6 +440,20 @@ __global__ void k_tf32_split(GomTf32SplitArgs a) {
         h.w = __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u); l.w = x.w - h.w;
         if (a.hi) reinterpret_cast<float4 *>(a.hi)[i] = h;
         reinterpret_cast<float4 *>(a.lo)[i] = l;
+        acc.x += x.x; acc.y += x.y; acc.z += x.z; acc.w += x.w;
+    }
+    if (a.col_sum) {
+        const int tpr = a.n_cols / 4;                       // threads per row; 256 / tpr row groups in this block
+        s_sum[threadIdx.x] = acc;
+        __syncthreads();
+        if ((int)threadIdx.x < tpr) {
+            for (int r = threadIdx.x + tpr; r < 256; r += tpr) {
+                const float4 o = s_sum[r];
+                acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
+            }
+            float *c = a.col_sum + 4 * threadIdx.x;
+            atomicAdd(c, acc.x); atomicAdd(c + 1, acc.y); atomicAdd(c + 2, acc.z); atomicAdd(c + 3, acc.w);
+        }
     }
 }
 
@@ -538,6 +558,8 @@ extern "C" int gom_tf32_split(const GomTf32SplitArgs *p, gom_stream_t stream) {
     GOM_REQUIRE(p->n > 0 && p->n % 4 == 0, "n must be a positive multiple of 4");
     GOM_REQUIRE(p->x && p->lo, "null pointer");
     GOM_REQUIRE(((uintptr_t)p->x % 16) == 0 && ((uintptr_t)p->lo % 16) == 0 && ((uintptr_t)p->hi % 16) == 0, "16-byte alignment");
+    GOM_REQUIRE(!p->col_sum || (p->n_cols >= 4 && p->n_cols % 4 == 0 && 1024 % p->n_cols == 0 && p->n % p->n_cols == 0),
+                "col_sum: n_cols must be a multiple of 4 that divides 1024 and n");
     int blocks = gom_div_up(p->n / 4, 256);
     if (blocks > 148 * 16) blocks = 148 * 16;
     k_tf32_split<<<blocks, 256, 0, (cudaStream_t)stream>>>(*p);

@@ -47,7 +47,7 @@ enum GomProfSlot { GOM_PROF_PREPROCESS = 0, GOM_PROF_SCAN, GOM_PROF_EMIT, GOM_PR
                    GOM_PROF_MESH_BIN, GOM_PROF_MESH_FWD, GOM_PROF_MESH_BWD,
                    GOM_PROF_SHADOW_COMPACT, GOM_PROF_SHADOW_FWD, GOM_PROF_SHADOW_BWD_DATA,
                    GOM_PROF_SHADOW_BWD_WEIGHTS, GOM_PROF_MESH_REG, GOM_PROF_CONV3X3_FWD, GOM_PROF_CONV3X3_DGRAD,
-                   GOM_PROF_WORKLIST, GOM_PROF_TILE_SORT, GOM_PROF_GEMM_TC,
+                   GOM_PROF_WORKLIST, GOM_PROF_TILE_SORT, GOM_PROF_GEMM_TC, GOM_PROF_WGRAD_TC,
                    GOM_PROF_NSLOTS };
 void gom_count_launch(void);
 void gom_prof_begin(int slot, cudaStream_t stream);

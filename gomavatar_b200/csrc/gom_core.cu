@@ -28,7 +28,7 @@ static ProfSlot g_prof[GOM_PROF_NSLOTS];
 static const char *kProfNames[GOM_PROF_NSLOTS] = {"preprocess", "scan_tiles", "emit", "blend_fwd", "blend_bwd",
     "preprocess_bwd", "joint_fwd", "joint_bwd", "lbs_fwd", "lbs_bwd", "face_fwd", "face_bwd", "photo_fwd", "photo_bwd",
     "camera", "lpips_input", "bias_relu", "relu_bwd", "lpips_tap_fwd", "lpips_tap_bwd", "eval_metrics", "conv_first_fwd", "conv_first_bwd", "adam", "mesh_bin", "mesh_raster_fwd", "mesh_raster_bwd",
-    "shadow_compact", "shadow_mlp_fwd", "shadow_mlp_bwd_data", "shadow_mlp_bwd_weights", "mesh_regularizers", "conv3x3_fwd", "conv3x3_dgrad", "worklist", "tile_sort", "gemm_tc"};
+    "shadow_compact", "shadow_mlp_fwd", "shadow_mlp_bwd_data", "shadow_mlp_bwd_weights", "mesh_regularizers", "conv3x3_fwd", "conv3x3_dgrad", "worklist", "tile_sort", "gemm_tc", "wgrad_tc"};
 
 static cudaEvent_t prof_next(int slot) {
     ProfSlot &s = g_prof[slot];

@@ -110,7 +110,9 @@ class _TcMlpStack(torch.autograd.Function):
     the encoding re-read by the layer in ``skips``) on the tcgen05 kernel of csrc/conv3x3_tc.cu (kernel_size 1: a GEMM over
     rows, bias + ReLU fused, the ReLU bit mask written by the forward and consumed by the dgrad of the layer above) with 3xTF32
     products = fp32-GEMM accuracy, what ``nn.Linear`` computes in the reference (torch never enables TF32 for matmul by
-    default).  Weight gradients are reductions over the ~1e5 rows and stay split-K batched GEMMs (see ``_Linear``).
+    default).  Weight gradients (contractions over the ~1e5 rows) run on csrc/wgrad_tc.cu (tcgen05 with MN-major operands,
+    split-K over the SMs) when the layer is 128 wide, the bias gradients are column sums formed by the TF32 split pass that
+    reads the gradient anyway; other widths keep the split-K batched GEMM of ``_Linear``.
 
     forward(x0 [R, in0], enc [R, E], cat_layers, *weights_and_biases) -> last hidden activation [R, width]."""
 
@@ -121,20 +123,22 @@ class _TcMlpStack(torch.autograd.Function):
         ws, bs = params[0::2], params[1::2]
         h = _pad_cols(x0.detach().float(), 32)
         encd = enc.detach().float()
-        saved_in, masks = [], []
+        saved_in, saved_lo, masks = [], [], []
         for i, (w, b) in enumerate(zip(ws, bs)):
             if i in cat_layers:
                 h = _pad_cols(torch.cat([h[:R, :ws[i - 1].shape[0]], encd], dim=1), 32)
             wp = w.detach().new_zeros(w.shape[0], h.shape[1])
             wp[:, :w.shape[1]] = w.detach()
             mask = C.new_mask(1, h.shape[0] // 16, 16, w.shape[0], h.device).view(h.shape[0], -1)
-            y = C.linear(h, C.pack_weights(wp, split=True), bias=b.detach().clone(), relu=True, mask_out=mask, precision="fp32")     # clone: 16-byte aligned (arena views are not)
+            h_lo = C.tf32_low_part(h)                      # kept: second operand of the weight gradient as well
+            y = C.linear(h, C.pack_weights(wp, split=True), bias=b.detach().clone(), relu=True, mask_out=mask, precision="fp32", x_lo=h_lo)     # clone: 16-byte aligned (arena views are not)
             saved_in.append(h)
+            saved_lo.append(h_lo)
             masks.append(mask)
             h = y
         ctx.cat_layers, ctx.R, ctx.n = tuple(cat_layers), R, len(ws)
         ctx.dims = (x0.shape[1], enc.shape[1])
-        ctx.save_for_backward(*saved_in, *masks, *ws)
+        ctx.save_for_backward(*saved_in, *masks, *ws, *saved_lo)
         ctx.last = h
         return h[:R]
 
@@ -144,7 +148,7 @@ class _TcMlpStack(torch.autograd.Function):
         from ._lib import GomReluBwdArgs, call, ptr
         n, R = ctx.n, ctx.R
         t = ctx.saved_tensors
-        saved_in, masks, ws = t[:n], t[n:2 * n], t[2 * n:]
+        saved_in, masks, ws, saved_lo = t[:n], t[n:2 * n], t[2 * n:3 * n], t[3 * n:]
         in0, E = ctx.dims
         R16 = saved_in[0].shape[0]
         if R16 == R:
@@ -158,16 +162,24 @@ class _TcMlpStack(torch.autograd.Function):
         ones = torch.ones(1, R16, dtype=gp.dtype, device=gp.device)
         for i in reversed(range(n)):
             w, hin = ws[i], saved_in[i]
-            # weight / bias gradients: reductions over the rows (split-K batched GEMM, GEMV with ones)
-            S = 64
-            while S > 1 and R16 % S:
-                S //= 2
-            if S >= 8 and R16 // S >= 512:
-                gw = torch.bmm(gp.view(S, R16 // S, -1).transpose(1, 2), hin.view(S, R16 // S, -1)).sum(0)
+            # weight / bias gradients: contractions over the rows.  128-wide layers: tensor cores (csrc/wgrad_tc.cu), the bias
+            # gradient = column sums formed by the TF32 split of gp; other widths: split-K batched GEMM, GEMV with ones
+            gp_lo = None
+            if gp.shape[1] == 128 and hin.shape[1] <= 256 and 1024 % gp.shape[1] == 0:
+                gb = torch.zeros(gp.shape[1], dtype=gp.dtype, device=gp.device)
+                gp_lo = C.tf32_low_part(gp, col_sum=gb)
+                gw = C.linear_wgrad(gp, gp_lo, hin, saved_lo[i])
             else:
-                gw = gp.t() @ hin
+                S = 64
+                while S > 1 and R16 % S:
+                    S //= 2
+                if S >= 8 and R16 // S >= 512:
+                    gw = torch.bmm(gp.view(S, R16 // S, -1).transpose(1, 2), hin.view(S, R16 // S, -1)).sum(0)
+                else:
+                    gw = gp.t() @ hin
+                gb = (ones @ gp)[0]
             grads[2 * i] = gw[:, :w.shape[1]]
-            grads[2 * i + 1] = (ones @ gp)[0]
+            grads[2 * i + 1] = gb
             if i == 0 and not (ctx.needs_input_grad[0] or ctx.needs_input_grad[1]):
                 break
             # input gradient with the ReLU backward of the layer below fused (bit mask; the re-read encoding columns and the
@@ -185,7 +197,7 @@ class _TcMlpStack(torch.autograd.Function):
                 wp = torch.cat([wp, wp.new_zeros(wp.shape[0], 64 - c_out % 64)], dim=1)
                 if mask_in is not None:
                     mask_in = torch.cat([mask_in, mask_in.new_full((R16, 1), -1)], dim=1).contiguous()
-            g_in = C.linear(gp, C.pack_weights(wp, transpose=True, split=True), mask_in=mask_in, precision="fp32")
+            g_in = C.linear(gp, C.pack_weights(wp, transpose=True, split=True), mask_in=mask_in, precision="fp32", x_lo=gp_lo)
             if i in ctx.cat_layers:
                 wprev = ws[i - 1].shape[0]
                 g_enc = g_in[:R, wprev:wprev + E] if g_enc is None else g_enc + g_in[:R, wprev:wprev + E]

@@ -401,13 +401,33 @@ typedef struct {
 } GomConv3x3Args;
 int gom_conv3x3(const GomConv3x3Args *a, gom_stream_t stream);
 
-/* hi = x truncated to TF32 (what the tensor core reads from an fp32 word; nullable), lo = x - hi; n a multiple of 4 */
+/* hi = x truncated to TF32 (what the tensor core reads from an fp32 word; nullable), lo = x - hi; n a multiple of 4.
+ * col_sum (nullable): x is a row-major [n / n_cols, n_cols] matrix (n_cols a multiple of 4 dividing 1024) and col_sum[n_cols]
+ * is INCREMENTED by its column sums (the bias gradient of a Linear layer, formed while the gradient is read anyway). */
 typedef struct {
     int64_t n;
     const float *x;
     float *hi, *lo;
+    float *col_sum;
+    int32_t n_cols, _pad;
 } GomTf32SplitArgs;
 int gom_tf32_split(const GomTf32SplitArgs *a, gom_stream_t stream);
+
+/* Weight gradient of a Linear layer over a tall batch of rows (reference: autograd of every nn.Linear of
+ * models/modules/non_rigid_module.py:75-147):  out[m, n] (+)= sum_r g[r, m] x[r, n]  with 3xTF32 products on the tensor cores
+ * (g x + g_lo x + g x_lo; g_lo, x_lo from gom_tf32_split).  g [rows, m], x [rows, n] row-major fp32; m = 128; n a multiple of
+ * 32, at most 256.  Split-K over the SMs, partial products meet in `out` through TMA reduce-add stores. */
+typedef struct {
+    int64_t rows;
+    int32_t m, n;
+    int32_t zero_first;          /* 1: out is zeroed first (on the stream); 0: the product is added to out */
+    int32_t _pad;
+    const float *g, *g_lo;       /* [rows, m] */
+    const float *x, *x_lo;       /* [rows, n] */
+    float *out;                  /* [m, n] */
+    uint32_t *status;            /* [1] nullable: GOM_STATUS_TIMEOUT */
+} GomLinearWgradArgs;
+int gom_linear_wgrad(const GomLinearWgradArgs *a, gom_stream_t stream);
 
 /* --------------------------------------------------------------------------------------------------------------
  * Evaluation metrics.  Replaces reference eval.py:101-108 (Evaluator.psnr_metric / ssim_metric: skimage 0.18
@@ -605,6 +625,7 @@ size_t gom_sizeof_conv_first_args(void);
 size_t gom_sizeof_conv3x3_args(void);
 size_t gom_sizeof_conv_pack_args(void);
 size_t gom_sizeof_tf32_split_args(void);
+size_t gom_sizeof_linear_wgrad_args(void);
 size_t gom_sizeof_adam_args(void);
 size_t gom_sizeof_mesh_raster_args(void);
 size_t gom_sizeof_shadow_mlp_args(void);

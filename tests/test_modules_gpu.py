@@ -74,3 +74,28 @@ def test_linear_kernel_matches_torch_at_full_size():
     refg = (gy.double() @ w.double()) * (x.double() @ w.double().t() + b.double() > 0)        # masked by THIS layer's output sign
     # the mask belongs to y (the layer's own output), so apply it to a gradient of the same shape: a square layer
     assert _rel(gx, refg) < 1e-5
+
+
+@pytest.mark.parametrize("R,N", [(4096, 128), (120272, 128), (5008, 192), (48, 32), (16016, 256), (120272, 192)])
+def test_linear_wgrad_kernel_matches_float64(R, N):
+    """csrc/wgrad_tc.cu: gw = g^T x over R rows with MN-major operands (3xTF32), rows not a multiple of the 32-row k-block, every
+    stage count; the bias gradient = column sums formed by the TF32 split pass.  Reference: autograd of nn.Linear
+    (models/modules/non_rigid_module.py:75-147)."""
+    from gomavatar_b200 import conv as C
+    torch.manual_seed(R + N)
+    g = torch.randn(R, 128, device=DEV) * torch.rand(1, 128, device=DEV)
+    x = torch.randn(R, N, device=DEV).relu_() + 0.01 * torch.randn(R, N, device=DEV)
+    gb = torch.zeros(128, device=DEV)
+    g_lo = C.tf32_low_part(g, col_sum=gb)
+    x_lo = C.tf32_low_part(x)
+    status = torch.zeros(1, dtype=torch.int32, device=DEV)
+    gw = C.linear_wgrad(g, g_lo, x, x_lo, status=status)
+    assert int(status[0]) == 0
+    ref = g.double().T @ x.double()
+    scale = g.double().abs().T @ x.double().abs()                 # what a rounding error of either operand is relative to
+    err = ((gw.double() - ref).abs() / scale).max()
+    assert float(err) < 2e-6, float(err)                          # TF32 alone would be ~1e-3
+    # accumulate into an existing buffer
+    gw2 = C.linear_wgrad(g, g_lo, x, x_lo, out=gw.clone(), accumulate=True)
+    assert float(((gw2.double() - 2 * ref).abs() / scale).max()) < 4e-6
+    assert float((gb.double() - g.double().sum(0)).abs().max() / g.double().abs().sum(0).max()) < 1e-5
