@@ -177,6 +177,22 @@ class GomMeshRasterArgs(ctypes.Structure):
                 ("dL_dalpha", c_void_p), ("dL_dverts_ndc", c_void_p), ("dL_dvert_normals", c_void_p)]
 
 
+class GomVertexNormalsArgs(ctypes.Structure):
+    _fields_ = [("n_frames", c_int32), ("n_verts", c_int32), ("n_faces", c_int32), ("faces_int64", c_int32), ("verts", c_void_p),
+                ("faces", c_void_p), ("E", c_void_p), ("acc", c_void_p), ("normals_cam", c_void_p), ("dL_dnormals_cam", c_void_p),
+                ("scratch", c_void_p), ("dL_dverts", c_void_p)]
+
+
+class GomNdcArgs(ctypes.Structure):
+    _fields_ = [("n_frames", c_int32), ("n_verts", c_int32), ("height", c_int32), ("width", c_int32), ("verts", c_void_p),
+                ("K", c_void_p), ("E", c_void_p), ("ndc", c_void_p), ("dL_dndc", c_void_p), ("dL_dverts", c_void_p)]
+
+
+class GomDilatedMaskL1Args(ctypes.Structure):
+    _fields_ = [("n_frames", c_int32), ("height", c_int32), ("width", c_int32), ("kernel_size", c_int32), ("dilate", c_int32),
+                ("grad_scale", c_float), ("pred", c_void_p), ("mask_gt", c_void_p), ("sum", c_void_p), ("grad", c_void_p)]
+
+
 class GomShadowMlpArgs(ctypes.Structure):
     _fields_ = [("n_pixels", c_int64), ("capacity", c_int64), ("multires", c_int32), ("width", c_int32), ("depth", c_int32),
                 ("save_hidden", c_int32), ("normals", c_void_p), ("W_in", c_void_p), ("b_in", c_void_p), ("W_hid", c_void_p),
@@ -211,6 +227,8 @@ EXPORTS = [
     "gom_sizeof_tf32_split_args", "gom_linear_wgrad", "gom_sizeof_linear_wgrad_args",
     "gom_adam_step", "gom_sizeof_adam_args",
     "gom_mesh_raster_forward", "gom_mesh_raster_backward", "gom_sizeof_mesh_raster_args",
+    "gom_vertex_normals_forward", "gom_vertex_normals_backward", "gom_ndc_forward", "gom_ndc_backward", "gom_dilated_mask_l1",
+    "gom_sizeof_vertex_normals_args", "gom_sizeof_ndc_args", "gom_sizeof_dilated_mask_l1_args",
     "gom_shadow_mlp_forward", "gom_shadow_mlp_backward", "gom_shadow_mlp_weight_image_bytes", "gom_shadow_mlp_tile_words",
     "gom_shadow_mlp_partial_floats", "gom_shadow_mlp_num_ctas", "gom_sizeof_shadow_mlp_args",
     "gom_mesh_regularizers", "gom_sizeof_mesh_reg_args",
@@ -225,7 +243,8 @@ _STRUCTS = {
     "conv_first": GomConvFirstArgs, "adam": GomAdamArgs,
     "conv3x3": GomConv3x3Args, "conv_pack": GomConvPackArgs, "tf32_split": GomTf32SplitArgs,
     "linear_wgrad": GomLinearWgradArgs,
-    "mesh_raster": GomMeshRasterArgs, "shadow_mlp": GomShadowMlpArgs, "mesh_reg": GomMeshRegArgs,
+    "mesh_raster": GomMeshRasterArgs, "vertex_normals": GomVertexNormalsArgs, "ndc": GomNdcArgs,
+    "dilated_mask_l1": GomDilatedMaskL1Args, "shadow_mlp": GomShadowMlpArgs, "mesh_reg": GomMeshRegArgs,
 }
 _ENTRY_POINTS = ["gom_camera_from_KE", "gom_raster_forward", "gom_raster_backward", "gom_joint_transforms_forward",
                  "gom_joint_transforms_backward", "gom_lbs_forward", "gom_lbs_backward", "gom_face_gaussians_forward",
@@ -234,7 +253,8 @@ _ENTRY_POINTS = ["gom_camera_from_KE", "gom_raster_forward", "gom_raster_backwar
                  "gom_lpips_tap_forward", "gom_lpips_tap_backward", "gom_eval_metrics",
                  "gom_conv_first_forward", "gom_conv_first_backward", "gom_adam_step",
                  "gom_conv3x3", "gom_conv3x3_pack_weights", "gom_tf32_split", "gom_linear_wgrad",
-                 "gom_mesh_raster_forward", "gom_mesh_raster_backward", "gom_shadow_mlp_forward", "gom_shadow_mlp_backward",
+                 "gom_mesh_raster_forward", "gom_mesh_raster_backward", "gom_vertex_normals_forward", "gom_vertex_normals_backward",
+                 "gom_ndc_forward", "gom_ndc_backward", "gom_dilated_mask_l1", "gom_shadow_mlp_forward", "gom_shadow_mlp_backward",
                  "gom_mesh_regularizers"]
 
 _lib = None

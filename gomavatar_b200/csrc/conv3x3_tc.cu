@@ -562,6 +562,7 @@ extern "C" int gom_tf32_split(const GomTf32SplitArgs *p, gom_stream_t stream) {
                 "col_sum: n_cols must be a multiple of 4 that divides 1024 and n");
     int blocks = gom_div_up(p->n / 4, 256);
     if (blocks > 148 * 16) blocks = 148 * 16;
+    if (p->col_sum && blocks > 148 * 2) blocks = 148 * 2;       // one atomic per column and block: keep the blocks few
     k_tf32_split<<<blocks, 256, 0, (cudaStream_t)stream>>>(*p);
     GOM_LAUNCH_CHECK();
     return GOM_OK;

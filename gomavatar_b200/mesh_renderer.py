@@ -15,7 +15,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib
-from ._lib import GomMeshRasterArgs, call, ptr
+from ._lib import GomMeshRasterArgs, GomNdcArgs, GomVertexNormalsArgs, call, ptr
 
 
 def ndc_T_world(xyzs_world, K, E, H, W):
@@ -43,6 +43,69 @@ def vertex_normals(verts_bv3, faces):
     n = n.index_add(1, f[:, 2], torch.cross(v0 - v2, v1 - v2, dim=-1))
     n = n.index_add(1, f[:, 0], torch.cross(v1 - v0, v2 - v0, dim=-1))
     return torch.nn.functional.normalize(n, eps=1e-6, dim=-1)
+
+
+class _NdcTWorld(torch.autograd.Function):
+    """``ndc_T_world`` as one launch each way (csrc/mesh_prep.cu); K and E are inputs of the step and get no gradient."""
+
+    @staticmethod
+    def forward(ctx, xyzs_world, K, E, H, W):
+        B, _, V = xyzs_world.shape
+        v, Kc, Ec = xyzs_world.detach().contiguous().float(), K.detach().contiguous().float(), E.detach().contiguous().float()
+        out = torch.empty(B, V, 3, dtype=torch.float32, device=v.device)
+        call("gom_ndc_forward", GomNdcArgs(n_frames=B, n_verts=V, height=H, width=W, verts=ptr(v), K=ptr(Kc), E=ptr(Ec), ndc=ptr(out)))
+        ctx.save_for_backward(v, Kc, Ec)
+        ctx.hw = (H, W)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        v, Kc, Ec = ctx.saved_tensors
+        B, _, V = v.shape
+        gc = g.contiguous().float()
+        gv = torch.empty_like(v)
+        call("gom_ndc_backward", GomNdcArgs(n_frames=B, n_verts=V, height=ctx.hw[0], width=ctx.hw[1], verts=ptr(v), K=ptr(Kc),
+                                            E=ptr(Ec), dL_dndc=ptr(gc), dL_dverts=ptr(gv)))
+        return gv, None, None, None, None
+
+
+class _VertexNormalsCam(torch.autograd.Function):
+    """PyTorch3D ``verts_normals_padded`` of the posed mesh rotated into the camera frame (reference models/model.py:271-273):
+    two launches each way (csrc/mesh_prep.cu) instead of ~15 + ~25 gather / cross / index_add / normalize kernels."""
+
+    @staticmethod
+    def forward(ctx, verts_b3v, faces, E):
+        B, _, V = verts_b3v.shape
+        v, Ec = verts_b3v.detach().contiguous().float(), E.detach().contiguous().float()
+        fc = faces.contiguous()
+        if fc.dtype not in (torch.int32, torch.int64):
+            fc = fc.long()
+        acc = torch.empty(B, V, 3, dtype=torch.float32, device=v.device)
+        out = torch.empty(B, V, 3, dtype=torch.float32, device=v.device)
+        call("gom_vertex_normals_forward", GomVertexNormalsArgs(n_frames=B, n_verts=V, n_faces=fc.shape[0], faces_int64=int(fc.dtype == torch.int64),
+                                                                verts=ptr(v), faces=ptr(fc), E=ptr(Ec), acc=ptr(acc), normals_cam=ptr(out)))
+        ctx.save_for_backward(v, fc, Ec, acc)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        v, fc, Ec, acc = ctx.saved_tensors
+        B, _, V = v.shape
+        gc = g.contiguous().float()
+        scratch, gv = torch.empty_like(acc), torch.empty_like(v)
+        call("gom_vertex_normals_backward", GomVertexNormalsArgs(n_frames=B, n_verts=V, n_faces=fc.shape[0], faces_int64=int(fc.dtype == torch.int64),
+                                                                 verts=ptr(v), faces=ptr(fc), E=ptr(Ec), acc=ptr(acc), dL_dnormals_cam=ptr(gc),
+                                                                 scratch=ptr(scratch), dL_dverts=ptr(gv)))
+        return gv, None, None
+
+
+def vertex_normals_cam(verts_b3v, faces, E):
+    """[B,3,V] posed vertices, faces [F,3], E [B,4,4] -> camera-space unit vertex normals [B,V,3] (CUDA kernels; the torch
+    formulation ``vertex_normals`` + bmm below is the readable definition and the CPU path of the tests)."""
+    if verts_b3v.is_cuda:
+        return _VertexNormalsCam.apply(verts_b3v, faces, E)
+    n = vertex_normals(verts_b3v.permute(0, 2, 1), faces)
+    return torch.bmm(E[:, :3, :3], n.permute(0, 2, 1)).permute(0, 2, 1)
 
 
 MESH_BIN = 8                 # pixels per side of a binning tile (csrc/mesh_raster.cu kBin)
@@ -144,7 +207,7 @@ class Renderer(nn.Module):
 
     def forward(self, xyzs_observation, vertex_normals, K, E, faces, **kwargs):
         W, H = self.img_size
-        xyzs_ndc = ndc_T_world(xyzs_observation, K, E, H, W)
+        xyzs_ndc = _NdcTWorld.apply(xyzs_observation, K, E, int(H), int(W)) if xyzs_observation.is_cuda else ndc_T_world(xyzs_observation, K, E, H, W)
         B = xyzs_ndc.shape[0]
         vn = vertex_normals if vertex_normals.dim() == 3 else vertex_normals[None]
         if vn.shape[0] != B:

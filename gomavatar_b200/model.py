@@ -188,8 +188,8 @@ class Model(nn.Module):
 
         normal = normal_mask = shadings = None
         if self.normal_renderer is not None and self.shadow_module is not None:     # reference model.py:271-287
-            normals = self._vertex_normals(vertices_observation)
-            normals = torch.bmm(E[:, :3, :3], normals.permute(0, 2, 1)).permute(0, 2, 1)
+            from .mesh_renderer import vertex_normals_cam
+            normals = vertex_normals_cam(vertices_observation, self.faces, E)        # model.py:271-273 in one launch each way
             normal, normal_mask = self.normal_renderer(vertices_observation, normals, K, E, faces=self.faces)
             shadings = self.shadow_module(normal.reshape(B, H * W, 3)).reshape(B, H, W, 1) * 2
             rgbs = albedos * shadings

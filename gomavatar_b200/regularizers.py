@@ -108,7 +108,30 @@ def color_consistency(color, face_connectivity):
     return (color.index_select(0, face_connectivity[:, 0]) - color.index_select(0, face_connectivity[:, 1])).abs().mean()
 
 
+class _DilatedMaskL1(torch.autograd.Function):
+    """mean |normal_mask - maxpool_k(mask_gt)| with its gradient in ONE launch (csrc/mesh_prep.cu; reference train.py:137-146)."""
+
+    @staticmethod
+    def forward(ctx, normal_mask, mask_gt, kernel_size, dilate):
+        from ._lib import GomDilatedMaskL1Args, call, ptr
+        B, H, W = normal_mask.shape
+        pred, gt = normal_mask.detach().contiguous().float(), mask_gt.detach().contiguous().float()
+        s = torch.empty(1, dtype=torch.float64, device=pred.device)
+        grad = torch.empty_like(pred)
+        call("gom_dilated_mask_l1", GomDilatedMaskL1Args(n_frames=B, height=H, width=W, kernel_size=int(kernel_size), dilate=int(bool(dilate)),
+                                                         grad_scale=1.0 / (B * H * W), pred=ptr(pred), mask_gt=ptr(gt), sum=ptr(s), grad=ptr(grad)))
+        ctx.save_for_backward(grad)
+        return (s[0] / (B * H * W)).float()
+
+    @staticmethod
+    def backward(ctx, g):
+        (grad,) = ctx.saved_tensors
+        return g * grad, None, None, None
+
+
 def normal_mask_loss(normal_mask, mask_gt, kernel_size=7, dilate=True):
+    if normal_mask.is_cuda and normal_mask.dim() == 3 and kernel_size % 2 == 1 and kernel_size <= 15:
+        return _DilatedMaskL1.apply(normal_mask, mask_gt, kernel_size, dilate)
     if dilate:
         mask_gt = F.max_pool2d(mask_gt.unsqueeze(1), kernel_size=kernel_size, stride=1, padding=kernel_size // 2).squeeze(1)
     return (normal_mask - mask_gt).abs().mean()

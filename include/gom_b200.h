@@ -491,6 +491,51 @@ typedef struct {
 int gom_mesh_raster_forward(const GomMeshRasterArgs *a, gom_stream_t stream);
 int gom_mesh_raster_backward(const GomMeshRasterArgs *a, gom_stream_t stream);
 
+/* Inputs of the mesh renderer, one launch each way instead of torch's gather / cross / index_add / normalize chains.
+ * gom_vertex_normals_*: PyTorch3D Meshes.verts_normals_padded (per face the three corner cross products accumulated on its
+ *   vertices, n / max(|n|, 1e-6)) rotated into the camera frame by E[:3,:3] — reference models/model.py:271-273.
+ * gom_ndc_*: reference utils/pc_util.py:30-46 ndc_T_world: (x_ndc, y_ndc, z_cam) per vertex. */
+typedef struct {
+    int32_t n_frames, n_verts, n_faces;
+    int32_t faces_int64;
+    const float *verts;          /* [B,3,V] posed vertices (world) */
+    const void *faces;           /* [F,3] */
+    const float *E;              /* [B,4,4] */
+    float *acc;                  /* [B,V,3] unnormalised normals: written by forward, read by backward */
+    float *normals_cam;          /* [B,V,3] out */
+    const float *dL_dnormals_cam;/* [B,V,3] (backward) */
+    float *scratch;              /* [B,V,3] (backward) */
+    float *dL_dverts;            /* [B,3,V] (backward; zeroed first) */
+} GomVertexNormalsArgs;
+int gom_vertex_normals_forward(const GomVertexNormalsArgs *a, gom_stream_t stream);
+int gom_vertex_normals_backward(const GomVertexNormalsArgs *a, gom_stream_t stream);
+
+typedef struct {
+    int32_t n_frames, n_verts, height, width;
+    const float *verts;          /* [B,3,V] */
+    const float *K;              /* [B,3,3] */
+    const float *E;              /* [B,4,4] */
+    float *ndc;                  /* [B,V,3] out */
+    const float *dL_dndc;        /* [B,V,3] (backward) */
+    float *dL_dverts;            /* [B,3,V] (backward; overwritten) */
+} GomNdcArgs;
+int gom_ndc_forward(const GomNdcArgs *a, gom_stream_t stream);
+int gom_ndc_backward(const GomNdcArgs *a, gom_stream_t stream);
+
+/* reference train.py:137-146: sum |pred - maxpool_k(mask_gt)| over all pixels (stride 1, padding k/2, -inf padding like
+ * F.max_pool2d; dilate = 0: plain L1) into sum[0] (zeroed first), and grad = sign(pred - dilated) * grad_scale (nullable). */
+typedef struct {
+    int32_t n_frames, height, width;
+    int32_t kernel_size;         /* odd, <= 15 */
+    int32_t dilate;
+    float grad_scale;            /* e.g. 1 / (B H W) for the mean */
+    const float *pred;           /* [B,H,W] soft silhouette of the mesh renderer */
+    const float *mask_gt;        /* [B,H,W] */
+    double *sum;                 /* [1] */
+    float *grad;                 /* [B,H,W] nullable */
+} GomDilatedMaskL1Args;
+int gom_dilated_mask_l1(const GomDilatedMaskL1Args *a, gom_stream_t stream);
+
 /* --------------------------------------------------------------------------------------------------------------
  * Adam over the flat parameter arena, one launch.  Replaces `optimizer.step()` of reference train.py:339 for the
  * parameter groups of models/model.py:305-324 (torch.optim.Adam semantics, amsgrad off, weight decay 0).  Segment s
@@ -628,6 +673,9 @@ size_t gom_sizeof_tf32_split_args(void);
 size_t gom_sizeof_linear_wgrad_args(void);
 size_t gom_sizeof_adam_args(void);
 size_t gom_sizeof_mesh_raster_args(void);
+size_t gom_sizeof_vertex_normals_args(void);
+size_t gom_sizeof_ndc_args(void);
+size_t gom_sizeof_dilated_mask_l1_args(void);
 size_t gom_sizeof_shadow_mlp_args(void);
 size_t gom_sizeof_mesh_reg_args(void);
 

@@ -104,3 +104,69 @@ def test_renderer_module_matches_oracle_render(training):
     go, gk = vo.grad.float().numpy(), xyz.grad[0].T.cpu().numpy()
     rel_l2 = np.sqrt(((gk - go) ** 2).sum() / (go ** 2).sum())
     assert rel_l2 < 3e-2, rel_l2
+
+
+@pytest.mark.parametrize("size", [(96, 96), (80, 56), (56, 80)])
+def test_ndc_and_vertex_normal_kernels_match_torch_float64(size):
+    """csrc/mesh_prep.cu: ndc_T_world (reference utils/pc_util.py:30-46) and camera-space vertex normals (reference
+    models/model.py:271-273 on PyTorch3D's verts_normals_padded), forward and backward, against the torch formulations of
+    gomavatar_b200.mesh_renderer evaluated in float64."""
+    from gomavatar_b200.mesh_renderer import _NdcTWorld, ndc_T_world, vertex_normals, vertex_normals_cam
+    W, H = size
+    sc = S.make_humanoid(3000, seed=0)
+    fr = S.make_frames(sc, 3, img_size=(W, H), seed=5, focal=537.0 * W / 512.0, base_size=W)
+    pr = S.make_params(sc, seed=1)
+    faces = t(sc.faces).long()
+    vs = []
+    for b in range(3):
+        v, _, _ = G.pose_geometry(t(pr["vertices"]), faces, t(sc.lbs_weights), t(pr["so3"]), t(pr["scale"]),
+                                  t(fr["cnl_gtfms"][b]), t(fr["dst_Rs"][b]), t(fr["dst_Ts"][b]))
+        vs.append(v.detach())
+    xyz = torch.stack(vs)                                                   # [B,3,V]
+    Kd, Ed = t(fr["K"]), t(fr["E"])
+    rng = np.random.default_rng(2)
+    g_ndc = t(rng.normal(size=(3, xyz.shape[2], 3)).astype(np.float32))
+    g_vn = t(rng.normal(size=(3, xyz.shape[2], 3)).astype(np.float32))
+    # float64 torch reference
+    xo = xyz.double().requires_grad_(True)
+    ndc_o = ndc_T_world(xo, Kd.double(), Ed.double(), H, W)
+    n_o = vertex_normals(xo.permute(0, 2, 1), faces)
+    n_o = torch.bmm(Ed[:, :3, :3].double(), n_o.permute(0, 2, 1)).permute(0, 2, 1)
+    ((ndc_o * g_ndc.double()).sum() + (n_o * g_vn.double()).sum()).backward()
+    # kernels, separately so that each gradient is checked on its own
+    xk = xyz.to(DEV).requires_grad_(True)
+    ndc_k = _NdcTWorld.apply(xk, Kd.to(DEV), Ed.to(DEV), H, W)
+    (ndc_k * g_ndc.to(DEV)).sum().backward()
+    g1 = xk.grad.clone(); xk.grad = None
+    n_k = vertex_normals_cam(xk, faces.to(DEV), Ed.to(DEV))
+    (n_k * g_vn.to(DEV)).sum().backward()
+    g2 = xk.grad.clone()
+    assert float((ndc_k.cpu().double() - ndc_o).abs().max()) < 2e-5
+    assert float((n_k.cpu().double() - n_o).abs().max()) < 2e-5
+    xo2 = xyz.double().requires_grad_(True)
+    (ndc_T_world(xo2, Kd.double(), Ed.double(), H, W) * g_ndc.double()).sum().backward()
+    g1_o = xo2.grad
+    g2_o = xo.grad - g1_o
+    assert float((g1.cpu().double() - g1_o).abs().max() / g1_o.abs().max()) < 2e-5
+    assert float((g2.cpu().double() - g2_o).abs().max() / g2_o.abs().max()) < 1e-4
+
+
+@pytest.mark.parametrize("B,H,W,k,dilate", [(2, 64, 64, 7, True), (1, 50, 70, 7, True), (3, 33, 40, 3, True), (2, 64, 48, 7, False),
+                                            (1, 40, 40, 15, True)])
+def test_dilated_mask_l1_kernel_matches_torch(B, H, W, k, dilate):
+    """csrc/mesh_prep.cu gom_dilated_mask_l1 against reference train.py:137-146 written with F.max_pool2d."""
+    import torch.nn.functional as F
+    from gomavatar_b200 import regularizers as RG
+    g = torch.Generator().manual_seed(B * H + k)
+    gt = (torch.rand(B, H, W, generator=g) > 0.7).float()
+    nm = torch.rand(B, H, W, generator=g)
+    nm[:, ::5, ::3] = 1.0                                                     # exact ties: |0| has gradient 0 in torch
+    ref_in = nm.clone().double().requires_grad_(True)
+    d = F.max_pool2d(gt.double().unsqueeze(1), kernel_size=k, stride=1, padding=k // 2).squeeze(1) if dilate else gt.double()
+    ref = (ref_in - d).abs().mean()
+    ref.backward()
+    x = nm.to(DEV).requires_grad_(True)
+    out = RG.normal_mask_loss(x, gt.to(DEV), k, dilate)
+    (out * 3.0).backward()
+    assert abs(float(out) - float(ref)) < 1e-6
+    assert float((x.grad.cpu().double() - 3.0 * ref_in.grad).abs().max()) < 1e-9 + 1e-6 * float(ref_in.grad.abs().max())
