@@ -211,6 +211,35 @@ class _TcMlpStack(torch.autograd.Function):
         return (g_x0, g_enc if ctx.needs_input_grad[1] else None, None) + tuple(grads)
 
 
+class _NonRigidInput(torch.autograd.Function):
+    """(canonical vertices [1|B,3,V], pose vectors [B,C]) -> (h0 [R16, cols] = [pose | windowed positional encoding | 0], enc
+    [R16, 6L]) in the padded layout ``_TcMlpStack`` reads, one launch each way (csrc/posenc.cu) instead of torch's sin / cos /
+    stack / window / cat / pad chain.  Reference models/modules/non_rigid_module.py:15-72,128-140."""
+
+    @staticmethod
+    def forward(ctx, xyz, posevec, alpha, multires, cols, rows_padded):
+        from ._lib import GomNonRigidInputArgs, call, ptr
+        B, C = posevec.shape
+        Bx, _, V = xyz.shape
+        x, pv = xyz.detach().contiguous().float(), posevec.detach().contiguous().float()
+        h0 = torch.empty(rows_padded, cols, dtype=torch.float32, device=x.device)
+        enc = torch.empty(rows_padded, 6 * multires, dtype=torch.float32, device=x.device)
+        ctx.args = dict(n_frames=B, n_verts=V, xyz_frames=Bx, cond=C, multires=multires, cols=cols, rows_padded=rows_padded, alpha=float(alpha))
+        call("gom_nonrigid_input_forward", GomNonRigidInputArgs(xyz=ptr(x), posevec=ptr(pv), h0=ptr(h0), enc=ptr(enc), **ctx.args))
+        ctx.save_for_backward(x)
+        return h0, enc
+
+    @staticmethod
+    def backward(ctx, g_h0, g_enc):
+        from ._lib import GomNonRigidInputArgs, call, ptr
+        (x,) = ctx.saved_tensors
+        gh = None if g_h0 is None else g_h0.contiguous().float()
+        ge = None if g_enc is None else g_enc.contiguous().float()
+        gx = torch.empty_like(x)
+        call("gom_nonrigid_input_backward", GomNonRigidInputArgs(xyz=ptr(x), g_h0=ptr(gh), g_enc=ptr(ge), g_xyz=ptr(gx), **ctx.args))
+        return gx, None, None, None, None, None
+
+
 def _run(mods, cat_at, h, enc):
     # hidden stack on the tensor cores when it is tall enough to matter and shaped like the reference's (width % 64 == 0)
     lin = [m for m in mods if isinstance(m, nn.Linear)]
@@ -279,6 +308,21 @@ class NonRigidModule(nn.Module):
 
     def forward(self, xyzs_skeleton, dst_posevec, i_iter, R=None, S=None):
         """xyzs_skeleton [B,3,V], dst_posevec [B,69] -> (xyzs_skeleton + offset [B,3,V], R, S)"""
+        lin = [m for m in self.block_mlps if isinstance(m, nn.Linear)]
+        Bp, V = dst_posevec.shape[0], xyzs_skeleton.shape[2]
+        if (xyzs_skeleton.is_cuda and _TC_MLP and Bp * V >= 4096 and xyzs_skeleton.shape[0] in (1, Bp) and self.multires <= 10
+                and not dst_posevec.requires_grad and len(lin) >= 2 and all(m.out_features % 64 == 0 for m in lin[:-1])):
+            # fused input rows (csrc/posenc.cu) -> tensor-core hidden stack -> last layer
+            C, E = dst_posevec.shape[1], 6 * self.multires
+            cols, rows = (C + E + 31) // 32 * 32, (Bp * V + 15) // 16 * 16
+            t = max(float(i_iter) - self.kick_in_iter, 0.0)
+            alpha = self.multires * t / (self.full_band_iter - self.kick_in_iter)
+            h0, enc = _NonRigidInput.apply(xyzs_skeleton, dst_posevec, alpha, self.multires, cols, rows)
+            cat_layers = tuple(sorted(i // 2 for i in self.layers_to_cat_inputs))
+            params = [p for m in lin[:-1] for p in (m.weight, m.bias)]
+            hid = _TcMlpStack.apply(h0, enc, cat_layers, *params)
+            offset = _linear(lin[-1], hid[:Bp * V]).reshape(Bp, V, 3)
+            return xyzs_skeleton + offset.permute(0, 2, 1), R, S
         xyzs = xyzs_skeleton.permute(0, 2, 1)
         B, N, _ = xyzs.shape
         if B != dst_posevec.shape[0]:

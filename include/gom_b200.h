@@ -429,6 +429,28 @@ typedef struct {
 } GomLinearWgradArgs;
 int gom_linear_wgrad(const GomLinearWgradArgs *a, gom_stream_t stream);
 
+/* Input rows of the non-rigid deformation MLP (reference models/modules/non_rigid_module.py:15-72,128-140), one launch each
+ * way: h0[r] = [ posevec[b] (cond) | enc(x_v) (6 multires) | 0 ... ] for r = b V + v, rows >= B V zero, and enc alone;
+ * enc[k 6 + s 3 + d] = w_k (s ? cos : sin)(2^k x_d), w_k = (1 - cos(pi clamp(alpha - k, 0, 1))) / 2 (Hann window, :33-43).
+ * backward: g_xyz from the encoding columns of g_h0 plus g_enc (either nullable); with xyz_frames = 1 the frames add up. */
+typedef struct {
+    int32_t n_frames, n_verts;
+    int32_t xyz_frames;          /* 1 (one canonical vertex set for all frames) or n_frames */
+    int32_t cond, multires;
+    int32_t cols;                /* row length of h0 (>= cond + 6 multires; a multiple of 32 for the GEMM) */
+    int64_t rows_padded;         /* rows of h0 / enc (>= B V; a multiple of 16 for the GEMM) */
+    float alpha;                 /* multires * max(iter - kick_in, 0) / (full_band - kick_in) */
+    int32_t _pad;
+    const float *xyz;            /* [xyz_frames,3,V] */
+    const float *posevec;        /* [B,cond] */
+    float *h0;                   /* [rows_padded, cols] out */
+    float *enc;                  /* [rows_padded, 6 multires] out */
+    const float *g_h0, *g_enc;   /* backward */
+    float *g_xyz;                /* [xyz_frames,3,V] backward */
+} GomNonRigidInputArgs;
+int gom_nonrigid_input_forward(const GomNonRigidInputArgs *a, gom_stream_t stream);
+int gom_nonrigid_input_backward(const GomNonRigidInputArgs *a, gom_stream_t stream);
+
 /* --------------------------------------------------------------------------------------------------------------
  * Evaluation metrics.  Replaces reference eval.py:101-108 (Evaluator.psnr_metric / ssim_metric: skimage 0.18
  * structural_similarity defaults — 7x7 uniform window, sample covariance, K1 .01, K2 .03, data_range 2, 3-px crop)
@@ -671,6 +693,7 @@ size_t gom_sizeof_conv3x3_args(void);
 size_t gom_sizeof_conv_pack_args(void);
 size_t gom_sizeof_tf32_split_args(void);
 size_t gom_sizeof_linear_wgrad_args(void);
+size_t gom_sizeof_nonrigid_input_args(void);
 size_t gom_sizeof_adam_args(void);
 size_t gom_sizeof_mesh_raster_args(void);
 size_t gom_sizeof_vertex_normals_args(void);
