@@ -43,8 +43,47 @@ def default_model_cfg(img_size=(512, 512), sigma=1e-3):
                            appearance=SimpleNamespace(color_init=0.5))
 
 
+class _Rodrigues(torch.autograd.Function):
+    """csrc/rodrigues.cu: the nine entries and their backward in one launch each (torch: ~50 + ~150 elementwise kernels)."""
+
+    @staticmethod
+    def forward(ctx, rvec, group, prepend_identity):
+        from ._lib import GomRodriguesArgs, call, ptr
+        r = rvec.detach().contiguous().float()
+        n = r.shape[0]
+        per = group + int(prepend_identity)
+        R = torch.empty(n // group, per, 3, 3, dtype=torch.float32, device=r.device)
+        ctx.args = dict(n_rot=n, group=group, prepend_identity=int(prepend_identity), eps=1e-5)
+        call("gom_rodrigues_forward", GomRodriguesArgs(rvec=ptr(r), R=ptr(R), **ctx.args))
+        ctx.save_for_backward(r)
+        return R
+
+    @staticmethod
+    def backward(ctx, g):
+        from ._lib import GomRodriguesArgs, call, ptr
+        (r,) = ctx.saved_tensors
+        gc = g.contiguous().float()
+        gr = torch.empty_like(r)
+        call("gom_rodrigues_backward", GomRodriguesArgs(rvec=ptr(r), g_R=ptr(gc), g_rvec=ptr(gr), **ctx.args))
+        return gr, None, None
+
+
+def rodrigues_grouped(rvec, group, prepend_identity=False):
+    """rvec [N,3] (N a multiple of ``group``) -> [N / group, group (+1), 3, 3]; with ``prepend_identity`` every group starts with
+    the identity (the unrefined root joint of reference models/modules/pose_refinement_module.py:39-48)."""
+    if rvec.is_cuda:
+        return _Rodrigues.apply(rvec, int(group), bool(prepend_identity))
+    Rs = rodrigues(rvec).view(-1, group, 3, 3)
+    if prepend_identity:
+        eye = torch.eye(3, device=Rs.device, dtype=Rs.dtype)[None, None].expand(Rs.shape[0], 1, 3, 3)
+        Rs = torch.cat([eye, Rs], dim=1)
+    return Rs
+
+
 def rodrigues(rvec):
     """reference utils/network_util.py:66-92 (RodriguesModule), theta = sqrt(1e-5 + |r|^2); rvec [B,3] -> [B,3,3]."""
+    if rvec.is_cuda:
+        return _Rodrigues.apply(rvec, 1, False).view(-1, 3, 3)
     theta = torch.sqrt(1e-5 + torch.sum(rvec ** 2, dim=1))
     r = rvec / theta[:, None]
     c, s = torch.cos(theta), torch.sin(theta)

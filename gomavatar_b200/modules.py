@@ -355,8 +355,6 @@ class PoseRefinementModule(nn.Module):
         nn.init.zeros_(layers[-1].bias)
 
     def forward(self, dst_posevec, **kwargs):
-        from .model import rodrigues
+        from .model import rodrigues_grouped
         rvec = self.block_mlps(dst_posevec).view(-1, 3)
-        Rs = rodrigues(rvec).view(-1, self.total_bones, 3, 3)
-        eye = torch.eye(3, device=Rs.device, dtype=Rs.dtype)[None, None].expand(Rs.shape[0], 1, 3, 3)
-        return torch.cat([eye, Rs], dim=1)
+        return rodrigues_grouped(rvec, self.total_bones, prepend_identity=True)     # identity in front: pose_refinement_module.py:44-46

@@ -451,6 +451,21 @@ typedef struct {
 int gom_nonrigid_input_forward(const GomNonRigidInputArgs *a, gom_stream_t stream);
 int gom_nonrigid_input_backward(const GomNonRigidInputArgs *a, gom_stream_t stream);
 
+/* Rodrigues formula of reference utils/network_util.py:66-92 (theta = sqrt(eps + |r|^2), eps = 1e-5 there) and its backward.
+ * rvec [n_rot,3] in groups of `group` consecutive rotations (one group per frame); R [n_rot / group, group + prepend_identity,
+ * 3,3]: prepend_identity = 1 puts the identity in front of every group (the root joint of
+ * models/modules/pose_refinement_module.py:39-48).  backward: g_rvec [n_rot,3] from g_R (same shape as R). */
+typedef struct {
+    int32_t n_rot, group, prepend_identity;
+    float eps;
+    const float *rvec;
+    float *R;
+    const float *g_R;
+    float *g_rvec;
+} GomRodriguesArgs;
+int gom_rodrigues_forward(const GomRodriguesArgs *a, gom_stream_t stream);
+int gom_rodrigues_backward(const GomRodriguesArgs *a, gom_stream_t stream);
+
 /* --------------------------------------------------------------------------------------------------------------
  * Evaluation metrics.  Replaces reference eval.py:101-108 (Evaluator.psnr_metric / ssim_metric: skimage 0.18
  * structural_similarity defaults — 7x7 uniform window, sample covariance, K1 .01, K2 .03, data_range 2, 3-px crop)
@@ -694,6 +709,7 @@ size_t gom_sizeof_conv_pack_args(void);
 size_t gom_sizeof_tf32_split_args(void);
 size_t gom_sizeof_linear_wgrad_args(void);
 size_t gom_sizeof_nonrigid_input_args(void);
+size_t gom_sizeof_rodrigues_args(void);
 size_t gom_sizeof_adam_args(void);
 size_t gom_sizeof_mesh_raster_args(void);
 size_t gom_sizeof_vertex_normals_args(void);

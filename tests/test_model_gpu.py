@@ -281,3 +281,26 @@ def test_hot_path_is_cuda_graph_capturable(golden_dir):
     for a, p in zip(got, params):
         ref = p.grad
         assert float((a - ref).abs().max()) <= 1e-4 * float(ref.abs().max()) + 1e-12      # atomics reorder the sums
+
+
+@pytest.mark.parametrize("group,prepend", [(23, True), (1, False), (4, False)])
+def test_rodrigues_kernel_matches_torch_float64(group, prepend):
+    """csrc/rodrigues.cu against the torch formulation of reference utils/network_util.py:66-92 in float64, forward and backward,
+    including rotation vectors at and near zero (theta -> sqrt(1e-5))."""
+    from gomavatar_b200.model import rodrigues_grouped
+    torch.manual_seed(group)
+    n = group * 6
+    r = torch.randn(n, 3) * 0.3
+    r[0] = 0.0
+    r[1] = 1e-6
+    r[2] = torch.tensor([2.5, -1.0, 0.7])
+    ro = r.double().requires_grad_(True)
+    Ro = rodrigues_grouped(ro, group, prepend)                      # CPU tensors take the torch path
+    g = torch.randn(Ro.shape)
+    (Ro * g.double()).sum().backward()
+    rk = r.to(DEV).requires_grad_(True)
+    Rk = rodrigues_grouped(rk, group, prepend)
+    (Rk * g.to(DEV)).sum().backward()
+    assert Rk.shape == Ro.shape
+    assert float((Rk.cpu().double() - Ro).abs().max()) < 2e-6
+    assert float((rk.grad.cpu().double() - ro.grad).abs().max() / ro.grad.abs().max()) < 2e-5
