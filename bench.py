@@ -54,6 +54,9 @@ def parse():
     ap.add_argument("--lpips-torch", action="store_true", help="A/B: plain torch LPIPS glue instead of csrc/lpips.cu")
     ap.add_argument("--lpips-conv", default="tcgen05", choices=["tcgen05", "cudnn"],
                     help="VGG convolutions conv1_2..conv5_3: csrc/conv3x3_tc.cu (default, the product path) or the cuDNN A/B baseline")
+    ap.add_argument("--lpips-streams", type=int, default=1,
+                    help="groups of frames taken through the LPIPS network on separate CUDA streams (a group's HBM-bound tap kernels "
+                         "overlap the other group's tensor-bound convolutions)")
     ap.add_argument("--lpips-epilogue", default="cudnn", choices=["kernel", "cudnn"],
                     help="(--lpips-conv cudnn only) bias+ReLU after each VGG convolution: own kernel, or cuDNN's fused conv-bias-activation")
     ap.add_argument("--no-cuda-graph", dest="cuda_graph", action="store_false",
@@ -200,7 +203,8 @@ class Trainer:
         self.model.train()
         heads = np.load(os.path.join(ROOT, "tests", "golden", "golden_lpips.npz"))
         self.lpips = LPIPS(seeded_random_trunk(0), [heads[f"lin{k}"] for k in range(5)], conv_precision=args.lpips_precision,
-                           fused=not args.lpips_torch, conv_epilogue=args.lpips_epilogue, conv_impl=args.lpips_conv).to(device)
+                           fused=not args.lpips_torch, conv_epilogue=args.lpips_epilogue, conv_impl=args.lpips_conv,
+                           streams=args.lpips_streams).to(device)
         # pool of frames: different poses / cameras / backgrounds per rank
         n_pool = self.B * args.pool_steps
         fr = S.make_frames(scene, n_pool, img_size=(W, H), seed=100 + rank)
@@ -610,6 +614,8 @@ def run_b200(args):
                 extras["b1"] = extra(frames_per_step=1)
             extras["full_model"] = extra(full_model=True)
             extras["full_model"]["note"] = "whole reference-shaped step of exps/zju-mocap_377.yaml (bench.py --full-model)"
+            if B != 1:        # ... and exactly what the reference's train.py runs: the full model at one frame per optimizer step
+                extras["full_model_b1"] = extra(full_model=True, frames_per_step=1)
         elif B % world == 0:  # fixed global batch of B frames split over the ranks (the headline keeps B frames per GPU)
             extras["strong_scaling"] = extra(frames_per_step=B // world)
 

@@ -41,15 +41,24 @@ struct FwdDev {
 };
 
 // ------------------------------------------------------------------------------------------- App. A.3 preprocess
+// Tile counters: the Gaussians of a block are neighbours on the mesh and touch the same few dozen tiles, so the block counts in
+// a shared-memory histogram of the tile grid and adds each non-zero bin to the global counter once (one global atomic per block
+// and tile instead of one per Gaussian and tile: at 220 416 Gaussians the contended global atomics were the whole kernel).
+constexpr int kMaxSmemTiles = 4096;         // tile grids up to 1024 x 1024 pixels; larger images count in global memory directly
+
 __global__ void __launch_bounds__(kThreads) k_preprocess(FwdDev a) {
     __shared__ float cam[34];
+    __shared__ uint32_t s_cnt[kMaxSmemTiles];
     const int b = blockIdx.y;
+    const bool smem_hist = a.T <= kMaxSmemTiles;
     if (threadIdx.x < 16) cam[threadIdx.x] = a.view[b * 16 + threadIdx.x];
     else if (threadIdx.x < 32) cam[threadIdx.x] = a.proj[b * 16 + threadIdx.x - 16];
     else if (threadIdx.x < 34) cam[threadIdx.x] = a.tanfov[b * 2 + threadIdx.x - 32];
+    if (smem_hist)
+        for (int t = threadIdx.x; t < a.T; t += kThreads) s_cnt[t] = 0u;
     __syncthreads();
     const int g = blockIdx.x * kThreads + threadIdx.x;
-    if (g >= a.P) return;
+    if (g < a.P) {
     const float *view = cam, *proj = cam + 16;
     const float tanfovx = cam[32], tanfovy = cam[33];
     const long long o = (long long)b * a.P + g;
@@ -95,7 +104,7 @@ __global__ void __launch_bounds__(kThreads) k_preprocess(FwdDev a) {
                 co = make_float4(xmul(q.c, det_inv), xmul(-q.b, det_inv), xmul(q.a, det_inv),
                                  a.opac[b * a.opac_stride + g]);
                 rc = make_int4(minx, miny, maxx, maxy);
-                uint32_t *cnt = a.tile_count + (long long)b * a.T;
+                uint32_t *cnt = smem_hist ? s_cnt : a.tile_count + (long long)b * a.T;
                 for (int y = miny; y < maxy; y++)
                     for (int x = minx; x < maxx; x++) atomicAdd(cnt + y * a.gx + x, 1u);
             }
@@ -106,6 +115,15 @@ __global__ void __launch_bounds__(kThreads) k_preprocess(FwdDev a) {
     a.xy[o] = pxy;
     a.conic_opacity[o] = co;
     a.rect[o] = rc;
+    }
+    if (smem_hist) {
+        __syncthreads();
+        uint32_t *cnt = a.tile_count + (long long)b * a.T;
+        for (int t = threadIdx.x; t < a.T; t += kThreads) {
+            const uint32_t c = s_cnt[t];
+            if (c) atomicAdd(cnt + t, c);
+        }
+    }
 }
 
 // ------------------------------------------------------------------------- per-frame exclusive scan of tile counts
@@ -154,20 +172,49 @@ __global__ void __launch_bounds__(1024) k_scan_tiles(FwdDev a) {
 
 // ----------------------------------------------------- App. A.4: one (depth,id) key per touched tile, into its segment
 __global__ void __launch_bounds__(kThreads) k_emit(FwdDev a) {
+    __shared__ uint32_t s_cnt[kMaxSmemTiles], s_base[kMaxSmemTiles];
     const int b = blockIdx.y;
     const int g = blockIdx.x * kThreads + threadIdx.x;
-    if (g >= a.P) return;
+    const bool smem_hist = a.T <= kMaxSmemTiles;
     const long long o = (long long)b * a.P + g;
-    const int4 rc = a.rect[o];
-    if (rc.z <= rc.x || rc.w <= rc.y) return;
-    const unsigned long long key = ((unsigned long long)__float_as_uint(a.depth[o]) << 32) | (uint32_t)g;
+    int4 rc = make_int4(0, 0, 0, 0);
+    unsigned long long key = 0ull;
+    if (g < a.P) {
+        rc = a.rect[o];
+        key = ((unsigned long long)__float_as_uint(a.depth[o]) << 32) | (uint32_t)g;
+    }
+    const bool live = rc.z > rc.x && rc.w > rc.y;
     uint32_t *cur = a.tile_cursor + (long long)b * a.T;
     unsigned long long *keys = a.inst_keys + (long long)b * a.cap;
-    for (int y = rc.y; y < rc.w; y++)
-        for (int x = rc.x; x < rc.z; x++) {
-            const uint32_t pos = atomicAdd(cur + y * a.gx + x, 1u);
-            if ((long long)pos < a.cap) keys[pos] = key;
-        }
+    if (!smem_hist) {                                     // huge tile grid: one global atomic per instance
+        if (live)
+            for (int y = rc.y; y < rc.w; y++)
+                for (int x = rc.x; x < rc.z; x++) {
+                    const uint32_t pos = atomicAdd(cur + y * a.gx + x, 1u);
+                    if ((long long)pos < a.cap) keys[pos] = key;
+                }
+        return;
+    }
+    // block-level reservation: count per tile in shared memory, reserve each tile's range with ONE global atomic, then hand
+    // out the slots of the range with shared-memory atomics (order inside a tile's segment is arbitrary anyway: it is sorted next)
+    for (int t = threadIdx.x; t < a.T; t += kThreads) s_cnt[t] = 0u;
+    __syncthreads();
+    if (live)
+        for (int y = rc.y; y < rc.w; y++)
+            for (int x = rc.x; x < rc.z; x++) atomicAdd(&s_cnt[y * a.gx + x], 1u);
+    __syncthreads();
+    for (int t = threadIdx.x; t < a.T; t += kThreads) {
+        const uint32_t c = s_cnt[t];
+        if (c) { s_base[t] = atomicAdd(cur + t, c); s_cnt[t] = 0u; }
+    }
+    __syncthreads();
+    if (live)
+        for (int y = rc.y; y < rc.w; y++)
+            for (int x = rc.x; x < rc.z; x++) {
+                const int t = y * a.gx + x;
+                const uint32_t pos = s_base[t] + atomicAdd(&s_cnt[t], 1u);
+                if ((long long)pos < a.cap) keys[pos] = key;
+            }
 }
 
 // --------------------------------------------------------------------- bitonic network for arbitrary n (in place)

@@ -200,8 +200,15 @@ class _FusedLpips(torch.autograd.Function):
 
 class LPIPS(nn.Module):
     def __init__(self, trunk_state, head_weights, conv_precision="tf32", channels_last=True, fused=True,
-                 conv_epilogue="cudnn", conv_impl="tcgen05"):
+                 conv_epilogue="cudnn", conv_impl="tcgen05", streams=1):
         super().__init__()
+        # streams > 1: the batch is cut into that many groups of frames, each taken through the whole network (forward and,
+        # through autograd, backward) on its own CUDA stream.  The step alternates tensor-bound convolutions (one persistent CTA
+        # per SM, ~200 KB of shared memory, 36 k registers) with HBM-bound tap / input / first-layer kernels (80 registers, no
+        # shared memory): with two groups in flight a group's HBM-bound kernel runs next to the other group's convolution on
+        # the same SMs instead of after it.  Per-image results do not depend on the grouping.
+        self.streams = int(streams)
+        self._side_streams = {}
         self.fused = bool(fused) and conv_precision != "bf16"      # the fused kernels are fp32-only
         assert conv_epilogue in ("kernel", "cudnn")
         assert conv_impl in ("tcgen05", "cudnn")
@@ -290,7 +297,27 @@ class LPIPS(nn.Module):
 
     def per_image(self, pred_nhwc, gt_nhwc, from_unit_range=True):
         """pred / gt contiguous [B,H,W,3] (in [0,1] when from_unit_range, else already in [-1,1]) -> LPIPS values [B]."""
-        return _FusedLpips.apply(pred_nhwc, gt_nhwc, self, from_unit_range)
+        B = pred_nhwc.shape[0]
+        n = min(self.streams, B)
+        if n <= 1 or not pred_nhwc.is_cuda:
+            return _FusedLpips.apply(pred_nhwc, gt_nhwc, self, from_unit_range)
+        dev = pred_nhwc.device
+        if dev not in self._side_streams or len(self._side_streams[dev]) < n:
+            self._side_streams[dev] = [torch.cuda.Stream(device=dev) for _ in range(n)]
+        cur = torch.cuda.current_stream(dev)
+        bounds = [B * i // n for i in range(n + 1)]
+        outs = []
+        for i in range(n):
+            st = self._side_streams[dev][i]
+            st.wait_stream(cur)                                  # fork (inside a CUDA-graph capture: joins the capture)
+            with torch.cuda.stream(st):
+                p, g = pred_nhwc[bounds[i]:bounds[i + 1]], gt_nhwc[bounds[i]:bounds[i + 1]]
+                o = _FusedLpips.apply(p, g, self, from_unit_range)
+                o.record_stream(cur)
+                outs.append(o)
+        for i in range(n):
+            cur.wait_stream(self._side_streams[dev][i])          # join
+        return torch.cat(outs)
 
     def _taps(self, x):
         h = (x - self.shift) / self.scale

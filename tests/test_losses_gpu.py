@@ -268,3 +268,44 @@ def test_first_convolution_kernels_match_torch_fp32(hw, tc):
         call("gom_conv_first_backward", GomConvFirstArgs(n_images=N, height=H, width=W, use_tensor_cores=1, weight=ptr(w), dL_dout=ptr(go),
                                                          dL_dx=ptr(dx2), scratch=ptr(scratch), act=ptr(act)))
         assert torch.equal(dx2, dx)
+
+
+def test_lpips_frame_groups_on_separate_streams_equal_one_stream(golden_dir):
+    """LPIPS(streams=2): the batch is cut into groups of frames that go through the network on their own CUDA streams (forward
+    and, through autograd, backward).  Values and the image gradient must equal the single-stream result (per-image math does
+    not depend on the grouping), eagerly and when the step is captured in a CUDA graph."""
+    from gomavatar_b200.lpips import LPIPS, seeded_random_trunk
+    B, H, W = 5, 48, 40
+    rng = np.random.default_rng(3)
+    x0 = t(rng.random((B, H, W, 3)).astype(np.float32)).to(DEV)
+    x1 = t(rng.random((B, H, W, 3)).astype(np.float32)).to(DEV)
+    wts = t(rng.normal(size=B).astype(np.float32)).to(DEV)
+    res = {}
+    for n in (1, 2):
+        net = LPIPS(seeded_random_trunk(0), _heads(golden_dir), conv_precision="fp32", streams=n).to(DEV)
+        k0 = x0.clone().requires_grad_(True)
+        v = net.per_image(k0, x1, from_unit_range=True)
+        (v * wts).sum().backward()
+        torch.cuda.synchronize()
+        res[n] = (v.detach().clone(), k0.grad.clone())
+    np.testing.assert_allclose(res[2][0].cpu().numpy(), res[1][0].cpu().numpy(), rtol=1e-6)
+    np.testing.assert_allclose(res[2][1].cpu().numpy(), res[1][1].cpu().numpy(), rtol=1e-5, atol=1e-9)
+    # captured: fork / join of the side streams inside the capture
+    net = LPIPS(seeded_random_trunk(0), _heads(golden_dir), conv_precision="fp32", streams=2).to(DEV)
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        k0 = x0.clone().requires_grad_(True)
+        for _ in range(2):
+            k0.grad = None
+            (net.per_image(k0, x1, from_unit_range=True) * wts).sum().backward()
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        k0.grad = None
+        with torch.cuda.graph(g, stream=s):
+            v = net.per_image(k0, x1, from_unit_range=True)
+            (v * wts).sum().backward()
+        k0.grad.zero_()
+        g.replay()
+        torch.cuda.synchronize()
+    np.testing.assert_allclose(v.detach().cpu().numpy(), res[1][0].cpu().numpy(), rtol=1e-6)
+    np.testing.assert_allclose(k0.grad.cpu().numpy(), res[1][1].cpu().numpy(), rtol=1e-5, atol=1e-9)

@@ -11,7 +11,7 @@ sys.path.insert(0, ROOT)
 import bench  # noqa: E402
 
 a = types.SimpleNamespace(gpus=1, steps=2, warmup=1, impl="b200", frames_per_step=8, faces=30000, img=512, pool_steps=2,
-                          lpips_precision="tf32", lpips_torch=False, lpips_epilogue="cudnn", lpips_conv="tcgen05", no_extras=True,
+                          lpips_precision="tf32", lpips_torch=False, lpips_epilogue="cudnn", lpips_conv="tcgen05", lpips_streams=1, no_extras=True,
                           cuda_graph=False, full_model=True, no_cpu_baseline=True, cpu_frames=1)
 dev = torch.device("cuda:0")
 tr = bench.Trainer(a, 0, 1, dev)
