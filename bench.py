@@ -204,7 +204,7 @@ class Trainer:
         heads = np.load(os.path.join(ROOT, "tests", "golden", "golden_lpips.npz"))
         self.lpips = LPIPS(seeded_random_trunk(0), [heads[f"lin{k}"] for k in range(5)], conv_precision=args.lpips_precision,
                            fused=not args.lpips_torch, conv_epilogue=args.lpips_epilogue, conv_impl=args.lpips_conv,
-                           streams=args.lpips_streams).to(device)
+                           streams=getattr(args, "lpips_streams", 1)).to(device)
         # pool of frames: different poses / cameras / backgrounds per rank
         n_pool = self.B * args.pool_steps
         fr = S.make_frames(scene, n_pool, img_size=(W, H), seed=100 + rank)

@@ -188,6 +188,11 @@ class GomRodriguesArgs(ctypes.Structure):
                 ("R", c_void_p), ("g_R", c_void_p), ("g_rvec", c_void_p)]
 
 
+class GomNarrowLinearArgs(ctypes.Structure):
+    _fields_ = [("rows", c_int64), ("c_in", c_int32), ("n_out", c_int32), ("x", c_void_p), ("weight", c_void_p), ("bias", c_void_p),
+                ("y", c_void_p), ("g_y", c_void_p), ("g_x", c_void_p), ("g_weight", c_void_p), ("g_bias", c_void_p)]
+
+
 class GomVertexNormalsArgs(ctypes.Structure):
     _fields_ = [("n_frames", c_int32), ("n_verts", c_int32), ("n_faces", c_int32), ("faces_int64", c_int32), ("verts", c_void_p),
                 ("faces", c_void_p), ("E", c_void_p), ("acc", c_void_p), ("normals_cam", c_void_p), ("dL_dnormals_cam", c_void_p),
@@ -238,6 +243,7 @@ EXPORTS = [
     "gom_sizeof_tf32_split_args", "gom_linear_wgrad", "gom_sizeof_linear_wgrad_args",
     "gom_nonrigid_input_forward", "gom_nonrigid_input_backward", "gom_sizeof_nonrigid_input_args",
     "gom_rodrigues_forward", "gom_rodrigues_backward", "gom_sizeof_rodrigues_args",
+    "gom_narrow_linear_forward", "gom_narrow_linear_backward", "gom_sizeof_narrow_linear_args",
     "gom_adam_step", "gom_sizeof_adam_args",
     "gom_mesh_raster_forward", "gom_mesh_raster_backward", "gom_sizeof_mesh_raster_args",
     "gom_vertex_normals_forward", "gom_vertex_normals_backward", "gom_ndc_forward", "gom_ndc_backward", "gom_dilated_mask_l1",
@@ -255,7 +261,7 @@ _STRUCTS = {
     "lpips_tap": GomLpipsTapArgs, "eval_metrics": GomEvalMetricsArgs,
     "conv_first": GomConvFirstArgs, "adam": GomAdamArgs,
     "conv3x3": GomConv3x3Args, "conv_pack": GomConvPackArgs, "tf32_split": GomTf32SplitArgs,
-    "linear_wgrad": GomLinearWgradArgs, "nonrigid_input": GomNonRigidInputArgs, "rodrigues": GomRodriguesArgs,
+    "linear_wgrad": GomLinearWgradArgs, "nonrigid_input": GomNonRigidInputArgs, "rodrigues": GomRodriguesArgs, "narrow_linear": GomNarrowLinearArgs,
     "mesh_raster": GomMeshRasterArgs, "vertex_normals": GomVertexNormalsArgs, "ndc": GomNdcArgs,
     "dilated_mask_l1": GomDilatedMaskL1Args, "shadow_mlp": GomShadowMlpArgs, "mesh_reg": GomMeshRegArgs,
 }
@@ -265,7 +271,7 @@ _ENTRY_POINTS = ["gom_camera_from_KE", "gom_raster_forward", "gom_raster_backwar
                  "gom_lpips_input_forward", "gom_lpips_input_backward", "gom_bias_relu", "gom_relu_backward",
                  "gom_lpips_tap_forward", "gom_lpips_tap_backward", "gom_eval_metrics",
                  "gom_conv_first_forward", "gom_conv_first_backward", "gom_adam_step",
-                 "gom_conv3x3", "gom_conv3x3_pack_weights", "gom_tf32_split", "gom_linear_wgrad", "gom_nonrigid_input_forward", "gom_nonrigid_input_backward", "gom_rodrigues_forward", "gom_rodrigues_backward",
+                 "gom_conv3x3", "gom_conv3x3_pack_weights", "gom_tf32_split", "gom_linear_wgrad", "gom_nonrigid_input_forward", "gom_nonrigid_input_backward", "gom_rodrigues_forward", "gom_rodrigues_backward", "gom_narrow_linear_forward", "gom_narrow_linear_backward",
                  "gom_mesh_raster_forward", "gom_mesh_raster_backward", "gom_vertex_normals_forward", "gom_vertex_normals_backward",
                  "gom_ndc_forward", "gom_ndc_backward", "gom_dilated_mask_l1", "gom_shadow_mlp_forward", "gom_shadow_mlp_backward",
                  "gom_mesh_regularizers"]

@@ -88,7 +88,40 @@ class _Linear(torch.autograd.Function):
         return gx, gw, gb
 
 
+class _NarrowLinear(torch.autograd.Function):
+    """A Linear layer with 1 .. 4 outputs over a tall batch of rows (the non-rigid MLP's 128 -> 3 output layer) as one pass over
+    the rows each way (csrc/narrow_linear.cu) instead of three SIMT cuBLAS GEMMs."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        from ._lib import GomNarrowLinearArgs, call, ptr
+        xc, w = x.detach().contiguous().float(), weight.detach().contiguous().float().clone()      # clone: 16-byte aligned (arena views are not)
+        b = None if bias is None else bias.detach().contiguous().float()
+        R, C = xc.shape
+        y = torch.empty(R, w.shape[0], dtype=torch.float32, device=xc.device)
+        call("gom_narrow_linear_forward", GomNarrowLinearArgs(rows=R, c_in=C, n_out=w.shape[0], x=ptr(xc), weight=ptr(w), bias=ptr(b), y=ptr(y)))
+        ctx.save_for_backward(xc, w)
+        ctx.has_bias = bias is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        from ._lib import GomNarrowLinearArgs, call, ptr
+        xc, w = ctx.saved_tensors
+        R, C = xc.shape
+        gc = g.contiguous().float()
+        gx = torch.empty_like(xc) if ctx.needs_input_grad[0] else None
+        gw = torch.empty_like(w)
+        gb = torch.empty(w.shape[0], dtype=torch.float32, device=xc.device) if ctx.has_bias else None
+        call("gom_narrow_linear_backward", GomNarrowLinearArgs(rows=R, c_in=C, n_out=w.shape[0], x=ptr(xc), weight=ptr(w), g_y=ptr(gc), g_x=ptr(gx),
+                                                               g_weight=ptr(gw), g_bias=ptr(gb)))
+        return gx, gw, gb
+
+
 def _linear(m, h):
+    if (h.is_cuda and _TC_MLP and h.dim() == 2 and h.shape[0] >= 4096 and m.out_features <= 4 and h.shape[1] % 4 == 0
+            and h.shape[1] <= 256 and (h.data_ptr() % 16) == 0):
+        return _NarrowLinear.apply(h, m.weight, m.bias)
     if h.is_cuda and h.dim() >= 2 and h.numel() // h.shape[-1] >= 4096 and torch.is_grad_enabled():
         return _Linear.apply(h.reshape(-1, h.shape[-1]), m.weight, m.bias).reshape(*h.shape[:-1], m.out_features)
     return m(h)

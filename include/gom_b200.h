@@ -466,6 +466,24 @@ typedef struct {
 int gom_rodrigues_forward(const GomRodriguesArgs *a, gom_stream_t stream);
 int gom_rodrigues_backward(const GomRodriguesArgs *a, gom_stream_t stream);
 
+/* Linear layer with 1 .. 4 outputs over a tall batch of rows (the 128 -> 3 output layer of reference
+ * models/modules/non_rigid_module.py:112-118): y = x W^T + b; backward: g_x = g_y W (nullable), g_weight = g_y^T x and
+ * g_bias = column sums of g_y (both zeroed first).  x [rows, c_in] row-major, c_in a multiple of 4, at most 256. */
+typedef struct {
+    int64_t rows;
+    int32_t c_in, n_out;
+    const float *x;              /* [rows, c_in] */
+    const float *weight;         /* [n_out, c_in] */
+    const float *bias;           /* [n_out] nullable */
+    float *y;                    /* [rows, n_out] (forward) */
+    const float *g_y;            /* [rows, n_out] (backward) */
+    float *g_x;                  /* [rows, c_in] (backward, nullable) */
+    float *g_weight;             /* [n_out, c_in] (backward) */
+    float *g_bias;               /* [n_out] (backward, nullable) */
+} GomNarrowLinearArgs;
+int gom_narrow_linear_forward(const GomNarrowLinearArgs *a, gom_stream_t stream);
+int gom_narrow_linear_backward(const GomNarrowLinearArgs *a, gom_stream_t stream);
+
 /* --------------------------------------------------------------------------------------------------------------
  * Evaluation metrics.  Replaces reference eval.py:101-108 (Evaluator.psnr_metric / ssim_metric: skimage 0.18
  * structural_similarity defaults — 7x7 uniform window, sample covariance, K1 .01, K2 .03, data_range 2, 3-px crop)
@@ -710,6 +728,7 @@ size_t gom_sizeof_tf32_split_args(void);
 size_t gom_sizeof_linear_wgrad_args(void);
 size_t gom_sizeof_nonrigid_input_args(void);
 size_t gom_sizeof_rodrigues_args(void);
+size_t gom_sizeof_narrow_linear_args(void);
 size_t gom_sizeof_adam_args(void);
 size_t gom_sizeof_mesh_raster_args(void);
 size_t gom_sizeof_vertex_normals_args(void);

@@ -99,3 +99,25 @@ def test_linear_wgrad_kernel_matches_float64(R, N):
     gw2 = C.linear_wgrad(g, g_lo, x, x_lo, out=gw.clone(), accumulate=True)
     assert float(((gw2.double() - 2 * ref).abs() / scale).max()) < 4e-6
     assert float((gb.double() - g.double().sum(0)).abs().max() / g.double().abs().sum(0).max()) < 1e-5
+
+
+@pytest.mark.parametrize("R,C,n_out", [(4096, 128, 3), (120272, 128, 3), (5001, 64, 1), (7000, 256, 4), (4100, 132, 2)])
+def test_narrow_linear_kernels_match_float64(R, C, n_out):
+    """csrc/narrow_linear.cu (the 128 -> 3 output layer of the non-rigid MLP, reference non_rigid_module.py:112-118) against
+    torch in float64: forward, input / weight / bias gradients."""
+    from gomavatar_b200.modules import _NarrowLinear
+    torch.manual_seed(R + C)
+    x = torch.randn(R, C, device=DEV)
+    w = torch.randn(n_out, C, device=DEV) * 0.1
+    b = torch.randn(n_out, device=DEV)
+    g = torch.randn(R, n_out, device=DEV)
+    xo, wo, bo = x.double().requires_grad_(True), w.double().requires_grad_(True), b.double().requires_grad_(True)
+    yo = xo @ wo.T + bo
+    (yo * g.double()).sum().backward()
+    xk, wk, bk = x.clone().requires_grad_(True), w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    yk = _NarrowLinear.apply(xk, wk, bk)
+    (yk * g).sum().backward()
+    assert _rel(yk.detach(), yo.detach()) < 1e-5
+    assert _rel(xk.grad, xo.grad) < 1e-5
+    assert _rel(wk.grad, wo.grad) < 2e-5
+    assert _rel(bk.grad, bo.grad) < 2e-5
