@@ -170,6 +170,10 @@ k_conv3x3(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
     const uint32_t tmem = tmem_slot;
     volatile int *ab = &abort_flag;
     const int items_per_tile = p.n_pass * p.c_blocks;             // halo loads per tile; each is followed by 9 weight tiles
+    // programmatic dependent launch: this CTA may have become resident (and done the set-up above) while the previous kernel
+    // of the stream was still draining; nothing below may touch global memory before that kernel has completed
+    gom_pdl_trigger();
+    gom_pdl_wait();
 
     if (warp == 0) {
         // ------------------------------------------------------------------------------------------- TMA producer
@@ -403,6 +407,8 @@ __global__ void k_pack_weights(GomConvPackArgs a) {
 // After a K-split convolution: out <- act(out + bias), ReLU bit mask written / applied.  One thread per pixel and 32 channels.
 struct FinishDev { long long n_words; int words_per_pixel, relu; float *out; const float *bias; const uint32_t *mask_in; uint32_t *mask_out; };
 __global__ void __launch_bounds__(256) k_conv_finish(FinishDev a) {
+    gom_pdl_trigger();
+    gom_pdl_wait();
     const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
     if (i >= a.n_words) return;
     const int wi = (int)(i % a.words_per_pixel);
@@ -528,11 +534,11 @@ int launch_conv(const GomConv3x3Args *p, ConvDev &d, cudaStream_t stream) {
     const int grid = d.n_tiles < g_sms ? d.n_tiles : g_sms;
     const size_t out_elems = (size_t)p->n_images * p->height * p->width * p->c_out;
     if (d.k_splits > 1) GOM_CUDA(cudaMemsetAsync(p->out, 0, out_elems * sizeof(float), stream));
-    k_conv3x3<NT, SUB, TPS, BST, TAPS><<<grid, Cfg::THREADS, Cfg::SMEM, stream>>>(ma, malo, mb, mo, d);
+    GOM_CUDA(gom_launch_pdl(k_conv3x3<NT, SUB, TPS, BST, TAPS>, dim3(grid), dim3(Cfg::THREADS), Cfg::SMEM, stream, ma, malo, mb, mo, d));
     GOM_LAUNCH_CHECK();
     if (d.k_splits > 1) {
         FinishDev f{(long long)(out_elems / 32), p->c_out / 32, p->relu, p->out, p->bias, p->mask_in, p->mask_out};
-        k_conv_finish<<<gom_div_up(f.n_words, 256), 256, 0, stream>>>(f);
+        GOM_CUDA(gom_launch_pdl(k_conv_finish, dim3(gom_div_up(f.n_words, 256)), dim3(256), 0, stream, f));
         GOM_LAUNCH_CHECK();
     }
     return GOM_OK;

@@ -93,6 +93,8 @@ __global__ void __launch_bounds__(Conv1Cfg<MODE>::THREADS, 1) k_conv1_gemm(Conv1
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    gom_pdl_trigger();            // programmatic dependent launch (gom_common.cuh): the set-up above only read weights
+    gom_pdl_wait();
     const uint32_t tmem = tmem_slot;
     const long long n_tiles = (a.rows + kTileRows - 1) / kTileRows;
     const long long stride = (long long)gridDim.x * G;
@@ -251,6 +253,8 @@ __global__ void __launch_bounds__(Conv1Cfg<MODE>::THREADS, 1) k_conv1_gemm(Conv1
 
 // dX[q, c] = sum over the 9 taps (r,s) of T[(r,s)][q - (r-1, s-1)].c   (pixels outside the image contribute nothing)
 __global__ void __launch_bounds__(256) k_conv1_stencil(Conv1Dev a) {
+    gom_pdl_trigger();
+    gom_pdl_wait();
     const long long q = (long long)blockIdx.x * 256 + threadIdx.x;
     if (q >= a.rows) return;
     const long long HW = (long long)a.H * a.W;
@@ -294,7 +298,7 @@ int gom_conv_first_forward_tc(const GomConvFirstArgs *p, cudaStream_t stream) {
     a.N = p->n_images; a.H = p->height; a.W = p->width; a.rows = (long long)a.N * a.H * a.W;
     a.x = p->x; a.weight = p->weight; a.bias = p->bias; a.out = p->out; a.status = nullptr;
     gom_prof_begin(GOM_PROF_CONV_FIRST_FWD, stream);
-    k_conv1_gemm<0><<<g_conv1_sms, Conv1Cfg<0>::THREADS, Conv1Cfg<0>::DYN_SMEM, stream>>>(a);
+    GOM_CUDA(gom_launch_pdl(k_conv1_gemm<0>, dim3(g_conv1_sms), dim3(Conv1Cfg<0>::THREADS), Conv1Cfg<0>::DYN_SMEM, stream, a));
     GOM_LAUNCH_CHECK();
     gom_prof_end(GOM_PROF_CONV_FIRST_FWD, stream);
     return GOM_OK;
@@ -309,9 +313,9 @@ int gom_conv_first_backward_tc(const GomConvFirstArgs *p, cudaStream_t stream) {
     a.weight = p->weight; a.dY = p->dL_dout; a.act = p->act; a.T = p->scratch; a.dX = p->dL_dx; a.status = nullptr;
     GOM_REQUIRE(((uintptr_t)p->act % 16) == 0, "act must be 16-byte aligned");
     gom_prof_begin(GOM_PROF_CONV_FIRST_BWD, stream);
-    k_conv1_gemm<1><<<g_conv1_sms, Conv1Cfg<1>::THREADS, Conv1Cfg<1>::DYN_SMEM, stream>>>(a);
+    GOM_CUDA(gom_launch_pdl(k_conv1_gemm<1>, dim3(g_conv1_sms), dim3(Conv1Cfg<1>::THREADS), Conv1Cfg<1>::DYN_SMEM, stream, a));
     GOM_LAUNCH_CHECK();
-    k_conv1_stencil<<<gom_div_up(a.rows, 256), 256, 0, stream>>>(a);
+    GOM_CUDA(gom_launch_pdl(k_conv1_stencil, dim3(gom_div_up(a.rows, 256)), dim3(256), 0, stream, a));
     GOM_LAUNCH_CHECK();
     gom_prof_end(GOM_PROF_CONV_FIRST_BWD, stream);
     return GOM_OK;

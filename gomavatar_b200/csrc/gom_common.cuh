@@ -55,6 +55,33 @@ void gom_prof_end(int slot, cudaStream_t stream);
 
 static inline int gom_div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
+// ------------------------------------------------------------------------- programmatic dependent launch (PDL)
+// The step is a chain of ~60 (one frame) kernels in one stream / CUDA graph; each boundary costs the drain of the previous
+// grid plus the launch and prologue of the next (barrier init, tensor-memory allocation, tensor-map fetch: ~5 us for the
+// persistent tcgen05 kernels).  A kernel launched with `gom_launch_pdl` may become resident as soon as every CTA of the
+// previous kernel has executed `gom_pdl_trigger()` (or exited) and SM resources are free, runs its prologue, and blocks in
+// `gom_pdl_wait()` until the previous grid has completed and its writes are visible.  Rules used throughout: trigger at kernel
+// entry; wait before the first global-memory access of any kind other than kernel parameters / weights (reads of produced data
+// and ALL writes: an output buffer may be recycled memory the previous kernel still reads).  Launches without the attribute,
+// memsets and copies keep full stream order, so a kernel that triggers is safe in front of anything.  Opt-in (GOM_PDL=1): measured
+// slower than plain stream order on the LPIPS chain (gom_core.cu), kept for experiments.
+#ifdef __CUDACC__
+__device__ __forceinline__ void gom_pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void gom_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#endif
+bool gom_pdl_enabled(void);
+template <typename... KArgs, typename... Args>
+static inline cudaError_t gom_launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args &&...args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = gom_pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 // ------------------------------------------------------------------------------- exactly-rounded fp32 arithmetic
 // Every integer decision of the rasterizer (cull, radius, tile rect, depth key) is computed with individually
 // rounded fp32 operations in a fixed association order, so that it is bit-identical to the CPU oracle

@@ -20,6 +20,14 @@ extern "C" const char *gom_last_error(void) { return g_err; }
 #include <vector>
 static std::atomic<long long> g_launches{0};
 void gom_count_launch(void) { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+#include <stdlib.h>
+bool gom_pdl_enabled(void) {
+    // measured on B200 (bench.py, whole step in one CUDA graph): 7.73 -> 7.99 ms at 8 frames, 1.636 -> 1.665 ms at one frame with
+    // the attribute on the LPIPS chain — the early-resident CTAs cost more than the hidden prologues — so it is opt-in
+    static const bool on = [] { const char *e = getenv("GOM_PDL"); return e && e[0] == '1'; }();
+    return on;
+}
 extern "C" long long gom_launch_count(void) { return g_launches.load(); }
 
 struct ProfSlot { std::vector<cudaEvent_t> ev; size_t used = 0; };

@@ -26,6 +26,8 @@ __constant__ float c_scale[3] = {.458f, .448f, .450f};
 
 __global__ void __launch_bounds__(kThreads) k_lpips_input_fwd(const float *pred, const float *gt, float *out,
                                                               long long n_half, float mul, float add) {
+    gom_pdl_trigger();            // programmatic dependent launch (gom_common.cuh)
+    gom_pdl_wait();
     // n_half = B*H*W*3 elements per half; out = [pred half | gt half]
     for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < 2 * n_half; i += (long long)gridDim.x * kThreads) {
         const float v = i < n_half ? pred[i] : gt[i - n_half];
@@ -35,6 +37,8 @@ __global__ void __launch_bounds__(kThreads) k_lpips_input_fwd(const float *pred,
 }
 
 __global__ void __launch_bounds__(kThreads) k_lpips_input_bwd(const float *g, float *d_pred, long long n_half, float mul) {
+    gom_pdl_trigger();
+    gom_pdl_wait();
     for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < n_half; i += (long long)gridDim.x * kThreads)
         d_pred[i] = g[i] * mul / c_scale[(int)(i % 3)];
 }
@@ -132,6 +136,8 @@ template <int LPP> __device__ __forceinline__ float group_sum(float a) {
 template <int C>
 __global__ void __launch_bounds__(kThreads) k_lpips_tap_fwd(TapDev a) {
     using L = TL<C>;
+    gom_pdl_trigger();
+    gom_pdl_wait();
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int grp = lane / L::LPP, sl = lane % L::LPP;
     const int b = blockIdx.y;
@@ -250,6 +256,8 @@ __global__ void __launch_bounds__(kThreads) k_lpips_tap_fwd(TapDev a) {
 template <int C>
 __global__ void __launch_bounds__(kThreads) k_lpips_tap_bwd(TapDev a) {
     using L = TL<C>;
+    gom_pdl_trigger();
+    gom_pdl_wait();
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int grp = lane / L::LPP, sl = lane % L::LPP;
     const int b = blockIdx.y;
@@ -354,6 +362,8 @@ __global__ void __launch_bounds__(kThreads) k_lpips_tap_bwd(TapDev a) {
 template <int C>
 __global__ void __launch_bounds__(kThreads) k_lpips_tap_bwd_pf(TapDev a) {
     using L = TL<C>;
+    gom_pdl_trigger();
+    gom_pdl_wait();
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int grp = lane / L::LPP, sl = lane % L::LPP;
     const int b = blockIdx.y;
@@ -493,10 +503,10 @@ template <int C> int launch_tap(const TapDev &d, bool bwd, cudaStream_t stream) 
     if (gx < 1) gx = 1;
     dim3 grid(gx, d.B);
     if (bwd) {
-        if constexpr (TL<C>::CPL * TL<C>::NIT <= 16) k_lpips_tap_bwd_pf<C><<<grid, kThreads, 0, stream>>>(d);
-        else k_lpips_tap_bwd<C><<<grid, kThreads, 0, stream>>>(d);
+        if constexpr (TL<C>::CPL * TL<C>::NIT <= 16) GOM_CUDA(gom_launch_pdl(k_lpips_tap_bwd_pf<C>, grid, dim3(kThreads), 0, stream, d));
+        else GOM_CUDA(gom_launch_pdl(k_lpips_tap_bwd<C>, grid, dim3(kThreads), 0, stream, d));
     }
-    else k_lpips_tap_fwd<C><<<grid, kThreads, 0, stream>>>(d);
+    else GOM_CUDA(gom_launch_pdl(k_lpips_tap_fwd<C>, grid, dim3(kThreads), 0, stream, d));
     GOM_LAUNCH_CHECK();
     return GOM_OK;
 }
@@ -527,8 +537,8 @@ extern "C" int gom_lpips_input_forward(const GomLpipsInputArgs *p, gom_stream_t 
     cudaStream_t stream = (cudaStream_t)stream_;
     const long long n_half = 3LL * p->n_frames * p->height * p->width;
     gom_prof_begin(GOM_PROF_LPIPS_INPUT, stream);
-    k_lpips_input_fwd<<<grid_for(2 * n_half, kThreads * 4), kThreads, 0, stream>>>(
-        p->pred, p->gt, p->out, n_half, p->from_unit_range ? 2.f : 1.f, p->from_unit_range ? -1.f : 0.f);
+    GOM_CUDA(gom_launch_pdl(k_lpips_input_fwd, dim3(grid_for(2 * n_half, kThreads * 4)), dim3(kThreads), 0, stream,
+                            p->pred, p->gt, p->out, n_half, p->from_unit_range ? 2.f : 1.f, p->from_unit_range ? -1.f : 0.f));
     GOM_LAUNCH_CHECK();
     gom_prof_end(GOM_PROF_LPIPS_INPUT, stream);
     return GOM_OK;
@@ -541,8 +551,8 @@ extern "C" int gom_lpips_input_backward(const GomLpipsInputArgs *p, gom_stream_t
     cudaStream_t stream = (cudaStream_t)stream_;
     const long long n_half = 3LL * p->n_frames * p->height * p->width;
     gom_prof_begin(GOM_PROF_LPIPS_INPUT, stream);
-    k_lpips_input_bwd<<<grid_for(n_half, kThreads * 4), kThreads, 0, stream>>>(p->dL_dout, p->dL_dpred, n_half,
-                                                                              p->from_unit_range ? 2.f : 1.f);
+    GOM_CUDA(gom_launch_pdl(k_lpips_input_bwd, dim3(grid_for(n_half, kThreads * 4)), dim3(kThreads), 0, stream, p->dL_dout, p->dL_dpred, n_half,
+                            p->from_unit_range ? 2.f : 1.f));
     GOM_LAUNCH_CHECK();
     gom_prof_end(GOM_PROF_LPIPS_INPUT, stream);
     return GOM_OK;
