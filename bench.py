@@ -57,6 +57,8 @@ def parse():
     ap.add_argument("--lpips-streams", type=int, default=1,
                     help="groups of frames taken through the LPIPS network on separate CUDA streams (a group's HBM-bound tap kernels "
                          "overlap the other group's tensor-bound convolutions)")
+    ap.add_argument("--side-stream", action="store_true",
+                    help="(--full-model) run the mesh normal-map / shadow branch on a side stream next to the splat branch (no gain measured)")
     ap.add_argument("--lpips-epilogue", default="cudnn", choices=["kernel", "cudnn"],
                     help="(--lpips-conv cudnn only) bias+ReLU after each VGG convolution: own kernel, or cuDNN's fused conv-bias-activation")
     ap.add_argument("--no-cuda-graph", dest="cuda_graph", action="store_false",
@@ -185,6 +187,7 @@ class Trainer:
                              "normal": {"mask_dilate": True, "kernel_size": 7, "coeff_mask": 1.0, "coeff_consist": 0.10},
                              "color_consist": {"coeff": 0.050}}
             self.model = Model(cfg, scene.canonical_info(), strict_raster=False).to(device)
+            self.model.mesh_side_stream = bool(getattr(args, "side_stream", False))
             self.model.normal_renderer.strict = False             # overflow flags stay on the device (graph capture)
             self.model.normal_renderer.capacity = 16 * args.faces
             self.model.shadow_module.strict = False

@@ -186,6 +186,13 @@ class Model(nn.Module):
         self.strict_raster = strict_raster
         self.last_raster_aux = None             # {'status', 'tile_offset', 'inst_capacity'} of the latest forward
         self.keep_raster_aux = False            # True: keep every intermediate raster buffer there (tests / debugging)
+        # The mesh branch (vertex normals -> normal map + soft silhouette -> shadow MLP) and the splat branch (face Gaussians ->
+        # rasterizer) both start from the posed vertices and meet at `rgbs = albedos * shadings`: on a CUDA device the mesh branch
+        # can run on a side stream (forward and, through autograd, backward); inside a CUDA-graph capture the side stream forks from /
+        # joins the capturing stream.  Measured (bench.py --full-model): 2.78 -> 2.75 ms at one frame, 10.53 -> 10.60 ms at 8 frames —
+        # within the noise, so it is off by default.
+        self.mesh_side_stream = False
+        self._side_streams = {}
 
     def forward(self, K, E, cnl_gtfms, dst_Rs, dst_Ts, dst_posevec=None, canonical_joints=None,
                 i_iter=1e7, bgcolor=None, global_R=None, global_T=None, tb=None):
@@ -211,6 +218,22 @@ class Model(nn.Module):
             gT = global_T.reshape(-1, 3)
             vertices_observation = Rg @ vertices_observation + gT[:, :, None]
 
+        normal = normal_mask = shadings = None
+        mesh_branch = self.normal_renderer is not None and self.shadow_module is not None
+        side = None
+        if mesh_branch and self.mesh_side_stream and vertices_observation.is_cuda:
+            dev = vertices_observation.device
+            if dev not in self._side_streams:
+                self._side_streams[dev] = torch.cuda.Stream(device=dev)
+            side, cur = self._side_streams[dev], torch.cuda.current_stream(dev)
+            side.wait_stream(cur)                                  # fork
+            with torch.cuda.stream(side):
+                normal, normal_mask, shadings = self._mesh_branch(vertices_observation, K, E, B, H, W)
+                for t_ in (normal, normal_mask, shadings):
+                    if t_ is not None:
+                        t_.record_stream(cur)
+            vertices_observation.record_stream(side)
+
         means3D, cov3D = face_gaussians(vertices_observation, self.faces, self.so3, self.scale, sigma)
         appearance, bg_feat = self.appearance_module()
         colors = torch.cat([appearance.permute(1, 0), torch.ones_like(appearance[:1]).permute(1, 0)], dim=1)   # [F,4]
@@ -225,12 +248,11 @@ class Model(nn.Module):
         self.last_raster_aux = aux if self.keep_raster_aux else {k: aux[k] for k in ("status", "tile_offset", "inst_capacity")}
         albedos, masks = rgba[..., :3], rgba[..., 3]
 
-        normal = normal_mask = shadings = None
-        if self.normal_renderer is not None and self.shadow_module is not None:     # reference model.py:271-287
-            from .mesh_renderer import vertex_normals_cam
-            normals = vertex_normals_cam(vertices_observation, self.faces, E)        # model.py:271-273 in one launch each way
-            normal, normal_mask = self.normal_renderer(vertices_observation, normals, K, E, faces=self.faces)
-            shadings = self.shadow_module(normal.reshape(B, H * W, 3)).reshape(B, H, W, 1) * 2
+        if mesh_branch:                                                            # reference model.py:271-287
+            if side is not None:
+                torch.cuda.current_stream(vertices_observation.device).wait_stream(side)      # join
+            else:
+                normal, normal_mask, shadings = self._mesh_branch(vertices_observation, K, E, B, H, W)
             rgbs = albedos * shadings
         else:
             rgbs = albedos
@@ -299,6 +321,14 @@ class Model(nn.Module):
 
     def get_lbs_weights(self):
         return self.lbs_weights
+
+    def _mesh_branch(self, vertices_observation, K, E, B, H, W):
+        """reference model.py:271-280: camera-space vertex normals -> normal map (+ soft silhouette) -> pseudo-shading"""
+        from .mesh_renderer import vertex_normals_cam
+        normals = vertex_normals_cam(vertices_observation, self.faces, E)            # model.py:271-273 in one launch each way
+        normal, normal_mask = self.normal_renderer(vertices_observation, normals, K, E, faces=self.faces)
+        shadings = self.shadow_module(normal.reshape(B, H * W, 3)).reshape(B, H, W, 1) * 2
+        return normal, normal_mask, shadings
 
     def _vertex_normals(self, verts_b3v):
         """PyTorch3D ``Meshes.verts_normals_padded`` semantics: area-weighted face normals
