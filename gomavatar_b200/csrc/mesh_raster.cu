@@ -173,39 +173,56 @@ __device__ __forceinline__ float edge_fn(float px, float py, float ax, float ay,
     return (px - ax) * (by - ay) - (py - ay) * (bx - ax);
 }
 
-// squared distance to segment (a, b); also the clamped parameter and whether the segment is degenerate
-__device__ __forceinline__ float seg_dist2(float px, float py, float ax, float ay, float bx, float by, float &tt, bool &degenerate) {
+// reciprocal squared length of edge (a, b), or -1 for a degenerate edge (PyTorch3D PointLineDistanceForward: l2 <= kEpsilon)
+__device__ __forceinline__ float inv_len2(float ax, float ay, float bx, float by) {
+    const float dx = bx - ax, dy = by - ay, l2 = dx * dx + dy * dy;
+    return l2 <= kEpsArea ? -1.f : 1.f / l2;
+}
+
+// squared distance to segment (a, b) with the reciprocal squared length prepared (il < 0: degenerate -> distance to b)
+__device__ __forceinline__ float seg_dist2_pre(float px, float py, float ax, float ay, float bx, float by, float il, float &tt) {
+    if (il < 0.f) { tt = 1.f; return (px - bx) * (px - bx) + (py - by) * (py - by); }
     const float dx = bx - ax, dy = by - ay;
-    const float l2 = dx * dx + dy * dy;
-    degenerate = l2 <= kEpsArea;
-    if (degenerate) { tt = 1.f; return (px - bx) * (px - bx) + (py - by) * (py - by); }
-    const float t = ((px - ax) * dx + (py - ay) * dy) / l2;
-    tt = fminf(fmaxf(t, 0.f), 1.f);
+    tt = fminf(fmaxf(((px - ax) * dx + (py - ay) * dy) * il, 0.f), 1.f);
     const float qx = ax + tt * dx, qy = ay + tt * dy;
     return (px - qx) * (px - qx) + (py - qy) * (py - qy);
 }
 
-// PyTorch3D CheckPixelInsideFace up to the queue insertion.  Returns false when the face does not count for the pixel.
+// PyTorch3D CheckPixelInsideFace after the bounding-box test, on a face with its reciprocals prepared (ia = 1 / (area + eps),
+// il** = inv_len2 of the three edges).  ONE definition for every kernel of this file: the backward replays the forward's
+// K-nearest cut by comparing recomputed depths with the stored one, so the arithmetic must be the same instruction for
+// instruction.  Returns false when the face does not count for the pixel.
+__device__ __forceinline__ bool pixel_face_core(float px, float py, float ax, float ay, float az, float bx, float by, float bz, float cx,
+                                                float cy, float cz, float ia, float il01, float il02, float il12, float blur, float &pz,
+                                                bool &inside, float &dist, int &edge, float &tt) {
+    const float w0 = edge_fn(px, py, bx, by, cx, cy) * ia;
+    const float w1 = edge_fn(px, py, cx, cy, ax, ay) * ia;
+    const float w2 = edge_fn(px, py, ax, ay, bx, by) * ia;
+    pz = w0 * az + w1 * bz + w2 * cz;
+    if (!(pz >= 0.f)) return false;
+    pz = fabsf(pz);                                            // -0 -> +0: depth keys are compared through their bit patterns
+    inside = w0 > 0.f && w1 > 0.f && w2 > 0.f;
+    float t01, t02, t12;
+    const float e01 = seg_dist2_pre(px, py, ax, ay, bx, by, il01, t01);
+    const float e02 = seg_dist2_pre(px, py, ax, ay, cx, cy, il02, t02);
+    const float e12 = seg_dist2_pre(px, py, bx, by, cx, cy, il12, t12);
+    dist = e01; edge = 0; tt = t01;
+    if (e02 < dist) { dist = e02; edge = 1; tt = t02; }
+    if (e12 < dist) { dist = e12; edge = 2; tt = t12; }
+    return inside || dist < blur;
+}
+
+// the one-block-per-tile kernel's entry: box test + reciprocals on the fly
 __device__ __forceinline__ bool pixel_face(const FaceRec &r, float px, float py, float blur, float br, float &pz, bool &inside,
                                            float &dist, int &edge, float &tt, bool &degenerate) {
     const float xmin = fminf(fminf(r.ax, r.bx), r.cx) - br, xmax = fmaxf(fmaxf(r.ax, r.bx), r.cx) + br;
     const float ymin = fminf(fminf(r.ay, r.by), r.cy) - br, ymax = fmaxf(fmaxf(r.ay, r.by), r.cy) + br;
     if (px > xmax || px < xmin || py > ymax || py < ymin) return false;
-    const float area = edge_fn(r.cx, r.cy, r.ax, r.ay, r.bx, r.by) + kEpsArea;
-    const float w0 = edge_fn(px, py, r.bx, r.by, r.cx, r.cy) / area;
-    const float w1 = edge_fn(px, py, r.cx, r.cy, r.ax, r.ay) / area;
-    const float w2 = edge_fn(px, py, r.ax, r.ay, r.bx, r.by) / area;
-    pz = w0 * r.az + w1 * r.bz + w2 * r.cz;
-    if (!(pz >= 0.f)) return false;
-    inside = w0 > 0.f && w1 > 0.f && w2 > 0.f;
-    float t01, t02, t12; bool g01, g02, g12;
-    const float e01 = seg_dist2(px, py, r.ax, r.ay, r.bx, r.by, t01, g01);
-    const float e02 = seg_dist2(px, py, r.ax, r.ay, r.cx, r.cy, t02, g02);
-    const float e12 = seg_dist2(px, py, r.bx, r.by, r.cx, r.cy, t12, g12);
-    dist = e01; edge = 0; tt = t01; degenerate = g01;
-    if (e02 < dist) { dist = e02; edge = 1; tt = t02; degenerate = g02; }
-    if (e12 < dist) { dist = e12; edge = 2; tt = t12; degenerate = g12; }
-    return inside || dist < blur;
+    const float ia = 1.f / (edge_fn(r.cx, r.cy, r.ax, r.ay, r.bx, r.by) + kEpsArea);
+    const float il01 = inv_len2(r.ax, r.ay, r.bx, r.by), il02 = inv_len2(r.ax, r.ay, r.cx, r.cy), il12 = inv_len2(r.bx, r.by, r.cx, r.cy);
+    const bool ok = pixel_face_core(px, py, r.ax, r.ay, r.az, r.bx, r.by, r.bz, r.cx, r.cy, r.cz, ia, il01, il02, il12, blur, pz, inside, dist, edge, tt);
+    degenerate = (edge == 0 ? il01 : edge == 1 ? il02 : il12) < 0.f;
+    return ok;
 }
 
 __device__ __forceinline__ FaceRec fetch_face(const MeshDev &a, int b, int f, int3 &id) {
@@ -372,12 +389,6 @@ struct TileSmem {
     int item, any;
 };
 
-// reciprocal squared length of edge (a, b), or -1 for a degenerate edge (PyTorch3D PointLineDistanceForward: l2 <= kEpsilon)
-__device__ __forceinline__ float inv_len2(float ax, float ay, float bx, float by) {
-    const float dx = bx - ax, dy = by - ay, l2 = dx * dx + dy * dy;
-    return l2 <= kEpsArea ? -1.f : 1.f / l2;
-}
-
 __device__ __forceinline__ void stage_face(const MeshDev &a, TileSmem &sm, int b, int f, int slot, float br, bool with_ids) {
     int3 id;
     const FaceRec r = fetch_face(a, b, f, id);
@@ -394,35 +405,12 @@ __device__ __forceinline__ void stage_face(const MeshDev &a, TileSmem &sm, int b
     if (with_ids) sm.vid[slot] = id;
 }
 
-// squared distance to segment (a, b) with the reciprocal squared length prepared (il < 0: degenerate -> distance to b)
-__device__ __forceinline__ float seg_dist2_pre(float px, float py, float ax, float ay, float bx, float by, float il, float &tt) {
-    if (il < 0.f) { tt = 1.f; return (px - bx) * (px - bx) + (py - by) * (py - by); }
-    const float dx = bx - ax, dy = by - ay;
-    tt = fminf(fmaxf(((px - ax) * dx + (py - ay) * dy) * il, 0.f), 1.f);
-    const float qx = ax + tt * dx, qy = ay + tt * dy;
-    return (px - qx) * (px - qx) + (py - qy) * (py - qy);
-}
-
 // CheckPixelInsideFace on the staged record `j` (the box test has already passed)
 __device__ __forceinline__ bool pixel_face_pre(const TileSmem &sm, int j, float px, float py, float blur, float &pz, bool &inside,
                                                float &dist, int &edge, float &tt) {
-    const float ax = sm.rec[R_AX][j], ay = sm.rec[R_AY][j], bx = sm.rec[R_BX][j], by = sm.rec[R_BY][j], cx = sm.rec[R_CX][j], cy = sm.rec[R_CY][j];
-    const float ia = sm.rec[R_IAREA][j];
-    const float w0 = edge_fn(px, py, bx, by, cx, cy) * ia;
-    const float w1 = edge_fn(px, py, cx, cy, ax, ay) * ia;
-    const float w2 = edge_fn(px, py, ax, ay, bx, by) * ia;
-    pz = w0 * sm.rec[R_AZ][j] + w1 * sm.rec[R_BZ][j] + w2 * sm.rec[R_CZ][j];
-    if (!(pz >= 0.f)) return false;
-    pz = fabsf(pz);                                            // -0 -> +0: depth keys are compared through their bit patterns
-    inside = w0 > 0.f && w1 > 0.f && w2 > 0.f;
-    float t01, t02, t12;
-    const float e01 = seg_dist2_pre(px, py, ax, ay, bx, by, sm.rec[R_IL01][j], t01);
-    const float e02 = seg_dist2_pre(px, py, ax, ay, cx, cy, sm.rec[R_IL02][j], t02);
-    const float e12 = seg_dist2_pre(px, py, bx, by, cx, cy, sm.rec[R_IL12][j], t12);
-    dist = e01; edge = 0; tt = t01;
-    if (e02 < dist) { dist = e02; edge = 1; tt = t02; }
-    if (e12 < dist) { dist = e12; edge = 2; tt = t12; }
-    return inside || dist < blur;
+    return pixel_face_core(px, py, sm.rec[R_AX][j], sm.rec[R_AY][j], sm.rec[R_AZ][j], sm.rec[R_BX][j], sm.rec[R_BY][j], sm.rec[R_BZ][j],
+                           sm.rec[R_CX][j], sm.rec[R_CY][j], sm.rec[R_CZ][j], sm.rec[R_IAREA][j], sm.rec[R_IL01][j], sm.rec[R_IL02][j],
+                           sm.rec[R_IL12][j], blur, pz, inside, dist, edge, tt);
 }
 
 // box test of this lane's faces of the staged chunk (every kSlices-th, starting at `slice`); survivors -> sm.idx[.][tid]

@@ -170,3 +170,49 @@ def test_dilated_mask_l1_kernel_matches_torch(B, H, W, k, dilate):
     (out * 3.0).backward()
     assert abs(float(out) - float(ref)) < 1e-6
     assert float((x.grad.cpu().double() - 3.0 * ref_in.grad).abs().max()) < 1e-9 + 1e-6 * float(ref_in.grad.abs().max())
+
+
+@pytest.mark.parametrize("n_faces,size,K", [(30000, (256, 256), 50), (12000, (160, 160), 50), (12000, (160, 160), 8)])
+def test_tile_kernels_equal_one_block_per_tile_kernel_on_dense_meshes(n_faces, size, K, monkeypatch):
+    """The worklist / 8-slice tile kernels (k_mesh_tiles_fwd/bwd) against round 1's one-block-per-tile forward kernel
+    (GOM_MESH_LEGACY=1, itself checked against the oracle above) where the K-nearest selection matters: faces much smaller than
+    a pixel, 50 - 400 soft candidates per pixel, most body pixels beyond K.  pix_to_face identical, alpha to rounding, the same
+    pixels carry a cut, with bit-identical cut depths / ids (the kernels share one definition of the per-(pixel, face) arithmetic;
+    the backward replays the cut by comparing recomputed depths with the stored one)."""
+    import os
+    from gomavatar_b200.mesh_renderer import _NdcTWorld, rasterize_mesh, vertex_normals_cam
+    W, H = size
+    sc, fr, verts = _posed_scene(n_faces, size)
+    faces = t(sc.faces).long().to(DEV)
+    xyz = verts.T[None].contiguous().to(DEV)
+    Kd, Ed = t(fr["K"][:1]).to(DEV), t(fr["E"][:1]).to(DEV)
+    ndc = _NdcTWorld.apply(xyz, Kd, Ed, H, W)
+    vn = vertex_normals_cam(xyz, faces, Ed)
+    blur = math.log(1. / 1e-4 - 1.) * 1e-5
+    rng = np.random.default_rng(0)
+    g_n, g_a = t(rng.normal(size=(1, H, W, 3)).astype(np.float32)).to(DEV), t(rng.normal(size=(1, H, W)).astype(np.float32)).to(DEV)
+    res = {}
+    for legacy in ("1", "0"):
+        monkeypatch.setenv("GOM_MESH_LEGACY", legacy)
+        a, b = ndc.detach().clone().requires_grad_(True), vn.detach().clone().requires_grad_(True)
+        aux = {}
+        nm, al, p2f = rasterize_mesh(a, b, faces, H, W, soft=True, blur_radius=blur, faces_per_pixel=K, aux=aux, capacity=32 * n_faces)
+        assert int(aux["status"][0]) == 0
+        torch.autograd.backward([nm, al], [g_n, g_a])
+        res[legacy] = (nm.detach(), al.detach(), p2f, aux["zcut"].clone(), aux["idcut"].clone(), a.grad.clone(), b.grad.clone())
+    monkeypatch.delenv("GOM_MESH_LEGACY")
+    (nm0, al0, p0, z0, i0, gv0, gn0), (nm1, al1, p1, z1, i1, gv1, gn1) = res["1"], res["0"]
+    assert float((p0 >= 0).float().mean()) > 0.02
+    assert bool((p0 == p1).all())
+    assert float((nm0 - nm1).abs().max()) == 0.0
+    assert float((al0 - al1).abs().max()) < 2e-6
+    cut0, cut1 = torch.isfinite(z0), torch.isfinite(z1)
+    assert float(cut0.float().mean()) > 0.005, "the K-nearest selection must be exercised"
+    assert bool((cut0 == cut1).all())
+    # every kernel of csrc/mesh_raster.cu shares ONE definition of the per-(pixel, face) arithmetic: the cuts are bit-identical
+    assert bool((z0[cut0] == z1[cut0]).all())
+    assert bool((i0[cut0] == i1[cut0]).all())
+    worst = float((gv0 - gv1).abs().max() / gv0.abs().max())
+    rel_l2 = float((gv0 - gv1).norm() / gv0.norm())
+    assert worst < 1e-4 and rel_l2 < 1e-5, (worst, rel_l2)          # same cut, same candidates: only the order of the float atomics differs
+    assert float((gn0 - gn1).abs().max() / gn0.abs().max()) < 1e-5
