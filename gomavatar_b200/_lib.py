@@ -216,7 +216,7 @@ class GomShadowMlpArgs(ctypes.Structure):
                 ("fg_index", c_void_p), ("n_fg", c_void_p), ("w_images", c_void_p), ("bg_value", c_void_p), ("out", c_void_p),
                 ("act_img", c_void_p), ("status", c_void_p), ("g_out", c_void_p), ("dz_img", c_void_p), ("g_normals", c_void_p),
                 ("dzo_sums", c_void_p), ("partials", c_void_p), ("g_W_in", c_void_p), ("g_b_in", c_void_p), ("g_W_hid", c_void_p),
-                ("g_b_hid", c_void_p), ("g_w_out", c_void_p), ("g_b_out", c_void_p)]
+                ("g_b_hid", c_void_p), ("g_w_out", c_void_p), ("g_b_out", c_void_p), ("bg_scratch", c_void_p)]
 
 
 class GomMeshRegArgs(ctypes.Structure):
@@ -248,8 +248,9 @@ EXPORTS = [
     "gom_mesh_raster_forward", "gom_mesh_raster_backward", "gom_sizeof_mesh_raster_args",
     "gom_vertex_normals_forward", "gom_vertex_normals_backward", "gom_ndc_forward", "gom_ndc_backward", "gom_dilated_mask_l1",
     "gom_sizeof_vertex_normals_args", "gom_sizeof_ndc_args", "gom_sizeof_dilated_mask_l1_args",
-    "gom_shadow_mlp_forward", "gom_shadow_mlp_backward", "gom_shadow_mlp_weight_image_bytes", "gom_shadow_mlp_tile_words",
+    "gom_shadow_mlp_forward", "gom_shadow_mlp_backward", "gom_shadow_mlp_background_prepare", "gom_shadow_mlp_background_apply", "gom_shadow_mlp_weight_image_bytes", "gom_shadow_mlp_tile_words",
     "gom_shadow_mlp_partial_floats", "gom_shadow_mlp_num_ctas", "gom_sizeof_shadow_mlp_args",
+    "gom_shadow_mlp_background_prepare", "gom_shadow_mlp_background_apply", "gom_shadow_mlp_bg_scratch_floats",
     "gom_mesh_regularizers", "gom_sizeof_mesh_reg_args",
 ]
 
@@ -273,7 +274,7 @@ _ENTRY_POINTS = ["gom_camera_from_KE", "gom_raster_forward", "gom_raster_backwar
                  "gom_conv_first_forward", "gom_conv_first_backward", "gom_adam_step",
                  "gom_conv3x3", "gom_conv3x3_pack_weights", "gom_tf32_split", "gom_linear_wgrad", "gom_nonrigid_input_forward", "gom_nonrigid_input_backward", "gom_rodrigues_forward", "gom_rodrigues_backward", "gom_narrow_linear_forward", "gom_narrow_linear_backward",
                  "gom_mesh_raster_forward", "gom_mesh_raster_backward", "gom_vertex_normals_forward", "gom_vertex_normals_backward",
-                 "gom_ndc_forward", "gom_ndc_backward", "gom_dilated_mask_l1", "gom_shadow_mlp_forward", "gom_shadow_mlp_backward",
+                 "gom_ndc_forward", "gom_ndc_backward", "gom_dilated_mask_l1", "gom_shadow_mlp_forward", "gom_shadow_mlp_backward", "gom_shadow_mlp_background_prepare", "gom_shadow_mlp_background_apply",
                  "gom_mesh_regularizers"]
 
 _lib = None
@@ -306,6 +307,7 @@ def lib():
         f.restype = c_int
         f.argtypes = [c_void_p, c_void_p]
     L.gom_shadow_mlp_weight_image_bytes.restype = c_size_t
+    L.gom_shadow_mlp_bg_scratch_floats.restype = c_size_t
     L.gom_shadow_mlp_weight_image_bytes.argtypes = [c_int]
     L.gom_shadow_mlp_tile_words.restype = c_size_t
     L.gom_shadow_mlp_tile_words.argtypes = [c_int, c_int]

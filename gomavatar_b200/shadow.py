@@ -112,13 +112,11 @@ class _ShadowMlp(torch.autograd.Function):
         dev = normals.device
         N = normals.shape[0]
         g_out = g_out.contiguous().float()
-        weights = [W_in] + ([W_hid[l] for l in range(depth - 1)] if depth > 1 else [])
-        biases = [b_in] + ([b_hid[l] for l in range(depth - 1)] if depth > 1 else [])
-        # the background row (normal 0): value gradient for those pixels, parameter gradients scaled by their summed g_out
-        _, g_x0, dWs0, dbs0, dw_out0, db_out0 = background_row(weights, biases, wo, bo, module.multires)
-        is_bg = (normals == 0).all(dim=1)
-        g_bg = (g_out * is_bg).sum()
-        g_normals = torch.where(is_bg[:, None], g_out[:, None] * g_x0, torch.zeros((), device=dev))
+        # the background row (normal 0) is handled by csrc/shadow_bg.cu: `prepare` writes g_normals for every pixel (the row's input
+        # gradient times g_out on the background, 0 elsewhere) and sums g_out over the background, `apply` adds that sum times the
+        # row's parameter gradients after the tcgen05 backward has written the foreground's
+        g_normals = torch.empty(N, 3, dtype=torch.float32, device=dev)
+        bg_scratch = torch.empty(int(_lib.lib().gom_shadow_mlp_bg_scratch_floats()), dtype=torch.float32, device=dev)
         e = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
         gW_in, gb_in, gw_out, gb_out = e(module.width, W_in.shape[1]), e(module.width), e(module.width), e(1)
         gW_hid = e(depth - 1, module.width, module.width) if depth > 1 else None
@@ -130,12 +128,14 @@ class _ShadowMlp(torch.autograd.Function):
                              act_img=ptr(ws["act_img"]), status=ptr(ws["status"]), g_out=ptr(g_out), dz_img=ptr(ws["dz_img"]),
                              g_normals=ptr(g_normals), dzo_sums=ptr(ws["dzo_sums"]), partials=ptr(ws["partials"]),
                              g_W_in=ptr(gW_in), g_b_in=ptr(gb_in), g_W_hid=ptr(gW_hid), g_b_hid=ptr(gb_hid),
-                             g_w_out=ptr(gw_out), g_b_out=ptr(gb_out))
+                             g_w_out=ptr(gw_out), g_b_out=ptr(gb_out), bg_scratch=ptr(bg_scratch))
+        call("gom_shadow_mlp_background_prepare", a)
         call("gom_shadow_mlp_backward", a)
-        grads = [gW_in + g_bg * dWs0[0], gb_in + g_bg * dbs0[0]]
+        call("gom_shadow_mlp_background_apply", a)
+        grads = [gW_in, gb_in]
         for l in range(1, depth):
-            grads += [gW_hid[l - 1] + g_bg * dWs0[l], gb_hid[l - 1] + g_bg * dbs0[l]]
-        return (None, None, g_normals, (gw_out + g_bg * dw_out0).reshape(1, -1), (gb_out + g_bg * db_out0).reshape(1), *grads)
+            grads += [gW_hid[l - 1], gb_hid[l - 1]]
+        return (None, None, g_normals, gw_out.reshape(1, -1), gb_out.reshape(1), *grads)
 
 
 class FusedShadowModule(_TorchShadowModule):

@@ -638,7 +638,9 @@ int gom_adam_step(const GomAdamArgs *a, gom_stream_t stream);
  * foreground rows; rows >= capacity are dropped and GOM_STATUS_OVERFLOW is set in status[0]) — and later
  * gom_shadow_mlp_backward with the SAME struct plus g_out: it writes dL/dnormal of every FOREGROUND pixel into g_normals
  * (background entries are left untouched) and the parameter gradients of the foreground rows into g_W_in ... g_b_out.
- * The background pixels share one row (normal 0); their contribution is the caller's (one row, see shadow.py).
+ * The background pixels share one row (normal 0): gom_shadow_mlp_background_prepare (BEFORE the backward: g_normals of every
+ * pixel — the row's input gradient times g_out on the background, 0 elsewhere — and the sum of g_out over the background) and
+ * gom_shadow_mlp_background_apply (AFTER it: parameter gradients += that sum times the row's gradients) add their share.
  * Two tcgen05 kernels (data gradients; split-K weight gradients with per-CTA partials) + a fixed-order reduction.
  */
 typedef struct {
@@ -669,9 +671,13 @@ typedef struct {
     float *g_W_in, *g_b_in;      /* [width, 3+6*multires], [width] out */
     float *g_W_hid, *g_b_hid;    /* [depth-1, width, width], [depth-1, width] out */
     float *g_w_out, *g_b_out;    /* [width], [1] out */
+    float *bg_scratch;           /* [gom_shadow_mlp_bg_scratch_floats()] (gom_shadow_mlp_background_* only) */
 } GomShadowMlpArgs;
 int gom_shadow_mlp_forward(const GomShadowMlpArgs *a, gom_stream_t stream);
 int gom_shadow_mlp_backward(const GomShadowMlpArgs *a, gom_stream_t stream);
+int gom_shadow_mlp_background_prepare(const GomShadowMlpArgs *a, gom_stream_t stream);
+int gom_shadow_mlp_background_apply(const GomShadowMlpArgs *a, gom_stream_t stream);
+size_t gom_shadow_mlp_bg_scratch_floats(void);
 size_t gom_shadow_mlp_weight_image_bytes(int depth);
 size_t gom_shadow_mlp_tile_words(int depth, int which);     /* which: 0 = act_img, 1 = dz_img */
 size_t gom_shadow_mlp_partial_floats(void);
