@@ -26,21 +26,26 @@ __global__ void __launch_bounds__(kWidth) k_shadow_bg_row(GomShadowMlpArgs a) {
     // posenc(0) = [0, 0, 0, (sin 0, sin 0, sin 0, cos 0, cos 0, cos 0) per octave]
     if (i < kMaxIn) s_in[i] = (i >= 3 && i < in_dim && ((i - 3) % 6) >= 3) ? 1.f : 0.f;
     __syncthreads();
-    float h;
-    {
-        float z = a.b_in[i];
-        for (int j = 0; j < in_dim; j++) z += a.W_in[i * in_dim + j] * s_in[j];
-        h = fmaxf(z, 0.f);
-    }
+    // z = W v + b with a warp per output row (coalesced reads of the row-major weights), lanes over the inputs
+    __shared__ float s_z[kWidth];
+    const int warp = i >> 5, lane = i & 31;
+    auto matvec = [&](const float *W, const float *bias, const float *v, int n_in) {
+        for (int r = warp; r < kWidth; r += kWidth / 32) {
+            float p = 0.f;
+            for (int j = lane; j < n_in; j += 32) p += W[(long long)r * n_in + j] * v[j];
+            p = warp_sum(p);
+            if (lane == 0) s_z[r] = p + bias[r];
+        }
+        __syncthreads();
+    };
+    matvec(a.W_in, a.b_in, s_in, in_dim);
+    float h = fmaxf(s_z[i], 0.f);
     sc[S_H + i] = h;
     for (int l = 1; l < a.depth; l++) {
         s_h[i] = h;
         __syncthreads();
-        const float *W = a.W_hid + (long long)(l - 1) * kWidth * kWidth + (long long)i * kWidth;
-        float z = a.b_hid[(l - 1) * kWidth + i];
-        for (int j = 0; j < kWidth; j++) z += W[j] * s_h[j];
-        __syncthreads();
-        h = fmaxf(z, 0.f);
+        matvec(a.W_hid + (long long)(l - 1) * kWidth * kWidth, a.b_hid + (l - 1) * kWidth, s_h, kWidth);
+        h = fmaxf(s_z[i], 0.f);
         sc[S_H + l * kWidth + i] = h;
     }
     // output unit: y0 = sigmoid(w_out . h + b_out), dz_out = y0 (1 - y0) for a unit upstream gradient

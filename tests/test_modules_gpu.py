@@ -120,4 +120,5 @@ def test_narrow_linear_kernels_match_float64(R, C, n_out):
     assert _rel(yk.detach(), yo.detach()) < 1e-5
     assert _rel(xk.grad, xo.grad) < 1e-5
     assert _rel(wk.grad, wo.grad) < 2e-5
-    assert _rel(bk.grad, bo.grad) < 2e-5
+    # a sum of R signed values: the rounding error scales with sum |g|, not with the (cancelling) result
+    assert float((bk.grad.double() - bo.grad).abs().max() / g.double().abs().sum(0).max()) < 2e-6
