@@ -129,7 +129,7 @@ class GomEvalMetricsArgs(ctypes.Structure):
 class GomConvFirstArgs(ctypes.Structure):
     _fields_ = [("n_images", c_int32), ("height", c_int32), ("width", c_int32), ("use_tensor_cores", c_int32), ("x", c_void_p),
                 ("weight", c_void_p), ("bias", c_void_p), ("out", c_void_p), ("dL_dout", c_void_p), ("dL_dx", c_void_p),
-                ("scratch", c_void_p), ("act", c_void_p)]
+                ("scratch", c_void_p), ("act", c_void_p), ("mask_out", c_void_p)]
 
 
 class GomConvPackArgs(ctypes.Structure):

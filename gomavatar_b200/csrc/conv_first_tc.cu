@@ -31,6 +31,7 @@ struct Conv1Dev {
     const float *x, *weight, *bias, *dY, *act;
     float *out, *T, *dX;
     uint32_t *status;
+    uint32_t *mask_out;                  // forward: ReLU bit mask of out, [rows, 2] (nullable)
 };
 
 __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
@@ -210,6 +211,12 @@ __global__ void __launch_bounds__(Conv1Cfg<MODE>::THREADS, 1) k_conv1_gemm(Conv1
                     uint32_t z[32];
                     tmem_ld32(d + c * 32, z);
                     tmem_wait_ld();
+                    if (a.mask_out && p < a.rows) {               // this pixel's ReLU bits of channels 32 c .. 32 c + 31
+                        uint32_t w = 0u;
+#pragma unroll
+                        for (int j = 0; j < 32; j++) w |= (__uint_as_float(z[j]) + s_bias[c * 32 + j] > 0.f ? 1u : 0u) << j;
+                        a.mask_out[p * 2 + c] = w;
+                    }
 #pragma unroll
                     for (int j = 0; j < 8; j++)
                         stg[lane * 16 + ((c * 8 + j) ^ (lane & 15))] =
@@ -296,7 +303,7 @@ int gom_conv_first_forward_tc(const GomConvFirstArgs *p, cudaStream_t stream) {
     if (int rc = conv1_setup()) return rc;
     Conv1Dev a{};
     a.N = p->n_images; a.H = p->height; a.W = p->width; a.rows = (long long)a.N * a.H * a.W;
-    a.x = p->x; a.weight = p->weight; a.bias = p->bias; a.out = p->out; a.status = nullptr;
+    a.x = p->x; a.weight = p->weight; a.bias = p->bias; a.out = p->out; a.status = nullptr; a.mask_out = p->mask_out;
     gom_prof_begin(GOM_PROF_CONV_FIRST_FWD, stream);
     GOM_CUDA(gom_launch_pdl(k_conv1_gemm<0>, dim3(g_conv1_sms), dim3(Conv1Cfg<0>::THREADS), Conv1Cfg<0>::DYN_SMEM, stream, a));
     GOM_LAUNCH_CHECK();

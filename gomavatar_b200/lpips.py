@@ -256,9 +256,13 @@ class LPIPS(nn.Module):
         N, hh, ww, _ = h.shape
         if ci == 0 and self.own_first_conv:
             y = torch.empty(N, hh, ww, 64, dtype=torch.float32, device=h.device)
+            # the ReLU bit mask of conv1_1's output, in the layout conv1_2's dgrad applies (the backward of conv1_1 then reads
+            # neither its own 1 GB activation nor a mask)
+            mask = _conv.new_mask(N, hh, ww, 64, h.device) if (want_mask and self.first_conv_tc and self.conv_impl == "tcgen05") else None
             call("gom_conv_first_forward", GomConvFirstArgs(n_images=N, height=hh, width=ww, use_tensor_cores=int(self.first_conv_tc),
-                                                            x=ptr(h), weight=ptr(self.w_first), bias=ptr(conv.bias), out=ptr(y)))
-            return y, None
+                                                            x=ptr(h), weight=ptr(self.w_first), bias=ptr(conv.bias), out=ptr(y),
+                                                            mask_out=ptr(mask)))
+            return y, mask
         if self.conv_impl == "tcgen05" and ci > 0:
             mask = _conv.new_mask(N, hh, ww, conv.out_channels, h.device) if want_mask else None
             y = _conv.conv3x3(h, self._packed(ci, False), bias=conv.bias, relu=True, mask_out=mask, precision=self.conv_precision)

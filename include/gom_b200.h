@@ -347,6 +347,9 @@ typedef struct {
     float *scratch;              /* [9, N*H*W, 4] floats (backward with use_tensor_cores), 16-byte aligned; else NULL */
     const float *act;            /* optional [N,H,W,64] (backward with use_tensor_cores): this convolution's ReLU output; when given,
                                     dL_dout is the UNMASKED gradient and the ReLU backward (dL_dout * [act > 0]) is fused in */
+    uint32_t *mask_out;          /* optional [N,H,W,2] (forward with use_tensor_cores): ReLU bit mask of `out` (bit j of word w =
+                                    [channel 32 w + j > 0]) in the layout gom_conv3x3's mask_in reads: the dgrad of conv1_2 then
+                                    applies this layer's ReLU backward itself and the backward here needs neither `act` nor a mask */
 } GomConvFirstArgs;
 int gom_conv_first_forward(const GomConvFirstArgs *a, gom_stream_t stream);
 int gom_conv_first_backward(const GomConvFirstArgs *a, gom_stream_t stream);
