@@ -515,7 +515,10 @@ def run_b200(args):
         "preprocess_bwd": 76 * F + 36 * F, "emit": 12 * n_dup + 20 * F, "scan_tiles": 12 * T, "worklist": 12 * T,
         "lbs_fwd": 120 * V, "lbs_bwd": 120 * V, "face_fwd": 72 * F, "face_bwd": 72 * F + 36 * F,
         "photo_fwd": 44 * HW, "photo_bwd": 60 * HW}
-    alg_bytes_per_frame.update(lpips_alg_bytes_per_frame(args.img, args.img, args.lpips_conv == "cudnn" and args.lpips_epilogue == "kernel"))
+    # tcgen05 path: conv1_1's ReLU backward is applied by conv1_2's dgrad through the bit mask the forward emits, so the backward of
+    # conv1_1 does not read its own activation
+    alg_bytes_per_frame.update(lpips_alg_bytes_per_frame(args.img, args.img, args.lpips_conv == "cudnn" and args.lpips_epilogue == "kernel",
+                                                         fused_first_relu=args.lpips_conv != "tcgen05"))
     if args.lpips_conv == "tcgen05":
         alg_bytes_per_frame["relu_bwd"] = 0.0                            # fused into the dgrad epilogues (bit masks)
     alg_bytes_per_frame["adam"] = 28.0 * tr.arena.numel / B          # param r/w, grad r, two moments r/w: per STEP
