@@ -345,15 +345,34 @@ def check(rc, what):
         raise GomError(f"{what} failed ({rc}): {lib().gom_last_error().decode()}")
 
 
-def stream_ptr():
-    """current torch CUDA stream as the gom_stream_t argument"""
+_get_device = None      # torch._C._cuda_getDevice / _cuda_getCurrentRawStream: the C entry points behind torch.cuda.current_device() /
+_get_raw_stream = None  # current_stream().cuda_stream, without their ~15 us of Python (lazy-init checks, Stream object) per launch
+
+
+def _fast_torch():
+    global _get_device, _get_raw_stream
     import torch
-    return c_void_p(torch.cuda.current_stream().cuda_stream)
+    try:
+        torch.cuda.init()
+    except Exception as e:                               # no driver / no device: there is no CPU path to fall back to
+        raise GomError(f"no usable CUDA device ({type(e).__name__}: {e}); libgom_b200 has no CPU path") from e
+    _get_device = getattr(torch._C, "_cuda_getDevice", None) or torch.cuda.current_device
+    raw = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+    _get_raw_stream = raw if raw is not None else (lambda dev: torch.cuda.current_stream(dev).cuda_stream)
+
+
+def stream_ptr():
+    """current torch CUDA stream (of the current device) as the gom_stream_t argument"""
+    if _get_raw_stream is None:
+        _fast_torch()
+    return c_void_p(_get_raw_stream(_get_device()))
 
 
 def call(name, args):
     """invoke an entry point on the current torch stream and raise on a non-zero return code"""
-    check(getattr(lib(), name)(ctypes.byref(args), stream_ptr()), name)
+    rc = getattr(lib(), name)(ctypes.byref(args), stream_ptr())
+    if rc != 0:
+        check(rc, name)
 
 
 def ptr(t):
@@ -363,8 +382,9 @@ def ptr(t):
     if t is None:
         return None
     if t.is_cuda:
-        import torch
-        if t.device.index != torch.cuda.current_device():
-            raise GomError(f"tensor on {t.device} but the current CUDA device is cuda:{torch.cuda.current_device()}: "
+        if _get_device is None:
+            _fast_torch()
+        if t.device.index != _get_device():
+            raise GomError(f"tensor on {t.device} but the current CUDA device is cuda:{_get_device()}: "
                            "call torch.cuda.set_device(...) (or use `with torch.cuda.device(...)`) before launching")
     return c_void_p(t.data_ptr())
