@@ -172,12 +172,14 @@ def test_dilated_mask_l1_kernel_matches_torch(B, H, W, k, dilate):
     assert float((x.grad.cpu().double() - 3.0 * ref_in.grad).abs().max()) < 1e-9 + 1e-6 * float(ref_in.grad.abs().max())
 
 
-@pytest.mark.parametrize("n_faces,size,K", [(30000, (256, 256), 50), (12000, (160, 160), 50), (12000, (160, 160), 8)])
+@pytest.mark.parametrize("n_faces,size,K", [(30000, (256, 256), 50), (12000, (160, 160), 50), (12000, (160, 160), 8), (120000, (512, 512), 50)])
 def test_tile_kernels_equal_one_block_per_tile_kernel_on_dense_meshes(n_faces, size, K, monkeypatch):
     """The worklist / 8-slice tile kernels (k_mesh_tiles_fwd/bwd) against round 1's one-block-per-tile forward kernel
     (GOM_MESH_LEGACY=1, itself checked against the oracle above) where the K-nearest selection matters: faces much smaller than
     a pixel, 50 - 400 soft candidates per pixel, most body pixels beyond K.  pix_to_face identical, alpha to rounding, the same
-    pixels carry a cut, with bit-identical cut depths / ids (the kernels share one definition of the per-(pixel, face) arithmetic;
+    pixels carry a cut, with bit-identical cut depths / ids (the kernels share one definition of the per-(pixel, face) arithmetic, written with
+    explicit rounding intrinsics so that nvcc cannot contract it differently in different kernels: at 120 000 faces plain
+    expressions made 1 cut pixel in 16 000 differ;
     the backward replays the cut by comparing recomputed depths with the stored one)."""
     import os
     from gomavatar_b200.mesh_renderer import _NdcTWorld, rasterize_mesh, vertex_normals_cam
