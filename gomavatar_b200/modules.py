@@ -192,7 +192,7 @@ class _TcMlpStack(torch.autograd.Function):
         call("gom_relu_backward", GomReluBwdArgs(n=gp.numel(), act=ptr(ctx.last), grad=ptr(gp)))      # ReLU of the last hidden layer
         g_enc = None
         grads = [None] * (2 * n)
-        ones = torch.ones(1, R16, dtype=gp.dtype, device=gp.device)
+        ones = None                                          # GEMV partner of the fallback bias gradient, made on first use
         for i in reversed(range(n)):
             w, hin = ws[i], saved_in[i]
             # weight / bias gradients: contractions over the rows.  128-wide layers: tensor cores (csrc/wgrad_tc.cu), the bias
@@ -210,6 +210,8 @@ class _TcMlpStack(torch.autograd.Function):
                     gw = torch.bmm(gp.view(S, R16 // S, -1).transpose(1, 2), hin.view(S, R16 // S, -1)).sum(0)
                 else:
                     gw = gp.t() @ hin
+                if ones is None:
+                    ones = torch.ones(1, R16, dtype=gp.dtype, device=gp.device)
                 gb = (ones @ gp)[0]
             grads[2 * i] = gw[:, :w.shape[1]]
             grads[2 * i + 1] = gb
