@@ -11,8 +11,9 @@
 //             A[p, (r,s,c)] = the 27 neighbourhood values of pixel p (zero padded, gathered by the pixel's thread straight
 //             into tensor memory), B[k, (r,s,c)] = W, one 128 x 64 x 32 product per 128 pixels.
 //   backward  T[p, (r,s,c)] = sum_k dY[p,k] W[k,c,r,s]      (128 x 32 x 64 product, A = the pixel's 64 gradients)
-//             dX[q, c] = sum_{r,s} T[q - (r-1, s-1), (r,s,c)]   (k_conv1_stencil: 9 coalesced float4 loads per pixel from the
-//             9 tap planes the GEMM epilogue writes)
+//             dX[q, c] = sum_{r,s} T[q - (r-1, s-1), (r,s,c)]: the sum over s (neighbours in the image row = neighbouring
+//             lanes) is taken in the GEMM epilogue with shuffles, which writes 3 row-sum planes H[r] (48 B per pixel) instead
+//             of the 9 tap planes (144 B); k_conv1_stencil takes the sum over r: 3 coalesced float4 loads per pixel
 //
 // One persistent CTA per SM running several independent producer/MMA/epilogue groups (see k_conv1_gemm).
 // The weight images (TF32 hi/lo, K-major SWIZZLE_128B) are built by each CTA in its own shared memory at start-up.
@@ -36,6 +37,16 @@ struct Conv1Dev {
 
 __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+// pixel index -> (image, row, column); 32-bit divisions whenever the index space allows (a 64-bit division is ~100 instructions)
+__device__ __forceinline__ void pixel_coords(long long p, long long rows, int H, int W, long long &n, int &y, int &x) {
+    if (rows < (1ll << 31)) {
+        const uint32_t hw = (uint32_t)H * (uint32_t)W, pu = (uint32_t)p, nu = pu / hw, yx = pu - nu * hw, yu = yx / (uint32_t)W;
+        n = nu; y = (int)yu; x = (int)(yx - yu * (uint32_t)W);
+    } else {
+        const long long HW = (long long)H * W, yx = p - (p / HW) * HW;
+        n = p / HW; y = (int)(yx / W); x = (int)(yx - (long long)y * W);
+    }
 }
 __device__ __forceinline__ int swz(int j, int q) { return j * 32 + ((((q >> 2) ^ (j & 7)) << 2) | (q & 3)); }
 
@@ -63,7 +74,7 @@ __global__ void __launch_bounds__(Conv1Cfg<MODE>::THREADS, 1) k_conv1_gemm(Conv1
     __shared__ uint64_t a_ready[G], z_ready[G];
     __shared__ uint32_t tmem_slot;
     __shared__ int abort_flag;
-    __shared__ float s_bias[64];
+    __shared__ __align__(16) float s_bias[64];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (warp == 0) {
@@ -145,8 +156,8 @@ __global__ void __launch_bounds__(Conv1Cfg<MODE>::THREADS, 1) k_conv1_gemm(Conv1
 #pragma unroll
                     for (int i = 0; i < 32; i++) v[i] = 0.f;
                     if (p < a.rows) {
-                        const long long n = p / HW, yx = p - n * HW;
-                        const int y = (int)(yx / a.W), x = (int)(yx - (long long)y * a.W);
+                        long long n; int y, x;
+                        pixel_coords(p, a.rows, a.H, a.W, n, y, x);
                         const float *img = a.x + n * HW * 3;
 #pragma unroll
                         for (int dy = -1; dy <= 1; dy++)
@@ -162,33 +173,42 @@ __global__ void __launch_bounds__(Conv1Cfg<MODE>::THREADS, 1) k_conv1_gemm(Conv1
                     }
                 } else {
                     // the warp's 32 gradient rows (and, for the fused ReLU backward, the 32 rows of this convolution's own
-                    // output) go global -> shared memory with cp.async: no registers are tied up by the 32 loads in flight
-                    __syncwarp();
+                    // output) go global -> shared memory with cp.async: no registers are tied up by the 32 loads in flight.
+                    // Without the ReLU rows the second half of the staging area is free: the rows of the NEXT tile are then
+                    // requested before this tile's MMAs / epilogue, whose latency hides their trip from HBM.
+                    const bool pipelined = a.act == nullptr;
+                    auto request_rows = [&](long long first_row, float4 *buf) {
 #pragma unroll
-                    for (int i = 0; i < 16; i++) {
-                        const int q = 2 * i + (lane >> 4), j = lane & 15;
-                        float4 *dst = &stg[q * 16 + (j ^ (q & 15))];
-                        if (p_warp + q < a.rows) {
-                            cp_async16(dst, reinterpret_cast<const float4 *>(a.dY + (p_warp + q) * 64) + j);
-                            if (a.act) cp_async16(dst + 512, reinterpret_cast<const float4 *>(a.act + (p_warp + q) * 64) + j);
-                        } else {
-                            *dst = make_float4(0.f, 0.f, 0.f, 0.f);
-                            if (a.act) dst[512] = make_float4(1.f, 1.f, 1.f, 1.f);
+                        for (int i = 0; i < 16; i++) {
+                            const int q = 2 * i + (lane >> 4), j = lane & 15;
+                            float4 *dst = &buf[q * 16 + (j ^ (q & 15))];
+                            if (first_row + q < a.rows) {
+                                cp_async16(dst, reinterpret_cast<const float4 *>(a.dY + (first_row + q) * 64) + j);
+                                if (a.act) cp_async16(dst + 512, reinterpret_cast<const float4 *>(a.act + (first_row + q) * 64) + j);
+                            } else {
+                                *dst = make_float4(0.f, 0.f, 0.f, 0.f);
+                                if (a.act) dst[512] = make_float4(1.f, 1.f, 1.f, 1.f);
+                            }
                         }
-                    }
-                    asm volatile("cp.async.commit_group;" ::: "memory");
+                        asm volatile("cp.async.commit_group;" ::: "memory");
+                    };
+                    float4 *cur = stg + (pipelined ? (it & 1u) * 512 : 0);
+                    __syncwarp();
+                    if (!pipelined || it == 0) request_rows(p_warp, cur);
                     asm volatile("cp.async.wait_group 0;" ::: "memory");
                     __syncwarp();
 #pragma unroll
                     for (int i = 0; i < 16; i++) {
-                        float4 f = stg[lane * 16 + (i ^ (lane & 15))];
+                        float4 f = cur[lane * 16 + (i ^ (lane & 15))];
                         if (a.act) {                                // fused ReLU backward of this convolution's own output
-                            const float4 y = stg[512 + lane * 16 + (i ^ (lane & 15))];
+                            const float4 y = cur[512 + lane * 16 + (i ^ (lane & 15))];
                             f.x = y.x > 0.f ? f.x : 0.f; f.y = y.y > 0.f ? f.y : 0.f;
                             f.z = y.z > 0.f ? f.z : 0.f; f.w = y.w > 0.f ? f.w : 0.f;
                         }
                         v[4 * i] = f.x; v[4 * i + 1] = f.y; v[4 * i + 2] = f.z; v[4 * i + 3] = f.w;
                     }
+                    // the other half was last read one iteration ago, before the __syncwarp above
+                    if (pipelined && tile + stride < n_tiles) request_rows(p_warp + stride * kTileRows, stg + ((it & 1u) ^ 1u) * 512);
                 }
 #pragma unroll
                 for (int c = 0; c < KB * 2; c++) {
@@ -211,19 +231,16 @@ __global__ void __launch_bounds__(Conv1Cfg<MODE>::THREADS, 1) k_conv1_gemm(Conv1
                     uint32_t z[32];
                     tmem_ld32(d + c * 32, z);
                     tmem_wait_ld();
-                    if (a.mask_out && p < a.rows) {               // this pixel's ReLU bits of channels 32 c .. 32 c + 31
-                        uint32_t w = 0u;
+                    uint32_t w = 0u;                              // this pixel's ReLU bits of channels 32 c .. 32 c + 31
 #pragma unroll
-                        for (int j = 0; j < 32; j++) w |= (__uint_as_float(z[j]) + s_bias[c * 32 + j] > 0.f ? 1u : 0u) << j;
-                        a.mask_out[p * 2 + c] = w;
+                    for (int j = 0; j < 8; j++) {
+                        const float4 b = *reinterpret_cast<const float4 *>(&s_bias[c * 32 + 4 * j]);
+                        const float v0 = __uint_as_float(z[4 * j]) + b.x, v1 = __uint_as_float(z[4 * j + 1]) + b.y;
+                        const float v2 = __uint_as_float(z[4 * j + 2]) + b.z, v3 = __uint_as_float(z[4 * j + 3]) + b.w;
+                        w |= ((v0 > 0.f ? 1u : 0u) | (v1 > 0.f ? 2u : 0u) | (v2 > 0.f ? 4u : 0u) | (v3 > 0.f ? 8u : 0u)) << (4 * j);
+                        stg[lane * 16 + ((c * 8 + j) ^ (lane & 15))] = make_float4(fmaxf(v0, 0.f), fmaxf(v1, 0.f), fmaxf(v2, 0.f), fmaxf(v3, 0.f));
                     }
-#pragma unroll
-                    for (int j = 0; j < 8; j++)
-                        stg[lane * 16 + ((c * 8 + j) ^ (lane & 15))] =
-                            make_float4(fmaxf(__uint_as_float(z[4 * j]) + s_bias[c * 32 + 4 * j], 0.f),
-                                        fmaxf(__uint_as_float(z[4 * j + 1]) + s_bias[c * 32 + 4 * j + 1], 0.f),
-                                        fmaxf(__uint_as_float(z[4 * j + 2]) + s_bias[c * 32 + 4 * j + 2], 0.f),
-                                        fmaxf(__uint_as_float(z[4 * j + 3]) + s_bias[c * 32 + 4 * j + 3], 0.f));
+                    if (a.mask_out && p < a.rows) a.mask_out[p * 2 + c] = w;
                 }
                 __syncwarp();
 #pragma unroll
@@ -233,17 +250,40 @@ __global__ void __launch_bounds__(Conv1Cfg<MODE>::THREADS, 1) k_conv1_gemm(Conv1
                         reinterpret_cast<float4 *>(a.out + (p_warp + q) * 64)[j] = stg[q * 16 + (j ^ (q & 15))];
                 }
             } else {
-                // T as 9 planes [tap][pixel] of float4 (dX channels 0..2 of that tap, pad): a warp's 32 consecutive pixels
-                // are 512 contiguous bytes per plane, for this store and for the stencil's loads
+                // This pixel's 27 products T[p][(r,s)][c] never reach global memory as such: the three taps of a kernel row r
+                // meet at pixel p from p itself (s = 1) and its two neighbours in the image row (T[p-1][(r,2)], T[p+1][(r,0)]),
+                // which are the neighbouring lanes — the horizontal half of the stencil is two shuffles per (r, c).  What is
+                // stored is H[r][p] = that row sum, 3 planes of float4 (48 B per pixel instead of 144; a warp's 32 consecutive
+                // pixels are 512 contiguous bytes per plane); the terms that cross the warp's 32-pixel segment go to two
+                // small edge arrays (lane 31's (r,2) products, lane 0's (r,0) products) that k_conv1_stencil adds back.
                 uint32_t z[32];
                 tmem_ld32(d, z);
                 tmem_wait_ld();
-                if (p < a.rows) {
-                    float4 *tp = reinterpret_cast<float4 *>(a.T) + p;
+                long long n_; int y_, x;
+                pixel_coords(p < a.rows ? p : 0, a.rows, a.H, a.W, n_, y_, x);
+                const bool has_l = lane > 0 && x > 0, has_r = lane < 31 && x < a.W - 1;
+                float4 *hp = reinterpret_cast<float4 *>(a.T);
+                const long long n_seg = (a.rows + 31) >> 5, seg = p_warp >> 5;
 #pragma unroll
-                    for (int t = 0; t < 9; t++)
-                        tp[(size_t)t * a.rows] = make_float4(__uint_as_float(z[3 * t]), __uint_as_float(z[3 * t + 1]),
-                                                             __uint_as_float(z[3 * t + 2]), 0.f);
+                for (int r = 0; r < 3; r++) {
+                    float h[3];
+#pragma unroll
+                    for (int c = 0; c < 3; c++) {
+                        const float from_l = __shfl_up_sync(0xFFFFFFFFu, __uint_as_float(z[(r * 3 + 2) * 3 + c]), 1);
+                        const float from_r = __shfl_down_sync(0xFFFFFFFFu, __uint_as_float(z[(r * 3 + 0) * 3 + c]), 1);
+                        h[c] = __uint_as_float(z[(r * 3 + 1) * 3 + c]);
+                        if (has_l) h[c] += from_l;
+                        if (has_r) h[c] += from_r;
+                    }
+                    if (p < a.rows) {
+                        hp[(size_t)r * a.rows + p] = make_float4(h[0], h[1], h[2], 0.f);
+                        if (lane == 31)
+                            hp[3 * a.rows + seg * 3 + r] = make_float4(__uint_as_float(z[(r * 3 + 2) * 3]), __uint_as_float(z[(r * 3 + 2) * 3 + 1]),
+                                                                       __uint_as_float(z[(r * 3 + 2) * 3 + 2]), 0.f);
+                        if (lane == 0)
+                            hp[3 * a.rows + (n_seg + seg) * 3 + r] = make_float4(__uint_as_float(z[r * 9]), __uint_as_float(z[r * 9 + 1]),
+                                                                                 __uint_as_float(z[r * 9 + 2]), 0.f);
+                    }
                 }
             }
             tc_fence_before();      // these tcgen05.ld are ordered before the next a_ready arrive (the next MMA overwrites D)
@@ -258,27 +298,37 @@ __global__ void __launch_bounds__(Conv1Cfg<MODE>::THREADS, 1) k_conv1_gemm(Conv1
     }
 }
 
-// dX[q, c] = sum over the 9 taps (r,s) of T[(r,s)][q - (r-1, s-1)].c   (pixels outside the image contribute nothing)
+// dX[q, c] = sum over the kernel rows r of H[r][q - (r-1) W] (+ the edge terms of the 32-pixel segments): the vertical half of
+// the stencil, 3 coalesced float4 loads per pixel.  Scratch layout (float4): H [3][rows] | E_right [segments][3] | E_left [segments][3].
 __global__ void __launch_bounds__(256) k_conv1_stencil(Conv1Dev a) {
     gom_pdl_trigger();
     gom_pdl_wait();
     const long long q = (long long)blockIdx.x * 256 + threadIdx.x;
     if (q >= a.rows) return;
     const long long HW = (long long)a.H * a.W;
-    const long long n = q / HW, yx = q - n * HW;
-    const int y = (int)(yx / a.W), x = (int)(yx - (long long)y * a.W);
-    const float4 *T = reinterpret_cast<const float4 *>(a.T);
+    long long n; int y, x;
+    pixel_coords(q, a.rows, a.H, a.W, n, y, x);
+    const float4 *Hp = reinterpret_cast<const float4 *>(a.T);
+    const long long n_seg = (a.rows + 31) >> 5;
+    const float4 *Er = Hp + 3 * a.rows, *El = Er + 3 * n_seg;
     float g0 = 0.f, g1 = 0.f, g2 = 0.f;
 #pragma unroll
-    for (int r = 0; r < 3; r++)
-#pragma unroll
-        for (int s = 0; s < 3; s++) {
-            const int yy = y - (r - 1), xx = x - (s - 1);
-            if (yy >= 0 && yy < a.H && xx >= 0 && xx < a.W) {
-                const float4 f = __ldg(T + (size_t)(r * 3 + s) * a.rows + n * HW + (long long)yy * a.W + xx);
-                g0 += f.x; g1 += f.y; g2 += f.z;
+    for (int r = 0; r < 3; r++) {
+        const int yy = y - (r - 1);
+        if (yy >= 0 && yy < a.H) {
+            const long long pp = n * HW + (long long)yy * a.W + x;
+            float4 f = __ldg(Hp + (size_t)r * a.rows + pp);
+            if ((pp & 31) == 0 && x > 0) {                         // the left neighbour is lane 31 of the previous segment
+                const float4 e = __ldg(Er + ((pp >> 5) - 1) * 3 + r);
+                f.x += e.x; f.y += e.y; f.z += e.z;
             }
+            if ((pp & 31) == 31 && x < a.W - 1) {                  // the right neighbour is lane 0 of the next segment
+                const float4 e = __ldg(El + ((pp >> 5) + 1) * 3 + r);
+                f.x += e.x; f.y += e.y; f.z += e.z;
+            }
+            g0 += f.x; g1 += f.y; g2 += f.z;
         }
+    }
     float *o = a.dX + q * 3;
     o[0] = g0; o[1] = g1; o[2] = g2;
 }
