@@ -383,6 +383,287 @@ k_conv3x3(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
     }
 }
 
+
+// ===================================================================================== CTA pairs (tcgen05 cta_group::2)
+// The same convolution with TWO CTAs (a thread-block cluster of 2 = the two SMs of a TPC) on one M = 256 tile: CTA r of the
+// pair owns the pixel tile at columns w0 + r TILE_W (its own halo, its own 128 accumulator rows per sub-tile in its own tensor
+// memory) and HALF of every weight tile (rows n0 + r NT/2 ...).  One tcgen05.mma.cta_group::2 issued by the leader (rank 0)
+// multiplies both CTAs' activation views with the weight tile that is spread over both shared memories: per MMA a CTA reads
+// 4 KB of activations + NT/2 rows of weights instead of NT rows — the shared-memory operand reads that bind cta_group::1
+// (128 B/clk: 8 KB per 64-cycle MMA at NT = 128, 6 KB per 32-cycle MMA at NT = 64) drop below the tensor rate, and every
+// weight byte crosses L2 -> shared memory once per PAIR.
+// Protocol: all TMA loads of both CTAs complete on the LEADER's full barriers (cp.async.bulk.tensor.cta_group::2 with the
+// barrier address of rank 0; the leader's producer expects the bytes of both); the leader's MMA warp releases stages /
+// publishes accumulators with multicast commits that arrive on the barrier of the same name in BOTH CTAs; the epilogue warps of
+// both CTAs hand an accumulator stage back on the leader's barrier (remote arrive).
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+constexpr uint32_t kLeaderMask = 0xFEFFFFFFu;        // shared::cluster address of the same offset in the pair's rank-0 CTA
+__device__ __forceinline__ void tma_load_4d_pair(uint32_t dst, const CUtensorMap *map, int c0, int c1, int c2, int c3, uint64_t *leader_bar) {
+    asm volatile("cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                 ::"r"(dst), "l"(map), "r"(smem_u32(leader_bar) & kLeaderMask), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_pair(uint32_t dst, const CUtensorMap *map, int c0, int c1, int c2, uint64_t *leader_bar) {
+    asm volatile("cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"(dst), "l"(map), "r"(smem_u32(leader_bar) & kLeaderMask), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tc_commit_pair(uint64_t *bar) {          // arrives on `bar` of both CTAs
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kLeaderMask) : "memory");
+}
+__device__ __forceinline__ void mma_tf32_pair(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc, uint32_t acc) {
+    asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %6, 0;\n\tmov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
+                 "tcgen05.mma.cta_group::2.kind::tf32 [%0], da, db, %5, p;\n\t}"
+                 ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(acc) : "memory");
+}
+__host__ __device__ constexpr uint32_t instr_desc_pair(int n) {           // M = 256 over the pair
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+}
+
+template <int NT, int SUB, int TPS, int BST> struct PairCfg {
+    using Base = ConvCfg<NT, SUB, TPS, BST, 9>;
+    static constexpr int B_TAP_BYTES = (NT / 2) * 128;          // this CTA's half of a tap's weight tile
+    static constexpr int B_BYTES = TPS * B_TAP_BYTES;
+    static constexpr int SMEM = Base::A_BUFS * Base::A_BYTES + BST * B_BYTES + Base::EPI_WARPS * kEpiWarpBytes + 1024;
+    static_assert(NT % 16 == 0 && (NT / 2) % 8 == 0, "half weight tiles are whole 8-row groups");
+};
+
+template <int NT, int SUB, int TPS, int BST>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(ConvCfg<NT, SUB, TPS, BST, 9>::THREADS, 1)
+k_conv3x3_pair(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_a_lo,
+               const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_out, const ConvDev p) {
+    using Cfg = ConvCfg<NT, SUB, TPS, BST, 9>;
+    using PC = PairCfg<NT, SUB, TPS, BST>;
+    constexpr int PITCH = Cfg::PITCH;
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ uint64_t afull_bar[Cfg::A_BUFS], aempty_bar[Cfg::A_BUFS], bfull_bar[BST], bempty_bar[BST], tfull_bar[2], tempty_bar[2];
+    __shared__ uint32_t tmem_slot;
+    __shared__ int abort_flag;
+
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t b_base = smem_base + Cfg::A_BUFS * Cfg::A_BYTES;
+    const uint32_t epi_base = b_base + BST * PC::B_BYTES;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int rank = (int)cluster_ctarank();
+    const bool leader = rank == 0;
+    const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < Cfg::A_BUFS; i++) { mbar_init(&afull_bar[i], 1); mbar_init(&aempty_bar[i], 1); }
+        for (int i = 0; i < BST; i++) { mbar_init(&bfull_bar[i], 1); mbar_init(&bempty_bar[i], 1); }
+        for (int i = 0; i < 2; i++) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 2 * Cfg::EPI_WARPS); }
+        abort_flag = 0;
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {                       // the same warp of both CTAs allocates the pair's tensor memory (same columns in both)
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(Cfg::TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                    // both CTAs' barriers exist before anything is signalled across the pair
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+    volatile int *ab = &abort_flag;
+    const int items_per_tile = p.n_pass * p.c_blocks;
+    gom_pdl_trigger();
+    gom_pdl_wait();
+
+    auto tile_of = [&](int tile) {         // this CTA's half of pair tile `tile`
+        TileCoord t = decode_tile(p, tile, NT, 2 * Cfg::TILE_W);
+        t.w0 += rank * Cfg::TILE_W;
+        return t;
+    };
+
+    if (warp == 0) {
+        // --------------------------------------------------------------------------- TMA producer (both CTAs, own operands)
+        if (elect_one()) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+        }
+        uint32_t bst = 0, bph = 0, a_count = 0;
+        bool ok = true;
+        int a_tile = pair, a_item = 0;
+        auto issue_halo = [&]() -> bool {
+            if (a_tile >= p.n_tiles) return true;
+            const TileCoord t = tile_of(a_tile);
+            const int pass = a_item / p.c_blocks, cb = a_item - pass * p.c_blocks;
+            const uint32_t buf = a_count % Cfg::A_BUFS, ph = (a_count / Cfg::A_BUFS) & 1u;
+            if (!mbar_wait(&aempty_bar[buf], ph ^ 1u, ab)) return false;
+            if (elect_one()) {
+                if (leader) mbar_expect_tx(&afull_bar[buf], 2 * Cfg::A_TX_BYTES);
+                tma_load_4d_pair(smem_base + buf * Cfg::A_BYTES, pass == 1 ? &map_a_lo : &map_a, cb * 32, t.w0 - 1, t.h0 - 1, t.img, &afull_bar[buf]);
+            }
+            __syncwarp();
+            a_count++;
+            if (++a_item == items_per_tile) { a_item = 0; a_tile += n_pairs; }
+            return true;
+        };
+        for (int i = 0; i < Cfg::A_BUFS - 1 && ok; i++) ok = issue_halo();
+        bool ready = mbar_test_wait(&bempty_bar[0], 1u);
+        for (int tile = pair; tile < p.n_tiles && ok; tile += n_pairs) {
+            const TileCoord t = tile_of(tile);
+            for (int item = 0; item < items_per_tile && ok; item++) {
+                const int pass = item / p.c_blocks, cb = item - pass * p.c_blocks;
+                const int tap_off = pass == 2 ? 9 : 0;
+                for (int grp = 0; grp < Cfg::GROUPS; grp++) {
+                    if (grp == Cfg::HALO_AT && !issue_halo()) { ok = false; break; }
+                    if (!ready && !mbar_wait(&bempty_bar[bst], bph ^ 1u, ab)) { ok = false; break; }
+                    const uint32_t dst = b_base + bst * PC::B_BYTES;
+                    uint64_t *fb = &bfull_bar[bst];
+                    if (++bst == BST) { bst = 0; bph ^= 1u; }
+                    ready = mbar_test_wait(&bempty_bar[bst], bph ^ 1u);
+                    if (elect_one()) {
+                        if (leader) mbar_expect_tx(fb, 2 * PC::B_BYTES);
+                        tma_load_3d_pair(dst, &map_b, cb * 32, t.n0 + rank * (NT / 2), tap_off + grp * TPS, fb);
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------------------ MMA issuer (leader CTA only)
+        if (leader) {
+        const uint32_t idesc = instr_desc_pair(NT);
+        const uint32_t a_desc0 = ((smem_base & 0x3FFFFu) >> 4) | (1u << 16);
+        const uint32_t b_desc0 = ((b_base & 0x3FFFFu) >> 4) | (1u << 16);
+        constexpr uint32_t kBHi = desc_hi(1024, 0);
+        uint32_t bst = 0, bph = 0, a_count = 0, tcount = 0;
+        bool ok = true;
+        bool ready = mbar_test_wait(&bfull_bar[0], 0u);
+        for (int tile = pair; tile < p.n_tiles && ok; tile += n_pairs, tcount++) {
+            const uint32_t acc = tcount & 1u, aph = (tcount >> 1) & 1u;
+            if (!mbar_wait(&tempty_bar[acc], aph ^ 1u, ab)) { ok = false; break; }
+            const uint32_t d0 = tmem + acc * Cfg::ACC_COLS;
+            for (int item = 0; item < items_per_tile && ok; item++, a_count++) {
+                const uint32_t abuf = a_count % Cfg::A_BUFS;
+                if (!mbar_wait(&afull_bar[abuf], (a_count / Cfg::A_BUFS) & 1u, ab)) { ok = false; break; }
+                const uint32_t a_buf_lo = a_desc0 + abuf * (Cfg::A_BYTES >> 4);
+#pragma unroll
+                for (int grp = 0; grp < Cfg::GROUPS; grp++) {
+                    if (!ready && !mbar_wait(&bfull_bar[bst], bph, ab)) { ok = false; break; }
+                    const uint32_t b_lo = b_desc0 + bst * (PC::B_BYTES >> 4);
+                    uint64_t *eb = &bempty_bar[bst];
+                    if (++bst == BST) { bst = 0; bph ^= 1u; }
+                    ready = mbar_test_wait(&bfull_bar[bst], bph);
+                    tc_fence_after();
+                    if (elect_one()) {
+                        constexpr uint32_t a_hi = desc_hi(PITCH * 128, 0);
+#pragma unroll
+                        for (int ti = 0; ti < TPS; ti++) {
+                            const int tap = grp * TPS + ti, r = tap / 3, s_ = tap % 3;
+#pragma unroll
+                            for (int m = 0; m < SUB; m++)
+#pragma unroll
+                                for (int k = 0; k < 4; k++) {
+                                    const uint32_t al = a_buf_lo + (((r * PITCH + s_ + 8 * m) * 128 + k * 32) >> 4);
+                                    const uint32_t bl = b_lo + ((ti * PC::B_TAP_BYTES + k * 32) >> 4);
+                                    mma_tf32_pair(d0 + m * NT, al, a_hi, bl, kBHi, idesc, (uint32_t)(!(k == 0 && tap == 0 && item == 0)));
+                                }
+                        }
+                        tc_commit_pair(eb);
+                        if (grp == Cfg::GROUPS - 1) {
+                            tc_commit_pair(&aempty_bar[abuf]);
+                            if (item == items_per_tile - 1) tc_commit_pair(&tfull_bar[acc]);
+                        }
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+        }
+    } else {
+        // ------------------------------------------------------------------ epilogue (both CTAs, own accumulator rows)
+        const int e = warp - 2;
+        const int m = e >> 2;
+        const int q = warp & 3;
+        const uint32_t sbuf = epi_base + e * kEpiWarpBytes;
+        const uint32_t row_off = lane * 128;
+        const int sw = lane & 7;
+        uint32_t tcount = 0;
+        bool ok = true;
+        for (int tile = pair; tile < p.n_tiles && ok; tile += n_pairs, tcount++) {
+            const TileCoord t = tile_of(tile);
+            const int hw = t.h0 + 4 * q, ww = t.w0 + 8 * m;
+            const int ph_ = hw + (lane >> 3), pw = ww + (lane & 7);
+            const bool inside = ph_ < p.H && pw < p.W;
+            const long long mask_idx = (((long long)t.img * p.H + ph_) * p.W + pw) * p.mask_words + (t.n0 >> 5);
+            const uint32_t acc = tcount & 1u, aph = (tcount >> 1) & 1u;
+            if (!mbar_wait(&tfull_bar[acc], aph, ab)) { ok = false; break; }
+            tc_fence_after();
+            constexpr int kChunks = NT / 32;
+#pragma unroll 1
+            for (int ch = 0; ch < kChunks; ch++) {
+                uint32_t v[32];
+                tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + acc * Cfg::ACC_COLS + m * NT + ch * 32, v);
+                uint32_t mword = 0xFFFFFFFFu;
+                if (p.mask_in && inside) mword = __ldg(p.mask_in + mask_idx + ch);
+                tmem_wait_ld();
+                if (ch == kChunks - 1) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_leader(&tempty_bar[acc]);
+                }
+                float f[32];
+#pragma unroll
+                for (int j = 0; j < 32; j++) f[j] = __uint_as_float(v[j]);
+                if (p.bias) {
+                    const float4 *bp = reinterpret_cast<const float4 *>(p.bias + t.n0 + ch * 32);
+#pragma unroll
+                    for (int j = 0; j < 8; j++) {
+                        const float4 b = __ldg(bp + j);
+                        f[4 * j] += b.x; f[4 * j + 1] += b.y; f[4 * j + 2] += b.z; f[4 * j + 3] += b.w;
+                    }
+                }
+                if (p.relu) {
+#pragma unroll
+                    for (int j = 0; j < 32; j++) f[j] = fmaxf(f[j], 0.f);
+                }
+                if (p.mask_in) {
+#pragma unroll
+                    for (int j = 0; j < 32; j++) f[j] = (mword >> j) & 1u ? f[j] : 0.f;
+                }
+                if (p.mask_out) {
+                    uint32_t w = 0;
+#pragma unroll
+                    for (int j = 0; j < 32; j++) w |= (f[j] > 0.f ? 1u : 0u) << j;
+                    if (inside) p.mask_out[mask_idx + ch] = w;
+                }
+                if (lane == 0) bulk_wait_read<0>();
+                __syncwarp();
+#pragma unroll
+                for (int j = 0; j < 8; j++)
+                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(sbuf + row_off + ((j ^ sw) << 4)), "f"(f[4 * j]), "f"(f[4 * j + 1]),
+                                 "f"(f[4 * j + 2]), "f"(f[4 * j + 3]) : "memory");
+                fence_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                    tma_store_4d(&map_out, sbuf, t.n0 + ch * 32, ww, hw, t.img);
+                    bulk_commit();
+                }
+            }
+        }
+        if (lane == 0) bulk_wait_read<0>();
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                    // neither CTA leaves (or frees tensor memory) while its peer may still signal / read it
+    if (threadIdx.x == 0 && abort_flag && p.status) atomicOr(p.status, GOM_STATUS_TIMEOUT);
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(Cfg::TMEM_COLS) : "memory");
+    }
+}
+
 // ------------------------------------------------------------------------------------------------------ helpers
 __global__ void k_pack_weights(GomConvPackArgs a) {
     const int K = a.c_out, C = a.c_in;
@@ -544,6 +825,37 @@ int launch_conv(const GomConv3x3Args *p, ConvDev &d, cudaStream_t stream) {
     return GOM_OK;
 }
 
+
+template <int NT, int SUB, int TPS, int BST>
+int launch_conv_pair(const GomConv3x3Args *p, ConvDev &d, cudaStream_t stream) {
+    using Cfg = ConvCfg<NT, SUB, TPS, BST, 9>;
+    using PC = PairCfg<NT, SUB, TPS, BST>;
+    static bool configured = false;
+    if (!configured) {
+        GOM_CUDA(cudaFuncSetAttribute(k_conv3x3_pair<NT, SUB, TPS, BST>, cudaFuncAttributeMaxDynamicSharedMemorySize, PC::SMEM));
+        configured = true;
+    }
+    d.tiles_w = gom_div_up(p->width, 2 * Cfg::TILE_W);           // PAIR tiles
+    d.tiles_h = gom_div_up(p->height, kTileH);
+    d.n_tiles_n = p->c_out / NT;
+    d.k_splits = 1;
+    d.c_blocks = p->c_in / 32;
+    const long long n_tiles = (long long)p->n_images * d.tiles_h * d.tiles_w * d.n_tiles_n;
+    GOM_REQUIRE(n_tiles < (1ll << 30), "too many tiles");
+    d.n_tiles = (int)n_tiles;
+    CUtensorMap ma, malo, mb, mo;
+    const bool round = p->tma_round && p->precision == 0;
+    if (int rc = make_act_map(&ma, p->x, p->n_images, p->height, p->width, p->c_in, Cfg::PITCH, Cfg::HALO_H, round)) return rc;
+    if (int rc = make_act_map(&malo, p->precision == 1 ? p->x_lo : p->x, p->n_images, p->height, p->width, p->c_in, Cfg::PITCH, Cfg::HALO_H, false)) return rc;
+    if (int rc = make_weight_map(&mb, p->w_packed, (p->precision == 1 ? 2 : 1) * 9, p->c_out, p->c_in, NT / 2, TPS)) return rc;
+    if (int rc = make_act_map(&mo, p->out, p->n_images, p->height, p->width, p->c_out, 8, 4, false)) return rc;
+    const int max_pairs = g_sms / 2;
+    const int grid = 2 * (d.n_tiles < max_pairs ? d.n_tiles : max_pairs);
+    GOM_CUDA(gom_launch_pdl(k_conv3x3_pair<NT, SUB, TPS, BST>, dim3(grid), dim3(Cfg::THREADS), PC::SMEM, stream, ma, malo, mb, mo, d));
+    GOM_LAUNCH_CHECK();
+    return GOM_OK;
+}
+
 }  // namespace
 
 extern "C" int gom_conv3x3_pack_weights(const GomConvPackArgs *p, gom_stream_t stream) {
@@ -653,7 +965,15 @@ extern "C" int gom_conv3x3(const GomConv3x3Args *p, gom_stream_t stream_) {
     }
     d.k_splits = best.ks;
     d.c_blocks = total_cb / best.ks;
-    if (best.nt == 128 && best.sub == 2) rc = launch_conv<128, 2, 1, 5>(p, d, stream);
+    // CTA pairs (cta_group::2, k_conv3x3_pair) for every shape without a K-split, when the image is at least one pair tile wide;
+    // GOM_CONV_PAIR=0 keeps the single-CTA kernel (A/B measurements: profiles/)
+    static const int pair_mode = [] { const char *e = getenv("GOM_CONV_PAIR"); return e ? atoi(e) : 1; }();
+    const bool pair_ok = pair_mode > 0 && best.ks == 1 && best.nt >= 64 && p->width >= 16 * best.sub;
+    if (pair_ok && best.nt == 128 && best.sub == 2) rc = launch_conv_pair<128, 2, 1, 5>(p, d, stream);
+    else if (pair_ok && best.nt == 128) rc = launch_conv_pair<128, 1, 3, 3>(p, d, stream);
+    else if (pair_ok && best.sub == 2) rc = launch_conv_pair<64, 2, 3, 4>(p, d, stream);
+    else if (pair_ok) rc = launch_conv_pair<64, 1, 3, 4>(p, d, stream);
+    else if (best.nt == 128 && best.sub == 2) rc = launch_conv<128, 2, 1, 5>(p, d, stream);
     else if (best.nt == 128) rc = launch_conv<128, 1, 3, 3>(p, d, stream);
     else if (best.nt == 64 && best.sub == 2) rc = launch_conv<64, 2, 3, 4>(p, d, stream);
     else if (best.nt == 64) rc = launch_conv<64, 1, 3, 4>(p, d, stream);
