@@ -967,7 +967,8 @@ extern "C" int gom_conv3x3(const GomConv3x3Args *p, gom_stream_t stream_) {
     d.c_blocks = total_cb / best.ks;
     // CTA pairs (cta_group::2, k_conv3x3_pair) for every shape without a K-split, when the image is at least one pair tile wide;
     // GOM_CONV_PAIR=0 keeps the single-CTA kernel (A/B measurements: profiles/)
-    static const int pair_mode = [] { const char *e = getenv("GOM_CONV_PAIR"); return e ? atoi(e) : 1; }();
+    const char *pair_env = getenv("GOM_CONV_PAIR");
+    const int pair_mode = pair_env ? atoi(pair_env) : 1;
     const bool pair_ok = pair_mode > 0 && best.ks == 1 && best.nt >= 64 && p->width >= 16 * best.sub;
     if (pair_ok && best.nt == 128 && best.sub == 2) rc = launch_conv_pair<128, 2, 1, 5>(p, d, stream);
     else if (pair_ok && best.nt == 128) rc = launch_conv_pair<128, 1, 3, 3>(p, d, stream);

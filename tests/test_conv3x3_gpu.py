@@ -120,3 +120,35 @@ def test_conv3x3_rejects_bad_arguments():
         gconv.conv3x3(torch.randn(1, 8, 8, 32, device=DEV), wp)                          # channel mismatch
     with pytest.raises(GomError):
         gconv.conv3x3(torch.randn(1, 8, 8, 64, device=DEV), wp, precision="fp32")        # 3xTF32 needs a split pack
+
+
+@pytest.mark.parametrize("case", [(3, 17, 33, 64, 128), (2, 20, 24, 64, 64), (1, 40, 48, 128, 256), (2, 64, 80, 64, 64), (2, 9, 50, 96, 160)])
+@pytest.mark.parametrize("shape", ["128,2", "128,1", "64,2", "64,1"])
+def test_cta_pair_kernel_equals_single_cta_kernel(case, shape, monkeypatch):
+    """k_conv3x3_pair (tcgen05 cta_group::2: two CTAs of a cluster on one M = 256 tile, each with its own halo and half of every
+    weight tile) accumulates every output element over the same sequence of MMAs as k_conv3x3, so outputs and ReLU masks must
+    be BIT-identical — also where the second CTA's pixel tile lies partly or wholly outside the image (W = 33, 24, 50) and
+    with 3xTF32.  GOM_CONV_PAIR=0 selects the single-CTA kernel."""
+    from gomavatar_b200 import conv as gconv
+    N, H, W, C, K = case
+    if K % int(shape.split(",")[0]):
+        pytest.skip("tile shape does not divide the channel count")
+    monkeypatch.setenv("GOM_CONV_SHAPE", shape)
+    g = torch.Generator(device="cpu").manual_seed(H * 31 + W)
+    x = torch.randn(N, H, W, C, generator=g).relu().to(DEV)
+    w = (torch.randn(K, C, 3, 3, generator=g) / (3 * C ** 0.5)).to(DEV)
+    b = (torch.randn(K, generator=g) * 0.1).to(DEV)
+    res = {}
+    for pair in ("0", "1"):
+        monkeypatch.setenv("GOM_CONV_PAIR", pair)
+        for precision in ("tf32", "fp32"):
+            status = torch.zeros(1, dtype=torch.int32, device=DEV)
+            mask = gconv.new_mask(N, H, W, K, DEV)
+            out = torch.full((N, H, W, K), float("nan"), device=DEV)
+            gconv.conv3x3(x, gconv.pack_weights(w, split=precision == "fp32"), bias=b, relu=True, mask_out=mask, precision=precision,
+                          out=out, status=status)
+            assert int(status.item()) == 0
+            res[pair, precision] = (out, mask)
+    for precision in ("tf32", "fp32"):
+        assert torch.equal(res["0", precision][0], res["1", precision][0])
+        assert torch.equal(res["0", precision][1], res["1", precision][1])
