@@ -961,16 +961,23 @@ extern "C" int gom_conv3x3(const GomConv3x3Args *p, gom_stream_t stream_) {
         if (got >= 2 && (nt == 64 || nt == 128) && (sub == 1 || sub == 2) && p->c_out % nt == 0) {
             if (got < 3 || ks < 1 || total_cb % ks) ks = 1;
             best = {nt, sub, ks};
+        } else if (got >= 2 && nt == 256 && sub == 1 && p->c_out % 256 == 0) {      // CTA pairs only (see below)
+            best = {256, 1, 1};
         }
     }
     d.k_splits = best.ks;
     d.c_blocks = total_cb / best.ks;
     // CTA pairs (cta_group::2, k_conv3x3_pair) for every shape without a K-split, when the image is at least one pair tile wide;
-    // GOM_CONV_PAIR=0 keeps the single-CTA kernel (A/B measurements: profiles/)
+    // GOM_CONV_PAIR=0 keeps the single-CTA kernel, 2 = pairs without the 256-channel tiles (A/B measurements: profiles/)
     const char *pair_env = getenv("GOM_CONV_PAIR");
     const int pair_mode = pair_env ? atoi(pair_env) : 1;
     const bool pair_ok = pair_mode > 0 && best.ks == 1 && best.nt >= 64 && p->width >= 16 * best.sub;
-    if (pair_ok && best.nt == 128 && best.sub == 2) rc = launch_conv_pair<128, 2, 1, 5>(p, d, stream);
+    if (best.nt == 256 && !pair_ok) best = {128, 2, 1};
+    // 256 output channels per pair tile (one sub-tile per CTA, the same number of work units): a CTA then reads 8 KB of operands
+    // per 128-cycle MMA instead of 6 KB per 64-cycle MMA (measured: -0.6 % of the step; GOM_CONV_PAIR=2 keeps NT = 128)
+    if (pair_mode == 1 && pair_ok && best.nt == 128 && best.sub == 2 && p->c_out % 256 == 0) best = {256, 1, 1};
+    if (pair_ok && best.nt == 256) rc = launch_conv_pair<256, 1, 1, 5>(p, d, stream);
+    else if (pair_ok && best.nt == 128 && best.sub == 2) rc = launch_conv_pair<128, 2, 1, 5>(p, d, stream);
     else if (pair_ok && best.nt == 128) rc = launch_conv_pair<128, 1, 3, 3>(p, d, stream);
     else if (pair_ok && best.sub == 2) rc = launch_conv_pair<64, 2, 3, 4>(p, d, stream);
     else if (pair_ok) rc = launch_conv_pair<64, 1, 3, 4>(p, d, stream);

@@ -35,7 +35,7 @@ def _err(a, b):
 
 @pytest.mark.parametrize("case", CASES)
 @pytest.mark.parametrize("precision", ["tf32", "fp32"])
-@pytest.mark.parametrize("shape", ["auto", "128,2", "128,1", "64,2", "64,1", "64,1,2", "128,2,4", "64,2,8"])
+@pytest.mark.parametrize("shape", ["auto", "128,2", "128,1", "64,2", "64,1", "64,1,2", "128,2,4", "64,2,8", "256,1"])
 def test_conv3x3_forward_and_dgrad_match_torch(case, precision, shape, monkeypatch):
     """``shape`` pins the kernel's tile shape (output channels per tile, M = 128 sub-tiles per tile[, K-splits: CTAs sharing
     the channel blocks of one tile, partial sums combined by TMA reduce-add + k_conv_finish]); "auto" is the cost model of

@@ -48,7 +48,7 @@ for (C, K, S) in LAYERS:
         wp = gconv.pack_weights(w)
         out = torch.empty(n, S, S, cout, device="cuda")
         row = {}
-        for shape in ["auto"] + [f"{nt},{sub},{ks}" for nt in (128, 64) for sub in (2, 1) for ks in (1, 2, 4, 8)]:
+        for shape in ["auto", "256,1,1"] + [f"{nt},{sub},{ks}" for nt in (128, 64) for sub in (2, 1) for ks in (1, 2, 4, 8)]:
             if shape != "auto":
                 nt, sub, ks = map(int, shape.split(","))
                 if cout % nt or (cin // 32) % ks or (cin // 32) // ks < 2:
