@@ -955,7 +955,9 @@ extern "C" int gom_conv3x3(const GomConv3x3Args *p, gom_stream_t stream_) {
                     if (cost < best_cost * 0.97) { best_cost = cost; best = {nt, sub, ks}; }   // prefer the earlier (larger, unsplit) shape on near ties
                 }
     }
-    if (const char *force = getenv("GOM_CONV_SHAPE")) {            // tests: "NT,SUB[,KS]" pins the tile shape (ignored if it does not divide)
+    bool forced = false;
+    if (const char *force = getenv("GOM_CONV_SHAPE")) {
+        forced = true;            // tests: "NT,SUB[,KS]" pins the tile shape (ignored if it does not divide)
         int nt = 0, sub = 0, ks = 1;
         const int got = sscanf(force, "%d,%d,%d", &nt, &sub, &ks);
         if (got >= 2 && (nt == 64 || nt == 128) && (sub == 1 || sub == 2) && p->c_out % nt == 0) {
@@ -975,7 +977,7 @@ extern "C" int gom_conv3x3(const GomConv3x3Args *p, gom_stream_t stream_) {
     if (best.nt == 256 && !pair_ok) best = {128, 2, 1};
     // 256 output channels per pair tile (one sub-tile per CTA, the same number of work units): a CTA then reads 8 KB of operands
     // per 128-cycle MMA instead of 6 KB per 64-cycle MMA (measured: -0.6 % of the step; GOM_CONV_PAIR=2 keeps NT = 128)
-    if (pair_mode == 1 && pair_ok && best.nt == 128 && best.sub == 2 && p->c_out % 256 == 0) best = {256, 1, 1};
+    if (pair_mode == 1 && !forced && pair_ok && best.nt == 128 && best.sub == 2 && p->c_out % 256 == 0) best = {256, 1, 1};
     if (pair_ok && best.nt == 256) rc = launch_conv_pair<256, 1, 1, 5>(p, d, stream);
     else if (pair_ok && best.nt == 128 && best.sub == 2) rc = launch_conv_pair<128, 2, 1, 5>(p, d, stream);
     else if (pair_ok && best.nt == 128) rc = launch_conv_pair<128, 1, 3, 3>(p, d, stream);

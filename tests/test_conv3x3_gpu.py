@@ -123,7 +123,7 @@ def test_conv3x3_rejects_bad_arguments():
 
 
 @pytest.mark.parametrize("case", [(3, 17, 33, 64, 128), (2, 20, 24, 64, 64), (1, 40, 48, 128, 256), (2, 64, 80, 64, 64), (2, 9, 50, 96, 160)])
-@pytest.mark.parametrize("shape", ["128,2", "128,1", "64,2", "64,1"])
+@pytest.mark.parametrize("shape", ["128,2", "128,1", "64,2", "64,1", "256,1"])
 def test_cta_pair_kernel_equals_single_cta_kernel(case, shape, monkeypatch):
     """k_conv3x3_pair (tcgen05 cta_group::2: two CTAs of a cluster on one M = 256 tile, each with its own halo and half of every
     weight tile) accumulates every output element over the same sequence of MMAs as k_conv3x3, so outputs and ReLU masks must
