@@ -23,6 +23,8 @@
 //     back instead of the activation itself (1/32 of the bytes, no shared-memory staging).
 // Warp roles (320 threads, one persistent CTA per SM): warp 0 TMA producer, warp 1 MMA issuer (+ TMEM allocation), warps 2-9
 // epilogue.  Every mbarrier wait is bounded (gomtc::mbar_wait) and reports GOM_STATUS_TIMEOUT.
+// Two kernels share this design: k_conv3x3 (one CTA per tile; also the K-split shapes and the 1x1 GEMM) and k_conv3x3_pair
+// (the default: two CTAs of a cluster on one M = 256 tile with tcgen05 cta_group::2, each holding half of every weight tile).
 #include <cuda.h>
 #include <stdlib.h>
 
