@@ -713,7 +713,7 @@ def cpu_path(args, n_frames, gpu_device=None, steps=1, warmup=0):
                 rgb, mask, _ = m(d["K"], d["E"], d["cnl_gtfms"], d["dst_Rs"], d["dst_Ts"])
             mse = float(((rgb[0].cpu().double() - img.detach()[0, ..., :3].double()) ** 2).mean())
             psnr = float("inf") if mse == 0 else -10.0 * np.log10(mse)
-        return float(loss)
+        return float(loss.detach())
 
     for _ in range(warmup):
         one_frame(0)
