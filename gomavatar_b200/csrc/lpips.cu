@@ -24,11 +24,30 @@ constexpr float kEps = 1e-10f;          // normalize_tensor eps (inside and outs
 __constant__ float c_shift[3] = {-.030f, -.088f, -.188f};
 __constant__ float c_scale[3] = {.458f, .448f, .450f};
 
+// A thread handles 12 consecutive floats = 4 pixels (three float4): the channel of every element is then a compile-time
+// constant (no 64-bit modulo per element) and all accesses are 16-byte vectors.  VEC = false: any size / alignment.
+template <bool VEC>
 __global__ void __launch_bounds__(kThreads) k_lpips_input_fwd(const float *pred, const float *gt, float *out,
                                                               long long n_half, float mul, float add) {
     gom_pdl_trigger();            // programmatic dependent launch (gom_common.cuh)
     gom_pdl_wait();
     // n_half = B*H*W*3 elements per half; out = [pred half | gt half]
+    if (VEC) {
+        const long long groups_half = n_half / 12;
+        for (long long gi = (long long)blockIdx.x * kThreads + threadIdx.x; gi < 2 * groups_half; gi += (long long)gridDim.x * kThreads) {
+            const bool second = gi >= groups_half;
+            const float4 *src = reinterpret_cast<const float4 *>(second ? gt : pred) + (second ? gi - groups_half : gi) * 3;
+            float4 *dst = reinterpret_cast<float4 *>(out) + gi * 3;
+            float v[12];
+#pragma unroll
+            for (int q = 0; q < 3; q++) { const float4 f = __ldg(src + q); v[4 * q] = f.x; v[4 * q + 1] = f.y; v[4 * q + 2] = f.z; v[4 * q + 3] = f.w; }
+#pragma unroll
+            for (int j = 0; j < 12; j++) v[j] = (v[j] * mul + add - c_shift[j % 3]) / c_scale[j % 3];
+#pragma unroll
+            for (int q = 0; q < 3; q++) dst[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        }
+        return;
+    }
     for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < 2 * n_half; i += (long long)gridDim.x * kThreads) {
         const float v = i < n_half ? pred[i] : gt[i - n_half];
         const int c = (int)(i % 3);
@@ -36,9 +55,24 @@ __global__ void __launch_bounds__(kThreads) k_lpips_input_fwd(const float *pred,
     }
 }
 
+template <bool VEC>
 __global__ void __launch_bounds__(kThreads) k_lpips_input_bwd(const float *g, float *d_pred, long long n_half, float mul) {
     gom_pdl_trigger();
     gom_pdl_wait();
+    if (VEC) {
+        for (long long gi = (long long)blockIdx.x * kThreads + threadIdx.x; gi < n_half / 12; gi += (long long)gridDim.x * kThreads) {
+            const float4 *src = reinterpret_cast<const float4 *>(g) + gi * 3;
+            float4 *dst = reinterpret_cast<float4 *>(d_pred) + gi * 3;
+            float v[12];
+#pragma unroll
+            for (int q = 0; q < 3; q++) { const float4 f = __ldg(src + q); v[4 * q] = f.x; v[4 * q + 1] = f.y; v[4 * q + 2] = f.z; v[4 * q + 3] = f.w; }
+#pragma unroll
+            for (int j = 0; j < 12; j++) v[j] = v[j] * mul / c_scale[j % 3];
+#pragma unroll
+            for (int q = 0; q < 3; q++) dst[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        }
+        return;
+    }
     for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < n_half; i += (long long)gridDim.x * kThreads)
         d_pred[i] = g[i] * mul / c_scale[(int)(i % 3)];
 }
@@ -537,8 +571,14 @@ extern "C" int gom_lpips_input_forward(const GomLpipsInputArgs *p, gom_stream_t 
     cudaStream_t stream = (cudaStream_t)stream_;
     const long long n_half = 3LL * p->n_frames * p->height * p->width;
     gom_prof_begin(GOM_PROF_LPIPS_INPUT, stream);
-    GOM_CUDA(gom_launch_pdl(k_lpips_input_fwd, dim3(grid_for(2 * n_half, kThreads * 4)), dim3(kThreads), 0, stream,
-                            p->pred, p->gt, p->out, n_half, p->from_unit_range ? 2.f : 1.f, p->from_unit_range ? -1.f : 0.f));
+    const bool vec = n_half % 12 == 0 && ((uintptr_t)p->pred % 16) == 0 && ((uintptr_t)p->gt % 16) == 0 && ((uintptr_t)p->out % 16) == 0;
+    if (vec) {
+        GOM_CUDA(gom_launch_pdl(k_lpips_input_fwd<true>, dim3(grid_for(2 * n_half / 12, kThreads)), dim3(kThreads), 0, stream,
+                                p->pred, p->gt, p->out, n_half, p->from_unit_range ? 2.f : 1.f, p->from_unit_range ? -1.f : 0.f));
+    } else {
+        GOM_CUDA(gom_launch_pdl(k_lpips_input_fwd<false>, dim3(grid_for(2 * n_half, kThreads * 4)), dim3(kThreads), 0, stream,
+                                p->pred, p->gt, p->out, n_half, p->from_unit_range ? 2.f : 1.f, p->from_unit_range ? -1.f : 0.f));
+    }
     GOM_LAUNCH_CHECK();
     gom_prof_end(GOM_PROF_LPIPS_INPUT, stream);
     return GOM_OK;
@@ -551,8 +591,13 @@ extern "C" int gom_lpips_input_backward(const GomLpipsInputArgs *p, gom_stream_t
     cudaStream_t stream = (cudaStream_t)stream_;
     const long long n_half = 3LL * p->n_frames * p->height * p->width;
     gom_prof_begin(GOM_PROF_LPIPS_INPUT, stream);
-    GOM_CUDA(gom_launch_pdl(k_lpips_input_bwd, dim3(grid_for(n_half, kThreads * 4)), dim3(kThreads), 0, stream, p->dL_dout, p->dL_dpred, n_half,
-                            p->from_unit_range ? 2.f : 1.f));
+    if (n_half % 12 == 0 && ((uintptr_t)p->dL_dout % 16) == 0 && ((uintptr_t)p->dL_dpred % 16) == 0) {
+        GOM_CUDA(gom_launch_pdl(k_lpips_input_bwd<true>, dim3(grid_for(n_half / 12, kThreads)), dim3(kThreads), 0, stream, p->dL_dout, p->dL_dpred,
+                                n_half, p->from_unit_range ? 2.f : 1.f));
+    } else {
+        GOM_CUDA(gom_launch_pdl(k_lpips_input_bwd<false>, dim3(grid_for(n_half, kThreads * 4)), dim3(kThreads), 0, stream, p->dL_dout, p->dL_dpred,
+                                n_half, p->from_unit_range ? 2.f : 1.f));
+    }
     GOM_LAUNCH_CHECK();
     gom_prof_end(GOM_PROF_LPIPS_INPUT, stream);
     return GOM_OK;

@@ -23,7 +23,12 @@ struct PhotoDev {
     float inv_n_rgb, inv_n_mask;
     float *d_rgb; long long d_rgb_ps;        // gradient wrt rgb, same pixel stride convention
     float *d_mask; long long d_mask_ps;
+    int rgba4, d_rgba4;                      // rgb | mask (resp. their gradients) are the channels of ONE 16-byte aligned [.,4] tensor
 };
+
+__device__ __forceinline__ int frame_of(long long i, long long n_pix_per_frame, long long total) {
+    return total < (1ll << 31) ? (int)((uint32_t)i / (uint32_t)n_pix_per_frame) : (int)(i / n_pix_per_frame);
+}
 
 __device__ __forceinline__ float sgn(float x) { return (x > 0.f) - (x < 0.f); }
 
@@ -31,10 +36,16 @@ __global__ void __launch_bounds__(kThreads) k_photo_fwd(PhotoDev a) {
     const long long total = a.n_pix_per_frame * a.B;
     float s_rgb = 0.f, s_mask = 0.f;
     for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < total; i += (long long)gridDim.x * kThreads) {
-        const int b = (int)(i / a.n_pix_per_frame);
-        const float m = a.mask[i * a.mask_ps];
-        const float *c = a.rgb + i * a.rgb_ps;
-        float u[3] = {c[0], c[1], c[2]};
+        const int b = frame_of(i, a.n_pix_per_frame, total);
+        float m, u[3];
+        if (a.rgba4) {
+            const float4 f = __ldg(reinterpret_cast<const float4 *>(a.rgb) + i);
+            u[0] = f.x; u[1] = f.y; u[2] = f.z; m = f.w;
+        } else {
+            m = a.mask[i * a.mask_ps];
+            const float *c = a.rgb + i * a.rgb_ps;
+            u[0] = c[0]; u[1] = c[1]; u[2] = c[2];
+        }
         if (a.bg) {
 #pragma unroll
             for (int k = 0; k < 3; k++) u[k] = u[k] * m + a.bg[3 * b + k] * (1.f - m);
@@ -62,9 +73,16 @@ __global__ void __launch_bounds__(kThreads) k_photo_bwd(PhotoDev a) {
     const long long total = a.n_pix_per_frame * a.B;
     const float w_rgb = a.g_loss ? a.g_loss[0] * a.inv_n_rgb : 0.f, w_mask = a.g_loss ? a.g_loss[1] * a.inv_n_mask : 0.f;
     for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < total; i += (long long)gridDim.x * kThreads) {
-        const int b = (int)(i / a.n_pix_per_frame);
-        const float m = a.mask[i * a.mask_ps];
-        const float *c = a.rgb + i * a.rgb_ps;
+        const int b = frame_of(i, a.n_pix_per_frame, total);
+        float m, c[3], d[3];
+        if (a.rgba4) {
+            const float4 f = __ldg(reinterpret_cast<const float4 *>(a.rgb) + i);
+            c[0] = f.x; c[1] = f.y; c[2] = f.z; m = f.w;
+        } else {
+            m = a.mask[i * a.mask_ps];
+            const float *cp = a.rgb + i * a.rgb_ps;
+            c[0] = cp[0]; c[1] = cp[1]; c[2] = cp[2];
+        }
         float dm = (a.gt_mask && a.g_loss) ? w_mask * sgn(m - a.gt_mask[i]) : 0.f;
 #pragma unroll
         for (int k = 0; k < 3; k++) {
@@ -73,13 +91,19 @@ __global__ void __launch_bounds__(kThreads) k_photo_bwd(PhotoDev a) {
             float gu = a.g_unpacked ? a.g_unpacked[3 * i + k] : 0.f;
             if (a.gt_rgb && a.g_loss) gu += w_rgb * sgn(u - a.gt_rgb[3 * i + k]);
             if (a.bg) {
-                a.d_rgb[i * a.d_rgb_ps + k] = gu * m;
+                d[k] = gu * m;
                 dm += gu * (c[k] - bgk);
             } else {
-                a.d_rgb[i * a.d_rgb_ps + k] = gu;
+                d[k] = gu;
             }
         }
-        a.d_mask[i * a.d_mask_ps] = dm;
+        if (a.d_rgba4) {
+            reinterpret_cast<float4 *>(a.d_rgb)[i] = make_float4(d[0], d[1], d[2], dm);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 3; k++) a.d_rgb[i * a.d_rgb_ps + k] = d[k];
+            a.d_mask[i * a.d_mask_ps] = dm;
+        }
     }
 }
 }  // namespace
@@ -95,6 +119,8 @@ static int photo_fill(const GomPhotoArgs *p, PhotoDev &a) {
     a.g_unpacked = p->dL_dunpacked; a.g_loss = p->dL_dlosses;
     a.inv_n_rgb = 1.0f / (3.0f * (float)a.n_pix_per_frame * a.B); a.inv_n_mask = 1.0f / ((float)a.n_pix_per_frame * a.B);
     a.d_rgb = p->dL_drgb; a.d_rgb_ps = p->dL_drgb_pixel_stride; a.d_mask = p->dL_dmask; a.d_mask_ps = p->dL_dmask_pixel_stride;
+    a.rgba4 = a.rgb_ps == 4 && a.mask_ps == 4 && a.mask == a.rgb + 3 && ((uintptr_t)a.rgb % 16) == 0;
+    a.d_rgba4 = a.d_rgb && a.d_rgb_ps == 4 && a.d_mask_ps == 4 && a.d_mask == a.d_rgb + 3 && ((uintptr_t)a.d_rgb % 16) == 0;
     return GOM_OK;
 }
 
