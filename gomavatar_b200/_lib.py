@@ -13,7 +13,7 @@ from ctypes import c_int, c_int32, c_int64, c_size_t, c_void_p, c_float, c_char_
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libgom_b200.so")
 
-ABI_VERSION = 10
+ABI_VERSION = 11
 STATUS_OVERFLOW = 1
 STATUS_TIMEOUT = 2
 
@@ -99,6 +99,11 @@ class GomPhotoArgs(ctypes.Structure):
                 ("loss_sums", c_void_p), ("dL_dunpacked", c_void_p), ("dL_dlosses", c_void_p),
                 ("dL_drgb", c_void_p), ("dL_drgb_pixel_stride", c_int64),
                 ("dL_dmask", c_void_p), ("dL_dmask_pixel_stride", c_int64)]
+
+
+class GomShadeArgs(ctypes.Structure):
+    _fields_ = [("n_pixels", c_int64), ("rgba", c_void_p), ("shading", c_void_p), ("rgbs", c_void_p), ("masks", c_void_p),
+                ("dL_drgbs", c_void_p), ("dL_dmasks", c_void_p), ("dL_drgba", c_void_p), ("dL_dshading", c_void_p)]
 
 
 class GomLpipsInputArgs(ctypes.Structure):
@@ -232,7 +237,7 @@ EXPORTS = [
     "gom_profile_slot_name", "gom_profile_read", "gom_camera_from_KE", "gom_raster_forward", "gom_raster_backward",
     "gom_joint_transforms_forward", "gom_joint_transforms_backward", "gom_lbs_forward", "gom_lbs_backward",
     "gom_face_gaussians_forward", "gom_face_gaussians_backward", "gom_photometric_forward", "gom_photometric_backward",
-    "gom_sizeof_photo_args", "gom_sizeof_camera_args", "gom_sizeof_raster_fwd_args", "gom_sizeof_raster_bwd_args",
+    "gom_sizeof_photo_args", "gom_shade_forward", "gom_shade_backward", "gom_sizeof_shade_args", "gom_sizeof_camera_args", "gom_sizeof_raster_fwd_args", "gom_sizeof_raster_bwd_args",
     "gom_sizeof_joint_fwd_args", "gom_sizeof_joint_bwd_args", "gom_sizeof_lbs_fwd_args", "gom_sizeof_lbs_bwd_args",
     "gom_sizeof_face_fwd_args", "gom_sizeof_face_bwd_args",
     "gom_lpips_input_forward", "gom_lpips_input_backward", "gom_bias_relu", "gom_relu_backward",
@@ -257,7 +262,7 @@ EXPORTS = [
 _STRUCTS = {
     "camera": GomCameraArgs, "raster_fwd": GomRasterFwdArgs, "raster_bwd": GomRasterBwdArgs,
     "joint_fwd": GomJointFwdArgs, "joint_bwd": GomJointBwdArgs, "lbs_fwd": GomLbsFwdArgs, "lbs_bwd": GomLbsBwdArgs,
-    "face_fwd": GomFaceFwdArgs, "face_bwd": GomFaceBwdArgs, "photo": GomPhotoArgs,
+    "face_fwd": GomFaceFwdArgs, "face_bwd": GomFaceBwdArgs, "photo": GomPhotoArgs, "shade": GomShadeArgs,
     "lpips_input": GomLpipsInputArgs, "bias_relu": GomBiasReluArgs, "relu_bwd": GomReluBwdArgs,
     "lpips_tap": GomLpipsTapArgs, "eval_metrics": GomEvalMetricsArgs,
     "conv_first": GomConvFirstArgs, "adam": GomAdamArgs,
@@ -268,7 +273,7 @@ _STRUCTS = {
 }
 _ENTRY_POINTS = ["gom_camera_from_KE", "gom_raster_forward", "gom_raster_backward", "gom_joint_transforms_forward",
                  "gom_joint_transforms_backward", "gom_lbs_forward", "gom_lbs_backward", "gom_face_gaussians_forward",
-                 "gom_face_gaussians_backward", "gom_photometric_forward", "gom_photometric_backward",
+                 "gom_face_gaussians_backward", "gom_photometric_forward", "gom_photometric_backward", "gom_shade_forward", "gom_shade_backward",
                  "gom_lpips_input_forward", "gom_lpips_input_backward", "gom_bias_relu", "gom_relu_backward",
                  "gom_lpips_tap_forward", "gom_lpips_tap_backward", "gom_eval_metrics",
                  "gom_conv_first_forward", "gom_conv_first_backward", "gom_adam_step",

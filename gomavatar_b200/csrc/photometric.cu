@@ -154,3 +154,50 @@ extern "C" int gom_photometric_backward(const GomPhotoArgs *p, gom_stream_t stre
     gom_prof_end(GOM_PROF_PHOTO_BWD, (cudaStream_t)stream_);
     return GOM_OK;
 }
+
+// ------------------------------------------------------------------------------------------------ pseudo-shading
+namespace {
+__global__ void __launch_bounds__(kThreads) k_shade_fwd(GomShadeArgs a) {
+    for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < a.n_pixels; i += (long long)gridDim.x * kThreads) {
+        const float4 f = __ldg(reinterpret_cast<const float4 *>(a.rgba) + i);
+        const float s = __ldg(a.shading + i);
+        a.rgbs[3 * i] = f.x * s; a.rgbs[3 * i + 1] = f.y * s; a.rgbs[3 * i + 2] = f.z * s;
+        a.masks[i] = f.w;
+    }
+}
+__global__ void __launch_bounds__(kThreads) k_shade_bwd(GomShadeArgs a) {
+    for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < a.n_pixels; i += (long long)gridDim.x * kThreads) {
+        const float4 f = __ldg(reinterpret_cast<const float4 *>(a.rgba) + i);
+        const float s = __ldg(a.shading + i);
+        float g0 = 0.f, g1 = 0.f, g2 = 0.f;
+        if (a.dL_drgbs) { g0 = a.dL_drgbs[3 * i]; g1 = a.dL_drgbs[3 * i + 1]; g2 = a.dL_drgbs[3 * i + 2]; }
+        const float gm = a.dL_dmasks ? a.dL_dmasks[i] : 0.f;
+        reinterpret_cast<float4 *>(a.dL_drgba)[i] = make_float4(g0 * s, g1 * s, g2 * s, gm);
+        a.dL_dshading[i] = g0 * f.x + g1 * f.y + g2 * f.z;
+    }
+}
+}  // namespace
+
+extern "C" int gom_shade_forward(const GomShadeArgs *p, gom_stream_t stream_) {
+    GOM_REQUIRE(p != nullptr, "args");
+    GOM_REQUIRE(p->n_pixels > 0, "sizes");
+    GOM_REQUIRE(p->rgba && p->shading && p->rgbs && p->masks, "null pointer");
+    GOM_REQUIRE(((uintptr_t)p->rgba % 16) == 0, "rgba must be 16-byte aligned");
+    const int grid = (int)std::min<long long>((p->n_pixels + kThreads - 1) / kThreads, 148 * 8);
+    k_shade_fwd<<<grid, kThreads, 0, (cudaStream_t)stream_>>>(*p);
+    GOM_LAUNCH_CHECK();
+    return GOM_OK;
+}
+
+extern "C" int gom_shade_backward(const GomShadeArgs *p, gom_stream_t stream_) {
+    GOM_REQUIRE(p != nullptr, "args");
+    GOM_REQUIRE(p->n_pixels > 0, "sizes");
+    GOM_REQUIRE(p->rgba && p->shading && p->dL_drgba && p->dL_dshading, "null pointer");
+    GOM_REQUIRE(((uintptr_t)p->rgba % 16) == 0 && ((uintptr_t)p->dL_drgba % 16) == 0, "rgba / dL_drgba must be 16-byte aligned");
+    const int grid = (int)std::min<long long>((p->n_pixels + kThreads - 1) / kThreads, 148 * 8);
+    k_shade_bwd<<<grid, kThreads, 0, (cudaStream_t)stream_>>>(*p);
+    GOM_LAUNCH_CHECK();
+    return GOM_OK;
+}
+
+extern "C" size_t gom_sizeof_shade_args(void) { return sizeof(GomShadeArgs); }

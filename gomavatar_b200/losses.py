@@ -12,7 +12,7 @@ from __future__ import annotations
 import torch
 
 from . import _lib
-from ._lib import GomPhotoArgs, call, ptr
+from ._lib import GomPhotoArgs, GomShadeArgs, call, ptr
 
 
 def _pixel_view(t, channels):
@@ -104,6 +104,42 @@ class _PhotometricL1RGBA(torch.autograd.Function):
             bgcolor=ptr(bg), gt_rgb=ptr(gt_rgb), gt_mask=ptr(gt_mask), dL_dunpacked=ptr(g_u), dL_dlosses=ptr(g_loss),
             dL_drgb=ptr(d), dL_drgb_pixel_stride=4, dL_dmask=ptr(d[..., 3]), dL_dmask_pixel_stride=4))
         return d, None, None, None
+
+
+class _ShadeRGBA(torch.autograd.Function):
+    """(rgba [B,H,W,4] contiguous, shading [B,H,W,1]) -> (rgba[..., :3] * shading, rgba[..., 3]) in one launch each way
+    (reference models/model.py:281-287).  The gradient reaches the rasterizer as ONE [B,H,W,4] tensor."""
+
+    @staticmethod
+    def forward(ctx, rgba, shading):
+        B, H, W, _ = rgba.shape
+        x, s = rgba.detach(), shading.detach().reshape(B, H, W).contiguous().float()
+        rgbs = torch.empty(B, H, W, 3, dtype=torch.float32, device=x.device)
+        masks = torch.empty(B, H, W, dtype=torch.float32, device=x.device)
+        call("gom_shade_forward", GomShadeArgs(n_pixels=B * H * W, rgba=ptr(x), shading=ptr(s), rgbs=ptr(rgbs), masks=ptr(masks)))
+        ctx.save_for_backward(x, s)
+        ctx.shading_shape = tuple(shading.shape)
+        return rgbs, masks
+
+    @staticmethod
+    def backward(ctx, g_rgbs, g_masks):
+        x, s = ctx.saved_tensors
+        B, H, W, _ = x.shape
+        g_rgbs = None if g_rgbs is None else g_rgbs.contiguous().float()
+        g_masks = None if g_masks is None else g_masks.contiguous().float()
+        d = torch.empty(B, H, W, 4, dtype=torch.float32, device=x.device)
+        ds = torch.empty(B, H, W, dtype=torch.float32, device=x.device)
+        call("gom_shade_backward", GomShadeArgs(n_pixels=B * H * W, rgba=ptr(x), shading=ptr(s), dL_drgbs=ptr(g_rgbs),
+                                                dL_dmasks=ptr(g_masks), dL_drgba=ptr(d), dL_dshading=ptr(ds)))
+        return d, ds.reshape(ctx.shading_shape)
+
+
+def shade_rgba(rgba, shading):
+    """rgba [B,H,W,4] (the rasterizer's output), shading [B,H,W,1] -> (rgbs [B,H,W,3] = albedo * shading, masks [B,H,W])."""
+    if rgba.is_cuda and rgba.dtype == torch.float32 and rgba.is_contiguous() and rgba.dim() == 4 and rgba.shape[-1] == 4 \
+            and shading.numel() == rgba.numel() // 4:
+        return _ShadeRGBA.apply(rgba, shading)
+    return rgba[..., :3] * shading, rgba[..., 3]
 
 
 def _rgba_base(rgbs, masks):

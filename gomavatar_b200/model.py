@@ -253,7 +253,8 @@ class Model(nn.Module):
                 torch.cuda.current_stream(vertices_observation.device).wait_stream(side)      # join
             else:
                 normal, normal_mask, shadings = self._mesh_branch(vertices_observation, K, E, B, H, W)
-            rgbs = albedos * shadings
+            from .losses import shade_rgba                  # albedo * shading and the alpha channel, one launch each way
+            rgbs, masks = shade_rgba(rgba, shadings)
         else:
             rgbs = albedos
 

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define GOM_ABI_VERSION 10
+#define GOM_ABI_VERSION 11
 #define GOM_TILE 16              /* 16x16-pixel tiles, as upstream's BLOCK_X/BLOCK_Y */
 #define GOM_MAX_CHANNELS 4
 #define GOM_MAX_JOINTS 64
@@ -275,6 +275,26 @@ typedef struct {
 } GomPhotoArgs;
 int gom_photometric_forward(const GomPhotoArgs *a, gom_stream_t stream);
 int gom_photometric_backward(const GomPhotoArgs *a, gom_stream_t stream);
+
+/* Pseudo-shading of the rasterizer's interleaved output, one launch each way (reference models/model.py:281-287:
+ * `rgbs = albedos * shadings` with albedos / masks the channel slices of the rendered RGBA image):
+ *   forward   rgbs[p,k] = rgba[p,k] * shading[p] (k < 3),  masks[p] = rgba[p,3]
+ *   backward  dL_drgba[p] = (dL_drgbs[p,:] * shading[p], dL_dmasks[p]),  dL_dshading[p] = sum_k dL_drgbs[p,k] * rgba[p,k]
+ * (replaces a strided multiply, its two product gradients, a channel reduction and autograd's slice backward: two zero
+ * fills, two strided copies and an add over the full image). */
+typedef struct {
+    int64_t n_pixels;            /* B*H*W */
+    const float *rgba;           /* [n,4], 16-byte aligned */
+    const float *shading;        /* [n] */
+    float *rgbs;                 /* [n,3] out (forward) */
+    float *masks;                /* [n]   out (forward) */
+    const float *dL_drgbs;       /* [n,3] (backward; NULL = zeros) */
+    const float *dL_dmasks;      /* [n]   (backward; NULL = zeros) */
+    float *dL_drgba;             /* [n,4] out (backward), 16-byte aligned */
+    float *dL_dshading;          /* [n]   out (backward) */
+} GomShadeArgs;
+int gom_shade_forward(const GomShadeArgs *a, gom_stream_t stream);
+int gom_shade_backward(const GomShadeArgs *a, gom_stream_t stream);
 
 /* --------------------------------------------------------------------------------------------------------------
  * LPIPS-VGG v0.1 perceptual loss — everything that is not a convolution (csrc/lpips.cu).  Replaces the torch ops of
@@ -725,6 +745,7 @@ size_t gom_sizeof_lbs_bwd_args(void);
 size_t gom_sizeof_face_fwd_args(void);
 size_t gom_sizeof_face_bwd_args(void);
 size_t gom_sizeof_photo_args(void);
+size_t gom_sizeof_shade_args(void);
 size_t gom_sizeof_lpips_input_args(void);
 size_t gom_sizeof_bias_relu_args(void);
 size_t gom_sizeof_relu_bwd_args(void);

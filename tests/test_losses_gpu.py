@@ -311,3 +311,29 @@ def test_lpips_frame_groups_on_separate_streams_equal_one_stream(golden_dir):
     np.testing.assert_allclose(v.detach().cpu().numpy(), res[1][0].cpu().numpy(), rtol=1e-6)
     # replay vs eager with the same grouping: equal up to the order of the float atomics (K-split reduce-adds, conv1_1 stencil)
     _grad_close(k0.grad.cpu().numpy(), res[2][1].cpu().numpy(), "graph replay vs eager", max_rel_l2=1e-3, max_abs=5e-3)
+
+
+def test_shade_rgba_matches_torch_formulation():
+    """``shade_rgba`` (csrc/photometric.cu::k_shade_fwd/bwd) against the reference's own expression
+    ``rgbs = albedos * shadings`` with albedos / masks the channel slices of the rendered image (models/model.py:281-287):
+    values exact, gradients to fp32 rounding (the channel sum of dL/dshading is three terms)."""
+    from gomavatar_b200.losses import shade_rgba
+    rng = np.random.default_rng(5)
+    B, H, W = 2, 37, 53
+    rgba = rng.random((B, H, W, 4)).astype(np.float32)
+    sh = (rng.random((B, H, W, 1)) * 2).astype(np.float32)
+    g_rgb, g_m = rng.normal(size=(B, H, W, 3)).astype(np.float32), rng.normal(size=(B, H, W)).astype(np.float32)
+    a, s = t(rgba).to(DEV).requires_grad_(True), t(sh).to(DEV).requires_grad_(True)
+    ref_rgb, ref_m = a[..., :3] * s, a[..., 3]
+    ((ref_rgb * t(g_rgb).to(DEV)).sum() + (ref_m * t(g_m).to(DEV)).sum()).backward()
+    a2, s2 = t(rgba).to(DEV).requires_grad_(True), t(sh).to(DEV).requires_grad_(True)
+    rgb, m = shade_rgba(a2, s2)
+    assert rgb.shape == (B, H, W, 3) and m.shape == (B, H, W)
+    assert torch.equal(rgb, ref_rgb.detach()) and torch.equal(m, ref_m.detach())
+    ((rgb * t(g_rgb).to(DEV)).sum() + (m * t(g_m).to(DEV)).sum()).backward()
+    assert torch.equal(a2.grad, a.grad)
+    np.testing.assert_allclose(s2.grad.cpu().numpy(), s.grad.cpu().numpy(), rtol=1e-5, atol=1e-6)
+    # only the colour part used (masks without a gradient)
+    a3, s3 = t(rgba).to(DEV).requires_grad_(True), t(sh).to(DEV).requires_grad_(True)
+    (shade_rgba(a3, s3)[0] * t(g_rgb).to(DEV)).sum().backward()
+    assert torch.equal(a3.grad[..., :3], a.grad[..., :3]) and float(a3.grad[..., 3].abs().max()) == 0.0
