@@ -12,6 +12,12 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
+# Batch-invariant convolutions: the 1-rank side pushes 2 x 4 images through the VGG trunk per launch, a rank of the 2-rank side
+# 2 x 2; with K-splits allowed the small deep layers pick different splits for the two and the tensor core's fp32 accumulation
+# order moves activations at the 1e-5 level (ReLU masks near zero flip: ~1e-3 of the gradient).  Without K-splits every tile
+# shape is bit-identical (tools/conv_auto_vs_pinned.py), so the comparison below tests the sharding / all-reduce semantics alone.
+os.environ["GOM_CONV_KSPLIT"] = "0"
+
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 
