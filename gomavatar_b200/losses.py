@@ -136,10 +136,12 @@ class _ShadeRGBA(torch.autograd.Function):
 
 def shade_rgba(rgba, shading):
     """rgba [B,H,W,4] (the rasterizer's output), shading [B,H,W,1] -> (rgbs [B,H,W,3] = albedo * shading, masks [B,H,W])."""
-    if rgba.is_cuda and rgba.dtype == torch.float32 and rgba.is_contiguous() and rgba.dim() == 4 and rgba.shape[-1] == 4 \
+    if not rgba.is_cuda:
+        raise _lib.GomError("shade_rgba: inputs must live on a CUDA device (no CPU path exists)")
+    if rgba.dtype == torch.float32 and rgba.is_contiguous() and rgba.dim() == 4 and rgba.shape[-1] == 4 \
             and shading.numel() == rgba.numel() // 4:
         return _ShadeRGBA.apply(rgba, shading)
-    return rgba[..., :3] * shading, rgba[..., 3]
+    return rgba[..., :3] * shading, rgba[..., 3]          # unusual layouts / dtypes: the reference's own expression, on the device
 
 
 def _rgba_base(rgbs, masks):

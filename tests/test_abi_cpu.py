@@ -68,3 +68,21 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f"{f} imports the oracle"
+
+
+def test_rgba_fast_paths_of_the_losses_refuse_cpu_tensors_and_foreign_views():
+    """Host logic of gomavatar_b200/losses.py: the fused RGBA paths are taken only for the channel slices of ONE contiguous
+    fp32 CUDA [B,H,W,4] tensor (what Model.forward returns); anything else keeps the general path, and CPU tensors are refused
+    loudly (there is no CPU path)."""
+    import pytest
+    import torch
+    from gomavatar_b200 import _lib, losses
+    rgba = torch.rand(2, 5, 7, 4)
+    assert losses._rgba_base(rgba[..., :3], rgba[..., 3]) is None                      # not on a CUDA device
+    assert losses._rgba_base(rgba[..., :3].contiguous(), rgba[..., 3]) is None         # not views of one tensor
+    other = torch.rand(2, 5, 7, 4)
+    assert losses._rgba_base(rgba[..., :3], other[..., 3]) is None
+    with pytest.raises(_lib.GomError):
+        losses.shade_rgba(rgba, torch.rand(2, 5, 7, 1))
+    with pytest.raises(_lib.GomError):
+        losses.photometric_l1(rgba[..., :3], rgba[..., 3], None, torch.rand(2, 5, 7, 3), torch.rand(2, 5, 7))
